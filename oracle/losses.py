@@ -1,0 +1,225 @@
+"""Oracle (test infrastructure): ``ComputeElement`` of the FiniteElementLoss family in NumPy f64.
+
+Every function is vectorised over a leading element axis and returns ``(energy (ne,),
+re (ne, nd), Ke (ne, nd, nd))`` exactly like the reference's ``ComputeElement`` returns
+``(energy, residual, stiffness)`` for one element.
+
+  mechanical   fol/loss_functions/mechanical.py:37-117
+  thermal      fol/loss_functions/thermal.py:28-49
+  neo-hooke    fol/loss_functions/mechanical_neohooke.py:49-91, 107-275
+               fol/constitutive_material_models/neo_hooke.py:14-109, utils.py:14-32, 103-130, 191-196
+"""
+import numpy as np
+
+from .geometry import ELEMENTS, point_data
+
+
+# ----------------------------------------------------------------------------- mechanical
+def d_matrix(dim, E, nu):
+    """mechanical.py:60-82 (2-D is plane stress)."""
+    if dim == 2:
+        return np.array([[1, nu, 0], [nu, 1, 0], [0, 0, (1 - nu) / 2]]) * (E / (1 - nu ** 2))
+    c1 = E / ((1.0 + nu) * (1.0 - 2.0 * nu))
+    c2, c3, c4 = c1 * (1.0 - nu), c1 * nu, c1 * 0.5 * (1.0 - 2.0 * nu)
+    D = np.zeros((6, 6))
+    D[:3, :3] = c3
+    D[0, 0] = D[1, 1] = D[2, 2] = c2
+    D[3, 3] = D[4, 4] = D[5, 5] = c4
+    return D
+
+
+def b_matrix(gradN):
+    """mechanical.py:37-58.  gradN (..., a, dim) -> B (..., nstrain, a*dim)."""
+    a, dim = gradN.shape[-2:]
+    lead = gradN.shape[:-2]
+    if dim == 2:
+        B = np.zeros(lead + (3, 2 * a))
+        B[..., 0, 0::2] = gradN[..., 0]
+        B[..., 1, 1::2] = gradN[..., 1]
+        B[..., 2, 0::2] = gradN[..., 1]
+        B[..., 2, 1::2] = gradN[..., 0]
+        return B
+    B = np.zeros(lead + (6, 3 * a))      # rows [xx, yy, zz, xy, yz, xz]
+    B[..., 0, 0::3] = gradN[..., 0]
+    B[..., 1, 1::3] = gradN[..., 1]
+    B[..., 2, 2::3] = gradN[..., 2]
+    B[..., 3, 0::3] = gradN[..., 1]
+    B[..., 3, 1::3] = gradN[..., 0]
+    B[..., 4, 1::3] = gradN[..., 2]
+    B[..., 4, 2::3] = gradN[..., 1]
+    B[..., 5, 0::3] = gradN[..., 2]
+    B[..., 5, 2::3] = gradN[..., 0]
+    return B
+
+
+def n_matrix(N, dim):
+    """mechanical.py:84-96.  N (g, a) -> (g, dim, a*dim)."""
+    g, a = N.shape
+    M = np.zeros((g, dim, dim * a))
+    for k in range(dim):
+        M[:, k, k::dim] = N
+    return M
+
+
+def body_force_vector(elem, Ns, detJ, w, body):
+    """Fe = sum_g w detJ N_mat^T b  -> (ne, nd)."""
+    Nm = n_matrix(Ns, elem.dim)                                   # (g, dim, nd)
+    return np.einsum("g,eg,gkn,k->en", w, detJ, Nm, np.asarray(body, float).reshape(-1))
+
+
+def mechanical_element(element_type, num_gp, X, de, u, E, nu, body=None):
+    """mechanical.py:98-117.  X (ne,a,3), de (ne,a), u (ne,nd)."""
+    elem = ELEMENTS[element_type]
+    Ns, gradN, detJ, w = point_data(elem, X, num_gp)
+    D = d_matrix(elem.dim, E, nu)
+    B = b_matrix(gradN)                                          # (ne, g, s, nd)
+    e_gp = np.einsum("ga,ea->eg", Ns, de)
+    Se = np.einsum("g,eg,eg,egsn,st,egtm->enm", w, detJ, e_gp, B, D, B, optimize=True)
+    body = np.zeros(elem.dim) if body is None else body
+    Fe = body_force_vector(elem, Ns, detJ, w, body)
+    re = np.einsum("enm,em->en", Se, u) - Fe
+    return np.einsum("en,en->e", u, re), re, Se
+
+
+# ----------------------------------------------------------------------------- thermal
+def thermal_element(element_type, num_gp, X, de, T, beta=0.0, c=1.0, body_force=0.0):
+    """thermal.py:28-49.  T (ne, a)."""
+    elem = ELEMENTS[element_type]
+    Ns, gradN, detJ, w = point_data(elem, X, num_gp)
+    T_gp = np.einsum("ga,ea->eg", Ns, T)
+    kappa = np.einsum("ga,ea->eg", Ns, de) * (1.0 + beta * T_gp ** c)
+    Se = np.einsum("eg,egai,egbi,eg,g->eab", kappa, gradN, gradN, detJ, w, optimize=True)
+    Fe = np.einsum("g,eg,ga->ea", w, detJ, Ns) * body_force
+    re = np.einsum("eab,eb->ea", Se, T) - Fe
+    return np.einsum("ea,ea->e", T, re), re, Se
+
+
+def thermal_energy_grads(element_type, num_gp, X, de, T, beta=0.0, c=1.0):
+    """Analytic cotangents of the thermal element energy under the reference's stop_gradient
+    placement (thermal.py:31, 45-49): dE/dT = re (element residual), dE/dK_a = sum_g N_a
+    (1 + beta T_g^c) |grad T_g|^2 detJ w.   Returns (dE/dT (ne,a), dE/dK (ne,a))."""
+    elem = ELEMENTS[element_type]
+    Ns, gradN, detJ, w = point_data(elem, X, num_gp)
+    _, re, _ = thermal_element(element_type, num_gp, X, de, T, beta, c)
+    T_gp = np.einsum("ga,ea->eg", Ns, T)
+    gT = np.einsum("egai,ea->egi", gradN, T)
+    dK = np.einsum("ga,eg,eg,eg,g->ea", Ns, 1.0 + beta * T_gp ** c,
+                   np.einsum("egi,egi->eg", gT, gT), detJ, w)
+    return re, dK
+
+
+# ----------------------------------------------------------------------------- neo-hooke
+_VOIGT3 = [(0, 0), (1, 1), (2, 2), (1, 2), (0, 2), (0, 1)]      # utils.py:14-32, 118-128
+_VOIGT2 = [(0, 0), (1, 1), (0, 1)]                               # utils.py:17-22, 107-116
+
+
+def _diad_special(A, B):
+    """utils.py:191-196."""
+    return 0.5 * (np.einsum("...ik,...jl->...ijkl", A, B) + np.einsum("...il,...jk->...ijkl", A, B))
+
+
+def neo_hooke_point(F, k, mu):
+    """neo_hooke.py:14-58 (2-D) and :64-109 (3-D).  F (..., d, d); k, mu (...).
+    Returns psi (...), S voigt (..., nv), C voigt (..., nv, nv)."""
+    d = F.shape[-1]
+    C = np.einsum("...ki,...kj->...ij", F, F)
+    invC = np.linalg.inv(C)
+    J = np.linalg.det(F)
+    p = 0.5 * k * (J - 1.0 / J)
+    dp_dJ = 0.5 * k * (1.0 + J ** (-2.0))
+    trC = np.trace(C, axis1=-2, axis2=-1)
+    Jm = J ** (-2.0 / d)
+    psi = (k / 4.0) * (J ** 2 - 2.0 * np.log(J) - 1.0) + 0.5 * mu * (Jm * trC - d)
+    eye = np.eye(d)
+    S_vol = (J * p)[..., None, None] * invC
+    # S_iso = J^(-2/d) * P : (mu I),  P = I4 - (1/d) invC (x) C
+    S_iso = (Jm * mu)[..., None, None] * (eye - (1.0 / d) * trC[..., None, None] * invC)
+    S = S_vol + S_iso
+    ii = np.einsum("...ij,...kl->...ijkl", invC, invC)
+    P_bar = _diad_special(invC, invC) - (1.0 / d) * ii
+    C_vol = (J * p + dp_dJ * J ** 2)[..., None, None, None, None] * ii \
+        - (2.0 * J * p)[..., None, None, None, None] * _diad_special(invC, invC)
+    C_iso = ((2.0 / d) * Jm * mu * trC)[..., None, None, None, None] * P_bar \
+        - (2.0 / d) * (np.einsum("...ij,...kl->...ijkl", invC, S_iso)
+                       + np.einsum("...ij,...kl->...ijkl", S_iso, invC))
+    C4 = C_vol + C_iso
+    vo = _VOIGT3 if d == 3 else _VOIGT2
+    Sv = np.stack([S[..., i, j] for (i, j) in vo], axis=-1)
+    if d == 3:
+        Cv = np.stack([np.stack([C4[..., i, j, kk, l] for (kk, l) in vo], axis=-1)
+                       for (i, j) in vo], axis=-2)
+    else:
+        # utils.py:107-116: lower triangle is a copy of the upper one
+        c00, c01, c02 = C4[..., 0, 0, 0, 0], C4[..., 0, 0, 1, 1], C4[..., 0, 0, 0, 1]
+        c11, c12, c22 = C4[..., 1, 1, 1, 1], C4[..., 1, 1, 0, 1], C4[..., 0, 1, 0, 1]
+        Cv = np.stack([np.stack([c00, c01, c02], -1), np.stack([c01, c11, c12], -1),
+                       np.stack([c02, c12, c22], -1)], axis=-2)
+    return psi, Sv, Cv
+
+
+def neo_hooke_b_matrix(gradN, F):
+    """mechanical_neohooke.py:49-91.  gradN (..., a, d), F (..., d, d) -> B (..., nv, a*d)."""
+    a, d = gradN.shape[-2:]
+    lead = gradN.shape[:-2]
+    g = gradN
+    if d == 2:
+        B = np.zeros(lead + (3, 2 * a))
+        for c in range(2):
+            B[..., 0, c::2] = F[..., c, 0, None] * g[..., 0]
+            B[..., 1, c::2] = F[..., c, 1, None] * g[..., 1]
+            B[..., 2, c::2] = F[..., c, 1, None] * g[..., 0] + F[..., c, 0, None] * g[..., 1]
+        return B
+    B = np.zeros(lead + (6, 3 * a))
+    for c in range(3):
+        B[..., 0, c::3] = F[..., c, 0, None] * g[..., 0]
+        B[..., 1, c::3] = F[..., c, 1, None] * g[..., 1]
+        B[..., 2, c::3] = F[..., c, 2, None] * g[..., 2]
+        B[..., 3, c::3] = F[..., c, 1, None] * g[..., 2] + F[..., c, 2, None] * g[..., 1]
+        B[..., 4, c::3] = F[..., c, 0, None] * g[..., 2] + F[..., c, 2, None] * g[..., 0]
+        B[..., 5, c::3] = F[..., c, 0, None] * g[..., 1] + F[..., c, 1, None] * g[..., 0]
+    return B
+
+
+def neo_hooke_element(element_type, num_gp, X, de, u, E, nu, body=None):
+    """mechanical_neohooke.py:243-275.  ``E`` scales the control field: E_gp = N . de (the
+    reference ignores ``young_modulus`` in ComputeElement, :253-255, so pass de = E*control
+    -- here ``E`` multiplies nothing and is kept only for a uniform signature)."""
+    elem = ELEMENTS[element_type]
+    d = elem.dim
+    Ns, gradN, detJ, w = point_data(elem, X, num_gp)
+    ne = X.shape[0]
+    U = u.reshape(ne, elem.nnode, d)
+    H = np.einsum("egai,eaj->egji", gradN, U)                    # H[j,i] = du_j/dX_i
+    F = H + np.eye(d)
+    e_gp = np.einsum("ga,ea->eg", Ns, de)
+    k_gp = e_gp / (3.0 * (1.0 - 2.0 * nu))
+    mu_gp = e_gp / (2.0 * (1.0 + nu))
+    psi, Sv, Cv = neo_hooke_point(F, k_gp, mu_gp)
+    B = neo_hooke_b_matrix(gradN, F)
+    wd = w[None, :] * detJ
+    Kmat = np.einsum("eg,egsn,egst,egtm->enm", wd, B, Cv, B, optimize=True)
+    vo = _VOIGT3 if d == 3 else _VOIGT2
+    S_mat = np.zeros(Sv.shape[:-1] + (d, d))
+    for v, (i, j) in enumerate(vo):
+        S_mat[..., i, j] = Sv[..., v]
+        S_mat[..., j, i] = Sv[..., v]
+    geo = np.einsum("eg,egai,egij,egbj->eab", wd, gradN, S_mat, gradN, optimize=True)
+    Kgeo = np.einsum("eab,ij->eaibj", geo, np.eye(d)).reshape(ne, elem.nnode * d, elem.nnode * d)
+    Fint = np.einsum("eg,egsn,egs->en", wd, B, Sv)
+    body = np.zeros(d) if body is None else body
+    Fe = body_force_vector(elem, Ns, detJ, w, body)
+    energy = np.einsum("eg,eg->e", wd, psi)
+    return energy, Fint - Fe, Kmat + Kgeo
+
+
+def neo_hooke_energy_dcontrol(element_type, num_gp, X, de, u, nu):
+    """d(energy)/d(de): psi is linear in (k, mu) and both are linear in E_gp = N.de."""
+    elem = ELEMENTS[element_type]
+    d = elem.dim
+    Ns, gradN, detJ, w = point_data(elem, X, num_gp)
+    ne = X.shape[0]
+    U = u.reshape(ne, elem.nnode, d)
+    F = np.einsum("egai,eaj->egji", gradN, U) + np.eye(d)
+    one = np.ones(F.shape[:-2])
+    psi1, _, _ = neo_hooke_point(F, one / (3.0 * (1.0 - 2.0 * nu)), one / (2.0 * (1.0 + nu)))
+    return np.einsum("g,eg,eg,ga->ea", w, detJ, psi1, Ns)
