@@ -1,0 +1,314 @@
+// extern "C" surface of libfolax_b200 (see include/folax_b200.h) + the host-buffer plan object.
+#include <vector>
+
+#include "assemble.cuh"
+#include "energy.cuh"
+
+namespace fol {
+int assemble_mech_f64(cudaStream_t, int, int, const AsmArgs<double>&);
+int assemble_mech_f32(cudaStream_t, int, int, const AsmArgs<float>&);
+int assemble_thermal_f64(cudaStream_t, int, int, const AsmArgs<double>&);
+int assemble_thermal_f32(cudaStream_t, int, int, const AsmArgs<float>&);
+int assemble_neohooke_f64(cudaStream_t, int, int, const AsmArgs<double>&);
+int assemble_neohooke_f32(cudaStream_t, int, int, const AsmArgs<float>&);
+int assemble_j2_f64(cudaStream_t, int, int, const AsmArgs<double>&);
+int assemble_j2_f32(cudaStream_t, int, int, const AsmArgs<float>&);
+int assemble_hex_mech_f64(cudaStream_t, const AsmArgs<double>&);
+
+template <class T>
+int energy_and_grads(cudaStream_t, int, int, int, const EnergyArgs<T>&);
+template <class T>
+int geometry_cache(cudaStream_t, int, int, long long, const T*, const int32_t*, T*);
+template <class T>
+int loss_reduce(cudaStream_t, long long, int, double, const T*, T*, T*, T*);
+template <class T>
+int scale_grads(cudaStream_t, long long, long long, long long, const T*, double, const uint8_t*, T*, T*);
+
+static bool valid_element(int e) { return e >= 0 && e <= 3; }
+
+template <class T>
+static int assemble_typed(cudaStream_t s, int physics, int element, int num_gp, int transpose, long long ne,
+                          const void* xyz, const int32_t* conn, const void* ctrl, const void* u, const uint8_t* dir,
+                          const double* params, void* ke, void* re, const void* st_in, void* st_out) {
+  AsmArgs<T> a;
+  a.xyz = (const T*)xyz;
+  a.conn = conn;
+  a.ctrl = (const T*)ctrl;
+  a.u = (const T*)u;
+  a.dir = dir;
+  a.ke = (T*)ke;
+  a.re = (T*)re;
+  a.state_in = (const T*)st_in;
+  a.state_out = (T*)st_out;
+  a.ne = ne;
+  a.transpose = transpose;
+  a.p = make_params<T>(params);
+  constexpr bool f64 = sizeof(T) == 8;
+  switch (physics) {
+    case FOL_MECHANICAL:
+      if constexpr (f64) return assemble_mech_f64(s, element, num_gp, a);
+      else return assemble_mech_f32(s, element, num_gp, a);
+    case FOL_THERMAL:
+      if constexpr (f64) return assemble_thermal_f64(s, element, num_gp, a);
+      else return assemble_thermal_f32(s, element, num_gp, a);
+    case FOL_NEOHOOKE:
+      if constexpr (f64) return assemble_neohooke_f64(s, element, num_gp, a);
+      else return assemble_neohooke_f32(s, element, num_gp, a);
+#ifdef FOL_HAVE_J2
+    case FOL_J2PLASTICITY:
+      if (!st_in || !st_out) return fail(FOL_ERR_INVALID, "J2 plasticity needs state_in/state_out");
+      if constexpr (f64) return assemble_j2_f64(s, element, num_gp, a);
+      else return assemble_j2_f32(s, element, num_gp, a);
+#endif
+  }
+  return fail(FOL_ERR_UNSUPPORTED, "fol_assemble_elements: unsupported physics");
+}
+
+}  // namespace fol
+
+using namespace fol;
+
+// ---- plan object (host-buffer entry point) -------------------------------------------------
+struct fol_plan {
+  int dtype, physics, element, num_gp, nnode, dim, dpn, nd;
+  long long ne, nn, ndof;
+  size_t esz;
+  double params[FOL_NUM_PARAMS];
+  cudaStream_t stream = nullptr;
+  void *xyz = nullptr, *ctrl = nullptr, *u = nullptr, *ke = nullptr, *re = nullptr, *R = nullptr;
+  int32_t *conn = nullptr, *adj_ptr = nullptr, *adj = nullptr, *work = nullptr, *dir_idx = nullptr;
+  uint8_t* dir = nullptr;
+};
+
+extern "C" {
+
+int fol_element_info(int element, int num_gp, int* nnode, int* dim, int* ngauss) {
+  FOL_REQUIRE(valid_element(element) && num_gp >= 1 && num_gp <= 3, "fol_element_info: bad element / num_gp");
+  if (nnode) *nnode = elem_nnode(element);
+  if (dim) *dim = elem_dim(element);
+  if (ngauss) *ngauss = elem_ngauss(element, num_gp);
+  return FOL_OK;
+}
+
+int fol_dofs_per_node(int physics, int element) {
+  if (!valid_element(element)) return FOL_ERR_INVALID;
+  return physics == FOL_THERMAL ? 1 : elem_dim(element);
+}
+
+int fol_assemble_elements(fol_stream_t s, int dtype, int physics, int element, int num_gp, int transpose, int64_t ne,
+                          int64_t nn, const void* xyz, const int32_t* conn, const void* ctrl, const void* u,
+                          const uint8_t* dir_flag, const double* params_host, void* ke_data, void* re_elem,
+                          const void* state_in, void* state_out) {
+  (void)nn;
+  FOL_REQUIRE(valid_element(element), "fol_assemble_elements: unknown element");
+  FOL_REQUIRE(num_gp >= 1 && num_gp <= 3, "fol_assemble_elements: num_gp must be 1, 2 or 3");
+  FOL_REQUIRE(xyz && conn && ctrl && u && dir_flag && ke_data && re_elem && params_host,
+              "fol_assemble_elements: null pointer");
+  FOL_REQUIRE(ne >= 0, "fol_assemble_elements: negative element count");
+  if (dtype == FOL_F64)
+    return assemble_typed<double>((cudaStream_t)s, physics, element, num_gp, transpose, ne, xyz, conn, ctrl, u,
+                                  dir_flag, params_host, ke_data, re_elem, state_in, state_out);
+  if (dtype == FOL_F32)
+    return assemble_typed<float>((cudaStream_t)s, physics, element, num_gp, transpose, ne, xyz, conn, ctrl, u,
+                                 dir_flag, params_host, ke_data, re_elem, state_in, state_out);
+  return fail(FOL_ERR_INVALID, "fol_assemble_elements: dtype must be FOL_F32 or FOL_F64");
+}
+
+int fol_geometry_cache(fol_stream_t s, int dtype, int element, int num_gp, int64_t ne, const void* xyz,
+                       const int32_t* conn, void* geom) {
+  FOL_REQUIRE(valid_element(element) && xyz && conn && geom, "fol_geometry_cache: bad arguments");
+  if (dtype == FOL_F64)
+    return geometry_cache<double>((cudaStream_t)s, element, num_gp, ne, (const double*)xyz, conn, (double*)geom);
+  return geometry_cache<float>((cudaStream_t)s, element, num_gp, ne, (const float*)xyz, conn, (float*)geom);
+}
+
+int64_t fol_energy_work_size(int64_t nn, int64_t nb) { return cdiv(nn, 128) * nb + nb + 8; }
+
+int fol_energy_and_grads(fol_stream_t s, int dtype, int physics, int element, int num_gp, int64_t ne, int64_t nn,
+                         int64_t nb, const void* geom, const int32_t* conn, const int32_t* adj_ptr,
+                         const int32_t* adj, const void* ctrl, const void* u, const double* params_host, void* grad_u,
+                         void* grad_k, void* energy, void* work) {
+  FOL_REQUIRE(valid_element(element), "fol_energy_and_grads: unknown element");
+  FOL_REQUIRE(geom && conn && adj_ptr && adj && ctrl && u && grad_u && energy && work && params_host,
+              "fol_energy_and_grads: null pointer");
+  FOL_REQUIRE(nb >= 1 && nb <= 65535LL * 2, "fol_energy_and_grads: batch size out of range");
+  const int nblocks = (int)cdiv(nn, 128);
+  if (dtype == FOL_F64) {
+    EnergyArgs<double> a{(const double*)geom, conn, adj_ptr, adj, (const double*)ctrl, (const double*)u,
+                         (double*)grad_u, (double*)grad_k, (double*)work, ne, nn, nb, make_params<double>(params_host)};
+    if (int rc = energy_and_grads<double>((cudaStream_t)s, physics, element, num_gp, a)) return rc;
+    // E_b = fixed-order sum of the block partials (exponent / scale are applied by fol_loss_reduce)
+    return loss_reduce<double>((cudaStream_t)s, nb, nblocks, 1.0, (const double*)work, (double*)energy,
+                               (double*)work + (size_t)nblocks * nb, (double*)work + (size_t)nblocks * nb + 4);
+  }
+  EnergyArgs<float> a{(const float*)geom, conn, adj_ptr, adj, (const float*)ctrl, (const float*)u,
+                      (float*)grad_u, (float*)grad_k, (float*)work, ne, nn, nb, make_params<float>(params_host)};
+  if (int rc = energy_and_grads<float>((cudaStream_t)s, physics, element, num_gp, a)) return rc;
+  return loss_reduce<float>((cudaStream_t)s, nb, nblocks, 1.0, (const float*)work, (float*)energy,
+                            (float*)work + (size_t)nblocks * nb, (float*)work + (size_t)nblocks * nb + 4);
+}
+
+int fol_loss_reduce(fol_stream_t s, int dtype, int64_t nb, double exponent, const void* energy, void* out4,
+                    void* scale) {
+  FOL_REQUIRE(energy && out4 && scale && nb >= 1, "fol_loss_reduce: bad arguments");
+  if (dtype == FOL_F64)
+    return loss_reduce<double>((cudaStream_t)s, nb, 0, exponent, nullptr, (double*)energy, (double*)out4,
+                               (double*)scale);
+  return loss_reduce<float>((cudaStream_t)s, nb, 0, exponent, nullptr, (float*)energy, (float*)out4, (float*)scale);
+}
+
+int fol_scale_grads(fol_stream_t s, int dtype, int64_t nb, int64_t ndof, int64_t nn, const void* scale,
+                    double upstream, const uint8_t* dir_flag, void* grad_u, void* grad_k) {
+  FOL_REQUIRE(scale && dir_flag && grad_u, "fol_scale_grads: null pointer");
+  if (dtype == FOL_F64)
+    return scale_grads<double>((cudaStream_t)s, nb, ndof, nn, (const double*)scale, upstream, dir_flag,
+                               (double*)grad_u, (double*)grad_k);
+  return scale_grads<float>((cudaStream_t)s, nb, ndof, nn, (const float*)scale, upstream, dir_flag, (float*)grad_u,
+                            (float*)grad_k);
+}
+
+// ---- plan ------------------------------------------------------------------------------------
+void fol_plan_destroy(fol_plan* p) {
+  if (!p) return;
+  void* bufs[] = {p->xyz, p->ctrl, p->u, p->ke, p->re, p->R, p->conn, p->adj_ptr, p->adj, p->work, p->dir_idx, p->dir};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+#define FOL_PLAN_CUDA(call)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (call);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      fol_plan_destroy(p);                                                                   \
+      return ::fol::fail(FOL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));  \
+    }                                                                                        \
+  } while (0)
+
+int fol_plan_create(fol_plan** plan, int dtype, int physics, int element, int num_gp, int64_t ne, int64_t nn,
+                    const void* xyz_host, const int32_t* conn_host, const int32_t* dir_idx_host, int64_t n_dir,
+                    const double* params_host) {
+  FOL_REQUIRE(plan && xyz_host && conn_host && params_host, "fol_plan_create: null pointer");
+  FOL_REQUIRE(valid_element(element) && num_gp >= 1 && num_gp <= 3, "fol_plan_create: bad element / num_gp");
+  FOL_REQUIRE(dtype == FOL_F32 || dtype == FOL_F64, "fol_plan_create: bad dtype");
+  FOL_REQUIRE(physics == FOL_MECHANICAL || physics == FOL_THERMAL || physics == FOL_NEOHOOKE,
+              "fol_plan_create: physics without history only");
+  fol_plan* p = new fol_plan();
+  p->dtype = dtype; p->physics = physics; p->element = element; p->num_gp = num_gp;
+  p->nnode = elem_nnode(element); p->dim = elem_dim(element);
+  p->dpn = physics == FOL_THERMAL ? 1 : p->dim;
+  p->nd = p->nnode * p->dpn;
+  p->ne = ne; p->nn = nn; p->ndof = nn * p->dpn;
+  p->esz = dtype == FOL_F64 ? 8 : 4;
+  for (int i = 0; i < FOL_NUM_PARAMS; ++i) p->params[i] = params_host[i];
+  FOL_PLAN_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  FOL_PLAN_CUDA(cudaMalloc(&p->xyz, p->esz * 3 * nn));
+  FOL_PLAN_CUDA(cudaMalloc(&p->ctrl, p->esz * nn));
+  FOL_PLAN_CUDA(cudaMalloc(&p->u, p->esz * p->ndof));
+  FOL_PLAN_CUDA(cudaMalloc(&p->R, p->esz * p->ndof));
+  FOL_PLAN_CUDA(cudaMalloc(&p->ke, p->esz * (size_t)ne * p->nd * p->nd));
+  FOL_PLAN_CUDA(cudaMalloc(&p->re, p->esz * (size_t)ne * p->nd));
+  FOL_PLAN_CUDA(cudaMalloc((void**)&p->conn, sizeof(int32_t) * (size_t)ne * p->nnode));
+  FOL_PLAN_CUDA(cudaMalloc((void**)&p->adj_ptr, sizeof(int32_t) * (size_t)(nn + 1)));
+  FOL_PLAN_CUDA(cudaMalloc((void**)&p->adj, sizeof(int32_t) * (size_t)ne * p->nnode));
+  FOL_PLAN_CUDA(cudaMalloc((void**)&p->work, sizeof(int32_t) * (size_t)nn));
+  FOL_PLAN_CUDA(cudaMalloc((void**)&p->dir, (size_t)p->ndof));
+  FOL_PLAN_CUDA(cudaMemcpyAsync(p->xyz, xyz_host, p->esz * 3 * nn, cudaMemcpyHostToDevice, p->stream));
+  FOL_PLAN_CUDA(cudaMemcpyAsync(p->conn, conn_host, sizeof(int32_t) * (size_t)ne * p->nnode, cudaMemcpyHostToDevice,
+                                p->stream));
+  if (n_dir > 0) {
+    FOL_PLAN_CUDA(cudaMalloc((void**)&p->dir_idx, sizeof(int32_t) * (size_t)n_dir));
+    FOL_PLAN_CUDA(cudaMemcpyAsync(p->dir_idx, dir_idx_host, sizeof(int32_t) * (size_t)n_dir, cudaMemcpyHostToDevice,
+                                  p->stream));
+  }
+  int rc = fol_dirichlet_flags(p->stream, p->dir_idx, n_dir, p->ndof, p->dir);
+  if (!rc) rc = fol_node_adjacency(p->stream, p->conn, ne, p->nnode, nn, p->adj_ptr, p->adj, p->work);
+  if (rc) {
+    fol_plan_destroy(p);
+    return rc;
+  }
+  FOL_PLAN_CUDA(cudaStreamSynchronize(p->stream));
+  *plan = p;
+  return FOL_OK;
+}
+
+fol_stream_t fol_plan_stream(fol_plan* p) { return p ? (fol_stream_t)p->stream : nullptr; }
+
+static int plan_run(fol_plan* p, int transpose, const void* ctrl, const void* u) {
+  int rc = fol_assemble_elements(p->stream, p->dtype, p->physics, p->element, p->num_gp, transpose, p->ne, p->nn,
+                                 p->xyz, p->conn, ctrl, u, p->dir, p->params, p->ke, p->re, nullptr, nullptr);
+  if (rc) return rc;
+  return fol_residual_gather(p->stream, p->dtype, p->nn, p->nnode, p->dpn, p->adj_ptr, p->adj, p->re, p->R);
+}
+
+int fol_plan_assemble_device(fol_plan* p, int transpose, const void* ctrl_dev, const void* u_dev, void** ke_dev,
+                             void** R_dev) {
+  FOL_REQUIRE(p && ctrl_dev && u_dev, "fol_plan_assemble_device: null pointer");
+  if (int rc = plan_run(p, transpose, ctrl_dev, u_dev)) return rc;
+  if (ke_dev) *ke_dev = p->ke;
+  if (R_dev) *R_dev = p->R;
+  return FOL_OK;
+}
+
+int fol_plan_assemble_host(fol_plan* p, int transpose, const void* ctrl_host, const void* u_host, void* ke_host,
+                           void* R_host) {
+  FOL_REQUIRE(p && ctrl_host && u_host && ke_host && R_host, "fol_plan_assemble_host: null pointer");
+  FOL_CUDA(cudaMemcpyAsync(p->ctrl, ctrl_host, p->esz * p->nn, cudaMemcpyHostToDevice, p->stream));
+  FOL_CUDA(cudaMemcpyAsync(p->u, u_host, p->esz * p->ndof, cudaMemcpyHostToDevice, p->stream));
+  if (int rc = plan_run(p, transpose, p->ctrl, p->u)) return rc;
+  FOL_CUDA(cudaMemcpyAsync(R_host, p->R, p->esz * p->ndof, cudaMemcpyDeviceToHost, p->stream));
+  FOL_CUDA(cudaMemcpyAsync(ke_host, p->ke, p->esz * (size_t)p->ne * p->nd * p->nd, cudaMemcpyDeviceToHost,
+                           p->stream));
+  FOL_CUDA(cudaStreamSynchronize(p->stream));
+  return FOL_OK;
+}
+
+}  // extern "C"
+
+// ---- FMA peak microbenchmark ------------------------------------------------------------------
+namespace fol {
+template <class T>
+__global__ void fma_peak_kernel(T* out, int iters) {
+  T a0 = (T)threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const T x = (T)1.0000001, y = (T)1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = a0 * x + y; a1 = a1 * x + y; a2 = a2 * x + y; a3 = a3 * x + y;
+    a4 = a4 * x + y; a5 = a5 * x + y; a6 = a6 * x + y; a7 = a7 * x + y;
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+template <class T>
+static int measure_peak(double* tflops) {
+  const int blocks = 148 * 8, threads = 256, iters = 1 << 14;
+  T* out = nullptr;
+  FOL_CUDA(cudaMalloc(&out, sizeof(T) * blocks * threads));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  fma_peak_kernel<T><<<blocks, threads>>>(out, iters);  // warm-up
+  float best = 1e30f;
+  for (int r = 0; r < 5; ++r) {
+    cudaEventRecord(e0);
+    fma_peak_kernel<T><<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  g_launches.fetch_add(6);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  FOL_CUDA(cudaGetLastError());
+  *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+  return FOL_OK;
+}
+}  // namespace fol
+
+extern "C" int fol_measure_fma_peak(int dtype, double* tflops) {
+  FOL_REQUIRE(tflops, "fol_measure_fma_peak: null pointer");
+  return dtype == FOL_F64 ? measure_peak<double>(tflops) : measure_peak<float>(tflops);
+}

@@ -1,0 +1,54 @@
+// Shared host-side plumbing of libfolax_b200: error strings, launch accounting, dtype dispatch.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include <string>
+
+#include "../../include/folax_b200.h"
+
+namespace fol {
+
+extern thread_local std::string g_last_error;
+extern std::atomic<long long> g_launches;
+
+inline int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+inline int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(FOL_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return FOL_OK;
+}
+
+#define FOL_CUDA(call)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (call);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return ::fol::fail(FOL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+#define FOL_REQUIRE(cond, msg) \
+  do {                         \
+    if (!(cond)) return ::fol::fail(FOL_ERR_INVALID, msg); \
+  } while (0)
+
+inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+// material / loss parameters in the arithmetic type of the call (see FOL_NUM_PARAMS)
+template <class T>
+struct Params {
+  T v[FOL_NUM_PARAMS];
+};
+template <class T>
+inline Params<T> make_params(const double* host) {
+  Params<T> p;
+  for (int i = 0; i < FOL_NUM_PARAMS; ++i) p.v[i] = host ? (T)host[i] : (T)0;
+  return p;
+}
+
+}  // namespace fol

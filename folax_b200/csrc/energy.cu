@@ -1,0 +1,90 @@
+// Instantiations + launchers of the batched energy / VJP kernels and the loss tail.
+#include "energy.cuh"
+
+namespace fol {
+
+template <class T, int ELEM, int ORDER, int PHYS>
+int launch_energy(cudaStream_t s, const EnergyArgs<T>& args) {
+  constexpr int BLOCK = 128;
+  // samples held in registers per thread: more for small elements
+  constexpr int ND = elem_nnode(ELEM) * phys_dpn(PHYS, ELEM);
+  constexpr int S = ND <= 4 ? 8 : (ND <= 8 ? 4 : 2);
+  dim3 grid((unsigned)cdiv(args.nn, BLOCK), (unsigned)cdiv(args.nb, S));
+  if (grid.x == 0 || grid.y == 0) return FOL_OK;
+  energy_grads_kernel<T, ELEM, ORDER, PHYS, S, BLOCK><<<grid, BLOCK, 0, s>>>(args);
+  return check_launch("energy_grads_kernel");
+}
+
+template <class T, int PHYS>
+int dispatch_energy(cudaStream_t s, int element, int num_gp, const EnergyArgs<T>& args) {
+#define FOL_CASE(E, O) \
+  if (element == E && num_gp == O) return launch_energy<T, E, O, PHYS>(s, args);
+  FOL_CASE(HEX, 1) FOL_CASE(HEX, 2) FOL_CASE(HEX, 3)
+  FOL_CASE(QUAD, 1) FOL_CASE(QUAD, 2) FOL_CASE(QUAD, 3)
+  FOL_CASE(TET, 1) FOL_CASE(TET, 2) FOL_CASE(TET, 3)
+  FOL_CASE(TRI, 1) FOL_CASE(TRI, 2) FOL_CASE(TRI, 3)
+#undef FOL_CASE
+  return fail(FOL_ERR_UNSUPPORTED, "unsupported element / num_gp");
+}
+
+template <class T>
+int energy_and_grads(cudaStream_t s, int physics, int element, int num_gp, const EnergyArgs<T>& a) {
+  if (physics == FOL_MECHANICAL) return dispatch_energy<T, MECH>(s, element, num_gp, a);
+  if (physics == FOL_THERMAL) return dispatch_energy<T, THERMAL>(s, element, num_gp, a);
+  if (physics == FOL_NEOHOOKE) return dispatch_energy<T, NEOHOOKE>(s, element, num_gp, a);
+  return fail(FOL_ERR_UNSUPPORTED, "fol_energy_and_grads: physics not supported yet");
+}
+template int energy_and_grads<double>(cudaStream_t, int, int, int, const EnergyArgs<double>&);
+template int energy_and_grads<float>(cudaStream_t, int, int, int, const EnergyArgs<float>&);
+
+template <class T, int ELEM>
+int launch_geom(cudaStream_t s, int num_gp, long long ne, const T* xyz, const int32_t* conn, T* geom) {
+#define FOL_CASE(O)                                                                                         \
+  if (num_gp == O) {                                                                                        \
+    const long long total = ne * elem_ngauss(ELEM, O);                                                      \
+    if (total == 0) return FOL_OK;                                                                          \
+    geometry_cache_kernel<T, ELEM, O><<<(unsigned)cdiv(total, 128), 128, 0, s>>>(xyz, conn, ne, geom);      \
+    return check_launch("geometry_cache_kernel");                                                           \
+  }
+  FOL_CASE(1) FOL_CASE(2) FOL_CASE(3)
+#undef FOL_CASE
+  return fail(FOL_ERR_UNSUPPORTED, "unsupported num_gp");
+}
+
+template <class T>
+int geometry_cache(cudaStream_t s, int element, int num_gp, long long ne, const T* xyz, const int32_t* conn, T* geom) {
+  switch (element) {
+    case HEX: return launch_geom<T, HEX>(s, num_gp, ne, xyz, conn, geom);
+    case QUAD: return launch_geom<T, QUAD>(s, num_gp, ne, xyz, conn, geom);
+    case TET: return launch_geom<T, TET>(s, num_gp, ne, xyz, conn, geom);
+    case TRI: return launch_geom<T, TRI>(s, num_gp, ne, xyz, conn, geom);
+  }
+  return fail(FOL_ERR_UNSUPPORTED, "unsupported element");
+}
+template int geometry_cache<double>(cudaStream_t, int, int, long long, const double*, const int32_t*, double*);
+template int geometry_cache<float>(cudaStream_t, int, int, long long, const float*, const int32_t*, float*);
+
+template <class T>
+int loss_reduce(cudaStream_t s, long long nb, int nblocks, double exponent, const T* partial, T* energy, T* out4,
+                T* scale) {
+  loss_reduce_kernel<T><<<1, 256, 0, s>>>(partial, nb, nblocks, exponent, energy, out4, scale);
+  return check_launch("loss_reduce_kernel");
+}
+template int loss_reduce<double>(cudaStream_t, long long, int, double, const double*, double*, double*, double*);
+template int loss_reduce<float>(cudaStream_t, long long, int, double, const float*, float*, float*, float*);
+
+template <class T>
+int scale_grads(cudaStream_t s, long long nb, long long ndof, long long nn, const T* scale, double up,
+                const uint8_t* dir, T* gu, T* gk) {
+  const long long m = ndof > nn ? ndof : nn;
+  dim3 grid((unsigned)cdiv(m, 256), (unsigned)nb);
+  if (grid.x == 0 || grid.y == 0) return FOL_OK;
+  scale_grads_kernel<T><<<grid, 256, 0, s>>>(nb, ndof, nn, scale, (T)up, dir, gu, gk);
+  return check_launch("scale_grads_kernel");
+}
+template int scale_grads<double>(cudaStream_t, long long, long long, long long, const double*, double, const uint8_t*,
+                                 double*, double*);
+template int scale_grads<float>(cudaStream_t, long long, long long, long long, const float*, double, const uint8_t*,
+                                float*, float*);
+
+}  // namespace fol

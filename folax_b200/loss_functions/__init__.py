@@ -1,0 +1,8 @@
+from .loss import Loss
+from .fe_loss import FiniteElementLoss
+from .mechanical import (MechanicalLoss, MechanicalLoss2DQuad, MechanicalLoss2DTri, MechanicalLoss3DHexa,
+                         MechanicalLoss3DTetra)
+from .thermal import ThermalLoss, ThermalLoss2DQuad, ThermalLoss2DTri, ThermalLoss3DHexa, ThermalLoss3DTetra
+from .mechanical_neohooke import (NeoHookeMechanicalLoss, NeoHookeMechanicalLoss2DQuad,
+                                  NeoHookeMechanicalLoss2DTri, NeoHookeMechanicalLoss3DHexa,
+                                  NeoHookeMechanicalLoss3DTetra)

@@ -1,0 +1,347 @@
+"""FiniteElementLoss: host side of the hot path, same API as fol/loss_functions/fe_loss.py:19-318.
+
+All arithmetic runs in the sm_100a kernels of libfolax_b200 (through the C ABI, include/
+folax_b200.h); this class only owns the device-resident *plan* of a mesh (coordinates,
+connectivity, Dirichlet flags, node->element adjacency, BCOO indices) and marshals pointers.
+PyTorch supplies device memory, streams and the autograd hook (the analogue of jax.custom_vjp).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..sparse import BCOO
+from ..tools import fol_error, fol_info
+from .loss import Loss
+
+
+class ElementInfo:
+    """What callers read off `loss.fe_element` (fol/geometries/geometry.py:12-47)."""
+
+    def __init__(self, element_type):
+        self.__name = element_type
+        self.code = _lib.ELEMENTS[element_type]
+        self.integration_method = "GI_GAUSS_1"
+        self.num_gp = 1
+
+    def GetName(self):
+        return self.__name
+
+    def SetGaussIntegrationMethod(self, gi_method: str):
+        order = {"GI_GAUSS_1": 1, "GI_GAUSS_2": 2, "GI_GAUSS_3": 3}.get(gi_method)
+        if order is None:
+            fol_error(f"{gi_method} integration method is not implemented.")
+        self.integration_method, self.num_gp = gi_method, order
+
+    def info(self):
+        a, d, g = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(_lib.load().fol_element_info(self.code, self.num_gp, C.byref(a), C.byref(d), C.byref(g)))
+        return a.value, d.value, g.value
+
+
+class _BatchLossFn(torch.autograd.Function):
+    """custom_vjp of ComputeBatchLoss: forward runs the fused energy+gradient kernel and the loss
+    tail, backward only rescales the saved (un-scaled) cotangents -- SURVEY.md A.7."""
+
+    @staticmethod
+    def forward(ctx, loss, batch_params, batch_dofs):
+        energy, grad_u, grad_k = loss._energy_and_grads(batch_params, batch_dofs)
+        out4 = torch.empty(4, dtype=loss.dtype, device=energy.device)
+        scale = torch.empty_like(energy)
+        _lib.check(_lib.load().fol_loss_reduce(_lib.stream_ptr(), loss._dt, energy.shape[0],
+                                               float(loss.loss_function_exponent), _lib.ptr(energy),
+                                               _lib.ptr(out4), _lib.ptr(scale)))
+        ctx.loss, ctx.grads, ctx.scale, ctx.used = loss, (grad_u, grad_k), scale, False
+        ctx.need = (ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+        ctx.mark_non_differentiable(energy)
+        return out4[0], out4[1], out4[2], out4[3], energy
+
+    @staticmethod
+    def backward(ctx, g_mean, g_min, g_max, g_mean2, _g_energy):
+        if ctx.used:
+            raise RuntimeError("ComputeBatchLoss: backward through the FFI loss a second time is not supported")
+        ctx.used = True
+        loss = ctx.loss
+        grad_u, grad_k = ctx.grads
+        up = 0.0
+        for g in (g_mean, g_mean2):
+            if g is not None:
+                up = up + g
+        up = float(up) if not isinstance(up, float) else up
+        nb = grad_u.shape[0]
+        _lib.check(_lib.load().fol_scale_grads(_lib.stream_ptr(), loss._dt, nb, loss.total_number_of_dofs,
+                                               loss.fe_mesh.GetNumberOfNodes(), _lib.ptr(ctx.scale), up,
+                                               _lib.ptr(loss._dir_flag), _lib.ptr(grad_u),
+                                               _lib.ptr(grad_k) if grad_k is not None else None))
+        return None, (grad_k if ctx.need[0] else None), (grad_u if ctx.need[1] else None)
+
+
+class FiniteElementLoss(Loss):
+    """FE-based loss; subclasses fix physics, compute_dims, ordered_dofs and element_type."""
+
+    physics = None  # key of _lib.PHYSICS
+
+    def __init__(self, name: str, loss_settings: dict, fe_mesh):
+        super().__init__(name)
+        self.loss_settings = loss_settings
+        self.dofs = self.loss_settings["ordered_dofs"]
+        self.element_type = self.loss_settings["element_type"]
+        self.fe_mesh = fe_mesh
+        if "dirichlet_bc_dict" not in self.loss_settings.keys():
+            fol_error("dirichlet_bc_dict should provided in the loss settings !", self.GetName())
+
+    # ------------------------------------------------------------------ setup
+    def _create_dofs_dict(self, dofs_list, dirichlet_bc_dict):
+        """fe_loss.py:34-55: dof-major, then boundary name, values broadcast per node set."""
+        d = len(dofs_list)
+        idx, val = [], []
+        for dof_index, dof in enumerate(dofs_list):
+            for boundary_name, boundary_value in dirichlet_bc_dict[dof].items():
+                nodes = np.asarray(self.fe_mesh.GetNodeSet(boundary_name), dtype=np.int64)
+                idx.append(d * nodes + dof_index)
+                val.append(np.full(nodes.shape, float(boundary_value)))
+        if idx:
+            self.dirichlet_indices = np.concatenate(idx).astype(np.int32)
+            self.dirichlet_values = np.concatenate(val)
+        else:
+            self.dirichlet_indices = np.zeros(0, dtype=np.int32)
+            self.dirichlet_values = np.zeros(0)
+        all_indices = np.arange(d * self.fe_mesh.GetNumberOfNodes())
+        self.non_dirichlet_indices = np.setdiff1d(all_indices, self.dirichlet_indices).astype(np.int32)
+
+    def _material_params(self):
+        """double[FOL_NUM_PARAMS] of include/folax_b200.h; subclasses fill it."""
+        return [0.0] * _lib.NUM_PARAMS
+
+    def Initialize(self, reinitialize=False) -> None:
+        if self.initialized and not reinitialize:
+            return
+        _lib.require_cuda()
+        lib = _lib.load()
+        self.dtype = {"float64": torch.float64, "float32": torch.float32}[
+            str(self.loss_settings.get("dtype", "float64")).replace("torch.", "")]
+        self._dt = _lib.dtype_code(self.dtype)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+        self.number_dofs_per_node = len(self.dofs)
+        self.total_number_of_dofs = len(self.dofs) * self.fe_mesh.GetNumberOfNodes()
+        self._create_dofs_dict(self.dofs, self.loss_settings["dirichlet_bc_dict"])
+        self.number_of_unknown_dofs = self.non_dirichlet_indices.size
+
+        self.fe_element = ElementInfo(self.element_type)
+        if "num_gp" in self.loss_settings.keys():
+            self.num_gp = self.loss_settings["num_gp"]
+            if self.num_gp not in (1, 2, 3):
+                raise ValueError(f" number gauss points {self.num_gp} is not supported ! ")
+        else:
+            self.loss_settings["num_gp"] = 1
+            self.num_gp = 1
+        self.fe_element.SetGaussIntegrationMethod(f"GI_GAUSS_{self.num_gp}")
+        if "compute_dims" not in self.loss_settings.keys():
+            raise ValueError(f"compute_dims must be provided in the loss settings of {self.GetName()}! ")
+        self.dim = self.loss_settings["compute_dims"]
+        self._nnode, self._edim, self._ngauss = self.fe_element.info()
+        expected = lib.fol_dofs_per_node(_lib.PHYSICS[self.physics], self.fe_element.code)
+        if expected != self.number_dofs_per_node:
+            raise ValueError(f"{self.GetName()}: {self.number_dofs_per_node} dofs per node given, "
+                             f"{self.physics} on {self.element_type} needs {expected}")
+        if self.loss_settings.get("parametric_boundary_learning"):
+            raise NotImplementedError("parametric_boundary_learning is not supported by folax_b200 yet")
+        self.loss_function_exponent = self.loss_settings.get("loss_function_exponent", 1.0)
+
+        # element batching of the reference (fe_loss.py:103-114) only bounds XLA memory; kept as
+        # attributes because callers may read them -- the kernels process the mesh in one launch
+        ne = self.fe_mesh.GetNumberOfElements(self.element_type)
+        self.adjusted_batch_size, self.num_element_batches = ne, 1
+
+        # ---- device-resident plan
+        conn = np.ascontiguousarray(self.fe_mesh.GetElementsNodes(self.element_type), dtype=np.int32)
+        nn = self.fe_mesh.GetNumberOfNodes()
+        if conn.ndim != 2 or conn.shape[1] != self._nnode:
+            raise ValueError(f"{self.element_type} connectivity must be (ne, {self._nnode})")
+        if ne and (conn.min() < 0 or conn.max() >= nn):
+            raise ValueError("connectivity refers to nodes outside the mesh")
+        self._ne, self._nn = ne, nn
+        self._nd = self._nnode * self.number_dofs_per_node
+        self._xyz = _lib.to_device(np.asarray(self.fe_mesh.GetNodesCoordinates(), dtype=np.float64), self.dtype)
+        self._conn = torch.as_tensor(conn, device=self.device)
+        self._dir_idx = torch.as_tensor(self.dirichlet_indices, device=self.device)
+        self._dir_val = _lib.to_device(self.dirichlet_values, self.dtype)
+        self._dir_flag = torch.empty(max(self.total_number_of_dofs, 1), dtype=torch.uint8, device=self.device)
+        s = _lib.stream_ptr()
+        _lib.check(lib.fol_dirichlet_flags(s, _lib.ptr(self._dir_idx), self._dir_idx.numel(),
+                                           self.total_number_of_dofs, _lib.ptr(self._dir_flag)))
+        self._adj_ptr = torch.empty(nn + 1, dtype=torch.int32, device=self.device)
+        self._adj = torch.empty(max(ne * self._nnode, 1), dtype=torch.int32, device=self.device)
+        work = torch.empty(max(nn, 1), dtype=torch.int32, device=self.device)
+        _lib.check(lib.fol_node_adjacency(s, _lib.ptr(self._conn), ne, self._nnode, nn, _lib.ptr(self._adj_ptr),
+                                          _lib.ptr(self._adj), _lib.ptr(work)))
+        self._indices = None   # BCOO indices, built on the first Jacobian request
+        self._geom = None      # geometry cache, built on the first batched-loss request
+        self._params = _lib.params_array(self._material_params())
+        self.initialized = True
+
+    # ------------------------------------------------------------------ small API
+    def GetFullDofVector(self, known_dofs, unknown_dofs):
+        """fe_loss.py:91-92: all_dofs[:, dirichlet_indices] = dirichlet_values (out of place)."""
+        u = self._as_batch(unknown_dofs, self.total_number_of_dofs).clone()
+        _lib.check(_lib.load().fol_apply_dirichlet(_lib.stream_ptr(), self._dt, u.shape[0],
+                                                   self.total_number_of_dofs, _lib.ptr(self._dir_idx),
+                                                   self._dir_idx.numel(), _lib.ptr(self._dir_val), 0, 1.0,
+                                                   _lib.ptr(u)))
+        return u
+
+    def GetParametersVectors(self, param_vector):
+        return param_vector
+
+    def Finalize(self) -> None:
+        pass
+
+    def GetNumberOfUnknowns(self):
+        return self.number_of_unknown_dofs
+
+    def GetTotalNumberOfDOFs(self):
+        return self.total_number_of_dofs
+
+    def GetDOFs(self):
+        return self.dofs
+
+    def ApplyDirichletBCOnDofVector(self, full_dof_vector, load_increment: float = 1.0):
+        """fe_loss.py:186-189: u[dirichlet_indices] = load_increment * dirichlet_values."""
+        u = _lib.to_device(full_dof_vector, self.dtype).reshape(1, -1).clone()
+        _lib.check(_lib.load().fol_apply_dirichlet(_lib.stream_ptr(), self._dt, 1, self.total_number_of_dofs,
+                                                   _lib.ptr(self._dir_idx), self._dir_idx.numel(),
+                                                   _lib.ptr(self._dir_val), 0, float(load_increment), _lib.ptr(u)))
+        return u.reshape(-1)
+
+    def _as_batch(self, x, width):
+        t = _lib.to_device(x, self.dtype) if not (isinstance(x, torch.Tensor) and x.is_cuda
+                                                   and x.dtype == self.dtype) else x
+        t = torch.atleast_2d(t)
+        t = t.reshape(t.shape[0], -1)
+        if t.shape[1] != width:
+            raise ValueError(f"{self.GetName()}: expected vectors of length {width}, got {t.shape[1]}")
+        return t.contiguous()
+
+    # ------------------------------------------------------------------ residual + Jacobian
+    def _bcoo_indices(self):
+        if self._indices is None:
+            n = self._ne * self._nd * self._nd
+            self._indices = torch.empty((n, 2), dtype=torch.int32, device=self.device)
+            _lib.check(_lib.load().fol_bcoo_indices(_lib.stream_ptr(), _lib.ptr(self._conn), self._ne,
+                                                    self._nnode, self.number_dofs_per_node,
+                                                    _lib.ptr(self._indices)))
+        return self._indices
+
+    def _assemble(self, controls, dofs, transpose, ke_out=None, state_in=None, state_out=None):
+        lib = _lib.load()
+        ctrl = _lib.to_device(controls, self.dtype).reshape(-1)
+        u = _lib.to_device(dofs, self.dtype).reshape(-1)
+        if ctrl.numel() != self._nn or u.numel() != self.total_number_of_dofs:
+            raise ValueError(f"{self.GetName()}: controls must have {self._nn} entries and dofs "
+                             f"{self.total_number_of_dofs}")
+        data = ke_out if ke_out is not None else torch.empty(self._ne * self._nd * self._nd, dtype=self.dtype,
+                                                             device=self.device)
+        re = torch.empty(max(self._ne * self._nd, 1), dtype=self.dtype, device=self.device)
+        R = torch.empty(self.total_number_of_dofs, dtype=self.dtype, device=self.device)
+        s = _lib.stream_ptr()
+        _lib.check(lib.fol_assemble_elements(s, self._dt, _lib.PHYSICS[self.physics], self.fe_element.code,
+                                             self.num_gp, int(bool(transpose)), self._ne, self._nn,
+                                             _lib.ptr(self._xyz), _lib.ptr(self._conn), _lib.ptr(ctrl), _lib.ptr(u),
+                                             _lib.ptr(self._dir_flag), self._params, _lib.ptr(data), _lib.ptr(re),
+                                             _lib.ptr(state_in), _lib.ptr(state_out)))
+        _lib.check(lib.fol_residual_gather(s, self._dt, self._nn, self._nnode, self.number_dofs_per_node,
+                                           _lib.ptr(self._adj_ptr), _lib.ptr(self._adj), _lib.ptr(re), _lib.ptr(R)))
+        return data, R
+
+    def ComputeJacobianMatrixAndResidualVector(self, total_control_vars, total_primal_vars,
+                                               transpose_jacobian: bool = False, new_implementation: bool = False):
+        """fe_loss.py:264-318 -> (BCOO with duplicates, residual vector)."""
+        data, R = self._assemble(total_control_vars, total_primal_vars, transpose_jacobian)
+        jac = BCOO((data, self._bcoo_indices()), shape=(self.total_number_of_dofs, self.total_number_of_dofs))
+        return jac, R
+
+    def ComputeElement(self, elem_xyz, elem_controls, elem_dofs):
+        """Single-element evaluation (the unit-test entry point): (energy, re (nd,1), Ke (nd,nd)).
+        Runs the same kernel on a one-element mesh."""
+        lib = _lib.load()
+        A, nd = self._nnode, self._nd
+        xyz = _lib.to_device(elem_xyz, self.dtype).reshape(A, 3)
+        ctrl = _lib.to_device(elem_controls, self.dtype).reshape(-1)
+        if ctrl.numel() == 1:
+            ctrl = ctrl.expand(A).contiguous()
+        u = _lib.to_device(elem_dofs, self.dtype).reshape(nd)
+        conn = torch.arange(A, dtype=torch.int32, device=self.device).reshape(1, A)
+        flags = torch.zeros(nd, dtype=torch.uint8, device=self.device)
+        ke = torch.empty(nd * nd, dtype=self.dtype, device=self.device)
+        re = torch.empty(nd, dtype=self.dtype, device=self.device)
+        _lib.check(lib.fol_assemble_elements(_lib.stream_ptr(), self._dt, _lib.PHYSICS[self.physics],
+                                             self.fe_element.code, self.num_gp, 0, 1, A, _lib.ptr(xyz),
+                                             _lib.ptr(conn), _lib.ptr(ctrl), _lib.ptr(u), _lib.ptr(flags),
+                                             self._params, _lib.ptr(ke), _lib.ptr(re), None, None))
+        energy = self._element_energy(xyz, conn, ctrl, u, re)
+        return energy, re.reshape(nd, 1), ke.reshape(nd, nd)
+
+    def _element_energy(self, xyz, conn, ctrl, u, re):
+        # mechanical.py:116-117 / thermal.py:45-49: energy = u^T stop_gradient(re)
+        return torch.dot(u, re)
+
+    # ------------------------------------------------------------------ batched loss
+    def _geometry_cache(self):
+        if self._geom is None:
+            width = self._nnode * self._edim + 1
+            self._geom = torch.empty(max(self._ne * self._ngauss * width, 1), dtype=self.dtype, device=self.device)
+            _lib.check(_lib.load().fol_geometry_cache(_lib.stream_ptr(), self._dt, self.fe_element.code,
+                                                      self.num_gp, self._ne, _lib.ptr(self._xyz),
+                                                      _lib.ptr(self._conn), _lib.ptr(self._geom)))
+        return self._geom
+
+    _has_control_gradient = True
+
+    def _energy_and_grads(self, batch_params, batch_dofs):
+        """(E_b, dE_b/du_b (un-masked assembled residual), dE_b/dK_b) for BC-applied dofs."""
+        lib = _lib.load()
+        nb = batch_dofs.shape[0]
+        geom = self._geometry_cache()
+        grad_u = torch.empty_like(batch_dofs)
+        grad_k = torch.empty_like(batch_params) if self._has_control_gradient else None
+        energy = torch.empty(nb, dtype=self.dtype, device=self.device)
+        work = torch.empty(lib.fol_energy_work_size(self._nn, nb), dtype=self.dtype, device=self.device)
+        _lib.check(lib.fol_energy_and_grads(_lib.stream_ptr(), self._dt, _lib.PHYSICS[self.physics],
+                                            self.fe_element.code, self.num_gp, self._ne, self._nn, nb,
+                                            _lib.ptr(geom), _lib.ptr(self._conn), _lib.ptr(self._adj_ptr),
+                                            _lib.ptr(self._adj), _lib.ptr(batch_params), _lib.ptr(batch_dofs),
+                                            self._params, _lib.ptr(grad_u), _lib.ptr(grad_k), _lib.ptr(energy),
+                                            _lib.ptr(work)))
+        return energy, grad_u, grad_k
+
+    def ComputeBatchLoss(self, batch_params, batch_dofs):
+        """fe_loss.py:250-262 -> (mean_b E_b^p, (min, max, mean)); differentiable w.r.t. both inputs
+        (torch.autograd.Function = the custom_vjp of the FFI call)."""
+        params = self._as_batch(batch_params, self._nn)
+        dofs = self._as_batch(batch_dofs, self.total_number_of_dofs)
+        full = _ApplyDirichlet.apply(self, dofs)
+        mean, mn, mx, mean2, _ = _BatchLossFn.apply(self, params, full)
+        return mean, (mn, mx, mean2)
+
+    def ComputeTotalEnergy(self, total_control_vars, total_primal_vars):
+        """fe_loss.py:175-176: sum of element energies for one sample (no Dirichlet overwrite)."""
+        params = self._as_batch(total_control_vars, self._nn)
+        dofs = self._as_batch(total_primal_vars, self.total_number_of_dofs)
+        energy, _, _ = self._energy_and_grads(params, dofs)
+        return energy[0]
+
+
+class _ApplyDirichlet(torch.autograd.Function):
+    """u -> u with Dirichlet entries overwritten (fe_loss.py:91-92); the cotangent is cut there."""
+
+    @staticmethod
+    def forward(ctx, loss, dofs):
+        ctx.loss = loss
+        return loss.GetFullDofVector(None, dofs)
+
+    @staticmethod
+    def backward(ctx, g):
+        # fol_scale_grads already zeroed the Dirichlet entries of the incoming cotangent
+        return None, g

@@ -1,0 +1,161 @@
+/* folax_b200 -- C ABI of the B200 (sm_100a) finite-element assembly / physics-loss kernels.
+ *
+ * Drop-in boundary for the hot path of Neural-Mechanics-Lab/folax `fol/loss_functions`.
+ * The reference's only FFI precedent is the XLA typed-FFI handler pair of
+ *   fol/loss_functions/ffi_functions/kr_small_displacement_element.cc:293-334
+ * (`compute_nodal_residuals`, `compute_elements`: stream from PlatformStream<cudaStream_t>,
+ * device buffers coords (nn,3), connectivity (ne,a) S32, properties, solution -> lhs (ne,nd,nd),
+ * rhs (ne,nd)).  Every entry point below keeps that shape: a stream, raw device pointers,
+ * explicit sizes, outputs preallocated by the caller, nothing retained, nothing synchronised.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - connectivity / indices are int32 (the reference requires S32, ...cc:102, 320);
+ *   - element DOF vector is node-major: local i = a*d + k  <->  global d*node + k
+ *     (fol/loss_functions/fe_loss.py:163-164, 178-181);
+ *   - return value 0 = success, <0 = error; fol_last_error() gives the message of the calling
+ *     thread's last failure (the reference returns ffi::Error::InvalidArgument/Internal,
+ *     ...cc:56, 218-223);
+ *   - `dtype` selects the arithmetic type of all floating-point buffers of the call.
+ */
+#ifndef FOLAX_B200_H
+#define FOLAX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fol_stream_t; /* cudaStream_t */
+
+enum fol_dtype { FOL_F32 = 0, FOL_F64 = 1 };
+/* fol/geometries/__init__.py:18-21 (fe_element_dict keys) */
+enum fol_element { FOL_HEXAHEDRON = 0, FOL_QUAD = 1, FOL_TETRA = 2, FOL_TRIANGLE = 3 };
+/* fol/loss_functions: mechanical.py, thermal.py, mechanical_neohooke.py, mechanical_elastoplasticity.py */
+enum fol_physics { FOL_MECHANICAL = 0, FOL_THERMAL = 1, FOL_NEOHOOKE = 2, FOL_J2PLASTICITY = 3 };
+
+#define FOL_OK 0
+#define FOL_ERR_INVALID (-1)
+#define FOL_ERR_CUDA (-2)
+#define FOL_ERR_UNSUPPORTED (-3)
+
+#define FOL_NUM_PARAMS 12
+/* material / loss parameters, always passed as double[FOL_NUM_PARAMS] on the HOST:
+ *   [0] young_modulus  [1] poisson_ratio  [2..4] body force (mechanical.py:26 "body_foce")
+ *   thermal: [5] beta  [6] c   (thermal.py:21-26)
+ *   J2:      [5] yield_limit  [6] iso_hardening_parameter_1  [7] iso_hardening_param_2
+ *            (mechanical_elastoplasticity.py:22-30)                                       */
+
+const char* fol_last_error(void);
+int fol_version(void);
+/* number of kernels launched by this library in the calling process (bench `gpu_launches`) */
+int64_t fol_launch_count(void);
+
+/* element table: nodes per element, spatial dim, Gauss points of integration order num_gp */
+int fol_element_info(int element, int num_gp, int* nnode, int* dim, int* ngauss);
+/* dofs per node of a physics on an element (1 for thermal, dim otherwise) */
+int fol_dofs_per_node(int physics, int element);
+
+/* ---- one-off integer plan kernels (bit-exact) ------------------------------------------- */
+
+/* BCOO index pairs of ComputeElementJacobianIndices (fe_loss.py:178-184, 313-314):
+ * indices[(e*nd*nd + i*nd + j)*2 + {0,1}] = (gdof(e,i), gdof(e,j)). */
+int fol_bcoo_indices(fol_stream_t s, const int32_t* conn, int64_t ne, int nnode, int dofs_per_node,
+                     int32_t* indices);
+
+/* dir_flag[ndof] = 1 on Dirichlet dofs else 0 (BC_vector / mask_BC_vector, fe_loss.py:268-271) */
+int fol_dirichlet_flags(fol_stream_t s, const int32_t* dirichlet_indices, int64_t n_dirichlet,
+                        int64_t ndof, uint8_t* dir_flag);
+
+/* node -> (element, local node) adjacency in CSR form, entries e*nnode+a sorted ascending:
+ * the fixed summation order of the atomics-free residual gather (replaces the scatter-add of
+ * fe_loss.py:301-306).  adj_ptr has nn+1 entries, adj has ne*nnode entries;
+ * `work` needs nn int32 of scratch. */
+int fol_node_adjacency(fol_stream_t s, const int32_t* conn, int64_t ne, int nnode, int64_t nn,
+                       int32_t* adj_ptr, int32_t* adj, int32_t* work);
+
+/* ---- residual + Jacobian assembly (fe_loss.py:264-318) ----------------------------------- */
+
+/* Element stage: gather -> ComputeElement -> optional transpose -> Dirichlet row mask, writes
+ *   ke_data[e*nd*nd + i*nd + j] = Ke'[i,j]            (the BCOO `data`, fe_loss.py:299)
+ *   re_elem[e*nd + i]           = re'[i]              (masked element residuals)
+ * state_in/state_out: (ne, ngauss, 7|4) Gauss-point history, J2 only (else NULL).
+ * u is the full dof vector (ndof), ctrl the nodal control field (nn). */
+int fol_assemble_elements(fol_stream_t s, int dtype, int physics, int element, int num_gp,
+                          int transpose, int64_t ne, int64_t nn, const void* xyz,
+                          const int32_t* conn, const void* ctrl, const void* u,
+                          const uint8_t* dir_flag, const double* params_host, void* ke_data,
+                          void* re_elem, const void* state_in, void* state_out);
+
+/* Residual stage: R[d*n+k] = sum over adjacency (fixed order) of re_elem -- deterministic. */
+int fol_residual_gather(fol_stream_t s, int dtype, int64_t nn, int nnode, int dofs_per_node,
+                        const int32_t* adj_ptr, const int32_t* adj, const void* re_elem,
+                        void* residual);
+
+/* ---- batched physics loss + VJP (fe_loss.py:250-262 and its JAX-AD gradient) -------------- */
+
+/* per-element, per-Gauss-point geometry factors shared by all samples:
+ * geom[e][g][0..a*dim-1] = grad N (a, dim), geom[e][g][a*dim] = w*detJ.   */
+int fol_geometry_cache(fol_stream_t s, int dtype, int element, int num_gp, int64_t ne,
+                       const void* xyz, const int32_t* conn, void* geom);
+
+/* For every sample b (rows of ctrl (nb, nn) and u (nb, ndof), Dirichlet entries of u already
+ * overwritten, fe_loss.py:255):
+ *   grad_u[b]  = assembled, UN-masked residual R(u_b)      (= dE_b/du_b)
+ *   grad_k[b]  = dE_b/dK_b                                  (NULL for mechanical: it is zero)
+ *   energy[b]  = E_b = sum_e energy_e                       (before the exponent)
+ * Deterministic (node-centric fixed-order sums). `work` needs nb*gridDim partials; pass
+ * fol_energy_work_size() doubles/floats. */
+int64_t fol_energy_work_size(int64_t nn, int64_t nb);
+int fol_energy_and_grads(fol_stream_t s, int dtype, int physics, int element, int num_gp,
+                         int64_t ne, int64_t nn, int64_t nb, const void* geom,
+                         const int32_t* conn, const int32_t* adj_ptr, const int32_t* adj,
+                         const void* ctrl, const void* u, const double* params_host,
+                         void* grad_u, void* grad_k, void* energy, void* work);
+
+/* loss tail: L = mean_b E_b^p, stats = (min, max, mean) of E_b^p, scale[b] = p E_b^(p-1)/nb.
+ * out[0..3] = L, min, max, mean (device). */
+int fol_loss_reduce(fol_stream_t s, int dtype, int64_t nb, double exponent, const void* energy,
+                    void* out4, void* scale);
+
+/* backward: grad_u[b,:] *= g*scale[b], zeroed at Dirichlet dofs; grad_k[b,:] *= g*scale[b]. */
+int fol_scale_grads(fol_stream_t s, int dtype, int64_t nb, int64_t ndof, int64_t nn,
+                    const void* scale, double upstream, const uint8_t* dir_flag, void* grad_u,
+                    void* grad_k);
+
+/* u[b, dirichlet_indices] = values (GetFullDofVector, fe_loss.py:91-92) or, when
+ * per_sample != 0, values is (nb, n_dirichlet) (parametric boundary learning, :94-95).
+ * load_factor multiplies the values (ApplyDirichletBCOnDofVector, :186-189). */
+int fol_apply_dirichlet(fol_stream_t s, int dtype, int64_t nb, int64_t ndof,
+                        const int32_t* dirichlet_indices, int64_t n_dirichlet, const void* values,
+                        int per_sample, double load_factor, void* u);
+
+/* ---- host-buffer entry point (what a non-GPU caller binds; used for the e2e measurement) -- */
+
+typedef struct fol_plan fol_plan;
+/* Builds the device-resident mesh plan (coords, connectivity, adjacency, flags) from HOST
+ * arrays; owns its device memory until fol_plan_destroy. */
+int fol_plan_create(fol_plan** plan, int dtype, int physics, int element, int num_gp,
+                    int64_t ne, int64_t nn, const void* xyz_host, const int32_t* conn_host,
+                    const int32_t* dirichlet_indices_host, int64_t n_dirichlet,
+                    const double* params_host);
+void fol_plan_destroy(fol_plan* plan);
+/* HOST in (ctrl, u) -> HOST out (ke_data (ne*nd*nd), residual (ndof)); copies and kernels are
+ * issued on the plan's stream, returns after the outputs are on the host. Host buffers should
+ * be pinned for full PCIe rate. */
+int fol_plan_assemble_host(fol_plan* plan, int transpose, const void* ctrl_host,
+                           const void* u_host, void* ke_data_host, void* residual_host);
+/* same plan, device-resident outputs owned by the plan (for timing without the copies) */
+int fol_plan_assemble_device(fol_plan* plan, int transpose, const void* ctrl_dev,
+                             const void* u_dev, void** ke_data_dev, void** residual_dev);
+fol_stream_t fol_plan_stream(fol_plan* plan);
+
+/* ---- measurement helpers ------------------------------------------------------------------ */
+/* FP64 (or FP32) FMA peak microbenchmark: returns achieved TFLOP/s through *tflops. */
+int fol_measure_fma_peak(int dtype, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOLAX_B200_H */

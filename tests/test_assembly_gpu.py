@@ -1,0 +1,130 @@
+"""GPU parity of the residual + Jacobian assembly against the NumPy oracle (through the C ABI).
+
+Bars (BASELINE.json north_star): sparsity pattern / indices bit-exact; values within 1e-12
+relative in float64 and 1e-5 in float32 -- measured norm-wise (atol = tol * max|ref|), because
+the reference's own scatter order is unspecified."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import assembly
+from tests import gpu_helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"float64": 1e-12, "float32": 1e-5}
+
+
+def _close(actual, ref, tol):
+    ref = np.asarray(ref)
+    scale = np.abs(ref).max() if ref.size else 1.0
+    err = np.abs(np.asarray(actual, dtype=np.float64) - ref).max() if ref.size else 0.0
+    assert err <= tol * max(scale, 1e-300), f"max err {err:.3e} vs scale {scale:.3e}"
+
+
+CASES = [(p, e, g) for p in ("mechanical", "thermal", "neohooke")
+         for e, gs in (("hexahedron", (1, 2, 3)), ("quad", (1, 2, 3)), ("tetra", (1, 2, 3)), ("triangle", (1, 2, 3)))
+         for g in gs]
+
+
+@pytest.mark.parametrize("physics,etype,num_gp", CASES)
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_assembly_matches_oracle(physics, etype, num_gp, dtype):
+    mesh = H.make_mesh(etype, 4 if etype in ("hexahedron", "tetra") else 7, seed=num_gp)
+    extra = {"body_foce": [0.3, -0.2, 0.1][: 3 if etype in ("hexahedron", "tetra") else 2]} if physics != "thermal" else {"beta": 2.0, "c": 4}
+    loss = H.make_loss(physics, etype, mesh, num_gp, dtype, extra)
+    K, u = H.fields(physics, mesh, loss, seed=num_gp)
+    if dtype == "float32":   # the oracle sees exactly the rounded inputs the kernel sees
+        K, u = K.astype(np.float32).astype(np.float64), u.astype(np.float32).astype(np.float64)
+    for transpose in (False, True):
+        jac, R = loss.ComputeJacobianMatrixAndResidualVector(K, u, transpose_jacobian=transpose)
+        coords = np.asarray(mesh.GetNodesCoordinates())
+        if dtype == "float32":
+            coords = coords.astype(np.float32).astype(np.float64)
+        data, idx, Rref = assembly.assemble(physics, etype, num_gp, coords, mesh.GetElementsNodes(etype), K, u,
+                                            loss.dirichlet_indices, H.oracle_params(loss), transpose)
+        got_idx = jac.indices.cpu().numpy()
+        assert got_idx.dtype == np.int32 and np.array_equal(got_idx, idx), "BCOO indices must be bit-exact"
+        assert jac.shape == (loss.total_number_of_dofs,) * 2
+        _close(jac.data.cpu().numpy(), data, TOL[dtype])
+        _close(R.cpu().numpy(), Rref, TOL[dtype] * 4)
+        # structural zeros / kept diagonals of Dirichlet rows are exact
+        ref_zero = data == 0.0
+        assert np.array_equal(jac.data.cpu().numpy()[ref_zero], data[ref_zero])
+
+
+def test_determinism_and_todense():
+    mesh = H.make_mesh("hexahedron", 5)
+    loss = H.make_loss("mechanical", "hexahedron", mesh, 2)
+    K, u = H.fields("mechanical", mesh, loss)
+    j1, r1 = loss.ComputeJacobianMatrixAndResidualVector(K, u)
+    j2, r2 = loss.ComputeJacobianMatrixAndResidualVector(K, u)
+    assert torch.equal(j1.data, j2.data) and torch.equal(r1, r2), "assembly must be run-to-run bit-identical"
+    dense = j1.todense().cpu().numpy()
+    free = np.asarray(loss.non_dirichlet_indices)
+    sub = dense[np.ix_(free, free)]
+    np.testing.assert_allclose(sub, sub.T, atol=1e-13)          # K_ff symmetric
+    v = np.random.default_rng(1).standard_normal(loss.total_number_of_dofs)
+    np.testing.assert_allclose((j1 @ v).cpu().numpy(), dense @ v, atol=1e-12)
+    for r in loss.dirichlet_indices:                            # row mask: only the diagonal survives
+        row = dense[r].copy()
+        assert row[r] != 0.0
+        row[r] = 0.0
+        assert not row.any()
+
+
+def test_linear_residual_is_K_times_u():
+    """Linearity property usable at any size: with no Dirichlet set and zero body force,
+    R(u) = J u and R(a u1 + b u2) = a R(u1) + b R(u2)."""
+    mesh = H.make_mesh("hexahedron", 6)
+    from folax_b200.loss_functions import MechanicalLoss3DHexa
+    loss = MechanicalLoss3DHexa("free", {"dirichlet_bc_dict": {"Ux": {}, "Uy": {}, "Uz": {}},
+                                         "material_dict": dict(H.MATERIAL)}, mesh)
+    loss.Initialize()
+    K, u1 = H.fields("mechanical", mesh, loss, seed=1)
+    _, u2 = H.fields("mechanical", mesh, loss, seed=2)
+    J, R1 = loss.ComputeJacobianMatrixAndResidualVector(K, u1)
+    _, R2 = loss.ComputeJacobianMatrixAndResidualVector(K, u2)
+    _, R12 = loss.ComputeJacobianMatrixAndResidualVector(K, 2.0 * u1 - 3.0 * u2)
+    scale = R1.abs().max().item()
+    assert (J @ u1 - R1).abs().max().item() <= 1e-12 * scale
+    assert (2.0 * R1 - 3.0 * R2 - R12).abs().max().item() <= 1e-12 * scale * 5
+    # rigid translation produces no force
+    t = np.tile([0.3, -0.1, 0.2], mesh.GetNumberOfNodes())
+    _, Rt = loss.ComputeJacobianMatrixAndResidualVector(K, t)
+    assert Rt.abs().max().item() <= 1e-13
+
+
+def test_unstructured_tetra_fixture():
+    """coarse_sphere.mdpa (reference fixture, 85 nodes / 249 tets): unstructured adjacency."""
+    import os
+    import folax_b200
+    from folax_b200.loss_functions import MechanicalLoss3DTetra
+    m = folax_b200.Mesh("s", "coarse_sphere.mdpa", os.path.join(os.path.dirname(__file__), "meshes"))
+    m.Initialize()
+    bc = {d: {"Partial_Skin_Part": 0.05} for d in ("Ux", "Uy", "Uz")}
+    loss = MechanicalLoss3DTetra("sphere", {"dirichlet_bc_dict": bc, "material_dict": dict(H.MATERIAL)}, m)
+    loss.Initialize()
+    K, u = H.fields("mechanical", m, loss, seed=3)
+    jac, R = loss.ComputeJacobianMatrixAndResidualVector(K, u)
+    data, idx, Rref = assembly.assemble("mechanical", "tetra", 1, np.asarray(m.GetNodesCoordinates()),
+                                        m.GetElementsNodes("tetra"), K, u, loss.dirichlet_indices,
+                                        H.oracle_params(loss))
+    assert np.array_equal(jac.indices.cpu().numpy(), idx)
+    _close(jac.data.cpu().numpy(), data, 1e-12)
+    _close(R.cpu().numpy(), Rref, 4e-12)
+
+
+def test_empty_dirichlet_and_single_element():
+    mesh = H.make_mesh("quad", 1, perturb=0)
+    from folax_b200.loss_functions import ThermalLoss2DQuad
+    loss = ThermalLoss2DQuad("one", {"dirichlet_bc_dict": {"T": {}}}, mesh)
+    loss.Initialize()
+    assert loss.GetNumberOfUnknowns() == 4 and loss.dirichlet_indices.size == 0
+    jac, R = loss.ComputeJacobianMatrixAndResidualVector(np.ones(4), np.arange(4.0))
+    data, idx, Rref = assembly.assemble("thermal", "quad", 2, np.asarray(mesh.GetNodesCoordinates()),
+                                        mesh.GetElementsNodes("quad"), np.ones(4), np.arange(4.0),
+                                        loss.dirichlet_indices, {})
+    assert np.array_equal(jac.indices.cpu().numpy(), idx)
+    _close(jac.data.cpu().numpy(), data, 1e-12)
+    _close(R.cpu().numpy(), Rref, 1e-12)

@@ -1,0 +1,71 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every
+symbol that include/folax_b200.h declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from folax_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.load()
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "folax_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fol_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    names = _declared_symbols()
+    assert len(names) >= 20
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in include/folax_b200.h but not exported"
+
+
+def test_binding_covers_header(lib):
+    assert set(_declared_symbols()) == set(_lib.SIGNATURES), "ctypes SIGNATURES out of sync with the header"
+
+
+def test_element_table(lib):
+    a, d, g = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    expect = {("hexahedron", 2): (8, 3, 8), ("hexahedron", 3): (8, 3, 27), ("quad", 2): (4, 2, 4),
+              ("tetra", 1): (4, 3, 1), ("tetra", 2): (4, 3, 4), ("triangle", 3): (3, 2, 4)}
+    for (name, order), want in expect.items():
+        assert lib.fol_element_info(_lib.ELEMENTS[name], order, ctypes.byref(a), ctypes.byref(d),
+                                    ctypes.byref(g)) == 0
+        assert (a.value, d.value, g.value) == want
+    assert lib.fol_element_info(7, 2, None, None, None) != 0
+    assert b"bad element" in lib.fol_last_error()
+    assert lib.fol_dofs_per_node(_lib.PHYSICS["thermal"], 0) == 1
+    assert lib.fol_dofs_per_node(_lib.PHYSICS["mechanical"], 1) == 2
+    assert lib.fol_version() >= 100
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import folax_b200
+    from folax_b200.loss_functions import ThermalLoss2DQuad
+    mesh = folax_b200.create_2D_square_mesh(1.0, 3)
+    loss = ThermalLoss2DQuad("t", {"dirichlet_bc_dict": {"T": {"left": 1.0, "right": 0.1}}}, mesh)
+    with pytest.raises(_lib.FolaxError):
+        loss.Initialize()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "folax_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
