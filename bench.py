@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the folax hot path on B200 (Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n 128]
+
+Metric (BASELINE.json): assembled elements/s (residual + Jacobian), 3-D hex linear elasticity,
+float64, 128^3 elements per GPU (configs[1]).  One JSON line on stdout (rank 0).
+  value       device-resident inputs, whole job (all ranks), CUDA-event timed, max over ranks
+  e2e         same metric through the host-buffer C-ABI call fol_plan_assemble_host (pinned host
+              inputs -> H2D, kernels, D2H of the BCOO data + residual inside the timed region)
+  roofline    dominant kernel (element stage) vs measured HBM copy bandwidth
+  cpu_baseline  NumPy oracle (port of the reference arithmetic) on the host cores, bounded sample
+  fol_loss_grad secondary metric: FOL physics loss + VJP samples/s (thermal 256x256 quads)
+`--impl reference` times the CPU port alone (the reference itself needs JAX, absent here).
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+ALG_BYTES_PER_ELEMENT_F64 = 4720.0   # 4608 Ke + 32 conn + 56 nodal in + 24 residual
+MATERIAL = {"young_modulus": 1.0, "poisson_ratio": 0.3}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index=0, period=0.1):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.period = period
+
+    def _run(self):
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------ CPU leg
+def cpu_assembly_rate(n_side, min_seconds, threads):
+    """Oracle (NumPy port of the reference arithmetic) on a n_side^3 hex box, chunks spread over
+    `threads` host threads (NumPy releases the GIL inside einsum/BLAS).  Returns elements/s."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import folax_b200
+    from oracle import assembly
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        threadpool_limits = None
+    mesh = folax_b200.create_3D_box_mesh(n_side, n_side, n_side, 1.0, 1.0, 1.0)
+    coords, conn = np.asarray(mesh.GetNodesCoordinates()), mesh.GetElementsNodes("hexahedron")
+    rng = np.random.default_rng(0)
+    K = rng.uniform(0.1, 1.0, len(coords))
+    u = 0.01 * rng.standard_normal(3 * len(coords))
+    sets = mesh.node_sets
+    didx, _ = assembly.dirichlet_vectors(["Ux", "Uy", "Uz"], {d: {"left": 0.0, "right": 0.1} for d in ("Ux", "Uy", "Uz")}, sets)
+    ne = len(conn)
+    chunk = 2048
+    parts = [slice(s, min(s + chunk, ne)) for s in range(0, ne, chunk)]
+
+    def work(sl):
+        data, _, R = assembly.assemble("mechanical", "hexahedron", 2, coords, conn[sl], K, u, didx, MATERIAL,
+                                       chunk=chunk)
+        return data.shape[0]
+
+    def one_pass():
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(work, parts))
+
+    ctx = threadpool_limits(limits=1) if threadpool_limits else None
+    if ctx:
+        ctx.__enter__()
+    try:
+        one_pass()  # warm-up
+        t0, done = time.perf_counter(), 0
+        while True:
+            one_pass()
+            done += ne
+            if time.perf_counter() - t0 >= min_seconds:
+                break
+        dt = time.perf_counter() - t0
+    finally:
+        if ctx:
+            ctx.__exit__(None, None, None)
+    return done / dt, done, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_side = 24
+    per_step = []
+    for _ in range(args.warmup):
+        cpu_assembly_rate(n_side, 0.0, threads)
+    t_budget = max(1.0, 20.0 / max(args.steps, 1))
+    total, total_t = 0, 0.0
+    for _ in range(args.steps):
+        rate, done, dt = cpu_assembly_rate(n_side, t_budget, threads)
+        per_step.append(dt)
+        total += done
+        total_t += dt
+    value = total / total_t
+    sample = f"{n_side}^3 hex elements (f64) per pass, repeated for >= {t_budget:.1f} s per step"
+    line = {"impl": "reference", "metric": "assembled_elements_per_s", "value": value, "unit": "elements/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * float(np.mean(per_step)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"hex{args.n}_linear_elastic_residual_jacobian_f64 (CPU leg timed on a bounded "
+                                   f"{n_side}^3 sample of the same mesh family)"},
+            "cpu_baseline": {"value": value, "unit": "elements/s", "cores": threads, "kind": "port", "sample": sample,
+                             "note": "restated reference arithmetic (NumPy oracle), not the JAX path: JAX is not "
+                                     "installable in this image"},
+            "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ GPU leg
+def event_time_ms(torch, fn, steps, stream=None):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def fol_loss_grad_bench(torch, dist, rank, world, steps, warmup):
+    """configs[2]: batch of 1024 random conductivity fields on a 256x256 thermal quad mesh,
+    physics loss + VJP through a small MLP, samples sharded over ranks, NCCL grad all-reduce."""
+    import folax_b200
+    from folax_b200 import _lib
+    from folax_b200.distributed import allreduce_gradients, shard_batch
+    from folax_b200.loss_functions import ThermalLoss2DQuad
+    B, N = 1024, 257
+    mesh = folax_b200.create_2D_square_mesh(1.0, N)
+    loss = ThermalLoss2DQuad("fol_thermal", {"dirichlet_bc_dict": {"T": {"left": 1.0, "right": 0.1}},
+                                             "beta": 2.0, "c": 4}, mesh)
+    loss.Initialize()
+    nn = mesh.GetNumberOfNodes()
+    sl = shard_batch(B * world, rank, world)       # weak scaling: 1024 samples per GPU
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    Kb = torch.rand((B, nn), generator=g, device="cuda", dtype=torch.float64) * 0.9 + 0.1
+    latent = torch.randn((B, 64), generator=g, device="cuda", dtype=torch.float64)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(64, 256), torch.nn.Tanh(), torch.nn.Linear(256, nn)).to("cuda", torch.float64)
+
+    def step():
+        for p in net.parameters():
+            p.grad = None
+        u = torch.sigmoid(net(latent))
+        mean, _ = loss.ComputeBatchLoss(Kb, u)
+        mean.backward()
+        allreduce_gradients(list(net.parameters()))
+
+    def physics_only():
+        u = ub.detach().requires_grad_(True)
+        k = Kb.detach().requires_grad_(True)
+        mean, _ = loss.ComputeBatchLoss(k, u)
+        mean.backward()
+
+    ub = torch.sigmoid(net(latent)).detach()
+    for _ in range(warmup):
+        step()
+        physics_only()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_step = event_time_ms(torch, step, steps)
+    ms_phys = event_time_ms(torch, physics_only, steps)
+    t = torch.tensor([ms_step, ms_phys], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, ms_phys = t.tolist()
+    hbm, _ = measured_peaks()
+    bytes_per_sample = 32.0 * nn  # read u, K; write dE/du, dE/dK (f64)
+    return {"metric": "fol_loss_grad_samples_per_s", "value": B * world / (ms_step * 1e-3), "unit": "samples/s",
+            "physics_only_samples_per_s": B * world / (ms_phys * 1e-3), "ms_per_step": ms_step,
+            "config": {"workload": "thermal_quad256_loss_vjp_f64", "batch_per_gpu": B, "mesh": "256x256 quads",
+                       "beta": 2.0, "c": 4, "network": "MLP 64-256-66049 (f64)", "parallelism": f"dp{world}"},
+            "roofline_physics": {"bound": "hbm", "achieved": bytes_per_sample * B / (ms_phys * 1e-3) / 1e9,
+                                 "peak": hbm, "unit": "GB/s",
+                                 "frac": bytes_per_sample * B / (ms_phys * 1e-3) / 1e9 / hbm}}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import folax_b200
+    from folax_b200 import _lib
+    from folax_b200.distributed import SlabPartition
+    from folax_b200.loss_functions import MechanicalLoss3DHexa
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _lib.load()
+    n = args.n
+    # weak scaling: every rank owns an n^3 slab of an (n, n, n*world) box; interface planes shared
+    part = SlabPartition(n, n, n * world, 1.0, 1.0, float(world), rank, world)
+    mesh = part.mesh
+    bc = {d: {"left": 0.0, "right": 0.1} for d in ("Ux", "Uy", "Uz")}
+    loss = MechanicalLoss3DHexa("bench", {"dirichlet_bc_dict": bc, "num_gp": 2, "material_dict": dict(MATERIAL)}, mesh)
+    loss.Initialize()
+    ne, nn, ndof = loss._ne, loss._nn, loss.total_number_of_dofs
+    rng = np.random.default_rng(rank)
+    K_host = rng.uniform(0.1, 1.0, nn)
+    u_host = 0.01 * rng.standard_normal(ndof)
+    K = torch.tensor(K_host, device="cuda")
+    u = loss.ApplyDirichletBCOnDofVector(torch.tensor(u_host, device="cuda"))
+    ke = torch.empty(ne * 576, dtype=torch.float64, device="cuda")
+
+    def step():
+        data, R = loss._assemble(K, u, False, ke_out=ke)
+        part.halo_sum(R, 3)
+        return data, R
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = lib.fol_launch_count()
+    with ClockSampler(local_rank) as clocks:
+        torch.cuda.synchronize()
+        ms = event_time_ms(torch, step, args.steps)
+        torch.cuda.synchronize()
+    launches = lib.fol_launch_count() - launches0
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = ne * world / (ms * 1e-3)
+
+    # dominant kernel alone (element stage), CUDA events on the launching stream
+    re_tmp = torch.empty(ne * 24, dtype=torch.float64, device="cuda")
+
+    def element_stage():
+        _lib.check(lib.fol_assemble_elements(_lib.stream_ptr(), loss._dt, 0, 0, 2, 0, ne, nn, _lib.ptr(loss._xyz),
+                                             _lib.ptr(loss._conn), _lib.ptr(K), _lib.ptr(u), _lib.ptr(loss._dir_flag),
+                                             loss._params, _lib.ptr(ke), _lib.ptr(re_tmp), None, None))
+    for _ in range(3):
+        element_stage()
+    ms_kernel = event_time_ms(torch, element_stage, max(args.steps, 5))
+    hbm, peak_src = measured_peaks()
+    achieved = ALG_BYTES_PER_ELEMENT_F64 * ne / (ms_kernel * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                "traffic": None, "kernel": "assemble_kernel<double,HEX,2,MECH> (element stage)",
+                "kernel_ms": ms_kernel, "algorithmic_bytes_per_element": ALG_BYTES_PER_ELEMENT_F64,
+                "peak_source": peak_src}
+
+    line = {"metric": "assembled_elements_per_s", "value": value, "unit": "elements/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"hex{n}_linear_elastic_residual_jacobian_f64", "elements_per_gpu": ne,
+                       "dofs_per_gpu": ndof, "num_gp": 2, "output": "BCOO data with duplicates + residual",
+                       "parallelism": f"element slabs x{world} + halo-DOF sum" if world > 1 else "single GPU",
+                       "l2_policy": "per-step working set (9.7 GB Ke stream) >> 126 MB L2"},
+            "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks.summary()}
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        # ---- e2e through the host-buffer C-ABI entry point (pinned host buffers)
+        try:
+            line["e2e"] = e2e_host(torch, lib, _lib, loss, mesh, K_host, u.cpu().numpy(), ne, nn, ndof, args)
+        except Exception as ex:  # report, never fake
+            line["e2e"] = {"value": None, "unit": "elements/s", "error": str(ex)[:200]}
+        # ---- fp64 FMA peak of this GPU (secondary bound)
+        tf = ctypes.c_double()
+        if lib.fol_measure_fma_peak(_lib.F64, ctypes.byref(tf)) == 0:
+            line["roofline"]["fp64_fma_peak_tflops_measured"] = tf.value
+        # ---- CPU baseline (bounded sample)
+        del ke
+        torch.cuda.empty_cache()
+        threads = os.cpu_count() or 1
+        rate, done, dt = cpu_assembly_rate(24, 10.0, threads)
+        line["cpu_baseline"] = {"value": rate, "unit": "elements/s", "cores": threads, "kind": "port",
+                                "sample": f"24^3-element hex box passes for {dt:.1f} s ({done} elements), NumPy "
+                                          "oracle (restated reference arithmetic, not the JAX path)"}
+    if not args.no_extras:
+        try:
+            sec = fol_loss_grad_bench(torch, dist, rank, world, max(3, min(args.steps, 10)), 3)
+            line["fol_loss_grad"] = sec
+        except Exception as ex:
+            line["fol_loss_grad"] = {"error": str(ex)[:200]}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def e2e_host(torch, lib, _lib, loss, mesh, K_host, u_host, ne, nn, ndof, args):
+    conn = np.ascontiguousarray(mesh.GetElementsNodes("hexahedron"), dtype=np.int32)
+    xyz = np.ascontiguousarray(mesh.GetNodesCoordinates(), dtype=np.float64)
+    didx = np.ascontiguousarray(loss.dirichlet_indices, dtype=np.int32)
+    plan = ctypes.c_void_p()
+    _lib.check(lib.fol_plan_create(ctypes.byref(plan), _lib.F64, 0, 0, 2, ne, nn, xyz.ctypes.data, conn.ctypes.data,
+                                   didx.ctypes.data, didx.size, loss._params))
+    try:
+        Kp = torch.tensor(K_host).pin_memory()
+        up = torch.tensor(u_host).pin_memory()
+        ke_host = torch.empty(ne * 576, dtype=torch.float64, pin_memory=True)
+        R_host = torch.empty(ndof, dtype=torch.float64, pin_memory=True)
+
+        def call():
+            _lib.check(lib.fol_plan_assemble_host(plan, 0, Kp.data_ptr(), up.data_ptr(), ke_host.data_ptr(),
+                                                  R_host.data_ptr()))
+        call()
+        steps = max(2, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            call()
+        dt = (time.perf_counter() - t0) / steps
+        h2d = (nn + ndof) * 8
+        d2h = (ne * 576 + ndof) * 8
+        return {"value": ne / dt, "unit": "elements/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": dt * 1e3, "steps": steps,
+                "api": "fol_plan_assemble_host (C ABI, pinned host buffers, returns after D2H)",
+                "note": "PCIe-bound: the reference contract hands the full duplicate-keeping BCOO (4608 B/element) "
+                        "to the host solver"}
+    finally:
+        lib.fol_plan_destroy(plan)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=128, help="hex elements per side per GPU")
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu baseline / secondary metric")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -524,8 +524,11 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
 template <class T, int ELEM, int ORDER, int PHYS>
 int launch_assemble(cudaStream_t s, const AsmArgs<T>& args) {
   using SM = GroupSmem<T, ELEM, ORDER, PHYS>;
-  constexpr int BLOCK = 128;
   constexpr int GW = (SM::A == 8) ? 8 : 4;
+  // 128 threads unless the per-group staging (high-order rules with constitutive point data)
+  // would not leave room for two resident blocks per SM
+  constexpr size_t kBudget = 100 * 1024;
+  constexpr int BLOCK = sizeof(SM) * (128 / GW) <= kBudget ? 128 : (sizeof(SM) * (64 / GW) <= kBudget ? 64 : 32);
   constexpr int GPB = BLOCK / GW;
   const size_t smem = sizeof(SM) * GPB;
   auto kern = assemble_kernel<T, ELEM, ORDER, PHYS, BLOCK>;

@@ -28,8 +28,10 @@ inline int check_launch(const char* what) {
 #define FOL_CUDA(call)                                                                     \
   do {                                                                                     \
     cudaError_t _e = (call);                                                               \
-    if (_e != cudaSuccess)                                                                 \
+    if (_e != cudaSuccess) {                                                               \
+      (void)cudaGetLastError(); /* clear the non-sticky error for the next call */         \
       return ::fol::fail(FOL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+    }                                                                                      \
   } while (0)
 
 #define FOL_REQUIRE(cond, msg) \

@@ -1,0 +1,112 @@
+"""Multi-GPU paths of the hot path (one process per GPU, torch.distributed / NCCL plumbing).
+
+* ``SlabPartition`` -- a single huge structured mesh split into contiguous element slabs along z
+  (the reference has no domain decomposition; this is the north-star's
+  element-partition + halo-DOF exchange).  Each rank owns its slab's elements (so its block of
+  the duplicate-keeping BCOO and its Gauss-point state need no exchange) and holds the nodes
+  those elements touch; the node planes between two slabs exist on both neighbours.
+  ``halo_sum`` adds the neighbour's partial sums on those planes to the local residual, after
+  which both copies hold the globally assembled value.
+* ``allreduce_gradients`` -- the data-parallel FOL path: samples are sharded over ranks and the
+  network gradients are summed with one bucketed NCCL all-reduce (the reference lets XLA insert
+  it: deep_network.py:225-242).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import mesh as _mesh
+
+
+class SlabPartition:
+    def __init__(self, Nx, Ny, Nz_global, Lx, Ly, Lz, rank, world, element_type="hexahedron"):
+        if Nz_global % world:
+            raise ValueError("Nz must be divisible by the number of ranks")
+        self.rank, self.world = rank, world
+        self.Nx, self.Ny, self.Nz_global = Nx, Ny, Nz_global
+        nz = Nz_global // world
+        self.nz_local = nz
+        hz = Lz / Nz_global
+        maker = _mesh.create_3D_box_mesh if element_type == "hexahedron" else _mesh.create_3D_tetra_box_mesh
+        m = maker(Nx, Ny, nz, Lx, Ly, hz * nz)
+        X = np.array(m.nodes_coordinates)
+        X[:, 2] += rank * nz * hz
+        m.nodes_coordinates = X
+        self.mesh = m
+        self.element_type = element_type
+        plane = (Nx + 1) * (Ny + 1)
+        self.plane_nodes = plane
+        self.lower_nodes = np.arange(plane, dtype=np.int64)                  # z = slab bottom
+        self.upper_nodes = np.arange(nz * plane, (nz + 1) * plane, dtype=np.int64)
+        # local node -> global node (global numbering = the same generator on the whole box)
+        self.node_offset = rank * nz * plane
+        self.element_offset = rank * m.GetNumberOfElements(element_type)
+
+    def global_node_ids(self):
+        return np.arange(self.mesh.GetNumberOfNodes(), dtype=np.int64) + self.node_offset
+
+    def halo_index(self, dofs_per_node, device):
+        """Flat dof indices of the lower / upper interface planes (contiguous ranges, because the
+        generator numbers nodes plane by plane)."""
+        d = dofs_per_node
+        lo = (0, self.plane_nodes * d)
+        up = (self.nz_local * self.plane_nodes * d, (self.nz_local + 1) * self.plane_nodes * d)
+        return lo, up
+
+    def halo_sum(self, residual, dofs_per_node, group=None):
+        """In-place neighbour sum of the interface-plane residual partial sums.  The planes are
+        contiguous slices of the local residual, so no pack / unpack kernels are needed: the
+        slices are sent as they are and the received partials are added."""
+        if self.world == 1:
+            return residual
+        (l0, l1), (u0, u1) = self.halo_index(dofs_per_node, residual.device)
+        ops, recv_lo, recv_up = [], None, None
+        if self.rank > 0:
+            recv_lo = torch.empty(l1 - l0, dtype=residual.dtype, device=residual.device)
+            ops.append(dist.P2POp(dist.isend, residual[l0:l1], self.rank - 1, group))
+            ops.append(dist.P2POp(dist.irecv, recv_lo, self.rank - 1, group))
+        if self.rank < self.world - 1:
+            recv_up = torch.empty(u1 - u0, dtype=residual.dtype, device=residual.device)
+            ops.append(dist.P2POp(dist.isend, residual[u0:u1], self.rank + 1, group))
+            ops.append(dist.P2POp(dist.irecv, recv_up, self.rank + 1, group))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        if recv_lo is not None:
+            residual[l0:l1] += recv_lo
+        if recv_up is not None:
+            residual[u0:u1] += recv_up
+        return residual
+
+
+def allreduce_gradients(parameters, group=None, bucket_bytes=64 << 20):
+    """Sum `.grad` of the given parameters over all ranks with as few NCCL calls as fit the
+    bucket size (flatten -> all_reduce -> unflatten)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    grads = [p.grad for p in parameters if p.grad is not None]
+    bucket, size = [], 0
+    def flush():
+        nonlocal bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        off = 0
+        for g in bucket:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        bucket, size = [], 0
+    for g in grads:
+        bucket.append(g)
+        size += g.numel() * g.element_size()
+        if size >= bucket_bytes:
+            flush()
+    flush()
+
+
+def shard_batch(n_samples, rank, world):
+    """Contiguous, even split of the sample axis (the reference's P('data') sharding)."""
+    if n_samples % world:
+        raise ValueError("batch must be divisible by the number of ranks")
+    per = n_samples // world
+    return slice(rank * per, (rank + 1) * per)

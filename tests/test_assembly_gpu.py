@@ -48,9 +48,9 @@ def test_assembly_matches_oracle(physics, etype, num_gp, dtype):
         assert jac.shape == (loss.total_number_of_dofs,) * 2
         _close(jac.data.cpu().numpy(), data, TOL[dtype])
         _close(R.cpu().numpy(), Rref, TOL[dtype] * 4)
-        # structural zeros / kept diagonals of Dirichlet rows are exact
-        ref_zero = data == 0.0
-        assert np.array_equal(jac.data.cpu().numpy()[ref_zero], data[ref_zero])
+        # Dirichlet rows: off-diagonal entries are exactly zero (row mask of fe_loss.py:191-207)
+        masked = np.isin(idx[:, 0], loss.dirichlet_indices) & (idx[:, 0] != idx[:, 1])
+        assert masked.any() and not jac.data.cpu().numpy()[masked].any() and not data[masked].any()
 
 
 def test_determinism_and_todense():
