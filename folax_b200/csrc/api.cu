@@ -25,6 +25,7 @@ template <class T>
 int scale_grads(cudaStream_t, long long, long long, long long, const T*, double, const uint8_t*, T*, T*);
 
 static bool valid_element(int e) { return e >= 0 && e <= 3; }
+static std::atomic<int> g_tuned{1};
 
 template <class T>
 static int assemble_typed(cudaStream_t s, int physics, int element, int num_gp, int transpose, long long ne,
@@ -46,8 +47,12 @@ static int assemble_typed(cudaStream_t s, int physics, int element, int num_gp, 
   constexpr bool f64 = sizeof(T) == 8;
   switch (physics) {
     case FOL_MECHANICAL:
-      if constexpr (f64) return assemble_mech_f64(s, element, num_gp, a);
-      else return assemble_mech_f32(s, element, num_gp, a);
+      if constexpr (f64) {
+        if (element == HEX && num_gp == 2 && g_tuned.load()) return assemble_hex_mech_f64(s, a);
+        return assemble_mech_f64(s, element, num_gp, a);
+      } else {
+        return assemble_mech_f32(s, element, num_gp, a);
+      }
     case FOL_THERMAL:
       if constexpr (f64) return assemble_thermal_f64(s, element, num_gp, a);
       else return assemble_thermal_f32(s, element, num_gp, a);
@@ -88,6 +93,10 @@ int fol_element_info(int element, int num_gp, int* nnode, int* dim, int* ngauss)
   if (dim) *dim = elem_dim(element);
   if (ngauss) *ngauss = elem_ngauss(element, num_gp);
   return FOL_OK;
+}
+
+int fol_set_tuned_kernels(int enable) {
+  return g_tuned.exchange(enable ? 1 : 0);
 }
 
 int fol_dofs_per_node(int physics, int element) {

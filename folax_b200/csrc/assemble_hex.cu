@@ -1,0 +1,252 @@
+// Tuned element-stage kernel for the north-star workload: 3-D Hex8 small-strain elasticity, float64,
+// 2x2x2 Gauss rule (MechanicalLoss3DHexa, mechanical.py:98-117 + fe_loss.py:191-230, 299).
+//
+// Same results as the generic kernel (assemble.cuh); different machine mapping:
+//   * persistent warps, each iteration owns a tile of 4 consecutive elements;
+//   * nodal gathers for tile i+1 (and connectivity for tile i+2) are in flight while tile i computes;
+//   * phase 1: lane (element, Gauss point) -> J, det J, grad N, coefficient: 32 independent
+//     geometry evaluations per warp, nothing computed twice;
+//   * phase 2: per element the 24x24 matrix P = sum_g s_g v_g v_g^T (v = grad N flattened) is a
+//     24x24x8 GEMM: 18 DMMA m8n8k4 (FP64 tensor path) fed straight from the staged gradients, the
+//     accumulator fragment of lane (a, k) being exactly the 3x3 blocks (a,2k), (a,2k+1);
+//     Ke = lam P + mu P^T + mu tr(P) I, re = Ke u - Fe, Dirichlet row mask in registers;
+//   * Ke rows are staged in shared memory and leave the SM as ONE contiguous 4608-byte bulk
+//     async copy per element (cp.async.bulk shared->global, the TMA engine): full-line writes, no
+//     store instructions on the LSU path, double-buffered so the copy overlaps the next element.
+// Ke of linear elasticity is symmetric bit for bit (same products, same order), so the transpose
+// switch is a no-op here.
+#include "assemble.cuh"
+
+namespace fol {
+
+namespace {
+
+constexpr int kWarps = 4;            // warps per CTA, each fully independent
+constexpr int kTile = 4;             // elements per warp iteration
+constexpr int kRow = 9;              // 8 nodes + 1 pad (16-byte units) -> conflict-free staging
+
+struct __align__(128) WarpSmem {
+  double stage[2][576];              // two Ke staging slots (bulk-copy sources)
+  double2 gxy[kTile][8][kRow];       // [element][gauss][node] (dN/dx, dN/dy)
+  double2 gzs[kTile][8][kRow];       // (dN/dz, w detJ E_g)
+  double X[kTile][25];               // nodal coordinates, padded rows
+  double u[kTile][25];               // element dofs
+  double de[kTile][9];               // nodal control values
+  double wd[kTile][8];               // w detJ per Gauss point (body force)
+  float bc[kTile][24];               // 1 = free dof, 0 = Dirichlet dof
+};
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, unsigned bytes) {
+  const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(saddr), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+struct NodeData {
+  double x[3], u[3], de;
+  float bc[3];
+};
+
+__device__ __forceinline__ NodeData load_node(const AsmArgs<double>& a, long long n) {
+  NodeData d;
+  const double* px = a.xyz + n * 3;
+  const double* pu = a.u + n * 3;
+  d.x[0] = __ldg(px); d.x[1] = __ldg(px + 1); d.x[2] = __ldg(px + 2);
+  d.u[0] = __ldg(pu); d.u[1] = __ldg(pu + 1); d.u[2] = __ldg(pu + 2);
+  d.de = __ldg(a.ctrl + n);
+  const uint8_t* pf = a.dir + n * 3;
+  d.bc[0] = __ldg(pf) ? 0.f : 1.f; d.bc[1] = __ldg(pf + 1) ? 0.f : 1.f; d.bc[2] = __ldg(pf + 2) ? 0.f : 1.f;
+  return d;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kWarps * 32, 2)
+assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles, const int has_body) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
+  const long long nwarps = (long long)gridDim.x * kWarps;
+  long long tile = (long long)blockIdx.x * kWarps + warp;
+  if (tile >= ntiles) return;
+
+  const double E = args.p.v[0], nu = args.p.v[1];
+  const double c1 = E / ((1.0 + nu) * (1.0 - 2.0 * nu));
+  const double lam = c1 * nu, mu = c1 * 0.5 * (1.0 - 2.0 * nu);
+
+  // lane roles
+  const int el_p = lane >> 3, sub = lane & 7;   // phases 0/1: (element in tile, node | gauss point)
+  const int ra = lane >> 2, kq = lane & 3;      // phase 2: (row node a, column pair k)
+
+  // Gauss point `sub` of the 2x2x2 rule and its reference shape data (constants per lane)
+  double xi[3], wq;
+  gauss_point<HEX, 2>(sub, xi, wq);
+  double N[8], dN[8][3];
+  shape_functions<HEX, double>(xi, N, dN);
+
+  // software pipeline of the gathers: node ids two tiles ahead, nodal data one tile ahead
+  auto node_of = [&](long long t) -> long long {
+    const long long e = t * kTile + el_p;
+    return (t < ntiles && e < args.ne) ? (long long)__ldg(args.conn + e * 8 + sub) : 0;
+  };
+  long long n_next = node_of(tile + nwarps);
+  NodeData cur = load_node(args, node_of(tile));
+  unsigned slot = 0;
+
+  for (; tile < ntiles; tile += nwarps) {
+    const long long e0 = tile * kTile;
+    const NodeData nxt = load_node(args, n_next);           // in flight during this tile
+    const long long n_next2 = node_of(tile + 2 * nwarps);
+
+    // ---- phase 0: lane (element, node) publishes its node
+    sm.X[el_p][sub * 3 + 0] = cur.x[0]; sm.X[el_p][sub * 3 + 1] = cur.x[1]; sm.X[el_p][sub * 3 + 2] = cur.x[2];
+    sm.u[el_p][sub * 3 + 0] = cur.u[0]; sm.u[el_p][sub * 3 + 1] = cur.u[1]; sm.u[el_p][sub * 3 + 2] = cur.u[2];
+    sm.de[el_p][sub] = cur.de;
+    sm.bc[el_p][sub * 3 + 0] = cur.bc[0]; sm.bc[el_p][sub * 3 + 1] = cur.bc[1]; sm.bc[el_p][sub * 3 + 2] = cur.bc[2];
+    __syncwarp();
+
+    // ---- phase 1: lane (element, Gauss point): geometry + coefficient (geometry.py:88-97)
+    {
+      double gN[8][3];
+      const double det = global_gradients<HEX, double>(sm.X[el_p], dN, gN);
+      double eg = 0.0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) eg += N[b] * sm.de[el_p][b];
+      const double wd = wq * det;
+      const double coef = wd * eg;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        sm.gxy[el_p][sub][b] = make_double2(gN[b][0], gN[b][1]);
+        sm.gzs[el_p][sub][b] = make_double2(gN[b][2], coef);
+      }
+      sm.wd[el_p][sub] = wd;
+    }
+    __syncwarp();
+
+    // ---- phase 2: one element at a time, lane (a, k)
+#pragma unroll 1
+    for (int el = 0; el < kTile; ++el) {
+      const long long e = e0 + el;
+      if (e >= args.ne) break;
+      // P = sum_g s_g v_g v_g^T on the FP64 tensor path: rows/cols ordered m = 8*dim + node
+      double c[3][3][2];
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) c[t][s][0] = c[t][s][1] = 0.0;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const double2 xy = sm.gxy[el][4 * kk + kq][ra];
+        const double2 zs = sm.gzs[el][4 * kk + kq][ra];
+        const double bf[3] = {xy.x, xy.y, zs.x};
+        const double af[3] = {zs.y * xy.x, zs.y * xy.y, zs.y * zs.x};
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+          for (int s = 0; s < 3; ++s) dmma884(c[t][s][0], c[t][s][1], af[t], bf[s]);
+      }
+      // Ke blocks (a, 2k) and (a, 2k+1): lam P + mu P^T + mu tr(P) I  (B^T D B of an isotropic D)
+      double K[2][3][3];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const double tr = c[0][0][h] + c[1][1][h] + c[2][2][h];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            K[h][i][j] = lam * c[i][j][h] + mu * c[j][i][h] + (i == j ? mu * tr : 0.0);
+      }
+      // re = Ke u - Fe: partial over this lane's 6 columns, then butterfly over the 4 k-lanes
+      double r[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) acc += K[h][i][j] * sm.u[el][(2 * kq + h) * 3 + j];
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        r[i] = acc;
+      }
+      if (has_body) {  // Fe_a = b * sum_g w detJ N_a(g)   (mechanical.py:110)
+        double nw = 0.0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const double fx = 1.0 + sgn_x(ra) * sgn_x(g) * FOL_S3, fy = 1.0 + sgn_y(ra) * sgn_y(g) * FOL_S3;
+          const double fz = 1.0 + sgn_z(ra) * sgn_z(g) * FOL_S3;
+          nw += sm.wd[el][g] * (0.125 * fx * fy * fz);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r[i] -= args.p.v[2 + i] * nw;
+      }
+      if (kq == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) args.re[e * 24 + ra * 3 + i] = (double)sm.bc[el][ra * 3 + i] * r[i];
+      }
+      // stage the masked rows (fe_loss.py:191-207) and hand them to the bulk-copy engine
+      if (lane == 0) bulk_wait_read<1>();   // the copy that last used this slot has drained
+      __syncwarp();
+      double* st = sm.stage[slot];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int row = ra * 3 + i;
+        const bool freerow = sm.bc[el][row] != 0.f;
+        double v[6];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const int col = (2 * kq + h) * 3 + j;
+            v[h * 3 + j] = (freerow || col == row) ? K[h][i][j] : 0.0;
+          }
+        double2* dst = reinterpret_cast<double2*>(st + row * 24 + kq * 6);
+        dst[0] = make_double2(v[0], v[1]);
+        dst[1] = make_double2(v[2], v[3]);
+        dst[2] = make_double2(v[4], v[5]);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) bulk_store(args.ke + e * 576, st, 576 * sizeof(double));
+      slot ^= 1u;
+    }
+    __syncwarp();  // everyone is done with X / u / gradients of this tile
+    cur = nxt;
+    n_next = n_next2;
+  }
+  if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last copies
+}
+
+int assemble_hex_mech_f64(cudaStream_t s, const AsmArgs<double>& args) {
+  static int grid = 0;
+  const size_t smem = sizeof(WarpSmem) * kWarps;
+  if (!grid) {
+    FOL_CUDA(cudaFuncSetAttribute(assemble_hex_mech_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    int dev = 0, sms = 148, per_sm = 1;
+    FOL_CUDA(cudaGetDevice(&dev));
+    FOL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    FOL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, assemble_hex_mech_f64_kernel, kWarps * 32, smem));
+    grid = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  if (args.ne == 0) return FOL_OK;
+  const long long ntiles = cdiv(args.ne, kTile);
+  const long long want = cdiv(ntiles, kWarps);
+  const int has_body = (args.p.v[2] != 0.0 || args.p.v[3] != 0.0 || args.p.v[4] != 0.0) ? 1 : 0;
+  assemble_hex_mech_f64_kernel<<<(unsigned)(want < grid ? want : grid), kWarps * 32, smem, s>>>(args, ntiles, has_body);
+  return check_launch("assemble_hex_mech_f64_kernel");
+}
+
+}  // namespace fol

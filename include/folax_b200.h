@@ -52,6 +52,10 @@ int fol_version(void);
 /* number of kernels launched by this library in the calling process (bench `gpu_launches`) */
 int64_t fol_launch_count(void);
 
+/* 1 (default): workloads with a tuned kernel (Hex8 elasticity f64, 2x2x2 rule) use it; 0: always the
+ * generic kernel (A/B parity checks).  Returns the previous setting. */
+int fol_set_tuned_kernels(int enable);
+
 /* element table: nodes per element, spatial dim, Gauss points of integration order num_gp */
 int fol_element_info(int element, int num_gp, int* nnode, int* dim, int* ngauss);
 /* dofs per node of a physics on an element (1 for thermal, dim otherwise) */

@@ -128,3 +128,45 @@ def test_empty_dirichlet_and_single_element():
     assert np.array_equal(jac.indices.cpu().numpy(), idx)
     _close(jac.data.cpu().numpy(), data, 1e-12)
     _close(R.cpu().numpy(), Rref, 1e-12)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (5, 3, 3), (7, 6, 5), (16, 9, 11)])
+@pytest.mark.parametrize("body", [None, [0.3, -0.2, 0.1]])
+def test_tuned_hex_kernel_matches_oracle_and_generic(shape, body):
+    """The DMMA + bulk-copy kernel (assemble_hex.cu) against the oracle and against the generic
+    kernel, including element counts that are not a multiple of its 4-element tile."""
+    import folax_b200
+    from folax_b200 import _lib
+    from folax_b200.loss_functions import MechanicalLoss3DHexa
+    mesh = folax_b200.create_3D_box_mesh(*shape, 1.0, 0.8, 1.1)
+    if min(shape) > 1:
+        folax_b200.perturb_interior_nodes(mesh, 0.25, seed=sum(shape))
+    settings = {"dirichlet_bc_dict": {d: {"left": 0.0, "right": 0.1} for d in ("Ux", "Uy", "Uz")},
+                "material_dict": dict(H.MATERIAL)}
+    if body:
+        settings["body_foce"] = body
+    loss = MechanicalLoss3DHexa("tuned", settings, mesh)
+    loss.Initialize()
+    K, u = H.fields("mechanical", mesh, loss, seed=11)
+    lib = _lib.load()
+    out = {}
+    for tuned in (1, 0):
+        prev = lib.fol_set_tuned_kernels(tuned)
+        try:
+            jac, R = loss.ComputeJacobianMatrixAndResidualVector(K, u)
+            jt, _ = loss.ComputeJacobianMatrixAndResidualVector(K, u, transpose_jacobian=True)
+            out[tuned] = (jac.data.cpu().numpy(), R.cpu().numpy(), jt.data.cpu().numpy())
+        finally:
+            lib.fol_set_tuned_kernels(prev)
+    data, idx, Rref = assembly.assemble("mechanical", "hexahedron", 2, np.asarray(mesh.GetNodesCoordinates()),
+                                        mesh.GetElementsNodes("hexahedron"), K, u, loss.dirichlet_indices,
+                                        H.oracle_params(loss))
+    dataT, _, _ = assembly.assemble("mechanical", "hexahedron", 2, np.asarray(mesh.GetNodesCoordinates()),
+                                    mesh.GetElementsNodes("hexahedron"), K, u, loss.dirichlet_indices,
+                                    H.oracle_params(loss), transpose=True)
+    for tuned in (1, 0):
+        _close(out[tuned][0], data, 1e-12)
+        _close(out[tuned][1], Rref, 4e-12)
+        _close(out[tuned][2], dataT, 1e-12)
+    masked = np.isin(idx[:, 0], loss.dirichlet_indices) & (idx[:, 0] != idx[:, 1])
+    assert not out[1][0][masked].any()
