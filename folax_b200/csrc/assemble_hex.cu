@@ -12,7 +12,7 @@
 //     Ke = lam P + mu P^T + mu tr(P) I, re = Ke u - Fe, Dirichlet row mask in registers;
 //   * Ke rows are staged in shared memory and leave the SM as ONE contiguous 4608-byte bulk
 //     async copy per element (cp.async.bulk shared->global, the TMA engine): full-line writes, no
-//     store instructions on the LSU path, double-buffered so the copy overlaps the next element.
+//     store instructions on the LSU path; the copy of element i drains while element i+1 is computed.
 // Ke of linear elasticity is symmetric bit for bit (same products, same order), so the transpose
 // switch is a no-op here.
 #include "assemble.cuh"
@@ -21,12 +21,12 @@ namespace fol {
 
 namespace {
 
-constexpr int kWarps = 4;            // warps per CTA, each fully independent
+constexpr int kWarps = 7;            // warps per CTA, each fully independent (2 CTAs = 14 warps / SM)
 constexpr int kTile = 4;             // elements per warp iteration
 constexpr int kRow = 9;              // 8 nodes + 1 pad (16-byte units) -> conflict-free staging
 
 struct __align__(128) WarpSmem {
-  double stage[2][576];              // two Ke staging slots (bulk-copy sources)
+  double stage[576];                 // Ke staging slot (bulk-copy source)
   double2 gxy[kTile][8][kRow];       // [element][gauss][node] (dN/dx, dN/dy)
   double2 gzs[kTile][8][kRow];       // (dN/dz, w detJ E_g)
   double X[kTile][25];               // nodal coordinates, padded rows
@@ -90,11 +90,20 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
   const int el_p = lane >> 3, sub = lane & 7;   // phases 0/1: (element in tile, node | gauss point)
   const int ra = lane >> 2, kq = lane & 3;      // phase 2: (row node a, column pair k)
 
-  // Gauss point `sub` of the 2x2x2 rule and its reference shape data (constants per lane)
-  double xi[3], wq;
-  gauss_point<HEX, 2>(sub, xi, wq);
-  double N[8], dN[8][3];
-  shape_functions<HEX, double>(xi, N, dN);
+  // Gauss point `sub` of the 2x2x2 rule (hexahedra_3d_8.py:23-33): xi = sgn(sub) / sqrt(3), w = 1.
+  // Trilinear shape data factorised per axis: f?[0] = 1 - xi_?, f?[1] = 1 + xi_? and the pair
+  // products below give N_a = fx*fyz, dN_a/dxi = sx(a)*fyz, ... with compile-time node signs.
+  const double px = sgn_x(sub) * FOL_S3, py = sgn_y(sub) * FOL_S3, pz = sgn_z(sub) * FOL_S3;
+  const double fx[2] = {1.0 - px, 1.0 + px};
+  double fyz[2][2], fxz[2][2], fxy[2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      fyz[i][j] = 0.125 * (i ? 1.0 + py : 1.0 - py) * (j ? 1.0 + pz : 1.0 - pz);
+      fxz[i][j] = 0.125 * (i ? 1.0 + px : 1.0 - px) * (j ? 1.0 + pz : 1.0 - pz);
+      fxy[i][j] = 0.125 * (i ? 1.0 + px : 1.0 - px) * (j ? 1.0 + py : 1.0 - py);
+    }
 
   // software pipeline of the gathers: node ids two tiles ahead, nodal data one tile ahead
   auto node_of = [&](long long t) -> long long {
@@ -102,34 +111,69 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
     return (t < ntiles && e < args.ne) ? (long long)__ldg(args.conn + e * 8 + sub) : 0;
   };
   long long n_next = node_of(tile + nwarps);
-  NodeData cur = load_node(args, node_of(tile));
-  unsigned slot = 0;
+  NodeData pre = load_node(args, node_of(tile));
 
   for (; tile < ntiles; tile += nwarps) {
     const long long e0 = tile * kTile;
-    const NodeData nxt = load_node(args, n_next);           // in flight during this tile
-    const long long n_next2 = node_of(tile + 2 * nwarps);
 
-    // ---- phase 0: lane (element, node) publishes its node
-    sm.X[el_p][sub * 3 + 0] = cur.x[0]; sm.X[el_p][sub * 3 + 1] = cur.x[1]; sm.X[el_p][sub * 3 + 2] = cur.x[2];
-    sm.u[el_p][sub * 3 + 0] = cur.u[0]; sm.u[el_p][sub * 3 + 1] = cur.u[1]; sm.u[el_p][sub * 3 + 2] = cur.u[2];
-    sm.de[el_p][sub] = cur.de;
-    sm.bc[el_p][sub * 3 + 0] = cur.bc[0]; sm.bc[el_p][sub * 3 + 1] = cur.bc[1]; sm.bc[el_p][sub * 3 + 2] = cur.bc[2];
+    // ---- phase 0: lane (element, node) publishes its node, then prefetches the next tile's
+    sm.X[el_p][sub * 3 + 0] = pre.x[0]; sm.X[el_p][sub * 3 + 1] = pre.x[1]; sm.X[el_p][sub * 3 + 2] = pre.x[2];
+    sm.u[el_p][sub * 3 + 0] = pre.u[0]; sm.u[el_p][sub * 3 + 1] = pre.u[1]; sm.u[el_p][sub * 3 + 2] = pre.u[2];
+    sm.de[el_p][sub] = pre.de;
+    sm.bc[el_p][sub * 3 + 0] = pre.bc[0]; sm.bc[el_p][sub * 3 + 1] = pre.bc[1]; sm.bc[el_p][sub * 3 + 2] = pre.bc[2];
     __syncwarp();
+    pre = load_node(args, n_next);                          // in flight during this tile
+    n_next = node_of(tile + 2 * nwarps);
 
-    // ---- phase 1: lane (element, Gauss point): geometry + coefficient (geometry.py:88-97)
+    // ---- phase 1: lane (element, Gauss point): J, det J, grad N, coefficient (geometry.py:88-97)
     {
-      double gN[8][3];
-      const double det = global_gradients<HEX, double>(sm.X[el_p], dN, gN);
+      const double* X = sm.X[el_p];
+      double J[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double j0 = 0.0, j1 = 0.0, j2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          const int bx = ((a & 3) == 1 || (a & 3) == 2), by = (a >> 1) & 1, bz = (a >> 2) & 1;
+          const double x = X[a * 3 + i];
+          j0 += (bx ? x : -x) * fyz[by][bz];
+          j1 += (by ? x : -x) * fxz[bx][bz];
+          j2 += (bz ? x : -x) * fxy[bx][by];
+        }
+        J[i][0] = j0; J[i][1] = j1; J[i][2] = j2;
+      }
+      const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+      const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+      const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+      const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+      const double rd = 1.0 / det;
+      double inv[3][3];
+      inv[0][0] = c00 * rd; inv[1][0] = c01 * rd; inv[2][0] = c02 * rd;
+      inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * rd;
+      inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * rd;
+      inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * rd;
+      inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * rd;
+      inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * rd;
+      inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * rd;
       double eg = 0.0;
 #pragma unroll
-      for (int b = 0; b < 8; ++b) eg += N[b] * sm.de[el_p][b];
-      const double wd = wq * det;
+      for (int a = 0; a < 8; ++a) {
+        const int bx = ((a & 3) == 1 || (a & 3) == 2), by = (a >> 1) & 1, bz = (a >> 2) & 1;
+        eg += fx[bx] * fyz[by][bz] * sm.de[el_p][a];
+      }
+      const double wd = det;  // Gauss weight is 1
       const double coef = wd * eg;
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        sm.gxy[el_p][sub][b] = make_double2(gN[b][0], gN[b][1]);
-        sm.gzs[el_p][sub][b] = make_double2(gN[b][2], coef);
+      for (int a = 0; a < 8; ++a) {
+        const int bx = ((a & 3) == 1 || (a & 3) == 2), by = (a >> 1) & 1, bz = (a >> 2) & 1;
+        const double d0 = bx ? fyz[by][bz] : -fyz[by][bz];
+        const double d1 = by ? fxz[bx][bz] : -fxz[bx][bz];
+        const double d2 = bz ? fxy[bx][by] : -fxy[bx][by];
+        double g[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) g[k] = d0 * inv[0][k] + d1 * inv[1][k] + d2 * inv[2][k];
+        sm.gxy[el_p][sub][a] = make_double2(g[0], g[1]);
+        sm.gzs[el_p][sub][a] = make_double2(g[2], coef);
       }
       sm.wd[el_p][sub] = wd;
     }
@@ -168,6 +212,30 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
           for (int j = 0; j < 3; ++j)
             K[h][i][j] = lam * c[i][j][h] + mu * c[j][i][h] + (i == j ? mu * tr : 0.0);
       }
+      // stage the masked rows (fe_loss.py:191-207) and hand them to the bulk-copy engine
+      if (lane == 0) bulk_wait_read<0>();   // the previous element's copy has drained the slot
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int row = ra * 3 + i;
+        const bool freerow = sm.bc[el][row] != 0.f;
+        double v[6];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const int col = (2 * kq + h) * 3 + j;
+            v[h * 3 + j] = (freerow || col == row) ? K[h][i][j] : 0.0;
+          }
+        double2* dst = reinterpret_cast<double2*>(sm.stage + row * 24 + kq * 6);
+        dst[0] = make_double2(v[0], v[1]);
+        dst[1] = make_double2(v[2], v[3]);
+        dst[2] = make_double2(v[4], v[5]);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) bulk_store(args.ke + e * 576, sm.stage, 576 * sizeof(double));
+
       // re = Ke u - Fe: partial over this lane's 6 columns, then butterfly over the 4 k-lanes
       double r[3];
 #pragma unroll
@@ -185,9 +253,9 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
         double nw = 0.0;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          const double fx = 1.0 + sgn_x(ra) * sgn_x(g) * FOL_S3, fy = 1.0 + sgn_y(ra) * sgn_y(g) * FOL_S3;
-          const double fz = 1.0 + sgn_z(ra) * sgn_z(g) * FOL_S3;
-          nw += sm.wd[el][g] * (0.125 * fx * fy * fz);
+          const double gx = 1.0 + sgn_x(ra) * sgn_x(g) * FOL_S3, gy = 1.0 + sgn_y(ra) * sgn_y(g) * FOL_S3;
+          const double gz = 1.0 + sgn_z(ra) * sgn_z(g) * FOL_S3;
+          nw += sm.wd[el][g] * (0.125 * gx * gy * gz);
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) r[i] -= args.p.v[2 + i] * nw;
@@ -196,35 +264,8 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
 #pragma unroll
         for (int i = 0; i < 3; ++i) args.re[e * 24 + ra * 3 + i] = (double)sm.bc[el][ra * 3 + i] * r[i];
       }
-      // stage the masked rows (fe_loss.py:191-207) and hand them to the bulk-copy engine
-      if (lane == 0) bulk_wait_read<1>();   // the copy that last used this slot has drained
-      __syncwarp();
-      double* st = sm.stage[slot];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int row = ra * 3 + i;
-        const bool freerow = sm.bc[el][row] != 0.f;
-        double v[6];
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const int col = (2 * kq + h) * 3 + j;
-            v[h * 3 + j] = (freerow || col == row) ? K[h][i][j] : 0.0;
-          }
-        double2* dst = reinterpret_cast<double2*>(st + row * 24 + kq * 6);
-        dst[0] = make_double2(v[0], v[1]);
-        dst[1] = make_double2(v[2], v[3]);
-        dst[2] = make_double2(v[4], v[5]);
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) bulk_store(args.ke + e * 576, st, 576 * sizeof(double));
-      slot ^= 1u;
     }
     __syncwarp();  // everyone is done with X / u / gradients of this tile
-    cur = nxt;
-    n_next = n_next2;
   }
   if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last copies
 }
