@@ -16,11 +16,11 @@ int assemble_j2_f32(cudaStream_t, int, int, const AsmArgs<float>&);
 int assemble_hex_mech_f64(cudaStream_t, const AsmArgs<double>&);
 
 template <class T>
-int energy_and_grads(cudaStream_t, int, int, int, const EnergyArgs<T>&);
+int energy_and_grads(cudaStream_t, int, int, int, const EnergyArgs<T>&, T*);
 template <class T>
 int geometry_cache(cudaStream_t, int, int, long long, const T*, const int32_t*, T*);
 template <class T>
-int loss_reduce(cudaStream_t, long long, int, double, const T*, T*, T*, T*);
+int loss_reduce(cudaStream_t, long long, double, const T*, T*, T*);
 template <class T>
 int scale_grads(cudaStream_t, long long, long long, long long, const T*, double, const uint8_t*, T*, T*);
 
@@ -131,39 +131,38 @@ int fol_geometry_cache(fol_stream_t s, int dtype, int element, int num_gp, int64
   return geometry_cache<float>((cudaStream_t)s, element, num_gp, ne, (const float*)xyz, conn, (float*)geom);
 }
 
-int64_t fol_energy_work_size(int64_t nn, int64_t nb) { return cdiv(nn, 128) * nb + nb + 8; }
+int64_t fol_energy_work_size(int64_t ntiles, int64_t nb) { return ntiles * nb + 16; }
 
 int fol_energy_and_grads(fol_stream_t s, int dtype, int physics, int element, int num_gp, int64_t ne, int64_t nn,
                          int64_t nb, const void* geom, const int32_t* conn, const int32_t* adj_ptr,
-                         const int32_t* adj, const void* ctrl, const void* u, const double* params_host, void* grad_u,
-                         void* grad_k, void* energy, void* work) {
+                         const int32_t* adj_local, const int32_t* tile_node_ptr, const int32_t* tile_nodes,
+                         const int32_t* tile_elem_ptr, const int32_t* tile_elems, int64_t ntiles, int64_t ecap,
+                         const void* ctrl, const void* u, const double* params_host, void* grad_u, void* grad_k,
+                         void* energy, void* work) {
   FOL_REQUIRE(valid_element(element), "fol_energy_and_grads: unknown element");
-  FOL_REQUIRE(geom && conn && adj_ptr && adj && ctrl && u && grad_u && energy && work && params_host,
+  FOL_REQUIRE(geom && conn && adj_ptr && adj_local && tile_node_ptr && tile_nodes && tile_elem_ptr && tile_elems &&
+                  ctrl && u && grad_u && energy && work && params_host,
               "fol_energy_and_grads: null pointer");
-  FOL_REQUIRE(nb >= 1 && nb <= 65535LL * 2, "fol_energy_and_grads: batch size out of range");
-  const int nblocks = (int)cdiv(nn, 128);
+  FOL_REQUIRE(nb >= 1 && ntiles >= 1 && ecap >= 1, "fol_energy_and_grads: bad sizes");
   if (dtype == FOL_F64) {
-    EnergyArgs<double> a{(const double*)geom, conn, adj_ptr, adj, (const double*)ctrl, (const double*)u,
-                         (double*)grad_u, (double*)grad_k, (double*)work, ne, nn, nb, make_params<double>(params_host)};
-    if (int rc = energy_and_grads<double>((cudaStream_t)s, physics, element, num_gp, a)) return rc;
-    // E_b = fixed-order sum of the block partials (exponent / scale are applied by fol_loss_reduce)
-    return loss_reduce<double>((cudaStream_t)s, nb, nblocks, 1.0, (const double*)work, (double*)energy,
-                               (double*)work + (size_t)nblocks * nb, (double*)work + (size_t)nblocks * nb + 4);
+    EnergyArgs<double> a{(const double*)geom, conn, adj_ptr, adj_local, tile_node_ptr, tile_nodes, tile_elem_ptr,
+                         tile_elems, (const double*)ctrl, (const double*)u, (double*)grad_u, (double*)grad_k,
+                         (double*)work, ne, nn, nb, (int)ntiles, (int)ecap, make_params<double>(params_host)};
+    return energy_and_grads<double>((cudaStream_t)s, physics, element, num_gp, a, (double*)energy);
   }
-  EnergyArgs<float> a{(const float*)geom, conn, adj_ptr, adj, (const float*)ctrl, (const float*)u,
-                      (float*)grad_u, (float*)grad_k, (float*)work, ne, nn, nb, make_params<float>(params_host)};
-  if (int rc = energy_and_grads<float>((cudaStream_t)s, physics, element, num_gp, a)) return rc;
-  return loss_reduce<float>((cudaStream_t)s, nb, nblocks, 1.0, (const float*)work, (float*)energy,
-                            (float*)work + (size_t)nblocks * nb, (float*)work + (size_t)nblocks * nb + 4);
+  FOL_REQUIRE(dtype == FOL_F32, "fol_energy_and_grads: bad dtype");
+  EnergyArgs<float> a{(const float*)geom, conn, adj_ptr, adj_local, tile_node_ptr, tile_nodes, tile_elem_ptr,
+                      tile_elems, (const float*)ctrl, (const float*)u, (float*)grad_u, (float*)grad_k, (float*)work,
+                      ne, nn, nb, (int)ntiles, (int)ecap, make_params<float>(params_host)};
+  return energy_and_grads<float>((cudaStream_t)s, physics, element, num_gp, a, (float*)energy);
 }
 
 int fol_loss_reduce(fol_stream_t s, int dtype, int64_t nb, double exponent, const void* energy, void* out4,
                     void* scale) {
   FOL_REQUIRE(energy && out4 && scale && nb >= 1, "fol_loss_reduce: bad arguments");
   if (dtype == FOL_F64)
-    return loss_reduce<double>((cudaStream_t)s, nb, 0, exponent, nullptr, (double*)energy, (double*)out4,
-                               (double*)scale);
-  return loss_reduce<float>((cudaStream_t)s, nb, 0, exponent, nullptr, (float*)energy, (float*)out4, (float*)scale);
+    return loss_reduce<double>((cudaStream_t)s, nb, exponent, (const double*)energy, (double*)out4, (double*)scale);
+  return loss_reduce<float>((cudaStream_t)s, nb, exponent, (const float*)energy, (float*)out4, (float*)scale);
 }
 
 int fol_scale_grads(fol_stream_t s, int dtype, int64_t nb, int64_t ndof, int64_t nn, const void* scale,

@@ -5,14 +5,25 @@ namespace fol {
 
 template <class T, int ELEM, int ORDER, int PHYS>
 int launch_energy(cudaStream_t s, const EnergyArgs<T>& args) {
-  constexpr int BLOCK = 128;
-  // samples held in registers per thread: more for small elements
+  constexpr int BLOCK = 192;           // >= nodes per tile (128) and, on the fast path, elements per tile
   constexpr int ND = elem_nnode(ELEM) * phys_dpn(PHYS, ELEM);
-  constexpr int S = ND <= 4 ? 8 : (ND <= 8 ? 4 : 2);
-  dim3 grid((unsigned)cdiv(args.nn, BLOCK), (unsigned)cdiv(args.nb, S));
-  if (grid.x == 0 || grid.y == 0) return FOL_OK;
-  energy_grads_kernel<T, ELEM, ORDER, PHYS, S, BLOCK><<<grid, BLOCK, 0, s>>>(args);
-  return check_launch("energy_grads_kernel");
+  constexpr int S = ND <= 8 ? 4 : 2;   // samples per CTA pass (shared-memory rows)
+  constexpr int KW = energy_kw(PHYS, ELEM);
+  const size_t smem = sizeof(T) * (size_t)S * KW * args.ecap;
+  if (smem > 200 * 1024) return fail(FOL_ERR_INVALID, "fol_energy_and_grads: tile element list too long");
+  auto kern = energy_tile_kernel<T, ELEM, ORDER, PHYS, S, BLOCK>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    FOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  if (args.ntiles == 0 || args.nb == 0) return FOL_OK;
+  long long y = cdiv(148LL * 16, args.ntiles);
+  const long long ymax = cdiv(args.nb, S);
+  y = y < 1 ? 1 : (y > ymax ? ymax : y);
+  dim3 grid((unsigned)args.ntiles, (unsigned)y);
+  kern<<<grid, BLOCK, smem, s>>>(args);
+  return check_launch("energy_tile_kernel");
 }
 
 template <class T, int PHYS>
@@ -28,22 +39,26 @@ int dispatch_energy(cudaStream_t s, int element, int num_gp, const EnergyArgs<T>
 }
 
 template <class T>
-int energy_and_grads(cudaStream_t s, int physics, int element, int num_gp, const EnergyArgs<T>& a) {
-  if (physics == FOL_MECHANICAL) return dispatch_energy<T, MECH>(s, element, num_gp, a);
-  if (physics == FOL_THERMAL) return dispatch_energy<T, THERMAL>(s, element, num_gp, a);
-  if (physics == FOL_NEOHOOKE) return dispatch_energy<T, NEOHOOKE>(s, element, num_gp, a);
-  return fail(FOL_ERR_UNSUPPORTED, "fol_energy_and_grads: physics not supported yet");
+int energy_and_grads(cudaStream_t s, int physics, int element, int num_gp, const EnergyArgs<T>& a, T* energy) {
+  int rc;
+  if (physics == FOL_MECHANICAL) rc = dispatch_energy<T, MECH>(s, element, num_gp, a);
+  else if (physics == FOL_THERMAL) rc = dispatch_energy<T, THERMAL>(s, element, num_gp, a);
+  else if (physics == FOL_NEOHOOKE) rc = dispatch_energy<T, NEOHOOKE>(s, element, num_gp, a);
+  else return fail(FOL_ERR_UNSUPPORTED, "fol_energy_and_grads: physics not supported");
+  if (rc) return rc;
+  energy_sum_kernel<T><<<(unsigned)cdiv(a.nb, 8), 256, 0, s>>>(a.partial, a.nb, a.ntiles, energy);
+  return check_launch("energy_sum_kernel");
 }
-template int energy_and_grads<double>(cudaStream_t, int, int, int, const EnergyArgs<double>&);
-template int energy_and_grads<float>(cudaStream_t, int, int, int, const EnergyArgs<float>&);
+template int energy_and_grads<double>(cudaStream_t, int, int, int, const EnergyArgs<double>&, double*);
+template int energy_and_grads<float>(cudaStream_t, int, int, int, const EnergyArgs<float>&, float*);
 
 template <class T, int ELEM>
 int launch_geom(cudaStream_t s, int num_gp, long long ne, const T* xyz, const int32_t* conn, T* geom) {
 #define FOL_CASE(O)                                                                                         \
   if (num_gp == O) {                                                                                        \
-    const long long total = ne * elem_ngauss(ELEM, O);                                                      \
-    if (total == 0) return FOL_OK;                                                                          \
-    geometry_cache_kernel<T, ELEM, O><<<(unsigned)cdiv(total, 128), 128, 0, s>>>(xyz, conn, ne, geom);      \
+    if (ne == 0) return FOL_OK;                                                                             \
+    dim3 grid((unsigned)cdiv(ne, 128), (unsigned)elem_ngauss(ELEM, O));                                     \
+    geometry_cache_kernel<T, ELEM, O><<<grid, 128, 0, s>>>(xyz, conn, ne, geom);                            \
     return check_launch("geometry_cache_kernel");                                                           \
   }
   FOL_CASE(1) FOL_CASE(2) FOL_CASE(3)
@@ -65,13 +80,12 @@ template int geometry_cache<double>(cudaStream_t, int, int, long long, const dou
 template int geometry_cache<float>(cudaStream_t, int, int, long long, const float*, const int32_t*, float*);
 
 template <class T>
-int loss_reduce(cudaStream_t s, long long nb, int nblocks, double exponent, const T* partial, T* energy, T* out4,
-                T* scale) {
-  loss_reduce_kernel<T><<<1, 256, 0, s>>>(partial, nb, nblocks, exponent, energy, out4, scale);
+int loss_reduce(cudaStream_t s, long long nb, double exponent, const T* energy, T* out4, T* scale) {
+  loss_reduce_kernel<T><<<1, 256, 0, s>>>(nb, exponent, energy, out4, scale);
   return check_launch("loss_reduce_kernel");
 }
-template int loss_reduce<double>(cudaStream_t, long long, int, double, const double*, double*, double*, double*);
-template int loss_reduce<float>(cudaStream_t, long long, int, double, const float*, float*, float*, float*);
+template int loss_reduce<double>(cudaStream_t, long long, double, const double*, double*, double*);
+template int loss_reduce<float>(cudaStream_t, long long, double, const float*, float*, float*);
 
 template <class T>
 int scale_grads(cudaStream_t s, long long nb, long long ndof, long long nn, const T* scale, double up,

@@ -1,14 +1,21 @@
 // Batched physics loss + its VJP (fe_loss.py:250-262 and the JAX-AD gradient of it).
 //
-// For every sample b the kernel produces, in ONE pass over the sample's nodal fields,
+// For every sample b:
 //   grad_u[b] = assembled UN-masked residual R(u_b)   (= dE_b/du_b because the reference
-//               stop_gradient's the element residual, mechanical.py:116, thermal.py:45-49)
+//               stop_gradient's the element residual, mechanical.py:116, thermal.py:45-49;
+//               for Neo-Hooke dE/du = F_int, mechanical_neohooke.py:262-275)
 //   grad_k[b] = dE_b/dK_b  (thermal / neo-hooke; identically zero for mechanical)
 //   E_b       = sum_e energy_e
-// Matrix-free (Ke is never formed), node-centric: thread (node n, sample block) walks the
-// node->element adjacency in fixed order, so the float sums are deterministic and need no atomics.
-// Geometry factors (grad N, w detJ per Gauss point) are shared by all samples and come from the
-// L2-resident geometry cache; each thread reuses them across S samples held in registers.
+// Matrix-free (Ke is never formed), atomics-free and single-pass: ONE kernel, no HBM scratch.
+// The mesh plan splits the nodes into compact tiles (Morton-ordered, <= 128 nodes) and lists, per
+// tile, the elements touching it.  A CTA owns (tile, a strided set of samples):
+//   phase A  thread (tile element, S samples): each listed element is evaluated once per sample from
+//            the geometry cache (grad N, w detJ per Gauss point; SoA, shared by all samples, L1/L2
+//            resident) and its vectors re_e, dK_e (psi_e) go to shared memory;
+//   phase B  thread (tile node, S samples): fixed-order sum over the node's adjacency (deterministic),
+//            coalesced write of grad_u / grad_k, block reduction of the sample's energy share.
+// Elements on tile borders are evaluated by each tile that needs them (~1.2x for compact tiles)
+// instead of being exchanged through memory.
 #pragma once
 #include "assemble.cuh"
 
@@ -16,27 +23,47 @@ namespace fol {
 
 template <class T>
 struct EnergyArgs {
-  const T* geom;           // [ne][NGP][A*D + 1]
+  const T* geom;              // [NGP][A*D + 1][ne]
   const int32_t* conn;
-  const int32_t* adj_ptr;
-  const int32_t* adj;
-  const T* ctrl;           // (nb, nn)
-  const T* u;              // (nb, ndof)
-  T* grad_u;               // (nb, ndof)
-  T* grad_k;               // (nb, nn) or null
-  T* partial;              // (nb, gridDim.x) block partial energies
+  const int32_t* adj_ptr;     // node -> adjacency range (same order as fol_node_adjacency)
+  const int32_t* adj_local;   // per adjacency entry: (element index within the node's tile)*A + a
+  const int32_t* tile_node_ptr;
+  const int32_t* tile_nodes;  // node ids grouped by tile
+  const int32_t* tile_elem_ptr;
+  const int32_t* tile_elems;  // element ids grouped by tile
+  const T* ctrl;              // (nb, nn)
+  const T* u;                 // (nb, ndof)
+  T* grad_u;                  // (nb, ndof)
+  T* grad_k;                  // (nb, nn) or null
+  T* partial;                 // (nb, ntiles) per-tile energy shares
   long long ne, nn, nb;
+  int ntiles, ecap;           // tiles, max elements per tile (shared-memory row length)
   Params<T> p;
 };
+
+// integer powers are evaluated by repeated multiplication, like lax.integer_pow does for the
+// reference's `T**c` with a Python-int exponent (thermal.py:34)
+template <class T>
+__device__ __forceinline__ T pow_c(T x, T c) {
+  const int ci = (int)c;
+  if ((T)ci == c && ci >= 0 && ci <= 15) {   // warp-uniform: c is a kernel parameter
+    const T x2 = x * x, x4 = x2 * x2, x8 = x4 * x4;
+    T r = (ci & 1) ? x : (T)1;
+    r = (ci & 2) ? r * x2 : r;
+    r = (ci & 4) ? r * x4 : r;
+    r = (ci & 8) ? r * x8 : r;
+    return r;
+  }
+  return (T)pow((double)x, (double)c);
+}
 
 template <class T, int ELEM, int ORDER>
 __global__ void geometry_cache_kernel(const T* __restrict__ xyz, const int32_t* __restrict__ conn, long long ne,
                                       T* __restrict__ geom) {
   constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM), NGP = elem_ngauss(ELEM, ORDER), W = A * D + 1;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= ne * NGP) return;
-  const long long e = t / NGP;
-  const int g = (int)(t % NGP);
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = blockIdx.y;
+  if (e >= ne) return;
   T X[A * 3];
 #pragma unroll
   for (int a = 0; a < A; ++a) {
@@ -49,238 +76,370 @@ __global__ void geometry_cache_kernel(const T* __restrict__ xyz, const int32_t* 
   T N[A], dN[A][D], gN[A][D];
   shape_functions<ELEM, T>(xi, N, dN);
   const T det = global_gradients<ELEM, T>(X, dN, gN);
-  T* out = geom + t * W;
+  T* out = geom + (long long)g * W * ne + e;
 #pragma unroll
   for (int a = 0; a < A; ++a)
 #pragma unroll
-    for (int k = 0; k < D; ++k) out[a * D + k] = gN[a][k];
-  out[A * D] = (T)w * det;
+    for (int k = 0; k < D; ++k) out[(long long)(a * D + k) * ne] = gN[a][k];
+  out[(long long)(A * D) * ne] = (T)w * det;
+  (void)NGP;
+}
+
+// scratch row count per element: re (ND) [+ dK (A)] [+ psi (1)]
+__host__ __device__ constexpr int energy_kw(int phys, int elem) {
+  return elem_nnode(elem) * phys_dpn(phys, elem) + (phys == MECH ? 0 : elem_nnode(elem)) + (phys == NEOHOOKE ? 1 : 0);
+}
+
+// Element vectors of element e for S samples starting at sample b0 (samples past nb are clamped):
+// re[s][nd], dK[s][a] (thermal / neo-hooke), en[s] (neo-hooke strain energy).
+// nodal gather of one sample for one element (fe_loss.py:155-164)
+template <class T, int A, int DPN>
+__device__ __forceinline__ void gather_sample(const EnergyArgs<T>& args, const int (&nodes)[A], long long b,
+                                              T (&ue)[1][A * DPN], T (&de)[1][A]) {
+  const long long bb = b < args.nb ? b : args.nb - 1;
+  const T* cb = args.ctrl + bb * args.nn;
+  const T* ub = args.u + bb * (args.nn * DPN);
+#pragma unroll
+  for (int a = 0; a < A; ++a) {
+    de[0][a] = __ldg(cb + nodes[a]);
+#pragma unroll
+    for (int k = 0; k < DPN; ++k) ue[0][a * DPN + k] = __ldg(ub + nodes[a] * DPN + k);
+  }
+}
+
+// geometry factors of one element fit in registers for the small elements / rules
+__host__ __device__ constexpr bool geom_in_regs(int elem, int order) {
+  return elem_ngauss(elem, order) * (elem_nnode(elem) * elem_dim(elem) + 1) <= 40;
+}
+
+template <class T, int ELEM, int ORDER, int PHYS, int S, bool REGS>
+__device__ __forceinline__ void element_vectors(const EnergyArgs<T>& args, long long e, const int (&nodes)[elem_nnode(ELEM)],
+                                                const T* greg,
+                                                const T (&ue)[S][elem_nnode(ELEM) * phys_dpn(PHYS, ELEM)],
+                                                const T (&de)[S][elem_nnode(ELEM)],
+                                                T (&re)[S][elem_nnode(ELEM) * phys_dpn(PHYS, ELEM)],
+                                                T (&dK)[S][elem_nnode(ELEM)], T (&en)[S]) {
+  constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM), DPN = phys_dpn(PHYS, ELEM), ND = A * DPN;
+  constexpr int NGP = elem_ngauss(ELEM, ORDER), V = voigt_size(D), W = A * D + 1;
+  const Params<T>& P = args.p;
+  (void)nodes;
+
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    en[s] = (T)0;
+#pragma unroll
+    for (int b = 0; b < A; ++b) {
+      dK[s][b] = (T)0;
+#pragma unroll
+      for (int k = 0; k < DPN; ++k) re[s][b * DPN + k] = (T)0;
+    }
+  }
+  T lam = (T)0, mu = (T)0;
+  if constexpr (PHYS == MECH) {
+    const T E = P.v[0], nu = P.v[1];
+    if constexpr (D == 3) {
+      const T c1 = E / (((T)1 + nu) * ((T)1 - (T)2 * nu));
+      lam = c1 * nu;
+      mu = c1 * (T)0.5 * ((T)1 - (T)2 * nu);
+    } else {
+      const T f = E / ((T)1 - nu * nu);
+      lam = f * nu;
+      mu = f * ((T)1 - nu) * (T)0.5;
+    }
+  }
+
+  // small rules are unrolled so the reference shape values N_a(xi_g) fold to constants
+  const T* gm = args.geom + e;
+  const long long ne = args.ne;
+#pragma unroll(NGP <= 4 ? NGP : 1)
+  for (int g = 0; g < NGP; ++g) {
+    T gN[A][D], wd;
+    if constexpr (REGS) {
+#pragma unroll
+      for (int b = 0; b < A; ++b)
+#pragma unroll
+        for (int k = 0; k < D; ++k) gN[b][k] = greg[g * W + b * D + k];
+      wd = greg[g * W + A * D];
+    } else {
+#pragma unroll
+      for (int b = 0; b < A; ++b)
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          gN[b][k] = __ldg(gm);
+          gm += ne;
+        }
+      wd = __ldg(gm);
+      gm += ne;
+    }
+    double xi[3], w;
+    gauss_point<ELEM, ORDER>(g, xi, w);
+    T N[A], dN[A][D];
+    shape_functions<ELEM, T>(xi, N, dN);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      T eg = (T)0;
+#pragma unroll
+      for (int b = 0; b < A; ++b) eg += N[b] * de[s][b];
+      if constexpr (PHYS == THERMAL) {
+        // kappa_g = (N.K)(1 + beta (N.T)^c); re_a += w detJ kappa_g grad N_a . grad T
+        // dE/dK_a += N_a (1 + beta T_g^c) |grad T|^2 w detJ        (thermal.py:28-49)
+        T tg = (T)0, gT[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) gT[k] = (T)0;
+#pragma unroll
+        for (int b = 0; b < A; ++b) {
+          tg += N[b] * ue[s][b];
+#pragma unroll
+          for (int k = 0; k < D; ++k) gT[k] += gN[b][k] * ue[s][b];
+        }
+        const T beta = P.v[5];
+        const T nl = (T)1 + ((beta != (T)0) ? beta * pow_c<T>(tg, P.v[6]) : (T)0);
+        T g2 = (T)0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) g2 += gT[k] * gT[k];
+        const T cf = wd * eg * nl, ck = wd * nl * g2;
+#pragma unroll
+        for (int b = 0; b < A; ++b) {
+          T flux = (T)0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) flux += gN[b][k] * gT[k];
+          re[s][b] += cf * flux;
+          dK[s][b] += ck * N[b];
+        }
+      } else if constexpr (PHYS == MECH) {
+        // H = grad u; sigma = E_g (lam tr(H) I + mu (H + H^T)); re_a += w detJ sigma grad N_a - Fe_a
+        T H[D][D];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            T acc = (T)0;
+#pragma unroll
+            for (int b = 0; b < A; ++b) acc += gN[b][j] * ue[s][b * D + i];
+            H[i][j] = acc;
+          }
+        T tr = (T)0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) tr += H[i][i];
+        const T cf = wd * eg;
+        T sig[D][D];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j) sig[i][j] = cf * (mu * (H[i][j] + H[j][i]) + (i == j ? lam * tr : (T)0));
+#pragma unroll
+        for (int b = 0; b < A; ++b)
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            T acc = -P.v[2 + i] * wd * N[b];
+#pragma unroll
+            for (int j = 0; j < D; ++j) acc += sig[i][j] * gN[b][j];
+            re[s][b * D + i] += acc;
+          }
+      } else {  // NEOHOOKE: psi and S are linear in E_g -> evaluate at unit modulus and scale
+        const T nu = P.v[1];
+        const T k1 = (T)1 / ((T)3 * ((T)1 - (T)2 * nu)), mu1 = (T)1 / ((T)2 * ((T)1 + nu));
+        T F[D][D];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            T acc = (i == j) ? (T)1 : (T)0;
+#pragma unroll
+            for (int b = 0; b < A; ++b) acc += gN[b][j] * ue[s][b * D + i];
+            F[i][j] = acc;
+          }
+        T Sv[V], Cv[V * V];
+        const T psi1 = neo_hooke_point<T, D>(F, k1, mu1, Sv, Cv);
+        en[s] += wd * eg * psi1;
+#pragma unroll
+        for (int b = 0; b < A; ++b) {
+          T Ba[V][D];
+          neo_hooke_B<T, D>(&F[0][0], gN[b], Ba);
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            T acc = (T)0;
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc += Ba[v][c] * Sv[v];
+            re[s][b * D + c] += wd * eg * acc;
+          }
+          dK[s][b] += wd * N[b] * psi1;
+        }
+      }
+    }
+  }
 }
 
 template <class T, int ELEM, int ORDER, int PHYS, int S, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) energy_grads_kernel(const EnergyArgs<T> args) {
-  constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM), DPN = phys_dpn(PHYS, ELEM), ND = A * DPN;
-  constexpr int NGP = elem_ngauss(ELEM, ORDER), W = A * D + 1, V = voigt_size(D);
-  const long long n = (long long)blockIdx.x * BLOCK + threadIdx.x;
-  const long long b0 = (long long)blockIdx.y * S;
+__global__ void __launch_bounds__(BLOCK, 2)
+energy_tile_kernel(const EnergyArgs<T> args) {
+  // S = samples per CTA pass; phase A work items are (element, sample) pairs, one per thread
+  constexpr int A = elem_nnode(ELEM), DPN = phys_dpn(PHYS, ELEM), ND = A * DPN, KW = energy_kw(PHYS, ELEM);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sv = reinterpret_cast<T*>(smem_raw);            // [S][KW][ecap]
+  __shared__ T red[S][BLOCK / 32];
+  const int t = blockIdx.x;
+  const int ecap = args.ecap;
+  const int e_beg = __ldg(args.tile_elem_ptr + t), n_el = __ldg(args.tile_elem_ptr + t + 1) - e_beg;
+  const int n_beg = __ldg(args.tile_node_ptr + t), n_nd = __ldg(args.tile_node_ptr + t + 1) - n_beg;
   const long long ndof = args.nn * DPN;
-  const Params<T>& P = args.p;
 
-  T R[S][DPN], dK[S], en[S];
+  // this thread's node (phase B) and its adjacency range are the same for every sample
+  const bool has_node = (int)threadIdx.x < n_nd;
+  const int n = has_node ? __ldg(args.tile_nodes + n_beg + threadIdx.x) : 0;
+  const int a_beg = has_node ? __ldg(args.adj_ptr + n) : 0, a_end = has_node ? __ldg(args.adj_ptr + n + 1) : 0;
+
+  // fast path: one thread per tile element, its geometry factors and node ids live in registers
+  constexpr bool REGS = geom_in_regs(ELEM, ORDER);
+  constexpr int GW = REGS ? elem_ngauss(ELEM, ORDER) * (A * elem_dim(ELEM) + 1) : 1;
+  const bool fast = REGS && n_el <= BLOCK;
+  T greg[GW];
+  int my_nodes[A];
+  long long my_el = -1;
+  if constexpr (REGS) {
+    if (fast && (int)threadIdx.x < n_el) {
+      my_el = __ldg(args.tile_elems + e_beg + threadIdx.x);
 #pragma unroll
-  for (int s = 0; s < S; ++s) {
-    dK[s] = (T)0;
-    en[s] = (T)0;
+      for (int b = 0; b < A; ++b) my_nodes[b] = __ldg(args.conn + my_el * A + b);
 #pragma unroll
-    for (int k = 0; k < DPN; ++k) R[s][k] = (T)0;
+      for (int k = 0; k < GW; ++k) greg[k] = __ldg(args.geom + (long long)k * args.ne + my_el);
+    }
   }
 
-  if (n < args.nn) {
-    T lam = (T)0, mu = (T)0;
-    if constexpr (PHYS == MECH) {
-      const T E = P.v[0], nu = P.v[1];
-      if constexpr (D == 3) {
-        const T c1 = E / (((T)1 + nu) * ((T)1 - (T)2 * nu));
-        lam = c1 * nu;
-        mu = c1 * (T)0.5 * ((T)1 - (T)2 * nu);
-      } else {
-        const T f = E / ((T)1 - nu * nu);
-        lam = f * nu;
-        mu = f * ((T)1 - nu) * (T)0.5;
+  for (long long b0 = (long long)blockIdx.y * S; b0 < args.nb; b0 += (long long)gridDim.y * S) {
+    const int ns = (args.nb - b0 < S) ? (int)(args.nb - b0) : S;
+    // ---- phase A: every element of the tile, once per sample
+    if constexpr (REGS) {
+      if (fast) {   // thread <-> element, geometry + connectivity stay in registers across samples
+        if (my_el >= 0) {
+          T ue[1][ND], de[1][A];
+          gather_sample<T, A, DPN>(args, my_nodes, b0, ue, de);
+          for (int sidx = 0; sidx < ns; ++sidx) {
+            T ue_n[1][ND], de_n[1][A];   // next sample's nodal values are in flight during this one
+            gather_sample<T, A, DPN>(args, my_nodes, b0 + sidx + 1, ue_n, de_n);
+            T re[1][ND], dK[1][A], en1[1];
+            element_vectors<T, ELEM, ORDER, PHYS, 1, true>(args, my_el, my_nodes, greg, ue, de, re, dK, en1);
+            T* out = sv + (sidx * KW) * ecap + threadIdx.x;
+#pragma unroll
+            for (int k = 0; k < ND; ++k) { *out = re[0][k]; out += ecap; }
+            if constexpr (PHYS != MECH) {
+#pragma unroll
+              for (int b = 0; b < A; ++b) { *out = dK[0][b]; out += ecap; }
+            }
+            if constexpr (PHYS == NEOHOOKE) *out = en1[0];
+#pragma unroll
+            for (int k = 0; k < ND; ++k) ue[0][k] = ue_n[0][k];
+#pragma unroll
+            for (int b = 0; b < A; ++b) de[0][b] = de_n[0][b];
+          }
+        }
       }
     }
-    const int beg = args.adj_ptr[n], end = args.adj_ptr[n + 1];
-    for (int it = beg; it < end; ++it) {
-      const int ea = args.adj[it];
-      const long long e = ea / A;
-      const int a = ea % A;
-      long long nodes[A];
+    if (!fast) {
+      const int items = n_el * ns;
+      int j = threadIdx.x, sidx = 0;
+      while (j >= n_el && sidx < ns) { j -= n_el; ++sidx; }
+      for (int it = threadIdx.x; it < items; it += BLOCK) {
+        const long long e = __ldg(args.tile_elems + e_beg + j);
+        int nodes[A];
 #pragma unroll
-      for (int b = 0; b < A; ++b) nodes[b] = args.conn[e * A + b];
-      T ue[S][ND], de[S][A];
+        for (int b = 0; b < A; ++b) nodes[b] = __ldg(args.conn + e * A + b);
+        T ue[1][ND], de[1][A], re[1][ND], dK[1][A], en1[1];
+        gather_sample<T, A, DPN>(args, nodes, b0 + sidx, ue, de);
+        element_vectors<T, ELEM, ORDER, PHYS, 1, false>(args, e, nodes, nullptr, ue, de, re, dK, en1);
+        T* out = sv + (sidx * KW) * ecap + j;
+#pragma unroll
+        for (int k = 0; k < ND; ++k) { *out = re[0][k]; out += ecap; }
+        if constexpr (PHYS != MECH) {
+#pragma unroll
+          for (int b = 0; b < A; ++b) { *out = dK[0][b]; out += ecap; }
+        }
+        if constexpr (PHYS == NEOHOOKE) *out = en1[0];
+        j += BLOCK;
+        while (j >= n_el) { j -= n_el; ++sidx; }
+      }
+    }
+    __syncthreads();
+    // ---- phase B: fixed-order adjacency sums for this tile's nodes
+    T en[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) en[s] = (T)0;
+    if (has_node) {
+      T R[S][DPN], dk[S];
 #pragma unroll
       for (int s = 0; s < S; ++s) {
-        const long long bb = (b0 + s < args.nb) ? b0 + s : args.nb - 1;
+        dk[s] = (T)0;
 #pragma unroll
-        for (int b = 0; b < A; ++b) {
-          de[s][b] = __ldg(args.ctrl + bb * args.nn + nodes[b]);
-#pragma unroll
-          for (int k = 0; k < DPN; ++k) ue[s][b * DPN + k] = __ldg(args.u + bb * ndof + nodes[b] * DPN + k);
-        }
+        for (int k = 0; k < DPN; ++k) R[s][k] = (T)0;
       }
-#pragma unroll 1
-      for (int g = 0; g < NGP; ++g) {
-        const T* gm = args.geom + (e * NGP + g) * W;
-        T gN[A][D];
-#pragma unroll
-        for (int b = 0; b < A; ++b)
-#pragma unroll
-          for (int k = 0; k < D; ++k) gN[b][k] = __ldg(gm + b * D + k);
-        const T wd = __ldg(gm + A * D);
-        double xi[3], w;
-        gauss_point<ELEM, ORDER>(g, xi, w);
-        T N[A], dN[A][D];
-        shape_functions<ELEM, T>(xi, N, dN);
-        // the local node `a` is a runtime index: select its row once
-        T ga[D], Na = (T)0;
-#pragma unroll
-        for (int k = 0; k < D; ++k) ga[k] = (T)0;
-#pragma unroll
-        for (int b = 0; b < A; ++b)
-          if (b == a) {
-            Na = N[b];
-#pragma unroll
-            for (int k = 0; k < D; ++k) ga[k] = gN[b][k];
-          }
+      for (int it = a_beg; it < a_end; ++it) {
+        const int ja = __ldg(args.adj_local + it);
+        const int jl = ja / A, a = ja - jl * A;
+        const T* in = sv + jl + (a * DPN) * ecap;
+        const T* ink = sv + jl + (ND + a) * ecap;
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-          if constexpr (PHYS == NEOHOOKE) break;
-          T eg = (T)0;
+          if (s < ns) {
 #pragma unroll
-          for (int b = 0; b < A; ++b) eg += N[b] * de[s][b];
-          if constexpr (PHYS == THERMAL) {
-            T tg = (T)0, gT[D];
-#pragma unroll
-            for (int k = 0; k < D; ++k) gT[k] = (T)0;
-#pragma unroll
-            for (int b = 0; b < A; ++b) {
-              tg += N[b] * ue[s][b];
-#pragma unroll
-              for (int k = 0; k < D; ++k) gT[k] += gN[b][k] * ue[s][b];
-            }
-            const T beta = P.v[5], cexp = P.v[6];
-            const T nl = (T)1 + ((beta != (T)0) ? beta * (T)pow((double)tg, (double)cexp) : (T)0);
-            T flux = (T)0, g2 = (T)0;
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-              flux += ga[k] * gT[k];
-              g2 += gT[k] * gT[k];
-            }
-            R[s][0] += wd * eg * nl * flux;
-            dK[s] += wd * Na * nl * g2;
-          } else if constexpr (PHYS == MECH) {
-            // H[i][j] = du_i/dx_j ; sigma = lam tr(eps) I + mu (H + H^T) scaled by wd*E_g
-            T H[D][D];
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-#pragma unroll
-              for (int j = 0; j < D; ++j) {
-                T acc = (T)0;
-#pragma unroll
-                for (int b = 0; b < A; ++b) acc += gN[b][j] * ue[s][b * D + i];
-                H[i][j] = acc;
-              }
-            T tr = (T)0;
-#pragma unroll
-            for (int i = 0; i < D; ++i) tr += H[i][i];
-            const T cf = wd * eg;
-#pragma unroll
-            for (int i = 0; i < D; ++i) {
-              T acc = lam * tr * ga[i];
-#pragma unroll
-              for (int j = 0; j < D; ++j) acc += mu * (H[i][j] + H[j][i]) * ga[j];
-              R[s][i] += cf * acc;
-            }
+            for (int k = 0; k < DPN; ++k) R[s][k] += in[(s * KW + k) * ecap];
+            if constexpr (PHYS != MECH) dk[s] += ink[(s * KW) * ecap];
+            // each element's strain energy is counted once: at its local node 0, by the tile owning it
+            if constexpr (PHYS == NEOHOOKE) en[s] += (a == 0) ? sv[jl + (s * KW + ND + A) * ecap] : (T)0;
           }
         }
-        if constexpr (PHYS == NEOHOOKE) {
-          // energy = sum_g wd psi (true strain energy, mechanical_neohooke.py:262, 271): psi, S are
-          // linear in E_g, so evaluate the law at unit modulus and scale.  dE/du = F_int (no Fe).
-          const T nu = P.v[1];
-          const T k1 = (T)1 / ((T)3 * ((T)1 - (T)2 * nu)), mu1 = (T)1 / ((T)2 * ((T)1 + nu));
+      }
 #pragma unroll
-          for (int s = 0; s < S; ++s) {
-            T eg = (T)0;
+      for (int s = 0; s < S; ++s) {
+        if (s < ns) {
+          const long long bb = b0 + s;
 #pragma unroll
-            for (int b = 0; b < A; ++b) eg += N[b] * de[s][b];
-            T F[D][D];
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-#pragma unroll
-              for (int j = 0; j < D; ++j) {
-                T acc = (i == j) ? (T)1 : (T)0;
-#pragma unroll
-                for (int b = 0; b < A; ++b) acc += gN[b][j] * ue[s][b * D + i];
-                F[i][j] = acc;
-              }
-            T Sv[V], Cv[V * V];
-            const T psi1 = neo_hooke_point<T, D>(F, k1, mu1, Sv, Cv);
-            T Ba[V][D];
-            neo_hooke_B<T, D>(&F[0][0], ga, Ba);
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-              T acc = (T)0;
-#pragma unroll
-              for (int v = 0; v < V; ++v) acc += Ba[v][c] * Sv[v];
-              R[s][c] += wd * eg * acc;
-            }
-            dK[s] += wd * Na * psi1;
-            if (a == 0) en[s] += wd * eg * psi1;  // each element's energy is counted at its node 0
+          for (int k = 0; k < DPN; ++k) {
+            if constexpr (PHYS != NEOHOOKE) en[s] += __ldg(args.u + bb * ndof + n * DPN + k) * R[s][k];  // u_b . R_b
+            args.grad_u[bb * ndof + n * DPN + k] = R[s][k];
           }
-        }
-        if constexpr (PHYS == MECH) {
-          // body force: Fe_a = b * w detJ N_a (same for every sample)
-#pragma unroll
-          for (int s = 0; s < S; ++s)
-#pragma unroll
-            for (int i = 0; i < D; ++i) R[s][i] -= P.v[2 + i] * wd * Na;
+          if constexpr (PHYS != MECH) {
+            if (args.grad_k) args.grad_k[bb * args.nn + n] = dk[s];
+          }
         }
       }
     }
-    // write gradients, accumulate this node's share of the energy E_b = u_b . R_b
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      const long long bb = b0 + s;
-      if (bb < args.nb) {
+      T v = en[s];
 #pragma unroll
-        for (int k = 0; k < DPN; ++k) {
-          if constexpr (PHYS != NEOHOOKE) {  // E_b = u_b . R_b (mechanical.py:116-117, thermal.py:45-49)
-            const T uk = __ldg(args.u + bb * ndof + n * DPN + k);
-            en[s] += uk * R[s][k];
-          }
-          args.grad_u[bb * ndof + n * DPN + k] = R[s][k];
-        }
-        if (args.grad_k) args.grad_k[bb * args.nn + n] = dK[s];
-      }
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) red[s][threadIdx.x >> 5] = v;
     }
-  }
-
-  // deterministic block reduction of the per-sample energies (fixed tree)
-  __shared__ T red[S][BLOCK / 32];
+    __syncthreads();  // also: everyone is done reading sv before the next sample batch overwrites it
+    if ((int)threadIdx.x < ns) {
+      T v = (T)0;
 #pragma unroll
-  for (int s = 0; s < S; ++s) {
-    T v = en[s];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) red[s][threadIdx.x >> 5] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < S) {
-    T v = (T)0;
-#pragma unroll
-    for (int w = 0; w < BLOCK / 32; ++w) v += red[threadIdx.x][w];
-    const long long bb = b0 + threadIdx.x;
-    if (bb < args.nb) args.partial[bb * gridDim.x + blockIdx.x] = v;
+      for (int w = 0; w < BLOCK / 32; ++w) v += red[threadIdx.x][w];
+      args.partial[(b0 + threadIdx.x) * args.ntiles + t] = v;
+    }
   }
 }
 
-// E_b = sum of block partials (fixed order), then L = mean E_b^p, (min, max, mean), scale_b
+// E_b = sum of block partials (fixed order); optionally L = mean E_b^p, (min, max, mean), scale_b
 template <class T>
-__global__ void loss_reduce_kernel(const T* __restrict__ partial, long long nb, int nblocks, double exponent,
-                                   T* __restrict__ energy, T* __restrict__ out4, T* __restrict__ scale) {
-  // single block; thread-strided over samples, then a fixed-order tree
+__global__ void energy_sum_kernel(const T* __restrict__ partial, long long nb, int nblocks, T* __restrict__ energy) {
+  // one warp per sample: lane-strided partial sums, then a fixed xor tree
+  const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= nb) return;
+  T acc = (T)0;
+  for (int k = threadIdx.x & 31; k < nblocks; k += 32) acc += partial[b * nblocks + k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) energy[b] = acc;
+}
+
+template <class T>
+__global__ void loss_reduce_kernel(long long nb, double exponent, const T* __restrict__ energy, T* __restrict__ out4,
+                                   T* __restrict__ scale) {
   __shared__ double s_sum[256], s_min[256], s_max[256];
   double lsum = 0.0, lmin = INFINITY, lmax = -INFINITY;
   for (long long b = threadIdx.x; b < nb; b += blockDim.x) {
-    double E;
-    if (nblocks > 0) {
-      T acc = (T)0;
-      for (int k = 0; k < nblocks; ++k) acc += partial[b * nblocks + k];
-      energy[b] = acc;
-      E = (double)acc;
-    } else {
-      E = (double)energy[b];
-    }
+    const double E = (double)energy[b];
     const double Ep = (exponent == 1.0) ? E : pow(E, exponent);
     const double dE = (exponent == 1.0) ? 1.0 : exponent * pow(E, exponent - 1.0);
     scale[b] = (T)(dE / (double)nb);

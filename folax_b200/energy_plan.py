@@ -1,0 +1,56 @@
+"""Integer tile plan of the fused batched-loss kernel (host side, built once per mesh).
+
+Nodes are ordered along a Morton (Z-order) curve of their coordinates and cut into tiles of at
+most TILE_NODES nodes, so every tile is a compact patch; per tile the plan lists the elements
+touching it and re-expresses the node->element adjacency in tile-local element indices.  Pure
+integer work, deterministic; the adjacency order equals fol_node_adjacency's (ascending e*A + a).
+"""
+import numpy as np
+
+TILE_NODES = 128
+
+
+def _morton_keys(coords, bits=16):
+    X = np.asarray(coords, dtype=np.float64)
+    lo, hi = X.min(0), X.max(0)
+    span = np.where(hi > lo, hi - lo, 1.0)
+    q = np.minimum(((X - lo) / span * (2 ** bits - 1)).astype(np.uint64), 2 ** bits - 1)
+    key = np.zeros(len(X), dtype=np.uint64)
+    for b in range(bits):
+        for d in range(3):
+            key |= ((q[:, d] >> np.uint64(b)) & np.uint64(1)) << np.uint64(3 * b + d)
+    return key
+
+
+def build(coords, conn, tile_nodes=TILE_NODES):
+    """Returns dict of int32 arrays: adj_ptr, adj_local, tile_node_ptr, tile_nodes, tile_elem_ptr,
+    tile_elems and ints ntiles, ecap."""
+    conn = np.asarray(conn, dtype=np.int64)
+    ne, A = conn.shape
+    nn = len(coords)
+    order = np.argsort(_morton_keys(coords), kind="stable")          # nodes in tile order
+    rank = np.empty(nn, dtype=np.int64)
+    rank[order] = np.arange(nn)
+    tile_of_node = rank // tile_nodes
+    ntiles = int((nn + tile_nodes - 1) // tile_nodes)
+    tile_node_ptr = np.minimum(np.arange(ntiles + 1, dtype=np.int64) * tile_nodes, nn)
+    # adjacency sorted by node, then by e*A + a (stable sort keeps ascending entry ids)
+    flat_nodes = conn.reshape(-1)
+    entries = np.argsort(flat_nodes, kind="stable")                   # values: e*A + a
+    counts = np.bincount(flat_nodes, minlength=nn)
+    adj_ptr = np.concatenate([[0], np.cumsum(counts)])
+    node_of_entry = flat_nodes[entries]
+    elem_of_entry = entries // A
+    a_of_entry = entries - elem_of_entry * A
+    key = tile_of_node[node_of_entry] * ne + elem_of_entry          # (tile, element) pairs
+    ukeys = np.unique(key)                                            # sorted
+    tile_elems = ukeys % ne
+    tile_of_ukey = ukeys // ne
+    tile_elem_ptr = np.searchsorted(tile_of_ukey, np.arange(ntiles + 1))
+    local = np.searchsorted(ukeys, key) - tile_elem_ptr[tile_of_node[node_of_entry]]
+    adj_local = local * A + a_of_entry
+    ecap = int(np.diff(tile_elem_ptr).max()) if ntiles else 1
+    i32 = lambda x: np.ascontiguousarray(x, dtype=np.int32)
+    return {"adj_ptr": i32(adj_ptr), "adj_local": i32(adj_local), "tile_node_ptr": i32(tile_node_ptr),
+            "tile_nodes": i32(order), "tile_elem_ptr": i32(tile_elem_ptr), "tile_elems": i32(tile_elems),
+            "ntiles": ntiles, "ecap": max(ecap, 1)}

@@ -299,21 +299,42 @@ class FiniteElementLoss(Loss):
 
     _has_control_gradient = True
 
+    def _energy_plan(self):
+        """Device-resident integer tile plan of the fused batched-loss kernel (energy_plan.py)."""
+        if self.__dict__.get("_eplan") is None:
+            from .. import energy_plan
+            plan = energy_plan.build(np.asarray(self.fe_mesh.GetNodesCoordinates()),
+                                     self.fe_mesh.GetElementsNodes(self.element_type))
+            self._eplan = {k: (torch.as_tensor(v, device=self.device) if isinstance(v, np.ndarray) else v)
+                           for k, v in plan.items()}
+        return self._eplan
+
+    def _energy_work(self, nb):
+        """Scratch of the batched-loss kernel, cached per batch size (no allocation on the hot call)."""
+        cache = self.__dict__.setdefault("_work_cache", {})
+        if nb not in cache:
+            n = _lib.load().fol_energy_work_size(self._energy_plan()["ntiles"], nb)
+            cache.clear()
+            cache[nb] = torch.empty(n, dtype=self.dtype, device=self.device)
+        return cache[nb]
+
     def _energy_and_grads(self, batch_params, batch_dofs):
         """(E_b, dE_b/du_b (un-masked assembled residual), dE_b/dK_b) for BC-applied dofs."""
         lib = _lib.load()
         nb = batch_dofs.shape[0]
-        geom = self._geometry_cache()
+        geom, ep = self._geometry_cache(), self._energy_plan()
         grad_u = torch.empty_like(batch_dofs)
         grad_k = torch.empty_like(batch_params) if self._has_control_gradient else None
         energy = torch.empty(nb, dtype=self.dtype, device=self.device)
-        work = torch.empty(lib.fol_energy_work_size(self._nn, nb), dtype=self.dtype, device=self.device)
+        work = self._energy_work(nb)
         _lib.check(lib.fol_energy_and_grads(_lib.stream_ptr(), self._dt, _lib.PHYSICS[self.physics],
                                             self.fe_element.code, self.num_gp, self._ne, self._nn, nb,
-                                            _lib.ptr(geom), _lib.ptr(self._conn), _lib.ptr(self._adj_ptr),
-                                            _lib.ptr(self._adj), _lib.ptr(batch_params), _lib.ptr(batch_dofs),
-                                            self._params, _lib.ptr(grad_u), _lib.ptr(grad_k), _lib.ptr(energy),
-                                            _lib.ptr(work)))
+                                            _lib.ptr(geom), _lib.ptr(self._conn), _lib.ptr(ep["adj_ptr"]),
+                                            _lib.ptr(ep["adj_local"]), _lib.ptr(ep["tile_node_ptr"]),
+                                            _lib.ptr(ep["tile_nodes"]), _lib.ptr(ep["tile_elem_ptr"]),
+                                            _lib.ptr(ep["tile_elems"]), ep["ntiles"], ep["ecap"],
+                                            _lib.ptr(batch_params), _lib.ptr(batch_dofs), self._params,
+                                            _lib.ptr(grad_u), _lib.ptr(grad_k), _lib.ptr(energy), _lib.ptr(work)))
         return energy, grad_u, grad_k
 
     def ComputeBatchLoss(self, batch_params, batch_dofs):

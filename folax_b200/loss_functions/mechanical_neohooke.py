@@ -18,22 +18,26 @@ class NeoHookeMechanicalLoss(MechanicalLoss):
 
     def _element_energy(self, xyz, conn, ctrl, u, re):
         # energy = sum_g w detJ psi (mechanical_neohooke.py:262, 271), not u . re
+        import numpy as np
         import torch
-        from .. import _lib
+        from .. import _lib, energy_plan
         lib = _lib.load()
         A, s = self._nnode, _lib.stream_ptr()
         width = A * self._edim + 1
         geom = torch.empty(self._ngauss * width, dtype=self.dtype, device=self.device)
         _lib.check(lib.fol_geometry_cache(s, self._dt, self.fe_element.code, self.num_gp, 1, _lib.ptr(xyz),
                                           _lib.ptr(conn), _lib.ptr(geom)))
-        adj_ptr = torch.arange(A + 1, dtype=torch.int32, device=self.device)
-        adj = torch.arange(A, dtype=torch.int32, device=self.device)
+        ep = {k: (torch.as_tensor(v, device=self.device) if isinstance(v, np.ndarray) else v)
+              for k, v in energy_plan.build(xyz.cpu().numpy(), conn.cpu().numpy()).items()}
         gu, gk = torch.empty_like(u), torch.empty_like(ctrl)
         energy = torch.empty(1, dtype=self.dtype, device=self.device)
-        work = torch.empty(lib.fol_energy_work_size(A, 1), dtype=self.dtype, device=self.device)
+        work = torch.empty(lib.fol_energy_work_size(ep["ntiles"], 1), dtype=self.dtype, device=self.device)
         _lib.check(lib.fol_energy_and_grads(s, self._dt, _lib.PHYSICS[self.physics], self.fe_element.code,
-                                            self.num_gp, 1, A, 1, _lib.ptr(geom), _lib.ptr(conn), _lib.ptr(adj_ptr),
-                                            _lib.ptr(adj), _lib.ptr(ctrl), _lib.ptr(u), self._params, _lib.ptr(gu),
+                                            self.num_gp, 1, A, 1, _lib.ptr(geom), _lib.ptr(conn),
+                                            _lib.ptr(ep["adj_ptr"]), _lib.ptr(ep["adj_local"]),
+                                            _lib.ptr(ep["tile_node_ptr"]), _lib.ptr(ep["tile_nodes"]),
+                                            _lib.ptr(ep["tile_elem_ptr"]), _lib.ptr(ep["tile_elems"]), ep["ntiles"],
+                                            ep["ecap"], _lib.ptr(ctrl), _lib.ptr(u), self._params, _lib.ptr(gu),
                                             _lib.ptr(gk), _lib.ptr(energy), _lib.ptr(work)))
         return energy[0]
 

@@ -99,8 +99,8 @@ int fol_residual_gather(fol_stream_t s, int dtype, int64_t nn, int nnode, int do
 
 /* ---- batched physics loss + VJP (fe_loss.py:250-262 and its JAX-AD gradient) -------------- */
 
-/* per-element, per-Gauss-point geometry factors shared by all samples:
- * geom[e][g][0..a*dim-1] = grad N (a, dim), geom[e][g][a*dim] = w*detJ.   */
+/* per-element, per-Gauss-point geometry factors shared by all samples, SoA over elements:
+ * geom[(g*(a*dim+1) + k)*ne + e] = grad N flattened (k < a*dim) | w*detJ (k = a*dim).   */
 int fol_geometry_cache(fol_stream_t s, int dtype, int element, int num_gp, int64_t ne,
                        const void* xyz, const int32_t* conn, void* geom);
 
@@ -109,13 +109,21 @@ int fol_geometry_cache(fol_stream_t s, int dtype, int element, int num_gp, int64
  *   grad_u[b]  = assembled, UN-masked residual R(u_b)      (= dE_b/du_b)
  *   grad_k[b]  = dE_b/dK_b                                  (NULL for mechanical: it is zero)
  *   energy[b]  = E_b = sum_e energy_e                       (before the exponent)
- * Deterministic (node-centric fixed-order sums). `work` needs nb*gridDim partials; pass
- * fol_energy_work_size() doubles/floats. */
-int64_t fol_energy_work_size(int64_t nn, int64_t nb);
+ * One fused kernel, deterministic (fixed-order sums, no atomics, no HBM scratch).  The integer
+ * tile plan is built once per mesh by the host (folax_b200/energy_plan.py):
+ *   tile_node_ptr (ntiles+1) / tile_nodes (nn): nodes grouped into compact tiles of <= 128 nodes
+ *   tile_elem_ptr (ntiles+1) / tile_elems: the elements touching each tile
+ *   adj_ptr (nn+1): node adjacency ranges (same order as fol_node_adjacency)
+ *   adj_local: per adjacency entry (index of the element within the node's tile list)*nnode + a
+ *   ecap: the longest tile element list.
+ * `work` is scratch of fol_energy_work_size(ntiles, nb) elements of the call's dtype. */
+int64_t fol_energy_work_size(int64_t ntiles, int64_t nb);
 int fol_energy_and_grads(fol_stream_t s, int dtype, int physics, int element, int num_gp,
                          int64_t ne, int64_t nn, int64_t nb, const void* geom,
-                         const int32_t* conn, const int32_t* adj_ptr, const int32_t* adj,
-                         const void* ctrl, const void* u, const double* params_host,
+                         const int32_t* conn, const int32_t* adj_ptr, const int32_t* adj_local,
+                         const int32_t* tile_node_ptr, const int32_t* tile_nodes,
+                         const int32_t* tile_elem_ptr, const int32_t* tile_elems, int64_t ntiles,
+                         int64_t ecap, const void* ctrl, const void* u, const double* params_host,
                          void* grad_u, void* grad_k, void* energy, void* work);
 
 /* loss tail: L = mean_b E_b^p, stats = (min, max, mean) of E_b^p, scale[b] = p E_b^(p-1)/nb.
