@@ -19,7 +19,7 @@ LIB = os.path.join(LIBDIR, "libfolax_b200.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr", "-DFOL_HAVE_J2"]
 
 
 def _sources():

@@ -6,3 +6,5 @@ from .thermal import ThermalLoss, ThermalLoss2DQuad, ThermalLoss2DTri, ThermalLo
 from .mechanical_neohooke import (NeoHookeMechanicalLoss, NeoHookeMechanicalLoss2DQuad,
                                   NeoHookeMechanicalLoss2DTri, NeoHookeMechanicalLoss3DHexa,
                                   NeoHookeMechanicalLoss3DTetra)
+from .mechanical_elastoplasticity import (ElastoplasticityLoss, ElastoplasticityLoss2DQuad,
+                                          ElastoplasticityLoss3DHexa, ElastoplasticityLoss3DTetra)

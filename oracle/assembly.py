@@ -166,3 +166,23 @@ def batch_loss_grads(physics, element_type, num_gp, coords, conn, batch_controls
     gK *= scale[:, None]
     gU[:, dirichlet_indices] = 0.0
     return gU, gK
+
+
+def assemble_j2(element_type, num_gp, coords, conn, dofs, state, dirichlet_indices, params, transpose=False):
+    """ElastoplasticityLoss.ComputeJacobianMatrixAndResidualVector
+    (mechanical_elastoplasticity.py:153-235) -> (new_state, data, indices, residual)."""
+    from . import j2
+    elem = ELEMENTS[element_type]
+    d = elem.dim
+    ndof = d * coords.shape[0]
+    bc_vec = np.ones(ndof)
+    bc_vec[dirichlet_indices] = 0.0
+    g = element_dof_ids(conn, d)
+    _, new_state, re, Ke = j2.j2_element(element_type, num_gp, coords[conn], dofs[g], state,
+                                         params["young_modulus"], params["poisson_ratio"], params["yield_limit"],
+                                         params["iso_hardening_parameter_1"], params["iso_hardening_param_2"],
+                                         params.get("body_force"))
+    re, Ke = apply_dirichlet(re, Ke, bc_vec[g], transpose)
+    R = np.zeros(ndof)
+    np.add.at(R, g.reshape(-1), re.reshape(-1))
+    return new_state, Ke.reshape(-1), bcoo_indices(conn, d), R
