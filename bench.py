@@ -247,7 +247,7 @@ def run_ours(args):
 
     import folax_b200
     from folax_b200 import _lib
-    from folax_b200.distributed import SlabPartition
+    from folax_b200.distributed import SlabPartition, assemble_overlapped
     from folax_b200.loss_functions import MechanicalLoss3DHexa
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -272,10 +272,12 @@ def run_ours(args):
     u = loss.ApplyDirichletBCOnDofVector(torch.tensor(u_host, device="cuda"))
     ke = torch.empty(ne * 576, dtype=torch.float64, device="cuda")
 
+    comm_stream = torch.cuda.Stream() if world > 1 else None
+
     def step():
-        data, R = loss._assemble(K, u, False, ke_out=ke)
-        part.halo_sum(R, 3)
-        return data, R
+        if world > 1:   # halo-DOF exchange hidden behind the interior element stage
+            return assemble_overlapped(loss, part, K, u, ke, comm_stream)
+        return loss._assemble(K, u, False, ke_out=ke)
 
     for _ in range(args.warmup):
         step()
@@ -308,7 +310,7 @@ def run_ours(args):
     hbm, peak_src = measured_peaks()
     achieved = ALG_BYTES_PER_ELEMENT_F64 * ne / (ms_kernel * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                "traffic": None, "kernel": "assemble_kernel<double,HEX,2,MECH> (element stage)",
+                "traffic": None, "kernel": "assemble_hex_mech_f64_kernel (element stage: DMMA m8n8k4 + cp.async.bulk stores)",
                 "kernel_ms": ms_kernel, "algorithmic_bytes_per_element": ALG_BYTES_PER_ELEMENT_F64,
                 "peak_source": peak_src}
 

@@ -78,6 +78,70 @@ class SlabPartition:
         return residual
 
 
+def assemble_overlapped(loss, part, controls, dofs, ke_out, comm_stream, group=None):
+    """Residual + Jacobian of one slab with the halo-DOF exchange hidden behind the element stage.
+
+    The element layers touching the slab interfaces are contiguous element ranges (the generator
+    numbers elements layer by layer), and the interface planes are contiguous node ranges, so:
+      1. element stage on the bottom and top element layers (two small launches),
+      2. deterministic residual gather of the two interface node planes,
+      3. on `comm_stream`: neighbour exchange + add of those planes (NCCL send/recv over NVLink),
+      4. meanwhile on the main stream: element stage on the interior layers, gather of all interior
+         nodes,
+      5. main stream joins the communication stream.
+    Returns (ke_out, residual)."""
+    from . import _lib
+    lib = _lib.load()
+    dt, d, A, nd = loss._dt, loss.number_dofs_per_node, loss._nnode, loss._nd
+    ne, nn = loss._ne, loss._nn
+    esz = 8 if loss.dtype == torch.float64 else 4
+    layer = ne // part.nz_local                     # elements per z-layer
+    plane = part.plane_nodes
+    K = _lib.to_device(controls, loss.dtype).reshape(-1)
+    u = _lib.to_device(dofs, loss.dtype).reshape(-1)
+    re = torch.empty(ne * nd, dtype=loss.dtype, device=loss.device)
+    R = torch.empty(loss.total_number_of_dofs, dtype=loss.dtype, device=loss.device)
+    phys, elem = _lib.PHYSICS[loss.physics], loss.fe_element.code
+    s = _lib.stream_ptr()
+
+    def elements(e0, cnt):
+        if cnt <= 0:
+            return
+        _lib.check(lib.fol_assemble_elements(s, dt, phys, elem, loss.num_gp, 0, cnt, nn, _lib.ptr(loss._xyz),
+                                             loss._conn.data_ptr() + 4 * A * e0, _lib.ptr(K), _lib.ptr(u),
+                                             _lib.ptr(loss._dir_flag), loss._params,
+                                             ke_out.data_ptr() + esz * nd * nd * e0, re.data_ptr() + esz * nd * e0,
+                                             None, None))
+
+    def gather(n0, cnt):
+        if cnt <= 0:
+            return
+        _lib.check(lib.fol_residual_gather(s, dt, cnt, A, d, loss._adj_ptr.data_ptr() + 4 * n0, _lib.ptr(loss._adj),
+                                           _lib.ptr(re), R.data_ptr() + esz * d * n0))
+
+    if part.world == 1 or part.nz_local < 3:
+        elements(0, ne)
+        gather(0, nn)
+        part.halo_sum(R, d, group)
+        return ke_out, R
+    # bottom-plane nodes touch only element layer 0, top-plane nodes only the last layer
+    elements(0, layer)
+    elements(ne - layer, layer)
+    gather(0, plane)
+    gather(nn - plane, plane)
+    ready = torch.cuda.Event()
+    ready.record()
+    with torch.cuda.stream(comm_stream):
+        comm_stream.wait_event(ready)
+        part.halo_sum(R, d, group)
+        done = torch.cuda.Event()
+        done.record()
+    elements(layer, ne - 2 * layer)
+    gather(plane, nn - 2 * plane)
+    torch.cuda.current_stream().wait_event(done)
+    return ke_out, R
+
+
 def allreduce_gradients(parameters, group=None, bucket_bytes=64 << 20):
     """Sum `.grad` of the given parameters over all ranks with as few NCCL calls as fit the
     bucket size (flatten -> all_reduce -> unflatten)."""
