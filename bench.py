@@ -9,7 +9,7 @@ float64, 128^3 elements per GPU (configs[1]).  One JSON line on stdout (rank 0).
   e2e         same metric through the host-buffer C-ABI call fol_plan_assemble_host (pinned host
               inputs -> H2D, kernels, D2H of the BCOO data + residual inside the timed region)
   roofline    dominant kernel (element stage) vs measured HBM copy bandwidth
-  cpu_baseline  NumPy oracle (port of the reference arithmetic) on the host cores, bounded sample
+  cpu_baseline  C/OpenMP port of the reference arithmetic (oracle/c) on all host cores, bounded sample
   fol_loss_grad secondary metric: FOL physics loss + VJP samples/s (thermal 256x256 quads)
 `--impl reference` times the CPU port alone (the reference itself needs JAX, absent here).
 """
@@ -92,51 +92,29 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------ CPU leg
 def cpu_assembly_rate(n_side, min_seconds, threads):
-    """Oracle (NumPy port of the reference arithmetic) on a n_side^3 hex box, chunks spread over
-    `threads` host threads (NumPy releases the GIL inside einsum/BLAS).  Returns elements/s."""
-    from concurrent.futures import ThreadPoolExecutor
-
+    """CPU baseline: the plain-C / OpenMP restatement of the reference arithmetic (oracle/c/hex_mech.c,
+    dense B^T D B per Gauss point exactly as mechanical.py:98-117 writes it) on an n_side^3 hex box, all
+    host threads.  Returns (elements/s, elements done, seconds)."""
     import folax_b200
-    from oracle import assembly
-    try:
-        from threadpoolctl import threadpool_limits
-    except Exception:
-        threadpool_limits = None
+    from oracle import assembly, c_oracle
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
     mesh = folax_b200.create_3D_box_mesh(n_side, n_side, n_side, 1.0, 1.0, 1.0)
     coords, conn = np.asarray(mesh.GetNodesCoordinates()), mesh.GetElementsNodes("hexahedron")
     rng = np.random.default_rng(0)
     K = rng.uniform(0.1, 1.0, len(coords))
     u = 0.01 * rng.standard_normal(3 * len(coords))
-    sets = mesh.node_sets
-    didx, _ = assembly.dirichlet_vectors(["Ux", "Uy", "Uz"], {d: {"left": 0.0, "right": 0.1} for d in ("Ux", "Uy", "Uz")}, sets)
+    didx, _ = assembly.dirichlet_vectors(["Ux", "Uy", "Uz"], {d: {"left": 0.0, "right": 0.1} for d in ("Ux", "Uy", "Uz")},
+                                         mesh.node_sets)
     ne = len(conn)
-    chunk = 2048
-    parts = [slice(s, min(s + chunk, ne)) for s in range(0, ne, chunk)]
-
-    def work(sl):
-        data, _, R = assembly.assemble("mechanical", "hexahedron", 2, coords, conn[sl], K, u, didx, MATERIAL,
-                                       chunk=chunk)
-        return data.shape[0]
-
-    def one_pass():
-        with ThreadPoolExecutor(threads) as ex:
-            list(ex.map(work, parts))
-
-    ctx = threadpool_limits(limits=1) if threadpool_limits else None
-    if ctx:
-        ctx.__enter__()
-    try:
-        one_pass()  # warm-up
-        t0, done = time.perf_counter(), 0
-        while True:
-            one_pass()
-            done += ne
-            if time.perf_counter() - t0 >= min_seconds:
-                break
-        dt = time.perf_counter() - t0
-    finally:
-        if ctx:
-            ctx.__exit__(None, None, None)
+    out = np.empty(ne * 576)
+    c_oracle.hex_mech_assemble(coords, conn, K, u, didx, 1.0, 0.3, out=out)  # warm-up (page faults, threads)
+    t0, done = time.perf_counter(), 0
+    while True:
+        c_oracle.hex_mech_assemble(coords, conn, K, u, didx, 1.0, 0.3, out=out)
+        done += ne
+        if time.perf_counter() - t0 >= min_seconds:
+            break
+    dt = time.perf_counter() - t0
     return done / dt, done, dt
 
 
@@ -145,7 +123,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_side = 24
+    n_side = 64
     per_step = []
     for _ in range(args.warmup):
         cpu_assembly_rate(n_side, 0.0, threads)
@@ -162,11 +140,12 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * float(np.mean(per_step)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"hex{args.n}_linear_elastic_residual_jacobian_f64 (CPU leg timed on a bounded "
-                                   f"{n_side}^3 sample of the same mesh family)"},
+            "config": {"workload": f"hex{args.n}_linear_elastic_residual_jacobian_f64", "num_gp": 2,
+                       "output": "BCOO data with duplicates + residual",
+                       "sample_note": f"CPU leg timed on a bounded {n_side}^3-element sample of the same mesh family"},
             "cpu_baseline": {"value": value, "unit": "elements/s", "cores": threads, "kind": "port", "sample": sample,
-                             "note": "restated reference arithmetic (NumPy oracle), not the JAX path: JAX is not "
-                                     "installable in this image"},
+                             "note": "restated reference arithmetic (plain C + OpenMP, oracle/c/hex_mech.c), not the JAX "
+                                     "path: JAX is not installable in this image"},
             "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -337,10 +316,10 @@ def run_ours(args):
         del ke
         torch.cuda.empty_cache()
         threads = os.cpu_count() or 1
-        rate, done, dt = cpu_assembly_rate(24, 10.0, threads)
+        rate, done, dt = cpu_assembly_rate(64, 10.0, threads)
         line["cpu_baseline"] = {"value": rate, "unit": "elements/s", "cores": threads, "kind": "port",
-                                "sample": f"24^3-element hex box passes for {dt:.1f} s ({done} elements), NumPy "
-                                          "oracle (restated reference arithmetic, not the JAX path)"}
+                                "sample": f"64^3-element hex box passes for {dt:.1f} s ({done} elements), C/OpenMP "
+                                          "restatement of the reference arithmetic (oracle/c), not the JAX path"}
     if not args.no_extras:
         try:
             sec = fol_loss_grad_bench(torch, dist, rank, world, max(3, min(args.steps, 10)), 3)

@@ -1,0 +1,139 @@
+// XLA typed-FFI handlers over the C ABI of libfolax_b200 -- the jax.ffi side of the drop-in boundary.
+//
+// Binding style mirrors the reference's only FFI precedent,
+//   fol/loss_functions/ffi_functions/kr_small_displacement_element.cc:293-337
+// (Ffi::Bind().Ctx<PlatformStream<cudaStream_t>>().Arg<AnyBuffer>()...Ret<AnyBuffer>(), F32/F64
+// dispatch on the buffer element type :49-57, S32 connectivity :102, 320), but instead of copying
+// to the host and looping over CPU elements the handlers enqueue the sm_100a kernels on XLA's
+// stream and return immediately (no synchronisation, no retained state).
+//
+// JAX / jaxlib (and therefore xla/ffi/api/ffi.h) are NOT available in this build image, so this
+// translation unit is compiled only where the header exists (see INTEGRATION.md for the build line
+// and the Python registration stub).  It is untested here and says so.
+#if defined(__has_include)
+#if __has_include("xla/ffi/api/ffi.h")
+#define FOLAX_HAVE_XLA_FFI 1
+#endif
+#endif
+
+#ifdef FOLAX_HAVE_XLA_FFI
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "../../include/folax_b200.h"
+#include "xla/ffi/api/ffi.h"
+
+namespace ffi = xla::ffi;
+
+namespace {
+
+ffi::Error FromRc(int rc) {
+  if (rc == FOL_OK) return ffi::Error::Success();
+  if (rc == FOL_ERR_INVALID) return ffi::Error::InvalidArgument(fol_last_error());
+  return ffi::Error::Internal(fol_last_error());
+}
+
+int DtypeOf(ffi::DataType t) { return t == ffi::F64 ? FOL_F64 : (t == ffi::F32 ? FOL_F32 : -1); }
+
+// compute_elements: (coords (nn,3), conn (ne,a) S32, ctrl (nn), u (ndof), dir_flag (ndof) U8, params (12) F64 host
+// attribute) -> ke_data (ne*nd*nd), re_elem (ne*nd).   Replaces compute_elements of ...cc:226-291.
+ffi::Error AssembleElementsImpl(cudaStream_t stream, ffi::AnyBuffer xyz, ffi::Buffer<ffi::S32> conn,
+                                ffi::AnyBuffer ctrl, ffi::AnyBuffer u, ffi::Buffer<ffi::U8> dir_flag,
+                                ffi::Result<ffi::AnyBuffer> ke, ffi::Result<ffi::AnyBuffer> re, int32_t physics,
+                                int32_t element, int32_t num_gp, int32_t transpose,
+                                ffi::Span<const double> params) {
+  const int dt = DtypeOf(xyz.element_type());
+  if (dt < 0) return ffi::Error::InvalidArgument("Unsupported data type for FFI call.");
+  if (params.size() != FOL_NUM_PARAMS) return ffi::Error::InvalidArgument("params must have 12 entries");
+  const auto cd = conn.dimensions();
+  const int64_t ne = cd[0], nn = xyz.dimensions()[0];
+  return FromRc(fol_assemble_elements(stream, dt, physics, element, num_gp, transpose, ne, nn, xyz.untyped_data(),
+                                      conn.typed_data(), ctrl.untyped_data(), u.untyped_data(),
+                                      dir_flag.typed_data(), params.begin(), ke->untyped_data(), re->untyped_data(),
+                                      nullptr, nullptr));
+}
+
+// residual_gather: (adj_ptr, adj, re_elem) -> residual (ndof).  Replaces the scatter-add of fe_loss.py:301-306.
+ffi::Error ResidualGatherImpl(cudaStream_t stream, ffi::Buffer<ffi::S32> adj_ptr, ffi::Buffer<ffi::S32> adj,
+                              ffi::AnyBuffer re, ffi::Result<ffi::AnyBuffer> residual, int32_t nnode,
+                              int32_t dofs_per_node) {
+  const int dt = DtypeOf(re.element_type());
+  if (dt < 0) return ffi::Error::InvalidArgument("Unsupported data type for FFI call.");
+  const int64_t nn = adj_ptr.dimensions()[0] - 1;
+  return FromRc(fol_residual_gather(stream, dt, nn, nnode, dofs_per_node, adj_ptr.typed_data(), adj.typed_data(),
+                                    re.untyped_data(), residual->untyped_data()));
+}
+
+// energy_and_grads: the forward of the custom_vjp'd batched loss (fe_loss.py:250-262).
+ffi::Error EnergyAndGradsImpl(cudaStream_t stream, ffi::AnyBuffer geom, ffi::Buffer<ffi::S32> conn,
+                              ffi::Buffer<ffi::S32> adj_ptr, ffi::Buffer<ffi::S32> adj_local,
+                              ffi::Buffer<ffi::S32> tile_node_ptr, ffi::Buffer<ffi::S32> tile_nodes,
+                              ffi::Buffer<ffi::S32> tile_elem_ptr, ffi::Buffer<ffi::S32> tile_elems,
+                              ffi::AnyBuffer ctrl, ffi::AnyBuffer u, ffi::Result<ffi::AnyBuffer> grad_u,
+                              ffi::Result<ffi::AnyBuffer> grad_k, ffi::Result<ffi::AnyBuffer> energy,
+                              ffi::Result<ffi::AnyBuffer> work, int32_t physics, int32_t element, int32_t num_gp,
+                              int64_t ecap, ffi::Span<const double> params) {
+  const int dt = DtypeOf(u.element_type());
+  if (dt < 0) return ffi::Error::InvalidArgument("Unsupported data type for FFI call.");
+  const int64_t ne = conn.dimensions()[0], nb = u.dimensions()[0], nn = ctrl.dimensions()[1];
+  const int64_t ntiles = tile_node_ptr.dimensions()[0] - 1;
+  return FromRc(fol_energy_and_grads(stream, dt, physics, element, num_gp, ne, nn, nb, geom.untyped_data(),
+                                     conn.typed_data(), adj_ptr.typed_data(), adj_local.typed_data(),
+                                     tile_node_ptr.typed_data(), tile_nodes.typed_data(), tile_elem_ptr.typed_data(),
+                                     tile_elems.typed_data(), ntiles, ecap, ctrl.untyped_data(), u.untyped_data(),
+                                     params.begin(), grad_u->untyped_data(), grad_k->untyped_data(),
+                                     energy->untyped_data(), work->untyped_data()));
+}
+
+}  // namespace
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FolAssembleElements, AssembleElementsImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()          // xyz
+                                  .Arg<ffi::Buffer<ffi::S32>>()   // conn
+                                  .Arg<ffi::AnyBuffer>()          // ctrl
+                                  .Arg<ffi::AnyBuffer>()          // u
+                                  .Arg<ffi::Buffer<ffi::U8>>()    // dir_flag
+                                  .Ret<ffi::AnyBuffer>()          // ke_data
+                                  .Ret<ffi::AnyBuffer>()          // re_elem
+                                  .Attr<int32_t>("physics")
+                                  .Attr<int32_t>("element")
+                                  .Attr<int32_t>("num_gp")
+                                  .Attr<int32_t>("transpose")
+                                  .Attr<ffi::Span<const double>>("params"));
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FolResidualGather, ResidualGatherImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Attr<int32_t>("nnode")
+                                  .Attr<int32_t>("dofs_per_node"));
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FolEnergyAndGrads, EnergyAndGradsImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Attr<int32_t>("physics")
+                                  .Attr<int32_t>("element")
+                                  .Attr<int32_t>("num_gp")
+                                  .Attr<int64_t>("ecap")
+                                  .Attr<ffi::Span<const double>>("params"));
+#endif  // FOLAX_HAVE_XLA_FFI

@@ -1,0 +1,44 @@
+"""Oracle (test infrastructure): ctypes loader of the plain-C / OpenMP restatement in oracle/c
+(Hex8 elasticity assembly).  Used as the CPU baseline of bench.py and cross-checked against the NumPy
+oracle in tests/test_oracle_c.py.  Never imported by the product."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "_build", "liboracle_hex.so")
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", os.path.join(_HERE, "c")], check=True)
+    return LIB
+
+
+def load():
+    if not os.path.exists(LIB):
+        build()
+    lib = ctypes.CDLL(LIB)
+    lib.oracle_hex_mech_assemble.restype = None
+    lib.oracle_hex_mech_assemble.argtypes = [ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 5 + \
+        [ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    return lib
+
+
+def hex_mech_assemble(coords, conn, ctrl, u, dirichlet_indices, E, nu, body=None, transpose=False, out=None):
+    lib = load()
+    coords = np.ascontiguousarray(coords, np.float64)
+    conn = np.ascontiguousarray(conn, np.int32)
+    ctrl = np.ascontiguousarray(ctrl, np.float64)
+    u = np.ascontiguousarray(u, np.float64)
+    nn, ne = len(coords), len(conn)
+    flags = np.zeros(3 * nn, np.uint8)
+    flags[np.asarray(dirichlet_indices, np.int64)] = 1
+    body = np.zeros(3) if body is None else np.ascontiguousarray(body, np.float64)
+    data = np.empty(ne * 576) if out is None else out
+    R = np.empty(3 * nn)
+    lib.oracle_hex_mech_assemble(ne, nn, coords.ctypes.data, conn.ctypes.data, ctrl.ctypes.data, u.ctypes.data,
+                                 flags.ctypes.data, float(E), float(nu), body.ctypes.data, int(transpose),
+                                 data.ctypes.data, R.ctypes.data)
+    return data, R
