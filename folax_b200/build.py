@@ -27,7 +27,7 @@ def _sources():
 
 
 def _stamp():
-    h = hashlib.sha256(" ".join(FLAGS).encode())
+    h = hashlib.sha256((" ".join(FLAGS) + repr(EXTRA)).encode())
     for f in sorted(os.listdir(CSRC)):
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(f.encode() + fh.read())
@@ -36,9 +36,13 @@ def _stamp():
     return h.hexdigest()
 
 
+# per-file extras (register caps of the tuned kernels)
+EXTRA = {"assemble_hex.cu": ["-maxrregcount=144"]}
+
+
 def _compile(src, verbose):
     obj = os.path.join(OBJDIR, src[:-3] + ".o")
-    cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [NVCC] + FLAGS + EXTRA.get(src, []) + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     with open(obj + ".log", "w") as fh:
         fh.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)

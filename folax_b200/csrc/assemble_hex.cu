@@ -21,7 +21,7 @@ namespace fol {
 
 namespace {
 
-constexpr int kWarps = 7;            // warps per CTA, each fully independent (2 CTAs = 14 warps / SM)
+constexpr int kWarps = 6;            // warps per CTA, each fully independent (2 CTAs = 12 warps / SM)
 constexpr int kTile = 4;             // elements per warp iteration
 constexpr int kRow = 9;              // 8 nodes + 1 pad (16-byte units) -> conflict-free staging
 
@@ -29,9 +29,9 @@ struct __align__(128) WarpSmem {
   double stage[576];                 // Ke staging slot (bulk-copy source)
   double2 gxy[kTile][8][kRow];       // [element][gauss][node] (dN/dx, dN/dy)
   double2 gzs[kTile][8][kRow];       // (dN/dz, w detJ E_g)
-  double X[kTile][25];               // nodal coordinates, padded rows
-  double u[kTile][25];               // element dofs
-  double de[kTile][9];               // nodal control values
+  double X[2][kTile][25];            // nodal coordinates, padded rows; double-buffered (cp.async target)
+  double u[2][kTile][25];            // element dofs
+  double de[2][kTile][9];            // nodal control values
   double wd[kTile][8];               // w detJ per Gauss point (body force)
   float bc[kTile][24];               // 1 = free dof, 0 = Dirichlet dof
 };
@@ -54,26 +54,16 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-struct NodeData {
-  double x[3], u[3], de;
-  float bc[3];
-};
-
-__device__ __forceinline__ NodeData load_node(const AsmArgs<double>& a, long long n) {
-  NodeData d;
-  const double* px = a.xyz + n * 3;
-  const double* pu = a.u + n * 3;
-  d.x[0] = __ldg(px); d.x[1] = __ldg(px + 1); d.x[2] = __ldg(px + 2);
-  d.u[0] = __ldg(pu); d.u[1] = __ldg(pu + 1); d.u[2] = __ldg(pu + 2);
-  d.de = __ldg(a.ctrl + n);
-  const uint8_t* pf = a.dir + n * 3;
-  d.bc[0] = __ldg(pf) ? 0.f : 1.f; d.bc[1] = __ldg(pf + 1) ? 0.f : 1.f; d.bc[2] = __ldg(pf + 2) ? 0.f : 1.f;
-  return d;
+__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
+  const unsigned saddr = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 }  // namespace
 
-__global__ void __launch_bounds__(kWarps * 32, 2)
+__global__ void __launch_bounds__(kWarps * 32)
 assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles, const int has_body) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -110,24 +100,46 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
     const long long e = t * kTile + el_p;
     return (t < ntiles && e < args.ne) ? (long long)__ldg(args.conn + e * 8 + sub) : 0;
   };
+  // asynchronous gather of one node straight into shared memory (no registers held across the tile)
+  auto gather_async = [&](int buf, long long n) {
+    const double* px = args.xyz + n * 3;
+    const double* pu = args.u + n * 3;
+    double* sx = &sm.X[buf][el_p][sub * 3];
+    double* su = &sm.u[buf][el_p][sub * 3];
+    cp_async8(sx, px); cp_async8(sx + 1, px + 1); cp_async8(sx + 2, px + 2);
+    cp_async8(su, pu); cp_async8(su + 1, pu + 1); cp_async8(su + 2, pu + 2);
+    cp_async8(&sm.de[buf][el_p][sub], args.ctrl + n);
+    cp_async_commit();
+  };
+  auto load_flags = [&](long long n) -> unsigned {   // three Dirichlet flags packed into one register
+    const uint8_t* pf = args.dir + n * 3;
+    return (unsigned)__ldg(pf) | ((unsigned)__ldg(pf + 1) << 8) | ((unsigned)__ldg(pf + 2) << 16);
+  };
   long long n_next = node_of(tile + nwarps);
-  NodeData pre = load_node(args, node_of(tile));
+  {
+    const long long n_cur = node_of(tile);
+    gather_async(0, n_cur);
+    sm.bc[el_p][sub * 3 + 0] = 0.f;  // overwritten below; keeps the first publish uniform
+  }
+  unsigned flags = load_flags(node_of(tile));
+  int buf = 0;
 
-  for (; tile < ntiles; tile += nwarps) {
+  for (; tile < ntiles; tile += nwarps, buf ^= 1) {
     const long long e0 = tile * kTile;
 
-    // ---- phase 0: lane (element, node) publishes its node, then prefetches the next tile's
-    sm.X[el_p][sub * 3 + 0] = pre.x[0]; sm.X[el_p][sub * 3 + 1] = pre.x[1]; sm.X[el_p][sub * 3 + 2] = pre.x[2];
-    sm.u[el_p][sub * 3 + 0] = pre.u[0]; sm.u[el_p][sub * 3 + 1] = pre.u[1]; sm.u[el_p][sub * 3 + 2] = pre.u[2];
-    sm.de[el_p][sub] = pre.de;
-    sm.bc[el_p][sub * 3 + 0] = pre.bc[0]; sm.bc[el_p][sub * 3 + 1] = pre.bc[1]; sm.bc[el_p][sub * 3 + 2] = pre.bc[2];
+    // ---- phase 0: this tile's nodal data has landed in shared memory; start the next gather
+    sm.bc[el_p][sub * 3 + 0] = (flags & 0xffu) ? 0.f : 1.f;
+    sm.bc[el_p][sub * 3 + 1] = (flags & 0xff00u) ? 0.f : 1.f;
+    sm.bc[el_p][sub * 3 + 2] = (flags & 0xff0000u) ? 0.f : 1.f;
+    cp_async_wait_all();
     __syncwarp();
-    pre = load_node(args, n_next);                          // in flight during this tile
+    gather_async(buf ^ 1, n_next);                          // in flight during this tile
+    flags = load_flags(n_next);
     n_next = node_of(tile + 2 * nwarps);
 
     // ---- phase 1: lane (element, Gauss point): J, det J, grad N, coefficient (geometry.py:88-97)
     {
-      const double* X = sm.X[el_p];
+      const double* X = sm.X[buf][el_p];
       double J[3][3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -159,7 +171,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
 #pragma unroll
       for (int a = 0; a < 8; ++a) {
         const int bx = ((a & 3) == 1 || (a & 3) == 2), by = (a >> 1) & 1, bz = (a >> 2) & 1;
-        eg += fx[bx] * fyz[by][bz] * sm.de[el_p][a];
+        eg += fx[bx] * fyz[by][bz] * sm.de[buf][el_p][a];
       }
       const double wd = det;  // Gauss weight is 1
       const double coef = wd * eg;
@@ -212,25 +224,39 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
           for (int j = 0; j < 3; ++j)
             K[h][i][j] = lam * c[i][j][h] + mu * c[j][i][h] + (i == j ? mu * tr : 0.0);
       }
-      // stage the masked rows (fe_loss.py:191-207) and hand them to the bulk-copy engine
+      // stage the rows and hand them to the bulk-copy engine.  The Dirichlet row mask
+      // (fe_loss.py:191-207) only matters for elements touching a fixed dof: warp-uniform test.
+      const bool fixed_rows = (sm.bc[el][ra * 3 + 0] == 0.f) | (sm.bc[el][ra * 3 + 1] == 0.f) |
+                              (sm.bc[el][ra * 3 + 2] == 0.f);
+      const bool any_fixed = __any_sync(0xffffffffu, fixed_rows);
       if (lane == 0) bulk_wait_read<0>();   // the previous element's copy has drained the slot
       __syncwarp();
+      if (!any_fixed) {
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int row = ra * 3 + i;
-        const bool freerow = sm.bc[el][row] != 0.f;
-        double v[6];
+        for (int i = 0; i < 3; ++i) {
+          double2* dst = reinterpret_cast<double2*>(sm.stage + (ra * 3 + i) * 24 + kq * 6);
+          dst[0] = make_double2(K[0][i][0], K[0][i][1]);
+          dst[1] = make_double2(K[0][i][2], K[1][i][0]);
+          dst[2] = make_double2(K[1][i][1], K[1][i][2]);
+        }
+      } else {
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int i = 0; i < 3; ++i) {
+          const int row = ra * 3 + i;
+          const bool freerow = sm.bc[el][row] != 0.f;
+          double v[6];
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const int col = (2 * kq + h) * 3 + j;
-            v[h * 3 + j] = (freerow || col == row) ? K[h][i][j] : 0.0;
-          }
-        double2* dst = reinterpret_cast<double2*>(sm.stage + row * 24 + kq * 6);
-        dst[0] = make_double2(v[0], v[1]);
-        dst[1] = make_double2(v[2], v[3]);
-        dst[2] = make_double2(v[4], v[5]);
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const int col = (2 * kq + h) * 3 + j;
+              v[h * 3 + j] = (freerow || col == row) ? K[h][i][j] : 0.0;
+            }
+          double2* dst = reinterpret_cast<double2*>(sm.stage + row * 24 + kq * 6);
+          dst[0] = make_double2(v[0], v[1]);
+          dst[1] = make_double2(v[2], v[3]);
+          dst[2] = make_double2(v[4], v[5]);
+        }
       }
       fence_async_smem();
       __syncwarp();
@@ -244,7 +270,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) acc += K[h][i][j] * sm.u[el][(2 * kq + h) * 3 + j];
+          for (int j = 0; j < 3; ++j) acc += K[h][i][j] * sm.u[buf][el][(2 * kq + h) * 3 + j];
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         r[i] = acc;
@@ -262,7 +288,8 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
       }
       if (kq == 0) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) args.re[e * 24 + ra * 3 + i] = (double)sm.bc[el][ra * 3 + i] * r[i];
+        for (int i = 0; i < 3; ++i)
+          args.re[e * 24 + ra * 3 + i] = (any_fixed && sm.bc[el][ra * 3 + i] == 0.f) ? 0.0 : r[i];
       }
     }
     __syncwarp();  // everyone is done with X / u / gradients of this tile
