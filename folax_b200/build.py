@@ -40,14 +40,58 @@ def _stamp():
 EXTRA = {"assemble_hex.cu": ["-maxrregcount=144"]}
 
 
-def _compile(src, verbose):
+def _headers_hash():
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith((".cuh", ".h")):
+            with open(os.path.join(CSRC, f), "rb") as fh:
+                h.update(f.encode() + fh.read())
+    with open(os.path.join(HERE, "..", "include", "folax_b200.h"), "rb") as fh:
+        h.update(fh.read())
+    return h.hexdigest()
+
+
+def _includes(src):
+    """Headers a source file includes (transitively, by name) -- recompile only when they change."""
+    seen, todo = set(), [src]
+    while todo:
+        f = todo.pop()
+        path = os.path.join(CSRC, f)
+        if not os.path.exists(path):
+            continue
+        for line in open(path):
+            line = line.strip()
+            if line.startswith('#include "'):
+                name = os.path.basename(line.split('"')[1])
+                if name not in seen:
+                    seen.add(name)
+                    todo.append(name)
+    return sorted(seen)
+
+
+def _file_stamp(src):
+    h = hashlib.sha256((" ".join(FLAGS) + repr(EXTRA.get(src, []))).encode())
+    for f in [src] + _includes(src):
+        path = os.path.join(CSRC, f) if f != "folax_b200.h" else os.path.join(HERE, "..", "include", f)
+        if os.path.exists(path):
+            with open(path, "rb") as fh:
+                h.update(f.encode() + fh.read())
+    return h.hexdigest()
+
+
+def _compile(src, verbose, force=False):
     obj = os.path.join(OBJDIR, src[:-3] + ".o")
+    stamp_file, stamp = obj + ".stamp", _file_stamp(src)
+    if not force and os.path.exists(obj) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return obj
     cmd = [NVCC] + FLAGS + EXTRA.get(src, []) + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     with open(obj + ".log", "w") as fh:
         fh.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+    with open(stamp_file, "w") as fh:
+        fh.write(stamp)
     if verbose:
         print(r.stderr)
     return obj
@@ -62,7 +106,7 @@ def build(force=False, verbose=False):
         return LIB
     srcs = _sources()
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = list(ex.map(lambda s: _compile(s, verbose), srcs))
+        objs = list(ex.map(lambda s: _compile(s, verbose, force), srcs))
     cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
