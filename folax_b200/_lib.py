@@ -62,8 +62,12 @@ def load():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise FolaxError(f"{LIB_PATH} is missing: run `python -m folax_b200.build` (nvcc, sm_100a). "
-                             "folax_b200 has no CPU fallback.")
+            try:   # build in-tree on first use (nvcc cross-compiles sm_100a without a GPU)
+                from . import build as _build
+                _build.build()
+            except Exception as ex:
+                raise FolaxError(f"{LIB_PATH} is missing and could not be built ({ex}); run "
+                                 "`python -m folax_b200.build` (nvcc, sm_100a). folax_b200 has no CPU fallback.")
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)

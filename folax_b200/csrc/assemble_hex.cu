@@ -23,15 +23,19 @@ namespace {
 
 constexpr int kWarps = 6;            // warps per CTA, each fully independent (2 CTAs = 12 warps / SM)
 constexpr int kTile = 4;             // elements per warp iteration
-constexpr int kRow = 9;              // 8 nodes + 1 pad (16-byte units) -> conflict-free staging
 
 struct __align__(128) WarpSmem {
   double stage[576];                 // Ke staging slot (bulk-copy source)
-  double2 gxy[kTile][8][kRow];       // [element][gauss][node] (dN/dx, dN/dy)
-  double2 gzs[kTile][8][kRow];       // (dN/dz, w detJ E_g)
-  double X[2][kTile][25];            // nodal coordinates, padded rows; double-buffered (cp.async target)
-  double u[2][kTile][25];            // element dofs
-  double de[2][kTile][9];            // nodal control values
+  // [element][gauss][node ^ swz(gauss)]: (dN/dx, dN/dy) and (dN/dz, w detJ E_g).  The XOR swizzle
+  // swz(g) = ((g & 3) << 1) | (g >> 2) makes both the phase-1 stores (lane = row) and the DMMA
+  // fragment loads (lane = (node, gauss mod 4)) bank-conflict free without padding.
+  double2 gxy[kTile][8][8];
+  double2 gzs[kTile][8][8];
+  // nodal data of the tile, SoA over the 32 (element, node) lanes: conflict-free cp.async targets;
+  // double-buffered (the next tile lands while this one computes)
+  double X[2][3][32];
+  double u[2][3][32];
+  double de[2][32];
   double wd[kTile][8];               // w detJ per Gauss point (body force)
   float bc[kTile][24];               // 1 = free dof, 0 = Dirichlet dof
 };
@@ -79,6 +83,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
   // lane roles
   const int el_p = lane >> 3, sub = lane & 7;   // phases 0/1: (element in tile, node | gauss point)
   const int ra = lane >> 2, kq = lane & 3;      // phase 2: (row node a, column pair k)
+  const int swz_p = ((sub & 3) << 1) | (sub >> 2);
 
   // Gauss point `sub` of the 2x2x2 rule (hexahedra_3d_8.py:23-33): xi = sgn(sub) / sqrt(3), w = 1.
   // Trilinear shape data factorised per axis: f?[0] = 1 - xi_?, f?[1] = 1 + xi_? and the pair
@@ -104,42 +109,37 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
   auto gather_async = [&](int buf, long long n) {
     const double* px = args.xyz + n * 3;
     const double* pu = args.u + n * 3;
-    double* sx = &sm.X[buf][el_p][sub * 3];
-    double* su = &sm.u[buf][el_p][sub * 3];
-    cp_async8(sx, px); cp_async8(sx + 1, px + 1); cp_async8(sx + 2, px + 2);
-    cp_async8(su, pu); cp_async8(su + 1, pu + 1); cp_async8(su + 2, pu + 2);
-    cp_async8(&sm.de[buf][el_p][sub], args.ctrl + n);
+    cp_async8(&sm.X[buf][0][lane], px); cp_async8(&sm.X[buf][1][lane], px + 1); cp_async8(&sm.X[buf][2][lane], px + 2);
+    cp_async8(&sm.u[buf][0][lane], pu); cp_async8(&sm.u[buf][1][lane], pu + 1); cp_async8(&sm.u[buf][2][lane], pu + 2);
+    cp_async8(&sm.de[buf][lane], args.ctrl + n);
     cp_async_commit();
   };
-  auto load_flags = [&](long long n) -> unsigned {   // three Dirichlet flags packed into one register
-    const uint8_t* pf = args.dir + n * 3;
-    return (unsigned)__ldg(pf) | ((unsigned)__ldg(pf + 1) << 8) | ((unsigned)__ldg(pf + 2) << 16);
-  };
+  // Dirichlet flags of the next tile's node: three byte loads kept in three registers, consumed one
+  // tile later (packing them right away would stall on the load latency)
   long long n_next = node_of(tile + nwarps);
-  {
-    const long long n_cur = node_of(tile);
-    gather_async(0, n_cur);
-    sm.bc[el_p][sub * 3 + 0] = 0.f;  // overwritten below; keeps the first publish uniform
-  }
-  unsigned flags = load_flags(node_of(tile));
+  gather_async(0, node_of(tile));
+  const uint8_t* pf0 = args.dir + node_of(tile) * 3;
+  unsigned f0 = __ldg(pf0), f1 = __ldg(pf0 + 1), f2 = __ldg(pf0 + 2);
   int buf = 0;
 
   for (; tile < ntiles; tile += nwarps, buf ^= 1) {
     const long long e0 = tile * kTile;
 
     // ---- phase 0: this tile's nodal data has landed in shared memory; start the next gather
-    sm.bc[el_p][sub * 3 + 0] = (flags & 0xffu) ? 0.f : 1.f;
-    sm.bc[el_p][sub * 3 + 1] = (flags & 0xff00u) ? 0.f : 1.f;
-    sm.bc[el_p][sub * 3 + 2] = (flags & 0xff0000u) ? 0.f : 1.f;
+    sm.bc[el_p][sub * 3 + 0] = f0 ? 0.f : 1.f;
+    sm.bc[el_p][sub * 3 + 1] = f1 ? 0.f : 1.f;
+    sm.bc[el_p][sub * 3 + 2] = f2 ? 0.f : 1.f;
     cp_async_wait_all();
     __syncwarp();
     gather_async(buf ^ 1, n_next);                          // in flight during this tile
-    flags = load_flags(n_next);
+    {
+      const uint8_t* pf = args.dir + n_next * 3;
+      f0 = __ldg(pf); f1 = __ldg(pf + 1); f2 = __ldg(pf + 2);
+    }
     n_next = node_of(tile + 2 * nwarps);
 
     // ---- phase 1: lane (element, Gauss point): J, det J, grad N, coefficient (geometry.py:88-97)
     {
-      const double* X = sm.X[buf][el_p];
       double J[3][3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -147,7 +147,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
           const int bx = ((a & 3) == 1 || (a & 3) == 2), by = (a >> 1) & 1, bz = (a >> 2) & 1;
-          const double x = X[a * 3 + i];
+          const double x = sm.X[buf][i][el_p * 8 + a];
           j0 += (bx ? x : -x) * fyz[by][bz];
           j1 += (by ? x : -x) * fxz[bx][bz];
           j2 += (bz ? x : -x) * fxy[bx][by];
@@ -171,7 +171,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
 #pragma unroll
       for (int a = 0; a < 8; ++a) {
         const int bx = ((a & 3) == 1 || (a & 3) == 2), by = (a >> 1) & 1, bz = (a >> 2) & 1;
-        eg += fx[bx] * fyz[by][bz] * sm.de[buf][el_p][a];
+        eg += fx[bx] * fyz[by][bz] * sm.de[buf][el_p * 8 + a];
       }
       const double wd = det;  // Gauss weight is 1
       const double coef = wd * eg;
@@ -184,8 +184,8 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
         double g[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) g[k] = d0 * inv[0][k] + d1 * inv[1][k] + d2 * inv[2][k];
-        sm.gxy[el_p][sub][a] = make_double2(g[0], g[1]);
-        sm.gzs[el_p][sub][a] = make_double2(g[2], coef);
+        sm.gxy[el_p][sub][a ^ swz_p] = make_double2(g[0], g[1]);
+        sm.gzs[el_p][sub][a ^ swz_p] = make_double2(g[2], coef);
       }
       sm.wd[el_p][sub] = wd;
     }
@@ -204,8 +204,8 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
         for (int s = 0; s < 3; ++s) c[t][s][0] = c[t][s][1] = 0.0;
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
-        const double2 xy = sm.gxy[el][4 * kk + kq][ra];
-        const double2 zs = sm.gzs[el][4 * kk + kq][ra];
+        const double2 xy = sm.gxy[el][4 * kk + kq][ra ^ ((kq << 1) | kk)];
+        const double2 zs = sm.gzs[el][4 * kk + kq][ra ^ ((kq << 1) | kk)];
         const double bf[3] = {xy.x, xy.y, zs.x};
         const double af[3] = {zs.y * xy.x, zs.y * xy.y, zs.y * zs.x};
 #pragma unroll
@@ -270,7 +270,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) acc += K[h][i][j] * sm.u[buf][el][(2 * kq + h) * 3 + j];
+          for (int j = 0; j < 3; ++j) acc += K[h][i][j] * sm.u[buf][j][el * 8 + 2 * kq + h];
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         r[i] = acc;
