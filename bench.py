@@ -270,7 +270,9 @@ def run_ours(args):
             return assemble_overlapped(loss, part, K, u, ke, comm_stream)
         return loss._assemble(K, u, False, ke_out=ke)
 
-    for _ in range(args.warmup):
+    # multi-GPU: NCCL's first send/recv rounds (connection set-up, proxy warm-up) take tens of iterations to
+    # reach steady state, so the W requested warm-up steps are preceded by extra untimed ones
+    for _ in range(args.warmup + (40 if world > 1 else 0)):
         step()
     torch.cuda.synchronize()
     if world > 1:

@@ -25,6 +25,7 @@ SIGNATURES = {
     "fol_version": (_int, []),
     "fol_launch_count": (_i64, []),
     "fol_set_tuned_kernels": (_int, [_int]),
+    "fol_set_grid_margin": (_int, [_int]),
     "fol_element_info": (_int, [_int, _int, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
     "fol_dofs_per_node": (_int, [_int, _int]),
     "fol_bcoo_indices": (_int, [_vp, _i32p, _i64, _int, _int, _i32p]),

@@ -14,6 +14,7 @@ int assemble_neohooke_f32(cudaStream_t, int, int, const AsmArgs<float>&);
 int assemble_j2_f64(cudaStream_t, int, int, const AsmArgs<double>&);
 int assemble_j2_f32(cudaStream_t, int, int, const AsmArgs<float>&);
 int assemble_hex_mech_f64(cudaStream_t, const AsmArgs<double>&);
+extern std::atomic<int> g_grid_margin;
 
 template <class T>
 int energy_and_grads(cudaStream_t, int, int, int, const EnergyArgs<T>&, T*);
@@ -98,6 +99,8 @@ int fol_element_info(int element, int num_gp, int* nnode, int* dim, int* ngauss)
 int fol_set_tuned_kernels(int enable) {
   return g_tuned.exchange(enable ? 1 : 0);
 }
+
+int fol_set_grid_margin(int ctas) { return g_grid_margin.exchange(ctas < 0 ? 0 : ctas); }
 
 int fol_dofs_per_node(int physics, int element) {
   if (!valid_element(element)) return FOL_ERR_INVALID;

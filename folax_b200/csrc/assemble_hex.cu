@@ -297,6 +297,8 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
   if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last copies
 }
 
+std::atomic<int> g_grid_margin{0};
+
 int assemble_hex_mech_f64(cudaStream_t s, const AsmArgs<double>& args) {
   static int grid = 0;
   const size_t smem = sizeof(WarpSmem) * kWarps;
@@ -313,7 +315,10 @@ int assemble_hex_mech_f64(cudaStream_t s, const AsmArgs<double>& args) {
   const long long ntiles = cdiv(args.ne, kTile);
   const long long want = cdiv(ntiles, kWarps);
   const int has_body = (args.p.v[2] != 0.0 || args.p.v[3] != 0.0 || args.p.v[4] != 0.0) ? 1 : 0;
-  assemble_hex_mech_f64_kernel<<<(unsigned)(want < grid ? want : grid), kWarps * 32, smem, s>>>(args, ntiles, has_body);
+  // persistent grid, optionally leaving room for communication kernels that must run concurrently
+  int g = grid - g_grid_margin.load();
+  if (g < 1) g = 1;
+  assemble_hex_mech_f64_kernel<<<(unsigned)(want < g ? want : g), kWarps * 32, smem, s>>>(args, ntiles, has_body);
   return check_launch("assemble_hex_mech_f64_kernel");
 }
 

@@ -78,6 +78,9 @@ class SlabPartition:
         return residual
 
 
+GRID_MARGIN_CTAS = 0   # measured on 2/4/8 B200: a margin does not pay; NCCL's kernels fit next to the persistent CTAs
+
+
 def assemble_overlapped(loss, part, controls, dofs, ke_out, comm_stream, group=None):
     """Residual + Jacobian of one slab with the halo-DOF exchange hidden behind the element stage.
 
@@ -136,7 +139,13 @@ def assemble_overlapped(loss, part, controls, dofs, ke_out, comm_stream, group=N
         part.halo_sum(R, d, group)
         done = torch.cuda.Event()
         done.record()
-    elements(layer, ne - 2 * layer)
+    # the interior element stage is a persistent kernel: leave a few thread blocks' worth of SM resources
+    # free so the NCCL send/recv kernels of the side stream are scheduled next to it, not after it
+    prev = lib.fol_set_grid_margin(GRID_MARGIN_CTAS)
+    try:
+        elements(layer, ne - 2 * layer)
+    finally:
+        lib.fol_set_grid_margin(prev)
     gather(plane, nn - 2 * plane)
     torch.cuda.current_stream().wait_event(done)
     return ke_out, R

@@ -56,6 +56,11 @@ int64_t fol_launch_count(void);
  * generic kernel (A/B parity checks).  Returns the previous setting. */
 int fol_set_tuned_kernels(int enable);
 
+/* Persistent kernels normally fill every SM.  A margin of `ctas` thread blocks leaves room for
+ * communication kernels (NCCL send/recv of the halo-DOF exchange) that must run concurrently.
+ * Returns the previous setting. */
+int fol_set_grid_margin(int ctas);
+
 /* element table: nodes per element, spatial dim, Gauss points of integration order num_gp */
 int fol_element_info(int element, int num_gp, int* nnode, int* dim, int* ngauss);
 /* dofs per node of a physics on an element (1 for thermal, dim otherwise) */
