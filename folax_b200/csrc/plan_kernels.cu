@@ -193,3 +193,46 @@ int fol_apply_dirichlet(fol_stream_t s, int dtype, int64_t nb, int64_t ndof, con
 }
 
 }  // extern "C"
+
+// ---- duplicate-free CSR values from the BCOO data (hand-off to fol/solvers: fe_solver.py:71-72, 82) ----
+// One thread per (node pair, i, j): fixed-order sum of the contributing element entries (ascending
+// e*A*A + a*A + b), so the CSR values are deterministic.  The integer plan (pair_ptr, contrib,
+// out_base, row_stride) is built once per mesh by folax_b200/csr_plan.py.
+namespace fol {
+template <class T>
+__global__ void csr_values_kernel(long long npairs, int d, int A, const int32_t* __restrict__ pair_ptr,
+                                  const int32_t* __restrict__ contrib, const int32_t* __restrict__ out_base,
+                                  const int32_t* __restrict__ row_stride, const T* __restrict__ data,
+                                  T* __restrict__ vals) {
+  const int dd = d * d, nd = A * d;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npairs * dd) return;
+  const long long p = t / dd;
+  const int ij = (int)(t - p * dd), i = ij / d, j = ij - i * d;
+  T acc = (T)0;
+  const int lo = __ldg(pair_ptr + p), hi = __ldg(pair_ptr + p + 1);
+  for (int k = lo; k < hi; ++k) {
+    const int c = __ldg(contrib + k);
+    const long long e = c / (A * A);
+    const int ab = c - (int)e * (A * A), a = ab / A, b = ab - a * A;
+    acc += __ldg(data + e * (long long)(nd * nd) + (a * d + i) * nd + (b * d + j));
+  }
+  vals[(long long)__ldg(out_base + p) + (long long)i * __ldg(row_stride + p) + j] = acc;
+}
+}  // namespace fol
+
+extern "C" int fol_csr_values(fol_stream_t s, int dtype, int64_t npairs, int d, int nnode, const int32_t* pair_ptr,
+                              const int32_t* contrib, const int32_t* out_base, const int32_t* row_stride,
+                              const void* data, void* vals) {
+  FOL_REQUIRE(pair_ptr && contrib && out_base && row_stride && data && vals, "fol_csr_values: null pointer");
+  const long long total = (long long)npairs * d * d;
+  if (total == 0) return FOL_OK;
+  const unsigned grid = (unsigned)cdiv(total, 256);
+  if (dtype == FOL_F64)
+    csr_values_kernel<double><<<grid, 256, 0, (cudaStream_t)s>>>(npairs, d, nnode, pair_ptr, contrib, out_base,
+                                                                row_stride, (const double*)data, (double*)vals);
+  else
+    csr_values_kernel<float><<<grid, 256, 0, (cudaStream_t)s>>>(npairs, d, nnode, pair_ptr, contrib, out_base,
+                                                               row_stride, (const float*)data, (float*)vals);
+  return check_launch("csr_values_kernel");
+}

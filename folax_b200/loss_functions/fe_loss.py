@@ -262,6 +262,27 @@ class FiniteElementLoss(Loss):
         jac = BCOO((data, self._bcoo_indices()), shape=(self.total_number_of_dofs, self.total_number_of_dofs))
         return jac, R
 
+    def _csr_plan(self):
+        if self.__dict__.get("_cplan") is None:
+            from .. import csr_plan
+            plan = csr_plan.build(self.fe_mesh.GetElementsNodes(self.element_type), self._nn,
+                                  self.number_dofs_per_node)
+            self._cplan = {k: (torch.as_tensor(v, device=self.device) if isinstance(v, np.ndarray) else v)
+                           for k, v in plan.items()}
+        return self._cplan
+
+    def JacobianToCSR(self, jacobian):
+        """Duplicate-free CSR (indptr, indices, values) of a Jacobian returned by
+        ComputeJacobianMatrixAndResidualVector -- the sum the reference's solvers do on the host with
+        scipy.sparse.csr_array (fe_solver.py:71-72), done on the GPU in a fixed order."""
+        cp = self._csr_plan()
+        vals = torch.empty(cp["nnz"], dtype=self.dtype, device=self.device)
+        _lib.check(_lib.load().fol_csr_values(_lib.stream_ptr(), self._dt, cp["npairs"], self.number_dofs_per_node,
+                                              self._nnode, _lib.ptr(cp["pair_ptr"]), _lib.ptr(cp["contrib"]),
+                                              _lib.ptr(cp["out_base"]), _lib.ptr(cp["row_stride"]),
+                                              _lib.ptr(jacobian.data), _lib.ptr(vals)))
+        return cp["indptr"], cp["indices"], vals
+
     def ComputeElement(self, elem_xyz, elem_controls, elem_dofs):
         """Single-element evaluation (the unit-test entry point): (energy, re (nd,1), Ke (nd,nd)).
         Runs the same kernel on a one-element mesh."""

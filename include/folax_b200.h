@@ -102,6 +102,16 @@ int fol_residual_gather(fol_stream_t s, int dtype, int64_t nn, int nnode, int do
                         const int32_t* adj_ptr, const int32_t* adj, const void* re_elem,
                         void* residual);
 
+/* Duplicate-free CSR values from the BCOO data (hand-off to fol/solvers: fe_solver.py:71-72, 82).
+ * The integer plan is built once per mesh by the host (folax_b200/csr_plan.py): node pairs (n, m) in
+ * row-major sorted order; pair_ptr/contrib list, per pair, the contributing element entries
+ * e*a*a + la*a + lb in ascending order (fixed summation order => deterministic values);
+ * out_base[p] is the CSR position of entry (i=0, j=0) of pair p, row_stride[p] the distance between
+ * consecutive dof rows of that node.  vals has d*d*npairs entries. */
+int fol_csr_values(fol_stream_t s, int dtype, int64_t npairs, int dofs_per_node, int nnode,
+                   const int32_t* pair_ptr, const int32_t* contrib, const int32_t* out_base,
+                   const int32_t* row_stride, const void* ke_data, void* vals);
+
 /* ---- batched physics loss + VJP (fe_loss.py:250-262 and its JAX-AD gradient) -------------- */
 
 /* per-element, per-Gauss-point geometry factors shared by all samples, SoA over elements:
