@@ -9,8 +9,9 @@ int launch_energy(cudaStream_t s, const EnergyArgs<T>& args) {
   constexpr int ND = elem_nnode(ELEM) * phys_dpn(PHYS, ELEM);
   constexpr int S = ND <= 8 ? 4 : 2;   // samples per CTA pass (shared-memory rows)
   constexpr int KW = energy_kw(PHYS, ELEM);
-  const size_t smem = sizeof(T) * (size_t)S * KW * args.ecap;
-  if (smem > 200 * 1024) return fail(FOL_ERR_INVALID, "fol_energy_and_grads: tile element list too long");
+  constexpr int C = phys_dpn(PHYS, ELEM) + 1;
+  const size_t smem = sizeof(T) * ((size_t)S * KW * args.ecap + (size_t)2 * S * C * args.lcap);
+  if (smem > 200 * 1024) return fail(FOL_ERR_INVALID, "fol_energy_and_grads: tile lists too long for shared memory");
   auto kern = energy_tile_kernel<T, ELEM, ORDER, PHYS, S, BLOCK>;
   static size_t configured = 0;
   if (smem > configured) {

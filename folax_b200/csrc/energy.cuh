@@ -31,13 +31,16 @@ struct EnergyArgs {
   const int32_t* tile_nodes;  // node ids grouped by tile
   const int32_t* tile_elem_ptr;
   const int32_t* tile_elems;  // element ids grouped by tile
+  const int32_t* tile_conn;   // (len(tile_elems), A): element nodes in tile-local numbering
+  const int32_t* tile_lnode_ptr;
+  const int32_t* tile_lnodes; // per tile: the nodes its elements touch (owned nodes first, tile order)
   const T* ctrl;              // (nb, nn)
   const T* u;                 // (nb, ndof)
   T* grad_u;                  // (nb, ndof)
   T* grad_k;                  // (nb, nn) or null
   T* partial;                 // (nb, ntiles) per-tile energy shares
   long long ne, nn, nb;
-  int ntiles, ecap;           // tiles, max elements per tile (shared-memory row length)
+  int ntiles, ecap, lcap;     // tiles, max elements per tile, max local nodes per tile (shared-memory rows)
   Params<T> p;
 };
 
@@ -92,19 +95,25 @@ __host__ __device__ constexpr int energy_kw(int phys, int elem) {
 
 // Element vectors of element e for S samples starting at sample b0 (samples past nb are clamped):
 // re[s][nd], dK[s][a] (thermal / neo-hooke), en[s] (neo-hooke strain energy).
-// nodal gather of one sample for one element (fe_loss.py:155-164)
+// element gather (fe_loss.py:155-164) from the tile's staged nodal rows: st = [C = DPN + 1][lcap] of one sample
 template <class T, int A, int DPN>
-__device__ __forceinline__ void gather_sample(const EnergyArgs<T>& args, const int (&nodes)[A], long long b,
-                                              T (&ue)[1][A * DPN], T (&de)[1][A]) {
-  const long long bb = b < args.nb ? b : args.nb - 1;
-  const T* cb = args.ctrl + bb * args.nn;
-  const T* ub = args.u + bb * (args.nn * DPN);
+__device__ __forceinline__ void gather_staged(const T* st, int lcap, const int (&ln)[A], T (&ue)[1][A * DPN],
+                                              T (&de)[1][A]) {
 #pragma unroll
   for (int a = 0; a < A; ++a) {
-    de[0][a] = __ldg(cb + nodes[a]);
 #pragma unroll
-    for (int k = 0; k < DPN; ++k) ue[0][a * DPN + k] = __ldg(ub + nodes[a] * DPN + k);
+    for (int k = 0; k < DPN; ++k) ue[0][a * DPN + k] = st[k * lcap + ln[a]];
+    de[0][a] = st[DPN * lcap + ln[a]];
   }
+}
+
+template <class T>
+__device__ __forceinline__ void cp_async_elem(T* sdst, const T* gsrc) {
+  const unsigned saddr = (unsigned)__cvta_generic_to_shared(sdst);
+  if constexpr (sizeof(T) == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(gsrc) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(saddr), "l"(gsrc) : "memory");
 }
 
 // geometry factors of one element fit in registers for the small elements / rules
@@ -273,65 +282,91 @@ __device__ __forceinline__ void element_vectors(const EnergyArgs<T>& args, long 
 template <class T, int ELEM, int ORDER, int PHYS, int S, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 2)
 energy_tile_kernel(const EnergyArgs<T> args) {
-  // S = samples per CTA pass; phase A work items are (element, sample) pairs, one per thread
+  // S = samples per CTA pass.  Shared memory: sv [S][KW][ecap] element vectors of the pass,
+  // stage [2][S][C][lcap] nodal rows (dofs + control) of the tile's nodes, double-buffered: the rows
+  // of pass p+1 arrive by cp.async while pass p computes, so no thread ever waits on a gather.
   constexpr int A = elem_nnode(ELEM), DPN = phys_dpn(PHYS, ELEM), ND = A * DPN, KW = energy_kw(PHYS, ELEM);
+  constexpr int C = DPN + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* sv = reinterpret_cast<T*>(smem_raw);            // [S][KW][ecap]
+  const int ecap = args.ecap, lcap = args.lcap;
+  T* sv = reinterpret_cast<T*>(smem_raw);
+  T* stage = sv + (size_t)S * KW * ecap;
   __shared__ T red[S][BLOCK / 32];
   const int t = blockIdx.x;
-  const int ecap = args.ecap;
   const int e_beg = __ldg(args.tile_elem_ptr + t), n_el = __ldg(args.tile_elem_ptr + t + 1) - e_beg;
   const int n_beg = __ldg(args.tile_node_ptr + t), n_nd = __ldg(args.tile_node_ptr + t + 1) - n_beg;
+  const int l_beg = __ldg(args.tile_lnode_ptr + t), n_ln = __ldg(args.tile_lnode_ptr + t + 1) - l_beg;
   const long long ndof = args.nn * DPN;
 
-  // this thread's node (phase B) and its adjacency range are the same for every sample
+  // phase B role: node threadIdx.x of the tile (= local node threadIdx.x) and its adjacency range
   const bool has_node = (int)threadIdx.x < n_nd;
   const int n = has_node ? __ldg(args.tile_nodes + n_beg + threadIdx.x) : 0;
   const int a_beg = has_node ? __ldg(args.adj_ptr + n) : 0, a_end = has_node ? __ldg(args.adj_ptr + n + 1) : 0;
 
-  // fast path: one thread per tile element, its geometry factors and node ids live in registers
+  // staging role: local node l = threadIdx.x (+ BLOCK ...) copies its S*C values per pass
+  auto stage_pass = [&](int buf, long long b0) {
+    T* dst0 = stage + (size_t)buf * S * C * lcap;
+    for (int l = threadIdx.x; l < n_ln; l += BLOCK) {
+      const long long gn = __ldg(args.tile_lnodes + l_beg + l);
+#pragma unroll
+      for (int sidx = 0; sidx < S; ++sidx) {
+        const long long bb = (b0 + sidx < args.nb) ? b0 + sidx : args.nb - 1;
+        T* dst = dst0 + (sidx * C) * lcap + l;
+#pragma unroll
+        for (int k = 0; k < DPN; ++k) cp_async_elem<T>(dst + k * lcap, args.u + bb * ndof + gn * DPN + k);
+        cp_async_elem<T>(dst + DPN * lcap, args.ctrl + bb * args.nn + gn);
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+
+  // fast path: one thread per tile element; geometry factors and local node ids live in registers
   constexpr bool REGS = geom_in_regs(ELEM, ORDER);
   constexpr int GW = REGS ? elem_ngauss(ELEM, ORDER) * (A * elem_dim(ELEM) + 1) : 1;
   const bool fast = REGS && n_el <= BLOCK;
   T greg[GW];
-  int my_nodes[A];
+  int my_ln[A];
   long long my_el = -1;
   if constexpr (REGS) {
     if (fast && (int)threadIdx.x < n_el) {
       my_el = __ldg(args.tile_elems + e_beg + threadIdx.x);
 #pragma unroll
-      for (int b = 0; b < A; ++b) my_nodes[b] = __ldg(args.conn + my_el * A + b);
+      for (int b = 0; b < A; ++b) my_ln[b] = __ldg(args.tile_conn + (long long)(e_beg + threadIdx.x) * A + b);
 #pragma unroll
       for (int k = 0; k < GW; ++k) greg[k] = __ldg(args.geom + (long long)k * args.ne + my_el);
     }
   }
 
-  for (long long b0 = (long long)blockIdx.y * S; b0 < args.nb; b0 += (long long)gridDim.y * S) {
+  auto store_vectors = [&](int sidx, int j, const T (&re)[1][ND], const T (&dK)[1][A], const T (&en1)[1]) {
+    T* out = sv + (sidx * KW) * ecap + j;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) { *out = re[0][k]; out += ecap; }
+    if constexpr (PHYS != MECH) {
+#pragma unroll
+      for (int b = 0; b < A; ++b) { *out = dK[0][b]; out += ecap; }
+    }
+    if constexpr (PHYS == NEOHOOKE) *out = en1[0];
+  };
+
+  long long b0 = (long long)blockIdx.y * S;
+  const long long bstep = (long long)gridDim.y * S;
+  int buf = 0;
+  if (b0 < args.nb) stage_pass(0, b0);
+  for (; b0 < args.nb; b0 += bstep, buf ^= 1) {
     const int ns = (args.nb - b0 < S) ? (int)(args.nb - b0) : S;
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();   // this pass's rows are visible; everyone is done with the previous pass's sv / rows
+    if (b0 + bstep < args.nb) stage_pass(buf ^ 1, b0 + bstep);
+    const T* st0 = stage + (size_t)buf * S * C * lcap;
+
     // ---- phase A: every element of the tile, once per sample
     if constexpr (REGS) {
-      if (fast) {   // thread <-> element, geometry + connectivity stay in registers across samples
-        if (my_el >= 0) {
-          T ue[1][ND], de[1][A];
-          gather_sample<T, A, DPN>(args, my_nodes, b0, ue, de);
-          for (int sidx = 0; sidx < ns; ++sidx) {
-            T ue_n[1][ND], de_n[1][A];   // next sample's nodal values are in flight during this one
-            gather_sample<T, A, DPN>(args, my_nodes, b0 + sidx + 1, ue_n, de_n);
-            T re[1][ND], dK[1][A], en1[1];
-            element_vectors<T, ELEM, ORDER, PHYS, 1, true>(args, my_el, my_nodes, greg, ue, de, re, dK, en1);
-            T* out = sv + (sidx * KW) * ecap + threadIdx.x;
-#pragma unroll
-            for (int k = 0; k < ND; ++k) { *out = re[0][k]; out += ecap; }
-            if constexpr (PHYS != MECH) {
-#pragma unroll
-              for (int b = 0; b < A; ++b) { *out = dK[0][b]; out += ecap; }
-            }
-            if constexpr (PHYS == NEOHOOKE) *out = en1[0];
-#pragma unroll
-            for (int k = 0; k < ND; ++k) ue[0][k] = ue_n[0][k];
-#pragma unroll
-            for (int b = 0; b < A; ++b) de[0][b] = de_n[0][b];
-          }
+      if (fast && my_el >= 0) {
+        for (int sidx = 0; sidx < ns; ++sidx) {
+          T ue[1][ND], de[1][A], re[1][ND], dK[1][A], en1[1];
+          gather_staged<T, A, DPN>(st0 + (sidx * C) * lcap, lcap, my_ln, ue, de);
+          element_vectors<T, ELEM, ORDER, PHYS, 1, true>(args, my_el, my_ln, greg, ue, de, re, dK, en1);
+          store_vectors(sidx, threadIdx.x, re, dK, en1);
         }
       }
     }
@@ -341,20 +376,13 @@ energy_tile_kernel(const EnergyArgs<T> args) {
       while (j >= n_el && sidx < ns) { j -= n_el; ++sidx; }
       for (int it = threadIdx.x; it < items; it += BLOCK) {
         const long long e = __ldg(args.tile_elems + e_beg + j);
-        int nodes[A];
+        int ln[A];
 #pragma unroll
-        for (int b = 0; b < A; ++b) nodes[b] = __ldg(args.conn + e * A + b);
+        for (int b = 0; b < A; ++b) ln[b] = __ldg(args.tile_conn + (long long)(e_beg + j) * A + b);
         T ue[1][ND], de[1][A], re[1][ND], dK[1][A], en1[1];
-        gather_sample<T, A, DPN>(args, nodes, b0 + sidx, ue, de);
-        element_vectors<T, ELEM, ORDER, PHYS, 1, false>(args, e, nodes, nullptr, ue, de, re, dK, en1);
-        T* out = sv + (sidx * KW) * ecap + j;
-#pragma unroll
-        for (int k = 0; k < ND; ++k) { *out = re[0][k]; out += ecap; }
-        if constexpr (PHYS != MECH) {
-#pragma unroll
-          for (int b = 0; b < A; ++b) { *out = dK[0][b]; out += ecap; }
-        }
-        if constexpr (PHYS == NEOHOOKE) *out = en1[0];
+        gather_staged<T, A, DPN>(st0 + (sidx * C) * lcap, lcap, ln, ue, de);
+        element_vectors<T, ELEM, ORDER, PHYS, 1, false>(args, e, ln, nullptr, ue, de, re, dK, en1);
+        store_vectors(sidx, j, re, dK, en1);
         j += BLOCK;
         while (j >= n_el) { j -= n_el; ++sidx; }
       }
@@ -394,8 +422,9 @@ energy_tile_kernel(const EnergyArgs<T> args) {
           const long long bb = b0 + s;
 #pragma unroll
           for (int k = 0; k < DPN; ++k) {
-            if constexpr (PHYS != NEOHOOKE) en[s] += __ldg(args.u + bb * ndof + n * DPN + k) * R[s][k];  // u_b . R_b
-            args.grad_u[bb * ndof + n * DPN + k] = R[s][k];
+            // E_b = u_b . R_b (mechanical.py:116-117, thermal.py:45-49); u from the staged rows
+            if constexpr (PHYS != NEOHOOKE) en[s] += st0[(s * C + k) * lcap + threadIdx.x] * R[s][k];
+            args.grad_u[bb * ndof + (long long)n * DPN + k] = R[s][k];
           }
           if constexpr (PHYS != MECH) {
             if (args.grad_k) args.grad_k[bb * args.nn + n] = dk[s];
@@ -410,7 +439,7 @@ energy_tile_kernel(const EnergyArgs<T> args) {
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if ((threadIdx.x & 31) == 0) red[s][threadIdx.x >> 5] = v;
     }
-    __syncthreads();  // also: everyone is done reading sv before the next sample batch overwrites it
+    __syncthreads();
     if ((int)threadIdx.x < ns) {
       T v = (T)0;
 #pragma unroll

@@ -28,10 +28,14 @@ def build(coords, conn, tile_nodes=TILE_NODES):
     conn = np.asarray(conn, dtype=np.int64)
     ne, A = conn.shape
     nn = len(coords)
-    order = np.argsort(_morton_keys(coords), kind="stable")          # nodes in tile order
+    morton = np.argsort(_morton_keys(coords), kind="stable")         # compact tiles: cut the Z-curve
+    tile_of_node = np.empty(nn, dtype=np.int64)
+    tile_of_node[morton] = np.arange(nn) // tile_nodes
+    # inside a tile, nodes are kept in ascending global id: neighbouring threads then touch
+    # neighbouring addresses (coalesced gradient writes, conflict-free shared-memory gathers)
+    order = np.lexsort((np.arange(nn), tile_of_node))
     rank = np.empty(nn, dtype=np.int64)
     rank[order] = np.arange(nn)
-    tile_of_node = rank // tile_nodes
     ntiles = int((nn + tile_nodes - 1) // tile_nodes)
     tile_node_ptr = np.minimum(np.arange(ntiles + 1, dtype=np.int64) * tile_nodes, nn)
     # adjacency sorted by node, then by e*A + a (stable sort keeps ascending entry ids)
@@ -50,7 +54,29 @@ def build(coords, conn, tile_nodes=TILE_NODES):
     local = np.searchsorted(ukeys, key) - tile_elem_ptr[tile_of_node[node_of_entry]]
     adj_local = local * A + a_of_entry
     ecap = int(np.diff(tile_elem_ptr).max()) if ntiles else 1
+    # local node lists: the tile's own nodes first (tile order), then the halo nodes its elements touch
+    tile_of_telem = np.repeat(np.arange(ntiles), np.diff(tile_elem_ptr))
+    tnodes = conn[tile_elems]                                         # (len(tile_elems), A) global ids
+    owned = tile_of_node[tnodes] == tile_of_telem[:, None]
+    halo_key = np.unique((tile_of_telem[:, None] * nn + tnodes)[~owned])          # (tile, node) pairs, sorted
+    halo_tile, halo_node = halo_key // nn, halo_key % nn
+    n_owned = np.diff(tile_node_ptr)
+    n_halo = np.bincount(halo_tile, minlength=ntiles)
+    tile_lnode_ptr = np.concatenate([[0], np.cumsum(n_owned + n_halo)])
+    tile_lnodes = np.empty(int(tile_lnode_ptr[-1]), dtype=np.int64)
+    halo_ptr = np.concatenate([[0], np.cumsum(n_halo)])
+    own_pos = tile_lnode_ptr[:-1][tile_of_node[order]] + (rank[order] - tile_node_ptr[:-1][tile_of_node[order]])
+    tile_lnodes[own_pos] = order
+    halo_pos = tile_lnode_ptr[:-1][halo_tile] + n_owned[halo_tile] + (np.arange(len(halo_key)) - halo_ptr[halo_tile])
+    tile_lnodes[halo_pos] = halo_node
+    # element connectivity in tile-local numbering
+    local_owned = rank[tnodes] - tile_node_ptr[:-1][tile_of_telem][:, None]
+    local_halo = n_owned[tile_of_telem][:, None] + (np.searchsorted(halo_key, tile_of_telem[:, None] * nn + tnodes)
+                                                    - halo_ptr[tile_of_telem][:, None])
+    tile_conn = np.where(owned, local_owned, local_halo)
+    lcap = int(np.diff(tile_lnode_ptr).max()) if ntiles else 1
     i32 = lambda x: np.ascontiguousarray(x, dtype=np.int32)
     return {"adj_ptr": i32(adj_ptr), "adj_local": i32(adj_local), "tile_node_ptr": i32(tile_node_ptr),
             "tile_nodes": i32(order), "tile_elem_ptr": i32(tile_elem_ptr), "tile_elems": i32(tile_elems),
-            "ntiles": ntiles, "ecap": max(ecap, 1)}
+            "tile_conn": i32(tile_conn), "tile_lnode_ptr": i32(tile_lnode_ptr), "tile_lnodes": i32(tile_lnodes),
+            "ntiles": ntiles, "ecap": max(ecap, 1), "lcap": max(lcap, 1)}

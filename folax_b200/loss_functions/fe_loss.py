@@ -353,7 +353,9 @@ class FiniteElementLoss(Loss):
                                             _lib.ptr(geom), _lib.ptr(self._conn), _lib.ptr(ep["adj_ptr"]),
                                             _lib.ptr(ep["adj_local"]), _lib.ptr(ep["tile_node_ptr"]),
                                             _lib.ptr(ep["tile_nodes"]), _lib.ptr(ep["tile_elem_ptr"]),
-                                            _lib.ptr(ep["tile_elems"]), ep["ntiles"], ep["ecap"],
+                                            _lib.ptr(ep["tile_elems"]), _lib.ptr(ep["tile_conn"]),
+                                            _lib.ptr(ep["tile_lnode_ptr"]), _lib.ptr(ep["tile_lnodes"]), ep["ntiles"],
+                                            ep["ecap"], ep["lcap"],
                                             _lib.ptr(batch_params), _lib.ptr(batch_dofs), self._params,
                                             _lib.ptr(grad_u), _lib.ptr(grad_k), _lib.ptr(energy), _lib.ptr(work)))
         return energy, grad_u, grad_k

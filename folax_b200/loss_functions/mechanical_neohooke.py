@@ -36,8 +36,9 @@ class NeoHookeMechanicalLoss(MechanicalLoss):
                                             self.num_gp, 1, A, 1, _lib.ptr(geom), _lib.ptr(conn),
                                             _lib.ptr(ep["adj_ptr"]), _lib.ptr(ep["adj_local"]),
                                             _lib.ptr(ep["tile_node_ptr"]), _lib.ptr(ep["tile_nodes"]),
-                                            _lib.ptr(ep["tile_elem_ptr"]), _lib.ptr(ep["tile_elems"]), ep["ntiles"],
-                                            ep["ecap"], _lib.ptr(ctrl), _lib.ptr(u), self._params, _lib.ptr(gu),
+                                            _lib.ptr(ep["tile_elem_ptr"]), _lib.ptr(ep["tile_elems"]), _lib.ptr(ep["tile_conn"]),
+                                            _lib.ptr(ep["tile_lnode_ptr"]), _lib.ptr(ep["tile_lnodes"]), ep["ntiles"],
+                                            ep["ecap"], ep["lcap"], _lib.ptr(ctrl), _lib.ptr(u), self._params, _lib.ptr(gu),
                                             _lib.ptr(gk), _lib.ptr(energy), _lib.ptr(work)))
         return energy[0]
 
