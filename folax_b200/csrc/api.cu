@@ -49,7 +49,8 @@ static int assemble_typed(cudaStream_t s, int physics, int element, int num_gp, 
   switch (physics) {
     case FOL_MECHANICAL:
       if constexpr (f64) {
-        if (element == HEX && num_gp == 2 && g_tuned.load()) return assemble_hex_mech_f64(s, a);
+        // (the tuned kernel writes Ke itself; the transpose switch of fe_loss.py:216-230 uses the generic kernel)
+        if (element == HEX && num_gp == 2 && !transpose && g_tuned.load()) return assemble_hex_mech_f64(s, a);
         return assemble_mech_f64(s, element, num_gp, a);
       } else {
         return assemble_mech_f32(s, element, num_gp, a);

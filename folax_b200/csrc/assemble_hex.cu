@@ -13,8 +13,8 @@
 //   * Ke rows are staged in shared memory and leave the SM as ONE contiguous 4608-byte bulk
 //     async copy per element (cp.async.bulk shared->global, the TMA engine): full-line writes, no
 //     store instructions on the LSU path; the copy of element i drains while element i+1 is computed.
-// Ke of linear elasticity is symmetric bit for bit (same products, same order), so the transpose
-// switch is a no-op here.
+// Ke is symmetric only to rounding here (the scale s_g rides on the A operand of the DMMA), so calls
+// with transpose_jacobian=True are served by the generic kernel, which transposes exactly.
 #include "assemble.cuh"
 
 namespace fol {

@@ -1,0 +1,93 @@
+"""BASELINE.json full-size configuration (128^3 Hex8 elements, 6.44 M dofs, float64) checked through
+size-independent properties -- the oracle cannot assemble 2 M elements in seconds, so parity at this
+size rests on: (i) a random sample of elements compared against the oracle, (ii) linearity of the
+residual, (iii) rigid-body null space, (iv) symmetry of the element blocks, (v) run-to-run
+bit-identity, (vi) tuned kernel == generic kernel to rounding."""
+import numpy as np
+import pytest
+import torch
+
+import folax_b200
+from folax_b200 import _lib
+from folax_b200.loss_functions import MechanicalLoss3DHexa
+from oracle import assembly
+
+pytestmark = pytest.mark.gpu
+
+N = 128
+MAT = {"young_modulus": 1.0, "poisson_ratio": 0.3}
+
+
+@pytest.fixture(scope="module")
+def big():
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs a large-memory GPU")
+    mesh = folax_b200.create_3D_box_mesh(N, N, N, 1.0, 1.0, 1.0)
+    bc = {d: {"left": 0.0, "right": 0.1} for d in ("Ux", "Uy", "Uz")}
+    loss = MechanicalLoss3DHexa("c2", {"dirichlet_bc_dict": bc, "num_gp": 2, "material_dict": dict(MAT)}, mesh)
+    loss.Initialize()
+    free = MechanicalLoss3DHexa("c2_free", {"dirichlet_bc_dict": {"Ux": {}, "Uy": {}, "Uz": {}}, "num_gp": 2,
+                                            "material_dict": dict(MAT)}, mesh)
+    free.Initialize()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    K = torch.rand(loss._nn, generator=g, device="cuda", dtype=torch.float64) * 0.9 + 0.1
+    u = torch.randn(loss.total_number_of_dofs, generator=g, device="cuda", dtype=torch.float64) * 0.01
+    return mesh, loss, free, K, u
+
+
+def test_sampled_elements_match_oracle(big):
+    mesh, loss, _, K, u = big
+    jac, R = loss.ComputeJacobianMatrixAndResidualVector(K, u)
+    assert jac.data.numel() == 2097152 * 576 and jac.shape == (6440067, 6440067)
+    rng = np.random.default_rng(1)
+    conn = mesh.GetElementsNodes("hexahedron")
+    left_layer = np.arange(0, len(conn), N)[:200]                      # elements touching the Dirichlet face x = 0
+    sample = np.unique(np.concatenate([rng.integers(0, len(conn), 2000), left_layer, [0, len(conn) - 1]]))
+    coords = np.asarray(mesh.GetNodesCoordinates())
+    Kh, uh = K.cpu().numpy(), u.cpu().numpy()
+    ref, _, _ = assembly.assemble("mechanical", "hexahedron", 2, coords, conn[sample], Kh, uh,
+                                  loss.dirichlet_indices, MAT)
+    got = jac.data.view(-1, 576)[torch.as_tensor(sample, device="cuda")].cpu().numpy().reshape(-1)
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+    # BCOO indices of the sampled elements, bit-exact
+    idx = jac.indices.view(-1, 576, 2)[torch.as_tensor(sample, device="cuda")].cpu().numpy().reshape(-1, 2)
+    assert np.array_equal(idx, assembly.bcoo_indices(conn[sample], 3))
+    # run-to-run bit-identity at full size
+    jac2, R2 = loss.ComputeJacobianMatrixAndResidualVector(K, u)
+    assert torch.equal(jac.data, jac2.data) and torch.equal(R, R2)
+    del jac2
+    # tuned kernel vs generic kernel
+    lib = _lib.load()
+    prev = lib.fol_set_tuned_kernels(0)
+    try:
+        jg, Rg = loss.ComputeJacobianMatrixAndResidualVector(K, u)
+    finally:
+        lib.fol_set_tuned_kernels(prev)
+    scale = jac.data.abs().max().item()
+    assert (jac.data - jg.data).abs().max().item() <= 1e-12 * scale
+    assert (R - Rg).abs().max().item() <= 4e-12 * R.abs().max().item()
+
+
+def test_linearity_rigid_modes_and_symmetry(big):
+    mesh, _, free, K, u = big
+    g = torch.Generator(device="cuda").manual_seed(5)
+    u2 = torch.randn(u.shape, generator=g, device="cuda", dtype=torch.float64) * 0.01
+    J, R1 = free.ComputeJacobianMatrixAndResidualVector(K, u)
+    # symmetry of the element matrices (to rounding: the Gauss-point scale rides on one DMMA operand)
+    blocks = J.data.view(-1, 24, 24)
+    assert (blocks[::97] - blocks[::97].transpose(1, 2)).abs().max().item() <= 1e-15 * blocks.abs().max().item()
+    # rows of an unconstrained element matrix sum to zero per displacement component (rigid translation)
+    tr = torch.zeros(24, 3, dtype=torch.float64, device="cuda")
+    for c in range(3):
+        tr[c::3, c] = 1.0
+    assert (blocks[::97] @ tr).abs().max().item() <= 1e-13 * blocks.abs().max().item()
+    del J, blocks
+    _, R2 = free.ComputeJacobianMatrixAndResidualVector(K, u2)
+    _, R12 = free.ComputeJacobianMatrixAndResidualVector(K, 2.0 * u - 3.0 * u2)
+    scale = R1.abs().max().item()
+    assert (2.0 * R1 - 3.0 * R2 - R12).abs().max().item() <= 1e-11 * scale
+    t = torch.tensor([0.3, -0.1, 0.2], dtype=torch.float64, device="cuda").repeat(free._nn)
+    _, Rt = free.ComputeJacobianMatrixAndResidualVector(K, t)
+    assert Rt.abs().max().item() <= 1e-12
+    # total force balance: the assembled internal forces of a free body sum to zero
+    assert abs(R1.view(-1, 3).sum(0)).max().item() <= 1e-9 * scale
