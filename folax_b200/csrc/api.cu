@@ -11,6 +11,8 @@ int assemble_thermal_f64(cudaStream_t, int, int, const AsmArgs<double>&);
 int assemble_thermal_f32(cudaStream_t, int, int, const AsmArgs<float>&);
 int assemble_neohooke_f64(cudaStream_t, int, int, const AsmArgs<double>&);
 int assemble_neohooke_f32(cudaStream_t, int, int, const AsmArgs<float>&);
+int assemble_stvk_f64(cudaStream_t, int, int, const AsmArgs<double>&);
+int assemble_stvk_f32(cudaStream_t, int, int, const AsmArgs<float>&);
 int assemble_j2_f64(cudaStream_t, int, int, const AsmArgs<double>&);
 int assemble_j2_f32(cudaStream_t, int, int, const AsmArgs<float>&);
 int assemble_hex_mech_f64(cudaStream_t, const AsmArgs<double>&);
@@ -61,6 +63,9 @@ static int assemble_typed(cudaStream_t s, int physics, int element, int num_gp, 
     case FOL_NEOHOOKE:
       if constexpr (f64) return assemble_neohooke_f64(s, element, num_gp, a);
       else return assemble_neohooke_f32(s, element, num_gp, a);
+    case FOL_STVENANT:
+      if constexpr (f64) return assemble_stvk_f64(s, element, num_gp, a);
+      else return assemble_stvk_f32(s, element, num_gp, a);
 #ifdef FOL_HAVE_J2
     case FOL_J2PLASTICITY:
       if (!st_in || !st_out) return fail(FOL_ERR_INVALID, "J2 plasticity needs state_in/state_out");
@@ -208,7 +213,8 @@ int fol_plan_create(fol_plan** plan, int dtype, int physics, int element, int nu
   FOL_REQUIRE(plan && xyz_host && conn_host && params_host, "fol_plan_create: null pointer");
   FOL_REQUIRE(valid_element(element) && num_gp >= 1 && num_gp <= 3, "fol_plan_create: bad element / num_gp");
   FOL_REQUIRE(dtype == FOL_F32 || dtype == FOL_F64, "fol_plan_create: bad dtype");
-  FOL_REQUIRE(physics == FOL_MECHANICAL || physics == FOL_THERMAL || physics == FOL_NEOHOOKE,
+  FOL_REQUIRE(physics == FOL_MECHANICAL || physics == FOL_THERMAL || physics == FOL_NEOHOOKE ||
+                  physics == FOL_STVENANT,
               "fol_plan_create: physics without history only");
   fol_plan* p = new fol_plan();
   p->dtype = dtype; p->physics = physics; p->element = element; p->num_gp = num_gp;

@@ -19,7 +19,10 @@
 
 namespace fol {
 
-enum : int { MECH = 0, THERMAL = 1, NEOHOOKE = 2, J2 = 3 };
+enum : int { MECH = 0, THERMAL = 1, NEOHOOKE = 2, J2 = 3, STVK = 4 };
+
+// finite-strain total-Lagrangian laws share one kernel skeleton (F-weighted B, geometric stiffness)
+__host__ __device__ constexpr bool finite_strain(int phys) { return phys == NEOHOOKE || phys == STVK; }
 
 __host__ __device__ constexpr int phys_dpn(int phys, int elem) { return phys == THERMAL ? 1 : elem_dim(elem); }
 __host__ __device__ constexpr int voigt_size(int dim) { return dim == 3 ? 6 : 3; }
@@ -48,7 +51,7 @@ struct PointDataSize {
   // MECH/THERMAL: nothing beyond coef.  NEOHOOKE: F (DIM*DIM) + S (V) + C (V*V).
   // J2: sigma (V) + tangent (V*V).
   static constexpr int V = voigt_size(DIM);
-  static constexpr int value = PHYS == NEOHOOKE ? DIM * DIM + V + V * V : (PHYS == J2 ? V + V * V : 0);
+  static constexpr int value = finite_strain(PHYS) ? DIM * DIM + V + V * V : (PHYS == J2 ? V + V * V : 0);
 };
 
 template <class T, int ELEM, int ORDER, int PHYS>
@@ -183,6 +186,47 @@ __device__ __forceinline__ T neo_hooke_point(const T (&F)[D][D], T k, T mu, T* S
   return psi;
 }
 
+// Saint-Venant-Kirchhoff, saint_venant.py:11-33: E = (F^T F - I)/2, psi = lam/2 tr(E)^2 + mu tr(E E),
+// S = lam tr(E) I + 2 mu E.  The reference builds the tangent from the UNsymmetrised fourth-order
+// identity (utils.py fourth_order_identity_tensor), so its Voigt shear entries are 2 mu (kept as is).
+template <class T, int D>
+__device__ __forceinline__ T st_venant_point(const T (&F)[D][D], T lam, T mu, T* S, T* Cv) {
+  constexpr int V = voigt_size(D);
+  T E[D][D];
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      T acc = (i == j) ? (T)-1 : (T)0;
+#pragma unroll
+      for (int m = 0; m < D; ++m) acc += F[m][i] * F[m][j];
+      E[i][j] = (T)0.5 * acc;
+    }
+  T tr = (T)0, ee = (T)0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    tr += E[i][i];
+#pragma unroll
+    for (int j = 0; j < D; ++j) ee += E[i][j] * E[j][i];
+  }
+  constexpr int vi3[6] = {0, 1, 2, 1, 0, 0}, vj3[6] = {0, 1, 2, 2, 2, 1};
+  constexpr int vi2[3] = {0, 1, 0}, vj2[3] = {0, 1, 1};
+#pragma unroll
+  for (int I = 0; I < V; ++I) {
+    const int i = D == 3 ? vi3[I] : vi2[I], j = D == 3 ? vj3[I] : vj2[I];
+    S[I] = (i == j ? lam * tr : (T)0) + (T)2 * mu * E[i][j];
+#pragma unroll
+    for (int Jv = 0; Jv < V; ++Jv) {
+      const int nrm = D;  // first D Voigt entries are the normal components
+      T c = (T)0;
+      if (I < nrm && Jv < nrm) c = lam + (I == Jv ? (T)2 * mu : (T)0);
+      else if (I == Jv) c = (T)2 * mu;
+      Cv[I * V + Jv] = c;
+    }
+  }
+  return (T)0.5 * lam * tr * tr + mu * ee;
+}
+
 // row a of the F-weighted strain-displacement matrix, mechanical_neohooke.py:49-91:
 // Ba[s][c] for Voigt row s and displacement component c of node a.
 template <class T, int D>
@@ -287,7 +331,7 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
         const T beta = P.v[5], cexp = P.v[6];
         const T nl = (beta != (T)0) ? beta * (T)pow((double)tg, (double)cexp) : (T)0;
         sm.coef[g] = wd * eg * ((T)1 + nl);
-      } else if constexpr (PHYS == NEOHOOKE) {
+      } else if constexpr (finite_strain(PHYS)) {
         T F[D][D];
 #pragma unroll
         for (int i = 0; i < D; ++i)
@@ -302,7 +346,8 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
         const T kk = eg / ((T)3 * ((T)1 - (T)2 * nu)), mu = eg / ((T)2 * ((T)1 + nu));
         T* pd = sm.pd + g * PD;
         T S[V], Cv[V * V];
-        neo_hooke_point<T, D>(F, kk, mu, S, Cv);
+        if constexpr (PHYS == NEOHOOKE) neo_hooke_point<T, D>(F, kk, mu, S, Cv);
+        else st_venant_point<T, D>(F, eg * nu / (((T)1 + nu) * ((T)1 - (T)2 * nu)), mu, S, Cv);
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
@@ -420,10 +465,10 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
     for (int g = 0; g < NGP; ++g) {
       const T wd = sm.coef[g];
       const T* pd = sm.pd + g * PD;
-      const T* Sv = (PHYS == NEOHOOKE) ? pd + D * D : pd;
+      const T* Sv = finite_strain(PHYS) ? pd + D * D : pd;
       const T* Cv = Sv + V;
       T Ba[V][D];
-      if constexpr (PHYS == NEOHOOKE) neo_hooke_B<T, D>(pd, sm.gN[g][a], Ba);
+      if constexpr (finite_strain(PHYS)) neo_hooke_B<T, D>(pd, sm.gN[g][a], Ba);
       else linear_B<T, D>(sm.gN[g][a], Ba);
       // BtC[c][t] = wd * sum_s Ba[s][c] C[s][t]
       T BtC[D][V];
@@ -444,7 +489,7 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
         fint[c] += wd * acc;
       }
       T Sg[D];  // S_mat g_a (geometric stiffness, mechanical_neohooke.py:107-241)
-      if constexpr (PHYS == NEOHOOKE) {
+      if constexpr (finite_strain(PHYS)) {
         constexpr int vmap3[3][3] = {{0, 5, 4}, {5, 1, 3}, {4, 3, 2}};
         constexpr int vmap2[2][2] = {{0, 2}, {2, 1}};
 #pragma unroll
@@ -458,10 +503,10 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
 #pragma unroll
       for (int b = 0; b < A; ++b) {
         T Bb[V][D];
-        if constexpr (PHYS == NEOHOOKE) neo_hooke_B<T, D>(pd, sm.gN[g][b], Bb);
+        if constexpr (finite_strain(PHYS)) neo_hooke_B<T, D>(pd, sm.gN[g][b], Bb);
         else linear_B<T, D>(sm.gN[g][b], Bb);
         T geo = (T)0;
-        if constexpr (PHYS == NEOHOOKE) {
+        if constexpr (finite_strain(PHYS)) {
 #pragma unroll
           for (int i = 0; i < D; ++i) geo += Sg[i] * sm.gN[g][b][i];
         }

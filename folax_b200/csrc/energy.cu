@@ -45,6 +45,7 @@ int energy_and_grads(cudaStream_t s, int physics, int element, int num_gp, const
   if (physics == FOL_MECHANICAL) rc = dispatch_energy<T, MECH>(s, element, num_gp, a);
   else if (physics == FOL_THERMAL) rc = dispatch_energy<T, THERMAL>(s, element, num_gp, a);
   else if (physics == FOL_NEOHOOKE) rc = dispatch_energy<T, NEOHOOKE>(s, element, num_gp, a);
+  else if (physics == FOL_STVENANT) rc = dispatch_energy<T, STVK>(s, element, num_gp, a);
   else return fail(FOL_ERR_UNSUPPORTED, "fol_energy_and_grads: physics not supported");
   if (rc) return rc;
   energy_sum_kernel<T><<<(unsigned)cdiv(a.nb, 8), 256, 0, s>>>(a.partial, a.nb, a.ntiles, energy);

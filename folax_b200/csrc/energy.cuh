@@ -90,7 +90,7 @@ __global__ void geometry_cache_kernel(const T* __restrict__ xyz, const int32_t* 
 
 // scratch row count per element: re (ND) [+ dK (A)] [+ psi (1)]
 __host__ __device__ constexpr int energy_kw(int phys, int elem) {
-  return elem_nnode(elem) * phys_dpn(phys, elem) + (phys == MECH ? 0 : elem_nnode(elem)) + (phys == NEOHOOKE ? 1 : 0);
+  return elem_nnode(elem) * phys_dpn(phys, elem) + (phys == MECH ? 0 : elem_nnode(elem)) + (finite_strain(phys) ? 1 : 0);
 }
 
 // Element vectors of element e for S samples starting at sample b0 (samples past nb are clamped):
@@ -259,7 +259,8 @@ __device__ __forceinline__ void element_vectors(const EnergyArgs<T>& args, long 
             F[i][j] = acc;
           }
         T Sv[V], Cv[V * V];
-        const T psi1 = neo_hooke_point<T, D>(F, k1, mu1, Sv, Cv);
+        const T psi1 = (PHYS == NEOHOOKE) ? neo_hooke_point<T, D>(F, k1, mu1, Sv, Cv)
+                                          : st_venant_point<T, D>(F, nu / (((T)1 + nu) * ((T)1 - (T)2 * nu)), mu1, Sv, Cv);
         en[s] += wd * eg * psi1;
 #pragma unroll
         for (int b = 0; b < A; ++b) {
@@ -345,7 +346,7 @@ energy_tile_kernel(const EnergyArgs<T> args) {
 #pragma unroll
       for (int b = 0; b < A; ++b) { *out = dK[0][b]; out += ecap; }
     }
-    if constexpr (PHYS == NEOHOOKE) *out = en1[0];
+    if constexpr (finite_strain(PHYS)) *out = en1[0];
   };
 
   long long b0 = (long long)blockIdx.y * S;
@@ -412,7 +413,7 @@ energy_tile_kernel(const EnergyArgs<T> args) {
             for (int k = 0; k < DPN; ++k) R[s][k] += in[(s * KW + k) * ecap];
             if constexpr (PHYS != MECH) dk[s] += ink[(s * KW) * ecap];
             // each element's strain energy is counted once: at its local node 0, by the tile owning it
-            if constexpr (PHYS == NEOHOOKE) en[s] += (a == 0) ? sv[jl + (s * KW + ND + A) * ecap] : (T)0;
+            if constexpr (finite_strain(PHYS)) en[s] += (a == 0) ? sv[jl + (s * KW + ND + A) * ecap] : (T)0;
           }
         }
       }
@@ -423,7 +424,7 @@ energy_tile_kernel(const EnergyArgs<T> args) {
 #pragma unroll
           for (int k = 0; k < DPN; ++k) {
             // E_b = u_b . R_b (mechanical.py:116-117, thermal.py:45-49); u from the staged rows
-            if constexpr (PHYS != NEOHOOKE) en[s] += st0[(s * C + k) * lcap + threadIdx.x] * R[s][k];
+            if constexpr (!finite_strain(PHYS)) en[s] += st0[(s * C + k) * lcap + threadIdx.x] * R[s][k];
             args.grad_u[bb * ndof + (long long)n * DPN + k] = R[s][k];
           }
           if constexpr (PHYS != MECH) {

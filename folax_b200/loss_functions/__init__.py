@@ -8,3 +8,6 @@ from .mechanical_neohooke import (NeoHookeMechanicalLoss, NeoHookeMechanicalLoss
                                   NeoHookeMechanicalLoss3DTetra)
 from .mechanical_elastoplasticity import (ElastoplasticityLoss, ElastoplasticityLoss2DQuad,
                                           ElastoplasticityLoss3DHexa, ElastoplasticityLoss3DTetra)
+from .mechanical_saint_venant import (SaintVenantMechanicalLoss, SaintVenantMechanicalLoss2DQuad,
+                                      SaintVenantMechanicalLoss2DTri, SaintVenantMechanicalLoss3DHexa,
+                                      SaintVenantMechanicalLoss3DTetra)

@@ -45,7 +45,8 @@ class _BatchLossFn(torch.autograd.Function):
     tail, backward only rescales the saved (un-scaled) cotangents -- SURVEY.md A.7."""
 
     @staticmethod
-    def forward(ctx, loss, batch_params, batch_dofs):
+    def forward(ctx, loss, batch_params, batch_dofs, mask_dirichlet=True):
+        ctx.mask_dirichlet = mask_dirichlet
         energy, grad_u, grad_k = loss._energy_and_grads(batch_params, batch_dofs)
         out4 = torch.empty(4, dtype=loss.dtype, device=energy.device)
         scale = torch.empty_like(energy)
@@ -72,9 +73,9 @@ class _BatchLossFn(torch.autograd.Function):
         nb = grad_u.shape[0]
         _lib.check(_lib.load().fol_scale_grads(_lib.stream_ptr(), loss._dt, nb, loss.total_number_of_dofs,
                                                loss.fe_mesh.GetNumberOfNodes(), _lib.ptr(ctx.scale), up,
-                                               _lib.ptr(loss._dir_flag), _lib.ptr(grad_u),
-                                               _lib.ptr(grad_k) if grad_k is not None else None))
-        return None, (grad_k if ctx.need[0] else None), (grad_u if ctx.need[1] else None)
+                                               _lib.ptr(loss._dir_flag if ctx.mask_dirichlet else loss._no_flag),
+                                               _lib.ptr(grad_u), _lib.ptr(grad_k) if grad_k is not None else None))
+        return None, (grad_k if ctx.need[0] else None), (grad_u if ctx.need[1] else None), None
 
 
 class FiniteElementLoss(Loss):
@@ -146,8 +147,8 @@ class FiniteElementLoss(Loss):
         if expected != self.number_dofs_per_node:
             raise ValueError(f"{self.GetName()}: {self.number_dofs_per_node} dofs per node given, "
                              f"{self.physics} on {self.element_type} needs {expected}")
-        if self.loss_settings.get("parametric_boundary_learning"):
-            raise NotImplementedError("parametric_boundary_learning is not supported by folax_b200 yet")
+        # fe_loss.py:94-100: in parametric boundary learning the batch parameters ARE the Dirichlet values
+        self._parametric = bool(self.loss_settings.get("parametric_boundary_learning"))
         self.loss_function_exponent = self.loss_settings.get("loss_function_exponent", 1.0)
 
         # element batching of the reference (fe_loss.py:103-114) only bounds XLA memory; kept as
@@ -177,6 +178,7 @@ class FiniteElementLoss(Loss):
         work = torch.empty(max(nn, 1), dtype=torch.int32, device=self.device)
         _lib.check(lib.fol_node_adjacency(s, _lib.ptr(self._conn), ne, self._nnode, nn, _lib.ptr(self._adj_ptr),
                                           _lib.ptr(self._adj), _lib.ptr(work)))
+        self._no_flag = torch.zeros_like(self._dir_flag)
         self._indices = None   # BCOO indices, built on the first Jacobian request
         self._geom = None      # geometry cache, built on the first batched-loss request
         self._params = _lib.params_array(self._material_params())
@@ -193,6 +195,11 @@ class FiniteElementLoss(Loss):
         return u
 
     def GetParametersVectors(self, param_vector):
+        """fe_loss.py:127-128 (identity) -- losses with a mesh-resident heterogeneity field override the
+        control field in parametric boundary learning (mechanical_saint_venant.py:59-66)."""
+        field = self.__dict__.get("heterogeneity_field")
+        if self.__dict__.get("_parametric") and field is not None:
+            return field
         return param_vector
 
     def Finalize(self) -> None:
@@ -363,10 +370,19 @@ class FiniteElementLoss(Loss):
     def ComputeBatchLoss(self, batch_params, batch_dofs):
         """fe_loss.py:250-262 -> (mean_b E_b^p, (min, max, mean)); differentiable w.r.t. both inputs
         (torch.autograd.Function = the custom_vjp of the FFI call)."""
-        params = self._as_batch(batch_params, self._nn)
         dofs = self._as_batch(batch_dofs, self.total_number_of_dofs)
-        full = _ApplyDirichlet.apply(self, dofs)
-        mean, mn, mx, mean2, _ = _BatchLossFn.apply(self, params, full)
+        if self._parametric:
+            known = self._as_batch(batch_params, self.dirichlet_indices.size)
+            full = _ApplyDirichletParametric.apply(self, known, dofs)
+            ctrl = _lib.to_device(self.GetParametersVectors(batch_params), self.dtype)
+            if ctrl.dim() == 1:
+                ctrl = ctrl.reshape(1, -1).expand(dofs.shape[0], -1)
+            params = self._as_batch(ctrl, self._nn)
+            mean, mn, mx, mean2, _ = _BatchLossFn.apply(self, params, full, False)
+        else:
+            params = self._as_batch(batch_params, self._nn)
+            full = _ApplyDirichlet.apply(self, dofs)
+            mean, mn, mx, mean2, _ = _BatchLossFn.apply(self, params, full, True)
         return mean, (mn, mx, mean2)
 
     def ComputeTotalEnergy(self, total_control_vars, total_primal_vars):
@@ -375,6 +391,28 @@ class FiniteElementLoss(Loss):
         dofs = self._as_batch(total_primal_vars, self.total_number_of_dofs)
         energy, _, _ = self._energy_and_grads(params, dofs)
         return energy[0]
+
+
+class _ApplyDirichletParametric(torch.autograd.Function):
+    """u[:, dirichlet_indices] = known (per sample): ConstructFullDofVectorParametricLearning, fe_loss.py:94-95.
+    The cotangent at the Dirichlet entries flows to `known`, the rest to the free dofs."""
+
+    @staticmethod
+    def forward(ctx, loss, known, dofs):
+        ctx.loss = loss
+        u = dofs.clone()
+        _lib.check(_lib.load().fol_apply_dirichlet(_lib.stream_ptr(), loss._dt, u.shape[0], loss.total_number_of_dofs,
+                                                   _lib.ptr(loss._dir_idx), loss._dir_idx.numel(),
+                                                   _lib.ptr(known.contiguous()), 1, 1.0, _lib.ptr(u)))
+        return u
+
+    @staticmethod
+    def backward(ctx, g):
+        idx = ctx.loss._dir_idx.to(torch.int64)
+        g_known = g.index_select(1, idx)
+        g_dofs = g.clone()
+        g_dofs[:, idx] = 0
+        return None, g_known, g_dofs
 
 
 class _ApplyDirichlet(torch.autograd.Function):

@@ -33,7 +33,8 @@ enum fol_dtype { FOL_F32 = 0, FOL_F64 = 1 };
 /* fol/geometries/__init__.py:18-21 (fe_element_dict keys) */
 enum fol_element { FOL_HEXAHEDRON = 0, FOL_QUAD = 1, FOL_TETRA = 2, FOL_TRIANGLE = 3 };
 /* fol/loss_functions: mechanical.py, thermal.py, mechanical_neohooke.py, mechanical_elastoplasticity.py */
-enum fol_physics { FOL_MECHANICAL = 0, FOL_THERMAL = 1, FOL_NEOHOOKE = 2, FOL_J2PLASTICITY = 3 };
+enum fol_physics { FOL_MECHANICAL = 0, FOL_THERMAL = 1, FOL_NEOHOOKE = 2, FOL_J2PLASTICITY = 3,
+                   FOL_STVENANT = 4 /* mechanical_saint_venant.py */ };
 
 #define FOL_OK 0
 #define FOL_ERR_INVALID (-1)

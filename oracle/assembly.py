@@ -73,9 +73,9 @@ def compute_elements(physics, element_type, num_gp, coords, conn, controls, dofs
     if physics == "mechanical":
         return losses.mechanical_element(element_type, num_gp, X, de, u, params["young_modulus"],
                                          params["poisson_ratio"], params.get("body_force"))
-    if physics == "neohooke":
+    if physics in ("neohooke", "stvenant"):
         return losses.neo_hooke_element(element_type, num_gp, X, de, u, params["young_modulus"],
-                                        params["poisson_ratio"], params.get("body_force"))
+                                        params["poisson_ratio"], params.get("body_force"), law=physics)
     raise ValueError(physics)
 
 
@@ -145,7 +145,7 @@ def batch_loss_grads(physics, element_type, num_gp, coords, conn, batch_controls
     for b in range(nb):
         en, re, _ = compute_elements(physics, element_type, num_gp, coords, conn, K[b], U[b], params)
         Eb[b] = en.sum()
-        if physics == "neohooke":
+        if physics in ("neohooke", "stvenant"):
             # energy = sum psi; its u-gradient is F_int (no body-force term)
             body = params.get("body_force")
             if body is not None:
@@ -154,7 +154,7 @@ def batch_loss_grads(physics, element_type, num_gp, coords, conn, batch_controls
                 Ns, _, detJ, w = point_data(elem, X, num_gp)
                 re = re + losses.body_force_vector(elem, Ns, detJ, w, body)
             dK = losses.neo_hooke_energy_dcontrol(element_type, num_gp, X, K[b][conn],
-                                                  U[b][g], params["poisson_ratio"])
+                                                  U[b][g], params["poisson_ratio"], law=physics)
             np.add.at(gK[b], conn.reshape(-1), dK.reshape(-1))
         elif physics == "thermal":
             _, dK = losses.thermal_energy_grads(element_type, num_gp, X, K[b][conn], U[b][conn],

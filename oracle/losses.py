@@ -157,6 +157,29 @@ def neo_hooke_point(F, k, mu):
     return psi, Sv, Cv
 
 
+def st_venant_point(F, lam, mu):
+    """saint_venant.py:11-33.  psi = lam/2 tr(E)^2 + mu tr(E E), S = lam tr(E) I + 2 mu E; the Voigt tangent
+    is taken from lam d_ij d_kl + 2 mu d_ik d_jl (UNsymmetrised identity), i.e. shear entries 2 mu."""
+    d = F.shape[-1]
+    E = 0.5 * (np.einsum("...ki,...kj->...ij", F, F) - np.eye(d))
+    tr = np.trace(E, axis1=-2, axis2=-1)
+    psi = 0.5 * lam * tr ** 2 + mu * np.einsum("...ij,...ji->...", E, E)
+    S = lam[..., None, None] * tr[..., None, None] * np.eye(d) + 2.0 * mu[..., None, None] * E
+    vo = _VOIGT3 if d == 3 else _VOIGT2
+    Sv = np.stack([S[..., i, j] for (i, j) in vo], axis=-1)
+    eye = np.eye(d)
+    C4 = lam[..., None, None, None, None] * np.einsum("ij,kl->ijkl", eye, eye) \
+        + 2.0 * mu[..., None, None, None, None] * np.einsum("ik,jl->ijkl", eye, eye)
+    if d == 3:
+        Cv = np.stack([np.stack([C4[..., i, j, kk, l] for (kk, l) in vo], axis=-1) for (i, j) in vo], axis=-2)
+    else:
+        c00, c01, c02 = C4[..., 0, 0, 0, 0], C4[..., 0, 0, 1, 1], C4[..., 0, 0, 0, 1]
+        c11, c12, c22 = C4[..., 1, 1, 1, 1], C4[..., 1, 1, 0, 1], C4[..., 0, 1, 0, 1]
+        Cv = np.stack([np.stack([c00, c01, c02], -1), np.stack([c01, c11, c12], -1),
+                       np.stack([c02, c12, c22], -1)], axis=-2)
+    return psi, Sv, Cv
+
+
 def neo_hooke_b_matrix(gradN, F):
     """mechanical_neohooke.py:49-91.  gradN (..., a, d), F (..., d, d) -> B (..., nv, a*d)."""
     a, d = gradN.shape[-2:]
@@ -180,7 +203,7 @@ def neo_hooke_b_matrix(gradN, F):
     return B
 
 
-def neo_hooke_element(element_type, num_gp, X, de, u, E, nu, body=None):
+def neo_hooke_element(element_type, num_gp, X, de, u, E, nu, body=None, law="neohooke"):
     """mechanical_neohooke.py:243-275.  ``E`` scales the control field: E_gp = N . de (the
     reference ignores ``young_modulus`` in ComputeElement, :253-255, so pass de = E*control
     -- here ``E`` multiplies nothing and is kept only for a uniform signature)."""
@@ -194,7 +217,10 @@ def neo_hooke_element(element_type, num_gp, X, de, u, E, nu, body=None):
     e_gp = np.einsum("ga,ea->eg", Ns, de)
     k_gp = e_gp / (3.0 * (1.0 - 2.0 * nu))
     mu_gp = e_gp / (2.0 * (1.0 + nu))
-    psi, Sv, Cv = neo_hooke_point(F, k_gp, mu_gp)
+    if law == "stvenant":     # mechanical_saint_venant.py:282-289
+        psi, Sv, Cv = st_venant_point(F, e_gp * nu / ((1.0 + nu) * (1.0 - 2.0 * nu)), mu_gp)
+    else:
+        psi, Sv, Cv = neo_hooke_point(F, k_gp, mu_gp)
     B = neo_hooke_b_matrix(gradN, F)
     wd = w[None, :] * detJ
     Kmat = np.einsum("eg,egsn,egst,egtm->enm", wd, B, Cv, B, optimize=True)
@@ -212,7 +238,7 @@ def neo_hooke_element(element_type, num_gp, X, de, u, E, nu, body=None):
     return energy, Fint - Fe, Kmat + Kgeo
 
 
-def neo_hooke_energy_dcontrol(element_type, num_gp, X, de, u, nu):
+def neo_hooke_energy_dcontrol(element_type, num_gp, X, de, u, nu, law="neohooke"):
     """d(energy)/d(de): psi is linear in (k, mu) and both are linear in E_gp = N.de."""
     elem = ELEMENTS[element_type]
     d = elem.dim
@@ -221,5 +247,8 @@ def neo_hooke_energy_dcontrol(element_type, num_gp, X, de, u, nu):
     U = u.reshape(ne, elem.nnode, d)
     F = np.einsum("egai,eaj->egji", gradN, U) + np.eye(d)
     one = np.ones(F.shape[:-2])
-    psi1, _, _ = neo_hooke_point(F, one / (3.0 * (1.0 - 2.0 * nu)), one / (2.0 * (1.0 + nu)))
+    if law == "stvenant":
+        psi1, _, _ = st_venant_point(F, one * nu / ((1.0 + nu) * (1.0 - 2.0 * nu)), one / (2.0 * (1.0 + nu)))
+    else:
+        psi1, _, _ = neo_hooke_point(F, one / (3.0 * (1.0 - 2.0 * nu)), one / (2.0 * (1.0 + nu)))
     return np.einsum("g,eg,eg,ga->ea", w, detJ, psi1, Ns)

@@ -13,6 +13,8 @@ LOSS_CLASSES = {
     ("thermal", "tetra"): lf.ThermalLoss3DTetra, ("thermal", "triangle"): lf.ThermalLoss2DTri,
     ("neohooke", "hexahedron"): lf.NeoHookeMechanicalLoss3DHexa, ("neohooke", "quad"): lf.NeoHookeMechanicalLoss2DQuad,
     ("neohooke", "tetra"): lf.NeoHookeMechanicalLoss3DTetra, ("neohooke", "triangle"): lf.NeoHookeMechanicalLoss2DTri,
+    ("stvenant", "hexahedron"): lf.SaintVenantMechanicalLoss3DHexa, ("stvenant", "quad"): lf.SaintVenantMechanicalLoss2DQuad,
+    ("stvenant", "tetra"): lf.SaintVenantMechanicalLoss3DTetra, ("stvenant", "triangle"): lf.SaintVenantMechanicalLoss2DTri,
 }
 
 
@@ -71,7 +73,7 @@ def fields(physics, mesh, loss, seed=0, batch=None):
     K = rng.uniform(0.1, 1.0, shape_k)
     if physics == "thermal":
         u = rng.uniform(0.1, 1.0, shape_u)
-    elif physics == "neohooke":
+    elif physics in ("neohooke", "stvenant"):
         h = 1.0 / max(2, round(nn ** (1.0 / loss.dim)))
         u = 0.02 * h * rng.standard_normal(shape_u)
     else:

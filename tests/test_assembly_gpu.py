@@ -22,7 +22,7 @@ def _close(actual, ref, tol):
     assert err <= tol * max(scale, 1e-300), f"max err {err:.3e} vs scale {scale:.3e}"
 
 
-CASES = [(p, e, g) for p in ("mechanical", "thermal", "neohooke")
+CASES = [(p, e, g) for p in ("mechanical", "thermal", "neohooke", "stvenant")
          for e, gs in (("hexahedron", (1, 2, 3)), ("quad", (1, 2, 3)), ("tetra", (1, 2, 3)), ("triangle", (1, 2, 3)))
          for g in gs]
 

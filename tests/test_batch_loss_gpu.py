@@ -13,7 +13,8 @@ CASES = [("thermal", "quad", 2, {"beta": 0.0, "c": 1}), ("thermal", "quad", 2, {
          ("thermal", "hexahedron", 2, {}), ("thermal", "tetra", 1, {}), ("thermal", "triangle", 1, {}),
          ("mechanical", "quad", 2, {}), ("mechanical", "hexahedron", 2, {"body_foce": [0.1, 0.2, -0.3]}),
          ("mechanical", "tetra", 1, {}), ("mechanical", "triangle", 1, {}),
-         ("neohooke", "tetra", 1, {}), ("neohooke", "hexahedron", 2, {}), ("neohooke", "quad", 2, {})]
+         ("neohooke", "tetra", 1, {}), ("neohooke", "hexahedron", 2, {}), ("neohooke", "quad", 2, {}),
+         ("stvenant", "tetra", 1, {}), ("stvenant", "quad", 2, {}), ("stvenant", "hexahedron", 2, {})]
 
 
 @pytest.mark.parametrize("physics,etype,num_gp,extra", CASES)
@@ -91,3 +92,40 @@ def test_total_energy_and_float32():
     ref0 = compute_elements("thermal", "quad", 2, coords, mesh.GetElementsNodes("quad"), K32[0].astype(np.float64),
                             u32[0].astype(np.float64), H.oracle_params(loss))[0].sum()
     assert abs(e0.item() - ref0) <= 1e-5 * abs(ref0)
+
+
+def test_parametric_boundary_learning():
+    """mechanical_saint_venant.py:59-66 + fe_loss.py:94-100: the batch parameters are the Dirichlet values of
+    every sample, the control field is the mesh's heterogeneity field; cotangents at the Dirichlet dofs flow
+    to the parameters."""
+    from folax_b200.loss_functions import SaintVenantMechanicalLoss3DTetra
+    mesh = H.make_mesh("tetra", 2, seed=3)
+    rng = np.random.default_rng(4)
+    mesh["K"] = rng.uniform(0.5, 1.0, mesh.GetNumberOfNodes())
+    bc = {d: {"left": 0.0, "right": 0.1} for d in ("Ux", "Uy", "Uz")}
+    loss = SaintVenantMechanicalLoss3DTetra("pbl", {"dirichlet_bc_dict": bc, "parametric_boundary_learning": True,
+                                                    "material_dict": {"young_modulus": 1.0, "poisson_ratio": 0.3}}, mesh)
+    loss.Initialize()
+    B, nd = 3, loss.dirichlet_indices.size
+    known = 0.02 * rng.standard_normal((B, nd))
+    u = 0.01 * rng.standard_normal((B, loss.total_number_of_dofs))
+    kt = torch.tensor(known, device="cuda", requires_grad=True)
+    ut = torch.tensor(u, device="cuda", requires_grad=True)
+    mean, _ = loss.ComputeBatchLoss(kt, ut)
+    mean.backward()
+    # oracle: same energy with the Dirichlet entries replaced per sample, control = heterogeneity field
+    full = u.copy()
+    full[:, loss.dirichlet_indices] = known
+    coords, conn = np.asarray(mesh.GetNodesCoordinates()), mesh.GetElementsNodes("tetra")
+    Kf = np.tile(mesh["K"], (B, 1))
+    none = np.zeros(0, dtype=np.int64)
+    ref, _, Eb = assembly.batch_loss("stvenant", "tetra", 1, coords, conn, Kf, full, none, np.zeros(0),
+                                     H.oracle_params(loss))
+    gU, _ = assembly.batch_loss_grads("stvenant", "tetra", 1, coords, conn, Kf, full, none, np.zeros(0),
+                                      H.oracle_params(loss))
+    assert abs(mean.item() - ref) <= 1e-12 * abs(Eb).max()
+    scale = np.abs(gU).max()
+    assert np.abs(kt.grad.cpu().numpy() - gU[:, loss.dirichlet_indices]).max() <= 1e-12 * scale
+    want = gU.copy()
+    want[:, loss.dirichlet_indices] = 0.0
+    assert np.abs(ut.grad.cpu().numpy() - want).max() <= 1e-12 * scale
