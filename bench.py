@@ -328,6 +328,9 @@ def run_ours(args):
         tf = ctypes.c_double()
         if lib.fol_measure_fma_peak(_lib.F64, ctypes.byref(tf)) == 0:
             line["roofline"]["fp64_fma_peak_tflops_measured"] = tf.value
+        wb = ctypes.c_double()
+        if lib.fol_measure_write_bandwidth(4 << 30, ctypes.byref(wb)) == 0:
+            line["roofline"]["write_stream_gbs_measured"] = wb.value   # pure store stream on this GPU, for context
         # ---- CPU baseline (bounded sample)
         del ke
         torch.cuda.empty_cache()
@@ -373,8 +376,19 @@ def e2e_host(torch, lib, _lib, loss, mesh, K_host, u_host, ne, nn, ndof, args):
         dt = (time.perf_counter() - t0) / steps
         h2d = (nn + ndof) * 8
         d2h = (ne * 576 + ndof) * 8
+        # the PCIe ceiling of this box: a plain pinned device->host copy of 1 GiB
+        probe_d = torch.empty(1 << 27, dtype=torch.float64, device="cuda")
+        probe_h = torch.empty(1 << 27, dtype=torch.float64, pin_memory=True)
+        probe_h.copy_(probe_d)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        probe_h.copy_(probe_d)
+        torch.cuda.synchronize()
+        pcie_gbs = (1 << 30) / (time.perf_counter() - t1) / 1e9
+        del probe_d, probe_h
         return {"value": ne / dt, "unit": "elements/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": dt * 1e3, "steps": steps,
+                "ms_per_step": dt * 1e3, "steps": steps, "d2h_gbs_achieved": d2h / dt / 1e9,
+                "pcie_d2h_gbs_measured": pcie_gbs,
                 "api": "fol_plan_assemble_host (C ABI, pinned host buffers, returns after D2H)",
                 "note": "PCIe-bound: the reference contract hands the full duplicate-keeping BCOO (4608 B/element) "
                         "to the host solver"}

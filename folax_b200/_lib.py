@@ -50,6 +50,7 @@ SIGNATURES = {
     "fol_plan_assemble_device": (_int, [_vp, _int, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "fol_plan_stream": (_vp, [_vp]),
     "fol_measure_fma_peak": (_int, [_int, C.POINTER(_dbl)]),
+    "fol_measure_write_bandwidth": (_int, [_i64, C.POINTER(_dbl)]),
 }
 
 _lib = None

@@ -330,6 +330,44 @@ static int measure_peak(double* tflops) {
 }
 }  // namespace fol
 
+namespace fol {
+// write-only streaming kernel: the ceiling of a kernel whose traffic is a pure store stream
+__global__ void write_stream_kernel(double2* __restrict__ out, long long n2, double v) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride)
+    __stcs(out + i, make_double2(v, v));
+}
+}  // namespace fol
+
+// Measured HBM bandwidth of a pure WRITE stream of `bytes` (best of 5), GB/s.
+extern "C" int fol_measure_write_bandwidth(int64_t bytes, double* gbs) {
+  FOL_REQUIRE(gbs && bytes >= (1 << 20), "fol_measure_write_bandwidth: bad arguments");
+  double2* buf = nullptr;
+  FOL_CUDA(cudaMalloc(&buf, (size_t)bytes));
+  const long long n2 = bytes / 16;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  write_stream_kernel<<<148 * 16, 256>>>(buf, n2, 1.0);
+  float best = 1e30f;
+  for (int r = 0; r < 5; ++r) {
+    cudaEventRecord(e0);
+    write_stream_kernel<<<148 * 16, 256>>>(buf, n2, (double)r);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  g_launches.fetch_add(6);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  FOL_CUDA(cudaGetLastError());
+  *gbs = (double)(n2 * 16) / (best * 1e-3) / 1e9;
+  return FOL_OK;
+}
+
 extern "C" int fol_measure_fma_peak(int dtype, double* tflops) {
   FOL_REQUIRE(tflops, "fol_measure_fma_peak: null pointer");
   return dtype == FOL_F64 ? measure_peak<double>(tflops) : measure_peak<float>(tflops);

@@ -186,6 +186,9 @@ fol_stream_t fol_plan_stream(fol_plan* plan);
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* FP64 (or FP32) FMA peak microbenchmark: returns achieved TFLOP/s through *tflops. */
 int fol_measure_fma_peak(int dtype, double* tflops);
+/* HBM bandwidth of a pure WRITE stream of `bytes` (16-byte streaming stores, best of 5) in GB/s: the
+ * ceiling of a store-dominated kernel such as the Jacobian assembly. */
+int fol_measure_write_bandwidth(int64_t bytes, double* gbs);
 
 #ifdef __cplusplus
 }
