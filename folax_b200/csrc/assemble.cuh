@@ -107,6 +107,27 @@ __device__ __forceinline__ void store_row(T* __restrict__ dst, F&& val) {
   }
 }
 
+// same as store_row but into the shared-memory staging area (plain vector stores)
+// element matrices up to 1152 bytes (Tet4 mechanics f64) are staged; see assemble_kernel
+template <class T>
+__host__ __device__ constexpr bool stage_output(int nd) { return (size_t)nd * nd * sizeof(T) <= 1152; }
+
+template <class T, int ND, class F>
+__device__ __forceinline__ void stage_row(T* __restrict__ dst, F&& val) {
+  constexpr int RB = ND * (int)sizeof(T);
+  if constexpr (sizeof(T) == 8 && RB % 16 == 0) {
+#pragma unroll
+    for (int c = 0; c < ND; c += 2) reinterpret_cast<double2*>(dst)[c / 2] = make_double2(val(c), val(c + 1));
+  } else if constexpr (sizeof(T) == 4 && RB % 16 == 0) {
+#pragma unroll
+    for (int c = 0; c < ND; c += 4)
+      reinterpret_cast<float4*>(dst)[c / 4] = make_float4(val(c), val(c + 1), val(c + 2), val(c + 3));
+  } else {
+#pragma unroll
+    for (int c = 0; c < ND; ++c) dst[c] = (T)val(c);
+  }
+}
+
 // ---- constitutive point laws (phase 1) ---------------------------------------------------
 
 // Neo-Hooke, neo_hooke.py:14-58 (2-D) and :64-109 (3-D).  Writes F, S (Voigt), C (Voigt x Voigt)
@@ -384,8 +405,13 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
     }
   }
   __syncwarp();
-  if (!active) return;
 
+  // small element matrices are staged in shared memory ([group][ND*ND], element-major like the output)
+  // and leave as one bulk copy per warp; large ones (Hex8 mechanics) are stored directly
+  constexpr bool STAGE = stage_output<T>(ND);
+  T* stage_all = reinterpret_cast<T*>(smem_raw + sizeof(SM) * GPB);
+  T* st = stage_all + (size_t)grp * (ND * ND);
+  if (active) {
   // ---- phase 2: row block a of Ke, re = Ke u - Fe
   T K[A][DPN][DPN];
   T fint[DPN];
@@ -533,21 +559,23 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
   }
 
   // ---- store: transpose switch + Dirichlet row mask (fe_loss.py:191-230), data of :299
-  T* ke = args.ke + e * (long long)(ND * ND);
 #pragma unroll
   for (int i = 0; i < DPN; ++i) {
     const int r = a * DPN + i;
     args.re[e * ND + r] = sm.bc[r] * fint[i];
   }
+  T* ke = args.ke + e * (long long)(ND * ND);
   if (!args.transpose) {
 #pragma unroll
     for (int i = 0; i < DPN; ++i) {
       const int r = a * DPN + i;
       const bool freerow = sm.bc[r] != (T)0;
-      store_row<T, ND>(ke + r * ND, [&](int c) -> T {
+      auto val = [&](int c) -> T {
         const T v = K[c / DPN][i][c % DPN];
         return (freerow || c == r) ? v : (T)0;
-      });
+      };
+      if constexpr (STAGE) stage_row<T, ND>(st + r * ND, val);
+      else store_row<T, ND>(ke + r * ND, val);
     }
   } else {
     // lane a holds rows a*DPN+i of Ke = columns of Ke^T
@@ -560,9 +588,39 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
 #pragma unroll
         for (int i = 0; i < DPN; ++i) {
           const int c = a * DPN + i;
-          ke[r * ND + c] = (freerow || c == r) ? K[b][i][j] : (T)0;
+          (STAGE ? st : ke)[r * ND + c] = (freerow || c == r) ? K[b][i][j] : (T)0;
         }
       }
+  }
+  }  // active
+
+  // ---- the warp's elements are consecutive: their staged matrices leave as ONE contiguous bulk
+  // async copy (cp.async.bulk shared -> global, TMA engine) instead of scattered 16-byte stores
+  if constexpr (STAGE) {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncwarp();
+    constexpr int GPWARP = 32 / GW;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long e_w = (long long)blockIdx.x * GPB + (long long)warp * GPWARP;
+    long long cnt = args.ne - e_w;
+    cnt = cnt < 0 ? 0 : (cnt > GPWARP ? GPWARP : cnt);
+    const T* src = stage_all + (size_t)warp * GPWARP * (ND * ND);
+    T* dst = args.ke + e_w * (long long)(ND * ND);
+    const unsigned bytes = (unsigned)(cnt * ND * ND * sizeof(T));
+    const bool bulk_ok = (bytes % 16u == 0u) && ((reinterpret_cast<unsigned long long>(dst) & 15ull) == 0ull);
+    if (cnt > 0) {
+      if (bulk_ok) {
+        if (lane == 0) {
+          const unsigned saddr = (unsigned)__cvta_generic_to_shared(src);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(saddr), "r"(bytes)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // smem must outlive the copy
+        }
+      } else {  // ragged tail / unaligned output: plain coalesced copy
+        for (int idx = lane; idx < (int)(cnt * ND * ND); idx += 32) dst[idx] = src[idx];
+      }
+    }
   }
 }
 
@@ -573,9 +631,10 @@ int launch_assemble(cudaStream_t s, const AsmArgs<T>& args) {
   // 128 threads unless the per-group staging (high-order rules with constitutive point data)
   // would not leave room for two resident blocks per SM
   constexpr size_t kBudget = 100 * 1024;
-  constexpr int BLOCK = sizeof(SM) * (128 / GW) <= kBudget ? 128 : (sizeof(SM) * (64 / GW) <= kBudget ? 64 : 32);
+  constexpr size_t kPerGroup = sizeof(SM) + (stage_output<T>(SM::ND) ? sizeof(T) * SM::ND * SM::ND : 0);  // + staged Ke'
+  constexpr int BLOCK = kPerGroup * (128 / GW) <= kBudget ? 128 : (kPerGroup * (64 / GW) <= kBudget ? 64 : 32);
   constexpr int GPB = BLOCK / GW;
-  const size_t smem = sizeof(SM) * GPB;
+  const size_t smem = kPerGroup * GPB;
   auto kern = assemble_kernel<T, ELEM, ORDER, PHYS, BLOCK>;
   static bool configured = false;
   if (!configured) {
