@@ -11,6 +11,10 @@ int assemble_thermal_f64(cudaStream_t, int, int, const AsmArgs<double>&);
 int assemble_thermal_f32(cudaStream_t, int, int, const AsmArgs<float>&);
 int assemble_neohooke_f64(cudaStream_t, int, int, const AsmArgs<double>&);
 int assemble_neohooke_f32(cudaStream_t, int, int, const AsmArgs<float>&);
+int assemble_tthermal_f64(cudaStream_t, int, int, const AsmArgs<double>&);
+int assemble_tthermal_f32(cudaStream_t, int, int, const AsmArgs<float>&);
+int assemble_allencahn_f64(cudaStream_t, int, int, const AsmArgs<double>&);
+int assemble_allencahn_f32(cudaStream_t, int, int, const AsmArgs<float>&);
 int assemble_stvk_f64(cudaStream_t, int, int, const AsmArgs<double>&);
 int assemble_stvk_f32(cudaStream_t, int, int, const AsmArgs<float>&);
 int assemble_j2_f64(cudaStream_t, int, int, const AsmArgs<double>&);
@@ -63,6 +67,13 @@ static int assemble_typed(cudaStream_t s, int physics, int element, int num_gp, 
     case FOL_NEOHOOKE:
       if constexpr (f64) return assemble_neohooke_f64(s, element, num_gp, a);
       else return assemble_neohooke_f32(s, element, num_gp, a);
+    case FOL_TRANSIENT_THERMAL:
+      if (!st_in) return fail(FOL_ERR_INVALID, "transient thermal needs the nodal heterogeneity k0 in aux_in");
+      if constexpr (f64) return assemble_tthermal_f64(s, element, num_gp, a);
+      else return assemble_tthermal_f32(s, element, num_gp, a);
+    case FOL_ALLEN_CAHN:
+      if constexpr (f64) return assemble_allencahn_f64(s, element, num_gp, a);
+      else return assemble_allencahn_f32(s, element, num_gp, a);
     case FOL_STVENANT:
       if constexpr (f64) return assemble_stvk_f64(s, element, num_gp, a);
       else return assemble_stvk_f32(s, element, num_gp, a);
@@ -110,7 +121,8 @@ int fol_set_grid_margin(int ctas) { return g_grid_margin.exchange(ctas < 0 ? 0 :
 
 int fol_dofs_per_node(int physics, int element) {
   if (!valid_element(element)) return FOL_ERR_INVALID;
-  return physics == FOL_THERMAL ? 1 : elem_dim(element);
+  return (physics == FOL_THERMAL || physics == FOL_TRANSIENT_THERMAL || physics == FOL_ALLEN_CAHN) ? 1
+                                                                                                    : elem_dim(element);
 }
 
 int fol_assemble_elements(fol_stream_t s, int dtype, int physics, int element, int num_gp, int transpose, int64_t ne,

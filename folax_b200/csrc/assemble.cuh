@@ -19,12 +19,17 @@
 
 namespace fol {
 
-enum : int { MECH = 0, THERMAL = 1, NEOHOOKE = 2, J2 = 3, STVK = 4 };
+enum : int { MECH = 0, THERMAL = 1, NEOHOOKE = 2, J2 = 3, STVK = 4, TTHERMAL = 5, ALLENCAHN = 6 };
+
+// implicit-Euler scalar losses: (current field, next field) in the (control, dof) slots
+__host__ __device__ constexpr bool implicit_scalar(int phys) { return phys == TTHERMAL || phys == ALLENCAHN; }
 
 // finite-strain total-Lagrangian laws share one kernel skeleton (F-weighted B, geometric stiffness)
 __host__ __device__ constexpr bool finite_strain(int phys) { return phys == NEOHOOKE || phys == STVK; }
 
-__host__ __device__ constexpr int phys_dpn(int phys, int elem) { return phys == THERMAL ? 1 : elem_dim(elem); }
+__host__ __device__ constexpr int phys_dpn(int phys, int elem) {
+  return (phys == THERMAL || phys == TTHERMAL || phys == ALLENCAHN) ? 1 : elem_dim(elem);
+}
 __host__ __device__ constexpr int voigt_size(int dim) { return dim == 3 ? 6 : 3; }
 // Gauss-point history width of the J2 model (plasticity.py:122-130)
 __host__ __device__ constexpr int j2_state_size(int dim) { return dim == 3 ? 7 : 4; }
@@ -51,7 +56,9 @@ struct PointDataSize {
   // MECH/THERMAL: nothing beyond coef.  NEOHOOKE: F (DIM*DIM) + S (V) + C (V*V).
   // J2: sigma (V) + tangent (V*V).
   static constexpr int V = voigt_size(DIM);
-  static constexpr int value = finite_strain(PHYS) ? DIM * DIM + V + V * V : (PHYS == J2 ? V + V * V : 0);
+  // implicit scalar losses: cNN, cBB, cNB, rN, rB, energy density, grad(next field)[DIM]
+  static constexpr int value = finite_strain(PHYS) ? DIM * DIM + V + V * V
+                               : (PHYS == J2 ? V + V * V : (implicit_scalar(PHYS) ? 6 + DIM : 0));
 };
 
 template <class T, int ELEM, int ORDER, int PHYS>
@@ -59,10 +66,11 @@ struct GroupSmem {
   static constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM), DPN = phys_dpn(PHYS, ELEM);
   static constexpr int ND = A * DPN, NGP = elem_ngauss(ELEM, ORDER);
   static constexpr int PD = PointDataSize<PHYS, D>::value;
-  static constexpr int RAW = A * 3 + A + ND + ND + NGP * A * D + NGP + NGP + NGP * A + NGP * PD;
+  static constexpr int RAW = A * 3 + A + A + ND + ND + NGP * A * D + NGP + NGP + NGP * A + NGP * PD;
   static constexpr int PAD = (RAW % 2 == 0) ? 1 : 2;  // odd element count -> groups on distinct banks
   T X[A * 3];
   T de[A];
+  T aux[A];
   T u[ND];
   T bc[ND];
   T gN[NGP][A][D];
@@ -105,6 +113,21 @@ __device__ __forceinline__ void store_row(T* __restrict__ dst, F&& val) {
 #pragma unroll
     for (int c = 0; c < ND; ++c) __stcs(dst + c, (T)val(c));
   }
+}
+
+// x^c with small non-negative integer exponents by repeated multiplication (0^0 = 1, like jnp power)
+template <class T>
+__device__ __forceinline__ T pow_ci(T x, T c) {
+  const int ci = (int)c;
+  if ((T)ci == c && ci >= 0 && ci <= 16) {
+    T r = (T)1, b = x;
+    for (int k = ci; k; k >>= 1) {
+      if (k & 1) r *= b;
+      b *= b;
+    }
+    return r;
+  }
+  return (T)pow((double)x, (double)c);
 }
 
 // same as store_row but into the shared-memory staging area (plain vector stores)
@@ -316,6 +339,7 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
 #pragma unroll
     for (int k = 0; k < 3; ++k) sm.X[a * 3 + k] = __ldg(args.xyz + n * 3 + k);
     sm.de[a] = __ldg(args.ctrl + n);
+    if constexpr (PHYS == TTHERMAL) sm.aux[a] = __ldg(args.state_in + n);   // nodal heterogeneity k0
 #pragma unroll
     for (int k = 0; k < DPN; ++k) {
       sm.u[a * DPN + k] = __ldg(args.u + n * DPN + k);
@@ -332,13 +356,13 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
       gauss_point<ELEM, ORDER>(g, xi, w);
       T N[A], dN[A][D], gN[A][D];
       shape_functions<ELEM, T>(xi, N, dN);
-      const T det = global_gradients<ELEM, T>(sm.X, dN, gN);
+      const T det = global_gradients<ELEM, T, implicit_scalar(PHYS)>(sm.X, dN, gN);
       const T wd = (T)w * det;
       T eg = (T)0;
 #pragma unroll
       for (int b = 0; b < A; ++b) {
         eg += N[b] * sm.de[b];
-        sm.Nw[g][b] = wd * N[b];
+        sm.Nw[g][b] = implicit_scalar(PHYS) ? N[b] : wd * N[b];
 #pragma unroll
         for (int k = 0; k < D; ++k) sm.gN[g][b][k] = gN[b][k];
       }
@@ -352,6 +376,48 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
         const T beta = P.v[5], cexp = P.v[6];
         const T nl = (beta != (T)0) ? beta * (T)pow((double)tg, (double)cexp) : (T)0;
         sm.coef[g] = wd * eg * ((T)1 + nl);
+      } else if constexpr (implicit_scalar(PHYS)) {
+        // eg = N . (current field); next field and its gradient at the point
+        T fn = (T)0, gf[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) gf[k] = (T)0;
+#pragma unroll
+        for (int b = 0; b < A; ++b) {
+          fn += N[b] * sm.u[b];
+#pragma unroll
+          for (int k = 0; k < D; ++k) gf[k] += gN[b][k] * sm.u[b];
+        }
+        T g2 = (T)0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) g2 += gf[k] * gf[k];
+        const T dt = P.v[10];
+        T* pd = sm.pd + g * PD;
+        if constexpr (PHYS == TTHERMAL) {   // transient_thermal.py:42-73
+          const T beta = P.v[5], cexp = P.v[6], rcp = P.v[8] * P.v[9];
+          T kg = (T)0;   // heterogeneity k0 (auxiliary nodal field) at the point
+#pragma unroll
+          for (int b = 0; b < A; ++b) kg += N[b] * sm.aux[b];
+          const T Kg = kg * ((T)1 + ((beta != (T)0) ? beta * pow_ci<T>(fn, cexp) : (T)0));
+          const T dk = (beta != (T)0) ? kg * beta * cexp * pow_ci<T>(fn, cexp - (T)1) : (T)0;
+          pd[0] = rcp * wd;
+          pd[1] = dt * wd * Kg;
+          pd[2] = dt * wd * dk;
+          pd[3] = rcp * wd * (fn - eg);
+          pd[4] = dt * wd * Kg;
+          pd[5] = (T)0.5 * Kg * wd * g2 + rcp * (T)0.5 / dt * wd * (fn - eg) * (fn - eg);
+        } else {                            // phase_field.py:38-70
+          const T ie2 = (T)1 / (P.v[11] * P.v[11]);
+          pd[0] = wd * ((T)1 - dt * ie2 * ((T)3 * fn * fn - (T)1));
+          pd[1] = dt * wd;
+          pd[2] = (T)0;
+          pd[3] = wd * ((fn - eg) + dt * ie2 * (fn * fn - (T)1) * fn);
+          pd[4] = dt * wd;
+          pd[5] = (T)0.5 * wd * g2 + wd * (T)0.25 * (fn * fn - (T)1) * (fn * fn - (T)1) * ie2 +
+                  (T)0.5 / dt * wd * (fn - eg) * (fn - eg);
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) pd[6 + k] = gf[k];
+        sm.coef[g] = wd;
       } else if constexpr (finite_strain(PHYS)) {
         T F[D][D];
 #pragma unroll
@@ -424,7 +490,38 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
 #pragma unroll
   for (int i = 0; i < DPN; ++i) fint[i] = (T)0;
 
-  if constexpr (PHYS == MECH || PHYS == THERMAL) {
+  if constexpr (implicit_scalar(PHYS)) {
+    // Ke_ab = sum_g cNN N_a N_b + cBB gN_a.gN_b + cNB N_a (g.gN_b);  re_a = sum_g rN N_a + rB gN_a.g
+#pragma unroll 1
+    for (int g = 0; g < NGP; ++g) {
+      const T* pd = sm.pd + g * PD;
+      const T Na = sm.Nw[g][a];
+      T ga[D], gf[D], gag = (T)0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        ga[k] = sm.gN[g][a][k];
+        gf[k] = pd[6 + k];
+        gag += ga[k] * gf[k];
+      }
+      fint[0] += pd[3] * Na + pd[4] * gag;
+#pragma unroll
+      for (int b = 0; b < A; ++b) {
+        T bb = (T)0, gb = (T)0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          bb += ga[k] * sm.gN[g][b][k];
+          gb += gf[k] * sm.gN[g][b][k];
+        }
+        K[b][0][0] += pd[0] * Na * sm.Nw[g][b] + pd[1] * bb + pd[2] * Na * gb;
+      }
+    }
+    if (a == 0 && args.state_out != nullptr) {   // element energy (the first return value of ComputeElement)
+      T en = (T)0;
+#pragma unroll 1
+      for (int g = 0; g < NGP; ++g) en += sm.pd[g * PD + 5];
+      args.state_out[e] = en;
+    }
+  } else if constexpr (PHYS == MECH || PHYS == THERMAL) {
     // K holds P_ab = sum_g coef g_a (x) g_b (MECH) or the scalar sum_g coef g_a.g_b (THERMAL)
 #pragma unroll(NGP <= 8 ? NGP : 1)
     for (int g = 0; g < NGP; ++g) {
@@ -550,7 +647,7 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
   }
 
   // body force Fe_a = b * sum_g w detJ N_a (mechanical.py:110; the thermal generic path has none)
-  if constexpr (PHYS != THERMAL) {
+  if constexpr (PHYS != THERMAL && !implicit_scalar(PHYS)) {
     T nw = (T)0;
 #pragma unroll 1
     for (int g = 0; g < NGP; ++g) nw += sm.Nw[g][a];

@@ -113,7 +113,9 @@ __device__ __forceinline__ void shape_functions(const double xi[3], T* N, T (*dN
 
 // J = (dN^T X)^T, its determinant and grad N = dN . J^-1 (geometry.py:88-97).
 // X is a*3 (2-D elements use the first two columns, quadrilateral_2d_4.py:68-70).
-template <int ELEM, class T>
+// TRANSPOSED = true reproduces `B_mat = invJ @ dN^T` of transient_thermal.py:57-58 / phase_field.py:47-48,
+// where the inverse Jacobian enters un-transposed: gN[a][k] = sum_j dN[a][j] inv[k][j].
+template <int ELEM, class T, bool TRANSPOSED = false>
 __device__ __forceinline__ T global_gradients(const T* X /* [A][3] */, const T (*dN)[elem_dim(ELEM)],
                                               T (*gN)[elem_dim(ELEM)]) {
   constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM);
@@ -154,7 +156,7 @@ __device__ __forceinline__ T global_gradients(const T* X /* [A][3] */, const T (
     for (int k = 0; k < D; ++k) {
       T acc = (T)0;
 #pragma unroll
-      for (int j = 0; j < D; ++j) acc += dN[a][j] * inv[j][k];
+      for (int j = 0; j < D; ++j) acc += dN[a][j] * (TRANSPOSED ? inv[k][j] : inv[j][k]);
       gN[a][k] = acc;
     }
   return det;

@@ -11,3 +11,6 @@ from .mechanical_elastoplasticity import (ElastoplasticityLoss, Elastoplasticity
 from .mechanical_saint_venant import (SaintVenantMechanicalLoss, SaintVenantMechanicalLoss2DQuad,
                                       SaintVenantMechanicalLoss2DTri, SaintVenantMechanicalLoss3DHexa,
                                       SaintVenantMechanicalLoss3DTetra)
+from .transient_thermal import (TransientThermalLoss, TransientThermalLoss2DQuad, TransientThermalLoss2DTri,
+                                TransientThermalLoss3DHexa, TransientThermalLoss3DTetra)
+from .phase_field import AllenCahnLoss, AllenCahnLoss2DQuad, AllenCahnLoss2DTri, AllenCahnLoss3DHexa

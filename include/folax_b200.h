@@ -34,7 +34,8 @@ enum fol_dtype { FOL_F32 = 0, FOL_F64 = 1 };
 enum fol_element { FOL_HEXAHEDRON = 0, FOL_QUAD = 1, FOL_TETRA = 2, FOL_TRIANGLE = 3 };
 /* fol/loss_functions: mechanical.py, thermal.py, mechanical_neohooke.py, mechanical_elastoplasticity.py */
 enum fol_physics { FOL_MECHANICAL = 0, FOL_THERMAL = 1, FOL_NEOHOOKE = 2, FOL_J2PLASTICITY = 3,
-                   FOL_STVENANT = 4 /* mechanical_saint_venant.py */ };
+                   FOL_STVENANT = 4 /* mechanical_saint_venant.py */,
+                   FOL_TRANSIENT_THERMAL = 5 /* transient_thermal.py */, FOL_ALLEN_CAHN = 6 /* phase_field.py */ };
 
 #define FOL_OK 0
 #define FOL_ERR_INVALID (-1)
@@ -46,7 +47,8 @@ enum fol_physics { FOL_MECHANICAL = 0, FOL_THERMAL = 1, FOL_NEOHOOKE = 2, FOL_J2
  *   [0] young_modulus  [1] poisson_ratio  [2..4] body force (mechanical.py:26 "body_foce")
  *   thermal: [5] beta  [6] c   (thermal.py:21-26)
  *   J2:      [5] yield_limit  [6] iso_hardening_parameter_1  [7] iso_hardening_param_2
- *            (mechanical_elastoplasticity.py:22-30)                                       */
+ *            (mechanical_elastoplasticity.py:22-30)
+ *   transient thermal: [5] beta [6] c [8] rho [9] cp [10] time_step;  Allen-Cahn: [10] dt [11] epsilon */
 
 const char* fol_last_error(void);
 int fol_version(void);
@@ -90,8 +92,10 @@ int fol_node_adjacency(fol_stream_t s, const int32_t* conn, int64_t ne, int nnod
 /* Element stage: gather -> ComputeElement -> optional transpose -> Dirichlet row mask, writes
  *   ke_data[e*nd*nd + i*nd + j] = Ke'[i,j]            (the BCOO `data`, fe_loss.py:299)
  *   re_elem[e*nd + i]           = re'[i]              (masked element residuals)
- * state_in/state_out: (ne, ngauss, 7|4) Gauss-point history, J2 only (else NULL).
- * u is the full dof vector (ndof), ctrl the nodal control field (nn). */
+ * state_in/state_out are the auxiliary input / output of the physics: J2: (ne, ngauss, 7|4) Gauss-point
+ * history in / out; transient thermal: state_in = nodal heterogeneity k0 (nn); transient thermal and
+ * Allen-Cahn: state_out = per-element energy (ne) or NULL, and (ctrl, u) = (current, next) nodal field.
+ * Otherwise NULL.  u is the full dof vector (ndof), ctrl the nodal control field (nn). */
 int fol_assemble_elements(fol_stream_t s, int dtype, int physics, int element, int num_gp,
                           int transpose, int64_t ne, int64_t nn, const void* xyz,
                           const int32_t* conn, const void* ctrl, const void* u,

@@ -68,6 +68,12 @@ def compute_elements(physics, element_type, num_gp, coords, conn, controls, dofs
     if physics == "thermal":
         return losses.thermal_element(element_type, num_gp, X, de, dofs[conn],
                                       params.get("beta", 0.0), params.get("c", 1.0))
+    if physics == "transient_thermal":      # (controls, dofs) = (current, next) temperatures
+        return losses.transient_thermal_element(element_type, num_gp, X, de, dofs[conn], params["k0"][conn],
+                                                params["rho"], params["cp"], params["time_step"],
+                                                params.get("beta", 0.0), params.get("c", 1.0))
+    if physics == "allen_cahn":             # (controls, dofs) = (current, next) phase field
+        return losses.allen_cahn_element(element_type, num_gp, X, de, dofs[conn], params["dt"], params["epsilon"])
     d = elem.dim
     u = dofs[element_dof_ids(conn, d)]
     if physics == "mechanical":
@@ -80,7 +86,7 @@ def compute_elements(physics, element_type, num_gp, coords, conn, controls, dofs
 
 
 def dofs_per_node(physics, element_type):
-    return 1 if physics == "thermal" else ELEMENTS[element_type].dim
+    return 1 if physics in ("thermal", "transient_thermal", "allen_cahn") else ELEMENTS[element_type].dim
 
 
 def assemble(physics, element_type, num_gp, coords, conn, controls, dofs, dirichlet_indices,

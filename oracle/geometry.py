@@ -154,13 +154,18 @@ def jacobian(elem, X, point):
     return np.swapaxes(np.einsum("aj,...ai->...ji", dN, Xd), -1, -2)
 
 
-def point_data(elem, X, order):
-    """Per Gauss point: N (g,a), gradN (..., g, a, dim), detJ (..., g), weights (g)."""
+def point_data(elem, X, order, transposed_inverse=False):
+    """Per Gauss point: N (g,a), gradN (..., g, a, dim), detJ (..., g), weights (g).
+    transposed_inverse=True reproduces `B_mat = invJ @ dN^T` of transient_thermal.py:57-58 and
+    phase_field.py:47-48 (the inverse Jacobian enters un-transposed there)."""
     pts, w = elem.gauss(order)
     Ns = np.stack([elem.N(p) for p in pts])
     grads, dets = [], []
     for p in pts:
         J = jacobian(elem, X, p)                      # (..., dim, dim)
-        grads.append(np.einsum("aj,...jk->...ak", elem.dN(p), np.linalg.inv(J)))
+        inv = np.linalg.inv(J)
+        if transposed_inverse:
+            inv = np.swapaxes(inv, -1, -2)
+        grads.append(np.einsum("aj,...jk->...ak", elem.dN(p), inv))
         dets.append(np.linalg.det(J))
     return Ns, np.stack(grads, axis=-3), np.stack(dets, axis=-1), w

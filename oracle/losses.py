@@ -252,3 +252,48 @@ def neo_hooke_energy_dcontrol(element_type, num_gp, X, de, u, nu, law="neohooke"
     else:
         psi1, _, _ = neo_hooke_point(F, one / (3.0 * (1.0 - 2.0 * nu)), one / (2.0 * (1.0 + nu)))
     return np.einsum("g,eg,eg,ga->ea", w, detJ, psi1, Ns)
+
+
+# ----------------------------------------------------------------------------- implicit-Euler scalar losses
+def transient_thermal_element(element_type, num_gp, X, Tc, Tn, k0, rho, cp, dt, beta, c):
+    """transient_thermal.py:42-73.  Tc / Tn: current / next nodal temperatures (ne, a); k0 nodal heterogeneity.
+    Returns (energy, re, Ke) with Ke = Me + dt * Se_dR (the linearisation of the conductivity included)."""
+    elem = ELEMENTS[element_type]
+    Ns, gradN, detJ, w = point_data(elem, X, num_gp, transposed_inverse=True)   # B_mat = invJ @ dN^T (:57-58)
+    wd = w[None, :] * detJ
+    Tn_g = np.einsum("ga,ea->eg", Ns, Tn)
+    Tc_g = np.einsum("ga,ea->eg", Ns, Tc)
+    k_g = np.einsum("ga,ea->eg", Ns, k0)
+    K_g = k_g * (1.0 + beta * Tn_g ** c)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dk = k_g * beta * c * Tn_g ** (c - 1.0)
+    dk = np.where(np.isfinite(dk), dk, 0.0)
+    BtB = np.einsum("egai,egbi->egab", gradN, gradN)
+    Se = np.einsum("eg,eg,egab->eab", K_g, wd, BtB)
+    Me = rho * cp * np.einsum("ga,gb,eg->eab", Ns, Ns, wd)
+    gT = np.einsum("egai,ea->egi", gradN, Tn)
+    gTB = np.einsum("egi,egbi->egb", gT, gradN)                   # (B Tn)^T B
+    Se_dR = np.einsum("eg,eg,ga,egb->eab", dk, wd, Ns, gTB) + Se
+    Te = rho * cp * 0.5 / dt * np.einsum("eg,eg->e", wd, (Tn_g - Tc_g) ** 2)
+    energy = 0.5 * np.einsum("ea,eab,eb->e", Tn, Se, Tn) + Te
+    re = np.einsum("eab,eb->ea", Me + dt * Se, Tn) - np.einsum("eab,eb->ea", Me, Tc)
+    return energy, re, Me + dt * Se_dR
+
+
+def allen_cahn_element(element_type, num_gp, X, pc, pn, dt, eps):
+    """phase_field.py:38-70."""
+    elem = ELEMENTS[element_type]
+    Ns, gradN, detJ, w = point_data(elem, X, num_gp, transposed_inverse=True)   # B_mat = invJ @ dN^T (:47-48)
+    wd = w[None, :] * detJ
+    pn_g = np.einsum("ga,ea->eg", Ns, pn)
+    pc_g = np.einsum("ga,ea->eg", Ns, pc)
+    Se = np.einsum("eg,egai,egbi->eab", wd, gradN, gradN)
+    NN = np.einsum("ga,gb->gab", Ns, Ns)
+    Me = np.einsum("gab,eg->eab", NN, wd)
+    Fe = np.einsum("eg,eg->e", wd, 0.25 * (pn_g ** 2 - 1.0) ** 2)
+    Fe_res = np.einsum("ga,eg,eg->ea", Ns, (pn_g ** 2 - 1.0) * pn_g, wd)
+    Te = 0.5 / dt * np.einsum("eg,eg->e", wd, (pn_g - pc_g) ** 2)
+    dFe = np.einsum("gab,eg,eg->eab", NN, 3.0 * pn_g ** 2 - 1.0, wd)
+    energy = 0.5 * np.einsum("ea,eab,eb->e", pn, Se, pn) + Fe / eps ** 2 + Te
+    re = np.einsum("eab,eb->ea", Me + dt * Se, pn) - (np.einsum("eab,eb->ea", Me, pc) - dt / eps ** 2 * Fe_res)
+    return energy, re, Me + dt * Se - dt / eps ** 2 * dFe

@@ -136,3 +136,34 @@ def test_global_assembly_dirichlet_transpose_golden(goldens):
         off = dense[r].copy()
         off[r] = 0.0
         assert np.all(off == 0.0) and dense[r, r] != 0.0
+
+
+TT = "tests/unit/test_nonlinear_transient_thermal.py"
+AC = "tests/unit/test_allencahn_loss.py"
+
+
+@pytest.mark.parametrize("test,etype,num_gp,coords", [
+    ("test_tetra", "tetra", 1, "tet_points_coordinates"), ("test_hexa", "hexahedron", 2, "hex_points_coordinates"),
+    ("test_tri", "triangle", 1, "tri_points_coordinates"), ("test_quad", "quad", 2, "quad_points_coordinates")])
+def test_transient_thermal_goldens(goldens, test, etype, num_gp, coords):
+    """test_nonlinear_transient_thermal.py:26-165: rho=cp=1, beta=1.5, c=1, dt=0.005, Tc=1, Tn=0, k0=1."""
+    rec = goldens[TT][test]
+    X = np.array(rec["assign"][coords], float)[None]
+    a = X.shape[1]
+    en, re, Ke = losses.transient_thermal_element(etype, num_gp, X, np.ones((1, a)), np.zeros((1, a)),
+                                                  np.ones((1, a)), 1.0, 1.0, 0.005, 1.5, 1.0)
+    _check(Ke[0], rec["asserts"][0])
+    _check(re[0], rec["asserts"][1])
+
+
+@pytest.mark.parametrize("test,etype,num_gp,coords", [
+    ("test_hexa", "hexahedron", 2, "hex_points_coordinates"), ("test_tri", "triangle", 1, "tri_points_coordinates"),
+    ("test_quad", "quad", 2, "quad_points_coordinates")])
+def test_allen_cahn_goldens(goldens, test, etype, num_gp, coords):
+    """test_allencahn_loss.py:19-105: dt=0.001, epsilon=0.2, phi_c=1, phi_n=0."""
+    rec = goldens[AC][test]
+    X = np.array(rec["assign"][coords], float)[None]
+    a = X.shape[1]
+    en, re, Ke = losses.allen_cahn_element(etype, num_gp, X, np.ones((1, a)), np.zeros((1, a)), 0.001, 0.2)
+    _check(Ke[0].reshape(-1), rec["asserts"][0])
+    _check(re[0], rec["asserts"][1])
