@@ -23,7 +23,7 @@ int assemble_hex_mech_f64(cudaStream_t, const AsmArgs<double>&);
 extern std::atomic<int> g_grid_margin;
 
 template <class T>
-int energy_and_grads(cudaStream_t, int, int, int, const EnergyArgs<T>&, T*);
+int energy_and_grads(cudaStream_t, int, int, int, const EnergyArgs<T>&, int, T*);
 template <class T>
 int geometry_cache(cudaStream_t, int, int, long long, const T*, const int32_t*, T*);
 template <class T>
@@ -152,34 +152,35 @@ int fol_geometry_cache(fol_stream_t s, int dtype, int element, int num_gp, int64
   return geometry_cache<float>((cudaStream_t)s, element, num_gp, ne, (const float*)xyz, conn, (float*)geom);
 }
 
-int64_t fol_energy_work_size(int64_t ntiles, int64_t nb) { return ntiles * nb + 16; }
+int64_t fol_energy_work_size(int64_t ntiles, int64_t nb) { return ntiles * nb * 10 + 16; }  // <= 10 warps per tile
 
 int fol_energy_and_grads(fol_stream_t s, int dtype, int physics, int element, int num_gp, int64_t ne, int64_t nn,
                          int64_t nb, const void* geom, const int32_t* conn, const int32_t* adj_ptr,
                          const int32_t* adj_local, const int32_t* tile_node_ptr, const int32_t* tile_nodes,
                          const int32_t* tile_elem_ptr, const int32_t* tile_elems, const int32_t* tile_conn,
                          const int32_t* tile_lnode_ptr, const int32_t* tile_lnodes, int64_t ntiles, int64_t ecap,
-                         int64_t lcap, const void* ctrl, const void* u, const double* params_host, void* grad_u, void* grad_k,
+                         int64_t lcap, int64_t ncap, const void* ctrl, const void* u, const double* params_host, void* grad_u,
+                         void* grad_k,
                          void* energy, void* work) {
   FOL_REQUIRE(valid_element(element), "fol_energy_and_grads: unknown element");
   FOL_REQUIRE(geom && conn && adj_ptr && adj_local && tile_node_ptr && tile_nodes && tile_elem_ptr && tile_elems &&
                   tile_conn && tile_lnode_ptr && tile_lnodes &&
                   ctrl && u && grad_u && energy && work && params_host,
               "fol_energy_and_grads: null pointer");
-  FOL_REQUIRE(nb >= 1 && ntiles >= 1 && ecap >= 1 && lcap >= 1, "fol_energy_and_grads: bad sizes");
+  FOL_REQUIRE(nb >= 1 && ntiles >= 1 && ecap >= 1 && lcap >= 1 && ncap >= 1, "fol_energy_and_grads: bad sizes");
   if (dtype == FOL_F64) {
     EnergyArgs<double> a{(const double*)geom, conn, adj_ptr, adj_local, tile_node_ptr, tile_nodes, tile_elem_ptr,
                          tile_elems, tile_conn, tile_lnode_ptr, tile_lnodes, (const double*)ctrl, (const double*)u,
                          (double*)grad_u, (double*)grad_k, (double*)work, ne, nn, nb, (int)ntiles, (int)ecap, (int)lcap,
                          make_params<double>(params_host)};
-    return energy_and_grads<double>((cudaStream_t)s, physics, element, num_gp, a, (double*)energy);
+    return energy_and_grads<double>((cudaStream_t)s, physics, element, num_gp, a, (int)ncap, (double*)energy);
   }
   FOL_REQUIRE(dtype == FOL_F32, "fol_energy_and_grads: bad dtype");
   EnergyArgs<float> a{(const float*)geom, conn, adj_ptr, adj_local, tile_node_ptr, tile_nodes, tile_elem_ptr,
                       tile_elems, tile_conn, tile_lnode_ptr, tile_lnodes, (const float*)ctrl, (const float*)u,
                       (float*)grad_u, (float*)grad_k, (float*)work, ne, nn, nb, (int)ntiles, (int)ecap, (int)lcap,
                       make_params<float>(params_host)};
-  return energy_and_grads<float>((cudaStream_t)s, physics, element, num_gp, a, (float*)energy);
+  return energy_and_grads<float>((cudaStream_t)s, physics, element, num_gp, a, (int)ncap, (float*)energy);
 }
 
 int fol_loss_reduce(fol_stream_t s, int dtype, int64_t nb, double exponent, const void* energy, void* out4,

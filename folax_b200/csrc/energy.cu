@@ -40,19 +40,33 @@ int dispatch_energy(cudaStream_t s, int element, int num_gp, const EnergyArgs<T>
 }
 
 template <class T>
-int energy_and_grads(cudaStream_t s, int physics, int element, int num_gp, const EnergyArgs<T>& a, T* energy) {
-  int rc;
-  if (physics == FOL_MECHANICAL) rc = dispatch_energy<T, MECH>(s, element, num_gp, a);
-  else if (physics == FOL_THERMAL) rc = dispatch_energy<T, THERMAL>(s, element, num_gp, a);
-  else if (physics == FOL_NEOHOOKE) rc = dispatch_energy<T, NEOHOOKE>(s, element, num_gp, a);
-  else if (physics == FOL_STVENANT) rc = dispatch_energy<T, STVK>(s, element, num_gp, a);
-  else return fail(FOL_ERR_UNSUPPORTED, "fol_energy_and_grads: physics not supported");
+int energy2_thermal(cudaStream_t, int, int, const EnergyArgs<T>&, int, int*);
+template <class T>
+int energy2_mech(cudaStream_t, int, int, int, const EnergyArgs<T>&, int, int*);
+
+// The pipelined kernel (energy2.cuh) runs when the plan fits it, energy_tile_kernel otherwise.
+// npart = energy shares per sample written by the kernel that ran (pipelined kernel: one per warp)
+template <class T>
+int energy_and_grads(cudaStream_t s, int physics, int element, int num_gp, const EnergyArgs<T>& a, int ncap, T* energy) {
+  if (a.ntiles == 0 || a.nb == 0) return FOL_OK;
+  int parts = 1;
+  int rc = (physics == FOL_THERMAL) ? energy2_thermal<T>(s, element, num_gp, a, ncap, &parts)
+                                    : energy2_mech<T>(s, physics, element, num_gp, a, ncap, &parts);
+  if (rc == 1) {
+    parts = 1;
+    if (physics == FOL_MECHANICAL) rc = dispatch_energy<T, MECH>(s, element, num_gp, a);
+    else if (physics == FOL_THERMAL) rc = dispatch_energy<T, THERMAL>(s, element, num_gp, a);
+    else if (physics == FOL_NEOHOOKE) rc = dispatch_energy<T, NEOHOOKE>(s, element, num_gp, a);
+    else if (physics == FOL_STVENANT) rc = dispatch_energy<T, STVK>(s, element, num_gp, a);
+    else return fail(FOL_ERR_UNSUPPORTED, "fol_energy_and_grads: physics not supported");
+  }
+  const int npart = a.ntiles * parts;
   if (rc) return rc;
-  energy_sum_kernel<T><<<(unsigned)cdiv(a.nb, 8), 256, 0, s>>>(a.partial, a.nb, a.ntiles, energy);
+  energy_sum_kernel<T><<<(unsigned)cdiv(a.nb, 8), 256, 0, s>>>(a.partial, a.nb, npart, energy);
   return check_launch("energy_sum_kernel");
 }
-template int energy_and_grads<double>(cudaStream_t, int, int, int, const EnergyArgs<double>&, double*);
-template int energy_and_grads<float>(cudaStream_t, int, int, int, const EnergyArgs<float>&, float*);
+template int energy_and_grads<double>(cudaStream_t, int, int, int, const EnergyArgs<double>&, int, double*);
+template int energy_and_grads<float>(cudaStream_t, int, int, int, const EnergyArgs<float>&, int, float*);
 
 template <class T, int ELEM>
 int launch_geom(cudaStream_t s, int num_gp, long long ne, const T* xyz, const int32_t* conn, T* geom) {

@@ -1,13 +1,17 @@
 """Integer tile plan of the fused batched-loss kernel (host side, built once per mesh).
 
-Nodes are ordered along a Morton (Z-order) curve of their coordinates and cut into tiles of at
-most TILE_NODES nodes, so every tile is a compact patch; per tile the plan lists the elements
-touching it and re-expresses the node->element adjacency in tile-local element indices.  Pure
-integer work, deterministic; the adjacency order equals fol_node_adjacency's (ascending e*A + a).
+Nodes are split into compact tiles of at most TILE_NODES nodes by recursive coordinate bisection
+(balanced: every tile holds about nn / ntiles nodes; the cut axis is the longest extent of the
+current box), so every tile is a compact patch; per tile the plan lists the elements touching it
+and re-expresses the node->element adjacency in tile-local element indices.  Pure integer work,
+deterministic; the adjacency order equals fol_node_adjacency's (ascending e*A + a).
+`max_elems` bounds the longest per-tile element list (the kernel's one-thread-per-element fast path
+needs it <= its block size): the node target is lowered until the bound holds.
 """
 import numpy as np
 
-TILE_NODES = 128
+TILE_NODES = 160
+MAX_ELEMS = 192     # block size of the pipelined kernel (csrc/energy2_launch.cuh: ENERGY2_BLOCK)
 
 
 def _morton_keys(coords, bits=16):
@@ -22,22 +26,79 @@ def _morton_keys(coords, bits=16):
     return key
 
 
-def build(coords, conn, tile_nodes=TILE_NODES):
+def _rcb_tiles(coords, tile_nodes):
+    """tile id per node: recursive coordinate bisection into ceil(nn / tile_nodes) balanced leaves."""
+    X = np.asarray(coords, dtype=np.float64)
+    nn = len(X)
+    tile_of_node = np.zeros(nn, dtype=np.int64)
+    ntiles = max(1, -(-nn // tile_nodes))
+    stack = [(np.arange(nn), ntiles, 0)]
+    while stack:
+        idx, k, first = stack.pop()
+        if k == 1:
+            tile_of_node[idx] = first
+            continue
+        k1 = k // 2
+        n1 = int(round(len(idx) * k1 / k))
+        n1 = min(k1 * tile_nodes, max(len(idx) - (k - k1) * tile_nodes, n1))
+        P = X[idx]
+        axis = int(np.argmax(P.max(0) - P.min(0))) if len(idx) else 0
+        order = np.argsort(P[:, axis], kind="stable")                 # ties: ascending node id
+        stack.append((idx[order[:n1]], k1, first))
+        stack.append((idx[order[n1:]], k - k1, first + k1))
+    return tile_of_node, ntiles
+
+
+def _recompute(plan, ne):
+    return float(plan["tile_elem_ptr"][-1]) / max(ne, 1)
+
+
+def build(coords, conn, tile_nodes=TILE_NODES, max_elems=MAX_ELEMS, method="rcb", generic_max_elems=None):
     """Returns dict of int32 arrays: adj_ptr, adj_local, tile_node_ptr, tile_nodes, tile_elem_ptr,
-    tile_elems and ints ntiles, ecap."""
+    tile_elems, tile_conn, tile_lnode_ptr, tile_lnodes and ints ntiles, ecap, lcap, ncap (longest
+    per-tile element / local-node / owned-node list).
+    max_elems: bound wanted by the pipelined kernel (one thread per tile element; None = not applicable).
+    The bounded plan is kept unless its smaller tiles recompute clearly more border elements than the
+    unbounded one (3-D / high-valence meshes); the generic kernel then loops over the element list, which
+    only has to fit its shared-memory rows (generic_max_elems)."""
+    ne = len(conn)
+    target, generic = tile_nodes, None
+    for _ in range(12):
+        generic = _build(coords, conn, target, method)
+        if generic_max_elems is None or generic["ecap"] <= generic_max_elems or target <= 4:
+            break
+        target = max(4, min(target - 1, int(target * generic_max_elems / generic["ecap"])))
+    if max_elems is None or generic["ecap"] <= max_elems:
+        return generic
+    target = tile_nodes
+    for _ in range(10):
+        target = max(4, min(target - 1, int(target * max_elems / generic["ecap"] if target == tile_nodes
+                                            else target * max_elems / plan["ecap"])))
+        plan = _build(coords, conn, target, method)
+        if plan["ecap"] <= max_elems:
+            return plan if _recompute(plan, ne) <= 1.15 * _recompute(generic, ne) else generic
+        if target <= 4:
+            break
+    return generic
+
+
+def _build(coords, conn, tile_nodes, method):
     conn = np.asarray(conn, dtype=np.int64)
     ne, A = conn.shape
     nn = len(coords)
-    morton = np.argsort(_morton_keys(coords), kind="stable")         # compact tiles: cut the Z-curve
-    tile_of_node = np.empty(nn, dtype=np.int64)
-    tile_of_node[morton] = np.arange(nn) // tile_nodes
+    if method == "rcb":
+        tile_of_node, ntiles = _rcb_tiles(coords, tile_nodes)
+    else:
+        morton = np.argsort(_morton_keys(coords), kind="stable")     # compact tiles: cut the Z-curve
+        tile_of_node = np.empty(nn, dtype=np.int64)
+        tile_of_node[morton] = np.arange(nn) // tile_nodes
+        ntiles = int((nn + tile_nodes - 1) // tile_nodes)
     # inside a tile, nodes are kept in ascending global id: neighbouring threads then touch
     # neighbouring addresses (coalesced gradient writes, conflict-free shared-memory gathers)
     order = np.lexsort((np.arange(nn), tile_of_node))
     rank = np.empty(nn, dtype=np.int64)
     rank[order] = np.arange(nn)
-    ntiles = int((nn + tile_nodes - 1) // tile_nodes)
-    tile_node_ptr = np.minimum(np.arange(ntiles + 1, dtype=np.int64) * tile_nodes, nn)
+    tile_node_ptr = np.concatenate([[0], np.cumsum(np.bincount(tile_of_node, minlength=ntiles))])
     # adjacency sorted by node, then by e*A + a (stable sort keeps ascending entry ids)
     flat_nodes = conn.reshape(-1)
     entries = np.argsort(flat_nodes, kind="stable")                   # values: e*A + a
@@ -79,4 +140,5 @@ def build(coords, conn, tile_nodes=TILE_NODES):
     return {"adj_ptr": i32(adj_ptr), "adj_local": i32(adj_local), "tile_node_ptr": i32(tile_node_ptr),
             "tile_nodes": i32(order), "tile_elem_ptr": i32(tile_elem_ptr), "tile_elems": i32(tile_elems),
             "tile_conn": i32(tile_conn), "tile_lnode_ptr": i32(tile_lnode_ptr), "tile_lnodes": i32(tile_lnodes),
-            "ntiles": ntiles, "ecap": max(ecap, 1), "lcap": max(lcap, 1)}
+            "ntiles": ntiles, "ecap": max(ecap, 1), "lcap": max(lcap, 1),
+            "ncap": max(int(np.diff(tile_node_ptr).max()) if ntiles else 1, 1)}

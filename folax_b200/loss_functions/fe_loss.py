@@ -331,8 +331,21 @@ class FiniteElementLoss(Loss):
         """Device-resident integer tile plan of the fused batched-loss kernel (energy_plan.py)."""
         if self.__dict__.get("_eplan") is None:
             from .. import energy_plan
+            import os
+            # rows of the generic kernel's shared memory: S samples x KW element-vector rows x ecap (energy.cu)
+            nd = self._nnode * self.number_dofs_per_node
+            kw_rows = nd + (self._nnode if self._has_control_gradient else 0) + 1
+            samples = 4 if nd <= 8 else 2
+            kw = {"generic_max_elems": int(150 * 1024 / (torch.empty(0, dtype=self.dtype).element_size() * samples * kw_rows))}
+            # the pipelined kernel exists where the geometry factors fit in registers (energy.cuh: geom_in_regs)
+            if (self.element_type, self.num_gp) not in (("quad", 1), ("quad", 2), ("triangle", 1), ("triangle", 2),
+                                                        ("tetra", 1), ("hexahedron", 1)):
+                kw["max_elems"] = None
+            if "FOL_ENERGY_MAX_ELEMS" in os.environ:      # tuning experiments only (scripts/energy_sweep.sh)
+                kw.update(max_elems=int(os.environ["FOL_ENERGY_MAX_ELEMS"]),
+                          tile_nodes=int(os.environ.get("FOL_ENERGY_TILE_NODES", energy_plan.TILE_NODES)))
             plan = energy_plan.build(np.asarray(self.fe_mesh.GetNodesCoordinates()),
-                                     self.fe_mesh.GetElementsNodes(self.element_type))
+                                     self.fe_mesh.GetElementsNodes(self.element_type), **kw)
             self._eplan = {k: (torch.as_tensor(v, device=self.device) if isinstance(v, np.ndarray) else v)
                            for k, v in plan.items()}
         return self._eplan
@@ -362,7 +375,7 @@ class FiniteElementLoss(Loss):
                                             _lib.ptr(ep["tile_nodes"]), _lib.ptr(ep["tile_elem_ptr"]),
                                             _lib.ptr(ep["tile_elems"]), _lib.ptr(ep["tile_conn"]),
                                             _lib.ptr(ep["tile_lnode_ptr"]), _lib.ptr(ep["tile_lnodes"]), ep["ntiles"],
-                                            ep["ecap"], ep["lcap"],
+                                            ep["ecap"], ep["lcap"], ep["ncap"],
                                             _lib.ptr(batch_params), _lib.ptr(batch_dofs), self._params,
                                             _lib.ptr(grad_u), _lib.ptr(grad_k), _lib.ptr(energy), _lib.ptr(work)))
         return energy, grad_u, grad_k

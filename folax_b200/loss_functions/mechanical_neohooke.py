@@ -38,7 +38,7 @@ class NeoHookeMechanicalLoss(MechanicalLoss):
                                             _lib.ptr(ep["tile_node_ptr"]), _lib.ptr(ep["tile_nodes"]),
                                             _lib.ptr(ep["tile_elem_ptr"]), _lib.ptr(ep["tile_elems"]), _lib.ptr(ep["tile_conn"]),
                                             _lib.ptr(ep["tile_lnode_ptr"]), _lib.ptr(ep["tile_lnodes"]), ep["ntiles"],
-                                            ep["ecap"], ep["lcap"], _lib.ptr(ctrl), _lib.ptr(u), self._params, _lib.ptr(gu),
+                                            ep["ecap"], ep["lcap"], ep["ncap"], _lib.ptr(ctrl), _lib.ptr(u), self._params, _lib.ptr(gu),
                                             _lib.ptr(gk), _lib.ptr(energy), _lib.ptr(work)))
         return energy[0]
 

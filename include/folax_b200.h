@@ -137,7 +137,9 @@ int fol_geometry_cache(fol_stream_t s, int dtype, int element, int num_gp, int64
  *   adj_local: per adjacency entry (index of the element within the node's tile list)*nnode + a
  *   tile_lnode_ptr / tile_lnodes: per tile, the nodes its elements touch (the tile's own nodes first,
  *   in tile order); tile_conn (len(tile_elems), nnode): element nodes in that tile-local numbering
- *   ecap / lcap: the longest tile element list / local node list.
+ *   ecap / lcap / ncap: the longest tile element list / local node list / owned node list.
+ * Plans whose element lists fit one thread per element (ecap, ncap <= 160) and whose geometry factors
+ * fit in registers run the pipelined kernel (csrc/energy2.cuh), the others energy_tile_kernel.
  * `work` is scratch of fol_energy_work_size(ntiles, nb) elements of the call's dtype. */
 int64_t fol_energy_work_size(int64_t ntiles, int64_t nb);
 int fol_energy_and_grads(fol_stream_t s, int dtype, int physics, int element, int num_gp,
@@ -147,7 +149,7 @@ int fol_energy_and_grads(fol_stream_t s, int dtype, int physics, int element, in
                          const int32_t* tile_elem_ptr, const int32_t* tile_elems,
                          const int32_t* tile_conn, const int32_t* tile_lnode_ptr,
                          const int32_t* tile_lnodes, int64_t ntiles, int64_t ecap, int64_t lcap,
-                         const void* ctrl, const void* u, const double* params_host,
+                         int64_t ncap, const void* ctrl, const void* u, const double* params_host,
                          void* grad_u, void* grad_k, void* energy, void* work);
 
 /* loss tail: L = mean_b E_b^p, stats = (min, max, mean) of E_b^p, scale[b] = p E_b^(p-1)/nb.
