@@ -29,7 +29,7 @@ int geometry_cache(cudaStream_t, int, int, long long, const T*, const int32_t*, 
 template <class T>
 int loss_reduce(cudaStream_t, long long, double, const T*, T*, T*);
 template <class T>
-int scale_grads(cudaStream_t, long long, long long, long long, const T*, double, const uint8_t*, T*, T*);
+int scale_grads(cudaStream_t, long long, long long, long long, const T*, double, const T*, int, const uint8_t*, T*, T*);
 
 static bool valid_element(int e) { return e >= 0 && e <= 3; }
 static std::atomic<int> g_tuned{1};
@@ -159,7 +159,8 @@ int fol_energy_and_grads(fol_stream_t s, int dtype, int physics, int element, in
                          const int32_t* adj_local, const int32_t* tile_node_ptr, const int32_t* tile_nodes,
                          const int32_t* tile_elem_ptr, const int32_t* tile_elems, const int32_t* tile_conn,
                          const int32_t* tile_lnode_ptr, const int32_t* tile_lnodes, int64_t ntiles, int64_t ecap,
-                         int64_t lcap, int64_t ncap, const void* ctrl, const void* u, const double* params_host, void* grad_u,
+                         int64_t lcap, int64_t ncap, const void* ctrl, const void* u, const void* dir_values,
+                         const uint8_t* dir_flag, double out_scale, const double* params_host, void* grad_u,
                          void* grad_k,
                          void* energy, void* work) {
   FOL_REQUIRE(valid_element(element), "fol_energy_and_grads: unknown element");
@@ -171,14 +172,16 @@ int fol_energy_and_grads(fol_stream_t s, int dtype, int physics, int element, in
   if (dtype == FOL_F64) {
     EnergyArgs<double> a{(const double*)geom, conn, adj_ptr, adj_local, tile_node_ptr, tile_nodes, tile_elem_ptr,
                          tile_elems, tile_conn, tile_lnode_ptr, tile_lnodes, (const double*)ctrl, (const double*)u,
-                         (double*)grad_u, (double*)grad_k, (double*)work, ne, nn, nb, (int)ntiles, (int)ecap, (int)lcap,
+                         (double*)grad_u, (double*)grad_k, (double*)work, (const double*)dir_values, dir_flag, out_scale,
+                         ne, nn, nb, (int)ntiles, (int)ecap, (int)lcap,
                          make_params<double>(params_host)};
     return energy_and_grads<double>((cudaStream_t)s, physics, element, num_gp, a, (int)ncap, (double*)energy);
   }
   FOL_REQUIRE(dtype == FOL_F32, "fol_energy_and_grads: bad dtype");
   EnergyArgs<float> a{(const float*)geom, conn, adj_ptr, adj_local, tile_node_ptr, tile_nodes, tile_elem_ptr,
                       tile_elems, tile_conn, tile_lnode_ptr, tile_lnodes, (const float*)ctrl, (const float*)u,
-                      (float*)grad_u, (float*)grad_k, (float*)work, ne, nn, nb, (int)ntiles, (int)ecap, (int)lcap,
+                      (float*)grad_u, (float*)grad_k, (float*)work, (const float*)dir_values, dir_flag, (float)out_scale,
+                      ne, nn, nb, (int)ntiles, (int)ecap, (int)lcap,
                       make_params<float>(params_host)};
   return energy_and_grads<float>((cudaStream_t)s, physics, element, num_gp, a, (int)ncap, (float*)energy);
 }
@@ -192,13 +195,14 @@ int fol_loss_reduce(fol_stream_t s, int dtype, int64_t nb, double exponent, cons
 }
 
 int fol_scale_grads(fol_stream_t s, int dtype, int64_t nb, int64_t ndof, int64_t nn, const void* scale,
-                    double upstream, const uint8_t* dir_flag, void* grad_u, void* grad_k) {
+                    double upstream, const void* upstream_dev, int prescaled, const uint8_t* dir_flag, void* grad_u,
+                    void* grad_k) {
   FOL_REQUIRE(scale && dir_flag && grad_u, "fol_scale_grads: null pointer");
   if (dtype == FOL_F64)
-    return scale_grads<double>((cudaStream_t)s, nb, ndof, nn, (const double*)scale, upstream, dir_flag,
-                               (double*)grad_u, (double*)grad_k);
-  return scale_grads<float>((cudaStream_t)s, nb, ndof, nn, (const float*)scale, upstream, dir_flag, (float*)grad_u,
-                            (float*)grad_k);
+    return scale_grads<double>((cudaStream_t)s, nb, ndof, nn, (const double*)scale, upstream,
+                               (const double*)upstream_dev, prescaled, dir_flag, (double*)grad_u, (double*)grad_k);
+  return scale_grads<float>((cudaStream_t)s, nb, ndof, nn, (const float*)scale, upstream, (const float*)upstream_dev,
+                            prescaled, dir_flag, (float*)grad_u, (float*)grad_k);
 }
 
 // ---- plan ------------------------------------------------------------------------------------

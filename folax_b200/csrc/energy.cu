@@ -104,17 +104,15 @@ template int loss_reduce<double>(cudaStream_t, long long, double, const double*,
 template int loss_reduce<float>(cudaStream_t, long long, double, const float*, float*, float*);
 
 template <class T>
-int scale_grads(cudaStream_t s, long long nb, long long ndof, long long nn, const T* scale, double up,
-                const uint8_t* dir, T* gu, T* gk) {
-  const long long m = ndof > nn ? ndof : nn;
-  dim3 grid((unsigned)cdiv(m, 256), (unsigned)nb);
-  if (grid.x == 0 || grid.y == 0) return FOL_OK;
-  scale_grads_kernel<T><<<grid, 256, 0, s>>>(nb, ndof, nn, scale, (T)up, dir, gu, gk);
+int scale_grads(cudaStream_t s, long long nb, long long ndof, long long nn, const T* scale, double up, const T* up_dev,
+                int prescaled, const uint8_t* dir, T* gu, T* gk) {
+  if (nb == 0 || (ndof == 0 && nn == 0)) return FOL_OK;
+  scale_grads_kernel<T><<<148 * 8, 256, 0, s>>>(nb, ndof, nn, scale, (T)up, up_dev, prescaled, dir, gu, gk);
   return check_launch("scale_grads_kernel");
 }
-template int scale_grads<double>(cudaStream_t, long long, long long, long long, const double*, double, const uint8_t*,
-                                 double*, double*);
-template int scale_grads<float>(cudaStream_t, long long, long long, long long, const float*, double, const uint8_t*,
-                                float*, float*);
+template int scale_grads<double>(cudaStream_t, long long, long long, long long, const double*, double, const double*, int,
+                                 const uint8_t*, double*, double*);
+template int scale_grads<float>(cudaStream_t, long long, long long, long long, const float*, double, const float*, int,
+                                const uint8_t*, float*, float*);
 
 }  // namespace fol

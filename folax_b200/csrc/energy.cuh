@@ -38,7 +38,12 @@ struct EnergyArgs {
   const T* u;                 // (nb, ndof)
   T* grad_u;                  // (nb, ndof)
   T* grad_k;                  // (nb, nn) or null
-  T* partial;                 // (nb, ntiles) per-tile energy shares
+  T* partial;                 // (nb, ntiles [* warps]) per-tile energy shares
+  const T* dir_values;        // (ndof) Dirichlet value per dof, NaN where free: overwrites u while staging
+                              //        (fe_loss.py:91-92, 255), or null
+  const uint8_t* dir_flag;    // (ndof) 1 where grad_u is to be written as zero (the cotangent is cut at the
+                              //        overwritten entries), or null
+  T out_scale;                // grad_u / grad_k are written multiplied by this (1/nb when the exponent is 1)
   long long ne, nn, nb;
   int ntiles, ecap, lcap;     // tiles, max elements per tile, max local nodes per tile (shared-memory rows)
   Params<T> p;
@@ -356,6 +361,20 @@ energy_tile_kernel(const EnergyArgs<T> args) {
   for (; b0 < args.nb; b0 += bstep, buf ^= 1) {
     const int ns = (args.nb - b0 < S) ? (int)(args.nb - b0) : S;
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    if (args.dir_values) {   // Dirichlet overwrite of the rows this thread staged (its own copies have landed)
+      T* dst0 = stage + (size_t)buf * S * C * lcap;
+      for (int l = threadIdx.x; l < n_ln; l += BLOCK) {
+        const long long gn = __ldg(args.tile_lnodes + l_beg + l);
+#pragma unroll
+        for (int k = 0; k < DPN; ++k) {
+          const T dv = __ldg(args.dir_values + gn * DPN + k);
+          if (dv == dv) {
+#pragma unroll
+            for (int sidx = 0; sidx < S; ++sidx) dst0[(sidx * C + k) * lcap + l] = dv;
+          }
+        }
+      }
+    }
     __syncthreads();   // this pass's rows are visible; everyone is done with the previous pass's sv / rows
     if (b0 + bstep < args.nb) stage_pass(buf ^ 1, b0 + bstep);
     const T* st0 = stage + (size_t)buf * S * C * lcap;
@@ -425,10 +444,11 @@ energy_tile_kernel(const EnergyArgs<T> args) {
           for (int k = 0; k < DPN; ++k) {
             // E_b = u_b . R_b (mechanical.py:116-117, thermal.py:45-49); u from the staged rows
             if constexpr (!finite_strain(PHYS)) en[s] += st0[(s * C + k) * lcap + threadIdx.x] * R[s][k];
-            args.grad_u[bb * ndof + (long long)n * DPN + k] = R[s][k];
+            const bool cut = args.dir_flag && args.dir_flag[(long long)n * DPN + k];
+            args.grad_u[bb * ndof + (long long)n * DPN + k] = cut ? (T)0 : args.out_scale * R[s][k];
           }
           if constexpr (PHYS != MECH) {
-            if (args.grad_k) args.grad_k[bb * args.nn + n] = dk[s];
+            if (args.grad_k) args.grad_k[bb * args.nn + n] = args.out_scale * dk[s];
           }
         }
       }
@@ -498,15 +518,24 @@ __global__ void loss_reduce_kernel(long long nb, double exponent, const T* __res
   }
 }
 
+// backward of the batched loss: grad_u[b,:] *= sc_b (zero at Dirichlet dofs), grad_k[b,:] *= sc_b with
+// sc_b = upstream * (*upstream_dev) * (prescaled ? 1 : scale[b]).  When the forward pass already wrote the
+// gradients with their final scale (exponent 1) and the upstream cotangent is 1, there is nothing to do.
 template <class T>
 __global__ void scale_grads_kernel(long long nb, long long ndof, long long nn, const T* __restrict__ scale,
-                                   T upstream, const uint8_t* __restrict__ dir, T* __restrict__ grad_u,
+                                   T upstream, const T* __restrict__ upstream_dev, int prescaled,
+                                   const uint8_t* __restrict__ dir, T* __restrict__ grad_u,
                                    T* __restrict__ grad_k) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long b = blockIdx.y;
-  const T sc = upstream * scale[b];
-  if (i < ndof) grad_u[b * ndof + i] = dir[i] ? (T)0 : sc * grad_u[b * ndof + i];
-  if (grad_k && i < nn) grad_k[b * nn + i] = sc * grad_k[b * nn + i];
+  const T up = upstream * (upstream_dev ? *upstream_dev : (T)1);
+  if (prescaled && up == (T)1) return;
+  const long long m = ndof > nn ? ndof : nn;
+  const long long chunks = (m + blockDim.x - 1) / blockDim.x;
+  for (long long w = blockIdx.x; w < chunks * nb; w += gridDim.x) {
+    const long long b = w / chunks, i = (w - b * chunks) * blockDim.x + threadIdx.x;
+    const T sc = up * (prescaled ? (T)1 : scale[b]);
+    if (i < ndof) grad_u[b * ndof + i] = dir[i] ? (T)0 : sc * grad_u[b * ndof + i];
+    if (grad_k && i < nn) grad_k[b * nn + i] = sc * grad_k[b * nn + i];
+  }
 }
 
 }  // namespace fol

@@ -94,16 +94,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) energy_tile2_kernel(const EnergyA
   const int n = has_node ? __ldg(args.tile_nodes + n_beg + lnode) : 0;
   const int a_beg = has_node ? __ldg(args.adj_ptr + n) : 0, a_end = has_node ? __ldg(args.adj_ptr + n + 1) : 0;
   const int cnt = a_end - a_beg;
-  int off[MAXADJ], offk[MAXADJ];
+  // off: row of the entry's first dof; the dK row is off + ND * BLOCK for one dof per node, else kept in offk
+  constexpr int NK = (DPN == 1 || PHYS == MECH) ? 1 : MAXADJ;
+  int off[MAXADJ], offk[NK];
   unsigned first_mask = 0;                  // entries whose local node is 0: they carry the element's strain energy
 #pragma unroll
   for (int i = 0; i < MAXADJ; ++i) {
-    off[i] = offk[i] = 0;
+    off[i] = 0;
+    if (i < NK) offk[i] = 0;
     if (i < cnt) {
       const int ja = __ldg(args.adj_local + a_beg + i);
       const int jl = ja / A, a = ja - jl * A;
       off[i] = jl + a * DPN * BLOCK;
-      offk[i] = jl + (ND + a) * BLOCK;
+      if constexpr (NK == MAXADJ) offk[i] = jl + (ND + a) * BLOCK;
       first_mask |= (a == 0 ? 1u : 0u) << i;
     }
   }
@@ -132,6 +135,31 @@ __global__ void __launch_bounds__(BLOCK, MINB) energy_tile2_kernel(const EnergyA
   int gnode[2];
 #pragma unroll
   for (int j = 0; j < 2; ++j) gnode[j] = (tid + j * BLOCK < n_ln) ? __ldg(args.tile_lnodes + l_beg + tid + j * BLOCK) : -1;
+  // Dirichlet values (NaN = free) of the rows this thread stages
+  T dval[2][DPN];
+  bool any_dir = false;
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int k = 0; k < DPN; ++k) {
+      dval[j][k] = (args.dir_values && gnode[j] >= 0) ? __ldg(args.dir_values + (long long)gnode[j] * DPN + k)
+                                                      : (T)NAN;
+      any_dir |= (dval[j][k] == dval[j][k]);
+    }
+  // Dirichlet overwrite (fe_loss.py:91-92, 255) of the rows this thread staged, once its own copies have landed
+  auto patch_pass = [&](int buf) {
+    if (!any_dir) return;
+    T* dst0 = stage + (size_t)buf * S * C * lcap + tid;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int k = 0; k < DPN; ++k) {
+        if (dval[j][k] == dval[j][k]) {
+#pragma unroll
+          for (int sidx = 0; sidx < S; ++sidx) dst0[(sidx * C + k) * lcap + j * BLOCK] = dval[j][k];
+        }
+      }
+  };
   auto stage_pass = [&](int buf, long long b0) {
     T* dst0 = stage + (size_t)buf * S * C * lcap + tid;
 #pragma unroll
@@ -156,6 +184,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) energy_tile2_kernel(const EnergyA
 #pragma unroll
     for (int k = 0; k < DPN; ++k) ukeep[s][k] = (T)0;
 
+  unsigned cut_mask = 0;                    // dofs of this node whose cotangent is cut (Dirichlet)
+  if (has_node && args.dir_flag) {
+#pragma unroll
+    for (int k = 0; k < DPN; ++k) cut_mask |= (args.dir_flag[(long long)n * DPN + k] ? 1u : 0u) << k;
+  }
   T* const gu_node = args.grad_u + (long long)n * DPN;
   T* const gk_node = args.grad_k ? args.grad_k + n : nullptr;
 
@@ -179,7 +212,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) energy_tile2_kernel(const EnergyA
         for (int s = 0; s < S; ++s) {
 #pragma unroll
           for (int k = 0; k < DPN; ++k) R[s][k] += svb[off[i] + (s * KW + k) * BLOCK];
-          if constexpr (PHYS != MECH) dk[s] += svb[offk[i] + (s * KW) * BLOCK];
+          if constexpr (PHYS != MECH) {
+            if constexpr (NK == MAXADJ) dk[s] += svb[offk[i] + (s * KW) * BLOCK];
+            else dk[s] += svb[off[i] + (s * KW + ND) * BLOCK];
+          }
           if constexpr (finite_strain(PHYS)) {
             // local node 0: off[i] is the element's column itself
             if ((first_mask >> i) & 1u) en[s] += svb[off[i] + (s * KW + ND + A) * BLOCK];
@@ -205,10 +241,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) energy_tile2_kernel(const EnergyA
           for (int k = 0; k < DPN; ++k) {
             // E_b = u_b . R_b (mechanical.py:116-117, thermal.py:45-49)
             if constexpr (!finite_strain(PHYS)) en[s] += ukeep[s][k] * R[s][k];
-            gu[k] = R[s][k];
+            gu[k] = ((cut_mask >> k) & 1u) ? (T)0 : args.out_scale * R[s][k];
           }
           if constexpr (PHYS != MECH) {
-            if (gk_node) gk_node[(b0 + s) * args.nn] = dk[s];
+            if (gk_node) gk_node[(b0 + s) * args.nn] = args.out_scale * dk[s];
           }
         }
       }
@@ -263,6 +299,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) energy_tile2_kernel(const EnergyA
   if (b0 >= args.nb) return;
   stage_pass(0, b0);
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  patch_pass(0);
   __syncthreads();
   // Between two barriers a warp owes phase B of the previous pass (latency-bound: shared-memory sums, shuffles,
   // stores) and phase A of this pass (FP64-bound).  Warps sharing a scheduler take them in opposite order, so one
@@ -290,6 +327,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) energy_tile2_kernel(const EnergyA
     }
     bprev = b0;
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    patch_pass(buf ^ 1);
     __syncthreads();   // sv[buf] complete and the next pass's rows visible; sv[buf^1] / stage[buf] free again
   }
   phase_b(sv + (buf ^ 1) * SVB, bprev, (args.nb - bprev < S) ? (int)(args.nb - bprev) : S);

@@ -75,7 +75,7 @@ ffi::Error EnergyAndGradsImpl(cudaStream_t stream, ffi::AnyBuffer geom, ffi::Buf
                               ffi::AnyBuffer ctrl, ffi::AnyBuffer u, ffi::Result<ffi::AnyBuffer> grad_u,
                               ffi::Result<ffi::AnyBuffer> grad_k, ffi::Result<ffi::AnyBuffer> energy,
                               ffi::Result<ffi::AnyBuffer> work, int32_t physics, int32_t element, int32_t num_gp,
-                              int64_t ecap, int64_t lcap, ffi::Span<const double> params) {
+                              int64_t ecap, int64_t lcap, int64_t ncap, ffi::Span<const double> params) {
   const int dt = DtypeOf(u.element_type());
   if (dt < 0) return ffi::Error::InvalidArgument("Unsupported data type for FFI call.");
   const int64_t ne = conn.dimensions()[0], nb = u.dimensions()[0], nn = ctrl.dimensions()[1];
@@ -84,8 +84,8 @@ ffi::Error EnergyAndGradsImpl(cudaStream_t stream, ffi::AnyBuffer geom, ffi::Buf
                                      conn.typed_data(), adj_ptr.typed_data(), adj_local.typed_data(),
                                      tile_node_ptr.typed_data(), tile_nodes.typed_data(), tile_elem_ptr.typed_data(),
                                      tile_elems.typed_data(), tile_conn.typed_data(), tile_lnode_ptr.typed_data(),
-                                     tile_lnodes.typed_data(), ntiles, ecap, lcap, ctrl.untyped_data(), u.untyped_data(),
-                                     params.begin(), grad_u->untyped_data(), grad_k->untyped_data(),
+                                     tile_lnodes.typed_data(), ntiles, ecap, lcap, ncap, ctrl.untyped_data(), u.untyped_data(),
+                                     /*dir_values=*/nullptr, /*dir_flag=*/nullptr, /*out_scale=*/1.0, params.begin(), grad_u->untyped_data(), grad_k->untyped_data(),
                                      energy->untyped_data(), work->untyped_data()));
 }
 
@@ -142,5 +142,6 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(FolEnergyAndGrads, EnergyAndGradsImpl,
                                   .Attr<int32_t>("num_gp")
                                   .Attr<int64_t>("ecap")
                                   .Attr<int64_t>("lcap")
+                                  .Attr<int64_t>("ncap")
                                   .Attr<ffi::Span<const double>>("params"));
 #endif  // FOLAX_HAVE_XLA_FFI

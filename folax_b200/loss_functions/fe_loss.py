@@ -42,12 +42,21 @@ class ElementInfo:
 
 class _BatchLossFn(torch.autograd.Function):
     """custom_vjp of ComputeBatchLoss: forward runs the fused energy+gradient kernel and the loss
-    tail, backward only rescales the saved (un-scaled) cotangents -- SURVEY.md A.7."""
+    tail, backward only rescales the saved cotangents -- SURVEY.md A.7.
+    fuse_dirichlet: `batch_dofs` are the raw dofs and the kernel overwrites the Dirichlet entries while it
+    stages them (fe_loss.py:91-92, 255) -- no full-dof copy is made.  With exponent 1 the kernel also writes the
+    cotangents with their final 1/B scale and zero Dirichlet entries, so backward is a no-op for an upstream
+    cotangent of 1 (decided on the device: no host synchronisation)."""
 
     @staticmethod
-    def forward(ctx, loss, batch_params, batch_dofs, mask_dirichlet=True):
+    def forward(ctx, loss, batch_params, batch_dofs, mask_dirichlet=True, fuse_dirichlet=False):
         ctx.mask_dirichlet = mask_dirichlet
-        energy, grad_u, grad_k = loss._energy_and_grads(batch_params, batch_dofs)
+        nb = batch_dofs.shape[0]
+        ctx.prescaled = float(loss.loss_function_exponent) == 1.0
+        energy, grad_u, grad_k = loss._energy_and_grads(
+            batch_params, batch_dofs, dir_values=loss._dir_full if fuse_dirichlet else None,
+            dir_flag=loss._dir_flag if (mask_dirichlet and ctx.prescaled) else None,
+            out_scale=(1.0 / nb) if ctx.prescaled else 1.0)
         out4 = torch.empty(4, dtype=loss.dtype, device=energy.device)
         scale = torch.empty_like(energy)
         _lib.check(_lib.load().fol_loss_reduce(_lib.stream_ptr(), loss._dt, energy.shape[0],
@@ -65,17 +74,20 @@ class _BatchLossFn(torch.autograd.Function):
         ctx.used = True
         loss = ctx.loss
         grad_u, grad_k = ctx.grads
-        up = 0.0
+        up = None
         for g in (g_mean, g_mean2):
             if g is not None:
-                up = up + g
-        up = float(up) if not isinstance(up, float) else up
+                up = g if up is None else up + g
+        if up is None:
+            up = torch.zeros((), dtype=loss.dtype, device=grad_u.device)
+        up = up.to(dtype=loss.dtype).contiguous()       # device scalar: the kernel reads it, the host never does
         nb = grad_u.shape[0]
         _lib.check(_lib.load().fol_scale_grads(_lib.stream_ptr(), loss._dt, nb, loss.total_number_of_dofs,
-                                               loss.fe_mesh.GetNumberOfNodes(), _lib.ptr(ctx.scale), up,
+                                               loss.fe_mesh.GetNumberOfNodes(), _lib.ptr(ctx.scale), 1.0, _lib.ptr(up),
+                                               1 if ctx.prescaled else 0,
                                                _lib.ptr(loss._dir_flag if ctx.mask_dirichlet else loss._no_flag),
                                                _lib.ptr(grad_u), _lib.ptr(grad_k) if grad_k is not None else None))
-        return None, (grad_k if ctx.need[0] else None), (grad_u if ctx.need[1] else None), None
+        return None, (grad_k if ctx.need[0] else None), (grad_u if ctx.need[1] else None), None, None
 
 
 class FiniteElementLoss(Loss):
@@ -179,6 +191,10 @@ class FiniteElementLoss(Loss):
         _lib.check(lib.fol_node_adjacency(s, _lib.ptr(self._conn), ne, self._nnode, nn, _lib.ptr(self._adj_ptr),
                                           _lib.ptr(self._adj), _lib.ptr(work)))
         self._no_flag = torch.zeros_like(self._dir_flag)
+        # Dirichlet value per dof, NaN where free (the batched-loss kernel overwrites while staging)
+        full = np.full(max(self.total_number_of_dofs, 1), np.nan)
+        full[np.asarray(self.dirichlet_indices, dtype=np.int64)] = np.asarray(self.dirichlet_values, dtype=float)
+        self._dir_full = _lib.to_device(full, self.dtype)
         self._indices = None   # BCOO indices, built on the first Jacobian request
         self._geom = None      # geometry cache, built on the first batched-loss request
         self._params = _lib.params_array(self._material_params())
@@ -359,8 +375,9 @@ class FiniteElementLoss(Loss):
             cache[nb] = torch.empty(n, dtype=self.dtype, device=self.device)
         return cache[nb]
 
-    def _energy_and_grads(self, batch_params, batch_dofs):
-        """(E_b, dE_b/du_b (un-masked assembled residual), dE_b/dK_b) for BC-applied dofs."""
+    def _energy_and_grads(self, batch_params, batch_dofs, dir_values=None, dir_flag=None, out_scale=1.0):
+        """(E_b, out_scale * dE_b/du_b (un-masked assembled residual, zero where dir_flag), out_scale * dE_b/dK_b);
+        the dofs are BC-applied already, or dir_values (ndof, NaN = free) is applied by the kernel."""
         lib = _lib.load()
         nb = batch_dofs.shape[0]
         geom, ep = self._geometry_cache(), self._energy_plan()
@@ -376,7 +393,10 @@ class FiniteElementLoss(Loss):
                                             _lib.ptr(ep["tile_elems"]), _lib.ptr(ep["tile_conn"]),
                                             _lib.ptr(ep["tile_lnode_ptr"]), _lib.ptr(ep["tile_lnodes"]), ep["ntiles"],
                                             ep["ecap"], ep["lcap"], ep["ncap"],
-                                            _lib.ptr(batch_params), _lib.ptr(batch_dofs), self._params,
+                                            _lib.ptr(batch_params), _lib.ptr(batch_dofs),
+                                            _lib.ptr(dir_values) if dir_values is not None else None,
+                                            _lib.ptr(dir_flag) if dir_flag is not None else None, float(out_scale),
+                                            self._params,
                                             _lib.ptr(grad_u), _lib.ptr(grad_k), _lib.ptr(energy), _lib.ptr(work)))
         return energy, grad_u, grad_k
 
@@ -391,11 +411,10 @@ class FiniteElementLoss(Loss):
             if ctrl.dim() == 1:
                 ctrl = ctrl.reshape(1, -1).expand(dofs.shape[0], -1)
             params = self._as_batch(ctrl, self._nn)
-            mean, mn, mx, mean2, _ = _BatchLossFn.apply(self, params, full, False)
+            mean, mn, mx, mean2, _ = _BatchLossFn.apply(self, params, full, False, False)
         else:
             params = self._as_batch(batch_params, self._nn)
-            full = _ApplyDirichlet.apply(self, dofs)
-            mean, mn, mx, mean2, _ = _BatchLossFn.apply(self, params, full, True)
+            mean, mn, mx, mean2, _ = _BatchLossFn.apply(self, params, dofs, True, True)
         return mean, (mn, mx, mean2)
 
     def ComputeTotalEnergy(self, total_control_vars, total_primal_vars):

@@ -27,8 +27,8 @@ class MechanicalLoss(FiniteElementLoss):
         p[2:5] = body.tolist()
         return p
 
-    def _energy_and_grads(self, batch_params, batch_dofs):
-        energy, grad_u, _ = super()._energy_and_grads(batch_params, batch_dofs)
+    def _energy_and_grads(self, batch_params, batch_dofs, **kw):
+        energy, grad_u, _ = super()._energy_and_grads(batch_params, batch_dofs, **kw)
         return energy, grad_u, None
 
 

@@ -12,9 +12,9 @@ class NeoHookeMechanicalLoss(MechanicalLoss):
         self.e = self.loss_settings["material_dict"]["young_modulus"]
         self.v = self.loss_settings["material_dict"]["poisson_ratio"]
 
-    def _energy_and_grads(self, batch_params, batch_dofs):
+    def _energy_and_grads(self, batch_params, batch_dofs, **kw):
         from .fe_loss import FiniteElementLoss
-        return FiniteElementLoss._energy_and_grads(self, batch_params, batch_dofs)
+        return FiniteElementLoss._energy_and_grads(self, batch_params, batch_dofs, **kw)
 
     def _element_energy(self, xyz, conn, ctrl, u, re):
         # energy = sum_g w detJ psi (mechanical_neohooke.py:262, 271), not u . re
@@ -38,7 +38,7 @@ class NeoHookeMechanicalLoss(MechanicalLoss):
                                             _lib.ptr(ep["tile_node_ptr"]), _lib.ptr(ep["tile_nodes"]),
                                             _lib.ptr(ep["tile_elem_ptr"]), _lib.ptr(ep["tile_elems"]), _lib.ptr(ep["tile_conn"]),
                                             _lib.ptr(ep["tile_lnode_ptr"]), _lib.ptr(ep["tile_lnodes"]), ep["ntiles"],
-                                            ep["ecap"], ep["lcap"], ep["ncap"], _lib.ptr(ctrl), _lib.ptr(u), self._params, _lib.ptr(gu),
+                                            ep["ecap"], ep["lcap"], ep["ncap"], _lib.ptr(ctrl), _lib.ptr(u), None, None, 1.0, self._params, _lib.ptr(gu),
                                             _lib.ptr(gk), _lib.ptr(energy), _lib.ptr(work)))
         return energy[0]
 

@@ -149,7 +149,8 @@ int fol_energy_and_grads(fol_stream_t s, int dtype, int physics, int element, in
                          const int32_t* tile_elem_ptr, const int32_t* tile_elems,
                          const int32_t* tile_conn, const int32_t* tile_lnode_ptr,
                          const int32_t* tile_lnodes, int64_t ntiles, int64_t ecap, int64_t lcap,
-                         int64_t ncap, const void* ctrl, const void* u, const double* params_host,
+                         int64_t ncap, const void* ctrl, const void* u, const void* dir_values,
+                         const uint8_t* dir_flag, double out_scale, const double* params_host,
                          void* grad_u, void* grad_k, void* energy, void* work);
 
 /* loss tail: L = mean_b E_b^p, stats = (min, max, mean) of E_b^p, scale[b] = p E_b^(p-1)/nb.
@@ -157,10 +158,13 @@ int fol_energy_and_grads(fol_stream_t s, int dtype, int physics, int element, in
 int fol_loss_reduce(fol_stream_t s, int dtype, int64_t nb, double exponent, const void* energy,
                     void* out4, void* scale);
 
-/* backward: grad_u[b,:] *= g*scale[b], zeroed at Dirichlet dofs; grad_k[b,:] *= g*scale[b]. */
+/* backward: grad_u[b,:] *= g*sc_b, zeroed at Dirichlet dofs; grad_k[b,:] *= g*sc_b, with
+ * g = upstream * (*upstream_dev, a device scalar of the call's dtype, or 1 when NULL -- no host
+ * synchronisation on the cotangent) and sc_b = scale[b], or 1 when `prescaled` (the forward call
+ * already applied out_scale = scale: exponent 1).  prescaled and g == 1 is a no-op. */
 int fol_scale_grads(fol_stream_t s, int dtype, int64_t nb, int64_t ndof, int64_t nn,
-                    const void* scale, double upstream, const uint8_t* dir_flag, void* grad_u,
-                    void* grad_k);
+                    const void* scale, double upstream, const void* upstream_dev, int prescaled,
+                    const uint8_t* dir_flag, void* grad_u, void* grad_k);
 
 /* u[b, dirichlet_indices] = values (GetFullDofVector, fe_loss.py:91-92) or, when
  * per_sample != 0, values is (nb, n_dirichlet) (parametric boundary learning, :94-95).

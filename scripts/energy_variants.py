@@ -38,3 +38,21 @@ print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("F
                   "samples_per_s": round(B / ms * 1e3), "ntiles": ep["ntiles"], "ecap": ep["ecap"], "lcap": ep["lcap"],
                   "E": e.sum().item(), "gu": gu.abs().sum().item(), "gk": gk.abs().sum().item(),
                   "hash": [float(e[17]), float(gu[5, 1234]), float(gk[1023 % B, 40000])]}))
+
+# whole physics step through the public API (ComputeBatchLoss + backward), as bench.py's physics_only leg
+def physics_only():
+    uu = u.detach().requires_grad_(True)
+    kk = K.detach().requires_grad_(True)
+    mean, _ = loss.ComputeBatchLoss(kk, uu)
+    mean.backward()
+
+
+for _ in range(3):
+    physics_only()
+torch.cuda.synchronize()
+ev[0].record()
+for _ in range(n):
+    physics_only()
+ev[1].record()
+torch.cuda.synchronize()
+print(json.dumps({"physics_only_ms": round(ev[0].elapsed_time(ev[1]) / n, 4)}))
