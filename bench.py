@@ -211,16 +211,59 @@ def fol_loss_grad_bench(torch, dist, rank, world, steps, warmup):
     ms_step, ms_phys = t.tolist()
     hbm, _ = measured_peaks()
     bytes_per_sample = 32.0 * nn  # read u, K; write dE/du, dE/dK (f64)
-    # f64 work per element and sample (SASS count of the fused kernel: 134 DFMA + 44 DMUL + 11 DADD)
-    flops_per_sample = (2 * 134 + 44 + 11) * 65536.0
+    # f64 work per sample (SASS count of energy_tile2_kernel, profiles/r1/energy_tile2_sass_hist.txt):
+    # element phase 133 DFMA + 28 DMUL per element, node phase 8 DADD + 1 DFMA + 2 DMUL per node
+    flops_per_sample = (2 * 133 + 28) * 65536.0 + (8 + 2 + 2) * float(nn)
+    # same physics step in float32 (the reference's default precision: jax_enable_x64 is off in its examples)
+    loss32 = ThermalLoss2DQuad("fol_thermal32", {"dirichlet_bc_dict": {"T": {"left": 1.0, "right": 0.1}},
+                                                 "beta": 2.0, "c": 4, "dtype": "float32"}, mesh)
+    loss32.Initialize()
+    K32, u32 = Kb.float(), ub.float()
+
+    def physics_only32():
+        uu = u32.detach().requires_grad_(True)
+        kk = K32.detach().requires_grad_(True)
+        mean, _ = loss32.ComputeBatchLoss(kk, uu)
+        mean.backward()
+    for _ in range(3):
+        physics_only32()
+    ms_phys32 = event_time_ms(torch, physics_only32, steps)
+    # same FOL step with the network in float32 (flax's default parameter dtype) feeding the float64 physics loss
+    torch.manual_seed(0)
+    net32 = torch.nn.Sequential(torch.nn.Linear(64, 256), torch.nn.Tanh(), torch.nn.Linear(256, nn)).to("cuda")
+    latent32 = latent.float()
+
+    def step_mixed():
+        for p in net32.parameters():
+            p.grad = None
+        uu = torch.sigmoid(net32(latent32)).double()
+        mean, _ = loss.ComputeBatchLoss(Kb, uu)
+        mean.backward()
+        allreduce_gradients(list(net32.parameters()))
+    for _ in range(3):
+        step_mixed()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_mixed = event_time_ms(torch, step_mixed, steps)
+    t = torch.tensor([ms_mixed], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_mixed = t.item()
     tf = ctypes.c_double()
     fp64_peak = tf.value if (rank == 0 and _lib.load().fol_measure_fma_peak(_lib.F64, ctypes.byref(tf)) == 0) else None
     ach_tf = flops_per_sample * B / (ms_phys * 1e-3) / 1e12
     return {"metric": "fol_loss_grad_samples_per_s", "value": B * world / (ms_step * 1e-3), "unit": "samples/s",
             "physics_only_samples_per_s": B * world / (ms_phys * 1e-3), "ms_per_step": ms_step,
             "ms_per_step_physics_only": ms_phys,
+            "physics_only_f32_samples_per_s_per_gpu": B / (ms_phys32 * 1e-3),
+            "f32_network_f64_physics": {"value": B * world / (ms_mixed * 1e-3), "unit": "samples/s",
+                                        "ms_per_step": ms_mixed,
+                                        "note": "MLP in float32 (flax default parameter dtype), physics loss + VJP in "
+                                                "float64; the headline value above keeps the whole step in float64"},
             "config": {"workload": "thermal_quad256_loss_vjp_f64", "batch_per_gpu": B, "mesh": "256x256 quads",
                        "beta": 2.0, "c": 4, "network": "MLP 64-256-66049 (f64, torch/cuBLAS: caller code, not the path)",
+                       "kernel": "energy_tile2_kernel (pipelined fused loss + VJP, Dirichlet overwrite and 1/B scale fused)",
                        "parallelism": f"dp{world}"},
             "roofline_physics": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                                  "frac": (ach_tf / fp64_peak) if fp64_peak else None,
