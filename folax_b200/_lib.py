@@ -36,6 +36,8 @@ SIGNATURES = {
                                      _u8p, C.POINTER(_dbl), _vp, _vp, _vp, _vp]),
     "fol_residual_gather": (_int, [_vp, _int, _i64, _int, _int, _i32p, _i32p, _vp, _vp]),
     "fol_csr_values": (_int, [_vp, _int, _i64, _int, _int, _i32p, _i32p, _i32p, _i32p, _vp, _vp]),
+    "fol_apply_jacobian_elements": (_int, [_vp, _int, _int, _int, _int, _int, _i64, _i64, _vp, _i32p, _vp, _vp, _u8p,
+                                           C.POINTER(_dbl), _vp, _vp, _vp]),
     "fol_geometry_cache": (_int, [_vp, _int, _int, _int, _i64, _vp, _i32p, _vp]),
     "fol_energy_work_size": (_i64, [_i64, _i64]),
     "fol_energy_and_grads": (_int, [_vp, _int, _int, _int, _int, _i64, _i64, _i64, _vp, _i32p, _i32p, _i32p,

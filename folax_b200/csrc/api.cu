@@ -37,8 +37,10 @@ static std::atomic<int> g_tuned{1};
 template <class T>
 static int assemble_typed(cudaStream_t s, int physics, int element, int num_gp, int transpose, long long ne,
                           const void* xyz, const int32_t* conn, const void* ctrl, const void* u, const uint8_t* dir,
-                          const double* params, void* ke, void* re, const void* st_in, void* st_out) {
+                          const double* params, void* ke, void* re, const void* st_in, void* st_out,
+                          const void* v = nullptr) {
   AsmArgs<T> a;
+  a.v = (const T*)v;
   a.xyz = (const T*)xyz;
   a.conn = conn;
   a.ctrl = (const T*)ctrl;
@@ -56,7 +58,7 @@ static int assemble_typed(cudaStream_t s, int physics, int element, int num_gp, 
     case FOL_MECHANICAL:
       if constexpr (f64) {
         // (the tuned kernel writes Ke itself; the transpose switch of fe_loss.py:216-230 uses the generic kernel)
-        if (element == HEX && num_gp == 2 && !transpose && g_tuned.load()) return assemble_hex_mech_f64(s, a);
+        if (element == HEX && num_gp == 2 && !transpose && !v && g_tuned.load()) return assemble_hex_mech_f64(s, a);
         return assemble_mech_f64(s, element, num_gp, a);
       } else {
         return assemble_mech_f32(s, element, num_gp, a);
@@ -79,7 +81,7 @@ static int assemble_typed(cudaStream_t s, int physics, int element, int num_gp, 
       else return assemble_stvk_f32(s, element, num_gp, a);
 #ifdef FOL_HAVE_J2
     case FOL_J2PLASTICITY:
-      if (!st_in || !st_out) return fail(FOL_ERR_INVALID, "J2 plasticity needs state_in/state_out");
+      if (!st_in || (!st_out && !v)) return fail(FOL_ERR_INVALID, "J2 plasticity needs state_in/state_out");
       if constexpr (f64) return assemble_j2_f64(s, element, num_gp, a);
       else return assemble_j2_f32(s, element, num_gp, a);
 #endif
@@ -142,6 +144,25 @@ int fol_assemble_elements(fol_stream_t s, int dtype, int physics, int element, i
     return assemble_typed<float>((cudaStream_t)s, physics, element, num_gp, transpose, ne, xyz, conn, ctrl, u,
                                  dir_flag, params_host, ke_data, re_elem, state_in, state_out);
   return fail(FOL_ERR_INVALID, "fol_assemble_elements: dtype must be FOL_F32 or FOL_F64");
+}
+
+int fol_apply_jacobian_elements(fol_stream_t s, int dtype, int physics, int element, int num_gp, int transpose,
+                                int64_t ne, int64_t nn, const void* xyz, const int32_t* conn, const void* ctrl,
+                                const void* u, const uint8_t* dir_flag, const double* params_host, const void* v,
+                                void* ye_elem, const void* state_in) {
+  (void)nn;
+  FOL_REQUIRE(valid_element(element), "fol_apply_jacobian_elements: unknown element");
+  FOL_REQUIRE(num_gp >= 1 && num_gp <= 3, "fol_apply_jacobian_elements: num_gp must be 1, 2 or 3");
+  FOL_REQUIRE(xyz && conn && ctrl && u && dir_flag && v && ye_elem && params_host,
+              "fol_apply_jacobian_elements: null pointer");
+  FOL_REQUIRE(ne >= 0, "fol_apply_jacobian_elements: negative element count");
+  if (dtype == FOL_F64)
+    return assemble_typed<double>((cudaStream_t)s, physics, element, num_gp, transpose, ne, xyz, conn, ctrl, u,
+                                  dir_flag, params_host, nullptr, ye_elem, state_in, nullptr, v);
+  if (dtype == FOL_F32)
+    return assemble_typed<float>((cudaStream_t)s, physics, element, num_gp, transpose, ne, xyz, conn, ctrl, u,
+                                 dir_flag, params_host, nullptr, ye_elem, state_in, nullptr, v);
+  return fail(FOL_ERR_INVALID, "fol_apply_jacobian_elements: dtype must be FOL_F32 or FOL_F64");
 }
 
 int fol_geometry_cache(fol_stream_t s, int dtype, int element, int num_gp, int64_t ne, const void* xyz,

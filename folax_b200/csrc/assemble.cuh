@@ -48,6 +48,7 @@ struct AsmArgs {
   long long ne;
   int transpose;
   Params<T> p;
+  const T* v = nullptr;   // matrix-free mode: re <- Ke'(u) v_e (element products of J v), ke is not written
 };
 
 // per-Gauss-point constitutive data handed from phase 1 to phase 2
@@ -465,7 +466,8 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
         T* pd = sm.pd + g * PD;
         j2_point<T, D>(eps, st, P.v[0], P.v[1], P.v[5], P.v[6], P.v[7], pd, pd + V, st_new);
 #pragma unroll
-        for (int s = 0; s < NS; ++s) args.state_out[sbase + s] = st_new[s];
+        for (int s = 0; s < NS; ++s)
+          if (args.state_out != nullptr) args.state_out[sbase + s] = st_new[s];
         sm.coef[g] = wd;
       }
     }
@@ -477,6 +479,21 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
   constexpr bool STAGE = stage_output<T>(ND);
   T* stage_all = reinterpret_cast<T*>(smem_raw + sizeof(SM) * GPB);
   T* st = stage_all + (size_t)grp * (ND * ND);
+  // matrix-free mode: the region after the groups holds, per group, v_e (ND) and the lanes' partial
+  // products of Ke^T v_e (A x ND) instead of staged matrices
+  const bool matvec = args.v != nullptr;
+  T* mv = stage_all + (size_t)grp * (ND * (A + 1));
+  T mv_diag[DPN];
+#pragma unroll
+  for (int i = 0; i < DPN; ++i) mv_diag[i] = (T)0;
+  if (matvec) {
+    if (active) {
+      const long long n = args.conn[e * A + a];
+#pragma unroll
+      for (int k = 0; k < DPN; ++k) mv[a * DPN + k] = __ldg(args.v + n * DPN + k);
+    }
+    __syncwarp();
+  }
   if (active) {
   // ---- phase 2: row block a of Ke, re = Ke u - Fe
   T K[A][DPN][DPN];
@@ -655,6 +672,34 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
     for (int i = 0; i < DPN; ++i) fint[i] -= P.v[2 + i] * nw;
   }
 
+  if (matvec) {
+    // ---- matrix-free product with the masked element matrix (fe_loss.py:191-230 applied to Ke or Ke^T):
+    //      y_r = free row ? sum_c Ke(^T)[r][c] v_c : Ke[r][r] v_r
+    if (!args.transpose) {
+#pragma unroll
+      for (int i = 0; i < DPN; ++i) {
+        const int r = a * DPN + i;
+        T acc = (T)0;
+#pragma unroll
+        for (int c = 0; c < ND; ++c) acc += K[c / DPN][i][c % DPN] * mv[c];
+        args.re[e * ND + r] = (sm.bc[r] != (T)0) ? acc : K[a][i][i] * mv[r];
+      }
+    } else {
+      // lane a holds rows (a, i) of Ke = columns of Ke^T: its share of (Ke^T v)_(b,j) is sum_i K[b][i][j] v_(a,i);
+      // the shares meet in shared memory and are summed in lane order after the warp barrier below
+#pragma unroll
+      for (int b = 0; b < A; ++b)
+#pragma unroll
+        for (int j = 0; j < DPN; ++j) {
+          T acc = (T)0;
+#pragma unroll
+          for (int i = 0; i < DPN; ++i) acc += K[b][i][j] * mv[a * DPN + i];
+          mv[ND + a * ND + b * DPN + j] = acc;
+        }
+#pragma unroll
+      for (int i = 0; i < DPN; ++i) mv_diag[i] = K[a][i][i];
+    }
+  } else {
   // ---- store: transpose switch + Dirichlet row mask (fe_loss.py:191-230), data of :299
 #pragma unroll
   for (int i = 0; i < DPN; ++i) {
@@ -689,7 +734,25 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
         }
       }
   }
+  }  // !matvec
   }  // active
+
+  if (matvec) {
+    if (args.transpose) {
+      __syncwarp();
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < DPN; ++i) {
+          const int r = a * DPN + i;
+          T acc = (T)0;
+#pragma unroll
+          for (int b = 0; b < A; ++b) acc += mv[ND + b * ND + r];
+          args.re[e * ND + r] = (sm.bc[r] != (T)0) ? acc : mv_diag[i] * mv[r];
+        }
+      }
+    }
+    return;
+  }
 
   // ---- the warp's elements are consecutive: their staged matrices leave as ONE contiguous bulk
   // async copy (cp.async.bulk shared -> global, TMA engine) instead of scattered 16-byte stores
@@ -731,11 +794,14 @@ int launch_assemble(cudaStream_t s, const AsmArgs<T>& args) {
   constexpr size_t kPerGroup = sizeof(SM) + (stage_output<T>(SM::ND) ? sizeof(T) * SM::ND * SM::ND : 0);  // + staged Ke'
   constexpr int BLOCK = kPerGroup * (128 / GW) <= kBudget ? 128 : (kPerGroup * (64 / GW) <= kBudget ? 64 : 32);
   constexpr int GPB = BLOCK / GW;
-  const size_t smem = kPerGroup * GPB;
+  // matrix-free mode keeps v_e and the partial products (ND * (A + 1) values per group) where the staged Ke' would be
+  constexpr size_t kPerGroupMv = sizeof(SM) + sizeof(T) * SM::ND * (SM::A + 1);
+  constexpr size_t kMaxSmem = (kPerGroup > kPerGroupMv ? kPerGroup : kPerGroupMv) * GPB;
+  const size_t smem = (args.v ? kPerGroupMv : kPerGroup) * GPB;
   auto kern = assemble_kernel<T, ELEM, ORDER, PHYS, BLOCK>;
   static bool configured = false;
   if (!configured) {
-    FOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     configured = true;
   }
   const long long grid = cdiv(args.ne, GPB);

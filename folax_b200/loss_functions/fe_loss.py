@@ -285,6 +285,32 @@ class FiniteElementLoss(Loss):
         jac = BCOO((data, self._bcoo_indices()), shape=(self.total_number_of_dofs, self.total_number_of_dofs))
         return jac, R
 
+    def ApplyJacobian(self, total_control_vars, total_primal_vars, vector, transpose_jacobian: bool = False,
+                      state_in=None):
+        """y = J(controls, dofs) @ vector without forming J: what the consumers of the BCOO do with
+        `jacobian @ v` (fe_solver.py:61) and what a Krylov solver needs every iteration.  J is the matrix
+        ComputeJacobianMatrixAndResidualVector(..., transpose_jacobian) returns (Dirichlet rows included);
+        the element matrices live in registers only, so the cost is the element arithmetic, not the
+        nd^2 * 8 bytes per element of the assembled format."""
+        lib = _lib.load()
+        ctrl = _lib.to_device(total_control_vars, self.dtype).reshape(-1)
+        u = _lib.to_device(total_primal_vars, self.dtype).reshape(-1)
+        v = _lib.to_device(vector, self.dtype).reshape(-1).contiguous()
+        if ctrl.numel() != self._nn or u.numel() != self.total_number_of_dofs or v.numel() != u.numel():
+            raise ValueError(f"{self.GetName()}: controls must have {self._nn} entries, dofs and vector "
+                             f"{self.total_number_of_dofs}")
+        ye = torch.empty(max(self._ne * self._nd, 1), dtype=self.dtype, device=self.device)
+        y = torch.empty(self.total_number_of_dofs, dtype=self.dtype, device=self.device)
+        s = _lib.stream_ptr()
+        _lib.check(lib.fol_apply_jacobian_elements(s, self._dt, _lib.PHYSICS[self.physics], self.fe_element.code,
+                                                   self.num_gp, int(bool(transpose_jacobian)), self._ne, self._nn,
+                                                   _lib.ptr(self._xyz), _lib.ptr(self._conn), _lib.ptr(ctrl),
+                                                   _lib.ptr(u), _lib.ptr(self._dir_flag), self._params, _lib.ptr(v),
+                                                   _lib.ptr(ye), _lib.ptr(state_in)))
+        _lib.check(lib.fol_residual_gather(s, self._dt, self._nn, self._nnode, self.number_dofs_per_node,
+                                           _lib.ptr(self._adj_ptr), _lib.ptr(self._adj), _lib.ptr(ye), _lib.ptr(y)))
+        return y
+
     def _csr_plan(self):
         if self.__dict__.get("_cplan") is None:
             from .. import csr_plan

@@ -119,6 +119,19 @@ int fol_csr_values(fol_stream_t s, int dtype, int64_t npairs, int dofs_per_node,
 
 /* ---- batched physics loss + VJP (fe_loss.py:250-262 and its JAX-AD gradient) -------------- */
 
+/* Matrix-free product with the Jacobian of fol_assemble_elements (what the reference's consumers do
+ * with `BCOO @ vector`, fe_solver.py:61, and what a Krylov solver needs): per element
+ *   ye_elem[e*nd + i] = sum_j Ke'[i,j] v[gdof(e,j)],  Ke' the (transposed, then) row-masked element
+ * matrix of fe_loss.py:191-230 evaluated at (ctrl, u) -- Ke is formed in registers and never written.
+ * fol_residual_gather(ye_elem) then gives y = J v (or J^T-variant v for transpose != 0) in the fixed
+ * summation order of the residual.  state_in: as fol_assemble_elements (J2 history is read, not
+ * advanced). */
+int fol_apply_jacobian_elements(fol_stream_t s, int dtype, int physics, int element, int num_gp,
+                                int transpose, int64_t ne, int64_t nn, const void* xyz,
+                                const int32_t* conn, const void* ctrl, const void* u,
+                                const uint8_t* dir_flag, const double* params_host, const void* v,
+                                void* ye_elem, const void* state_in);
+
 /* per-element, per-Gauss-point geometry factors shared by all samples, SoA over elements:
  * geom[(g*(a*dim+1) + k)*ne + e] = grad N flattened (k < a*dim) | w*detJ (k = a*dim).   */
 int fol_geometry_cache(fol_stream_t s, int dtype, int element, int num_gp, int64_t ne,
