@@ -39,6 +39,8 @@ SIGNATURES = {
     "fol_apply_jacobian_elements": (_int, [_vp, _int, _int, _int, _int, _int, _i64, _i64, _vp, _i32p, _vp, _vp, _u8p,
                                            C.POINTER(_dbl), _vp, _vp, _vp]),
     "fol_geometry_cache": (_int, [_vp, _int, _int, _int, _i64, _vp, _i32p, _vp]),
+    "fol_geometry_width": (_int, [_int, _int]),
+    "fol_geometry_cache_physics": (_int, [_vp, _int, _int, _int, _int, _i64, _vp, _i32p, _vp, _vp]),
     "fol_energy_work_size": (_i64, [_i64, _i64]),
     "fol_energy_and_grads": (_int, [_vp, _int, _int, _int, _int, _i64, _i64, _i64, _vp, _i32p, _i32p, _i32p,
                                     _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i64, _i64, _i64, _i64,

@@ -25,7 +25,7 @@ extern std::atomic<int> g_grid_margin;
 template <class T>
 int energy_and_grads(cudaStream_t, int, int, int, const EnergyArgs<T>&, int, T*);
 template <class T>
-int geometry_cache(cudaStream_t, int, int, long long, const T*, const int32_t*, T*);
+int geometry_cache(cudaStream_t, int, int, int, long long, const T*, const int32_t*, const T*, T*);
 template <class T>
 int loss_reduce(cudaStream_t, long long, double, const T*, T*, T*);
 template <class T>
@@ -165,12 +165,24 @@ int fol_apply_jacobian_elements(fol_stream_t s, int dtype, int physics, int elem
   return fail(FOL_ERR_INVALID, "fol_apply_jacobian_elements: dtype must be FOL_F32 or FOL_F64");
 }
 
-int fol_geometry_cache(fol_stream_t s, int dtype, int element, int num_gp, int64_t ne, const void* xyz,
-                       const int32_t* conn, void* geom) {
+int fol_geometry_width(int physics, int element) {
+  if (!valid_element(element)) return FOL_ERR_INVALID;
+  return geom_width(physics, element);
+}
+
+int fol_geometry_cache_physics(fol_stream_t s, int dtype, int physics, int element, int num_gp, int64_t ne,
+                               const void* xyz, const int32_t* conn, const void* aux, void* geom) {
   FOL_REQUIRE(valid_element(element) && xyz && conn && geom, "fol_geometry_cache: bad arguments");
   if (dtype == FOL_F64)
-    return geometry_cache<double>((cudaStream_t)s, element, num_gp, ne, (const double*)xyz, conn, (double*)geom);
-  return geometry_cache<float>((cudaStream_t)s, element, num_gp, ne, (const float*)xyz, conn, (float*)geom);
+    return geometry_cache<double>((cudaStream_t)s, physics, element, num_gp, ne, (const double*)xyz, conn,
+                                  (const double*)aux, (double*)geom);
+  return geometry_cache<float>((cudaStream_t)s, physics, element, num_gp, ne, (const float*)xyz, conn,
+                               (const float*)aux, (float*)geom);
+}
+
+int fol_geometry_cache(fol_stream_t s, int dtype, int element, int num_gp, int64_t ne, const void* xyz,
+                       const int32_t* conn, void* geom) {
+  return fol_geometry_cache_physics(s, dtype, FOL_MECHANICAL, element, num_gp, ne, xyz, conn, nullptr, geom);
 }
 
 int64_t fol_energy_work_size(int64_t ntiles, int64_t nb) { return ntiles * nb * 10 + 16; }  // <= 10 warps per tile

@@ -43,6 +43,8 @@ template <class T>
 int energy2_thermal(cudaStream_t, int, int, const EnergyArgs<T>&, int, int*);
 template <class T>
 int energy2_mech(cudaStream_t, int, int, int, const EnergyArgs<T>&, int, int*);
+template <class T>
+int energy2_scalar(cudaStream_t, int, int, int, const EnergyArgs<T>&, int, int*);
 
 // The pipelined kernel (energy2.cuh) runs when the plan fits it, energy_tile_kernel otherwise.
 // npart = energy shares per sample written by the kernel that ran (pipelined kernel: one per warp)
@@ -50,7 +52,9 @@ template <class T>
 int energy_and_grads(cudaStream_t s, int physics, int element, int num_gp, const EnergyArgs<T>& a, int ncap, T* energy) {
   if (a.ntiles == 0 || a.nb == 0) return FOL_OK;
   int parts = 1;
+  const bool scalar_implicit = physics == FOL_TRANSIENT_THERMAL || physics == FOL_ALLEN_CAHN;
   int rc = (physics == FOL_THERMAL) ? energy2_thermal<T>(s, element, num_gp, a, ncap, &parts)
+           : scalar_implicit        ? energy2_scalar<T>(s, physics, element, num_gp, a, ncap, &parts)
                                     : energy2_mech<T>(s, physics, element, num_gp, a, ncap, &parts);
   if (rc == 1) {
     parts = 1;
@@ -58,6 +62,8 @@ int energy_and_grads(cudaStream_t s, int physics, int element, int num_gp, const
     else if (physics == FOL_THERMAL) rc = dispatch_energy<T, THERMAL>(s, element, num_gp, a);
     else if (physics == FOL_NEOHOOKE) rc = dispatch_energy<T, NEOHOOKE>(s, element, num_gp, a);
     else if (physics == FOL_STVENANT) rc = dispatch_energy<T, STVK>(s, element, num_gp, a);
+    else if (physics == FOL_TRANSIENT_THERMAL) rc = dispatch_energy<T, TTHERMAL>(s, element, num_gp, a);
+    else if (physics == FOL_ALLEN_CAHN) rc = dispatch_energy<T, ALLENCAHN>(s, element, num_gp, a);
     else return fail(FOL_ERR_UNSUPPORTED, "fol_energy_and_grads: physics not supported");
   }
   const int npart = a.ntiles * parts;
@@ -68,13 +74,13 @@ int energy_and_grads(cudaStream_t s, int physics, int element, int num_gp, const
 template int energy_and_grads<double>(cudaStream_t, int, int, int, const EnergyArgs<double>&, int, double*);
 template int energy_and_grads<float>(cudaStream_t, int, int, int, const EnergyArgs<float>&, int, float*);
 
-template <class T, int ELEM>
-int launch_geom(cudaStream_t s, int num_gp, long long ne, const T* xyz, const int32_t* conn, T* geom) {
+template <class T, int ELEM, bool TR, bool AUX>
+int launch_geom(cudaStream_t s, int num_gp, long long ne, const T* xyz, const int32_t* conn, const T* aux, T* geom) {
 #define FOL_CASE(O)                                                                                         \
   if (num_gp == O) {                                                                                        \
     if (ne == 0) return FOL_OK;                                                                             \
     dim3 grid((unsigned)cdiv(ne, 128), (unsigned)elem_ngauss(ELEM, O));                                     \
-    geometry_cache_kernel<T, ELEM, O><<<grid, 128, 0, s>>>(xyz, conn, ne, geom);                            \
+    geometry_cache_kernel<T, ELEM, O, TR, AUX><<<grid, 128, 0, s>>>(xyz, conn, ne, aux, geom);              \
     return check_launch("geometry_cache_kernel");                                                           \
   }
   FOL_CASE(1) FOL_CASE(2) FOL_CASE(3)
@@ -82,18 +88,33 @@ int launch_geom(cudaStream_t s, int num_gp, long long ne, const T* xyz, const in
   return fail(FOL_ERR_UNSUPPORTED, "unsupported num_gp");
 }
 
-template <class T>
-int geometry_cache(cudaStream_t s, int element, int num_gp, long long ne, const T* xyz, const int32_t* conn, T* geom) {
+template <class T, bool TR, bool AUX>
+int geometry_cache_variant(cudaStream_t s, int element, int num_gp, long long ne, const T* xyz, const int32_t* conn,
+                           const T* aux, T* geom) {
   switch (element) {
-    case HEX: return launch_geom<T, HEX>(s, num_gp, ne, xyz, conn, geom);
-    case QUAD: return launch_geom<T, QUAD>(s, num_gp, ne, xyz, conn, geom);
-    case TET: return launch_geom<T, TET>(s, num_gp, ne, xyz, conn, geom);
-    case TRI: return launch_geom<T, TRI>(s, num_gp, ne, xyz, conn, geom);
+    case HEX: return launch_geom<T, HEX, TR, AUX>(s, num_gp, ne, xyz, conn, aux, geom);
+    case QUAD: return launch_geom<T, QUAD, TR, AUX>(s, num_gp, ne, xyz, conn, aux, geom);
+    case TET: return launch_geom<T, TET, TR, AUX>(s, num_gp, ne, xyz, conn, aux, geom);
+    case TRI: return launch_geom<T, TRI, TR, AUX>(s, num_gp, ne, xyz, conn, aux, geom);
   }
   return fail(FOL_ERR_UNSUPPORTED, "unsupported element");
 }
-template int geometry_cache<double>(cudaStream_t, int, int, long long, const double*, const int32_t*, double*);
-template int geometry_cache<float>(cudaStream_t, int, int, long long, const float*, const int32_t*, float*);
+
+// geometry factors in the layout / gradient convention of `physics` (energy.cuh: geom_width)
+template <class T>
+int geometry_cache(cudaStream_t s, int physics, int element, int num_gp, long long ne, const T* xyz,
+                   const int32_t* conn, const T* aux, T* geom) {
+  if (physics == FOL_TRANSIENT_THERMAL) {
+    if (!aux) return fail(FOL_ERR_INVALID, "fol_geometry_cache: transient thermal needs the nodal heterogeneity k0");
+    return geometry_cache_variant<T, true, true>(s, element, num_gp, ne, xyz, conn, aux, geom);
+  }
+  if (physics == FOL_ALLEN_CAHN) return geometry_cache_variant<T, true, false>(s, element, num_gp, ne, xyz, conn, aux, geom);
+  return geometry_cache_variant<T, false, false>(s, element, num_gp, ne, xyz, conn, aux, geom);
+}
+template int geometry_cache<double>(cudaStream_t, int, int, int, long long, const double*, const int32_t*, const double*,
+                                    double*);
+template int geometry_cache<float>(cudaStream_t, int, int, int, long long, const float*, const int32_t*, const float*,
+                                   float*);
 
 template <class T>
 int loss_reduce(cudaStream_t s, long long nb, double exponent, const T* energy, T* out4, T* scale) {

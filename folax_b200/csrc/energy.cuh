@@ -65,37 +65,48 @@ __device__ __forceinline__ T pow_c(T x, T c) {
   return (T)pow((double)x, (double)c);
 }
 
-template <class T, int ELEM, int ORDER>
+// the element energy is a sum of Gauss-point densities (a true potential) rather than u . re
+__host__ __device__ constexpr bool point_energy(int phys) { return finite_strain(phys) || implicit_scalar(phys); }
+// geometry-cache rows per Gauss point: grad N (A*D), w detJ [, the nodal heterogeneity k0 at the point]
+__host__ __device__ constexpr int geom_width(int phys, int elem) {
+  return elem_nnode(elem) * elem_dim(elem) + 1 + (phys == TTHERMAL ? 1 : 0);
+}
+
+// TRANSPOSED: the gradient convention of transient_thermal.py:57-58 / phase_field.py:47-48 (elements.cuh);
+// AUX: one more row, N . aux (aux = nodal heterogeneity k0 of the transient thermal loss, mesh-resident)
+template <class T, int ELEM, int ORDER, bool TRANSPOSED, bool AUX>
 __global__ void geometry_cache_kernel(const T* __restrict__ xyz, const int32_t* __restrict__ conn, long long ne,
-                                      T* __restrict__ geom) {
-  constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM), NGP = elem_ngauss(ELEM, ORDER), W = A * D + 1;
+                                      const T* __restrict__ aux, T* __restrict__ geom) {
+  constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM), W = A * D + 1 + (AUX ? 1 : 0);
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int g = blockIdx.y;
   if (e >= ne) return;
   T X[A * 3];
+  T ax = (T)0;
+  double xi[3], w;
+  gauss_point<ELEM, ORDER>(g, xi, w);
+  T N[A], dN[A][D], gN[A][D];
+  shape_functions<ELEM, T>(xi, N, dN);
 #pragma unroll
   for (int a = 0; a < A; ++a) {
     const long long n = conn[e * A + a];
 #pragma unroll
     for (int k = 0; k < 3; ++k) X[a * 3 + k] = xyz[n * 3 + k];
+    if constexpr (AUX) ax += N[a] * aux[n];
   }
-  double xi[3], w;
-  gauss_point<ELEM, ORDER>(g, xi, w);
-  T N[A], dN[A][D], gN[A][D];
-  shape_functions<ELEM, T>(xi, N, dN);
-  const T det = global_gradients<ELEM, T>(X, dN, gN);
+  const T det = global_gradients<ELEM, T, TRANSPOSED>(X, dN, gN);
   T* out = geom + (long long)g * W * ne + e;
 #pragma unroll
   for (int a = 0; a < A; ++a)
 #pragma unroll
     for (int k = 0; k < D; ++k) out[(long long)(a * D + k) * ne] = gN[a][k];
   out[(long long)(A * D) * ne] = (T)w * det;
-  (void)NGP;
+  if constexpr (AUX) out[(long long)(A * D + 1) * ne] = ax;
 }
 
 // scratch row count per element: re (ND) [+ dK (A)] [+ psi (1)]
 __host__ __device__ constexpr int energy_kw(int phys, int elem) {
-  return elem_nnode(elem) * phys_dpn(phys, elem) + (phys == MECH ? 0 : elem_nnode(elem)) + (finite_strain(phys) ? 1 : 0);
+  return elem_nnode(elem) * phys_dpn(phys, elem) + (phys == MECH ? 0 : elem_nnode(elem)) + (point_energy(phys) ? 1 : 0);
 }
 
 // Element vectors of element e for S samples starting at sample b0 (samples past nb are clamped):
@@ -122,8 +133,8 @@ __device__ __forceinline__ void cp_async_elem(T* sdst, const T* gsrc) {
 }
 
 // geometry factors of one element fit in registers for the small elements / rules
-__host__ __device__ constexpr bool geom_in_regs(int elem, int order) {
-  return elem_ngauss(elem, order) * (elem_nnode(elem) * elem_dim(elem) + 1) <= 40;
+__host__ __device__ constexpr bool geom_in_regs(int elem, int order, int phys = MECH) {
+  return elem_ngauss(elem, order) * geom_width(phys, elem) <= 40;
 }
 
 template <class T, int ELEM, int ORDER, int PHYS, int S, bool REGS>
@@ -134,7 +145,7 @@ __device__ __forceinline__ void element_vectors(const EnergyArgs<T>& args, long 
                                                 T (&re)[S][elem_nnode(ELEM) * phys_dpn(PHYS, ELEM)],
                                                 T (&dK)[S][elem_nnode(ELEM)], T (&en)[S]) {
   constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM), DPN = phys_dpn(PHYS, ELEM), ND = A * DPN;
-  constexpr int NGP = elem_ngauss(ELEM, ORDER), V = voigt_size(D), W = A * D + 1;
+  constexpr int NGP = elem_ngauss(ELEM, ORDER), V = voigt_size(D), W = geom_width(PHYS, ELEM);
   const Params<T>& P = args.p;
   (void)nodes;
 
@@ -167,13 +178,14 @@ __device__ __forceinline__ void element_vectors(const EnergyArgs<T>& args, long 
   const long long ne = args.ne;
 #pragma unroll(NGP <= 4 ? NGP : 1)
   for (int g = 0; g < NGP; ++g) {
-    T gN[A][D], wd;
+    T gN[A][D], wd, kq = (T)0;   // kq: heterogeneity k0 at the point (transient thermal)
     if constexpr (REGS) {
 #pragma unroll
       for (int b = 0; b < A; ++b)
 #pragma unroll
         for (int k = 0; k < D; ++k) gN[b][k] = greg[g * W + b * D + k];
       wd = greg[g * W + A * D];
+      if constexpr (PHYS == TTHERMAL) kq = greg[g * W + A * D + 1];
     } else {
 #pragma unroll
       for (int b = 0; b < A; ++b)
@@ -184,7 +196,12 @@ __device__ __forceinline__ void element_vectors(const EnergyArgs<T>& args, long 
         }
       wd = __ldg(gm);
       gm += ne;
+      if constexpr (PHYS == TTHERMAL) {
+        kq = __ldg(gm);
+        gm += ne;
+      }
     }
+    (void)kq;
     double xi[3], w;
     gauss_point<ELEM, ORDER>(g, xi, w);
     T N[A], dN[A][D];
@@ -219,6 +236,46 @@ __device__ __forceinline__ void element_vectors(const EnergyArgs<T>& args, long 
           for (int k = 0; k < D; ++k) flux += gN[b][k] * gT[k];
           re[s][b] += cf * flux;
           dK[s][b] += ck * N[b];
+        }
+      } else if constexpr (implicit_scalar(PHYS)) {
+        // implicit-Euler scalar potentials (transient_thermal.py:42-73, phase_field.py:38-70), fully differentiated:
+        // ue = next field, de = current field; re <- dE/d(next), dK <- dE/d(current), en <- E
+        T fn = (T)0, gf[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) gf[k] = (T)0;
+#pragma unroll
+        for (int b = 0; b < A; ++b) {
+          fn += N[b] * ue[s][b];
+#pragma unroll
+          for (int k = 0; k < D; ++k) gf[k] += gN[b][k] * ue[s][b];
+        }
+        T g2 = (T)0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) g2 += gf[k] * gf[k];
+        const T dt = P.v[10], df = fn - eg;
+        T cflux, cn, rate;
+        if constexpr (PHYS == TTHERMAL) {
+          const T beta = P.v[5], cexp = P.v[6];
+          const T Kg = kq * ((T)1 + ((beta != (T)0) ? beta * pow_ci<T>(fn, cexp) : (T)0));
+          const T dk = (beta != (T)0) ? kq * beta * cexp * pow_ci<T>(fn, cexp - (T)1) : (T)0;
+          rate = P.v[8] * P.v[9] / dt * wd * df;
+          cflux = Kg * wd;
+          cn = (T)0.5 * dk * wd * g2 + rate;
+          en[s] += (T)0.5 * Kg * wd * g2 + (T)0.5 * rate * df;
+        } else {
+          const T ie2 = (T)1 / (P.v[11] * P.v[11]), f2 = fn * fn - (T)1;
+          rate = wd / dt * df;
+          cflux = wd;
+          cn = wd * ie2 * f2 * fn + rate;
+          en[s] += (T)0.5 * wd * g2 + wd * ie2 * (T)0.25 * f2 * f2 + (T)0.5 * rate * df;
+        }
+#pragma unroll
+        for (int b = 0; b < A; ++b) {
+          T flux = (T)0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) flux += gN[b][k] * gf[k];
+          re[s][b] += cflux * flux + cn * N[b];
+          dK[s][b] -= rate * N[b];
         }
       } else if constexpr (PHYS == MECH) {
         // H = grad u; sigma = E_g (lam tr(H) I + mu (H + H^T)); re_a += w detJ sigma grad N_a - Fe_a
@@ -327,8 +384,8 @@ energy_tile_kernel(const EnergyArgs<T> args) {
   };
 
   // fast path: one thread per tile element; geometry factors and local node ids live in registers
-  constexpr bool REGS = geom_in_regs(ELEM, ORDER);
-  constexpr int GW = REGS ? elem_ngauss(ELEM, ORDER) * (A * elem_dim(ELEM) + 1) : 1;
+  constexpr bool REGS = geom_in_regs(ELEM, ORDER, PHYS);
+  constexpr int GW = REGS ? elem_ngauss(ELEM, ORDER) * geom_width(PHYS, ELEM) : 1;
   const bool fast = REGS && n_el <= BLOCK;
   T greg[GW];
   int my_ln[A];
@@ -351,7 +408,7 @@ energy_tile_kernel(const EnergyArgs<T> args) {
 #pragma unroll
       for (int b = 0; b < A; ++b) { *out = dK[0][b]; out += ecap; }
     }
-    if constexpr (finite_strain(PHYS)) *out = en1[0];
+    if constexpr (point_energy(PHYS)) *out = en1[0];
   };
 
   long long b0 = (long long)blockIdx.y * S;
@@ -432,7 +489,7 @@ energy_tile_kernel(const EnergyArgs<T> args) {
             for (int k = 0; k < DPN; ++k) R[s][k] += in[(s * KW + k) * ecap];
             if constexpr (PHYS != MECH) dk[s] += ink[(s * KW) * ecap];
             // each element's strain energy is counted once: at its local node 0, by the tile owning it
-            if constexpr (finite_strain(PHYS)) en[s] += (a == 0) ? sv[jl + (s * KW + ND + A) * ecap] : (T)0;
+            if constexpr (point_energy(PHYS)) en[s] += (a == 0) ? sv[jl + (s * KW + ND + A) * ecap] : (T)0;
           }
         }
       }
@@ -443,7 +500,7 @@ energy_tile_kernel(const EnergyArgs<T> args) {
 #pragma unroll
           for (int k = 0; k < DPN; ++k) {
             // E_b = u_b . R_b (mechanical.py:116-117, thermal.py:45-49); u from the staged rows
-            if constexpr (!finite_strain(PHYS)) en[s] += st0[(s * C + k) * lcap + threadIdx.x] * R[s][k];
+            if constexpr (!point_energy(PHYS)) en[s] += st0[(s * C + k) * lcap + threadIdx.x] * R[s][k];
             const bool cut = args.dir_flag && args.dir_flag[(long long)n * DPN + k];
             args.grad_u[bb * ndof + (long long)n * DPN + k] = cut ? (T)0 : args.out_scale * R[s][k];
           }

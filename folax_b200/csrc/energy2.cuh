@@ -71,10 +71,10 @@ template <class T, int ELEM, int ORDER, int PHYS, int NL, int S, int BLOCK, int 
 __global__ void __launch_bounds__(BLOCK, MINB) energy_tile2_kernel(const EnergyArgs<T> args) {
   constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM), DPN = phys_dpn(PHYS, ELEM), ND = A * DPN;
   constexpr int KW = energy_kw(PHYS, ELEM), C = DPN + 1, NW = BLOCK / 32;
-  constexpr int GW = elem_ngauss(ELEM, ORDER) * (A * D + 1);
+  constexpr int GW = elem_ngauss(ELEM, ORDER) * geom_width(PHYS, ELEM);
   constexpr int MAXADJ = 8;                 // adjacency entries held in registers; longer lists continue from global
   constexpr int SVB = S * KW * BLOCK;       // one element-vector buffer
-  static_assert(geom_in_regs(ELEM, ORDER), "energy_tile2_kernel keeps the geometry factors in registers");
+  static_assert(geom_in_regs(ELEM, ORDER, PHYS), "energy_tile2_kernel keeps the geometry factors in registers");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int lcap = LCAP;                // row stride of the staged nodal rows (>= plan lcap, checked by the host)
   T* sv = reinterpret_cast<T*>(smem_raw);   // [2][S][KW][BLOCK]
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) energy_tile2_kernel(const EnergyA
             if constexpr (NK == MAXADJ) dk[s] += svb[offk[i] + (s * KW) * BLOCK];
             else dk[s] += svb[off[i] + (s * KW + ND) * BLOCK];
           }
-          if constexpr (finite_strain(PHYS)) {
+          if constexpr (point_energy(PHYS)) {
             // local node 0: off[i] is the element's column itself
             if ((first_mask >> i) & 1u) en[s] += svb[off[i] + (s * KW + ND + A) * BLOCK];
           }
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) energy_tile2_kernel(const EnergyA
 #pragma unroll
           for (int k = 0; k < DPN; ++k) R[s][k] += svb[jl + (s * KW + a * DPN + k) * BLOCK];
           if constexpr (PHYS != MECH) dk[s] += svb[jl + (s * KW + ND + a) * BLOCK];
-          if constexpr (finite_strain(PHYS)) en[s] += (a == 0) ? svb[jl + (s * KW + ND + A) * BLOCK] : (T)0;
+          if constexpr (point_energy(PHYS)) en[s] += (a == 0) ? svb[jl + (s * KW + ND + A) * BLOCK] : (T)0;
         }
       }
 #pragma unroll
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) energy_tile2_kernel(const EnergyA
 #pragma unroll
           for (int k = 0; k < DPN; ++k) {
             // E_b = u_b . R_b (mechanical.py:116-117, thermal.py:45-49)
-            if constexpr (!finite_strain(PHYS)) en[s] += ukeep[s][k] * R[s][k];
+            if constexpr (!point_energy(PHYS)) en[s] += ukeep[s][k] * R[s][k];
             gu[k] = ((cut_mask >> k) & 1u) ? (T)0 : args.out_scale * R[s][k];
           }
           if constexpr (PHYS != MECH) {
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) energy_tile2_kernel(const EnergyA
 #pragma unroll
           for (int b = 0; b < A; ++b) out[(ND + b) * BLOCK] = dK[0][b];
         }
-        if constexpr (finite_strain(PHYS)) out[(ND + A) * BLOCK] = en1[0];
+        if constexpr (point_energy(PHYS)) out[(ND + A) * BLOCK] = en1[0];
       }
     }
   };

@@ -358,13 +358,17 @@ class FiniteElementLoss(Loss):
         return torch.dot(u, re)
 
     # ------------------------------------------------------------------ batched loss
+    _geom_aux = None   # nodal field folded into the geometry cache (transient thermal: k0)
+
     def _geometry_cache(self):
         if self._geom is None:
-            width = self._nnode * self._edim + 1
+            lib, phys = _lib.load(), _lib.PHYSICS[self.physics]
+            width = lib.fol_geometry_width(phys, self.fe_element.code)
             self._geom = torch.empty(max(self._ne * self._ngauss * width, 1), dtype=self.dtype, device=self.device)
-            _lib.check(_lib.load().fol_geometry_cache(_lib.stream_ptr(), self._dt, self.fe_element.code,
+            _lib.check(lib.fol_geometry_cache_physics(_lib.stream_ptr(), self._dt, phys, self.fe_element.code,
                                                       self.num_gp, self._ne, _lib.ptr(self._xyz),
-                                                      _lib.ptr(self._conn), _lib.ptr(self._geom)))
+                                                      _lib.ptr(self._conn), _lib.ptr(self._geom_aux),
+                                                      _lib.ptr(self._geom)))
         return self._geom
 
     _has_control_gradient = True

@@ -51,8 +51,6 @@ class AllenCahnLoss(FiniteElementLoss):
         self._assemble(nodal_current_phi, nodal_next_phi, False, state_out=en)
         return en.sum()
 
-    def ComputeBatchLoss(self, batch_params, batch_dofs):
-        raise NotImplementedError("the batched energy loss of the implicit-Euler losses is not accelerated yet")
 
 
 class AllenCahnLoss2DQuad(AllenCahnLoss):

@@ -31,6 +31,7 @@ class TransientThermalLoss(ThermalLoss):
             fol_error("time step should be provided in the time_integration_dict ", self.GetName())
         super().Initialize(reinitialize)
         self._k0 = _lib.to_device(k0, self.dtype)
+        self._geom_aux = self._k0      # interpolated into the geometry cache of the batched loss
 
     def _material_params(self):
         p = [0.0] * _lib.NUM_PARAMS
@@ -71,8 +72,6 @@ class TransientThermalLoss(ThermalLoss):
         self._assemble(nodal_current_temps, nodal_next_temps, False, state_in=self._k0, state_out=en)
         return en.sum()
 
-    def ComputeBatchLoss(self, batch_params, batch_dofs):
-        raise NotImplementedError("the batched energy loss of the implicit-Euler losses is not accelerated yet")
 
 
 class TransientThermalLoss3DTetra(TransientThermalLoss):

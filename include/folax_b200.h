@@ -136,6 +136,14 @@ int fol_apply_jacobian_elements(fol_stream_t s, int dtype, int physics, int elem
  * geom[(g*(a*dim+1) + k)*ne + e] = grad N flattened (k < a*dim) | w*detJ (k = a*dim).   */
 int fol_geometry_cache(fol_stream_t s, int dtype, int element, int num_gp, int64_t ne,
                        const void* xyz, const int32_t* conn, void* geom);
+/* Same in the layout of `physics`: W = fol_geometry_width(physics, element) rows per Gauss point.  The
+ * implicit-Euler scalar losses use the gradient convention of transient_thermal.py:57-58 /
+ * phase_field.py:47-48; transient thermal adds one row, the nodal heterogeneity `aux` = k0 (nn)
+ * interpolated to the point (it is mesh-resident, transient_thermal.py:98-99). */
+int fol_geometry_width(int physics, int element);
+int fol_geometry_cache_physics(fol_stream_t s, int dtype, int physics, int element, int num_gp,
+                               int64_t ne, const void* xyz, const int32_t* conn, const void* aux,
+                               void* geom);
 
 /* For every sample b (rows of ctrl (nb, nn) and u (nb, ndof), Dirichlet entries of u already
  * overwritten, fe_loss.py:255):

@@ -162,6 +162,13 @@ def batch_loss_grads(physics, element_type, num_gp, coords, conn, batch_controls
             dK = losses.neo_hooke_energy_dcontrol(element_type, num_gp, X, K[b][conn],
                                                   U[b][g], params["poisson_ratio"], law=physics)
             np.add.at(gK[b], conn.reshape(-1), dK.reshape(-1))
+        elif physics in ("transient_thermal", "allen_cahn"):
+            # true potentials: both gradients come from the energy itself, not from the element residual
+            p_el = dict(params)
+            if "k0" in p_el:
+                p_el["k0"] = np.asarray(params["k0"])[conn]
+            re, dK = losses.implicit_scalar_energy_grads(physics, element_type, num_gp, X, K[b][conn], U[b][conn], p_el)
+            np.add.at(gK[b], conn.reshape(-1), dK.reshape(-1))
         elif physics == "thermal":
             _, dK = losses.thermal_energy_grads(element_type, num_gp, X, K[b][conn], U[b][conn],
                                                 params.get("beta", 0.0), params.get("c", 1.0))

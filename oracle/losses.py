@@ -297,3 +297,33 @@ def allen_cahn_element(element_type, num_gp, X, pc, pn, dt, eps):
     energy = 0.5 * np.einsum("ea,eab,eb->e", pn, Se, pn) + Fe / eps ** 2 + Te
     re = np.einsum("eab,eb->ea", Me + dt * Se, pn) - (np.einsum("eab,eb->ea", Me, pc) - dt / eps ** 2 * Fe_res)
     return energy, re, Me + dt * Se - dt / eps ** 2 * dFe
+
+
+def implicit_scalar_energy_grads(physics, element_type, num_gp, X, fc, fn, params):
+    """Gradients of the element energy of the implicit-Euler scalar losses (the first return value of
+    transient_thermal.py:42-73 / phase_field.py:38-70, fully differentiated as jax.grad does -- the energies
+    carry no stop_gradient) w.r.t. the next field fn and the current field fc, both (ne, a)."""
+    elem = ELEMENTS[element_type]
+    Ns, gradN, detJ, w = point_data(elem, X, num_gp, transposed_inverse=True)
+    wd = w[None, :] * detJ
+    fn_g = np.einsum("ga,ea->eg", Ns, fn)
+    fc_g = np.einsum("ga,ea->eg", Ns, fc)
+    gf = np.einsum("egai,ea->egi", gradN, fn)                     # grad of the next field
+    flux = np.einsum("egai,egi->ega", gradN, gf)                  # grad N_a . grad f
+    g2 = np.einsum("egi,egi->eg", gf, gf)
+    if physics == "transient_thermal":
+        rho, cp, dt = params["rho"], params["cp"], params["time_step"]
+        beta, c = params.get("beta", 0.0), params.get("c", 1.0)
+        k_g = np.einsum("ga,ea->eg", Ns, params["k0"])
+        K_g = k_g * (1.0 + beta * fn_g ** c)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dk = k_g * beta * c * fn_g ** (c - 1.0)
+        dk = np.where(np.isfinite(dk), dk, 0.0)
+        rate = rho * cp / dt * wd * (fn_g - fc_g)
+        dn = np.einsum("eg,ega->ea", K_g * wd, flux) + np.einsum("eg,ga->ea", 0.5 * dk * wd * g2 + rate, Ns)
+    else:
+        dt, eps = params["dt"], params["epsilon"]
+        rate = wd / dt * (fn_g - fc_g)
+        dn = np.einsum("eg,ega->ea", wd, flux) + np.einsum("eg,ga->ea", wd / eps ** 2 * (fn_g ** 2 - 1.0) * fn_g + rate, Ns)
+    dc = -np.einsum("eg,ga->ea", rate, Ns)
+    return dn, dc

@@ -93,3 +93,49 @@ def test_mesh_assembly_matches_oracle(kind, etype):
         assert np.abs(R.cpu().numpy() - Rref).max() <= 4e-12 * np.abs(Rref).max()
     en_ref = assembly.compute_elements(phys, etype, loss.num_gp, coords, conn, cur, nxt, params)[0].sum()
     assert abs(loss.ComputeTotalEnergy(cur, nxt).item() - en_ref) <= 1e-12 * abs(en_ref)
+
+
+@pytest.mark.parametrize("kind,etype", [("tt", "quad"), ("tt", "tetra"), ("tt", "hexahedron"), ("ac", "quad"),
+                                        ("ac", "triangle"), ("ac", "hexahedron")])
+@pytest.mark.parametrize("exponent", [1.0, 2.0])
+def test_batch_loss_and_vjp_match_oracle(kind, etype, exponent):
+    """ComputeBatchLoss of the implicit-Euler losses: (params, dofs) = (current, next) fields; the energies are true
+    potentials, so both cotangents come from the energy (oracle pinned on finite differences in the CPU suite)."""
+    import torch
+    mesh = H.make_mesh(etype, 3 if etype in ("hexahedron", "tetra") else 6, seed=8)
+    rng = np.random.default_rng(3)
+    nn = mesh.GetNumberOfNodes()
+    B = 5
+    cur, nxt = rng.uniform(0.2, 1.0, (B, nn)), rng.uniform(0.2, 1.0, (B, nn))
+    if kind == "tt":
+        cls = {"quad": lf.TransientThermalLoss2DQuad, "hexahedron": lf.TransientThermalLoss3DHexa,
+               "tetra": lf.TransientThermalLoss3DTetra}[etype]
+        k0 = rng.uniform(0.5, 1.5, nn)
+        loss = cls("tt", {"dirichlet_bc_dict": {"T": {"left": 1.0, "right": 0.1}}, "c": 3,
+                          "loss_function_exponent": exponent,
+                          "material_dict": {"rho": 1.3, "cp": 0.7, "beta": 1.5, "k0": k0},
+                          "time_integration_dict": {"time_step": 0.01}}, mesh)
+        params = {"rho": 1.3, "cp": 0.7, "beta": 1.5, "c": 3, "k0": k0, "time_step": 0.01}
+        phys = "transient_thermal"
+    else:
+        cls = {"quad": lf.AllenCahnLoss2DQuad, "triangle": lf.AllenCahnLoss2DTri,
+               "hexahedron": lf.AllenCahnLoss3DHexa}[etype]
+        loss = cls("ac", {"dirichlet_bc_dict": {"Phi": {"left": 1.0}}, "loss_function_exponent": exponent,
+                          "material_dict": {"rho": 1.0, "cp": 1.0, "dt": 0.002, "epsilon": 0.3}}, mesh)
+        params = {"dt": 0.002, "epsilon": 0.3}
+        phys = "allen_cahn"
+    loss.Initialize()
+    ct = torch.tensor(cur, device="cuda", requires_grad=True)
+    nt = torch.tensor(nxt, device="cuda", requires_grad=True)
+    mean, (mn, mx, mean2) = loss.ComputeBatchLoss(ct, nt)
+    coords, conn = np.asarray(mesh.GetNodesCoordinates()), mesh.GetElementsNodes(etype)
+    args = (phys, etype, loss.num_gp, coords, conn, cur, nxt, loss.dirichlet_indices, loss.dirichlet_values, params)
+    ref_mean, (rmin, rmax, _), Eb = assembly.batch_loss(*args, exponent=exponent)
+    tol = 1e-12 * abs(Eb).max()
+    assert abs(mean.item() - ref_mean) <= tol and abs(mn.item() - rmin) <= tol and abs(mx.item() - rmax) <= tol
+    (1.5 * mean).backward()
+    gN, gC = assembly.batch_loss_grads(*args, exponent=exponent)
+    gn, gc = nt.grad.cpu().numpy() / 1.5, ct.grad.cpu().numpy() / 1.5
+    assert np.abs(gn - gN).max() <= 1e-12 * np.abs(gN).max()
+    assert np.abs(gc - gC).max() <= 1e-12 * np.abs(gC).max()
+    assert not gn[:, loss.dirichlet_indices].any()

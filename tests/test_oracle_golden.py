@@ -167,3 +167,38 @@ def test_allen_cahn_goldens(goldens, test, etype, num_gp, coords):
     en, re, Ke = losses.allen_cahn_element(etype, num_gp, X, np.ones((1, a)), np.zeros((1, a)), 0.001, 0.2)
     _check(Ke[0].reshape(-1), rec["asserts"][0])
     _check(re[0], rec["asserts"][1])
+
+
+@pytest.mark.parametrize("physics,etype,num_gp", [("transient_thermal", "quad", 2), ("transient_thermal", "tetra", 1),
+                                                  ("allen_cahn", "quad", 2), ("allen_cahn", "hexahedron", 2)])
+def test_implicit_scalar_batch_gradients_vs_finite_differences(physics, etype, num_gp):
+    """Pins the analytic cotangents of the implicit-Euler scalar losses (true potentials: jax.grad of the energy of
+    transient_thermal.py:42-73 / phase_field.py:38-70) on central differences of batch_loss."""
+    from oracle import assembly
+    from tests import gpu_helpers as H
+    mesh = H.make_mesh(etype, 2 if etype in ("hexahedron", "tetra") else 3, seed=3)
+    coords, conn = np.asarray(mesh.GetNodesCoordinates()), mesh.GetElementsNodes(etype)
+    nn = len(coords)
+    rng = np.random.default_rng(5)
+    cur, nxt = rng.uniform(0.2, 1.0, (2, nn)), rng.uniform(0.2, 1.0, (2, nn))
+    if physics == "transient_thermal":
+        params = {"rho": 1.3, "cp": 0.7, "beta": 1.5, "c": 3, "k0": rng.uniform(0.5, 1.5, nn), "time_step": 0.05}
+    else:
+        params = {"dt": 0.02, "epsilon": 0.3}
+    didx = np.asarray(mesh.GetNodeSet("left"), dtype=np.int64)
+    dval = np.full(didx.size, 0.7)
+    args = (physics, etype, num_gp, coords, conn)
+    gU, gK = assembly.batch_loss_grads(*args, cur, nxt, didx, dval, params, exponent=2.0)
+    free = np.setdiff1d(np.arange(nn), didx)
+    h = 1e-6
+    for _ in range(5):
+        b, i, j = rng.integers(2), rng.choice(free), rng.integers(nn)
+        for arr, idx, grad in ((nxt, i, gU), (cur, j, gK)):
+            ap, am = arr.copy(), arr.copy()
+            ap[b, idx] += h
+            am[b, idx] -= h
+            pair = (lambda a: (cur, a)) if arr is nxt else (lambda a: (a, nxt))
+            fp = assembly.batch_loss(*args, *pair(ap), didx, dval, params, exponent=2.0)[0]
+            fm = assembly.batch_loss(*args, *pair(am), didx, dval, params, exponent=2.0)[0]
+            assert abs((fp - fm) / (2 * h) - grad[b, idx]) <= 2e-6 * max(1.0, np.abs(grad).max())
+    assert not gU[:, didx].any()
