@@ -99,7 +99,8 @@ struct fol_plan {
   long long ne, nn, ndof;
   size_t esz;
   double params[FOL_NUM_PARAMS];
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t chunk_done[16] = {};
   void *xyz = nullptr, *ctrl = nullptr, *u = nullptr, *ke = nullptr, *re = nullptr, *R = nullptr;
   int32_t *conn = nullptr, *adj_ptr = nullptr, *adj = nullptr, *work = nullptr, *dir_idx = nullptr;
   uint8_t* dir = nullptr;
@@ -244,6 +245,9 @@ void fol_plan_destroy(fol_plan* p) {
   void* bufs[] = {p->xyz, p->ctrl, p->u, p->ke, p->re, p->R, p->conn, p->adj_ptr, p->adj, p->work, p->dir_idx, p->dir};
   for (void* b : bufs)
     if (b) cudaFree(b);
+  for (cudaEvent_t ev : p->chunk_done)
+    if (ev) cudaEventDestroy(ev);
+  if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
@@ -275,6 +279,8 @@ int fol_plan_create(fol_plan** plan, int dtype, int physics, int element, int nu
   p->esz = dtype == FOL_F64 ? 8 : 4;
   for (int i = 0; i < FOL_NUM_PARAMS; ++i) p->params[i] = params_host[i];
   FOL_PLAN_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  FOL_PLAN_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+  for (cudaEvent_t& ev : p->chunk_done) FOL_PLAN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   FOL_PLAN_CUDA(cudaMalloc(&p->xyz, p->esz * 3 * nn));
   FOL_PLAN_CUDA(cudaMalloc(&p->ctrl, p->esz * nn));
   FOL_PLAN_CUDA(cudaMalloc(&p->u, p->esz * p->ndof));
@@ -328,11 +334,27 @@ int fol_plan_assemble_host(fol_plan* p, int transpose, const void* ctrl_host, co
   FOL_REQUIRE(p && ctrl_host && u_host && ke_host && R_host, "fol_plan_assemble_host: null pointer");
   FOL_CUDA(cudaMemcpyAsync(p->ctrl, ctrl_host, p->esz * p->nn, cudaMemcpyHostToDevice, p->stream));
   FOL_CUDA(cudaMemcpyAsync(p->u, u_host, p->esz * p->ndof, cudaMemcpyHostToDevice, p->stream));
-  if (int rc = plan_run(p, transpose, p->ctrl, p->u)) return rc;
+  // The BCOO data (nd^2 values per element) dominates the transfer: the element stage runs in chunks and each
+  // chunk's matrices start their way to the host as soon as they exist, so the link never waits for the kernels.
+  constexpr int kChunks = 16;
+  const long long per = (p->ne + kChunks - 1) / kChunks;
+  const size_t ke_elem = p->esz * (size_t)p->nd * p->nd, re_elem = p->esz * (size_t)p->nd;
+  for (int c = 0; c < kChunks; ++c) {
+    const long long e0 = c * per, cnt = (e0 + per <= p->ne ? per : p->ne - e0);
+    if (cnt <= 0) break;
+    int rc = fol_assemble_elements(p->stream, p->dtype, p->physics, p->element, p->num_gp, transpose, cnt, p->nn, p->xyz,
+                                   p->conn + e0 * p->nnode, p->ctrl, p->u, p->dir, p->params,
+                                   (char*)p->ke + e0 * ke_elem, (char*)p->re + e0 * re_elem, nullptr, nullptr);
+    if (rc) return rc;
+    FOL_CUDA(cudaEventRecord(p->chunk_done[c], p->stream));
+    FOL_CUDA(cudaStreamWaitEvent(p->copy_stream, p->chunk_done[c], 0));
+    FOL_CUDA(cudaMemcpyAsync((char*)ke_host + e0 * ke_elem, (char*)p->ke + e0 * ke_elem, cnt * ke_elem,
+                             cudaMemcpyDeviceToHost, p->copy_stream));
+  }
+  if (int rc = fol_residual_gather(p->stream, p->dtype, p->nn, p->nnode, p->dpn, p->adj_ptr, p->adj, p->re, p->R)) return rc;
   FOL_CUDA(cudaMemcpyAsync(R_host, p->R, p->esz * p->ndof, cudaMemcpyDeviceToHost, p->stream));
-  FOL_CUDA(cudaMemcpyAsync(ke_host, p->ke, p->esz * (size_t)p->ne * p->nd * p->nd, cudaMemcpyDeviceToHost,
-                           p->stream));
   FOL_CUDA(cudaStreamSynchronize(p->stream));
+  FOL_CUDA(cudaStreamSynchronize(p->copy_stream));
   return FOL_OK;
 }
 
