@@ -26,6 +26,15 @@ sys.path.insert(0, ROOT)
 
 import numpy as np
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 ALG_BYTES_PER_ELEMENT_F64 = 4720.0   # 4608 Ke + 32 conn + 56 nodal in + 24 residual
 MATERIAL = {"young_modulus": 1.0, "poisson_ratio": 0.3}
 
@@ -148,7 +157,7 @@ def run_reference(args):
                                      "path: JAX is not installable in this image"},
             "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------ GPU leg
@@ -389,7 +398,7 @@ def run_ours(args):
         except Exception as ex:
             line["fol_loss_grad"] = {"error": str(ex)[:200]}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -439,7 +448,18 @@ def e2e_host(torch, lib, _lib, loss, mesh, K_host, u_host, ne, nn, ndof, args):
         lib.fol_plan_destroy(plan)
 
 
+def _claim_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) may write to fd 1; the contract is ONE JSON line on
+    stdout, so everything else is sent to stderr and only the final line goes to the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
