@@ -100,10 +100,23 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
       fxy[i][j] = 0.125 * (i ? 1.0 + px : 1.0 - px) * (j ? 1.0 + py : 1.0 - py);
     }
 
-  // software pipeline of the gathers: node ids two tiles ahead, nodal data one tile ahead
-  auto node_of = [&](long long t) -> long long {
+  // software pipeline of the gathers: node ids two tiles ahead, nodal data one tile ahead.
+  // The id comes back through a predicated load straight into its 32-bit register and is widened only where it is
+  // used, one tile later (hold_back below): any earlier dependent instruction -- a select, a sign extension --
+  // would make the warp sit out the full DRAM latency of the connectivity load (21 % of the stall samples before).
+  auto node_of = [&](long long t) -> int {
     const long long e = t * kTile + el_p;
-    return (t < ntiles && e < args.ne) ? (long long)__ldg(args.conn + e * 8 + sub) : 0;
+    const int ok = (t < ntiles && e < args.ne) ? 1 : 0;
+    const int32_t* src = args.conn + (ok ? e * 8 + sub : 0);
+    int n;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\tmov.s32 %0, 0;\n\t@p ld.global.nc.s32 %0, [%1];\n\t}\n"
+        : "=r"(n)
+        : "l"(src), "r"(ok));
+    return n;
+  };
+  auto hold_back = [](int& a, unsigned& b, unsigned& c, unsigned& d) {
+    asm volatile("" : "+r"(a), "+r"(b), "+r"(c), "+r"(d));
   };
   // asynchronous gather of one node straight into shared memory (no registers held across the tile)
   auto gather_async = [&](int buf, long long n) {
@@ -116,14 +129,16 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
   };
   // Dirichlet flags of the next tile's node: three byte loads kept in three registers, consumed one
   // tile later (packing them right away would stall on the load latency)
-  long long n_next = node_of(tile + nwarps);
-  gather_async(0, node_of(tile));
-  const uint8_t* pf0 = args.dir + node_of(tile) * 3;
+  int n_next = node_of(tile + nwarps);
+  const long long n_first = node_of(tile);
+  gather_async(0, n_first);
+  const uint8_t* pf0 = args.dir + n_first * 3;
   unsigned f0 = __ldg(pf0), f1 = __ldg(pf0 + 1), f2 = __ldg(pf0 + 2);
   int buf = 0;
 
   for (; tile < ntiles; tile += nwarps, buf ^= 1) {
     const long long e0 = tile * kTile;
+    hold_back(n_next, f0, f1, f2);   // loaded one tile ago; nothing may consume them before this point
 
     // ---- phase 0: this tile's nodal data has landed in shared memory; start the next gather
     sm.bc[el_p][sub * 3 + 0] = f0 ? 0.f : 1.f;
@@ -131,9 +146,9 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
     sm.bc[el_p][sub * 3 + 2] = f2 ? 0.f : 1.f;
     cp_async_wait_all();
     __syncwarp();
-    gather_async(buf ^ 1, n_next);                          // in flight during this tile
+    gather_async(buf ^ 1, (long long)n_next);               // in flight during this tile
     {
-      const uint8_t* pf = args.dir + n_next * 3;
+      const uint8_t* pf = args.dir + (long long)n_next * 3;
       f0 = __ldg(pf); f1 = __ldg(pf + 1); f2 = __ldg(pf + 2);
     }
     n_next = node_of(tile + 2 * nwarps);
@@ -224,6 +239,31 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
           for (int j = 0; j < 3; ++j)
             K[h][i][j] = lam * c[i][j][h] + mu * c[j][i][h] + (i == j ? mu * tr : 0.0);
       }
+      // (done before touching the staging slot: the previous element's copy keeps draining meanwhile)
+      // re = Ke u - Fe: partial over this lane's 6 columns, then butterfly over the 4 k-lanes
+      double r[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) acc += K[h][i][j] * sm.u[buf][j][el * 8 + 2 * kq + h];
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        r[i] = acc;
+      }
+      if (has_body) {  // Fe_a = b * sum_g w detJ N_a(g)   (mechanical.py:110)
+        double nw = 0.0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const double gx = 1.0 + sgn_x(ra) * sgn_x(g) * FOL_S3, gy = 1.0 + sgn_y(ra) * sgn_y(g) * FOL_S3;
+          const double gz = 1.0 + sgn_z(ra) * sgn_z(g) * FOL_S3;
+          nw += sm.wd[el][g] * (0.125 * gx * gy * gz);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r[i] -= args.p.v[2 + i] * nw;
+      }
       // stage the rows and hand them to the bulk-copy engine.  The Dirichlet row mask
       // (fe_loss.py:191-207) only matters for elements touching a fixed dof: warp-uniform test.
       const bool fixed_rows = (sm.bc[el][ra * 3 + 0] == 0.f) | (sm.bc[el][ra * 3 + 1] == 0.f) |
@@ -262,30 +302,6 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
       __syncwarp();
       if (lane == 0) bulk_store(args.ke + e * 576, sm.stage, 576 * sizeof(double));
 
-      // re = Ke u - Fe: partial over this lane's 6 columns, then butterfly over the 4 k-lanes
-      double r[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        double acc = 0.0;
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) acc += K[h][i][j] * sm.u[buf][j][el * 8 + 2 * kq + h];
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        r[i] = acc;
-      }
-      if (has_body) {  // Fe_a = b * sum_g w detJ N_a(g)   (mechanical.py:110)
-        double nw = 0.0;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const double gx = 1.0 + sgn_x(ra) * sgn_x(g) * FOL_S3, gy = 1.0 + sgn_y(ra) * sgn_y(g) * FOL_S3;
-          const double gz = 1.0 + sgn_z(ra) * sgn_z(g) * FOL_S3;
-          nw += sm.wd[el][g] * (0.125 * gx * gy * gz);
-        }
-#pragma unroll
-        for (int i = 0; i < 3; ++i) r[i] -= args.p.v[2 + i] * nw;
-      }
       if (kq == 0) {
 #pragma unroll
         for (int i = 0; i < 3; ++i)
