@@ -37,7 +37,7 @@ def _stamp():
 
 
 # per-file extras (register caps of the tuned kernels)
-EXTRA = {"assemble_hex.cu": ["-maxrregcount=144"]}
+EXTRA = {"assemble_hex.cu": ["-maxrregcount=144"] + os.environ.get("FOL_HEX_DEFS", "").split()}
 
 
 def _headers_hash():

@@ -318,7 +318,9 @@ __device__ __forceinline__ void linear_B(const T* g, T (&Ba)[voigt_size(D)][D]) 
 
 namespace fol {
 
-template <class T, int ELEM, int ORDER, int PHYS, int BLOCK>
+// MATVEC = matrix-free mode (args.v): a separate instantiation, so the assembling kernels carry none of its
+// registers or branches (as a run-time flag it cost them 10-20 %)
+template <class T, int ELEM, int ORDER, int PHYS, int BLOCK, bool MATVEC = false>
 __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) {
   using SM = GroupSmem<T, ELEM, ORDER, PHYS>;
   constexpr int A = SM::A, D = SM::D, DPN = SM::DPN, ND = SM::ND, NGP = SM::NGP, PD = SM::PD;
@@ -481,12 +483,12 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
   T* st = stage_all + (size_t)grp * (ND * ND);
   // matrix-free mode: the region after the groups holds, per group, v_e (ND) and the lanes' partial
   // products of Ke^T v_e (A x ND) instead of staged matrices
-  const bool matvec = args.v != nullptr;
+  constexpr bool matvec = MATVEC;
   T* mv = stage_all + (size_t)grp * (ND * (A + 1));
   T mv_diag[DPN];
 #pragma unroll
   for (int i = 0; i < DPN; ++i) mv_diag[i] = (T)0;
-  if (matvec) {
+  if constexpr (matvec) {
     if (active) {
       const long long n = args.conn[e * A + a];
 #pragma unroll
@@ -672,7 +674,7 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
     for (int i = 0; i < DPN; ++i) fint[i] -= P.v[2 + i] * nw;
   }
 
-  if (matvec) {
+  if constexpr (matvec) {
     // ---- matrix-free product with the masked element matrix (fe_loss.py:191-230 applied to Ke or Ke^T):
     //      y_r = free row ? sum_c Ke(^T)[r][c] v_c : Ke[r][r] v_r
     if (!args.transpose) {
@@ -737,7 +739,7 @@ __global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) 
   }  // !matvec
   }  // active
 
-  if (matvec) {
+  if constexpr (matvec) {
     if (args.transpose) {
       __syncwarp();
       if (active) {
@@ -798,13 +800,24 @@ int launch_assemble(cudaStream_t s, const AsmArgs<T>& args) {
   constexpr size_t kPerGroupMv = sizeof(SM) + sizeof(T) * SM::ND * (SM::A + 1);
   constexpr size_t kMaxSmem = (kPerGroup > kPerGroupMv ? kPerGroup : kPerGroupMv) * GPB;
   const size_t smem = (args.v ? kPerGroupMv : kPerGroup) * GPB;
-  auto kern = assemble_kernel<T, ELEM, ORDER, PHYS, BLOCK>;
+  const long long grid = cdiv(args.ne, GPB);
+  if (args.v) {
+    auto kern = assemble_kernel<T, ELEM, ORDER, PHYS, BLOCK, true>;
+    static bool configured = false;
+    if (!configured) {
+      FOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+      configured = true;
+    }
+    if (grid == 0) return FOL_OK;
+    kern<<<(unsigned)grid, BLOCK, smem, s>>>(args);
+    return check_launch("assemble_kernel (matrix-free)");
+  }
+  auto kern = assemble_kernel<T, ELEM, ORDER, PHYS, BLOCK, false>;
   static bool configured = false;
   if (!configured) {
     FOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
     configured = true;
   }
-  const long long grid = cdiv(args.ne, GPB);
   if (grid == 0) return FOL_OK;
   kern<<<(unsigned)grid, BLOCK, smem, s>>>(args);
   return check_launch("assemble_kernel");

@@ -21,11 +21,18 @@ namespace fol {
 
 namespace {
 
-constexpr int kWarps = 6;            // warps per CTA, each fully independent (2 CTAs = 12 warps / SM)
+#ifndef FOL_HEX_WARPS
+#define FOL_HEX_WARPS 6
+#endif
+#ifndef FOL_HEX_SLOTS
+#define FOL_HEX_SLOTS 1
+#endif
+constexpr int kWarps = FOL_HEX_WARPS;   // warps per CTA, each fully independent (2 CTAs = 12 warps / SM)
+constexpr int kSlots = FOL_HEX_SLOTS;   // Ke staging slots per warp
 constexpr int kTile = 4;             // elements per warp iteration
 
 struct __align__(128) WarpSmem {
-  double stage[576];                 // Ke staging slot (bulk-copy source)
+  double stage[kSlots][576];         // Ke staging slots (bulk-copy sources)
   // [element][gauss][node ^ swz(gauss)]: (dN/dx, dN/dy) and (dN/dz, w detJ E_g).  The XOR swizzle
   // swz(g) = ((g & 3) << 1) | (g >> 2) makes both the phase-1 stores (lane = row) and the DMMA
   // fragment loads (lane = (node, gauss mod 4)) bank-conflict free without padding.
@@ -269,12 +276,13 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
       const bool fixed_rows = (sm.bc[el][ra * 3 + 0] == 0.f) | (sm.bc[el][ra * 3 + 1] == 0.f) |
                               (sm.bc[el][ra * 3 + 2] == 0.f);
       const bool any_fixed = __any_sync(0xffffffffu, fixed_rows);
-      if (lane == 0) bulk_wait_read<0>();   // the previous element's copy has drained the slot
+      double* const slot = sm.stage[kSlots > 1 ? (el & (kSlots - 1)) : 0];
+      if (lane == 0) bulk_wait_read<kSlots - 1>();   // the copy that last used this slot has drained it
       __syncwarp();
       if (!any_fixed) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          double2* dst = reinterpret_cast<double2*>(sm.stage + (ra * 3 + i) * 24 + kq * 6);
+          double2* dst = reinterpret_cast<double2*>(slot + (ra * 3 + i) * 24 + kq * 6);
           dst[0] = make_double2(K[0][i][0], K[0][i][1]);
           dst[1] = make_double2(K[0][i][2], K[1][i][0]);
           dst[2] = make_double2(K[1][i][1], K[1][i][2]);
@@ -292,7 +300,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
               const int col = (2 * kq + h) * 3 + j;
               v[h * 3 + j] = (freerow || col == row) ? K[h][i][j] : 0.0;
             }
-          double2* dst = reinterpret_cast<double2*>(sm.stage + row * 24 + kq * 6);
+          double2* dst = reinterpret_cast<double2*>(slot + row * 24 + kq * 6);
           dst[0] = make_double2(v[0], v[1]);
           dst[1] = make_double2(v[2], v[3]);
           dst[2] = make_double2(v[4], v[5]);
@@ -300,7 +308,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) bulk_store(args.ke + e * 576, sm.stage, 576 * sizeof(double));
+      if (lane == 0) bulk_store(args.ke + e * 576, slot, 576 * sizeof(double));
 
       if (kq == 0) {
 #pragma unroll

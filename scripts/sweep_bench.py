@@ -78,3 +78,7 @@ del tet
 hex96 = folax_b200.create_3D_box_mesh(96, 96, 96, 1.0, 1.0, 1.0)
 case("hex96_neohooke_f64", lf.NeoHookeMechanicalLoss3DHexa, hex96, "hexahedron", {"dirichlet_bc_dict": bc3, "material_dict": MAT}, "float64", lambda x: 0.02 / 96 * x)
 case("hex96_j2_f64 (config 5 per-GPU share is 128^3)", lf.ElastoplasticityLoss3DHexa, hex96, "hexahedron", {"dirichlet_bc_dict": bc3, "material_dict": J2MAT}, "float64", lambda x: 0.15 / 96 * x, state=True)
+del hex96
+hex128 = folax_b200.create_3D_box_mesh(128, 128, 128, 1.0, 1.0, 1.0)
+case("hex128_j2_f64 (config 5: per-GPU share of the 256^3 mesh on 8 GPUs)", lf.ElastoplasticityLoss3DHexa, hex128, "hexahedron",
+     {"dirichlet_bc_dict": bc3, "material_dict": J2MAT}, "float64", lambda x: 0.15 / 128 * x, state=True)
