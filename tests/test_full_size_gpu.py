@@ -91,3 +91,48 @@ def test_linearity_rigid_modes_and_symmetry(big):
     assert Rt.abs().max().item() <= 1e-12
     # total force balance: the assembled internal forces of a free body sum to zero
     assert abs(R1.view(-1, 3).sum(0)).max().item() <= 1e-9 * scale
+
+
+def test_fol_config3_full_size_batched_loss():
+    """configs[2] at full size: 1024 conductivity fields on the 256x256 thermal quad mesh.  The pipelined kernel runs
+    with several sample chunks per tile here (unlike the small parity cases): sampled rows against the oracle, the whole
+    batch against the generic kernel, and run-to-run bit-identity."""
+    import os
+    import torch
+    from folax_b200.loss_functions import ThermalLoss2DQuad
+    mesh = folax_b200.create_2D_square_mesh(1.0, 257)
+    loss = ThermalLoss2DQuad("fol", {"dirichlet_bc_dict": {"T": {"left": 1.0, "right": 0.1}}, "beta": 2.0, "c": 4}, mesh)
+    loss.Initialize()
+    nn, B = mesh.GetNumberOfNodes(), 1024
+    g = torch.Generator(device="cuda").manual_seed(3)
+    K = torch.rand((B, nn), generator=g, device="cuda", dtype=torch.float64) * 0.9 + 0.1
+    u = torch.rand((B, nn), generator=g, device="cuda", dtype=torch.float64)
+
+    def run():
+        kk, uu = K.clone().requires_grad_(True), u.clone().requires_grad_(True)
+        mean, (mn, mx, _) = loss.ComputeBatchLoss(kk, uu)
+        mean.backward()
+        return mean.detach(), mn.detach(), mx.detach(), uu.grad, kk.grad
+
+    a = run()
+    b = run()
+    assert all(bool((x == y).all()) for x, y in zip(a, b))                     # deterministic
+    os.environ["FOL_ENERGY_V1"] = "1"                                          # generic kernel, same plan
+    try:
+        c = run()
+    finally:
+        del os.environ["FOL_ENERGY_V1"]
+    for x, y in zip(a, c):
+        assert (x - y).abs().max().item() <= 1e-13 * y.abs().max().item()
+    coords, conn = np.asarray(mesh.GetNodesCoordinates()), mesh.GetElementsNodes("quad")
+    rows = [0, 511, 1023]
+    Ks, us = K[rows].cpu().numpy(), u[rows].cpu().numpy()
+    args = ("thermal", "quad", 2, coords, conn, Ks, us, loss.dirichlet_indices, loss.dirichlet_values,
+            {"beta": 2.0, "c": 4})
+    gU, gK = assembly.batch_loss_grads(*args)                                  # scaled by 1/3 (its own batch)
+    _, _, Eb = assembly.batch_loss(*args)
+    gu, gk = a[3][rows].cpu().numpy() * B / 3.0, a[4][rows].cpu().numpy() * B / 3.0
+    assert np.abs(gu - gU).max() <= 1e-12 * np.abs(gU).max()
+    assert np.abs(gk - gK).max() <= 1e-12 * np.abs(gK).max()
+    energies = loss._energy_and_grads(K, loss.GetFullDofVector(None, u))[0][rows].cpu().numpy()
+    assert np.abs(energies - Eb).max() <= 1e-12 * np.abs(Eb).max()
