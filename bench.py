@@ -316,6 +316,12 @@ def run_ours(args):
     ke = torch.empty(ne * 576, dtype=torch.float64, device="cuda")
 
     comm_stream = torch.cuda.Stream() if world > 1 else None
+    halo_mode = "none"
+    if world > 1:
+        try:   # NVLink peer stores fused with the interface-plane gather (csrc/halo.cu); NCCL send/recv otherwise
+            halo_mode = "nvlink peer stores fused with the plane gather" if part.enable_peer_halo(loss) else "nccl send/recv"
+        except Exception as ex:
+            halo_mode = f"nccl send/recv (peer memory unavailable: {str(ex)[:80]})"
 
     def step():
         if world > 1:   # halo-DOF exchange hidden behind the interior element stage
@@ -366,7 +372,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"hex{n}_linear_elastic_residual_jacobian_f64", "elements_per_gpu": ne,
                        "dofs_per_gpu": ndof, "num_gp": 2, "output": "BCOO data with duplicates + residual",
-                       "parallelism": f"element slabs x{world} + halo-DOF sum" if world > 1 else "single GPU",
+                       "parallelism": f"element slabs x{world} + halo-DOF sum ({halo_mode})" if world > 1 else "single GPU",
                        "l2_policy": "per-step working set (9.7 GB Ke stream) >> 126 MB L2"},
             "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks.summary()}
 

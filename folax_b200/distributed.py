@@ -78,6 +78,42 @@ class SlabPartition:
         return residual
 
 
+    # ---- NVLink peer-memory exchange (csrc/halo.cu): gather of an interface plane fused with the transfer
+    _halo = None
+    _halo_step = 0
+
+    def enable_peer_halo(self, loss, group=None):
+        """Create this rank's receive buffers, swap CUDA IPC handles with the neighbours (one all_gather of 64
+        bytes per rank) and open theirs.  After this, assemble_overlapped pushes the interface-plane partial sums
+        straight into the neighbour's memory from the gather kernel instead of calling NCCL send/recv."""
+        import ctypes as C
+        from . import _lib
+        if self.world == 1:
+            return False
+        lib = _lib.load()
+        d = loss.number_dofs_per_node
+        h = C.c_void_p()
+        _lib.check(lib.fol_halo_create(C.byref(h), loss._dt, self.plane_nodes * d))
+        raw = (C.c_ubyte * 64)()
+        _lib.check(lib.fol_halo_export(h, raw))
+        mine = torch.tensor(list(raw), dtype=torch.uint8, device=loss.device)
+        handles = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(handles, mine, group=group)
+        for side, nb in ((0, self.rank - 1), (1, self.rank + 1)):
+            if 0 <= nb < self.world:
+                buf = (C.c_ubyte * 64)(*handles[nb].cpu().tolist())
+                _lib.check(lib.fol_halo_connect(h, side, buf))
+        self._halo, self._halo_step = h, 0
+        return True
+
+    def close_peer_halo(self):
+        if self._halo is not None:
+            from . import _lib
+            torch.cuda.synchronize()
+            _lib.load().fol_halo_destroy(self._halo)
+            self._halo = None
+
+
 GRID_MARGIN_CTAS = 0   # measured on 2/4/8 B200: a margin does not pay; NCCL's kernels fit next to the persistent CTAs
 
 
@@ -122,6 +158,27 @@ def assemble_overlapped(loss, part, controls, dofs, ke_out, comm_stream, group=N
         _lib.check(lib.fol_residual_gather(s, dt, cnt, A, d, loss._adj_ptr.data_ptr() + 4 * n0, _lib.ptr(loss._adj),
                                            _lib.ptr(re), R.data_ptr() + esz * d * n0))
 
+    if part.world > 1 and part._halo is not None:
+        # NVLink peer path: plane gather + push in one kernel, add after the interior work (no NCCL, no side stream)
+        step, h = part._halo_step, part._halo
+        part._halo_step += 1
+
+        def push(side, n0):
+            _lib.check(lib.fol_halo_gather_push(s, h, side, step, n0, plane, d, _lib.ptr(loss._adj_ptr),
+                                                _lib.ptr(loss._adj), _lib.ptr(re), _lib.ptr(R)))
+        if part.nz_local == 1:
+            elements(0, ne)
+        else:
+            elements(0, layer)
+            elements(ne - layer, layer)
+        push(0, 0)
+        push(1, nn - plane)
+        if part.nz_local > 2:
+            elements(layer, ne - 2 * layer)
+        gather(plane, nn - 2 * plane)
+        for side, n0 in ((0, 0), (1, nn - plane)):
+            _lib.check(lib.fol_halo_add(s, h, side, step, n0, plane, d, _lib.ptr(R)))
+        return ke_out, R
     if part.world == 1 or part.nz_local < 3:
         elements(0, ne)
         gather(0, nn)

@@ -221,6 +221,25 @@ int fol_measure_fma_peak(int dtype, double* tflops);
  * ceiling of a store-dominated kernel such as the Jacobian assembly. */
 int fol_measure_write_bandwidth(int64_t bytes, double* gbs);
 
+/* ---- halo-DOF exchange of a slab-partitioned mesh over NVLink peer memory (one process per GPU) ----
+ * Each rank creates one object for its interface planes (plane_dofs = nodes per plane * dofs per node),
+ * exports a 64-byte CUDA IPC handle, receives its neighbours' handles through whatever transport the
+ * host has (torch.distributed here) and connects them (side 0 = rank-1, side 1 = rank+1).
+ * fol_halo_gather_push = deterministic residual gather of one interface plane FUSED with the peer
+ * stores into the neighbour's receive buffer and an arrival signal; fol_halo_add = wait (on the device)
+ * for the neighbour's push of `step` and add it to the plane.  Every rank calls push(step) before
+ * add(step), with the same step sequence 0, 1, 2, ... */
+typedef struct fol_halo fol_halo;
+int fol_halo_create(fol_halo** halo, int dtype, int64_t plane_dofs);
+void fol_halo_destroy(fol_halo* halo);
+int fol_halo_export(fol_halo* halo, void* handle64);
+int fol_halo_connect(fol_halo* halo, int side, const void* handle64);
+int fol_halo_gather_push(fol_stream_t s, fol_halo* halo, int side, int64_t step, int64_t n0,
+                         int64_t count, int dofs_per_node, const int32_t* adj_ptr,
+                         const int32_t* adj, const void* re_elem, void* residual);
+int fol_halo_add(fol_stream_t s, fol_halo* halo, int side, int64_t step, int64_t n0, int64_t count,
+                 int dofs_per_node, void* residual);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,15 @@ def _worker(rank, world, port, out):
         for _ in range(3):
             data, R = assemble_overlapped(loss, part, K, u, ke, comm)
         torch.cuda.synchronize()
+        R_nccl = R.clone()
+        # same exchange over NVLink peer memory (csrc/halo.cu): gather fused with the push, device-side arrival wait
+        assert part.enable_peer_halo(loss)
+        for _ in range(5):                         # several steps: both buffer parities, counters keep counting
+            data, R = assemble_overlapped(loss, part, K, u, ke, comm)
+        torch.cuda.synchronize()
+        assert bool((R == R_nccl).all()), "peer-memory halo sum differs from the NCCL send/recv path"
+        dist.barrier()
+        part.close_peer_halo()
         out[rank] = (gids, R.cpu().numpy(), data.cpu().numpy(), part.element_offset)
     finally:
         dist.destroy_process_group()
