@@ -227,8 +227,14 @@ def allreduce_gradients(parameters, group=None, bucket_bytes=64 << 20):
             off += g.numel()
         bucket, size = [], 0
     for g in grads:
+        nbytes = g.numel() * g.element_size()
+        if nbytes >= bucket_bytes // 4 and g.is_contiguous():
+            # a large gradient (the output layer of a FOL network) is reduced in place: flattening it into a bucket
+            # and copying it back would cost two extra passes over it
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+            continue
         bucket.append(g)
-        size += g.numel() * g.element_size()
+        size += nbytes
         if size >= bucket_bytes:
             flush()
     flush()
