@@ -361,7 +361,7 @@ def run_ours(args):
     hbm, peak_src = measured_peaks()
     achieved = ALG_BYTES_PER_ELEMENT_F64 * ne / (ms_kernel * 1e-3) / 1e9
     # DRAM bytes per launch of this kernel from the committed ncu --set full capture (128^3 only)
-    traffic = 10.347e9 if (n == 128 and world == 1) else None
+    traffic = 10.356e9 if (n == 128 and world == 1) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                 "traffic": traffic, "traffic_source": "profiles/r1/assemble_hex_ncu_summary.txt (dram read + write)", "kernel": "assemble_hex_mech_f64_kernel (element stage: DMMA m8n8k4 + cp.async.bulk stores)",
                 "kernel_ms": ms_kernel, "algorithmic_bytes_per_element": ALG_BYTES_PER_ELEMENT_F64,
