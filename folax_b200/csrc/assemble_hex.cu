@@ -29,6 +29,10 @@ namespace {
 #endif
 constexpr int kWarps = FOL_HEX_WARPS;   // warps per CTA, each fully independent (2 CTAs = 12 warps / SM)
 constexpr int kSlots = FOL_HEX_SLOTS;   // Ke staging slots per warp
+#ifndef FOL_HEX_HALVES
+#define FOL_HEX_HALVES 0
+#endif
+constexpr bool kHalves = FOL_HEX_HALVES != 0;   // release / refill the staging slot in two halves
 constexpr int kTile = 4;             // elements per warp iteration
 
 struct __align__(128) WarpSmem {
@@ -277,43 +281,66 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
                               (sm.bc[el][ra * 3 + 2] == 0.f);
       const bool any_fixed = __any_sync(0xffffffffu, fixed_rows);
       double* const slot = sm.stage[kSlots > 1 ? (el & (kSlots - 1)) : 0];
-      if (lane == 0) bulk_wait_read<kSlots - 1>();   // the copy that last used this slot has drained it
-      __syncwarp();
-      if (!any_fixed) {
+      auto write_rows = [&]() {
+        if (!any_fixed) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          double2* dst = reinterpret_cast<double2*>(slot + (ra * 3 + i) * 24 + kq * 6);
-          dst[0] = make_double2(K[0][i][0], K[0][i][1]);
-          dst[1] = make_double2(K[0][i][2], K[1][i][0]);
-          dst[2] = make_double2(K[1][i][1], K[1][i][2]);
+          for (int i = 0; i < 3; ++i) {
+            double2* dst = reinterpret_cast<double2*>(slot + (ra * 3 + i) * 24 + kq * 6);
+            dst[0] = make_double2(K[0][i][0], K[0][i][1]);
+            dst[1] = make_double2(K[0][i][2], K[1][i][0]);
+            dst[2] = make_double2(K[1][i][1], K[1][i][2]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const int row = ra * 3 + i;
+            const bool freerow = sm.bc[el][row] != 0.f;
+            double v[6];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                const int col = (2 * kq + h) * 3 + j;
+                v[h * 3 + j] = (freerow || col == row) ? K[h][i][j] : 0.0;
+              }
+            double2* dst = reinterpret_cast<double2*>(slot + row * 24 + kq * 6);
+            dst[0] = make_double2(v[0], v[1]);
+            dst[1] = make_double2(v[2], v[3]);
+            dst[2] = make_double2(v[4], v[5]);
+          }
         }
+      };
+      auto store_re = [&]() {
+        if (kq == 0) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            args.re[e * 24 + ra * 3 + i] = (any_fixed && sm.bc[el][ra * 3 + i] == 0.f) ? 0.0 : r[i];
+        }
+      };
+      if constexpr (kHalves) {
+        // the slot is released and refilled in two halves (rows 0-11, 12-23), each its own bulk copy: a half only
+        // waits for the copy issued two copies earlier, so the engine always has one copy in flight
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        if (ra < 4) write_rows();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) bulk_store(args.ke + e * 576, slot, 288 * sizeof(double));
+        store_re();
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        if (ra >= 4) write_rows();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) bulk_store(args.ke + e * 576 + 288, slot + 288, 288 * sizeof(double));
       } else {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const int row = ra * 3 + i;
-          const bool freerow = sm.bc[el][row] != 0.f;
-          double v[6];
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              const int col = (2 * kq + h) * 3 + j;
-              v[h * 3 + j] = (freerow || col == row) ? K[h][i][j] : 0.0;
-            }
-          double2* dst = reinterpret_cast<double2*>(slot + row * 24 + kq * 6);
-          dst[0] = make_double2(v[0], v[1]);
-          dst[1] = make_double2(v[2], v[3]);
-          dst[2] = make_double2(v[4], v[5]);
-        }
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) bulk_store(args.ke + e * 576, slot, 576 * sizeof(double));
-
-      if (kq == 0) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-          args.re[e * 24 + ra * 3 + i] = (any_fixed && sm.bc[el][ra * 3 + i] == 0.f) ? 0.0 : r[i];
+        if (lane == 0) bulk_wait_read<kSlots - 1>();   // the copy that last used this slot has drained it
+        __syncwarp();
+        write_rows();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) bulk_store(args.ke + e * 576, slot, 576 * sizeof(double));
+        store_re();
       }
     }
     __syncwarp();  // everyone is done with X / u / gradients of this tile
