@@ -77,8 +77,14 @@ def _grad_worker(rank, world, port, out):
         sl = shard_batch(6, rank, world)
         loss = net(x[sl]).pow(2).sum() / 6
         loss.backward()
-        allreduce_gradients(list(net.parameters()), bucket_bytes=64)   # tiny buckets: several NCCL-style calls
+        ref = [p.grad.clone() for p in net.parameters()]
+        allreduce_gradients(list(net.parameters()), bucket_bytes=64)        # every gradient is "large": reduced in place
         out[rank] = [p.grad.numpy().copy() for p in net.parameters()]
+        for p, g in zip(net.parameters(), ref):
+            p.grad = g.clone()
+        allreduce_gradients(list(net.parameters()), bucket_bytes=1 << 20)   # all in one flattened bucket
+        for p, g in zip(net.parameters(), out[rank]):
+            np.testing.assert_allclose(p.grad.numpy(), g, atol=1e-15)
     finally:
         dist.destroy_process_group()
 
