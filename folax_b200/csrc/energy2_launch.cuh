@@ -58,7 +58,9 @@ int launch_energy2(cudaStream_t s, const EnergyArgs<T>& args, int ncap, int* par
 template <class T, int ELEM, int ORDER, int PHYS, int NL = -1>
 int launch_energy2_default(cudaStream_t s, const EnergyArgs<T>& args, int ncap, int* parts) {
   constexpr int S = energy2_samples<T, ELEM, PHYS, ENERGY2_BLOCK, ENERGY2_LCAP>();
-  return launch_energy2<T, ELEM, ORDER, PHYS, NL, S, ENERGY2_BLOCK, 2, ENERGY2_LCAP>(s, args, ncap, parts);
+  // float32 halves the registers of the geometry factors and the shared memory: three CTAs per SM
+  constexpr int MINB = (sizeof(T) == 4 && (PHYS == THERMAL || PHYS == MECH)) ? 3 : 2;
+  return launch_energy2<T, ELEM, ORDER, PHYS, NL, S, ENERGY2_BLOCK, MINB, ENERGY2_LCAP>(s, args, ncap, parts);
 }
 
 }  // namespace fol
