@@ -106,7 +106,7 @@ def cpu_assembly_rate(n_side, min_seconds, threads):
     host threads.  Returns (elements/s, elements done, seconds)."""
     import folax_b200
     from oracle import assembly, c_oracle
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    threads = c_oracle.set_threads(threads)   # torchrun exports OMP_NUM_THREADS=1: set the count explicitly
     mesh = folax_b200.create_3D_box_mesh(n_side, n_side, n_side, 1.0, 1.0, 1.0)
     coords, conn = np.asarray(mesh.GetNodesCoordinates()), mesh.GetElementsNodes("hexahedron")
     rng = np.random.default_rng(0)

@@ -8,6 +8,9 @@
  * Built by oracle/c/Makefile into oracle/_build/liboracle_hex.so; never linked by the product. */
 #include <math.h>
 #include <stdint.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <string.h>
 
 static const double SX[8] = {-1, 1, 1, -1, -1, 1, 1, -1};
@@ -86,6 +89,22 @@ static void element(const double X[8][3], const double de[8], const double u[24]
 }
 
 /* data (ne*576), residual (3*nn, zeroed here); dir_flag[ndof] = 1 on Dirichlet dofs */
+/* thread count of the parallel loops (the launcher may have exported OMP_NUM_THREADS=1, e.g. torchrun) */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
 void oracle_hex_mech_assemble(int64_t ne, int64_t nn, const double* xyz, const int32_t* conn, const double* ctrl,
                               const double* uvec, const uint8_t* dir_flag, double E, double nu, const double* body,
                               int transpose, double* data, double* residual) {

@@ -23,7 +23,16 @@ def load():
     lib.oracle_hex_mech_assemble.restype = None
     lib.oracle_hex_mech_assemble.argtypes = [ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 5 + \
         [ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    lib.oracle_set_threads.argtypes = [ctypes.c_int]
+    lib.oracle_max_threads.restype = ctypes.c_int
     return lib
+
+
+def set_threads(n):
+    """Thread count of the OpenMP loops, whatever OMP_NUM_THREADS the launcher exported; returns the count in effect."""
+    lib = load()
+    lib.oracle_set_threads(int(n))
+    return int(lib.oracle_max_threads())
 
 
 def hex_mech_assemble(coords, conn, ctrl, u, dirichlet_indices, E, nu, body=None, transpose=False, out=None):
