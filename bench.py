@@ -50,7 +50,7 @@ def measured_peaks():
 class ClockSampler:
     """Samples SM clock + throttle reasons during the timed region (NVML)."""
 
-    def __init__(self, index=0, period=0.1):
+    def __init__(self, index=0, period=0.005):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thread = None
@@ -340,7 +340,14 @@ def run_ours(args):
         torch.cuda.synchronize()
         ms = event_time_ms(torch, step, args.steps)
         torch.cuda.synchronize()
-    launches = lib.fol_launch_count() - launches0
+        launches = lib.fol_launch_count() - launches0
+        # the timed region is only tens of milliseconds: keep the same step running (untimed) under the sampler
+        # until it has seen the clocks under this load for >= 0.25 s
+        t_load = time.perf_counter()
+        while time.perf_counter() - t_load < 0.25:
+            for _ in range(10):
+                step()
+            torch.cuda.synchronize()
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.barrier()
