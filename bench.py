@@ -336,23 +336,23 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     launches0 = lib.fol_launch_count()
-    with ClockSampler(local_rank) as clocks:
-        torch.cuda.synchronize()
-        ms = event_time_ms(torch, step, args.steps)
-        torch.cuda.synchronize()
-        launches = lib.fol_launch_count() - launches0
-        # the timed region is only tens of milliseconds: keep the same step running (untimed) under the sampler
-        # until it has seen the clocks under this load for >= 0.25 s
-        t_load = time.perf_counter()
-        while time.perf_counter() - t_load < 0.25:
-            for _ in range(10):
-                step()
-            torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()
+    torch.cuda.synchronize()
+    ms = event_time_ms(torch, step, args.steps)
+    torch.cuda.synchronize()
+    launches = lib.fol_launch_count() - launches0
     t = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.barrier()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
+    # the timed region is only tens of milliseconds: keep the same step running (untimed) under the clock sampler for
+    # ~0.25 s more.  The count comes from the all-reduced time, so every rank runs the same number of exchanges.
+    for _ in range(int(min(2000, max(10, 250.0 / ms)))):
+        step()
+    torch.cuda.synchronize()
+    clocks.__exit__()
     value = ne * world / (ms * 1e-3)
 
     # dominant kernel alone (element stage), CUDA events on the launching stream
@@ -413,6 +413,7 @@ def run_ours(args):
     if rank == 0:
         emit(line)
     if world > 1:
+        part.close_peer_halo()   # raises if a halo wait ever timed out
         dist.barrier()
         dist.destroy_process_group()
 

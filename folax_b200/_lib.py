@@ -57,6 +57,7 @@ SIGNATURES = {
     "fol_halo_connect": (_int, [_vp, _int, _vp]),
     "fol_halo_gather_push": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _int, _i32p, _i32p, _vp, _vp]),
     "fol_halo_add": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _int, _vp]),
+    "fol_halo_timeouts": (_i64, [_vp]),
     "fol_plan_assemble_host": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
     "fol_plan_assemble_device": (_int, [_vp, _int, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "fol_plan_stream": (_vp, [_vp]),

@@ -41,11 +41,17 @@ __global__ void halo_gather_push_kernel(long long n0, long long count, int d, co
 template <class T>
 __global__ void halo_add_kernel(long long n0, long long count, int d, const T* __restrict__ recv,
                                 const unsigned long long* __restrict__ arrive, unsigned long long target,
-                                T* __restrict__ R) {
+                                unsigned long long* __restrict__ timeouts, T* __restrict__ R) {
   if (threadIdx.x == 0) {
     unsigned long long seen;
+    const long long t0 = clock64();
     do {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(arrive) : "memory");
+      // a neighbour that died must not hang this GPU: give up after ~2 s and count it (fol_halo_timeouts)
+      if (seen < target && clock64() - t0 > 4000000000LL) {
+        atomicAdd(timeouts, 1ULL);
+        break;
+      }
     } while (seen < target);
   }
   __syncthreads();
@@ -67,6 +73,7 @@ struct fol_halo {
   unsigned char* peer[2] = {nullptr, nullptr};   // opened allocations of the lower / upper neighbour
   size_t recv_off(int side, int parity) const { return ((size_t)side * 2 + parity) * plane_dofs * esz; }
   size_t arrive_off(int side, int parity) const { return (size_t)4 * plane_dofs * esz + ((size_t)side * 2 + parity) * 8; }
+  size_t timeout_off() const { return (size_t)4 * plane_dofs * esz + 32; }
 };
 
 extern "C" {
@@ -146,13 +153,22 @@ int fol_halo_add(fol_stream_t s, fol_halo* h, int side, int64_t step, int64_t n0
   const unsigned long long target = (unsigned long long)(step / 2 + 1) * h->ctas;
   const void* recv = h->base + h->recv_off(side, parity);
   const auto* arrive = reinterpret_cast<const unsigned long long*>(h->base + h->arrive_off(side, parity));
+  auto* timeouts = reinterpret_cast<unsigned long long*>(h->base + h->timeout_off());
   if (h->dtype == FOL_F64)
     halo_add_kernel<double><<<h->ctas, 256, 0, (cudaStream_t)s>>>(n0, count, d, (const double*)recv, arrive, target,
-                                                                 (double*)residual);
+                                                                 timeouts, (double*)residual);
   else
     halo_add_kernel<float><<<h->ctas, 256, 0, (cudaStream_t)s>>>(n0, count, d, (const float*)recv, arrive, target,
-                                                                (float*)residual);
+                                                                timeouts, (float*)residual);
   return check_launch("halo_add_kernel");
+}
+
+/* number of arrival waits that gave up (a neighbour never pushed): synchronising read, 0 in a healthy run */
+int64_t fol_halo_timeouts(fol_halo* h) {
+  if (!h) return -1;
+  unsigned long long v = 0;
+  if (cudaMemcpy(&v, h->base + h->timeout_off(), sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)v;
 }
 
 }  // extern "C"

@@ -107,11 +107,15 @@ class SlabPartition:
         return True
 
     def close_peer_halo(self):
+        """Releases the peer buffers; raises if any arrival wait gave up (a neighbour never pushed)."""
         if self._halo is not None:
             from . import _lib
             torch.cuda.synchronize()
+            lost = _lib.load().fol_halo_timeouts(self._halo)
             _lib.load().fol_halo_destroy(self._halo)
             self._halo = None
+            if lost:
+                raise _lib.FolaxError(f"halo exchange: {lost} arrival waits timed out (a neighbour rank never pushed)")
 
 
 GRID_MARGIN_CTAS = 0   # measured on 2/4/8 B200: a margin does not pay; NCCL's kernels fit next to the persistent CTAs

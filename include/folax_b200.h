@@ -239,6 +239,8 @@ int fol_halo_gather_push(fol_stream_t s, fol_halo* halo, int side, int64_t step,
                          const int32_t* adj, const void* re_elem, void* residual);
 int fol_halo_add(fol_stream_t s, fol_halo* halo, int side, int64_t step, int64_t n0, int64_t count,
                  int dofs_per_node, void* residual);
+/* arrival waits that gave up after ~2 s (a neighbour never pushed); synchronises; 0 in a healthy run */
+int64_t fol_halo_timeouts(fol_halo* halo);
 
 #ifdef __cplusplus
 }
