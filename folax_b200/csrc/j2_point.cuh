@@ -9,9 +9,10 @@
 // sum_g w detJ B^T (d sigma/d eps) B with d sigma/d eps the forward-mode derivative of the algorithm.
 // Here the iteration (x0 = 0, stop on ||r|| <= 1e-6 or 50 steps tested on primal values, 1e-12 regulariser in
 // n = s/(sigma_eq + 1e-12)) is replayed with its derivative: the iterate x is a dual number (value + V strain
-// tangents); each step factorises the analytic 7x7 Newton Jacobian ONCE in real arithmetic and reuses the
-// factors for the tangent of the step, J dx' = -(r' + J' dx) -- algebraically what dual-number elimination does,
-// at a third of the arithmetic and without a 7x8 matrix of dual numbers in local memory.
+// tangents); each step sets up the solve with the analytic 7x7 Newton Jacobian ONCE in real arithmetic (closed form:
+// a structured block, a rank-one update and a scalar Schur complement) and reuses it for the tangent of the step,
+// J dx' = -(r' + J' dx) -- algebraically what dual-number elimination does, at a fraction of the arithmetic and
+// without a 7x8 matrix of dual numbers in local memory.
 #pragma once
 #include <math.h>
 
@@ -196,91 +197,62 @@ __device__ void j2_point(const T* eps, const T* state, T E, T nu, T y0, T h1, T 
       nrm += r[6].v * r[6].v;
       if (!((T)sqrt((double)nrm) > tol && it < max_iter)) break;   // utils.py:222-226
 
-      // primal Jacobian d r / d x (columns k < 6: d/d(d eps_p)_k, column 6: d/d(d lambda))
-      T Jm[7][7];
-      const T iq = iqe.v;
+      // Newton matrix J = d r / d x in closed form.  With alpha = 2G dl / (q + 1e-12), Pd = the deviatoric projector
+      // on the normal components (identity on the shears) and dq_k = d q / d x_k:
+      //   J = [ I + alpha Pd + dl s (dq iq^2)^T   | -s iq     ]      M = I + alpha Pd inverts in closed form
+      //       [ dq^T                               | -h1 h2 hx ]      (normal block (I + alpha/3 11^T)/(1+alpha)),
+      // the rest is a rank-one update (Sherman-Morrison) and a scalar Schur complement: ~60 flops per right-hand
+      // side, no 7x7 factorisation and no matrix held in registers (same solution as the LU to ~1e-14).
+      const T iq = iqe.v, dl = x[6].v;
+      const T alpha = (T)2 * G * dl * iq, ia = (T)1 / ((T)1 + alpha), a3 = ia * alpha * ((T)1 / (T)3);
+      T sv[6], dq[6], vv[6], Mu[6], Ac[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        // d s / d x_k = -2G dev(T_k), T_k the unit array-tensor (off-diagonals symmetric)
-        T ds[6];
+      for (int m = 0; m < 6; ++m) sv[m] = s2.c[m].v;
+      const T trs3 = (sv[0] + sv[1] + sv[2]) * ((T)1 / (T)3), rq = (T)1 / q2.v;
 #pragma unroll
-        for (int m = 0; m < 6; ++m) ds[m] = (T)0;
-        if (k < 3) {
-#pragma unroll
-          for (int m = 0; m < 3; ++m) ds[m] = (T)(-2) * G * ((m == k ? (T)1 : (T)0) - (T)1 / (T)3);
-        } else {
-          ds[k] = (T)(-2) * G;
-        }
-        T sds = (T)0;   // s : ds  (off-diagonal entries count twice in the Frobenius product)
-#pragma unroll
-        for (int m = 0; m < 6; ++m)
-          if (ds[m] != (T)0) sds += ((m < 3 ? (T)1 : (T)2) * ds[m]) * s2.c[m].v;
-        const T dq = ((T)1.5 * sds) / q2.v;
-        const T dqq = dq * iq * iq;
-#pragma unroll
-        for (int m = 0; m < 6; ++m) Jm[m][k] = (m == k ? (T)1 : (T)0) - x[6].v * (ds[m] * iq - s2.c[m].v * dqq);
-        Jm[6][k] = dq;
+      for (int m = 0; m < 6; ++m) {
+        dq[m] = (m < 3) ? (T)(-3) * G * (sv[m] - trs3) * rq : (T)(-6) * G * sv[m] * rq;
+        vv[m] = dq[m] * iq * iq;
+        Mu[m] = dl * sv[m];
       }
+      auto minv = [&](T (&b)[6]) {
+        const T add = a3 * (b[0] + b[1] + b[2]);
 #pragma unroll
-      for (int m = 0; m < 6; ++m) Jm[m][6] = -(s2.c[m].v * iq);
-      Jm[6][6] = (-(h1 * h2)) * hx.v;
-
-      // LU with partial pivoting, fully unrolled (row swaps by predicated exchange: no dynamic indexing)
-      int piv[7];
-      T idiag[7];
+        for (int m = 0; m < 6; ++m) b[m] = b[m] * ia + (m < 3 ? add : (T)0);
+      };
+      minv(Mu);
+      T den = (T)1;
 #pragma unroll
-      for (int c = 0; c < 7; ++c) {
-        int p = c;
-        T best = fabs((double)Jm[c][c]);
+      for (int m = 0; m < 6; ++m) den += vv[m] * Mu[m];
+      const T iden = (T)1 / den;
+      auto ainv = [&](T (&b)[6]) {
+        minv(b);
+        T f = (T)0;
 #pragma unroll
-        for (int rr = c + 1; rr < 7; ++rr) {
-          const T a = fabs((double)Jm[rr][c]);
-          if (a > best) { best = a; p = rr; }
-        }
-        piv[c] = p;
+        for (int m = 0; m < 6; ++m) f += vv[m] * b[m];
+        f *= iden;
 #pragma unroll
-        for (int rr = c + 1; rr < 7; ++rr) {
-          const bool sw = (rr == p);
+        for (int m = 0; m < 6; ++m) b[m] -= Mu[m] * f;
+      };
 #pragma unroll
-          for (int k = 0; k < 7; ++k) {
-            const T u0 = Jm[c][k], u1 = Jm[rr][k];
-            Jm[c][k] = sw ? u1 : u0;
-            Jm[rr][k] = sw ? u0 : u1;
-          }
-        }
-        idiag[c] = (T)1 / Jm[c][c];
+      for (int m = 0; m < 6; ++m) Ac[m] = -(sv[m] * iq);
+      ainv(Ac);
+      T schur = (-(h1 * h2)) * hx.v;
 #pragma unroll
-        for (int rr = c + 1; rr < 7; ++rr) {
-          const T f = Jm[rr][c] * idiag[c];
-          Jm[rr][c] = f;
-#pragma unroll
-          for (int k = c + 1; k < 7; ++k) Jm[rr][k] -= f * Jm[c][k];
-        }
-      }
-      // (whole rows were exchanged, multipliers included, so all exchanges apply to b before the forward sweep)
+      for (int m = 0; m < 6; ++m) schur -= dq[m] * Ac[m];
+      const T ischur = (T)1 / schur;
       auto lu_solve = [&](T (&b)[7]) {
+        T y[6];
 #pragma unroll
-        for (int c = 0; c < 7; ++c) {
+        for (int m = 0; m < 6; ++m) y[m] = b[m];
+        ainv(y);
+        T z = b[6];
 #pragma unroll
-          for (int rr = c + 1; rr < 7; ++rr) {
-            const bool sw = (rr == piv[c]);
-            const T u0 = b[c], u1 = b[rr];
-            b[c] = sw ? u1 : u0;
-            b[rr] = sw ? u0 : u1;
-          }
-        }
+        for (int m = 0; m < 6; ++m) z -= dq[m] * y[m];
+        z *= ischur;
 #pragma unroll
-        for (int c = 0; c < 7; ++c) {
-#pragma unroll
-          for (int rr = c + 1; rr < 7; ++rr) b[rr] -= Jm[rr][c] * b[c];
-        }
-#pragma unroll
-        for (int i = 6; i >= 0; --i) {
-          T acc = b[i];
-#pragma unroll
-          for (int k = i + 1; k < 7; ++k) acc -= Jm[i][k] * b[k];
-          b[i] = acc * idiag[i];
-        }
+        for (int m = 0; m < 6; ++m) b[m] = y[m] - Ac[m] * z;
+        b[6] = z;
       };
       T w[7];
 #pragma unroll
