@@ -176,26 +176,34 @@ __device__ void j2_point(const T* eps, const T* state, T E, T nu, T y0, T h1, T 
     Du x[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) x[k] = dconst<T, V>((T)0);
+    // The tangents are carried one strain direction at a time with SCALAR dual numbers (D1): the primal quantities
+    // of the step are evaluated once, then each direction re-evaluates the (cheap) residual and J w with its own
+    // seed.  Same numbers as V-wide duals, a fraction of the live registers.
+    using D1 = Dual<T, 1>;
+    constexpr int comp3[6] = {0, 1, 2, 3, 4, 5}, comp2[3] = {0, 1, 3};   // tensor component seeded by direction t
     for (int it = 0;; ++it) {
-      // residual at x
-      Sym3<Du> e2, sg2, s2;
-      Du q2;
+      // residual at x (primal)
+      T rv[7], sv[6], q2v, iq, hxv;
+      {
+        Sym3<D1> e2, sg2, s2;
+        D1 q2;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) e2.c[k] = et.c[k] - ep.c[k] - x[k];
-      stress_dev_eq<T, V>(e2, lam, G, sg2, s2, q2);
-      const Du qe = q2 + dconst<T, V>((T)1e-12);
-      const Du iqe = dconst<T, V>((T)1) / qe;
-      Du r[7];
-      T nrm = (T)0;
+        for (int k = 0; k < 6; ++k) e2.c[k] = dconst<T, 1>(et.c[k].v - ep.c[k].v - x[k].v);
+        stress_dev_eq<T, 1>(e2, lam, G, sg2, s2, q2);
+        q2v = q2.v;
+        iq = (T)1 / (q2v + (T)1e-12);
+        hxv = (T)exp((double)(-h2 * (xi + x[6].v)));
+        T nrm = (T)0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        r[k] = x[k] - x[6] * (s2.c[k] * iqe);
-        nrm += r[k].v * r[k].v;
+        for (int k = 0; k < 6; ++k) {
+          sv[k] = s2.c[k].v;
+          rv[k] = x[k].v - x[6].v * (sv[k] * iq);
+          nrm += rv[k] * rv[k];
+        }
+        rv[6] = q2v - ((y0 + h1) - h1 * hxv);
+        nrm += rv[6] * rv[6];
+        if (!((T)sqrt((double)nrm) > tol && it < max_iter)) break;   // utils.py:222-226
       }
-      const Du hx = dexp((-h2) * (dconst<T, V>(xi) + x[6]));
-      r[6] = q2 - (dconst<T, V>(y0 + h1) - h1 * hx);
-      nrm += r[6].v * r[6].v;
-      if (!((T)sqrt((double)nrm) > tol && it < max_iter)) break;   // utils.py:222-226
 
       // Newton matrix J = d r / d x in closed form.  With alpha = 2G dl / (q + 1e-12), Pd = the deviatoric projector
       // on the normal components (identity on the shears) and dq_k = d q / d x_k:
@@ -203,12 +211,10 @@ __device__ void j2_point(const T* eps, const T* state, T E, T nu, T y0, T h1, T 
       //       [ dq^T                               | -h1 h2 hx ]      (normal block (I + alpha/3 11^T)/(1+alpha)),
       // the rest is a rank-one update (Sherman-Morrison) and a scalar Schur complement: ~60 flops per right-hand
       // side, no 7x7 factorisation and no matrix held in registers (same solution as the LU to ~1e-14).
-      const T iq = iqe.v, dl = x[6].v;
+      const T dl = x[6].v;
       const T alpha = (T)2 * G * dl * iq, ia = (T)1 / ((T)1 + alpha), a3 = ia * alpha * ((T)1 / (T)3);
-      T sv[6], dq[6], vv[6], Mu[6], Ac[6];
-#pragma unroll
-      for (int m = 0; m < 6; ++m) sv[m] = s2.c[m].v;
-      const T trs3 = (sv[0] + sv[1] + sv[2]) * ((T)1 / (T)3), rq = (T)1 / q2.v;
+      T dq[6], vv[6], Mu[6], Ac[6];
+      const T trs3 = (sv[0] + sv[1] + sv[2]) * ((T)1 / (T)3), rq = (T)1 / q2v;
 #pragma unroll
       for (int m = 0; m < 6; ++m) {
         dq[m] = (m < 3) ? (T)(-3) * G * (sv[m] - trs3) * rq : (T)(-6) * G * sv[m] * rq;
@@ -237,11 +243,11 @@ __device__ void j2_point(const T* eps, const T* state, T E, T nu, T y0, T h1, T 
 #pragma unroll
       for (int m = 0; m < 6; ++m) Ac[m] = -(sv[m] * iq);
       ainv(Ac);
-      T schur = (-(h1 * h2)) * hx.v;
+      T schur = (-(h1 * h2)) * hxv;
 #pragma unroll
       for (int m = 0; m < 6; ++m) schur -= dq[m] * Ac[m];
       const T ischur = (T)1 / schur;
-      auto lu_solve = [&](T (&b)[7]) {
+      auto solve7 = [&](T (&b)[7]) {
         T y[6];
 #pragma unroll
         for (int m = 0; m < 6; ++m) y[m] = b[m];
@@ -256,38 +262,57 @@ __device__ void j2_point(const T* eps, const T* state, T E, T nu, T y0, T h1, T 
       };
       T w[7];
 #pragma unroll
-      for (int m = 0; m < 7; ++m) w[m] = -r[m].v;
-      lu_solve(w);
+      for (int m = 0; m < 7; ++m) w[m] = -rv[m];
+      solve7(w);
+      const T wm = (w[0] + w[1] + w[2]) * ((T)1 / (T)3);
+      T W[6];   // -2G dev(w): d s / d x applied to the step
+#pragma unroll
+      for (int m = 0; m < 6; ++m) W[m] = (T)(-2) * G * (m < 3 ? (w[m] - wm) : w[m]);
 
-      // g = J(x, eps) w in dual arithmetic, w fixed: its dual part is J' w
-      Du g[7];
-      {
-        const T wm = (w[0] + w[1] + w[2]) * ((T)1 / (T)3);
-        T W[6];
-#pragma unroll
-        for (int m = 0; m < 6; ++m) W[m] = (T)(-2) * G * (m < 3 ? (w[m] - wm) : w[m]);
-        Du sW = dconst<T, V>((T)0);
-#pragma unroll
-        for (int m = 0; m < 6; ++m) sW = sW + ((m < 3 ? (T)1 : (T)2) * W[m]) * s2.c[m];
-        const Du dqW = ((T)1.5 * sW) / q2;
-        const Du dqqW = dqW * iqe * iqe;
-#pragma unroll
-        for (int m = 0; m < 6; ++m)
-          g[m] = dconst<T, V>(w[m]) - x[6] * (W[m] * iqe - s2.c[m] * dqqW) - w[6] * (s2.c[m] * iqe);
-        g[6] = dqW + ((-(h1 * h2)) * w[6]) * hx;
-      }
-      // tangent right-hand sides with the same factors
-#pragma unroll
-      for (int m = 0; m < 7; ++m) x[m].v += w[m];
+      // tangent of the step, direction by direction: J dx' = -(r' + J' dx)
 #pragma unroll
       for (int t = 0; t < V; ++t) {
+        const int ct = (D == 3) ? comp3[t] : comp2[t];
+        Sym3<D1> e2, sg2, s2;
+        D1 q2, xt[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          xt[k].v = x[k].v;
+          xt[k].d[0] = x[k].d[t];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          e2.c[k].v = et.c[k].v - ep.c[k].v - x[k].v;
+          e2.c[k].d[0] = (k == ct ? (T)1 : (T)0) - x[k].d[t];
+        }
+        stress_dev_eq<T, 1>(e2, lam, G, sg2, s2, q2);
+        const D1 iqe = dconst<T, 1>((T)1) / (q2 + dconst<T, 1>((T)1e-12));
+        const D1 hx = dexp((-h2) * (dconst<T, 1>(xi) + xt[6]));
+        // r' : dual part of the residual;  (J w)' : dual part of J(x, eps) w with w fixed
+        D1 sW = dconst<T, 1>((T)0);
+#pragma unroll
+        for (int m = 0; m < 6; ++m) sW = sW + ((m < 3 ? (T)1 : (T)2) * W[m]) * s2.c[m];
+        const D1 dqW = ((T)1.5 * sW) / q2;
+        const D1 dqqW = dqW * iqe * iqe;
         T b[7];
 #pragma unroll
-        for (int m = 0; m < 7; ++m) b[m] = -(r[m].d[t] + g[m].d[t]);
-        lu_solve(b);
+        for (int m = 0; m < 6; ++m) {
+          const D1 n = s2.c[m] * iqe;
+          const D1 r = xt[m] - xt[6] * n;
+          const D1 g = dconst<T, 1>(w[m]) - xt[6] * (W[m] * iqe - s2.c[m] * dqqW) - w[6] * n;
+          b[m] = -(r.d[0] + g.d[0]);
+        }
+        {
+          const D1 r6 = q2 - (dconst<T, 1>(y0 + h1) - h1 * hx);
+          const D1 g6 = dqW + ((-(h1 * h2)) * w[6]) * hx;
+          b[6] = -(r6.d[0] + g6.d[0]);
+        }
+        solve7(b);
 #pragma unroll
         for (int m = 0; m < 7; ++m) x[m].d[t] += b[m];
       }
+#pragma unroll
+      for (int m = 0; m < 7; ++m) x[m].v += w[m];
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) ep_new.c[k] = ep.c[k] + x[k];
