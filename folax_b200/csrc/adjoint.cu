@@ -1,0 +1,201 @@
+// Kernels + C ABI of the adjoint-sensitivity element routines (adjoint.cuh): one element per thread.
+// The per-thread bodies are __host__ __device__ functions (adjoint_threads.cuh) so that tests/host_shim runs
+// exactly the code of a kernel thread -- indexing included -- on the CPU.
+#include "adjoint_threads.cuh"
+
+namespace fol {
+
+template <class T, int ELEM, int ORDER>
+__global__ void __launch_bounds__(128) gauss_interpolate_kernel(const InterpArgs<T> a) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < a.ne) gauss_interpolate_thread<T, ELEM, ORDER>(e, a);
+}
+
+template <class T, int ELEM, int ORDER>
+__global__ void __launch_bounds__(128) response_kernel(const ResponseArgs<T> a) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < a.ne) response_thread<T, ELEM, ORDER>(e, a);
+}
+
+template <class T, int ELEM, int ORDER, int PHYS>
+__global__ void __launch_bounds__(128) residual_adjoint_kernel(const AdjointArgs<T> a) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < a.ne) residual_adjoint_thread<T, ELEM, ORDER, PHYS>(e, a);
+}
+
+// out[0] = sum x[0..n): one block, fixed order (thread-strided partial sums, then a shared-memory tree)
+template <class T>
+__global__ void __launch_bounds__(1024) sum_kernel(const T* __restrict__ x, long long n, T* __restrict__ out) {
+  __shared__ T part[1024];
+  T acc = (T)0;
+  for (long long i = threadIdx.x; i < n; i += 1024) acc += x[i];
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = part[0];
+}
+
+#define FOL_ELEM_ORDER_CASES(X)                                                                    \
+  X(HEX, 1) X(HEX, 2) X(HEX, 3) X(QUAD, 1) X(QUAD, 2) X(QUAD, 3) X(TET, 1) X(TET, 2) X(TET, 3)     \
+  X(TRI, 1) X(TRI, 2) X(TRI, 3)
+
+template <class T>
+static int launch_interp(cudaStream_t s, int element, int num_gp, const InterpArgs<T>& a) {
+  if (a.ne == 0) return FOL_OK;
+  const unsigned grid = (unsigned)cdiv(a.ne, 128);
+#define X(E, O)                                                       \
+  if (element == E && num_gp == O) {                                  \
+    gauss_interpolate_kernel<T, E, O><<<grid, 128, 0, s>>>(a);        \
+    return check_launch("gauss_interpolate_kernel");                  \
+  }
+  FOL_ELEM_ORDER_CASES(X)
+#undef X
+  return fail(FOL_ERR_UNSUPPORTED, "fol_gauss_interpolate: unsupported element / num_gp");
+}
+
+template <class T>
+static int launch_response(cudaStream_t s, int element, int num_gp, const ResponseArgs<T>& a) {
+  if (a.ne == 0) return FOL_OK;
+  const unsigned grid = (unsigned)cdiv(a.ne, 128);
+#define X(E, O)                                              \
+  if (element == E && num_gp == O) {                         \
+    response_kernel<T, E, O><<<grid, 128, 0, s>>>(a);        \
+    return check_launch("response_kernel");                  \
+  }
+  FOL_ELEM_ORDER_CASES(X)
+#undef X
+  return fail(FOL_ERR_UNSUPPORTED, "fol_response_elements: unsupported element / num_gp");
+}
+
+template <class T, int PHYS>
+static int launch_adjoint(cudaStream_t s, int element, int num_gp, const AdjointArgs<T>& a) {
+  if (a.ne == 0) return FOL_OK;
+  const unsigned grid = (unsigned)cdiv(a.ne, 128);
+#define X(E, O)                                                            \
+  if (element == E && num_gp == O) {                                       \
+    residual_adjoint_kernel<T, E, O, PHYS><<<grid, 128, 0, s>>>(a);        \
+    return check_launch("residual_adjoint_kernel");                        \
+  }
+  FOL_ELEM_ORDER_CASES(X)
+#undef X
+  return fail(FOL_ERR_UNSUPPORTED, "fol_residual_adjoint_elements: unsupported element / num_gp");
+}
+
+template <class T>
+static int interp_typed(cudaStream_t s, int element, int num_gp, int dpn, long long ne, const int32_t* conn,
+                        const void* ctrl, const void* u, void* kg, void* ug) {
+  InterpArgs<T> a;
+  a.conn = conn;
+  a.ctrl = (const T*)ctrl;
+  a.u = (const T*)u;
+  a.kg = (T*)kg;
+  a.ug = (T*)ug;
+  a.ne = ne;
+  a.dpn = dpn;
+  return launch_interp<T>(s, element, num_gp, a);
+}
+
+template <class T>
+static int response_typed(cudaStream_t s, int element, int num_gp, int dpn, long long ne, const void* xyz,
+                          const int32_t* conn, const void* f, const void* fk, const void* fu, void* val, void* du,
+                          void* dk, void* dx) {
+  ResponseArgs<T> a;
+  a.xyz = (const T*)xyz;
+  a.conn = conn;
+  a.f = (const T*)f;
+  a.fk = (const T*)fk;
+  a.fu = (const T*)fu;
+  a.val = (T*)val;
+  a.du = (T*)du;
+  a.dk = (T*)dk;
+  a.dx = (T*)dx;
+  a.ne = ne;
+  a.dpn = dpn;
+  return launch_response<T>(s, element, num_gp, a);
+}
+
+template <class T>
+static int adjoint_typed(cudaStream_t s, int physics, int element, int num_gp, int accumulate, long long ne,
+                         const void* xyz, const int32_t* conn, const void* ctrl, const void* u, const void* lam,
+                         const double* params, void* dk, void* dx) {
+  AdjointArgs<T> a;
+  a.xyz = (const T*)xyz;
+  a.conn = conn;
+  a.ctrl = (const T*)ctrl;
+  a.u = (const T*)u;
+  a.lam = (const T*)lam;
+  a.dk = (T*)dk;
+  a.dx = (T*)dx;
+  a.ne = ne;
+  a.accumulate = accumulate;
+  a.p = make_params<T>(params);
+  if (physics == FOL_MECHANICAL) return launch_adjoint<T, ADJ_MECH>(s, element, num_gp, a);
+  if (physics == FOL_THERMAL) return launch_adjoint<T, ADJ_THERMAL>(s, element, num_gp, a);
+  return fail(FOL_ERR_UNSUPPORTED,
+              "fol_residual_adjoint_elements: closed-form residual sensitivities exist for the mechanical and "
+              "thermal losses only");
+}
+
+}  // namespace fol
+
+using namespace fol;
+
+extern "C" {
+
+int fol_gauss_interpolate(fol_stream_t s, int dtype, int element, int num_gp, int dofs_per_node, int64_t ne,
+                          const int32_t* conn, const void* ctrl, const void* u, void* k_gp, void* u_gp) {
+  FOL_REQUIRE(element >= 0 && element <= 3 && num_gp >= 1 && num_gp <= 3, "fol_gauss_interpolate: bad element / num_gp");
+  FOL_REQUIRE(dofs_per_node >= 1 && dofs_per_node <= 3, "fol_gauss_interpolate: dofs_per_node must be 1..3");
+  FOL_REQUIRE(ne >= 0 && conn && ctrl && u && k_gp && u_gp, "fol_gauss_interpolate: null pointer / negative size");
+  if (dtype == FOL_F64)
+    return interp_typed<double>((cudaStream_t)s, element, num_gp, dofs_per_node, ne, conn, ctrl, u, k_gp, u_gp);
+  if (dtype == FOL_F32)
+    return interp_typed<float>((cudaStream_t)s, element, num_gp, dofs_per_node, ne, conn, ctrl, u, k_gp, u_gp);
+  return fail(FOL_ERR_INVALID, "fol_gauss_interpolate: unknown dtype");
+}
+
+int fol_response_elements(fol_stream_t s, int dtype, int element, int num_gp, int dofs_per_node, int64_t ne,
+                          const void* xyz, const int32_t* conn, const void* f_gp, const void* fk_gp,
+                          const void* fu_gp, void* value_elem, void* du_elem, void* dk_elem, void* dx_elem) {
+  FOL_REQUIRE(element >= 0 && element <= 3 && num_gp >= 1 && num_gp <= 3, "fol_response_elements: bad element / num_gp");
+  FOL_REQUIRE(dofs_per_node >= 1 && dofs_per_node <= 3, "fol_response_elements: dofs_per_node must be 1..3");
+  FOL_REQUIRE(ne >= 0 && xyz && conn && f_gp, "fol_response_elements: null pointer / negative size");
+  FOL_REQUIRE(!du_elem || fu_gp, "fol_response_elements: du_elem needs fu_gp");
+  FOL_REQUIRE(!dk_elem || fk_gp, "fol_response_elements: dk_elem needs fk_gp");
+  if (dtype == FOL_F64)
+    return response_typed<double>((cudaStream_t)s, element, num_gp, dofs_per_node, ne, xyz, conn, f_gp, fk_gp, fu_gp,
+                                  value_elem, du_elem, dk_elem, dx_elem);
+  if (dtype == FOL_F32)
+    return response_typed<float>((cudaStream_t)s, element, num_gp, dofs_per_node, ne, xyz, conn, f_gp, fk_gp, fu_gp,
+                                 value_elem, du_elem, dk_elem, dx_elem);
+  return fail(FOL_ERR_INVALID, "fol_response_elements: unknown dtype");
+}
+
+int fol_residual_adjoint_elements(fol_stream_t s, int dtype, int physics, int element, int num_gp, int accumulate,
+                                  int64_t ne, const void* xyz, const int32_t* conn, const void* ctrl, const void* u,
+                                  const void* adj, const double* params_host, void* dk_elem, void* dx_elem) {
+  FOL_REQUIRE(element >= 0 && element <= 3 && num_gp >= 1 && num_gp <= 3,
+              "fol_residual_adjoint_elements: bad element / num_gp");
+  FOL_REQUIRE(ne >= 0 && xyz && conn && ctrl && u && adj && params_host && (dk_elem || dx_elem),
+              "fol_residual_adjoint_elements: null pointer / negative size");
+  if (dtype == FOL_F64)
+    return adjoint_typed<double>((cudaStream_t)s, physics, element, num_gp, accumulate, ne, xyz, conn, ctrl, u, adj,
+                                 params_host, dk_elem, dx_elem);
+  if (dtype == FOL_F32)
+    return adjoint_typed<float>((cudaStream_t)s, physics, element, num_gp, accumulate, ne, xyz, conn, ctrl, u, adj,
+                                params_host, dk_elem, dx_elem);
+  return fail(FOL_ERR_INVALID, "fol_residual_adjoint_elements: unknown dtype");
+}
+
+int fol_sum(fol_stream_t s, int dtype, int64_t n, const void* x, void* out) {
+  FOL_REQUIRE(n >= 0 && out && (x || n == 0), "fol_sum: null pointer / negative size");
+  if (dtype == FOL_F64) sum_kernel<double><<<1, 1024, 0, (cudaStream_t)s>>>((const double*)x, n, (double*)out);
+  else if (dtype == FOL_F32) sum_kernel<float><<<1, 1024, 0, (cudaStream_t)s>>>((const float*)x, n, (float*)out);
+  else return fail(FOL_ERR_INVALID, "fol_sum: unknown dtype");
+  return check_launch("sum_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+// Adjoint sensitivities of a finite-element response: the element routines behind
+// folax_b200/responses/fe_response.py, i.e. the arithmetic of fol/responses/fe_response.py
+//   :91-124   ComputeResponseElementValue        sum_g w detJ f(N.de, N_mat u_e)
+//   :126-168  its gradients w.r.t. u_e, de, x_e  (JAX AD in the reference)
+//   :312-331  ComputeLossElementShapeGrad         lam_e^T d re/d x_e   (jacrev of ComputeElement(...)[1])
+//   :424-442  ComputeLossElementControlGrad       lam_e^T d re/d de
+// The reference differentiates with JAX AD; here the derivatives are closed forms.  With W = grad(dx)
+// (W_kj = sum_b dx_bk dN_b/dx_j) a node perturbation changes the geometry by
+//   d(detJ) = detJ tr(W),      d(grad v) = -(grad v) W     (v any nodal field; N itself does not change)
+// so for  phi = lam_e^T re  of
+//   mechanical.py:98-117   phi = sum_g w detJ [(N.de) sigma(u):grad(lam) - b.(N lam)]
+//       d phi/d de_a  = sum_g w detJ N_a q,                       q = sigma(u):grad(lam)
+//       d phi/d x_bk  = sum_g w detJ [(N.de)(q dN_b/dx_k - (M grad N_b)_k) - b.(N lam) dN_b/dx_k],
+//                       M = grad(lam)^T sigma(u) + grad(u)^T sigma(lam)
+//   thermal.py:28-49       phi = sum_g w detJ kappa_g grad(lam).grad(T),  kappa_g = (N.de)(1 + beta (N.T)^c)
+//       d phi/d de_a  = sum_g w detJ N_a (1 + beta T_g^c) grad(lam).grad(T)
+//       d phi/d x_bk  = sum_g w detJ kappa_g [gl.gt dN_b/dx_k - gl_k (gt.grad N_b) - gt_k (gl.grad N_b)]
+// Every routine is a sequential per-element function, __host__ __device__: the kernels of adjoint.cu run one
+// element per thread, and tests/host_shim compiles the same functions for the CPU to check them against the
+// complex-step oracle where no GPU is available.  Not a hot path (one call per design iteration, next to a
+// linear solve); written for clarity.
+#pragma once
+#include <math.h>
+
+#include "common.cuh"
+#include "elements.cuh"
+
+namespace fol {
+
+// enum values of assemble.cuh, repeated to keep this header free of the assembly kernels
+enum : int { ADJ_MECH = 0, ADJ_THERMAL = 1 };
+
+template <int ELEM, int ORDER, class T>
+struct ElemPoint {
+  static constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM);
+  T N[A];
+  T gN[A][D];
+  T wd;   // w * detJ
+};
+
+template <int ELEM, int ORDER, class T>
+__host__ __device__ inline void eval_point(const T* X, int g, ElemPoint<ELEM, ORDER, T>& p) {
+  constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM);
+  double xi[3], w;
+  gauss_point<ELEM, ORDER>(g, xi, w);
+  T dN[A][D];
+  shape_functions<ELEM, T>(xi, p.N, dN);
+  const T det = global_gradients<ELEM, T, false>(X, dN, p.gN);
+  p.wd = (T)w * det;
+}
+
+// Kg[g] = N_g . de ;  Ug[k * ustride + g] = sum_a N_g[a] ue[a*DPN + k]      (fe_response.py:112-115)
+template <class T, int ELEM, int ORDER>
+__host__ __device__ inline void gauss_interpolate_element(int dpn, const T* de, const T* ue, T* Kg, T* Ug,
+                                                          long long ustride) {
+  constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM), NGP = elem_ngauss(ELEM, ORDER);
+  for (int g = 0; g < NGP; ++g) {
+    double xi[3], w;
+    gauss_point<ELEM, ORDER>(g, xi, w);
+    T N[A], dN[A][D];
+    shape_functions<ELEM, T>(xi, N, dN);
+    T kg = (T)0;
+    for (int a = 0; a < A; ++a) kg += N[a] * de[a];
+    Kg[g] = kg;
+    for (int k = 0; k < dpn; ++k) {
+      T acc = (T)0;
+      for (int a = 0; a < A; ++a) acc += N[a] * ue[a * dpn + k];
+      Ug[k * ustride + g] = acc;
+    }
+  }
+}
+
+// value_e and its gradients from the formula values f[g] and partials fK[g], fU[k*ustride + g] at the Gauss
+// points.  Outputs may be null.  With accumulate the results are added to what the arrays hold.
+template <class T, int ELEM, int ORDER>
+__host__ __device__ inline void response_element(int dpn, const T* X, const T* f, const T* fK, const T* fU,
+                                                 long long ustride, T* val, T* dU, T* dK, T* dX) {
+  constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM), NGP = elem_ngauss(ELEM, ORDER);
+  T v = (T)0;
+  if (dU) for (int i = 0; i < A * dpn; ++i) dU[i] = (T)0;
+  if (dK) for (int a = 0; a < A; ++a) dK[a] = (T)0;
+  if (dX) for (int i = 0; i < A * 3; ++i) dX[i] = (T)0;
+  for (int g = 0; g < NGP; ++g) {
+    ElemPoint<ELEM, ORDER, T> p;
+    eval_point<ELEM, ORDER, T>(X, g, p);
+    v += p.wd * f[g];
+    for (int a = 0; a < A; ++a) {
+      if (dK && fK) dK[a] += p.wd * p.N[a] * fK[g];
+      if (dU && fU)
+        for (int k = 0; k < dpn; ++k) dU[a * dpn + k] += p.wd * p.N[a] * fU[k * ustride + g];
+      if (dX)
+        for (int k = 0; k < D; ++k) dX[a * 3 + k] += p.wd * f[g] * p.gN[a][k];   // d(detJ)/dx = detJ grad N
+    }
+  }
+  if (val) *val = v;
+}
+
+// lam_e^T d re / d de  (A)  and  lam_e^T d re / d x_e  (A x 3, unused coordinates zero); see the header comment.
+template <class T, int ELEM, int ORDER, int PHYS>
+__host__ __device__ inline void residual_adjoint_element(const T* X, const T* de, const T* ue, const T* le,
+                                                         const Params<T>& P, T* dK, T* dX) {
+  constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM), NGP = elem_ngauss(ELEM, ORDER);
+  for (int a = 0; a < A; ++a) dK[a] = (T)0;
+  for (int i = 0; i < A * 3; ++i) dX[i] = (T)0;
+  for (int g = 0; g < NGP; ++g) {
+    ElemPoint<ELEM, ORDER, T> p;
+    eval_point<ELEM, ORDER, T>(X, g, p);
+    T kg = (T)0;
+    for (int a = 0; a < A; ++a) kg += p.N[a] * de[a];
+    if constexpr (PHYS == ADJ_MECH) {
+      // isotropic D of mechanical.py:60-82 as (lam, mu): 3-D c3, c4; 2-D plane stress
+      const T E = P.v[0], nu = P.v[1];
+      T lam, mu;
+      if constexpr (D == 3) {
+        const T c1 = E / (((T)1 + nu) * ((T)1 - (T)2 * nu));
+        lam = c1 * nu;
+        mu = c1 * (T)0.5 * ((T)1 - (T)2 * nu);
+      } else {
+        const T fpl = E / ((T)1 - nu * nu);
+        lam = fpl * nu;
+        mu = fpl * ((T)1 - nu) * (T)0.5;
+      }
+      T Gu[D][D], Gl[D][D], lg[D];
+      for (int i = 0; i < D; ++i) {
+        lg[i] = (T)0;
+        for (int a = 0; a < A; ++a) lg[i] += p.N[a] * le[a * D + i];
+        for (int j = 0; j < D; ++j) {
+          T su = (T)0, sl = (T)0;
+          for (int a = 0; a < A; ++a) {
+            su += ue[a * D + i] * p.gN[a][j];
+            sl += le[a * D + i] * p.gN[a][j];
+          }
+          Gu[i][j] = su;
+          Gl[i][j] = sl;
+        }
+      }
+      T tru = (T)0, trl = (T)0;
+      for (int i = 0; i < D; ++i) {
+        tru += Gu[i][i];
+        trl += Gl[i][i];
+      }
+      T Su[D][D], Sl[D][D];
+      for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) {
+          Su[i][j] = mu * (Gu[i][j] + Gu[j][i]) + (i == j ? lam * tru : (T)0);
+          Sl[i][j] = mu * (Gl[i][j] + Gl[j][i]) + (i == j ? lam * trl : (T)0);
+        }
+      T q = (T)0;
+      for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) q += Su[i][j] * Gl[i][j];
+      T M[D][D];
+      for (int k = 0; k < D; ++k)
+        for (int j = 0; j < D; ++j) {
+          T acc = (T)0;
+          for (int i = 0; i < D; ++i) acc += Gl[i][k] * Su[i][j] + Gu[i][k] * Sl[i][j];
+          M[k][j] = acc;
+        }
+      T bl = (T)0;   // body force . (N lam)
+      for (int i = 0; i < D; ++i) bl += P.v[2 + i] * lg[i];
+      for (int b = 0; b < A; ++b) {
+        dK[b] += p.wd * p.N[b] * q;
+        for (int k = 0; k < D; ++k) {
+          T mg = (T)0;
+          for (int j = 0; j < D; ++j) mg += M[k][j] * p.gN[b][j];
+          dX[b * 3 + k] += p.wd * (kg * (q * p.gN[b][k] - mg) - bl * p.gN[b][k]);
+        }
+      }
+    } else {   // ADJ_THERMAL
+      const T beta = P.v[5], cexp = P.v[6];
+      T tg = (T)0, gt[D], gl[D];
+      for (int a = 0; a < A; ++a) tg += p.N[a] * ue[a];
+      for (int k = 0; k < D; ++k) {
+        T st = (T)0, sl = (T)0;
+        for (int a = 0; a < A; ++a) {
+          st += ue[a] * p.gN[a][k];
+          sl += le[a] * p.gN[a][k];
+        }
+        gt[k] = st;
+        gl[k] = sl;
+      }
+      const T nl = (T)1 + ((beta != (T)0) ? beta * (T)pow((double)tg, (double)cexp) : (T)0);
+      T q = (T)0;
+      for (int k = 0; k < D; ++k) q += gl[k] * gt[k];
+      const T kappa = kg * nl;
+      for (int b = 0; b < A; ++b) {
+        dK[b] += p.wd * p.N[b] * nl * q;
+        T tb = (T)0, lb = (T)0;
+        for (int k = 0; k < D; ++k) {
+          tb += gt[k] * p.gN[b][k];
+          lb += gl[k] * p.gN[b][k];
+        }
+        for (int k = 0; k < D; ++k) dX[b * 3 + k] += p.wd * kappa * (q * p.gN[b][k] - gl[k] * tb - gt[k] * lb);
+      }
+    }
+  }
+}
+
+}  // namespace fol

@@ -1,5 +1,7 @@
 // Element library for the sm_100a kernels: Gauss rules, shape functions, local gradients.
 // Same tables as the reference element classes (cited per block); evaluated in registers.
+// (__host__ __device__ so that tests/host_shim can run the sequential per-element routines of adjoint.cuh on
+//  the CPU; the library itself never calls them on the host.)
 //   fol/geometries/hexahedra_3d_8.py:17-114, quadrilateral_2d_4.py:17-70,
 //   tetrahedra_3d_4.py:17-60, triangle_2d_3.py:17-58, geometry.py:88-97
 #pragma once
@@ -25,13 +27,13 @@ __host__ __device__ constexpr int elem_ngauss(int e, int order) {
 
 // sign patterns of the tensor-product elements (node order of hexahedra_3d_8.py:79-88 and
 // quadrilateral_2d_4.py:54-58)
-__device__ __forceinline__ double sgn_x(int a) { return ((a & 3) == 1 || (a & 3) == 2) ? 1.0 : -1.0; }
-__device__ __forceinline__ double sgn_y(int a) { return (a & 2) ? 1.0 : -1.0; }
-__device__ __forceinline__ double sgn_z(int a) { return (a & 4) ? 1.0 : -1.0; }
+__host__ __device__ __forceinline__ double sgn_x(int a) { return ((a & 3) == 1 || (a & 3) == 2) ? 1.0 : -1.0; }
+__host__ __device__ __forceinline__ double sgn_y(int a) { return (a & 2) ? 1.0 : -1.0; }
+__host__ __device__ __forceinline__ double sgn_z(int a) { return (a & 4) ? 1.0 : -1.0; }
 
 // Gauss point g of integration order ORDER: xi[3] and weight.
 template <int ELEM, int ORDER>
-__device__ __forceinline__ void gauss_point(int g, double xi[3], double& w) {
+__host__ __device__ __forceinline__ void gauss_point(int g, double xi[3], double& w) {
   if constexpr (ELEM == HEX) {
     if constexpr (ORDER == 1) { xi[0] = xi[1] = xi[2] = 0.0; w = 8.0; }
     else if constexpr (ORDER == 2) {  // ordered like the nodes, hexahedra_3d_8.py:23-33
@@ -79,7 +81,7 @@ __device__ __forceinline__ void gauss_point(int g, double xi[3], double& w) {
 
 // Shape-function values N[a] and local gradients dN[a][dim] at xi.
 template <int ELEM, class T>
-__device__ __forceinline__ void shape_functions(const double xi[3], T* N, T (*dN)[elem_dim(ELEM)]) {
+__host__ __device__ __forceinline__ void shape_functions(const double xi[3], T* N, T (*dN)[elem_dim(ELEM)]) {
   if constexpr (ELEM == HEX) {
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
@@ -116,7 +118,7 @@ __device__ __forceinline__ void shape_functions(const double xi[3], T* N, T (*dN
 // TRANSPOSED = true reproduces `B_mat = invJ @ dN^T` of transient_thermal.py:57-58 / phase_field.py:47-48,
 // where the inverse Jacobian enters un-transposed: gN[a][k] = sum_j dN[a][j] inv[k][j].
 template <int ELEM, class T, bool TRANSPOSED = false>
-__device__ __forceinline__ T global_gradients(const T* X /* [A][3] */, const T (*dN)[elem_dim(ELEM)],
+__host__ __device__ __forceinline__ T global_gradients(const T* X /* [A][3] */, const T (*dN)[elem_dim(ELEM)],
                                               T (*gN)[elem_dim(ELEM)]) {
   constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM);
   T J[D][D];

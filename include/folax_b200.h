@@ -194,6 +194,38 @@ int fol_apply_dirichlet(fol_stream_t s, int dtype, int64_t nb, int64_t ndof,
                         const int32_t* dirichlet_indices, int64_t n_dirichlet, const void* values,
                         int per_sample, double load_factor, void* u);
 
+/* ---- adjoint sensitivities of a response (fol/responses/fe_response.py) ------
+ * The response is value = sum_e sum_g w detJ f(K_g, U_g) with a user formula f of the control and the dofs
+ * at the Gauss point (fe_response.py:59-66, 91-124).  The formula itself is caller code: the host evaluates it
+ * (and its partials) pointwise over the Gauss-point arrays these kernels produce and consume.
+ * All element-major outputs are in the layout fol_residual_gather sums to the nodes (dofs_per_node = the
+ * per-node width of the array: dofs for du_elem, 1 for dk_elem, 3 for dx_elem). */
+
+/* k_gp[e*g + q] = N_q . ctrl[conn[e]],  u_gp[(k*ne + e)*g + q] = sum_a N_q[a] u[d*conn[e,a] + k]  (:112-115) */
+int fol_gauss_interpolate(fol_stream_t s, int dtype, int element, int num_gp, int dofs_per_node, int64_t ne,
+                          const int32_t* conn, const void* ctrl, const void* u, void* k_gp, void* u_gp);
+
+/* From f_gp (ne, g) and the partials fk_gp (ne, g) = df/dK, fu_gp (d, ne, g) = df/dU[k]:
+ *   value_elem[e] = sum_q w detJ f                                   (:116-124)
+ *   du_elem[e, a*d+k] = sum_q w detJ N_a df/dU[k]                    (:126-138, the adjoint right-hand side)
+ *   dk_elem[e, a]     = sum_q w detJ N_a df/dK                       (:140-152)
+ *   dx_elem[e, a*3+k] = sum_q w f d(detJ)/dx_ak                      (:154-168; unused coordinates 0)
+ * Any output (and the partial it needs) may be NULL. */
+int fol_response_elements(fol_stream_t s, int dtype, int element, int num_gp, int dofs_per_node, int64_t ne,
+                          const void* xyz, const int32_t* conn, const void* f_gp, const void* fk_gp,
+                          const void* fu_gp, void* value_elem, void* du_elem, void* dk_elem, void* dx_elem);
+
+/* dk_elem[e, a] (+)= adj_e^T d re/d ctrl_a,  dx_elem[e, a*3+k] (+)= adj_e^T d re/d x_ak, re = the element
+ * residual of ComputeElement BEFORE the Dirichlet mask (fe_response.py:312-331, 424-442: jacrev there, closed
+ * forms here).  accumulate != 0 adds to the arrays (they hold the response part).  Physics: FOL_MECHANICAL,
+ * FOL_THERMAL; others return FOL_ERR_UNSUPPORTED. */
+int fol_residual_adjoint_elements(fol_stream_t s, int dtype, int physics, int element, int num_gp, int accumulate,
+                                  int64_t ne, const void* xyz, const int32_t* conn, const void* ctrl, const void* u,
+                                  const void* adj, const double* params_host, void* dk_elem, void* dx_elem);
+
+/* out[0] = sum of x[0..n) in a fixed order (one block): ComputeValue's jnp.sum, fe_response.py:216 */
+int fol_sum(fol_stream_t s, int dtype, int64_t n, const void* x, void* out);
+
 /* ---- host-buffer entry point (what a non-GPU caller binds; used for the e2e measurement) -- */
 
 typedef struct fol_plan fol_plan;

@@ -33,13 +33,13 @@ def b_matrix(gradN):
     a, dim = gradN.shape[-2:]
     lead = gradN.shape[:-2]
     if dim == 2:
-        B = np.zeros(lead + (3, 2 * a))
+        B = np.zeros(lead + (3, 2 * a), dtype=gradN.dtype)
         B[..., 0, 0::2] = gradN[..., 0]
         B[..., 1, 1::2] = gradN[..., 1]
         B[..., 2, 0::2] = gradN[..., 1]
         B[..., 2, 1::2] = gradN[..., 0]
         return B
-    B = np.zeros(lead + (6, 3 * a))      # rows [xx, yy, zz, xy, yz, xz]
+    B = np.zeros(lead + (6, 3 * a), dtype=gradN.dtype)      # rows [xx, yy, zz, xy, yz, xz]
     B[..., 0, 0::3] = gradN[..., 0]
     B[..., 1, 1::3] = gradN[..., 1]
     B[..., 2, 2::3] = gradN[..., 2]
@@ -186,13 +186,13 @@ def neo_hooke_b_matrix(gradN, F):
     lead = gradN.shape[:-2]
     g = gradN
     if d == 2:
-        B = np.zeros(lead + (3, 2 * a))
+        B = np.zeros(lead + (3, 2 * a), dtype=np.result_type(gradN, F))
         for c in range(2):
             B[..., 0, c::2] = F[..., c, 0, None] * g[..., 0]
             B[..., 1, c::2] = F[..., c, 1, None] * g[..., 1]
             B[..., 2, c::2] = F[..., c, 1, None] * g[..., 0] + F[..., c, 0, None] * g[..., 1]
         return B
-    B = np.zeros(lead + (6, 3 * a))
+    B = np.zeros(lead + (6, 3 * a), dtype=np.result_type(gradN, F))
     for c in range(3):
         B[..., 0, c::3] = F[..., c, 0, None] * g[..., 0]
         B[..., 1, c::3] = F[..., c, 1, None] * g[..., 1]
@@ -225,7 +225,7 @@ def neo_hooke_element(element_type, num_gp, X, de, u, E, nu, body=None, law="neo
     wd = w[None, :] * detJ
     Kmat = np.einsum("eg,egsn,egst,egtm->enm", wd, B, Cv, B, optimize=True)
     vo = _VOIGT3 if d == 3 else _VOIGT2
-    S_mat = np.zeros(Sv.shape[:-1] + (d, d))
+    S_mat = np.zeros(Sv.shape[:-1] + (d, d), dtype=Sv.dtype)
     for v, (i, j) in enumerate(vo):
         S_mat[..., i, j] = Sv[..., v]
         S_mat[..., j, i] = Sv[..., v]
