@@ -121,7 +121,7 @@ class SlabPartition:
 GRID_MARGIN_CTAS = 0   # measured on 2/4/8 B200: a margin does not pay; NCCL's kernels fit next to the persistent CTAs
 
 
-def assemble_overlapped(loss, part, controls, dofs, ke_out, comm_stream, group=None):
+def assemble_overlapped(loss, part, controls, dofs, ke_out, comm_stream, group=None, state_in=None, state_out=None):
     """Residual + Jacobian of one slab with the halo-DOF exchange hidden behind the element stage.
 
     The element layers touching the slab interfaces are contiguous element ranges (the generator
@@ -132,6 +132,9 @@ def assemble_overlapped(loss, part, controls, dofs, ke_out, comm_stream, group=N
       4. meanwhile on the main stream: element stage on the interior layers, gather of all interior
          nodes,
       5. main stream joins the communication stream.
+    History-dependent elements (J2 elastoplasticity, BASELINE.json configs[4]): `state_in` / `state_out` are this
+    slab's Gauss-point history (ne, g, 7|4); the state is element-local, so like the Jacobian blocks it needs no
+    exchange -- every element-range launch reads and writes its own slice.
     Returns (ke_out, residual)."""
     from . import _lib
     lib = _lib.load()
@@ -146,6 +149,18 @@ def assemble_overlapped(loss, part, controls, dofs, ke_out, comm_stream, group=N
     R = torch.empty(loss.total_number_of_dofs, dtype=loss.dtype, device=loss.device)
     phys, elem = _lib.PHYSICS[loss.physics], loss.fe_element.code
     s = _lib.stream_ptr()
+    st_bytes = 0                                    # bytes of Gauss-point history per element
+    if state_in is not None or state_out is not None:
+        if loss.physics != "j2plasticity":
+            raise ValueError("assemble_overlapped: Gauss-point state is an input of the elastoplastic losses only")
+        if state_in is None or state_out is None:
+            raise ValueError("assemble_overlapped: state_in and state_out go together")
+        state_in = _lib.to_device(state_in, loss.dtype)
+        if (not state_out.is_cuda or not state_out.is_contiguous() or state_out.dtype != loss.dtype
+                or state_out.numel() != state_in.numel() or state_in.numel() % max(ne, 1)):
+            raise ValueError("assemble_overlapped: state_out must be a contiguous CUDA tensor shaped like state_in "
+                             "(ne, g, 7|4)")
+        st_bytes = esz * (state_in.numel() // max(ne, 1))
 
     def elements(e0, cnt):
         if cnt <= 0:
@@ -154,7 +169,8 @@ def assemble_overlapped(loss, part, controls, dofs, ke_out, comm_stream, group=N
                                              loss._conn.data_ptr() + 4 * A * e0, _lib.ptr(K), _lib.ptr(u),
                                              _lib.ptr(loss._dir_flag), loss._params,
                                              ke_out.data_ptr() + esz * nd * nd * e0, re.data_ptr() + esz * nd * e0,
-                                             None, None))
+                                             (state_in.data_ptr() + st_bytes * e0) if st_bytes else None,
+                                             (state_out.data_ptr() + st_bytes * e0) if st_bytes else None))
 
     def gather(n0, cnt):
         if cnt <= 0:
