@@ -803,20 +803,20 @@ int launch_assemble(cudaStream_t s, const AsmArgs<T>& args) {
   const long long grid = cdiv(args.ne, GPB);
   if (args.v) {
     auto kern = assemble_kernel<T, ELEM, ORDER, PHYS, BLOCK, true>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.need()) {
       FOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-      configured = true;
+      configured.done();
     }
     if (grid == 0) return FOL_OK;
     kern<<<(unsigned)grid, BLOCK, smem, s>>>(args);
     return check_launch("assemble_kernel (matrix-free)");
   }
   auto kern = assemble_kernel<T, ELEM, ORDER, PHYS, BLOCK, false>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     FOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
-    configured = true;
+    configured.done();
   }
   if (grid == 0) return FOL_OK;
   kern<<<(unsigned)grid, BLOCK, smem, s>>>(args);

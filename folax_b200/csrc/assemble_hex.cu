@@ -352,8 +352,9 @@ std::atomic<int> g_grid_margin{0};
 
 int assemble_hex_mech_f64(cudaStream_t s, const AsmArgs<double>& args) {
   static int grid = 0;
+  static PerDeviceOnce configured;
   const size_t smem = sizeof(WarpSmem) * kWarps;
-  if (!grid) {
+  if (configured.need() || !grid) {
     FOL_CUDA(cudaFuncSetAttribute(assemble_hex_mech_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     int dev = 0, sms = 148, per_sm = 1;
@@ -361,6 +362,7 @@ int assemble_hex_mech_f64(cudaStream_t s, const AsmArgs<double>& args) {
     FOL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     FOL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, assemble_hex_mech_f64_kernel, kWarps * 32, smem));
     grid = sms * (per_sm > 0 ? per_sm : 1);
+    configured.done();
   }
   if (args.ne == 0) return FOL_OK;
   const long long ntiles = cdiv(args.ne, kTile);

@@ -41,6 +41,21 @@ inline int check_launch(const char* what) {
 
 inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
+// One-time kernel configuration (cudaFuncSetAttribute) is PER DEVICE: remembered per call site and device, so a
+// process that drives several GPUs configures each of them; safe to race (the attribute call is idempotent).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};   // devices 0..63; others are configured on every call
+  bool need() const {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    return ((mask.load(std::memory_order_relaxed) >> d) & 1ull) == 0ull;
+  }
+  void done() {
+    int d = 0;
+    if (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 64) mask.fetch_or(1ull << d, std::memory_order_relaxed);
+  }
+};
+
 // material / loss parameters in the arithmetic type of the call (see FOL_NUM_PARAMS)
 template <class T>
 struct Params {

@@ -13,10 +13,12 @@ int launch_energy(cudaStream_t s, const EnergyArgs<T>& args) {
   const size_t smem = sizeof(T) * ((size_t)S * KW * args.ecap + (size_t)2 * S * C * args.lcap);
   if (smem > 200 * 1024) return fail(FOL_ERR_INVALID, "fol_energy_and_grads: tile lists too long for shared memory");
   auto kern = energy_tile_kernel<T, ELEM, ORDER, PHYS, S, BLOCK>;
-  static size_t configured = 0;
-  if (smem > configured) {
+  static size_t configured[64] = {};   // largest size set so far, per device (the attribute is per device)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
+  if (dev < 0 || smem > configured[dev]) {
     FOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+    if (dev >= 0) configured[dev] = smem;
   }
   if (args.ntiles == 0 || args.nb == 0) return FOL_OK;
   long long y = cdiv(148LL * 16, args.ntiles);

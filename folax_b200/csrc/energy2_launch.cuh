@@ -32,10 +32,10 @@ int launch_energy2(cudaStream_t s, const EnergyArgs<T>& args, int ncap, int* par
   if (smem > 220 * 1024 || args.lcap > LCAP || args.ecap > BLOCK || ncap > BLOCK) return 1;
   *parts = BLOCK / 32;
   auto kern = energy_tile2_kernel<T, ELEM, ORDER, PHYS, NL, S, BLOCK, MINB, LCAP>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     FOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configured.done();
   }
   // sample chunks per tile: the grid should fill whole rounds of the 148 * MINB resident CTAs (a fractional
   // last round idles SMs) while every CTA keeps >= 16 passes to amortise its tile set-up
