@@ -73,6 +73,12 @@ class _BatchLossFn(torch.autograd.Function):
             raise RuntimeError("ComputeBatchLoss: backward through the FFI loss a second time is not supported")
         ctx.used = True
         loss = ctx.loss
+        if torch.is_grad_enabled():
+            # create_graph=True: the caller differentiates THROUGH this gradient (the latent-code steps of
+            # meta_implicit_parametric_operator_learning.py:95-105).  The cotangents returned below carry no
+            # graph, i.e. they are constants of the outer differentiation -- which is what the reference computes
+            # only where the element residual sits under stop_gradient.  Anything else must not pass silently.
+            loss._check_second_order(params_need_grad=ctx.needs_input_grad[1])
         grad_u, grad_k = ctx.grads
         up = None
         for g in (g_mean, g_mean2):
@@ -429,6 +435,23 @@ class FiniteElementLoss(Loss):
                                             self._params,
                                             _lib.ptr(grad_u), _lib.ptr(grad_k), _lib.ptr(energy), _lib.ptr(work)))
         return energy, grad_u, grad_k
+
+    # how the reference's energy behaves under a SECOND differentiation:
+    #   "zero"        E = u^T stop_gradient(re) (mechanical.py:116): every second derivative is zero
+    #   "zero_in_u"   thermal.py:31, 45-46: T is stopped inside Se and re, so d2E/dT2 = 0, but d2E/dT dK is not
+    #   None          a true potential (Neo-Hooke, St-Venant, transient thermal, Allen-Cahn): the Hessian is the
+    #                 tangent stiffness; not available through this entry point (ApplyJacobian gives J v)
+    _second_order = None
+
+    def _check_second_order(self, params_need_grad):
+        if float(self.loss_function_exponent) == 1.0:       # E^p with p != 1 adds p(p-1)E^(p-2) dE dE^T
+            if self._second_order == "zero":
+                return
+            if self._second_order == "zero_in_u" and not params_need_grad:
+                return
+        raise NotImplementedError(
+            f"{self.GetName()}: second-order differentiation of ComputeBatchLoss is not available for this loss "
+            "(the first-order cotangents would be treated as constants, which differs from the reference here)")
 
     def ComputeBatchLoss(self, batch_params, batch_dofs):
         """fe_loss.py:250-262 -> (mean_b E_b^p, (min, max, mean)); differentiable w.r.t. both inputs

@@ -8,6 +8,7 @@ from .fe_loss import FiniteElementLoss
 
 class MechanicalLoss(FiniteElementLoss):
     physics = "mechanical"
+    _second_order = "zero"
     _has_control_gradient = False  # Se sits inside stop_gradient (mechanical.py:116): dE/dK = 0
 
     def Initialize(self, reinitialize=False) -> None:

@@ -11,6 +11,7 @@ from .mechanical import MechanicalLoss
 
 class ElastoplasticityLoss(MechanicalLoss):
     physics = "j2plasticity"
+    _second_order = None
 
     def _material_params(self):
         p = super()._material_params()

@@ -5,6 +5,7 @@ from .fe_loss import FiniteElementLoss
 
 class ThermalLoss(FiniteElementLoss):
     physics = "thermal"
+    _second_order = "zero_in_u"
 
     def Initialize(self, reinitialize=False) -> None:
         if self.initialized and not reinitialize:

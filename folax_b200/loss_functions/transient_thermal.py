@@ -12,6 +12,7 @@ from .thermal import ThermalLoss
 
 class TransientThermalLoss(ThermalLoss):
     physics = "transient_thermal"
+    _second_order = None       # a true potential (transient_thermal.py:42-73)
 
     def Initialize(self, reinitialize=False) -> None:
         if self.initialized and not reinitialize:
