@@ -51,7 +51,7 @@ SIGNATURES = {
     "fol_gauss_interpolate": (_int, [_vp, _int, _int, _int, _int, _i64, _i32p, _vp, _vp, _vp, _vp]),
     "fol_response_elements": (_int, [_vp, _int, _int, _int, _int, _i64, _vp, _i32p, _vp, _vp, _vp, _vp, _vp, _vp,
                                      _vp]),
-    "fol_residual_adjoint_elements": (_int, [_vp, _int, _int, _int, _int, _int, _i64, _vp, _i32p, _vp, _vp, _vp,
+    "fol_residual_adjoint_elements": (_int, [_vp, _int, _int, _int, _int, _int, _i64, _vp, _i32p, _vp, _vp, _vp, _vp,
                                              C.POINTER(_dbl), _vp, _vp]),
     "fol_sum": (_int, [_vp, _int, _i64, _vp, _vp]),
     "fol_plan_create": (_int, [C.POINTER(_vp), _int, _int, _int, _int, _i64, _i64, _vp, _i32p, _i32p, _i64,

@@ -120,13 +120,14 @@ static int response_typed(cudaStream_t s, int element, int num_gp, int dpn, long
 template <class T>
 static int adjoint_typed(cudaStream_t s, int physics, int element, int num_gp, int accumulate, long long ne,
                          const void* xyz, const int32_t* conn, const void* ctrl, const void* u, const void* lam,
-                         const double* params, void* dk, void* dx) {
+                         const void* aux, const double* params, void* dk, void* dx) {
   AdjointArgs<T> a;
   a.xyz = (const T*)xyz;
   a.conn = conn;
   a.ctrl = (const T*)ctrl;
   a.u = (const T*)u;
   a.lam = (const T*)lam;
+  a.aux = (const T*)aux;
   a.dk = (T*)dk;
   a.dx = (T*)dx;
   a.ne = ne;
@@ -134,9 +135,15 @@ static int adjoint_typed(cudaStream_t s, int physics, int element, int num_gp, i
   a.p = make_params<T>(params);
   if (physics == FOL_MECHANICAL) return launch_adjoint<T, ADJ_MECH>(s, element, num_gp, a);
   if (physics == FOL_THERMAL) return launch_adjoint<T, ADJ_THERMAL>(s, element, num_gp, a);
+  if (physics == FOL_NEOHOOKE) return launch_adjoint<T, ADJ_NEOHOOKE>(s, element, num_gp, a);
+  if (physics == FOL_STVENANT) return launch_adjoint<T, ADJ_STVK>(s, element, num_gp, a);
+  if (physics == FOL_ALLEN_CAHN) return launch_adjoint<T, ADJ_ALLENCAHN>(s, element, num_gp, a);
+  if (physics == FOL_TRANSIENT_THERMAL) {
+    if (!aux) return fail(FOL_ERR_INVALID, "fol_residual_adjoint_elements: transient thermal needs the nodal k0 in aux");
+    return launch_adjoint<T, ADJ_TTHERMAL>(s, element, num_gp, a);
+  }
   return fail(FOL_ERR_UNSUPPORTED,
-              "fol_residual_adjoint_elements: closed-form residual sensitivities exist for the mechanical and "
-              "thermal losses only");
+              "fol_residual_adjoint_elements: no residual sensitivities for history-dependent (J2) elements");
 }
 
 }  // namespace fol
@@ -176,17 +183,18 @@ int fol_response_elements(fol_stream_t s, int dtype, int element, int num_gp, in
 
 int fol_residual_adjoint_elements(fol_stream_t s, int dtype, int physics, int element, int num_gp, int accumulate,
                                   int64_t ne, const void* xyz, const int32_t* conn, const void* ctrl, const void* u,
-                                  const void* adj, const double* params_host, void* dk_elem, void* dx_elem) {
+                                  const void* adj, const void* aux, const double* params_host, void* dk_elem,
+                                  void* dx_elem) {
   FOL_REQUIRE(element >= 0 && element <= 3 && num_gp >= 1 && num_gp <= 3,
               "fol_residual_adjoint_elements: bad element / num_gp");
   FOL_REQUIRE(ne >= 0 && xyz && conn && ctrl && u && adj && params_host && (dk_elem || dx_elem),
               "fol_residual_adjoint_elements: null pointer / negative size");
   if (dtype == FOL_F64)
     return adjoint_typed<double>((cudaStream_t)s, physics, element, num_gp, accumulate, ne, xyz, conn, ctrl, u, adj,
-                                 params_host, dk_elem, dx_elem);
+                                 aux, params_host, dk_elem, dx_elem);
   if (dtype == FOL_F32)
     return adjoint_typed<float>((cudaStream_t)s, physics, element, num_gp, accumulate, ne, xyz, conn, ctrl, u, adj,
-                                params_host, dk_elem, dx_elem);
+                                aux, params_host, dk_elem, dx_elem);
   return fail(FOL_ERR_INVALID, "fol_residual_adjoint_elements: unknown dtype");
 }
 

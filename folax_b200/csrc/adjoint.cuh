@@ -195,4 +195,225 @@ __host__ __device__ inline void residual_adjoint_element(const T* X, const T* de
   }
 }
 
+
+// ---- forward-mode route for the other losses ---------------------------------------------------------------
+// phi = lam_e^T re(x_e, de) written once in a generic scalar type S; with S = Dual<T> one evaluation gives one
+// directional derivative, and the A*D + A directions of an element are swept one after the other (no closed form
+// to derive per constitutive law).  Used for the finite-strain losses (mechanical_neohooke.py:243-275,
+// mechanical_saint_venant.py) and the implicit-Euler scalar losses (transient_thermal.py:42-73,
+// phase_field.py:38-70); the linear-elastic and thermal closed forms above are checked against it in the tests.
+enum : int { ADJ_NEOHOOKE = 2, ADJ_STVK = 4, ADJ_TTHERMAL = 5, ADJ_ALLENCAHN = 6 };
+
+template <class T>
+struct Dual {
+  T v, d;
+  __host__ __device__ Dual() : v((T)0), d((T)0) {}
+  __host__ __device__ Dual(T a, T b) : v(a), d(b) {}
+  __host__ __device__ Dual(double a) : v((T)a), d((T)0) {}
+  __host__ __device__ Dual(float a) : v((T)a), d((T)0) {}
+  __host__ __device__ Dual(int a) : v((T)a), d((T)0) {}
+  __host__ __device__ friend Dual operator+(const Dual& a, const Dual& b) { return Dual(a.v + b.v, a.d + b.d); }
+  __host__ __device__ friend Dual operator-(const Dual& a, const Dual& b) { return Dual(a.v - b.v, a.d - b.d); }
+  __host__ __device__ friend Dual operator-(const Dual& a) { return Dual(-a.v, -a.d); }
+  __host__ __device__ friend Dual operator*(const Dual& a, const Dual& b) {
+    return Dual(a.v * b.v, a.v * b.d + a.d * b.v);
+  }
+  __host__ __device__ friend Dual operator/(const Dual& a, const Dual& b) {
+    const T r = (T)1 / b.v, q = a.v * r;
+    return Dual(q, (a.d - q * b.d) * r);
+  }
+  __host__ __device__ Dual& operator+=(const Dual& b) { v += b.v; d += b.d; return *this; }
+  __host__ __device__ Dual& operator-=(const Dual& b) { v -= b.v; d -= b.d; return *this; }
+  __host__ __device__ Dual& operator*=(const Dual& b) { *this = *this * b; return *this; }
+};
+
+__host__ __device__ inline double fol_log(double x) { return log(x); }
+__host__ __device__ inline float fol_log(float x) { return logf(x); }
+__host__ __device__ inline double fol_pow(double x, double a) { return pow(x, a); }
+__host__ __device__ inline float fol_pow(float x, double a) { return powf(x, (float)a); }
+template <class T>
+__host__ __device__ inline Dual<T> fol_log(const Dual<T>& x) { return Dual<T>(fol_log(x.v), x.d / x.v); }
+template <class T>
+__host__ __device__ inline Dual<T> fol_pow(const Dual<T>& x, double a) {
+  const T p1 = fol_pow(x.v, a - 1.0);
+  return Dual<T>(p1 * x.v, (T)a * p1 * x.d);
+}
+
+template <class S, int D>
+__host__ __device__ inline S det_small(const S (&M)[D][D]) {
+  if constexpr (D == 2) return M[0][0] * M[1][1] - M[0][1] * M[1][0];
+  else
+    return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) + M[0][1] * (M[1][2] * M[2][0] - M[1][0] * M[2][2]) +
+           M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+}
+
+template <class S, int D>
+__host__ __device__ inline void inv_sym_small(const S (&C)[D][D], S (&iC)[D][D]) {
+  const S r = S(1) / det_small<S, D>(C);
+  if constexpr (D == 2) {
+    iC[0][0] = C[1][1] * r; iC[0][1] = -C[0][1] * r; iC[1][0] = -C[1][0] * r; iC[1][1] = C[0][0] * r;
+  } else {
+    iC[0][0] = (C[1][1] * C[2][2] - C[1][2] * C[2][1]) * r;
+    iC[0][1] = (C[0][2] * C[2][1] - C[0][1] * C[2][2]) * r;
+    iC[0][2] = (C[0][1] * C[1][2] - C[0][2] * C[1][1]) * r;
+    iC[1][0] = (C[1][2] * C[2][0] - C[1][0] * C[2][2]) * r;
+    iC[1][1] = (C[0][0] * C[2][2] - C[0][2] * C[2][0]) * r;
+    iC[1][2] = (C[0][2] * C[1][0] - C[0][0] * C[1][2]) * r;
+    iC[2][0] = (C[1][0] * C[2][1] - C[1][1] * C[2][0]) * r;
+    iC[2][1] = (C[0][1] * C[2][0] - C[0][0] * C[2][1]) * r;
+    iC[2][2] = (C[0][0] * C[1][1] - C[0][1] * C[1][0]) * r;
+  }
+}
+
+// phi = lam_e^T re for one element; X (A x 3) and de (A) in S, the dofs, the adjoint and the auxiliary nodal
+// field (transient thermal: k0) in T.  PHYS uses the values of fol_physics.
+template <class S, class T, int ELEM, int ORDER, int PHYS>
+__host__ __device__ inline S element_phi(const S* X, const S* de, const T* ue, const T* le, const T* aux,
+                                         const Params<T>& P) {
+  constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM), NGP = elem_ngauss(ELEM, ORDER);
+  constexpr bool SCALAR = (PHYS == ADJ_THERMAL || PHYS == ADJ_TTHERMAL || PHYS == ADJ_ALLENCAHN);
+  constexpr bool TRANSPOSED = (PHYS == ADJ_TTHERMAL || PHYS == ADJ_ALLENCAHN);
+  S phi = S(0);
+  for (int g = 0; g < NGP; ++g) {
+    double xi[3], w;
+    gauss_point<ELEM, ORDER>(g, xi, w);
+    S N[A], dN[A][D], gN[A][D];
+    shape_functions<ELEM, S>(xi, N, dN);
+    const S det = global_gradients<ELEM, S, TRANSPOSED>(X, dN, gN);
+    const S wd = S(w) * det;
+    S eg = S(0);
+    for (int b = 0; b < A; ++b) eg += N[b] * de[b];
+    if constexpr (SCALAR) {
+      S fn = S(0), lg = S(0), kg = S(0), q = S(0);
+      for (int b = 0; b < A; ++b) {
+        fn += N[b] * S(ue[b]);
+        lg += N[b] * S(le[b]);
+        if (aux) kg += N[b] * S(aux[b]);
+      }
+      for (int k = 0; k < D; ++k) {
+        S gf = S(0), gl = S(0);
+        for (int b = 0; b < A; ++b) {
+          gf += gN[b][k] * S(ue[b]);
+          gl += gN[b][k] * S(le[b]);
+        }
+        q += gf * gl;
+      }
+      if constexpr (PHYS == ADJ_THERMAL) {
+        const T beta = P.v[5];
+        const S nl = S(1) + ((beta != (T)0) ? S(beta) * fol_pow(fn, (double)P.v[6]) : S(0));
+        phi += wd * eg * nl * q;
+      } else if constexpr (PHYS == ADJ_TTHERMAL) {
+        const T beta = P.v[5], dt = P.v[10], rcp = P.v[8] * P.v[9];
+        const S Kg = kg * (S(1) + ((beta != (T)0) ? S(beta) * fol_pow(fn, (double)P.v[6]) : S(0)));
+        phi += wd * (S(rcp) * (fn - eg) * lg + S(dt) * Kg * q);
+      } else {
+        const T dt = P.v[10], ie2 = (T)1 / (P.v[11] * P.v[11]);
+        phi += wd * (((fn - eg) + S(dt * ie2) * (fn * fn - S(1)) * fn) * lg + S(dt) * q);
+      }
+    } else {
+      S Gu[D][D], Gl[D][D];
+      S bl = S(0);
+      for (int i = 0; i < D; ++i) {
+        S lgi = S(0);
+        for (int b = 0; b < A; ++b) lgi += N[b] * S(le[b * D + i]);
+        bl += S(P.v[2 + i]) * lgi;
+        for (int j = 0; j < D; ++j) {
+          S su = S(0), sl = S(0);
+          for (int b = 0; b < A; ++b) {
+            su += gN[b][j] * S(ue[b * D + i]);
+            sl += gN[b][j] * S(le[b * D + i]);
+          }
+          Gu[i][j] = su;
+          Gl[i][j] = sl;
+        }
+      }
+      const T nu = P.v[1];
+      S q = S(0);
+      if constexpr (PHYS == ADJ_MECH) {
+        const T E = P.v[0];
+        T lam, mu;
+        if constexpr (D == 3) {
+          const T c1 = E / (((T)1 + nu) * ((T)1 - (T)2 * nu));
+          lam = c1 * nu;
+          mu = c1 * (T)0.5 * ((T)1 - (T)2 * nu);
+        } else {
+          const T fpl = E / ((T)1 - nu * nu);
+          lam = fpl * nu;
+          mu = fpl * ((T)1 - nu) * (T)0.5;
+        }
+        S tru = S(0);
+        for (int i = 0; i < D; ++i) tru += Gu[i][i];
+        for (int i = 0; i < D; ++i)
+          for (int j = 0; j < D; ++j)
+            q += (S(mu) * (Gu[i][j] + Gu[j][i]) + (i == j ? S(lam) * tru : S(0))) * Gl[i][j];
+        q = eg * q;
+      } else {
+        S F[D][D], C[D][D], Sm[D][D];
+        for (int i = 0; i < D; ++i)
+          for (int j = 0; j < D; ++j) F[i][j] = Gu[i][j] + (i == j ? S(1) : S(0));
+        for (int i = 0; i < D; ++i)
+          for (int j = 0; j < D; ++j) {
+            S acc = S(0);
+            for (int m = 0; m < D; ++m) acc += F[m][i] * F[m][j];
+            C[i][j] = acc;
+          }
+        const S mu = eg / S((T)2 * ((T)1 + nu));
+        if constexpr (PHYS == ADJ_NEOHOOKE) {   // neo_hooke.py:14-58, 64-109
+          S iC[D][D];
+          inv_sym_small<S, D>(C, iC);
+          const S J = det_small<S, D>(F);
+          S trC = S(0);
+          for (int i = 0; i < D; ++i) trC += C[i][i];
+          const S kk = eg / S((T)3 * ((T)1 - (T)2 * nu));
+          const S p = S(0.5) * kk * (J - S(1) / J);
+          const S Jm = (D == 2) ? S(1) / J : fol_pow(J, -2.0 / 3.0);
+          for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j)
+              Sm[i][j] = J * p * iC[i][j] + Jm * mu * ((i == j ? S(1) : S(0)) - trC * iC[i][j] / S((T)D));
+        } else {                                // saint_venant.py:11-33
+          const S lam = eg * S(nu / (((T)1 + nu) * ((T)1 - (T)2 * nu)));
+          S trE = S(0);
+          for (int i = 0; i < D; ++i) trE += S(0.5) * (C[i][i] - S(1));
+          for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j)
+              Sm[i][j] = (i == j ? lam * trE : S(0)) + mu * (C[i][j] - (i == j ? S(1) : S(0)));
+        }
+        for (int i = 0; i < D; ++i)
+          for (int j = 0; j < D; ++j) {
+            S ftl = S(0);
+            for (int c = 0; c < D; ++c) ftl += F[c][i] * Gl[c][j];
+            q += Sm[i][j] * ftl;
+          }
+      }
+      phi += wd * (q - bl);
+    }
+  }
+  return phi;
+}
+
+// The A*D + A directional derivatives of phi, one forward sweep each.
+template <class T, int ELEM, int ORDER, int PHYS>
+__host__ __device__ inline void residual_adjoint_element_dual(const T* X, const T* de, const T* ue, const T* le,
+                                                              const T* aux, const Params<T>& P, T* dK, T* dX) {
+  constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM);
+  using S = Dual<T>;
+  S Xs[A * 3], ds[A];
+  for (int i = 0; i < A * 3; ++i) Xs[i] = S(X[i], (T)0);
+  for (int b = 0; b < A; ++b) ds[b] = S(de[b], (T)0);
+  for (int b = 0; b < A; ++b) {
+    for (int k = 0; k < 3; ++k) {
+      if (k >= D) {
+        dX[b * 3 + k] = (T)0;
+        continue;
+      }
+      Xs[b * 3 + k].d = (T)1;
+      dX[b * 3 + k] = element_phi<S, T, ELEM, ORDER, PHYS>(Xs, ds, ue, le, aux, P).d;
+      Xs[b * 3 + k].d = (T)0;
+    }
+    ds[b].d = (T)1;
+    dK[b] = element_phi<S, T, ELEM, ORDER, PHYS>(Xs, ds, ue, le, aux, P).d;
+    ds[b].d = (T)0;
+  }
+}
+
 }  // namespace fol

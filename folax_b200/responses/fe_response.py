@@ -11,8 +11,8 @@ order, no atomics).  The formula is the caller's Python expression, exactly as i
 pointwise over the (ne, g) Gauss-point arrays on the device, and its partials df/dK, df/dU come from one
 torch.autograd.grad over those arrays (the reference uses jax.grad for the same purpose).  No CPU fallback.
 
-Residual sensitivities exist in closed form for the mechanical and thermal loss families
-(MechanicalLoss*/ThermalLoss*); other losses raise FolaxError from the C ABI.
+Residual sensitivities: closed forms for the mechanical and thermal loss families, forward-mode sweeps for
+Neo-Hooke, St-Venant, transient thermal and Allen-Cahn; the history-dependent J2 loss raises FolaxError.
 """
 import math
 
@@ -160,8 +160,8 @@ class FiniteElementResponse(Response):
         L = self.fe_loss
         _lib.check(_lib.load().fol_residual_adjoint_elements(
             _lib.stream_ptr(), L._dt, _lib.PHYSICS[L.physics], L.fe_element.code, L.num_gp, 1, L._ne,
-            _lib.ptr(L._xyz), _lib.ptr(L._conn), _lib.ptr(ctrl), _lib.ptr(u), _lib.ptr(lam), L._params,
-            _lib.ptr(dk), _lib.ptr(dx)))
+            _lib.ptr(L._xyz), _lib.ptr(L._conn), _lib.ptr(ctrl), _lib.ptr(u), _lib.ptr(lam),
+            _lib.ptr(getattr(L, "_geom_aux", None)), L._params, _lib.ptr(dk), _lib.ptr(dx)))
 
     # ------------------------------------------------------------------ API of fe_response.py
     def ComputeValue(self, nodal_control_values, nodal_dof_values):

@@ -216,12 +216,15 @@ int fol_response_elements(fol_stream_t s, int dtype, int element, int num_gp, in
                           const void* fu_gp, void* value_elem, void* du_elem, void* dk_elem, void* dx_elem);
 
 /* dk_elem[e, a] (+)= adj_e^T d re/d ctrl_a,  dx_elem[e, a*3+k] (+)= adj_e^T d re/d x_ak, re = the element
- * residual of ComputeElement BEFORE the Dirichlet mask (fe_response.py:312-331, 424-442: jacrev there, closed
- * forms here).  accumulate != 0 adds to the arrays (they hold the response part).  Physics: FOL_MECHANICAL,
- * FOL_THERMAL; others return FOL_ERR_UNSUPPORTED. */
+ * residual of ComputeElement BEFORE the Dirichlet mask (fe_response.py:312-331, 424-442: jacrev there).
+ * accumulate != 0 adds to the arrays (they hold the response part).  Mechanical and thermal: closed forms;
+ * Neo-Hooke, St-Venant, transient thermal (aux = nodal k0, (ctrl, u) = (current, next) field) and Allen-Cahn:
+ * forward-mode sweeps of the element's A*dim + A directions; J2 returns FOL_ERR_UNSUPPORTED.  aux: NULL unless
+ * the physics has an auxiliary nodal field. */
 int fol_residual_adjoint_elements(fol_stream_t s, int dtype, int physics, int element, int num_gp, int accumulate,
                                   int64_t ne, const void* xyz, const int32_t* conn, const void* ctrl, const void* u,
-                                  const void* adj, const double* params_host, void* dk_elem, void* dx_elem);
+                                  const void* adj, const void* aux, const double* params_host, void* dk_elem,
+                                  void* dx_elem);
 
 /* out[0] = sum of x[0..n) in a fixed order (one block): ComputeValue's jnp.sum, fe_response.py:216 */
 int fol_sum(fol_stream_t s, int dtype, int64_t n, const void* x, void* out);

@@ -41,6 +41,12 @@ def _element_residual(physics, element_type, num_gp, X, de, ue, params):
     if physics in ("neohooke", "stvenant"):
         return losses.neo_hooke_element(element_type, num_gp, X, de, ue, params["young_modulus"],
                                         params["poisson_ratio"], params.get("body_force"), law=physics)[1]
+    if physics == "transient_thermal":       # (de, ue) = (current, next) temperatures; k0 per element node
+        return losses.transient_thermal_element(element_type, num_gp, X, de, ue, params["k0"], params["rho"],
+                                                params["cp"], params["time_step"], params.get("beta", 0.0),
+                                                params.get("c", 1.0))[1]
+    if physics == "allen_cahn":
+        return losses.allen_cahn_element(element_type, num_gp, X, de, ue, params["dt"], params["epsilon"])[1]
     raise ValueError(physics)
 
 
@@ -89,6 +95,14 @@ def residual_adjoint_grads(physics, element_type, num_gp, X, de, ue, lam_e, para
     return _complex_step(phi_k, de), _complex_step(phi_x, X.reshape(ne, a * 3))
 
 
+def _element_params(params, conn):
+    """Nodal auxiliary fields (transient thermal: k0) gathered to the elements."""
+    if "k0" in params and np.ndim(params["k0"]) == 1:
+        params = dict(params)
+        params["k0"] = np.asarray(params["k0"], float)[conn]
+    return params
+
+
 def _gather(physics, element_type, coords, conn, controls, dofs):
     d = assembly.dofs_per_node(physics, element_type)
     return d, coords[conn].astype(float), controls[conn].astype(float), dofs[assembly.element_dof_ids(conn, d)]
@@ -125,6 +139,7 @@ def control_derivatives(f, physics, element_type, num_gp, coords, conn, controls
     """fe_response.py:486-524 (one control per node)."""
     d, X, de, ue = _gather(physics, element_type, coords, conn, controls, dofs)
     lam_e = adj_dofs[assembly.element_dof_ids(conn, d)]
+    params = _element_params(params, conn)
     _, dK, _ = element_value_grads(f, element_type, num_gp, d, X, de, ue)
     rK, _ = residual_adjoint_grads(physics, element_type, num_gp, X, de, ue, lam_e, params)
     out = np.zeros(coords.shape[0])
@@ -136,6 +151,7 @@ def shape_derivatives(f, physics, element_type, num_gp, coords, conn, controls, 
     """fe_response.py:358-394 -> (3*nn,), node-major."""
     d, X, de, ue = _gather(physics, element_type, coords, conn, controls, dofs)
     lam_e = adj_dofs[assembly.element_dof_ids(conn, d)]
+    params = _element_params(params, conn)
     _, _, dX = element_value_grads(f, element_type, num_gp, d, X, de, ue)
     _, rX = residual_adjoint_grads(physics, element_type, num_gp, X, de, ue, lam_e, params)
     out = np.zeros(3 * coords.shape[0])

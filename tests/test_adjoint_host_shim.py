@@ -50,16 +50,69 @@ def _case(etype, physics, seed=0):
     return coords, conn, d, K, u, lam
 
 
-def _params(physics, dim):
+PHYS = {"mechanical": 0, "thermal": 1, "neohooke": 2, "stvenant": 4, "transient_thermal": 5, "allen_cahn": 6}
+
+
+def _params(physics, dim, conn=None, nn=0):
+    """(double[12] of include/folax_b200.h, the oracle's parameter dict, nodal aux field or None)."""
     arr = np.zeros(12)
-    if physics == "mechanical":
+    if physics in ("mechanical", "neohooke", "stvenant"):
         arr[0], arr[1] = 1.3, 0.3
         arr[2:2 + dim] = [0.2, -0.4, 0.7][:dim]
-        return arr, {"young_modulus": 1.3, "poisson_ratio": 0.3, "body_force": arr[2:2 + dim].copy()}
-    arr[5], arr[6] = 2.0, 4.0
-    return arr, {"beta": 2.0, "c": 4.0}
+        return arr, {"young_modulus": 1.3, "poisson_ratio": 0.3, "body_force": arr[2:2 + dim].copy()}, None
+    if physics == "thermal":
+        arr[5], arr[6] = 2.0, 4.0
+        return arr, {"beta": 2.0, "c": 4.0}, None
+    if physics == "transient_thermal":
+        arr[5], arr[6], arr[8], arr[9], arr[10] = 1.5, 2.0, 1.2, 0.8, 0.05
+        k0 = np.random.default_rng(42).uniform(0.5, 1.5, nn)
+        return arr, {"beta": 1.5, "c": 2.0, "rho": 1.2, "cp": 0.8, "time_step": 0.05, "k0": k0[conn]}, k0
+    arr[10], arr[11] = 0.01, 0.3
+    return arr, {"dt": 0.01, "epsilon": 0.3}, None
 
 
+@pytest.mark.parametrize("physics", list(PHYS))
+@pytest.mark.parametrize("etype", list(ELEM))
+@pytest.mark.parametrize("num_gp", [1, 2, 3])
+def test_residual_adjoint_sensitivities(shim, physics, etype, num_gp):
+    """fe_response.py:312-331, 424-442: lam_e^T d re/d K_e and lam_e^T d re/d x_e -- the closed forms
+    (mechanical, thermal) and the forward-mode sweeps (the other losses) of csrc/adjoint.cuh against complex-step
+    differentiation of the oracle's ComputeElement."""
+    coords, conn, d, K, u, lam = _case(etype, physics, seed=3)
+    if physics in ("neohooke", "stvenant"):
+        u = 0.05 * (u - 0.5)                                            # keep det F > 0
+    ne, a = conn.shape
+    dim = 3 if etype in ("hexahedron", "tetra") else 2
+    arr, par, aux = _params(physics, dim, conn, coords.shape[0])
+    dk, dx = np.full((ne, a), 0.5), np.full((ne, a * 3), -0.25)        # accumulate on top of these
+    assert shim.host_residual_adjoint_elements(PHYS[physics], ELEM[etype], num_gp, 1, C.c_longlong(ne), _p(coords),
+                                               _p(conn), _p(K), _p(u), _p(lam), _p(aux), _p(arr), _p(dk), _p(dx)) == 0
+    g = assembly.element_dof_ids(conn, d)
+    rK, rX = responses.residual_adjoint_grads(physics, etype, num_gp, coords[conn], K[conn], u[g], lam[g], par)
+    assert np.abs(dk - 0.5 - rK).max() <= 1e-11 * np.abs(rK).max()
+    assert np.abs(dx + 0.25 - rX).max() <= 1e-11 * np.abs(rX).max()
+    if dim == 2:
+        assert np.all(dx[:, 2::3] == -0.25)                             # unused coordinate: exact zeros added
+    # overwrite mode, one output only
+    dk2 = np.full((ne, a), 9.0)
+    assert shim.host_residual_adjoint_elements(PHYS[physics], ELEM[etype], num_gp, 0, C.c_longlong(ne), _p(coords),
+                                               _p(conn), _p(K), _p(u), _p(lam), _p(aux), _p(arr), _p(dk2), None) == 0
+    assert np.abs(dk2 - rK).max() <= 1e-11 * np.abs(rK).max()
+
+
+@pytest.mark.parametrize("physics", ["mechanical", "thermal"])
+@pytest.mark.parametrize("etype,num_gp", [("hexahedron", 2), ("quad", 3), ("tetra", 2), ("triangle", 1)])
+def test_closed_forms_equal_forward_mode(shim, physics, etype, num_gp):
+    """The two differentiation routes of csrc/adjoint.cuh on the same inputs."""
+    coords, conn, d, K, u, lam = _case(etype, physics, seed=5)
+    ne, a = conn.shape
+    arr, _, _ = _params(physics, 3 if etype in ("hexahedron", "tetra") else 2)
+    dk, dx, dk2, dx2 = np.zeros((ne, a)), np.zeros((ne, a * 3)), np.zeros((ne, a)), np.zeros((ne, a * 3))
+    assert shim.host_residual_adjoint_elements(PHYS[physics], ELEM[etype], num_gp, 0, C.c_longlong(ne), _p(coords),
+                                               _p(conn), _p(K), _p(u), _p(lam), None, _p(arr), _p(dk), _p(dx)) == 0
+    assert shim.host_residual_adjoint_dual_reference(PHYS[physics], ELEM[etype], num_gp, C.c_longlong(ne), _p(coords),
+                                                     _p(conn), _p(K), _p(u), _p(lam), _p(arr), _p(dk2), _p(dx2)) == 0
+    assert np.abs(dk - dk2).max() <= 1e-12 * np.abs(dk).max() and np.abs(dx - dx2).max() <= 1e-12 * np.abs(dx).max()
 @pytest.mark.parametrize("etype", list(ELEM))
 @pytest.mark.parametrize("num_gp", [1, 2, 3])
 def test_gauss_interpolation_and_response(shim, etype, num_gp):
@@ -93,27 +146,3 @@ def test_gauss_interpolation_and_response(shim, etype, num_gp):
         assert np.abs(got - ref).max() <= 1e-12 * max(np.abs(ref).max(), 1e-300)
 
 
-@pytest.mark.parametrize("physics", ["mechanical", "thermal"])
-@pytest.mark.parametrize("etype", list(ELEM))
-@pytest.mark.parametrize("num_gp", [1, 2, 3])
-def test_residual_adjoint_closed_forms(shim, physics, etype, num_gp):
-    """fe_response.py:312-331, 424-442: lam_e^T d re/d K_e and lam_e^T d re/d x_e -- closed forms of
-    csrc/adjoint.cuh against complex-step differentiation of the oracle's ComputeElement."""
-    coords, conn, d, K, u, lam = _case(etype, physics, seed=3)
-    ne, a = conn.shape
-    dim = 3 if etype in ("hexahedron", "tetra") else 2
-    arr, par = _params(physics, dim)
-    dk, dx = np.full((ne, a), 0.5), np.full((ne, a * 3), -0.25)        # accumulate on top of these
-    assert shim.host_residual_adjoint_elements(0 if physics == "mechanical" else 1, ELEM[etype], num_gp, 1,
-                                               C.c_longlong(ne), _p(coords), _p(conn), _p(K), _p(u), _p(lam),
-                                               _p(arr), _p(dk), _p(dx)) == 0
-    g = assembly.element_dof_ids(conn, d)
-    rK, rX = responses.residual_adjoint_grads(physics, etype, num_gp, coords[conn], K[conn], u[g], lam[g], par)
-    assert np.abs(dk - 0.5 - rK).max() <= 1e-11 * np.abs(rK).max()
-    assert np.abs(dx + 0.25 - rX).max() <= 1e-11 * np.abs(rX).max()
-    # overwrite mode, one output only
-    dk2 = np.full((ne, a), 9.0)
-    assert shim.host_residual_adjoint_elements(0 if physics == "mechanical" else 1, ELEM[etype], num_gp, 0,
-                                               C.c_longlong(ne), _p(coords), _p(conn), _p(K), _p(u), _p(lam),
-                                               _p(arr), _p(dk2), None) == 0
-    assert np.abs(dk2 - rK).max() <= 1e-11 * np.abs(rK).max()

@@ -42,10 +42,10 @@ class _FakeLib:
         return self.shim.host_response_elements(element, num_gp, d, C.c_longlong(ne),
                                                 *map(C.c_void_p, (xyz, conn, f, fk, fu, val, du, dk, dx)))
 
-    def fol_residual_adjoint_elements(self, s, dt, physics, element, num_gp, acc, ne, xyz, conn, ctrl, u, lam, params,
-                                      dk, dx):
+    def fol_residual_adjoint_elements(self, s, dt, physics, element, num_gp, acc, ne, xyz, conn, ctrl, u, lam, aux,
+                                      params, dk, dx):
         return self.shim.host_residual_adjoint_elements(physics, element, num_gp, acc, C.c_longlong(ne),
-                                                        *map(C.c_void_p, (xyz, conn, ctrl, u, lam)), params,
+                                                        *map(C.c_void_p, (xyz, conn, ctrl, u, lam, aux)), params,
                                                         C.c_void_p(dk), C.c_void_p(dx))
 
     def fol_residual_gather(self, s, dt, nn, nnode, width, adj_ptr, adj, elem, out):

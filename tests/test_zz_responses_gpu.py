@@ -107,10 +107,68 @@ def test_against_oracle(physics, etype, num_gp, dtype, tol):
     assert np.array_equal(sd, resp.ComputeAdjointNodalShapeDerivatives(K, u, lam).cpu().numpy())
 
 
-def test_unsupported_physics_raises():
+EXTRA = [("neohooke", "quad", 2), ("neohooke", "tetra", 1), ("neohooke", "hexahedron", 2), ("stvenant", "triangle", 1),
+         ("stvenant", "hexahedron", 2), ("transient_thermal", "quad", 2), ("transient_thermal", "tetra", 1),
+         ("allen_cahn", "quad", 2), ("allen_cahn", "hexahedron", 2)]
+
+
+@pytest.mark.parametrize("physics,etype,num_gp", EXTRA)
+def test_forward_mode_physics_against_oracle(physics, etype, num_gp):
+    """Residual sensitivities of the finite-strain and implicit-Euler scalar losses (forward-mode sweeps in
+    csrc/adjoint.cuh) + the response part, float64, against the complex-step oracle."""
+    from folax_b200 import loss_functions as lf
+    mesh = gh.make_mesh(etype, 3, perturb=0.2, seed=5)
+    rng = np.random.default_rng(13)
+    nn = mesh.GetNumberOfNodes()
+    coords, conn = np.asarray(mesh.GetNodesCoordinates()), mesh.GetElementsNodes(etype)
+    if physics in ("neohooke", "stvenant"):
+        loss = gh.make_loss(physics, etype, mesh, num_gp=num_gp, extra={"body_foce": [0.2, -0.4, 0.7][:3 if etype in ("hexahedron", "tetra") else 2]})
+        par = gh.oracle_params(loss)
+        K, u = gh.fields(physics, mesh, loss, seed=3)
+        name = "U"
+    elif physics == "transient_thermal":
+        cls = {"quad": lf.TransientThermalLoss2DQuad, "tetra": lf.TransientThermalLoss3DTetra}[etype]
+        k0 = rng.uniform(0.5, 1.5, nn)
+        loss = cls("tt", {"dirichlet_bc_dict": {"T": {"left": 1.0, "right": 0.1}}, "c": 3, "num_gp": num_gp,
+                          "material_dict": {"rho": 1.3, "cp": 0.7, "beta": 1.5, "k0": k0},
+                          "time_integration_dict": {"time_step": 0.01}}, mesh)
+        loss.Initialize()
+        par = {"rho": 1.3, "cp": 0.7, "beta": 1.5, "c": 3, "k0": k0, "time_step": 0.01}
+        K, u = rng.uniform(0.2, 1.0, nn), rng.uniform(0.2, 1.0, nn)      # (current, next) temperatures
+        name = "T"
+    else:
+        cls = {"quad": lf.AllenCahnLoss2DQuad, "hexahedron": lf.AllenCahnLoss3DHexa}[etype]
+        loss = cls("ac", {"dirichlet_bc_dict": {"Phi": {"left": 1.0}}, "num_gp": num_gp,
+                          "material_dict": {"rho": 1.0, "cp": 1.0, "dt": 0.002, "epsilon": 0.3}}, mesh)
+        loss.Initialize()
+        par = {"dt": 0.002, "epsilon": 0.3}
+        K, u = rng.uniform(-1.0, 1.0, nn), rng.uniform(-1.0, 1.0, nn)    # (current, next) phase field
+        name = "P"
+    assert loss.num_gp == num_gp
+    lam = rng.standard_normal(loss.total_number_of_dofs)
+    formula = f"jnp.cos(K)*{name}[0]**2 + K*{name}[-1]"
+    resp = FiniteElementResponse("r", formula, loss, NodalControl("K", mesh))
+    resp.Initialize()
+    f = responses.response_function(formula, "K", loss.dofs[0])
+    ref_cd = responses.control_derivatives(f, physics, etype, num_gp, coords, conn, K, u, lam, par)
+    ref_sd = responses.shape_derivatives(f, physics, etype, num_gp, coords, conn, K, u, lam, par)
+    cd = resp.ComputeAdjointNodalControlDerivatives(K, u, lam).cpu().numpy()
+    sd = resp.ComputeAdjointNodalShapeDerivatives(K, u, lam).cpu().numpy()
+    assert np.abs(cd - ref_cd).max() <= 1e-11 * np.abs(ref_cd).max()
+    assert np.abs(sd - ref_sd).max() <= 1e-11 * np.abs(ref_sd).max()
+    _, _, ref_rhs = responses.adjoint_jacobian_and_rhs(f, physics, etype, num_gp, coords, conn, K, u,
+                                                       loss.dirichlet_indices, par)
+    _, rhs = resp.ComputeAdjointJacobianMatrixAndRHSVector(K, u)
+    assert np.abs(rhs.cpu().numpy() - ref_rhs).max() <= 1e-11 * np.abs(ref_rhs).max()
+
+
+def test_history_dependent_loss_raises():
     from folax_b200 import _lib
+    from folax_b200.loss_functions import ElastoplasticityLoss2DQuad
     mesh = gh.make_mesh("quad", 3)
-    loss = gh.make_loss("neohooke", "quad", mesh, num_gp=2)
+    loss = ElastoplasticityLoss2DQuad("ep", {"dirichlet_bc_dict": BC, "material_dict": {
+        "young_modulus": 3.0, "poisson_ratio": 0.3, "iso_hardening_parameter_1": 0.4, "iso_hardening_param_2": 10.0,
+        "yield_limit": 0.2}}, mesh)
     resp = FiniteElementResponse("r", "K*U[0]", loss, NodalControl("K", mesh))
     resp.Initialize()
     nn, ndof = mesh.GetNumberOfNodes(), loss.total_number_of_dofs
