@@ -54,6 +54,11 @@ SIGNATURES = {
     "fol_residual_adjoint_elements": (_int, [_vp, _int, _int, _int, _int, _int, _i64, _vp, _i32p, _vp, _vp, _vp, _vp,
                                              C.POINTER(_dbl), _vp, _vp]),
     "fol_sum": (_int, [_vp, _int, _i64, _vp, _vp]),
+    "fol_gather_values": (_int, [_vp, _int, _i64, _i32p, _vp, _vp]),
+    "fol_sell_spmv": (_int, [_vp, _int, _i64, _vp, _i32p, _vp, _vp, _vp]),
+    "fol_vec_op": (_int, [_vp, _int, _int, _i64, _dbl, _vp, _dbl, _vp, _vp]),
+    "fol_dot_work_size": (_i64, []),
+    "fol_dot": (_int, [_vp, _int, _i64, _vp, _vp, _vp, _vp]),
     "fol_plan_create": (_int, [C.POINTER(_vp), _int, _int, _int, _int, _i64, _i64, _vp, _i32p, _i32p, _i64,
                                C.POINTER(_dbl)]),
     "fol_plan_destroy": (None, [_vp]),

@@ -1,0 +1,57 @@
+// Per-thread bodies of the linear-algebra kernels behind folax_b200/solvers (krylov.cu): sparse matrix-vector
+// product on the sliced-ELLPACK copy of the duplicate-free CSR, value gather, vector updates.
+// __host__ __device__ so that tests/host_shim can loop them on the CPU (same approach as adjoint_threads.cuh).
+//
+// Layout (built once per mesh by folax_b200/sell_plan.py from the CSR structure of csr_plan.py): rows are cut into
+// slices of 32 consecutive rows; a slice of width w (its longest row) owns w*32 entries starting at
+// slice_ptr[s], stored COLUMN-major: entry k of row r sits at slice_ptr[r/32] + k*32 + r%32.  One thread per row
+// then reads 32 consecutive values / column indices per step -- coalesced without any cross-lane reduction, and
+// the per-row sum runs in the fixed CSR order, so products are deterministic.  FE rows have near-uniform length
+// (81 entries for interior Hex8 elasticity dofs), so the padding (value 0, column 0) is a few per cent.
+#pragma once
+#include "common.cuh"
+
+namespace fol {
+
+template <class T>
+struct SellArgs {
+  const long long* slice_ptr;   // (nslices + 1), in entries
+  const int32_t* cols;          // padded entries: column 0
+  const T* vals;                // padded entries: 0
+  const T* x;
+  T* y;
+  long long nrows;
+};
+
+template <class T>
+__host__ __device__ inline void sell_spmv_thread(long long row, const SellArgs<T>& a) {
+  const long long s = row >> 5;
+  const int lane = (int)(row & 31);
+  const long long base = a.slice_ptr[s];
+  const int width = (int)((a.slice_ptr[s + 1] - base) >> 5);
+  T acc = (T)0;
+  for (int k = 0; k < width; ++k) {
+    const long long idx = base + (long long)k * 32 + lane;
+    acc += a.vals[idx] * a.x[a.cols[idx]];
+  }
+  a.y[row] = acc;
+}
+
+// dst[i] = src_index[i] >= 0 ? src[src_index[i]] : 0   (CSR values -> SELL values; CSR values -> diagonal)
+template <class T>
+__host__ __device__ inline void gather_values_thread(long long i, const int32_t* src_index, const T* src, T* dst) {
+  const int32_t k = src_index[i];
+  dst[i] = k >= 0 ? src[k] : (T)0;
+}
+
+enum : int { VEC_AXPBY = 0, VEC_AXY = 1, VEC_AX_OVER_Y = 2 };
+
+// op 0: out = a x + b y (y may be null when b == 0);  op 1: out = a x * y;  op 2: out = a x / y
+template <class T>
+__host__ __device__ inline void vec_op_thread(long long i, int op, T a, const T* x, T b, const T* y, T* out) {
+  if (op == VEC_AXPBY) out[i] = y ? a * x[i] + b * y[i] : a * x[i];
+  else if (op == VEC_AXY) out[i] = a * x[i] * y[i];
+  else out[i] = a * x[i] / y[i];
+}
+
+}  // namespace fol

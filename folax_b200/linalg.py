@@ -1,0 +1,157 @@
+"""Device-resident sparse operator and BiCGSTAB: the GPU side of fol/solvers/fe_solver.py:60-103.
+
+The reference converts the duplicate-keeping BCOO to a SciPy CSR on the host (fe_solver.py:71-72) or hands it to
+`jax.scipy.sparse.linalg.bicgstab` (:62-67).  Here the Jacobian never leaves the device: `fol_csr_values` sums the
+duplicates in a fixed order, `fol_gather_values` permutes the values into the sliced-ELLPACK layout, and the Krylov
+iteration runs on `fol_sell_spmv` / `fol_vec_op` / `fol_dot` (csrc/krylov.cu).  PyTorch only owns the vectors.
+The host reads five scalars per iteration (the BiCGSTAB coefficients); everything else stays on the stream.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class SellOperator:
+    """y = J x for a Jacobian returned by `ComputeJacobianMatrixAndResidualVector` (duplicates summed)."""
+
+    def __init__(self, loss, jacobian):
+        self.loss = loss
+        lib = _lib.load()
+        self.indptr, self.indices, self.csr_values = loss.JacobianToCSR(jacobian)
+        sp = loss._sell_plan()
+        self.plan = sp
+        self.n = sp["nrows"]
+        self.values = torch.empty(max(sp["total"], 1), dtype=loss.dtype, device=loss.device)
+        _lib.check(lib.fol_gather_values(_lib.stream_ptr(), loss._dt, sp["total"], _lib.ptr(sp["src"]),
+                                         _lib.ptr(self.csr_values), _lib.ptr(self.values)))
+
+    def matvec(self, x, out=None):
+        L = self.loss
+        if out is None:
+            out = torch.empty_like(x)
+        _lib.check(_lib.load().fol_sell_spmv(_lib.stream_ptr(), L._dt, self.n, _lib.ptr(self.plan["slice_ptr"]),
+                                             _lib.ptr(self.plan["cols"]), _lib.ptr(self.values), _lib.ptr(x),
+                                             _lib.ptr(out)))
+        return out
+
+    def diagonal(self):
+        L = self.loss
+        d = torch.empty(max(self.n, 1), dtype=L.dtype, device=L.device)
+        _lib.check(_lib.load().fol_gather_values(_lib.stream_ptr(), L._dt, self.n, _lib.ptr(self.plan["diag_src"]),
+                                                 _lib.ptr(self.csr_values), _lib.ptr(d)))
+        return d
+
+    def to_scipy_csr(self):
+        import scipy.sparse as sp
+        return sp.csr_array((self.csr_values.cpu().numpy(), self.indices.cpu().numpy(), self.indptr.cpu().numpy()),
+                            shape=(self.n, self.n))
+
+
+class _Vectors:
+    """Vector updates and dot products of one solve, through the C ABI."""
+
+    def __init__(self, dt, n, dtype, device):
+        self.lib, self.dt, self.n = _lib.load(), dt, n
+        self.work = torch.empty(int(self.lib.fol_dot_work_size()), dtype=dtype, device=device)
+        self.slots = torch.zeros(4, dtype=dtype, device=device)
+
+    def axpby(self, a, x, b, y, out):
+        _lib.check(self.lib.fol_vec_op(_lib.stream_ptr(), self.dt, 0, self.n, float(a), _lib.ptr(x), float(b),
+                                       _lib.ptr(y) if y is not None else None, _lib.ptr(out)))
+        return out
+
+    def divide(self, x, y, out):
+        _lib.check(self.lib.fol_vec_op(_lib.stream_ptr(), self.dt, 2, self.n, 1.0, _lib.ptr(x), 0.0, _lib.ptr(y),
+                                       _lib.ptr(out)))
+        return out
+
+    def dot_into(self, x, y, slot):
+        _lib.check(self.lib.fol_dot(_lib.stream_ptr(), self.dt, self.n, _lib.ptr(x), _lib.ptr(y), _lib.ptr(self.work),
+                                    self.slots.data_ptr() + slot * self.slots.element_size()))
+
+    def read(self, count=1):
+        vals = self.slots[:count].tolist()             # one device -> host read for `count` scalars
+        return vals[0] if count == 1 else vals
+
+    def dot(self, x, y):
+        self.dot_into(x, y, 0)
+        return self.read()
+
+
+def norm(loss, x):
+    v = _Vectors(loss._dt, x.numel(), loss.dtype, loss.device)
+    return math.sqrt(max(v.dot(x, x), 0.0))
+
+
+def bicgstab(A, b, x0=None, tol=1e-5, atol=0.0, maxiter=None, M_diagonal=None):
+    """BiCGSTAB with the recurrences, start (rho = alpha = omega = 1, p = q = 0), stopping rule
+    (|r|^2 <= max(tol^2 |b|^2, atol^2), also tested on the half step) and break-down codes of
+    `jax.scipy.sparse.linalg.bicgstab`, which fe_solver.py:62-67 calls (JAX 0.8; restated from its documented
+    algorithm -- the JAX sources are not in the reference tree).  A: SellOperator; b, x0: device vectors;
+    M_diagonal: optional Jacobi preconditioner (the diagonal; the reference passes no preconditioner).
+    Returns (x, info): info = number of iterations, or -10 / -11 on a rho / (alpha, omega) break-down."""
+    L = A.loss
+    n = b.numel()
+    v = _Vectors(L._dt, n, L.dtype, L.device)
+    if maxiter is None:
+        maxiter = 10 * n
+    new = lambda: torch.empty_like(b)
+    x = b.new_zeros(n) if x0 is None else _lib.to_device(x0, L.dtype).reshape(-1).clone()
+    q, r = A.matvec(x), new()
+    v.axpby(1.0, b, -1.0, q, r)                        # r0 = b - A x0
+    rhat = r.clone()
+    p, phat, s, shat, t, tmp = b.new_zeros(n), new(), new(), new(), new(), new()
+    q.zero_()
+    v.dot_into(b, b, 0)
+    v.dot_into(r, r, 1)
+    bb, rs = v.read(2)
+    atol2 = max(tol * tol * bb, atol * atol)
+    rho = alpha = omega = 1.0
+    k = 0
+    while rs > atol2 and 0 <= k < maxiter:
+        rho_new = v.dot(rhat, r)
+        if rho_new == 0.0:
+            k = -10
+            break
+        beta = rho_new / rho * alpha / omega
+        v.axpby(1.0, p, -omega, q, tmp)                # p = r + beta (p - omega q)
+        v.axpby(1.0, r, beta, tmp, p)
+        if M_diagonal is not None:
+            v.divide(p, M_diagonal, phat)
+        else:
+            phat = p
+        A.matvec(phat, q)
+        rq = v.dot(rhat, q)
+        if rq == 0.0:
+            k = -11
+            break
+        alpha = rho_new / rq
+        v.axpby(1.0, r, -alpha, q, s)
+        ss = v.dot(s, s)
+        if ss < atol2:                                  # converged on the half step
+            v.axpby(1.0, x, alpha, phat, x)
+            r, s = s, r
+            rs, rho, k = ss, rho_new, k + 1
+            continue
+        if M_diagonal is not None:
+            v.divide(s, M_diagonal, shat)
+        else:
+            shat = s
+        A.matvec(shat, t)
+        v.dot_into(t, s, 0)
+        v.dot_into(t, t, 1)
+        ts, tt = v.read(2)
+        omega = ts / tt if tt != 0.0 else 0.0
+        v.axpby(1.0, x, alpha, phat, x)
+        v.axpby(1.0, x, omega, shat, x)
+        v.axpby(1.0, s, -omega, t, r)
+        rs = v.dot(r, r)
+        rho = rho_new
+        if omega == 0.0 or alpha == 0.0:
+            k = -11
+            break
+        k += 1
+    return x, k

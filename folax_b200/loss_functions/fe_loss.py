@@ -326,6 +326,16 @@ class FiniteElementLoss(Loss):
                            for k, v in plan.items()}
         return self._cplan
 
+    def _sell_plan(self):
+        """Device-resident sliced-ELLPACK plan of the duplicate-free CSR (sell_plan.py), for the Krylov solvers."""
+        if self.__dict__.get("_splan") is None:
+            from .. import sell_plan
+            cp = self._csr_plan()
+            plan = sell_plan.build(cp["indptr"].cpu().numpy(), cp["indices"].cpu().numpy())
+            self._splan = {k: (torch.as_tensor(v, device=self.device) if isinstance(v, np.ndarray) else v)
+                           for k, v in plan.items()}
+        return self._splan
+
     def JacobianToCSR(self, jacobian):
         """Duplicate-free CSR (indptr, indices, values) of a Jacobian returned by
         ComputeJacobianMatrixAndResidualVector -- the sum the reference's solvers do on the host with

@@ -1,0 +1,76 @@
+"""FiniteElementSolver: linear-solver selection of fol/solvers/fe_solver.py:22-103 on the device-resident Jacobian.
+
+  "JAX-bicgstab"  (default)  BiCGSTAB on the GPU (folax_b200/linalg.py: SELL SpMV + vector kernels), same arguments
+                             as the reference's call `bicgstab(A, -r, x0=dofs, tol, atol, maxiter)` (:62-67)
+  "JAX-direct"               sparse direct solve: the duplicate-free CSR is BUILT on the GPU and factorised by SciPy
+                             on the host -- the reference's spsolve path is a host factorisation as well (:70-80);
+                             what changes is that 1/2.4 of the bytes cross PCIe (no duplicates) and no host sort
+  "PETSc-*"                  petsc4py is not in this image: falls back to BiCGSTAB with a warning, as :47-49 does
+
+Extra setting (not in the reference): "pre-conditioner": "jacobi" applies the diagonal to BiCGSTAB.
+"""
+import numpy as np
+import torch
+
+from .. import _lib, linalg
+from ..tools import fol_error, fol_info
+from .solver import Solver
+
+
+class FiniteElementSolver(Solver):
+    def __init__(self, fe_solver_name: str, fe_loss_function, fe_solver_settings: dict = {}) -> None:
+        super().__init__(fe_solver_name)
+        self.fe_loss_function = fe_loss_function
+        self.fe_solver_settings = fe_solver_settings
+        self.linear_solver_settings = {"solver": "JAX-bicgstab", "tol": 1e-6, "atol": 1e-6, "maxiter": 1000,
+                                       "pre-conditioner": "ilu"}
+        self.last_linear_solve_info = None
+
+    def Initialize(self) -> None:
+        if "linear_solver_settings" in self.fe_solver_settings.keys():
+            self.linear_solver_settings = {**self.linear_solver_settings,
+                                           **self.fe_solver_settings["linear_solver_settings"]}
+        linear_solver = self.linear_solver_settings["solver"]
+        available_linear_solver = ["PETSc-bcgsl", "PETSc-tfqmr", "PETSc-minres", "PETSc-gmres", "JAX-direct",
+                                   "JAX-bicgstab"]
+        if linear_solver == "JAX-direct":
+            self.LinearSolve = self.JaxDirectLinearSolver
+        elif linear_solver == "JAX-bicgstab":
+            self.LinearSolve = self.JaxBicgstabLinearSolver
+        elif linear_solver in available_linear_solver:
+            fol_info("petsc4py is not available, falling back to the default iterative solver: JAX-bicgstab ")
+            self.LinearSolve = self.JaxBicgstabLinearSolver
+        else:
+            fol_error(f"linear solver {linear_solver} does exist, available options are {available_linear_solver}")
+
+    # names kept from the reference so that subclasses / callers that pick a method by name keep working
+    def JaxBicgstabLinearSolver(self, tangent_matrix, residual_vector, dofs_vector):
+        L = self.fe_loss_function
+        A = linalg.SellOperator(L, tangent_matrix)
+        r = _lib.to_device(residual_vector, L.dtype).reshape(-1)
+        rhs = torch.empty_like(r)
+        _lib.check(_lib.load().fol_vec_op(_lib.stream_ptr(), L._dt, 0, r.numel(), -1.0, _lib.ptr(r), 0.0, None,
+                                          _lib.ptr(rhs)))
+        s = self.linear_solver_settings
+        diag = A.diagonal() if str(s.get("pre-conditioner", "")).lower() == "jacobi" else None
+        x, info = linalg.bicgstab(A, rhs, x0=dofs_vector, tol=s["tol"], atol=s["atol"], maxiter=s["maxiter"],
+                                  M_diagonal=diag)
+        self.last_linear_solve_info = info
+        return x
+
+    def JaxDirectLinearSolver(self, tangent_matrix, residual_vector, dofs_vector):
+        import scipy.sparse.linalg as spla
+        L = self.fe_loss_function
+        A = linalg.SellOperator.__new__(linalg.SellOperator)           # CSR only: no SELL copy for a host solve
+        A.loss, A.n = L, L.total_number_of_dofs
+        A.indptr, A.indices, A.csr_values = L.JacobianToCSR(tangent_matrix)
+        r = _lib.to_device(residual_vector, L.dtype).reshape(-1)
+        delta = spla.spsolve(A.to_scipy_csr().tocsc(), -r.cpu().numpy().astype(np.float64))
+        self.last_linear_solve_info = 0
+        return _lib.to_device(delta, L.dtype)
+
+    def Solve(self, current_control_vars, current_dofs):
+        raise NotImplementedError
+
+    def Finalize(self) -> None:
+        pass

@@ -229,6 +229,25 @@ int fol_residual_adjoint_elements(fol_stream_t s, int dtype, int physics, int el
 /* out[0] = sum of x[0..n) in a fixed order (one block): ComputeValue's jnp.sum, fe_response.py:216 */
 int fol_sum(fol_stream_t s, int dtype, int64_t n, const void* x, void* out);
 
+/* ---- device-resident linear algebra for fol/solvers (fe_solver.py:60-103) -----
+ * The reference ships the BCOO to the host and lets SciPy / jax.scipy solve; with the Jacobian assembled and
+ * de-duplicated on the device (fol_csr_values) the Krylov iteration can stay there.  Matrix layout: sliced
+ * ELLPACK built once per mesh by the host from the CSR structure (folax_b200/sell_plan.py): slices of 32 rows,
+ * entry k of row r at slice_ptr[r/32] + k*32 + r%32; padded entries have value 0 and column 0. */
+
+/* dst[i] = src_index[i] >= 0 ? src[src_index[i]] : 0  (CSR values -> SELL values, CSR values -> diagonal) */
+int fol_gather_values(fol_stream_t s, int dtype, int64_t n, const int32_t* src_index, const void* src, void* dst);
+/* y = A x, one thread per row, per-row sums in CSR order (deterministic); x and y must not alias */
+int fol_sell_spmv(fol_stream_t s, int dtype, int64_t nrows, const int64_t* slice_ptr, const int32_t* cols,
+                  const void* vals, const void* x, void* y);
+/* op 0: out = a x + b y (y may be NULL when b == 0)   op 1: out = a x*y   op 2: out = a x/y;  out may alias x or y */
+int fol_vec_op(fol_stream_t s, int dtype, int op, int64_t n, double a, const void* x, double b, const void* y,
+               void* out);
+/* out[0] = x . y on the device (fixed two-stage reduction tree: run-to-run identical); `work` needs
+ * fol_dot_work_size() elements of the call's dtype */
+int64_t fol_dot_work_size(void);
+int fol_dot(fol_stream_t s, int dtype, int64_t n, const void* x, const void* y, void* work, void* out);
+
 /* ---- host-buffer entry point (what a non-GPU caller binds; used for the e2e measurement) -- */
 
 typedef struct fol_plan fol_plan;

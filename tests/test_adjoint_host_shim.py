@@ -7,7 +7,6 @@ differentiation route -- on every element type and integration order.  The GPU r
 tests/test_zz_responses_gpu.py."""
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -22,15 +21,7 @@ NGP = {("hexahedron", 1): 1, ("hexahedron", 2): 8, ("hexahedron", 3): 27, ("quad
        ("triangle", 2): 3, ("triangle", 3): 4}
 
 
-@pytest.fixture(scope="module")
-def shim(tmp_path_factory):
-    out = str(tmp_path_factory.mktemp("shim") / "libadjoint_host.so")
-    src = os.path.join(ROOT, "tests", "host_shim", "adjoint_host.cu")
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    r = subprocess.run([nvcc, "-O2", "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets",
-                        "-shared", "-Xcompiler", "-fPIC", src, "-o", out], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
-    return C.CDLL(out)
+from tests.cpu_backend import shim  # noqa: E402,F401  (session fixture: the compiled host shim)
 
 
 def _p(a):

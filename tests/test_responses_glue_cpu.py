@@ -19,88 +19,18 @@ from folax_b200 import _lib
 from folax_b200.responses import FiniteElementResponse, NodalControl
 from folax_b200.sparse import BCOO
 from oracle import assembly
-from tests.test_adjoint_host_shim import shim  # noqa: F401  (fixture)
+from tests.cpu_backend import cpu_backend, fake_loss, shim  # noqa: F401  (fixtures)
 from tests.test_oracle_golden import _square_mesh
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _arr(ptr, n, ctype=C.c_double):
-    return np.ctypeslib.as_array((ctype * n).from_address(ptr)) if n else np.zeros(0)
-
-
-class _FakeLib:
-    """fol_* entry points used by FiniteElementResponse, on host pointers (float64 only)."""
-
-    def __init__(self, shim_lib, ne, nnode):
-        self.shim, self.ne, self.nnode = shim_lib, ne, nnode
-
-    def fol_gauss_interpolate(self, s, dt, element, num_gp, d, ne, conn, ctrl, u, kg, ug):
-        return self.shim.host_gauss_interpolate(element, num_gp, d, C.c_longlong(ne), *map(C.c_void_p, (conn, ctrl, u, kg, ug)))
-
-    def fol_response_elements(self, s, dt, element, num_gp, d, ne, xyz, conn, f, fk, fu, val, du, dk, dx):
-        return self.shim.host_response_elements(element, num_gp, d, C.c_longlong(ne),
-                                                *map(C.c_void_p, (xyz, conn, f, fk, fu, val, du, dk, dx)))
-
-    def fol_residual_adjoint_elements(self, s, dt, physics, element, num_gp, acc, ne, xyz, conn, ctrl, u, lam, aux,
-                                      params, dk, dx):
-        return self.shim.host_residual_adjoint_elements(physics, element, num_gp, acc, C.c_longlong(ne),
-                                                        *map(C.c_void_p, (xyz, conn, ctrl, u, lam, aux)), params,
-                                                        C.c_void_p(dk), C.c_void_p(dx))
-
-    def fol_residual_gather(self, s, dt, nn, nnode, width, adj_ptr, adj, elem, out):
-        ap, ad = _arr(adj_ptr, nn + 1, C.c_int32), _arr(adj, self.ne * nnode, C.c_int32)
-        ev, o = _arr(elem, self.ne * nnode * width), _arr(out, nn * width)
-        for n in range(nn):
-            for k in range(width):
-                o[n * width + k] = sum(ev[int(x) * width + k] for x in ad[ap[n]:ap[n + 1]])
-        return 0
-
-    def fol_sum(self, s, dt, n, x, out):
-        _arr(out, 1)[0] = _arr(x, n).sum()
-        return 0
-
-
-def _fake_loss(N, K_unused=None):
+def _fake_loss(N):
     coords, conn, sets = _square_mesh(N)
     bc = {"Ux": {"left": 0.0, "right": 0.05}, "Uy": {"left": 0.0, "right": 0.05}}
-    didx, dval = assembly.dirichlet_vectors(["Ux", "Uy"], bc, sets)
     params = {"young_modulus": 1.0, "poisson_ratio": 0.3}
-    ne, nn = conn.shape[0], coords.shape[0]
-    order = np.argsort(conn.reshape(-1), kind="stable")            # entries e*a + local, ascending per node
-    counts = np.bincount(conn.reshape(-1), minlength=nn)
-    L = types.SimpleNamespace(
-        physics="mechanical", dofs=["Ux", "Uy"], dtype=torch.float64, device=torch.device("cpu"), _dt=_lib.F64,
-        _ne=ne, _nn=nn, _nnode=4, _ngauss=4, num_gp=2, number_dofs_per_node=2, total_number_of_dofs=2 * nn, dim=2,
-        fe_element=types.SimpleNamespace(code=_lib.ELEMENTS["quad"]),
-        fe_mesh=types.SimpleNamespace(GetNumberOfNodes=lambda: nn),
-        _xyz=torch.as_tensor(coords), _conn=torch.as_tensor(conn),
-        _adj_ptr=torch.as_tensor(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)),
-        _adj=torch.as_tensor(order.astype(np.int32)), _dir_idx=torch.as_tensor(didx.astype(np.int32)),
-        _params=_lib.params_array([1.0, 0.3] + [0.0] * 10), Initialize=lambda reinitialize=False: None,
-        dirichlet_indices=didx, dirichlet_values=dval)
-
-    def jac_and_res(ctrl, u, transpose=False):
-        data, idx, R = assembly.assemble("mechanical", "quad", 2, coords, conn, ctrl.numpy(), u.numpy(), didx, params,
-                                         transpose=transpose)
-        return BCOO((torch.as_tensor(data), torch.as_tensor(idx)), shape=(2 * nn, 2 * nn)), torch.as_tensor(R)
-
-    L.ComputeJacobianMatrixAndResidualVector = jac_and_res
-    return L, coords, conn, didx, dval, params
-
-
-@pytest.fixture()
-def cpu_backend(monkeypatch, shim):  # noqa: F811
-    def install(loss):
-        fake = _FakeLib(shim, loss._ne, loss._nnode)
-        monkeypatch.setattr(_lib, "load", lambda: fake)
-        monkeypatch.setattr(_lib, "check", lambda rc: (_ for _ in ()).throw(RuntimeError(rc)) if rc else None)
-        monkeypatch.setattr(_lib, "stream_ptr", lambda: 0)
-        monkeypatch.setattr(_lib, "ptr", lambda t: None if t is None else t.data_ptr())
-        monkeypatch.setattr(_lib, "to_device",
-                            lambda x, dtype, device=None: torch.as_tensor(np.asarray(x)).to(dtype).contiguous()
-                            if not isinstance(x, torch.Tensor) else x.to(dtype).contiguous())
-    return install
+    L = fake_loss("mechanical", "quad", 2, coords, conn, sets, ["Ux", "Uy"], bc, params, [1.0, 0.3] + [0.0] * 10)
+    return L, coords, conn, L.dirichlet_indices, L.dirichlet_values, params
 
 
 @pytest.fixture(scope="module")

@@ -1,0 +1,160 @@
+"""CPU check of folax_b200.solvers / folax_b200.linalg (the API of fol/solvers on the device-resident Jacobian).
+
+No GPU here: the C ABI is the stand-in of tests/cpu_backend.py -- the SpMV, gather and vector kernels run as their
+own per-thread code compiled for the CPU (tests/host_shim/krylov_host.cu), the loss is backed by the oracle.  What
+is exercised for real: the sliced-ELLPACK plan, BiCGSTAB, the Newton / load-step logic, the adjoint solve, against
+SciPy and against the reference's integration golden (tests/integration/test_mechanical_2D_sa.py:81-113).
+GPU runs of the same classes: tests/test_zz_solvers_gpu.py."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+import torch
+
+import folax_b200
+from folax_b200 import linalg, sell_plan
+from folax_b200.responses import FiniteElementResponse, NodalControl
+from folax_b200.solvers import (AdjointFiniteElementSolver, FiniteElementLinearResidualBasedSolver,
+                                FiniteElementNonLinearResidualBasedSolver)
+from oracle import assembly
+from tests.cpu_backend import cpu_backend, fake_loss, shim  # noqa: F401  (fixtures)
+from tests.test_oracle_golden import _square_mesh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BC = {"Ux": {"left": 0.0, "right": 0.05}, "Uy": {"left": 0.0, "right": 0.05}}
+MAT = {"young_modulus": 1.0, "poisson_ratio": 0.3}
+
+
+def _mech_loss(N):
+    coords, conn, sets = _square_mesh(N)
+    return fake_loss("mechanical", "quad", 2, coords, conn, sets, ["Ux", "Uy"], BC, MAT, [1.0, 0.3] + [0.0] * 10)
+
+
+def test_sell_plan_and_spmv_on_a_fe_matrix(shim):  # noqa: F811
+    """Sliced-ELLPACK product (the kernel's per-thread code) == SciPy CSR product, on a 3-D hex elasticity matrix
+    whose row lengths vary (corner / edge / face / interior dofs) and whose row count is not a multiple of 32."""
+    mesh = folax_b200.create_3D_box_mesh(3, 4, 2, 1.0, 1.0, 1.0)
+    coords, conn = np.asarray(mesh.GetNodesCoordinates()), mesh.GetElementsNodes("hexahedron")
+    rng = np.random.default_rng(0)
+    nn = len(coords)
+    didx, _ = assembly.dirichlet_vectors(["Ux", "Uy", "Uz"], {d: {"left": 0.0, "right": 0.1} for d in ("Ux", "Uy", "Uz")},
+                                         mesh.node_sets)
+    data, idx, _ = assembly.assemble("mechanical", "hexahedron", 2, coords, conn, rng.uniform(0.1, 1, nn),
+                                     np.zeros(3 * nn), didx, MAT)
+    A = sp.csr_array((data, (idx[:, 0], idx[:, 1])), shape=(3 * nn, 3 * nn))
+    A.sum_duplicates()
+    A.sort_indices()
+    assert A.shape[0] % 32 != 0
+    plan = sell_plan.build(A.indptr, A.indices)
+    assert plan["total"] >= A.nnz and plan["total"] <= 1.5 * A.nnz          # little padding on FE matrices
+    vals = np.zeros(plan["total"])
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert shim.host_gather_values(C.c_longlong(plan["total"]), p(plan["src"]), p(A.data), p(vals)) == 0
+    x, y = rng.standard_normal(3 * nn), np.full(3 * nn, np.nan)
+    assert shim.host_sell_spmv(C.c_longlong(plan["nrows"]), p(plan["slice_ptr"]), p(plan["cols"]), p(vals), p(x), p(y)) == 0
+    ref = A @ x
+    assert np.abs(y - ref).max() <= 1e-13 * np.abs(ref).max()
+    diag = np.zeros(3 * nn)
+    assert shim.host_gather_values(C.c_longlong(3 * nn), p(plan["diag_src"]), p(A.data), p(diag)) == 0
+    assert np.array_equal(diag, A.diagonal())
+
+
+@pytest.mark.parametrize("precond", [None, "jacobi"])
+def test_bicgstab_matches_direct_solve(cpu_backend, precond):  # noqa: F811
+    L = _mech_loss(9)
+    fake = cpu_backend(L)
+    rng = np.random.default_rng(1)
+    K = rng.uniform(0.2, 1.0, L._nn)
+    u0 = L.ApplyDirichletBCOnDofVector(np.zeros(L.total_number_of_dofs))
+    jac, R = L.ComputeJacobianMatrixAndResidualVector(K, u0)
+    A = linalg.SellOperator(L, jac)
+    b = -R
+    x, info = linalg.bicgstab(A, b, x0=None, tol=1e-12, atol=0.0, maxiter=2000,
+                              M_diagonal=A.diagonal() if precond else None)
+    ref = spla.spsolve(A.to_scipy_csr().tocsc(), b.numpy())
+    assert info > 0, info
+    assert np.abs(x.numpy() - ref).max() <= 1e-8 * np.abs(ref).max()
+    assert fake.calls["sell_spmv"] == 2 * info + 1 or fake.calls["sell_spmv"] == 2 * info   # 2 products per iteration
+    # the operator itself
+    v = torch.as_tensor(rng.standard_normal(L.total_number_of_dofs))
+    assert np.abs(A.matvec(v).numpy() - A.to_scipy_csr() @ v.numpy()).max() <= 1e-13
+
+
+def test_linear_and_adjoint_solvers_reproduce_the_reference_integration_golden(cpu_backend):  # noqa: F811
+    """tests/integration/test_mechanical_2D_sa.py with its own settings (JAX-direct for both solves)."""
+    with open(os.path.join(ROOT, "tests", "golden", "reference_unit_goldens.json")) as fh:
+        rec = json.load(fh)["tests/integration/test_mechanical_2D_sa.py"]
+    K = np.array(rec["setUp"]["assign"]["random_K"])
+    L = _mech_loss(5)
+    cpu_backend(L)
+    resp = FiniteElementResponse("test_response", "(E**2)*U[0]", L, NodalControl("E", L.fe_mesh))
+    fe_setting = {"linear_solver_settings": {"solver": "JAX-direct", "tol": 1e-6, "atol": 1e-6, "maxiter": 1000,
+                                             "pre-conditioner": "ilu"},
+                  "nonlinear_solver_settings": {"rel_tol": 1e-5, "abs_tol": 1e-5, "maxiter": 10, "load_incr": 5}}
+    linear_fe_solver = FiniteElementLinearResidualBasedSolver("linear_fe_solver", L, fe_setting)
+    adj_fe_solver = AdjointFiniteElementSolver("first_adj_fe_solver", resp, {"linear_solver_settings": {"solver": "JAX-direct"}})
+    resp.Initialize()
+    linear_fe_solver.Initialize()
+    adj_fe_solver.Initialize()
+    ndof = L.total_number_of_dofs
+    FE_UV = linear_fe_solver.Solve(K, np.zeros(ndof))
+    FE_adj_UV = adj_fe_solver.Solve(K, FE_UV, np.ones(ndof))
+    a = rec["test_sensitivites"]["asserts"]
+    np.testing.assert_allclose(resp.ComputeAdjointNodalControlDerivatives(K, FE_UV, FE_adj_UV).numpy(), a[0]["value"],
+                               rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(resp.ComputeAdjointNodalShapeDerivatives(K, FE_UV, FE_adj_UV).numpy(), a[1]["value"],
+                               rtol=1e-5, atol=1e-5)
+    # the same two solves with the device BiCGSTAB (the reference's default linear solver)
+    it = {"linear_solver_settings": {"solver": "JAX-bicgstab", "tol": 1e-12, "atol": 1e-14, "maxiter": 500}}
+    s2 = FiniteElementLinearResidualBasedSolver("it", L, it)
+    a2 = AdjointFiniteElementSolver("it_adj", resp, it)
+    s2.Initialize()
+    a2.Initialize()
+    u_it = s2.Solve(K, np.zeros(ndof))
+    assert s2.last_linear_solve_info > 0
+    assert np.abs(u_it.numpy() - FE_UV.numpy()).max() <= 1e-9 * np.abs(FE_UV.numpy()).max()
+    lam_it = a2.Solve(K, u_it, np.zeros(ndof))
+    assert np.abs(lam_it.numpy() - FE_adj_UV.numpy()).max() <= 1e-8 * np.abs(FE_adj_UV.numpy()).max()
+
+
+def test_newton_solver_follows_the_reference_loop(cpu_backend):  # noqa: F811
+    """fe_nonlinear_residual_based_solver.py:107-170 on a Neo-Hooke quad mesh: same iterates as the loop written
+    out with the oracle and SciPy, including the reference's habit of NOT applying the update of the converged
+    iteration."""
+    coords, conn, sets = _square_mesh(6)
+    bc = {"Ux": {"left": 0.0, "right": 0.3}, "Uy": {"left": 0.0, "right": 0.05}}
+    L = fake_loss("neohooke", "quad", 2, coords, conn, sets, ["Ux", "Uy"], bc, MAT, [1.0, 0.3] + [0.0] * 10)
+    cpu_backend(L)
+    K = np.random.default_rng(2).uniform(0.5, 1.0, L._nn)
+    settings = {"linear_solver_settings": {"solver": "JAX-direct"},
+                "nonlinear_solver_settings": {"rel_tol": 1e-9, "abs_tol": 1e-9, "maxiter": 8, "load_incr": 3}}
+    solver = FiniteElementNonLinearResidualBasedSolver("nl", L, settings)
+    solver.Initialize()
+    ndof = L.total_number_of_dofs
+    u = solver.Solve(K, np.zeros(ndof)).numpy()
+
+    didx, dval = L.dirichlet_indices, L.dirichlet_values
+    ref = np.zeros(ndof)
+    hist = {}
+    for step in range(1, 4):
+        ref[didx] = step / 3 * dval
+        hist[step] = []
+        for i in range(1, 9):
+            data, idx, R = assembly.assemble("neohooke", "quad", 2, coords, conn, K, ref, didx, MAT)
+            A = sp.csr_array((data, (idx[:, 0], idx[:, 1])), shape=(ndof, ndof))
+            du = spla.spsolve(A.tocsc(), -R)
+            rn, dn = np.linalg.norm(R), np.linalg.norm(du)
+            hist[step].append(rn)
+            if rn < 1e-9 or dn < 1e-9 or i == 8:
+                break
+            ref = ref + du
+    assert np.abs(u - ref).max() <= 1e-10 * np.abs(ref).max()
+    for step in range(1, 4):
+        got = solver.convergence_history[step]["res_norm"]
+        assert len(got) == len(hist[step]) and len(got) >= 4
+        assert np.allclose(got, hist[step], rtol=1e-6, atol=1e-13)
+        assert got[-1] < 1e-7                                    # quadratic convergence reached the tolerance
