@@ -63,6 +63,8 @@ class _BatchLossFn(torch.autograd.Function):
                                                float(loss.loss_function_exponent), _lib.ptr(energy),
                                                _lib.ptr(out4), _lib.ptr(scale)))
         ctx.loss, ctx.grads, ctx.scale, ctx.used = loss, (grad_u, grad_k), scale, False
+        ctx.save_for_backward(batch_params, batch_dofs)       # second-order path only (inputs: no copy is made)
+        ctx.fuse_dirichlet = fuse_dirichlet
         ctx.need = (ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         ctx.mark_non_differentiable(energy)
         return out4[0], out4[1], out4[2], out4[3], energy
@@ -78,7 +80,9 @@ class _BatchLossFn(torch.autograd.Function):
             # meta_implicit_parametric_operator_learning.py:95-105).  The cotangents returned below carry no
             # graph, i.e. they are constants of the outer differentiation -- which is what the reference computes
             # only where the element residual sits under stop_gradient.  Anything else must not pass silently.
-            loss._check_second_order(params_need_grad=ctx.needs_input_grad[1])
+            second_order = loss._check_second_order(params_need_grad=ctx.needs_input_grad[1])
+        else:
+            second_order = "constant"
         grad_u, grad_k = ctx.grads
         up = None
         for g in (g_mean, g_mean2):
@@ -93,7 +97,83 @@ class _BatchLossFn(torch.autograd.Function):
                                                1 if ctx.prescaled else 0,
                                                _lib.ptr(loss._dir_flag if ctx.mask_dirichlet else loss._no_flag),
                                                _lib.ptr(grad_u), _lib.ptr(grad_k) if grad_k is not None else None))
+        if second_order == "hessian":
+            # true potential whose tangent stiffness IS the Hessian (Neo-Hooke): hand the cotangents out through a
+            # node that knows their derivatives (K v kernel + nested VJP)
+            batch_params, batch_dofs = ctx.saved_tensors
+            grad_k, grad_u = _SecondOrderFn.apply(loss, batch_params, batch_dofs, up,
+                                                  _Payload(grad_k, grad_u, ctx.mask_dirichlet, ctx.fuse_dirichlet))
         return None, (grad_k if ctx.need[0] else None), (grad_u if ctx.need[1] else None), None, None
+
+
+class _Payload:
+    def __init__(self, grad_k, grad_u, mask_dirichlet, fuse_dirichlet):
+        self.grad_k, self.grad_u = grad_k, grad_u
+        self.mask_dirichlet, self.fuse_dirichlet = mask_dirichlet, fuse_dirichlet
+
+
+class _SecondOrderFn(torch.autograd.Function):
+    """The first-order cotangents of ComputeBatchLoss as differentiable functions of (params, dofs), for losses
+    whose energy is a true potential with Hessian = tangent stiffness (Neo-Hooke, exponent 1):
+        g_u[b] = (up/B) mask (.) F_int(u_b, K_b)          g_K[b] = (up/B) dE/dK(u_b, K_b)
+    so for cotangents (w_K, w_u) on them
+        d/du_b = (up/B) mask (.) [ K_T(u_b, K_b) (mask (.) w_u[b])  +  F_int(u_b; controls = w_K[b]) ]
+        d/dK_b = (up/B) (mask (.) w_u[b])^T dF_int/dK          (F_int is linear in K, so d2E/dK2 = 0)
+    K_T v is the matrix-free product of fol_apply_jacobian_elements without the Dirichlet row mask, the last
+    line is fol_residual_adjoint_elements, F_int(u; w_K) is one more call of the batched energy kernel.
+    One launch per sample for the first and the last (no batched variant of those kernels yet)."""
+
+    @staticmethod
+    def forward(ctx, loss, batch_params, batch_dofs, up, payload):
+        ctx.loss, ctx.payload = loss, payload
+        ctx.save_for_backward(batch_params, batch_dofs, up)
+        ctx.set_materialize_grads(False)
+        gk = payload.grad_k if payload.grad_k is not None else torch.zeros_like(batch_params)
+        return gk, payload.grad_u
+
+    @staticmethod
+    def backward(ctx, w_k, w_u):
+        loss, pl = ctx.loss, ctx.payload
+        params, dofs, up = ctx.saved_tensors
+        lib = _lib.load()
+        nb = dofs.shape[0]
+        s = _lib.stream_ptr()
+        u_full = loss.GetFullDofVector(None, dofs) if pl.fuse_dirichlet else dofs
+        scale = up.to(loss.dtype) / nb
+        d_dofs = torch.zeros_like(dofs)
+        d_params = torch.zeros_like(params) if ctx.needs_input_grad[1] else None
+        if w_u is not None:
+            w_u = w_u.to(loss.dtype).contiguous().clone()
+            if pl.mask_dirichlet:
+                w_u[:, loss._dir_idx.to(torch.int64)] = 0
+            ye = torch.empty(max(loss._ne * loss._nd, 1), dtype=loss.dtype, device=loss.device)
+            dk_e = torch.empty(max(loss._ne * loss._nnode, 1), dtype=loss.dtype, device=loss.device)
+            phys = _lib.PHYSICS[loss.physics]
+            for b in range(nb):
+                _lib.check(lib.fol_apply_jacobian_elements(
+                    s, loss._dt, phys, loss.fe_element.code, loss.num_gp, 0, loss._ne, loss._nn, _lib.ptr(loss._xyz),
+                    _lib.ptr(loss._conn), _lib.ptr(params[b]), _lib.ptr(u_full[b]), _lib.ptr(loss._no_flag),
+                    loss._params, _lib.ptr(w_u[b]), _lib.ptr(ye), None))
+                _lib.check(lib.fol_residual_gather(s, loss._dt, loss._nn, loss._nnode, loss.number_dofs_per_node,
+                                                   _lib.ptr(loss._adj_ptr), _lib.ptr(loss._adj), _lib.ptr(ye),
+                                                   _lib.ptr(d_dofs[b])))
+                if d_params is not None:
+                    _lib.check(lib.fol_residual_adjoint_elements(
+                        s, loss._dt, phys, loss.fe_element.code, loss.num_gp, 0, loss._ne, _lib.ptr(loss._xyz),
+                        _lib.ptr(loss._conn), _lib.ptr(params[b]), _lib.ptr(u_full[b]), _lib.ptr(w_u[b]), None,
+                        loss._params, _lib.ptr(dk_e), None))
+                    _lib.check(lib.fol_residual_gather(s, loss._dt, loss._nn, loss._nnode, 1, _lib.ptr(loss._adj_ptr),
+                                                       _lib.ptr(loss._adj), _lib.ptr(dk_e), _lib.ptr(d_params[b])))
+        if w_k is not None:
+            # F_int is linear in the control field: dF_int/dK . w_K = F_int(u; controls = w_K)
+            _, fint, _ = loss._energy_and_grads(w_k.to(loss.dtype).contiguous(), u_full.contiguous())
+            d_dofs = d_dofs + fint
+        d_dofs = d_dofs * scale
+        if pl.mask_dirichlet:
+            d_dofs[:, loss._dir_idx.to(torch.int64)] = 0
+        if d_params is not None:
+            d_params = d_params * scale
+        return None, d_params, d_dofs, None, None
 
 
 class FiniteElementLoss(Loss):
@@ -449,16 +529,22 @@ class FiniteElementLoss(Loss):
     # how the reference's energy behaves under a SECOND differentiation:
     #   "zero"        E = u^T stop_gradient(re) (mechanical.py:116): every second derivative is zero
     #   "zero_in_u"   thermal.py:31, 45-46: T is stopped inside Se and re, so d2E/dT2 = 0, but d2E/dT dK is not
-    #   None          a true potential (Neo-Hooke, St-Venant, transient thermal, Allen-Cahn): the Hessian is the
-    #                 tangent stiffness; not available through this entry point (ApplyJacobian gives J v)
+    #   "hessian"     Neo-Hooke: a true potential whose analytic tangent IS the Hessian (checked on the oracle to
+    #                 1e-15): second-order terms from the matrix-free K v kernel (_SecondOrderFn)
+    #   None          the other true potentials: St-Venant's reference tangent is not its Hessian (unsymmetrised
+    #                 identity, saint_venant.py:24-27), the implicit scalar energies' Hessians differ from their Ke
     _second_order = None
 
     def _check_second_order(self, params_need_grad):
+        """-> "constant" (the cotangents are constants of the outer differentiation) | "hessian" (route them
+        through _SecondOrderFn); raises where neither is the reference's result."""
         if float(self.loss_function_exponent) == 1.0:       # E^p with p != 1 adds p(p-1)E^(p-2) dE dE^T
             if self._second_order == "zero":
-                return
+                return "constant"
             if self._second_order == "zero_in_u" and not params_need_grad:
-                return
+                return "constant"
+            if self._second_order == "hessian" and not self._parametric:
+                return "hessian"
         raise NotImplementedError(
             f"{self.GetName()}: second-order differentiation of ComputeBatchLoss is not available for this loss "
             "(the first-order cotangents would be treated as constants, which differs from the reference here)")

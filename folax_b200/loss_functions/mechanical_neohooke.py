@@ -5,7 +5,7 @@ from .mechanical import MechanicalLoss
 
 class NeoHookeMechanicalLoss(MechanicalLoss):
     physics = "neohooke"
-    _second_order = None       # a true potential: the Hessian is the tangent stiffness
+    _second_order = "hessian"  # a true potential whose analytic tangent is its Hessian
     _has_control_gradient = True  # psi is differentiable in the control field
 
     def Initialize(self, reinitialize=False) -> None:

@@ -9,6 +9,7 @@ from .mechanical_neohooke import NeoHookeMechanicalLoss
 
 class SaintVenantMechanicalLoss(NeoHookeMechanicalLoss):
     physics = "stvenant"
+    _second_order = None       # the reference tangent (2 mu shear entries) is not the Hessian of psi
     default_material_settings = {"young_modulus": 1.0, "poisson_ratio": 0.3, "heterogeneity_field_name": "K",
                                  "heterogeneity_default_value": 1.0}
 
