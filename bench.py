@@ -10,7 +10,8 @@ float64, 128^3 elements per GPU (configs[1]).  One JSON line on stdout (rank 0).
               inputs -> H2D, kernels, D2H of the BCOO data + residual inside the timed region)
   roofline    dominant kernel (element stage) vs measured HBM copy bandwidth
   cpu_baseline  C/OpenMP port of the reference arithmetic (oracle/c) on all host cores, bounded sample
-  fol_loss_grad secondary metric: FOL physics loss + VJP samples/s (thermal 256x256 quads)
+  fol_loss_grad secondary metric: FOL physics loss + VJP samples/s (thermal 256x256 quads), with its own
+              cpu_baseline (C/OpenMP port of the batched loss + gradient, physics only) at N = 1
 `--impl reference` times the CPU port alone (the reference itself needs JAX, absent here).
 """
 import argparse
@@ -121,6 +122,31 @@ def cpu_assembly_rate(n_side, min_seconds, threads):
     while True:
         c_oracle.hex_mech_assemble(coords, conn, K, u, didx, 1.0, 0.3, out=out)
         done += ne
+        if time.perf_counter() - t0 >= min_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done, dt
+
+
+def cpu_fol_rate(min_seconds, threads):
+    """CPU baseline of the secondary metric: the plain-C / OpenMP restatement of the batched thermal loss and its
+    gradient (oracle/c/quad_thermal_loss.c: dense Se per element as thermal.py:28-49 writes it, samples in
+    parallel) on the 256x256 quad mesh of configs[2], physics only (no network).  Returns (samples/s, samples, s)."""
+    import folax_b200
+    from oracle import assembly, c_oracle
+    threads = c_oracle.set_threads(threads)
+    mesh = folax_b200.create_2D_square_mesh(1.0, 257)
+    coords, conn = np.asarray(mesh.GetNodesCoordinates()), mesh.GetElementsNodes("quad")
+    didx, dval = assembly.dirichlet_vectors(["T"], {"T": {"left": 1.0, "right": 0.1}}, mesh.node_sets)
+    rng = np.random.default_rng(0)
+    nb = max(2 * threads, 8)
+    K = rng.uniform(0.1, 1.0, (nb, len(coords)))
+    U = assembly.full_dof_vector(rng.uniform(0.0, 1.0, (nb, len(coords))), didx, dval)
+    c_oracle.quad_thermal_batch_loss_grads(coords, conn, K, U, 2.0, 4.0)      # warm-up
+    t0, done = time.perf_counter(), 0
+    while True:
+        c_oracle.quad_thermal_batch_loss_grads(coords, conn, K, U, 2.0, 4.0)
+        done += nb
         if time.perf_counter() - t0 >= min_seconds:
             break
     dt = time.perf_counter() - t0
@@ -408,6 +434,18 @@ def run_ours(args):
         try:
             sec = fol_loss_grad_bench(torch, dist, rank, world, max(3, min(args.steps, 10)), 3)
             line["fol_loss_grad"] = sec
+            if rank == 0 and world == 1:
+                try:
+                    threads = os.cpu_count() or 1
+                    rate, done, dt = cpu_fol_rate(5.0, threads)
+                    sec["cpu_baseline"] = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
+                                           "sample": f"{done} samples in {dt:.1f} s on the same 256x256 thermal quad "
+                                                     "mesh, physics loss + gradient only (compare with "
+                                                     "physics_only_samples_per_s), C/OpenMP restatement of the "
+                                                     "reference arithmetic (oracle/c/quad_thermal_loss.c), not the "
+                                                     "JAX path"}
+                except Exception as ex:
+                    sec["cpu_baseline"] = {"error": str(ex)[:200]}
         except Exception as ex:
             line["fol_loss_grad"] = {"error": str(ex)[:200]}
     if rank == 0:

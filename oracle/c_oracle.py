@@ -17,12 +17,16 @@ def build():
 
 
 def load():
-    if not os.path.exists(LIB):
+    srcs = [os.path.join(_HERE, "c", f) for f in ("hex_mech.c", "quad_thermal_loss.c", "Makefile")]
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(f) for f in srcs):
         build()
     lib = ctypes.CDLL(LIB)
     lib.oracle_hex_mech_assemble.restype = None
     lib.oracle_hex_mech_assemble.argtypes = [ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 5 + \
         [ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    lib.oracle_quad_thermal_loss_grads.restype = None
+    lib.oracle_quad_thermal_loss_grads.argtypes = [ctypes.c_int64] * 3 + [ctypes.c_void_p] * 4 + \
+        [ctypes.c_double, ctypes.c_double] + [ctypes.c_void_p] * 3
     lib.oracle_set_threads.argtypes = [ctypes.c_int]
     lib.oracle_max_threads.restype = ctypes.c_int
     return lib
@@ -51,3 +55,19 @@ def hex_mech_assemble(coords, conn, ctrl, u, dirichlet_indices, E, nu, body=None
                                  flags.ctypes.data, float(E), float(nu), body.ctypes.data, int(transpose),
                                  data.ctypes.data, R.ctypes.data)
     return data, R
+
+
+def quad_thermal_batch_loss_grads(coords, conn, batch_controls, batch_dofs_full, beta=0.0, c=1.0):
+    """Batched thermal Quad4 (2x2 rule) energies and their gradients: (E_b (nb), dE_b/dT (nb, nn), dE_b/dK (nb, nn)).
+    batch_dofs_full must carry the Dirichlet values already (fe_loss.py:255)."""
+    lib = load()
+    coords = np.ascontiguousarray(coords, np.float64)
+    conn = np.ascontiguousarray(conn, np.int32)
+    K = np.ascontiguousarray(np.atleast_2d(batch_controls), np.float64)
+    U = np.ascontiguousarray(np.atleast_2d(batch_dofs_full), np.float64)
+    nb, nn = U.shape
+    energy, gU, gK = np.empty(nb), np.empty((nb, nn)), np.empty((nb, nn))
+    lib.oracle_quad_thermal_loss_grads(nb, len(conn), nn, coords.ctypes.data, conn.ctypes.data, K.ctypes.data,
+                                       U.ctypes.data, float(beta), float(c), energy.ctypes.data, gU.ctypes.data,
+                                       gK.ctypes.data)
+    return energy, gU, gK
