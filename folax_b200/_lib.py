@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libfolax_b200.so")
 F32, F64 = 0, 1
 ELEMENTS = {"hexahedron": 0, "quad": 1, "tetra": 2, "triangle": 3}
 PHYSICS = {"mechanical": 0, "thermal": 1, "neohooke": 2, "j2plasticity": 3, "stvenant": 4,
-           "transient_thermal": 5, "allen_cahn": 6}
+           "transient_thermal": 5, "allen_cahn": 6, "neohooke_ad": 7, "stvenant_ad": 8}
 NUM_PARAMS = 12
 
 _vp, _i32p, _u8p, _i64, _int, _dbl = C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double

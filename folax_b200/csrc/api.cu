@@ -3,6 +3,7 @@
 
 #include "assemble.cuh"
 #include "energy.cuh"
+#include "assemble_ad_args.cuh"
 
 namespace fol {
 int assemble_mech_f64(cudaStream_t, int, int, const AsmArgs<double>&);
@@ -20,6 +21,8 @@ int assemble_stvk_f32(cudaStream_t, int, int, const AsmArgs<float>&);
 int assemble_j2_f64(cudaStream_t, int, int, const AsmArgs<double>&);
 int assemble_j2_f32(cudaStream_t, int, int, const AsmArgs<float>&);
 int assemble_hex_mech_f64(cudaStream_t, const AsmArgs<double>&);
+template <class T>
+int assemble_ad(cudaStream_t, int, int, int, const AdAsmArgs<T>&);
 extern std::atomic<int> g_grid_margin;
 
 template <class T>
@@ -79,6 +82,12 @@ static int assemble_typed(cudaStream_t s, int physics, int element, int num_gp, 
     case FOL_STVENANT:
       if constexpr (f64) return assemble_stvk_f64(s, element, num_gp, a);
       else return assemble_stvk_f32(s, element, num_gp, a);
+    case FOL_NEOHOOKE_AD:
+    case FOL_STVENANT_AD: {
+      if (v) return fail(FOL_ERR_UNSUPPORTED, "fol_apply_jacobian_elements: not available for the AD loss variants");
+      AdAsmArgs<T> ad{a.xyz, a.conn, a.ctrl, a.u, a.dir, a.ke, a.re, (T*)st_out, ne, transpose, a.p};
+      return assemble_ad<T>(s, physics, element, num_gp, ad);
+    }
 #ifdef FOL_HAVE_J2
     case FOL_J2PLASTICITY:
       if (!st_in || (!st_out && !v)) return fail(FOL_ERR_INVALID, "J2 plasticity needs state_in/state_out");

@@ -458,7 +458,7 @@ class FiniteElementLoss(Loss):
 
     def _geometry_cache(self):
         if self._geom is None:
-            lib, phys = _lib.load(), _lib.PHYSICS[self.physics]
+            lib, phys = _lib.load(), _lib.PHYSICS[self._batch_physics()]
             width = lib.fol_geometry_width(phys, self.fe_element.code)
             self._geom = torch.empty(max(self._ne * self._ngauss * width, 1), dtype=self.dtype, device=self.device)
             _lib.check(lib.fol_geometry_cache_physics(_lib.stream_ptr(), self._dt, phys, self.fe_element.code,
@@ -468,6 +468,10 @@ class FiniteElementLoss(Loss):
         return self._geom
 
     _has_control_gradient = True
+
+    def _batch_physics(self):
+        """Physics tag of the batched energy kernels (the element stage uses self.physics)."""
+        return self.physics
 
     def _energy_plan(self):
         """Device-resident integer tile plan of the fused batched-loss kernel (energy_plan.py)."""
@@ -511,7 +515,7 @@ class FiniteElementLoss(Loss):
         grad_k = torch.empty_like(batch_params) if self._has_control_gradient else None
         energy = torch.empty(nb, dtype=self.dtype, device=self.device)
         work = self._energy_work(nb)
-        _lib.check(lib.fol_energy_and_grads(_lib.stream_ptr(), self._dt, _lib.PHYSICS[self.physics],
+        _lib.check(lib.fol_energy_and_grads(_lib.stream_ptr(), self._dt, _lib.PHYSICS[self._batch_physics()],
                                             self.fe_element.code, self.num_gp, self._ne, self._nn, nb,
                                             _lib.ptr(geom), _lib.ptr(self._conn), _lib.ptr(ep["adj_ptr"]),
                                             _lib.ptr(ep["adj_local"]), _lib.ptr(ep["tile_node_ptr"]),

@@ -35,7 +35,10 @@ enum fol_element { FOL_HEXAHEDRON = 0, FOL_QUAD = 1, FOL_TETRA = 2, FOL_TRIANGLE
 /* fol/loss_functions: mechanical.py, thermal.py, mechanical_neohooke.py, mechanical_elastoplasticity.py */
 enum fol_physics { FOL_MECHANICAL = 0, FOL_THERMAL = 1, FOL_NEOHOOKE = 2, FOL_J2PLASTICITY = 3,
                    FOL_STVENANT = 4 /* mechanical_saint_venant.py */,
-                   FOL_TRANSIENT_THERMAL = 5 /* transient_thermal.py */, FOL_ALLEN_CAHN = 6 /* phase_field.py */ };
+                   FOL_TRANSIENT_THERMAL = 5 /* transient_thermal.py */, FOL_ALLEN_CAHN = 6 /* phase_field.py */,
+                   /* the *_AD.py variants (stiffness = jacfwd of the residual; element stage only, see
+                    * csrc/assemble_ad_threads.cuh): state_out = per-element energy (ne) or NULL */
+                   FOL_NEOHOOKE_AD = 7 /* mechanical_neohooke_AD.py */, FOL_STVENANT_AD = 8 /* mechanical_saint_venant_AD.py */ };
 
 #define FOL_OK 0
 #define FOL_ERR_INVALID (-1)

@@ -327,3 +327,70 @@ def implicit_scalar_energy_grads(physics, element_type, num_gp, X, fc, fn, param
         dn = np.einsum("eg,ega->ea", wd, flux) + np.einsum("eg,ga->ea", wd / eps ** 2 * (fn_g ** 2 - 1.0) * fn_g + rate, Ns)
     dc = -np.einsum("eg,ga->ea", rate, Ns)
     return dn, dc
+
+
+# ----------------------------------------------------------------------------- the *_AD.py variants
+def _ad_point(F, k, mu, lam, law):
+    """The AD material models differentiate an energy written in the VOIGT vector of C (or E), which
+    `VoigtToTensor` (utils.py:34-57) enters twice per shear component: their Voigt shear stresses are therefore
+    2x the tensor components (neo_hooke.py:112-157, 159-209; saint_venant.py:36-64).  Returns
+    (psi, S_voigt) with that doubling; F (..., d, d)."""
+    d = F.shape[-1]
+    C = np.einsum("...ki,...kj->...ij", F, F)
+    eye = np.eye(d)
+    if law == "neohooke_ad":
+        invC = np.linalg.inv(C)
+        J = np.sqrt(np.linalg.det(C))
+        lnJ = np.log(J)
+        trC = np.trace(C, axis1=-2, axis2=-1)
+        if d == 3:      # psi = mu/2 (J^-2/3 tr C - 3) - mu ln J + lam/2 ln^2 J      (neo_hooke.py:128-134)
+            Jm = J ** (-2.0 / 3.0)
+            psi = 0.5 * mu * (Jm * trC - 3.0) - mu * lnJ + 0.5 * lam * lnJ ** 2
+            S = (mu * Jm)[..., None, None] * (eye - (trC / 3.0)[..., None, None] * invC) \
+                + (lam * lnJ - mu)[..., None, None] * invC
+        else:           # psi = mu/2 (tr C - 2) - mu ln J + lam/2 ln^2 J            (neo_hooke.py:178-181)
+            psi = 0.5 * mu * (trC - 2.0) - mu * lnJ + 0.5 * lam * lnJ ** 2
+            S = mu[..., None, None] * (eye - invC) + (lam * lnJ)[..., None, None] * invC
+    else:               # stvenant_ad: psi = lam/2 tr(E)^2 + mu tr(E E)                (saint_venant.py:51-54)
+        E = 0.5 * (C - eye)
+        tr = np.trace(E, axis1=-2, axis2=-1)
+        psi = 0.5 * lam * tr ** 2 + mu * np.einsum("...ij,...ji->...", E, E)
+        S = (lam * tr)[..., None, None] * eye + 2.0 * mu[..., None, None] * E
+    vo = _VOIGT3 if d == 3 else _VOIGT2
+    Sv = np.stack([S[..., i, j] * (1.0 if i == j else 2.0) for (i, j) in vo], axis=-1)
+    return psi, Sv
+
+
+def ad_variant_residual(element_type, num_gp, X, de, u, nu, body, law):
+    """(energy, Fint - Fe) of mechanical_neohooke_AD.py:254-293 / mechanical_saint_venant_AD.py:271-310."""
+    elem = ELEMENTS[element_type]
+    d = elem.dim
+    Ns, gradN, detJ, w = point_data(elem, X, num_gp)
+    ne = X.shape[0]
+    U = u.reshape(ne, elem.nnode, d)
+    F = np.einsum("egai,eaj->egji", gradN, U) + np.eye(d)
+    e_gp = np.einsum("ga,ea->eg", Ns, de)
+    k_gp = e_gp / (3.0 * (1.0 - 2.0 * nu))
+    mu_gp = e_gp / (2.0 * (1.0 + nu))
+    lam_gp = e_gp * nu / ((1.0 + nu) * (1.0 - 2.0 * nu))
+    psi, Sv = _ad_point(F, k_gp, mu_gp, lam_gp, law)
+    B = neo_hooke_b_matrix(gradN, F)
+    wd = w[None, :] * detJ
+    Fint = np.einsum("eg,egsn,egs->en", wd, B, Sv)
+    body = np.zeros(d) if body is None else body
+    Fe = body_force_vector(elem, Ns, detJ, w, body)
+    return np.einsum("eg,eg->e", wd, psi), Fint - Fe
+
+
+def ad_variant_element(element_type, num_gp, X, de, u, nu, body=None, law="neohooke_ad"):
+    """ComputeElement of the AD variants: the stiffness is `jax.jacfwd(residual)` there
+    (mechanical_neohooke_AD.py:275, 283); here a complex-step Jacobian of the same residual."""
+    energy, re = ad_variant_residual(element_type, num_gp, X, de, u, nu, body, law)
+    nd = u.shape[1]
+    Ke = np.zeros((u.shape[0], nd, nd))
+    h = 1e-30
+    for j in range(nd):
+        up = u.astype(complex)
+        up[:, j] += 1j * h
+        Ke[:, :, j] = ad_variant_residual(element_type, num_gp, X, de, up, nu, body, law)[1].imag / h
+    return energy.real if np.iscomplexobj(energy) else energy, re, Ke

@@ -23,10 +23,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def build_shim(out_dir):
-    """nvcc -shared of the two host shims (host code only is ever called)."""
+    """nvcc -shared of the host shims (host code only is ever called)."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     out = os.path.join(str(out_dir), "libfolax_host_shim.so")
-    srcs = [os.path.join(ROOT, "tests", "host_shim", f) for f in ("adjoint_host.cu", "krylov_host.cu")]
+    srcs = [os.path.join(ROOT, "tests", "host_shim", f) for f in ("adjoint_host.cu", "krylov_host.cu", "assemble_ad_host.cu")]
     r = subprocess.run([nvcc, "-O2", "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-shared",
                         "-Xcompiler", "-fPIC"] + srcs + ["-o", out], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
