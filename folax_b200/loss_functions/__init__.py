@@ -14,3 +14,4 @@ from .mechanical_saint_venant import (SaintVenantMechanicalLoss, SaintVenantMech
 from .transient_thermal import (TransientThermalLoss, TransientThermalLoss2DQuad, TransientThermalLoss2DTri,
                                 TransientThermalLoss3DHexa, TransientThermalLoss3DTetra)
 from .phase_field import AllenCahnLoss, AllenCahnLoss2DQuad, AllenCahnLoss2DTri, AllenCahnLoss3DHexa
+from .kratos_small_displacement import KratosSmallDisplacement3DTetra

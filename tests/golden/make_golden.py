@@ -28,6 +28,7 @@ FILES = [
     "tests/unit/test_nonlinear_transient_thermal.py",
     "tests/unit/test_allencahn_loss.py",
     "tests/integration/test_mechanical_2D_sa.py",
+    "tests/unit/test_kratos_ffi_mechanical_loss.py",
 ]
 
 

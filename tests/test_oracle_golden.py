@@ -202,3 +202,24 @@ def test_implicit_scalar_batch_gradients_vs_finite_differences(physics, etype, n
             fm = assembly.batch_loss(*args, *pair(am), didx, dval, params, exponent=2.0)[0]
             assert abs((fp - fm) / (2 * h) - grad[b, idx]) <= 2e-6 * max(1.0, np.abs(grad).max())
     assert not gU[:, didx].any()
+
+
+def _tf32(x):
+    """Round float32 values to TF32 (10 explicit mantissa bits, round to nearest)."""
+    b = np.asarray(x, np.float32).view(np.uint32)
+    return ((b + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def test_kratos_ffi_class_jacobian_golden(goldens):
+    """tests/unit/test_kratos_ffi_mechanical_loss.py:72: the dense Jacobian of KratosSmallDisplacement3DTetra on one
+    tet (E = 1, nu = 0.3).  Its values carry only 11 significant bits: they are the TF32 rounding of the float32
+    stiffness (JAX's default matmul precision on the GPU that produced them, in the 0/1 mask products of
+    fe_loss.py:203-207).  The constant-strain Tet4 of the oracle, rounded the same way, reproduces them exactly --
+    which pins the Kratos element (SmallDisplacementElement3D4N + LinearElastic3DLaw) to MechanicalLoss3DTetra with a
+    unit control field.  (The energy / residual goldens of that test need JAX's PRNG and cannot be used here.)"""
+    rec = goldens["tests/unit/test_kratos_ffi_mechanical_loss.py"]["test_tetra"]
+    X = np.array(rec["assign"]["tet_points_coordinates"], float)[None]
+    jac = np.array([a for a in rec["asserts"] if "jac" in a["expr"]][0]["value"])
+    _, _, Ke = losses.mechanical_element("tetra", 1, X, np.ones((1, 4)), np.zeros((1, 12)), 1.0, 0.3, None)
+    assert np.abs(_tf32(Ke[0].reshape(-1)) - jac).max() <= 1e-12
+    assert np.abs(Ke[0].reshape(-1) - jac).max() <= 2.0 ** -11 * np.abs(jac).max()
