@@ -53,6 +53,8 @@ SIGNATURES = {
                                      _vp]),
     "fol_residual_adjoint_elements": (_int, [_vp, _int, _int, _int, _int, _int, _i64, _vp, _i32p, _vp, _vp, _vp, _vp,
                                              C.POINTER(_dbl), _vp, _vp]),
+    "fol_element_energies": (_int, [_vp, _int, _int, _int, _int, _i64, _vp, _i32p, _vp, _vp, _vp, C.POINTER(_dbl),
+                                    _vp]),
     "fol_sum": (_int, [_vp, _int, _i64, _vp, _vp]),
     "fol_gather_values": (_int, [_vp, _int, _i64, _i32p, _vp, _vp]),
     "fol_sell_spmv": (_int, [_vp, _int, _i64, _vp, _i32p, _vp, _vp, _vp]),

@@ -23,6 +23,12 @@ __global__ void __launch_bounds__(128) residual_adjoint_kernel(const AdjointArgs
   if (e < a.ne) residual_adjoint_thread<T, ELEM, ORDER, PHYS>(e, a);
 }
 
+template <class T, int ELEM, int ORDER, int PHYS>
+__global__ void __launch_bounds__(128) element_energy_kernel(const AdjointArgs<T> a) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < a.ne) element_energy_thread<T, ELEM, ORDER, PHYS>(e, a);
+}
+
 // out[0] = sum x[0..n): one block, fixed order (thread-strided partial sums, then a shared-memory tree)
 template <class T>
 __global__ void __launch_bounds__(1024) sum_kernel(const T* __restrict__ x, long long n, T* __restrict__ out) {
@@ -82,6 +88,49 @@ static int launch_adjoint(cudaStream_t s, int element, int num_gp, const Adjoint
   FOL_ELEM_ORDER_CASES(X)
 #undef X
   return fail(FOL_ERR_UNSUPPORTED, "fol_residual_adjoint_elements: unsupported element / num_gp");
+}
+
+template <class T, int PHYS>
+static int launch_energy(cudaStream_t s, int element, int num_gp, const AdjointArgs<T>& a) {
+  if (a.ne == 0) return FOL_OK;
+  const unsigned grid = (unsigned)cdiv(a.ne, 128);
+#define X(E, O)                                                          \
+  if (element == E && num_gp == O) {                                     \
+    element_energy_kernel<T, E, O, PHYS><<<grid, 128, 0, s>>>(a);        \
+    return check_launch("element_energy_kernel");                        \
+  }
+  FOL_ELEM_ORDER_CASES(X)
+#undef X
+  return fail(FOL_ERR_UNSUPPORTED, "fol_element_energies: unsupported element / num_gp");
+}
+
+template <class T>
+static int energies_typed(cudaStream_t s, int physics, int element, int num_gp, long long ne, const void* xyz,
+                          const int32_t* conn, const void* ctrl, const void* u, const void* aux, const double* params,
+                          void* energy) {
+  AdjointArgs<T> a;
+  a.xyz = (const T*)xyz;
+  a.conn = conn;
+  a.ctrl = (const T*)ctrl;
+  a.u = (const T*)u;
+  a.lam = nullptr;
+  a.aux = (const T*)aux;
+  a.dk = (T*)energy;
+  a.dx = nullptr;
+  a.ne = ne;
+  a.accumulate = 0;
+  a.p = make_params<T>(params);
+  switch (physics) {
+    case FOL_MECHANICAL: return launch_energy<T, ADJ_MECH>(s, element, num_gp, a);
+    case FOL_THERMAL: return launch_energy<T, ADJ_THERMAL>(s, element, num_gp, a);
+    case FOL_NEOHOOKE: return launch_energy<T, ADJ_NEOHOOKE>(s, element, num_gp, a);
+    case FOL_STVENANT: return launch_energy<T, ADJ_STVK>(s, element, num_gp, a);
+    case FOL_ALLEN_CAHN: return launch_energy<T, ADJ_ALLENCAHN>(s, element, num_gp, a);
+    case FOL_TRANSIENT_THERMAL:
+      if (!aux) return fail(FOL_ERR_INVALID, "fol_element_energies: transient thermal needs the nodal k0 in aux");
+      return launch_energy<T, ADJ_TTHERMAL>(s, element, num_gp, a);
+  }
+  return fail(FOL_ERR_UNSUPPORTED, "fol_element_energies: no stateless element energy for this physics");
 }
 
 template <class T>
@@ -196,6 +245,21 @@ int fol_residual_adjoint_elements(fol_stream_t s, int dtype, int physics, int el
     return adjoint_typed<float>((cudaStream_t)s, physics, element, num_gp, accumulate, ne, xyz, conn, ctrl, u, adj,
                                 aux, params_host, dk_elem, dx_elem);
   return fail(FOL_ERR_INVALID, "fol_residual_adjoint_elements: unknown dtype");
+}
+
+int fol_element_energies(fol_stream_t s, int dtype, int physics, int element, int num_gp, int64_t ne, const void* xyz,
+                         const int32_t* conn, const void* ctrl, const void* u, const void* aux,
+                         const double* params_host, void* energy_elem) {
+  FOL_REQUIRE(element >= 0 && element <= 3 && num_gp >= 1 && num_gp <= 3, "fol_element_energies: bad element / num_gp");
+  FOL_REQUIRE(ne >= 0 && xyz && conn && ctrl && u && params_host && energy_elem,
+              "fol_element_energies: null pointer / negative size");
+  if (dtype == FOL_F64)
+    return energies_typed<double>((cudaStream_t)s, physics, element, num_gp, ne, xyz, conn, ctrl, u, aux, params_host,
+                                  energy_elem);
+  if (dtype == FOL_F32)
+    return energies_typed<float>((cudaStream_t)s, physics, element, num_gp, ne, xyz, conn, ctrl, u, aux, params_host,
+                                 energy_elem);
+  return fail(FOL_ERR_INVALID, "fol_element_energies: unknown dtype");
 }
 
 int fol_sum(fol_stream_t s, int dtype, int64_t n, const void* x, void* out) {

@@ -391,6 +391,89 @@ __host__ __device__ inline S element_phi(const S* X, const S* de, const T* ue, c
   return phi;
 }
 
+// Element energy, the first return value of ComputeElement (fe_loss.py:149-176: ComputeElementsEnergies):
+//   mechanical.py:116-117 / thermal.py:45-49   u^T (Ke u - Fe)                  (= phi with lam = u)
+//   mechanical_neohooke.py:262, 271            sum_g w detJ psi,  psi of neo_hooke.py:14-58 / 64-109
+//   mechanical_saint_venant.py                 sum_g w detJ (lam/2 tr(E)^2 + mu tr(E E))
+//   transient_thermal.py:42-73                 sum_g w detJ [K(T_n)/2 |grad T_n|^2 + rho cp/(2 dt) (T_n - T_c)^2]
+//   phase_field.py:38-70                       sum_g w detJ [|grad p_n|^2/2 + (p_n^2 - 1)^2/(4 eps^2) + (p_n - p_c)^2/(2 dt)]
+template <class T, int ELEM, int ORDER, int PHYS>
+__host__ __device__ inline T element_energy(const T* X, const T* de, const T* ue, const T* aux, const Params<T>& P) {
+  constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM), NGP = elem_ngauss(ELEM, ORDER);
+  if constexpr (PHYS == ADJ_MECH || PHYS == ADJ_THERMAL) {
+    return element_phi<T, T, ELEM, ORDER, PHYS>(X, de, ue, ue, aux, P);
+  } else {
+    constexpr bool TRANSPOSED = (PHYS == ADJ_TTHERMAL || PHYS == ADJ_ALLENCAHN);
+    T en = (T)0;
+    for (int g = 0; g < NGP; ++g) {
+      double xi[3], w;
+      gauss_point<ELEM, ORDER>(g, xi, w);
+      T N[A], dN[A][D], gN[A][D];
+      shape_functions<ELEM, T>(xi, N, dN);
+      const T wd = (T)w * global_gradients<ELEM, T, TRANSPOSED>(X, dN, gN);
+      T eg = (T)0;
+      for (int b = 0; b < A; ++b) eg += N[b] * de[b];
+      if constexpr (TRANSPOSED) {
+        T fn = (T)0, kg = (T)0, g2 = (T)0;
+        for (int b = 0; b < A; ++b) {
+          fn += N[b] * ue[b];
+          if (aux) kg += N[b] * aux[b];
+        }
+        for (int k = 0; k < D; ++k) {
+          T gf = (T)0;
+          for (int b = 0; b < A; ++b) gf += gN[b][k] * ue[b];
+          g2 += gf * gf;
+        }
+        const T dt = P.v[10];
+        if constexpr (PHYS == ADJ_TTHERMAL) {
+          const T beta = P.v[5], rcp = P.v[8] * P.v[9];
+          const T Kg = kg * ((T)1 + ((beta != (T)0) ? beta * fol_pow(fn, (double)P.v[6]) : (T)0));
+          en += (T)0.5 * Kg * wd * g2 + rcp * (T)0.5 / dt * wd * (fn - eg) * (fn - eg);
+        } else {
+          const T ie2 = (T)1 / (P.v[11] * P.v[11]);
+          en += (T)0.5 * wd * g2 + wd * (T)0.25 * (fn * fn - (T)1) * (fn * fn - (T)1) * ie2 +
+                (T)0.5 / dt * wd * (fn - eg) * (fn - eg);
+        }
+      } else {
+        T F[D][D], C[D][D];
+        for (int i = 0; i < D; ++i)
+          for (int j = 0; j < D; ++j) {
+            T acc = (i == j) ? (T)1 : (T)0;
+            for (int b = 0; b < A; ++b) acc += gN[b][j] * ue[b * D + i];
+            F[i][j] = acc;
+          }
+        T trC = (T)0;
+        for (int i = 0; i < D; ++i)
+          for (int j = 0; j < D; ++j) {
+            T acc = (T)0;
+            for (int m = 0; m < D; ++m) acc += F[m][i] * F[m][j];
+            C[i][j] = acc;
+            if (i == j) trC += acc;
+          }
+        const T nu = P.v[1];
+        const T mu = eg / ((T)2 * ((T)1 + nu));
+        if constexpr (PHYS == ADJ_NEOHOOKE) {
+          const T J = det_small<T, D>(F);
+          const T kk = eg / ((T)3 * ((T)1 - (T)2 * nu));
+          const T Jm = (D == 2) ? (T)1 / J : fol_pow(J, -2.0 / 3.0);
+          en += wd * ((kk * (T)0.25) * (J * J - (T)2 * fol_log(J) - (T)1) + (T)0.5 * mu * (Jm * trC - (T)D));
+        } else {
+          const T lam = eg * nu / (((T)1 + nu) * ((T)1 - (T)2 * nu));
+          T trE = (T)0, ee = (T)0;
+          for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j) {
+              const T Eij = (T)0.5 * (C[i][j] - (i == j ? (T)1 : (T)0));
+              if (i == j) trE += Eij;
+              ee += Eij * Eij;
+            }
+          en += wd * ((T)0.5 * lam * trE * trE + mu * ee);
+        }
+      }
+    }
+    return en;
+  }
+}
+
 // The A*D + A directional derivatives of phi, one forward sweep each.
 template <class T, int ELEM, int ORDER, int PHYS>
 __host__ __device__ inline void residual_adjoint_element_dual(const T* X, const T* de, const T* ue, const T* le,

@@ -113,6 +113,22 @@ __host__ __device__ inline void residual_adjoint_thread(long long e, const Adjoi
     }
 }
 
+// energy_elem[e] = element energy (ComputeElementsEnergies); the arrays of AdjointArgs, `dk` receives the energies
+template <class T, int ELEM, int ORDER, int PHYS>
+__host__ __device__ inline void element_energy_thread(long long e, const AdjointArgs<T>& a) {
+  constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM);
+  constexpr int DPN = (PHYS == ADJ_THERMAL || PHYS == ADJ_TTHERMAL || PHYS == ADJ_ALLENCAHN) ? 1 : D;
+  T X[A * 3], de[A], ue[A * DPN], ax[A];
+  for (int b = 0; b < A; ++b) {
+    const long long n = a.conn[e * A + b];
+    for (int k = 0; k < 3; ++k) X[b * 3 + k] = a.xyz[n * 3 + k];
+    de[b] = a.ctrl[n];
+    ax[b] = a.aux ? a.aux[n] : (T)0;
+    for (int k = 0; k < DPN; ++k) ue[b * DPN + k] = a.u[n * DPN + k];
+  }
+  a.dk[e] = element_energy<T, ELEM, ORDER, PHYS>(X, de, ue, a.aux ? ax : nullptr, a.p);
+}
+
 // the forward-mode route on a physics that also has a closed form (test cross-check only)
 template <class T, int ELEM, int ORDER, int PHYS>
 __host__ __device__ inline void residual_adjoint_dual_reference_thread(long long e, const AdjointArgs<T>& a) {

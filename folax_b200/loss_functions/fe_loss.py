@@ -453,6 +453,55 @@ class FiniteElementLoss(Loss):
         # mechanical.py:116-117 / thermal.py:45-49: energy = u^T stop_gradient(re)
         return torch.dot(u, re)
 
+    # ------------------------------------------------------------------ element-level helpers of the reference API
+    def ComputeElementEnergy(self, elem_xyz, elem_controls, elem_dofs):
+        """fe_loss.py:149-153."""
+        return self.ComputeElement(elem_xyz, elem_controls, elem_dofs)[0]
+
+    def ComputeElementsEnergies(self, total_control_vars, total_primal_vars):
+        """fe_loss.py:166-173 -> (ne,) energies, the first return value of ComputeElement for every element
+        (one kernel over the mesh, csrc/adjoint.cuh: element_energy)."""
+        ctrl = _lib.to_device(total_control_vars, self.dtype).reshape(-1)
+        u = _lib.to_device(total_primal_vars, self.dtype).reshape(-1)
+        if ctrl.numel() != self._nn or u.numel() != self.total_number_of_dofs:
+            raise ValueError(f"{self.GetName()}: controls must have {self._nn} entries and dofs "
+                             f"{self.total_number_of_dofs}")
+        en = torch.empty(max(self._ne, 1), dtype=self.dtype, device=self.device)
+        _lib.check(_lib.load().fol_element_energies(
+            _lib.stream_ptr(), self._dt, _lib.PHYSICS[self.physics], self.fe_element.code, self.num_gp, self._ne,
+            _lib.ptr(self._xyz), _lib.ptr(self._conn), _lib.ptr(ctrl), _lib.ptr(u), _lib.ptr(self._geom_aux),
+            self._params, _lib.ptr(en)))
+        return en[:self._ne]
+
+    def ComputeElementJacobianIndices(self, nodes_ids):
+        """fe_loss.py:178-184 -> (nd*nd, 2) global (row, col) pairs of one element, in the order of the BCOO."""
+        nodes = torch.as_tensor(np.ascontiguousarray(np.asarray(nodes_ids).reshape(1, -1), dtype=np.int32),
+                                device=self.device)
+        nd = nodes.shape[1] * self.number_dofs_per_node
+        out = torch.empty((nd * nd, 2), dtype=torch.int32, device=self.device)
+        _lib.check(_lib.load().fol_bcoo_indices(_lib.stream_ptr(), _lib.ptr(nodes), 1, nodes.shape[1],
+                                                self.number_dofs_per_node, _lib.ptr(out)))
+        return out
+
+    def ApplyDirichletBCOnElementResidualAndJacobian(self, elem_res, elem_jac, elem_BC_vec, elem_mask_BC_vec):
+        """fe_loss.py:191-207 on ONE element given as arrays: BC (.) re,  diag(BC) Ke + diag(diag(M Ke M)), M = diag(mask).
+        (Inside the assembly kernels this is a row mask applied while storing; this method exists for callers that
+        hold an element matrix.)"""
+        re = _lib.to_device(elem_res, self.dtype).reshape(-1, 1)
+        ke = _lib.to_device(elem_jac, self.dtype)
+        bc = _lib.to_device(elem_BC_vec, self.dtype).reshape(-1)
+        mask = _lib.to_device(elem_mask_BC_vec, self.dtype).reshape(-1)
+        kept = mask * mask * torch.diagonal(ke)
+        return bc.reshape(-1, 1) * re, bc.reshape(-1, 1) * ke + torch.diag(kept)
+
+    def ComputeElementResidualAndJacobian(self, elem_xyz, elem_controls, elem_dofs, elem_BC, elem_mask_BC,
+                                          transpose_jac: bool):
+        """fe_loss.py:209-230: ComputeElement, optional transpose, then the Dirichlet treatment above."""
+        _, re, ke = self.ComputeElement(elem_xyz, elem_controls, elem_dofs)
+        if transpose_jac:
+            ke = ke.t()
+        return self.ApplyDirichletBCOnElementResidualAndJacobian(re, ke, elem_BC, elem_mask_BC)
+
     # ------------------------------------------------------------------ batched loss
     _geom_aux = None   # nodal field folded into the geometry cache (transient thermal: k0)
 

@@ -229,6 +229,14 @@ int fol_residual_adjoint_elements(fol_stream_t s, int dtype, int physics, int el
                                   const void* adj, const void* aux, const double* params_host, void* dk_elem,
                                   void* dx_elem);
 
+/* energy_elem[e] = the element energy ComputeElement returns first (ComputeElementsEnergies, fe_loss.py:149-176):
+ * u^T(Ke u - Fe) for the mechanical / thermal losses, sum_g w detJ psi for Neo-Hooke / St-Venant, the implicit-Euler
+ * potentials of transient thermal (aux = nodal k0) and Allen-Cahn.  J2 and the AD variants: FOL_ERR_UNSUPPORTED
+ * (their element stage returns the energies itself). */
+int fol_element_energies(fol_stream_t s, int dtype, int physics, int element, int num_gp, int64_t ne, const void* xyz,
+                         const int32_t* conn, const void* ctrl, const void* u, const void* aux,
+                         const double* params_host, void* energy_elem);
+
 /* out[0] = sum of x[0..n) in a fixed order (one block): ComputeValue's jnp.sum, fe_response.py:216 */
 int fol_sum(fol_stream_t s, int dtype, int64_t n, const void* x, void* out);
 

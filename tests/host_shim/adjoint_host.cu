@@ -70,6 +70,30 @@ int host_residual_adjoint_elements(int physics, int element, int num_gp, int acc
   return -3;
 }
 
+int host_element_energies(int physics, int element, int num_gp, long long ne, const double* xyz, const int32_t* conn,
+                          const double* ctrl, const double* u, const double* aux, const double* params,
+                          double* energy) {
+  AdjointArgs<double> a{xyz, conn, ctrl, u, nullptr, aux, energy, nullptr, ne, 0, make_params<double>(params)};
+#define X(E, O)                                                                                   \
+  if (element == E && num_gp == O) {                                                              \
+    for (long long e = 0; e < ne; ++e) {                                                          \
+      switch (physics) {                                                                          \
+        case 0: element_energy_thread<double, E, O, ADJ_MECH>(e, a); break;                       \
+        case 1: element_energy_thread<double, E, O, ADJ_THERMAL>(e, a); break;                    \
+        case 2: element_energy_thread<double, E, O, ADJ_NEOHOOKE>(e, a); break;                   \
+        case 4: element_energy_thread<double, E, O, ADJ_STVK>(e, a); break;                       \
+        case 5: element_energy_thread<double, E, O, ADJ_TTHERMAL>(e, a); break;                   \
+        case 6: element_energy_thread<double, E, O, ADJ_ALLENCAHN>(e, a); break;                  \
+        default: return -3;                                                                       \
+      }                                                                                           \
+    }                                                                                             \
+    return 0;                                                                                     \
+  }
+  CASES(X)
+#undef X
+  return -3;
+}
+
 // forward-mode route on the two physics that also have closed forms (cross-check of the two routes)
 int host_residual_adjoint_dual_reference(int physics, int element, int num_gp, long long ne, const double* xyz,
                                          const int32_t* conn, const double* ctrl, const double* u, const double* lam,

@@ -137,3 +137,23 @@ def test_gauss_interpolation_and_response(shim, etype, num_gp):
         assert np.abs(got - ref).max() <= 1e-12 * max(np.abs(ref).max(), 1e-300)
 
 
+
+
+@pytest.mark.parametrize("physics", list(PHYS))
+@pytest.mark.parametrize("etype,num_gp", [("hexahedron", 2), ("hexahedron", 3), ("quad", 2), ("tetra", 1), ("tetra", 2),
+                                          ("triangle", 1), ("triangle", 3)])
+def test_element_energies(shim, physics, etype, num_gp):
+    """ComputeElementsEnergies (fe_loss.py:149-176): the first return value of ComputeElement per element."""
+    coords, conn, d, K, u, _ = _case(etype, physics, seed=9)
+    if physics in ("neohooke", "stvenant"):
+        u = 0.05 * (u - 0.5)
+    ne = conn.shape[0]
+    dim = 3 if etype in ("hexahedron", "tetra") else 2
+    arr, par, aux = _params(physics, dim, conn, coords.shape[0])
+    if "k0" in par:
+        par = dict(par, k0=aux)                                          # compute_elements gathers the nodal field itself
+    en = np.full(ne, np.nan)
+    assert shim.host_element_energies(PHYS[physics], ELEM[etype], num_gp, C.c_longlong(ne), _p(coords), _p(conn), _p(K),
+                                      _p(u), _p(aux), _p(arr), _p(en)) == 0
+    ref = assembly.compute_elements(physics, etype, num_gp, coords, conn, K, u, par)[0]
+    assert np.abs(en - ref).max() <= 1e-12 * np.abs(ref).max()
