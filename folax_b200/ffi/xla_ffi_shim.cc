@@ -9,7 +9,9 @@
 //
 // JAX / jaxlib (and therefore xla/ffi/api/ffi.h) are NOT available in this build image, so this
 // translation unit is compiled only where the header exists (see INTEGRATION.md for the build line
-// and the Python registration stub).  It is untested here and says so.
+// and the Python registration stub).  It is untested under XLA here and says so; tests/test_cabi.py
+// compiles it against a stand-in header (tests/xla_stub) to keep it valid C++ that matches the C ABI and whose handler
+// signatures match their Ffi::Bind() chains.
 #if defined(__has_include)
 #if __has_include("xla/ffi/api/ffi.h")
 #define FOLAX_HAVE_XLA_FFI 1
@@ -89,7 +91,119 @@ ffi::Error EnergyAndGradsImpl(cudaStream_t stream, ffi::AnyBuffer geom, ffi::Buf
                                      energy->untyped_data(), work->untyped_data()));
 }
 
+// apply_jacobian_elements: ye_elem = Ke'(ctrl, u) v_e without forming Ke (what `BCOO @ v` does, fe_solver.py:61).
+ffi::Error ApplyJacobianElementsImpl(cudaStream_t stream, ffi::AnyBuffer xyz, ffi::Buffer<ffi::S32> conn,
+                                     ffi::AnyBuffer ctrl, ffi::AnyBuffer u, ffi::Buffer<ffi::U8> dir_flag,
+                                     ffi::AnyBuffer v, ffi::Result<ffi::AnyBuffer> ye, int32_t physics, int32_t element,
+                                     int32_t num_gp, int32_t transpose, ffi::Span<const double> params) {
+  const int dt = DtypeOf(xyz.element_type());
+  if (dt < 0) return ffi::Error::InvalidArgument("Unsupported data type for FFI call.");
+  if (params.size() != FOL_NUM_PARAMS) return ffi::Error::InvalidArgument("params must have 12 entries");
+  return FromRc(fol_apply_jacobian_elements(stream, dt, physics, element, num_gp, transpose, conn.dimensions()[0],
+                                            xyz.dimensions()[0], xyz.untyped_data(), conn.typed_data(),
+                                            ctrl.untyped_data(), u.untyped_data(), dir_flag.typed_data(),
+                                            params.begin(), v.untyped_data(), ye->untyped_data(), nullptr));
+}
+
+// the three kernels behind FiniteElementResponse (fe_response.py:91-524); the formula and its jax.grad stay in Python
+ffi::Error GaussInterpolateImpl(cudaStream_t stream, ffi::Buffer<ffi::S32> conn, ffi::AnyBuffer ctrl, ffi::AnyBuffer u,
+                                ffi::Result<ffi::AnyBuffer> k_gp, ffi::Result<ffi::AnyBuffer> u_gp, int32_t element,
+                                int32_t num_gp, int32_t dofs_per_node) {
+  const int dt = DtypeOf(u.element_type());
+  if (dt < 0) return ffi::Error::InvalidArgument("Unsupported data type for FFI call.");
+  return FromRc(fol_gauss_interpolate(stream, dt, element, num_gp, dofs_per_node, conn.dimensions()[0],
+                                      conn.typed_data(), ctrl.untyped_data(), u.untyped_data(), k_gp->untyped_data(),
+                                      u_gp->untyped_data()));
+}
+
+ffi::Error ResponseElementsImpl(cudaStream_t stream, ffi::AnyBuffer xyz, ffi::Buffer<ffi::S32> conn, ffi::AnyBuffer f_gp,
+                                ffi::AnyBuffer fk_gp, ffi::AnyBuffer fu_gp, ffi::Result<ffi::AnyBuffer> value_elem,
+                                ffi::Result<ffi::AnyBuffer> du_elem, ffi::Result<ffi::AnyBuffer> dk_elem,
+                                ffi::Result<ffi::AnyBuffer> dx_elem, int32_t element, int32_t num_gp,
+                                int32_t dofs_per_node) {
+  const int dt = DtypeOf(xyz.element_type());
+  if (dt < 0) return ffi::Error::InvalidArgument("Unsupported data type for FFI call.");
+  return FromRc(fol_response_elements(stream, dt, element, num_gp, dofs_per_node, conn.dimensions()[0],
+                                      xyz.untyped_data(), conn.typed_data(), f_gp.untyped_data(), fk_gp.untyped_data(),
+                                      fu_gp.untyped_data(), value_elem->untyped_data(), du_elem->untyped_data(),
+                                      dk_elem->untyped_data(), dx_elem->untyped_data()));
+}
+
+ffi::Error ResidualAdjointElementsImpl(cudaStream_t stream, ffi::AnyBuffer xyz, ffi::Buffer<ffi::S32> conn,
+                                       ffi::AnyBuffer ctrl, ffi::AnyBuffer u, ffi::AnyBuffer adj,
+                                       ffi::Result<ffi::AnyBuffer> dk_elem, ffi::Result<ffi::AnyBuffer> dx_elem,
+                                       int32_t physics, int32_t element, int32_t num_gp,
+                                       ffi::Span<const double> params) {
+  const int dt = DtypeOf(xyz.element_type());
+  if (dt < 0) return ffi::Error::InvalidArgument("Unsupported data type for FFI call.");
+  if (params.size() != FOL_NUM_PARAMS) return ffi::Error::InvalidArgument("params must have 12 entries");
+  return FromRc(fol_residual_adjoint_elements(stream, dt, physics, element, num_gp, /*accumulate=*/0,
+                                              conn.dimensions()[0], xyz.untyped_data(), conn.typed_data(),
+                                              ctrl.untyped_data(), u.untyped_data(), adj.untyped_data(),
+                                              /*aux=*/nullptr, params.begin(), dk_elem->untyped_data(),
+                                              dx_elem->untyped_data()));
+}
+
 }  // namespace
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FolApplyJacobianElements, ApplyJacobianElementsImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()          // xyz
+                                  .Arg<ffi::Buffer<ffi::S32>>()   // conn
+                                  .Arg<ffi::AnyBuffer>()          // ctrl
+                                  .Arg<ffi::AnyBuffer>()          // u
+                                  .Arg<ffi::Buffer<ffi::U8>>()    // dir_flag
+                                  .Arg<ffi::AnyBuffer>()          // v
+                                  .Ret<ffi::AnyBuffer>()          // ye_elem
+                                  .Attr<int32_t>("physics")
+                                  .Attr<int32_t>("element")
+                                  .Attr<int32_t>("num_gp")
+                                  .Attr<int32_t>("transpose")
+                                  .Attr<ffi::Span<const double>>("params"));
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FolGaussInterpolate, GaussInterpolateImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Attr<int32_t>("element")
+                                  .Attr<int32_t>("num_gp")
+                                  .Attr<int32_t>("dofs_per_node"));
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FolResponseElements, ResponseElementsImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Attr<int32_t>("element")
+                                  .Attr<int32_t>("num_gp")
+                                  .Attr<int32_t>("dofs_per_node"));
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FolResidualAdjointElements, ResidualAdjointElementsImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Attr<int32_t>("physics")
+                                  .Attr<int32_t>("element")
+                                  .Attr<int32_t>("num_gp")
+                                  .Attr<ffi::Span<const double>>("params"));
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(FolAssembleElements, AssembleElementsImpl,
                               ffi::Ffi::Bind()

@@ -69,3 +69,25 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+
+
+def test_xla_ffi_shim_compiles_against_a_stub_of_the_ffi_header(tmp_path):
+    """JAX / jaxlib are absent, so folax_b200/ffi/xla_ffi_shim.cc is normally preprocessed away.  Compiled here
+    against tests/xla_stub (a stand-in for the part of xla/ffi/api/ffi.h it uses): valid C++, calls that match the
+    current include/folax_b200.h, and handler signatures that match their Ffi::Bind() chains.  Not a behavioural
+    test -- XLA itself is not involved."""
+    import shutil
+    import subprocess
+    cuda_inc = "/usr/local/cuda/include"
+    if shutil.which("g++") is None or not os.path.isdir(cuda_inc):
+        pytest.skip("needs g++ and the CUDA headers")
+    obj = str(tmp_path / "shim.o")
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror=return-type", "-c",
+                        os.path.join(ROOT, "folax_b200", "ffi", "xla_ffi_shim.cc"),
+                        "-I", os.path.join(ROOT, "tests", "xla_stub"), "-I", cuda_inc, "-o", obj],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    syms = subprocess.run(["nm", obj], capture_output=True, text=True).stdout
+    for name in ("FolAssembleElements", "FolResidualGather", "FolEnergyAndGrads", "FolApplyJacobianElements",
+                 "FolGaussInterpolate", "FolResponseElements", "FolResidualAdjointElements"):
+        assert f"{name}_stub_marker" in syms, f"{name} was not compiled (is the shim still header-guarded away?)"
