@@ -5,8 +5,8 @@
 # 1. the not-yet-run GPU tests first (short, the news), 2. the whole GPU suite, 3. timings of the new kernels,
 # 4. the headline bench, 5. launch list + one full ncu capture of the SELL SpMV.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
-python -m pytest tests/test_zz_responses_gpu.py tests/test_zz_solvers_gpu.py tests/test_zz_second_order_gpu.py \
-       tests/test_zz_config3_newton_gpu.py tests/test_zz_config5_slabs_gpu.py tests/test_zz_ad_variants_gpu.py tests/test_zz_kratos_class_gpu.py tests/test_zz_element_api_gpu.py -m gpu -q > gpurun_out/new_tests.log 2>&1
+python -m pytest tests/test_zz1_responses_gpu.py tests/test_zz2_solvers_gpu.py tests/test_zz7_second_order_gpu.py \
+       tests/test_zz3_config3_newton_gpu.py tests/test_zz4_config5_slabs_gpu.py tests/test_zz8_ad_variants_gpu.py tests/test_zz6_kratos_class_gpu.py tests/test_zz5_element_api_gpu.py -m gpu -q > gpurun_out/new_tests.log 2>&1
 echo "new tests rc=$?"; tail -5 gpurun_out/new_tests.log
 python -m pytest tests -m gpu -q -x > gpurun_out/all_tests.log 2>&1
 echo "all tests rc=$?"; tail -3 gpurun_out/all_tests.log

@@ -4,7 +4,7 @@ The per-thread bodies of the kernels are __host__ __device__ functions; tests/ho
 them over the elements on the CPU (test infrastructure, never part of libfolax_b200).  Here they are compared,
 in float64, with the complex-step oracle (oracle/responses.py) -- closed forms against an independent
 differentiation route -- on every element type and integration order.  The GPU run of the same functions is
-tests/test_zz_responses_gpu.py."""
+tests/test_zz1_responses_gpu.py."""
 import ctypes as C
 import os
 

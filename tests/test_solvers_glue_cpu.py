@@ -4,7 +4,7 @@ No GPU here: the C ABI is the stand-in of tests/cpu_backend.py -- the SpMV, gath
 own per-thread code compiled for the CPU (tests/host_shim/krylov_host.cu), the loss is backed by the oracle.  What
 is exercised for real: the sliced-ELLPACK plan, BiCGSTAB, the Newton / load-step logic, the adjoint solve, against
 SciPy and against the reference's integration golden (tests/integration/test_mechanical_2D_sa.py:81-113).
-GPU runs of the same classes: tests/test_zz_solvers_gpu.py."""
+GPU runs of the same classes: tests/test_zz2_solvers_gpu.py."""
 import ctypes as C
 import json
 import os

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
                                                   ("thermal", "quad", 2), ("thermal", "tetra", 1),
                                                   ("neohooke", "tetra", 1), ("neohooke", "quad", 2),
                                                   ("stvenant", "hexahedron", 2)])
-@pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("float32", 2e-5)])
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-12), ("float32", 1e-4)])
 def test_elements_energies(physics, etype, num_gp, dtype, tol):
     mesh = gh.make_mesh(etype, 4, seed=6)
     extra = {"beta": 2.0, "c": 4.0} if physics == "thermal" else {"body_foce": [0.2, -0.4, 0.7][:3 if etype in ("hexahedron", "tetra") else 2]}

@@ -61,7 +61,7 @@ CLASSES = {("neohooke_ad", "hexahedron"): nh_ad.NeoHookeMechanicalLoss3DHexa, ("
 
 @pytest.mark.parametrize("law", ["neohooke_ad", "stvenant_ad"])
 @pytest.mark.parametrize("etype", ["hexahedron", "tetra", "quad", "triangle"])
-@pytest.mark.parametrize("dtype,tol", [("float64", 1e-11), ("float32", 5e-5)])
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-11), ("float32", 2e-4)])
 def test_mesh_assembly_against_oracle(law, etype, dtype, tol):
     mesh = gh.make_mesh(etype, 3, perturb=0.2, seed=4)
     dofs = gh.dofs_of("mechanical", etype)
