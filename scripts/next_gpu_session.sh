@@ -12,6 +12,8 @@ python -m pytest tests -m gpu -q -x > gpurun_out/all_tests.log 2>&1
 echo "all tests rc=$?"; tail -3 gpurun_out/all_tests.log
 N=${N:-128} python scripts/solver_bench.py > gpurun_out/solver_bench.json 2> gpurun_out/solver_bench.err
 echo "solver bench rc=$?"; cat gpurun_out/solver_bench.json
+N=${NT:-70} python scripts/newton_bench.py > gpurun_out/newton_bench.json 2> gpurun_out/newton_bench.err
+echo "newton bench rc=$?"; cat gpurun_out/newton_bench.json
 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench.err
 echo "bench rc=$?"; cut -c1-600 gpurun_out/bench_n1.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/solver_launches.csv \
