@@ -260,6 +260,26 @@ def allreduce_gradients(parameters, group=None, bucket_bytes=64 << 20):
     flush()
 
 
+def allreduce_loss_statistics(mean, stats, group=None):
+    """Global (mean, (min, max, mean)) of `ComputeBatchLoss` when the samples are sharded evenly over the ranks
+    (fe_loss.py:262 takes them over the whole batch): two tiny collectives on a packed 3-vector -- SUM for the mean,
+    MAX for (-min, max).  Returns detached device scalars; the differentiable local mean stays the one to call
+    `.backward()` on (its gradient, divided by the world size by `allreduce_gradients`' caller or summed as is, is
+    the caller's choice of normalisation)."""
+    mn, mx, _ = stats
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        m = mean.detach()
+        return m, (mn.detach(), mx.detach(), m)
+    world = dist.get_world_size(group)
+    packed = torch.stack([mean.detach(), -mn.detach(), mx.detach()]).contiguous()
+    total = packed[:1].clone()
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    ext = packed[1:].clone()
+    dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=group)
+    m = total[0] / world
+    return m, (-ext[0], ext[1], m)
+
+
 def shard_batch(n_samples, rank, world):
     """Contiguous, even split of the sample axis (the reference's P('data') sharding)."""
     if n_samples % world:

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from folax_b200.distributed import SlabPartition, allreduce_gradients, shard_batch
+from folax_b200.distributed import SlabPartition, allreduce_gradients, allreduce_loss_statistics, shard_batch
 
 
 def _free_port():
@@ -100,6 +100,29 @@ def test_data_parallel_gradient_allreduce():
     for rank in range(world):
         for g, p in zip(out[rank], net.parameters()):
             np.testing.assert_allclose(g, p.grad.numpy(), atol=1e-14)
+
+
+def _stats_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        E = torch.tensor([3.0, -1.0, 4.0, 1.5, 9.0, 2.5], dtype=torch.float64)[shard_batch(6, rank, world)]
+        mean, (mn, mx, mean2) = allreduce_loss_statistics(E.mean(), (E.min(), E.max(), E.mean()))
+        out[rank] = (float(mean), float(mn), float(mx), float(mean2))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_loss_statistics_over_ranks():
+    """(mean, (min, max, mean)) of fe_loss.py:262 over a batch sharded on 2 ranks."""
+    world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_stats_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    E = np.array([3.0, -1.0, 4.0, 1.5, 9.0, 2.5])
+    for rank in range(world):
+        assert np.allclose(out[rank], (E.mean(), E.min(), E.max(), E.mean()), rtol=0, atol=1e-15)
+    m, (mn, mx, m2) = allreduce_loss_statistics(torch.tensor(2.0), (torch.tensor(1.0), torch.tensor(3.0), torch.tensor(2.0)))
+    assert (float(m), float(mn), float(mx), float(m2)) == (2.0, 1.0, 3.0, 2.0)        # single process: pass-through
 
 
 def test_shard_batch():
