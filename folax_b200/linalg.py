@@ -50,13 +50,51 @@ class SellOperator:
                             shape=(self.n, self.n))
 
 
+class SlabOperator:
+    """The Jacobian of a slab-partitioned mesh (distributed.SlabPartition: one process per GPU, contiguous element
+    slabs along z) as ONE operator: every rank holds the SELL matrix of its own elements, so its local product
+    carries partial sums on the two interface node planes; the neighbour exchange that completes the residual
+    (`SlabPartition.halo_sum`, or the NVLink peer path) completes the product too.  Vectors are stored per rank with
+    both interface planes, identical on the two ranks that share them; dot products count each shared dof once
+    (the rank below owns the plane) and are summed with one all-reduce per read.  The Dirichlet treatment (rows
+    zeroed, diagonal kept per element, fe_loss.py:191-207) is element-local, so the summed rows equal those of
+    the undivided mesh."""
+
+    def __init__(self, loss, jacobian, part, group=None):
+        self.local = SellOperator(loss, jacobian)
+        self.loss, self.part, self.group, self.n = loss, part, group, self.local.n
+        d = loss.number_dofs_per_node
+        w = torch.ones(self.n, dtype=loss.dtype, device=loss.device)
+        if part.world > 1 and part.rank > 0:
+            w[:part.plane_nodes * d] = 0                 # the lower plane is owned by the rank below
+        self.weights = w
+
+    def matvec(self, x, out=None):
+        out = self.local.matvec(x, out)
+        self.part.halo_sum(out, self.loss.number_dofs_per_node, self.group)
+        return out
+
+    def diagonal(self):
+        diag = self.local.diagonal()
+        self.part.halo_sum(diag, self.loss.number_dofs_per_node, self.group)
+        return diag
+
+    def vectors(self, n):
+        return _Vectors(self.loss._dt, n, self.loss.dtype, self.loss.device, weights=self.weights, group=self.group)
+
+
 class _Vectors:
     """Vector updates and dot products of one solve, through the C ABI."""
 
-    def __init__(self, dt, n, dtype, device):
+    def __init__(self, dt, n, dtype, device, weights=None, group=None):
+        """weights / group: slab-partitioned vectors (SlabOperator) -- every interface dof lives on two ranks, the
+        weights (1 on owned dofs, 0 on the copies) make each dof count once, and `read` sums the ranks' partial
+        dot products with one all-reduce."""
         self.lib, self.dt, self.n = _lib.load(), dt, n
         self.work = torch.empty(int(self.lib.fol_dot_work_size()), dtype=dtype, device=device)
         self.slots = torch.zeros(4, dtype=dtype, device=device)
+        self.weights, self.group = weights, group
+        self.tmp = torch.empty(n, dtype=dtype, device=device) if weights is not None else None
 
     def axpby(self, a, x, b, y, out):
         _lib.check(self.lib.fol_vec_op(_lib.stream_ptr(), self.dt, 0, self.n, float(a), _lib.ptr(x), float(b),
@@ -69,10 +107,18 @@ class _Vectors:
         return out
 
     def dot_into(self, x, y, slot):
+        if self.weights is not None:                    # count every shared dof once
+            _lib.check(self.lib.fol_vec_op(_lib.stream_ptr(), self.dt, 1, self.n, 1.0, _lib.ptr(x), 0.0,
+                                           _lib.ptr(self.weights), _lib.ptr(self.tmp)))
+            x = self.tmp
         _lib.check(self.lib.fol_dot(_lib.stream_ptr(), self.dt, self.n, _lib.ptr(x), _lib.ptr(y), _lib.ptr(self.work),
                                     self.slots.data_ptr() + slot * self.slots.element_size()))
 
     def read(self, count=1):
+        if self.weights is not None:
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                dist.all_reduce(self.slots, op=dist.ReduceOp.SUM, group=self.group)
         vals = self.slots[:count].tolist()             # one device -> host read for `count` scalars
         return vals[0] if count == 1 else vals
 
@@ -95,7 +141,7 @@ def bicgstab(A, b, x0=None, tol=1e-5, atol=0.0, maxiter=None, M_diagonal=None):
     Returns (x, info): info = number of iterations, or -10 / -11 on a rho / (alpha, omega) break-down."""
     L = A.loss
     n = b.numel()
-    v = _Vectors(L._dt, n, L.dtype, L.device)
+    v = A.vectors(n) if hasattr(A, "vectors") else _Vectors(L._dt, n, L.dtype, L.device)
     if maxiter is None:
         maxiter = 10 * n
     new = lambda: torch.empty_like(b)

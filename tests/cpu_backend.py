@@ -159,6 +159,19 @@ def fake_loss(physics, element_type, num_gp, coords, conn, node_sets, ordered_do
     return L
 
 
+def install_globally(loss, shim_lib):
+    """The same routing without pytest's monkeypatch -- for spawned worker processes (gloo tests), which end with
+    the test and need no clean-up."""
+    fake = FakeLib(shim_lib, loss._ne, loss._nnode)
+    _lib.load = lambda: fake
+    _lib.check = lambda rc: (_ for _ in ()).throw(RuntimeError(rc)) if rc else None
+    _lib.stream_ptr = lambda: 0
+    _lib.ptr = lambda t: None if t is None else t.data_ptr()
+    _lib.to_device = (lambda x, dtype, device=None: torch.as_tensor(np.asarray(x)).to(dtype).contiguous()
+                      if not isinstance(x, torch.Tensor) else x.to(dtype).contiguous())
+    return fake
+
+
 @pytest.fixture()
 def cpu_backend(monkeypatch, shim):
     """install(loss) -> FakeLib: routes folax_b200._lib to the stand-ins for the duration of one test."""
