@@ -1,31 +1,19 @@
-"""Loss ABC: the same contract as fol/loss_functions/loss.py:9-62."""
-from abc import ABC, abstractmethod
+"""What every loss provides (the contract of fol/loss_functions/loss.py:9-62): a name, `Initialize` / `Finalize`,
+`GetFullDofVector(known_dofs, unknown_dofs)`, `GetNumberOfUnknowns()` and `ComputeBatchLoss(batch_params, batch_dofs)`."""
 
 
-class Loss(ABC):
+class Loss:
+    _required = ("Initialize", "GetFullDofVector", "GetNumberOfUnknowns", "ComputeBatchLoss", "Finalize")
+
     def __init__(self, loss_name: str) -> None:
-        self.__name = loss_name
         self.initialized = False
+        self._loss_name = loss_name
 
     def GetName(self) -> str:
-        return self.__name
+        return self._loss_name
 
-    @abstractmethod
-    def Initialize(self) -> None:
-        pass
-
-    @abstractmethod
-    def GetFullDofVector(self, known_dofs, unknown_dofs):
-        pass
-
-    @abstractmethod
-    def GetNumberOfUnknowns(self) -> int:
-        pass
-
-    @abstractmethod
-    def ComputeBatchLoss(self) -> None:
-        pass
-
-    @abstractmethod
-    def Finalize(self) -> None:
-        pass
+    def __new__(cls, *args, **kwargs):
+        missing = [m for m in Loss._required if not callable(getattr(cls, m, None))]
+        if missing:
+            raise TypeError(f"Can't instantiate {cls.__name__}: it does not define {', '.join(missing)}")
+        return super().__new__(cls)
