@@ -58,6 +58,7 @@ SIGNATURES = {
     "fol_sum": (_int, [_vp, _int, _i64, _vp, _vp]),
     "fol_gather_values": (_int, [_vp, _int, _i64, _i32p, _vp, _vp]),
     "fol_sell_spmv": (_int, [_vp, _int, _i64, _vp, _i32p, _vp, _vp, _vp]),
+    "fol_sell_spmv_block": (_int, [_vp, _int, _int, _i64, _vp, _i32p, _vp, _vp, _vp]),
     "fol_vec_op": (_int, [_vp, _int, _int, _i64, _dbl, _vp, _dbl, _vp, _vp]),
     "fol_dot_work_size": (_i64, []),
     "fol_dot": (_int, [_vp, _int, _i64, _vp, _vp, _vp, _vp]),

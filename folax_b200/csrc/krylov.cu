@@ -1,6 +1,7 @@
 // Kernels + C ABI of the GPU linear algebra behind folax_b200/solvers: what replaces the host round trip of
 // fe_solver.py:60-103 (BCOO -> scipy CSR -> solve) once the Jacobian is assembled on the device.
 //   fol_sell_spmv      y = A x on the sliced-ELLPACK layout (one thread per row, coalesced, deterministic)
+//   fol_sell_spmv_block  the same with one column index per run of D dofs of a neighbour node (8 + 4/D B per entry)
 //   fol_gather_values  value permutation (CSR -> SELL, CSR -> diagonal)
 //   fol_vec_op         a x + b y | a x*y | a x/y
 //   fol_dot            x . y with a fixed two-stage reduction tree (deterministic, no atomics)
@@ -14,6 +15,12 @@ template <class T>
 __global__ void __launch_bounds__(128) sell_spmv_kernel(const SellArgs<T> a) {
   const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (row < a.nrows) sell_spmv_thread<T>(row, a);
+}
+
+template <class T, int D>
+__global__ void __launch_bounds__(128) sell_spmv_block_kernel(const BlockSellArgs<T> a) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row < a.nrows) sell_spmv_block_thread<T, D>(row, a);
 }
 
 template <class T>
@@ -93,6 +100,27 @@ int fol_sell_spmv(fol_stream_t s, int dtype, int64_t nrows, const int64_t* slice
     return fail(FOL_ERR_INVALID, "fol_sell_spmv: unknown dtype");
   }
   return check_launch("sell_spmv_kernel");
+}
+
+int fol_sell_spmv_block(fol_stream_t s, int dtype, int dofs_per_node, int64_t nrows, const int64_t* slice_ptr,
+                        const int32_t* node_cols, const void* vals, const void* x, void* y) {
+  FOL_REQUIRE(nrows >= 0 && slice_ptr && node_cols && vals && x && y, "fol_sell_spmv_block: null pointer / negative size");
+  FOL_REQUIRE(x != y, "fol_sell_spmv_block: x and y must not alias");
+  FOL_REQUIRE(dofs_per_node == 2 || dofs_per_node == 3, "fol_sell_spmv_block: dofs_per_node must be 2 or 3");
+  FOL_REQUIRE(dtype == FOL_F64 || dtype == FOL_F32, "fol_sell_spmv_block: unknown dtype");
+  if (nrows == 0) return FOL_OK;
+  const unsigned grid = (unsigned)cdiv(nrows, 128);
+  cudaStream_t st = (cudaStream_t)s;
+  if (dtype == FOL_F64) {
+    BlockSellArgs<double> a{(const long long*)slice_ptr, node_cols, (const double*)vals, (const double*)x, (double*)y, nrows};
+    if (dofs_per_node == 3) sell_spmv_block_kernel<double, 3><<<grid, 128, 0, st>>>(a);
+    else sell_spmv_block_kernel<double, 2><<<grid, 128, 0, st>>>(a);
+  } else {
+    BlockSellArgs<float> a{(const long long*)slice_ptr, node_cols, (const float*)vals, (const float*)x, (float*)y, nrows};
+    if (dofs_per_node == 3) sell_spmv_block_kernel<float, 3><<<grid, 128, 0, st>>>(a);
+    else sell_spmv_block_kernel<float, 2><<<grid, 128, 0, st>>>(a);
+  }
+  return check_launch("sell_spmv_block_kernel");
 }
 
 int fol_gather_values(fol_stream_t s, int dtype, int64_t n, const int32_t* src_index, const void* src, void* dst) {

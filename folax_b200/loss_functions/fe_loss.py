@@ -411,7 +411,7 @@ class FiniteElementLoss(Loss):
         if self.__dict__.get("_splan") is None:
             from .. import sell_plan
             cp = self._csr_plan()
-            plan = sell_plan.build(cp["indptr"].cpu().numpy(), cp["indices"].cpu().numpy())
+            plan = sell_plan.build(cp["indptr"].cpu().numpy(), cp["indices"].cpu().numpy(), self.number_dofs_per_node)
             self._splan = {k: (torch.as_tensor(v, device=self.device) if isinstance(v, np.ndarray) else v)
                            for k, v in plan.items()}
         return self._splan

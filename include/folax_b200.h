@@ -251,6 +251,12 @@ int fol_gather_values(fol_stream_t s, int dtype, int64_t n, const int32_t* src_i
 /* y = A x, one thread per row, per-row sums in CSR order (deterministic); x and y must not alias */
 int fol_sell_spmv(fol_stream_t s, int dtype, int64_t nrows, const int64_t* slice_ptr, const int32_t* cols,
                   const void* vals, const void* x, void* y);
+/* The same product for Jacobians with d = 2 or 3 dofs per node whose rows consist of runs of d consecutive dofs of a
+ * neighbour node (what folax_b200/csr_plan.py builds): node_cols holds ONE node index per run -- at
+ * slice_ptr[r/32]/d + q*32 + r%32 for run q of row r -- so a stored entry costs 8 + 4/d bytes instead of 12.  Same
+ * values array, same summation order, bit-identical result. */
+int fol_sell_spmv_block(fol_stream_t s, int dtype, int dofs_per_node, int64_t nrows, const int64_t* slice_ptr,
+                        const int32_t* node_cols, const void* vals, const void* x, void* y);
 /* op 0: out = a x + b y (y may be NULL when b == 0)   op 1: out = a x*y   op 2: out = a x/y;  out may alias x or y */
 int fol_vec_op(fol_stream_t s, int dtype, int op, int64_t n, double a, const void* x, double b, const void* y,
                void* out);

@@ -50,8 +50,12 @@ out["csr_values_ms"] = timeit(lambda: loss.JacobianToCSR(jac), steps=5)
 A = linalg.SellOperator(loss, jac)
 y = torch.empty_like(v)
 out["sell_spmv_ms"] = timeit(lambda: A.matvec(v, y), steps=20)
-bytes_spmv = 12.0 * sp["total"] + 16.0 * sp["nrows"]
+bytes_spmv = (8.0 + 4.0 / 3.0) * sp["total"] + 16.0 * sp["nrows"]          # block-column kernel, d = 3
 out["sell_spmv_gbs"] = bytes_spmv / (out["sell_spmv_ms"] * 1e-3) / 1e9
+A.use_block_kernel = False
+out["sell_spmv_scalar_columns_ms"] = timeit(lambda: A.matvec(v, y), steps=20)
+out["sell_spmv_scalar_columns_gbs"] = (12.0 * sp["total"] + 16.0 * sp["nrows"]) / (out["sell_spmv_scalar_columns_ms"] * 1e-3) / 1e9
+A.use_block_kernel = True
 out["apply_jacobian_ms"] = timeit(lambda: loss.ApplyJacobian(K, u, v))
 vec = linalg._Vectors(loss._dt, v.numel(), loss.dtype, loss.device)
 out["dot_ms"] = timeit(lambda: vec.dot_into(v, y, 0), steps=20)

@@ -91,6 +91,12 @@ class FakeLib:
         assert x != y
         return self.shim.host_sell_spmv(C.c_longlong(nrows), *map(C.c_void_p, (slice_ptr, cols, vals, x, y)))
 
+    def fol_sell_spmv_block(self, s, dt, d, nrows, slice_ptr, node_cols, vals, x, y):
+        self._count("sell_spmv")
+        self._count("sell_spmv_block")
+        assert x != y
+        return self.shim.host_sell_spmv_block(d, C.c_longlong(nrows), *map(C.c_void_p, (slice_ptr, node_cols, vals, x, y)))
+
     def fol_vec_op(self, s, dt, op, n, a, x, b, y, out):
         self._count("vec_op")
         return self.shim.host_vec_op(op, C.c_longlong(n), C.c_double(a), C.c_void_p(x), C.c_double(b), C.c_void_p(y),
@@ -148,7 +154,7 @@ def fake_loss(physics, element_type, num_gp, coords, conn, node_sets, ordered_do
 
     def splan():
         if getattr(L, "_splan", None) is None:
-            plan = sell_plan.build(*L._csr_structure)
+            plan = sell_plan.build(*L._csr_structure, L.number_dofs_per_node)
             L._splan = {k: (torch.as_tensor(v) if isinstance(v, np.ndarray) else v) for k, v in plan.items()}
         return L._splan
 

@@ -13,6 +13,16 @@ int host_sell_spmv(long long nrows, const long long* slice_ptr, const int32_t* c
   return 0;
 }
 
+int host_sell_spmv_block(int d, long long nrows, const long long* slice_ptr, const int32_t* node_cols, const double* vals,
+                         const double* x, double* y) {
+  BlockSellArgs<double> a{slice_ptr, node_cols, vals, x, y, nrows};
+  for (long long r = 0; r < nrows; ++r) {
+    if (d == 3) sell_spmv_block_thread<double, 3>(r, a);
+    else sell_spmv_block_thread<double, 2>(r, a);
+  }
+  return 0;
+}
+
 int host_gather_values(long long n, const int32_t* src_index, const double* src, double* dst) {
   for (long long i = 0; i < n; ++i) gather_values_thread<double>(i, src_index, src, dst);
   return 0;

@@ -61,6 +61,30 @@ def test_sell_plan_and_spmv_on_a_fe_matrix(shim):  # noqa: F811
     diag = np.zeros(3 * nn)
     assert shim.host_gather_values(C.c_longlong(3 * nn), p(plan["diag_src"]), p(A.data), p(diag)) == 0
     assert np.array_equal(diag, A.diagonal())
+    # block variant: one node index per run of 3 dofs, same values array, bit-identical product
+    bplan = sell_plan.build(A.indptr, A.indices, 3)
+    assert bplan["node_cols"] is not None and bplan["node_cols"].size * 3 == bplan["total"]
+    yb = np.full(3 * nn, np.nan)
+    assert shim.host_sell_spmv_block(3, C.c_longlong(bplan["nrows"]), p(bplan["slice_ptr"]), p(bplan["node_cols"]), p(vals),
+                                     p(x), p(yb)) == 0
+    assert np.array_equal(yb, y)
+    # a structure that does not consist of whole runs is refused by the plan (falls back to the scalar kernel)
+    B = sp.csr_array(np.triu(np.ones((6, 6))))
+    assert sell_plan.build(B.indptr, B.indices, 3)["node_cols"] is None
+
+
+def test_block_kernel_is_used_and_equals_the_scalar_one(cpu_backend):  # noqa: F811
+    L = _mech_loss(6)                                            # 2 dofs per node
+    fake = cpu_backend(L)
+    K = np.random.default_rng(3).uniform(0.2, 1.0, L._nn)
+    jac, _ = L.ComputeJacobianMatrixAndResidualVector(K, L.ApplyDirichletBCOnDofVector(np.zeros(L.total_number_of_dofs)))
+    A = linalg.SellOperator(L, jac)
+    v = torch.as_tensor(np.random.default_rng(4).standard_normal(L.total_number_of_dofs))
+    y_block = A.matvec(v).clone()
+    assert fake.calls.get("sell_spmv_block", 0) == 1
+    A.use_block_kernel = False
+    y_scalar = A.matvec(v)
+    assert fake.calls["sell_spmv_block"] == 1 and torch.equal(y_block, y_scalar)
 
 
 @pytest.mark.parametrize("precond", [None, "jacobi"])

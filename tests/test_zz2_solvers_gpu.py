@@ -39,6 +39,10 @@ def test_sell_spmv_matches_scipy(dtype, tol):
     want = ref @ xt.cpu().numpy().astype(np.float64)
     assert np.abs(y.cpu().numpy() - want).max() <= tol * np.abs(want).max()
     assert torch.equal(y, A.matvec(xt))                                   # deterministic
+    assert A.plan["node_cols"] is not None                                # 3 dofs per node: the block-column kernel ran
+    A.use_block_kernel = False
+    assert torch.equal(y, A.matvec(xt))                                   # scalar-column kernel: bit-identical
+    A.use_block_kernel = True
     assert np.array_equal(A.diagonal().cpu().numpy(), ref.diagonal().astype(y.cpu().numpy().dtype))
     # the same product without the matrix (ApplyJacobian) agrees
     y_mf = loss.ApplyJacobian(K, u, xt)
