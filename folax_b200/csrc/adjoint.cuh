@@ -391,6 +391,219 @@ __host__ __device__ inline S element_phi(const S* X, const S* de, const T* ue, c
   return phi;
 }
 
+// ---- the same sensitivities at the cost of the POINT law ---------------------------------------------------
+// phi_g depends on the geometry only through grad u, grad lam and w detJ, so the chain rule splits into the closed-form
+// geometric part used above for linear elasticity (d detJ = detJ tr W, d grad v = -(grad v) W) and the derivative of the
+// point function f(Gu, Gl) w.r.t. its two gradients:  with  Au = df/dGu,  Al = df/dGl,  M = Gu^T Au + Gl^T Al
+//     d phi/d x_bk = w detJ [ (f - b.(N lam)) dN_b/dx_k - (M grad N_b)_k ],      d phi/d de_a = w detJ N_a df/d(N.de).
+// Finite strain (f = S(F):(F^T Gl), linear in the modulus N.de): Al = F S in closed form, Au by dim^2 dual-number
+// evaluations of the POINT function -- instead of A*dim + A sweeps over the whole element (same result to rounding;
+// the element-sweep version stays as the cross-check of the tests).
+
+// f at unit modulus for finite strain; also returns F and S (unit modulus) when asked (value evaluation)
+template <class S, class T, int D, int PHYS>
+__host__ __device__ inline S finite_strain_point_f(const S (&Gu)[D][D], const T (&Gl)[D][D], T nu, S (*Fout)[D],
+                                                   S (*Sout)[D]) {
+  S F[D][D], C[D][D], Sm[D][D];
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) F[i][j] = Gu[i][j] + (i == j ? S(1) : S(0));
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) {
+      S acc = S(0);
+      for (int m = 0; m < D; ++m) acc += F[m][i] * F[m][j];
+      C[i][j] = acc;
+    }
+  const T mu = (T)1 / ((T)2 * ((T)1 + nu));
+  if constexpr (PHYS == ADJ_NEOHOOKE) {
+    S iC[D][D];
+    inv_sym_small<S, D>(C, iC);
+    const S J = det_small<S, D>(F);
+    S trC = S(0);
+    for (int i = 0; i < D; ++i) trC += C[i][i];
+    const T kk = (T)1 / ((T)3 * ((T)1 - (T)2 * nu));
+    const S p = S((T)0.5 * kk) * (J - S(1) / J);
+    const S Jm = (D == 2) ? S(1) / J : fol_pow(J, -2.0 / 3.0);
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < D; ++j)
+        Sm[i][j] = J * p * iC[i][j] + Jm * S(mu) * ((i == j ? S(1) : S(0)) - trC * iC[i][j] / S((T)D));
+  } else {
+    const T lam = nu / (((T)1 + nu) * ((T)1 - (T)2 * nu));
+    S trE = S(0);
+    for (int i = 0; i < D; ++i) trE += S(0.5) * (C[i][i] - S(1));
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < D; ++j)
+        Sm[i][j] = (i == j ? S(lam) * trE : S(0)) + S(mu) * (C[i][j] - (i == j ? S(1) : S(0)));
+  }
+  S f = S(0);
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) {
+      S ftl = S(0);
+      for (int c = 0; c < D; ++c) ftl += F[c][i] * S(Gl[c][j]);
+      f += Sm[i][j] * ftl;
+      if (Fout) Fout[i][j] = F[i][j];
+      if (Sout) Sout[i][j] = Sm[i][j];
+    }
+  return f;
+}
+
+template <class T, int ELEM, int ORDER, int PHYS>
+__host__ __device__ inline void residual_adjoint_element_point(const T* X, const T* de, const T* ue, const T* le,
+                                                               const T* aux, const Params<T>& P, T* dK, T* dX) {
+  constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM), NGP = elem_ngauss(ELEM, ORDER);
+  for (int a = 0; a < A; ++a) dK[a] = (T)0;
+  for (int i = 0; i < A * 3; ++i) dX[i] = (T)0;
+  for (int g = 0; g < NGP; ++g) {
+    double xi[3], w;
+    gauss_point<ELEM, ORDER>(g, xi, w);
+    T N[A], dN[A][D];
+    shape_functions<ELEM, T>(xi, N, dN);
+    T eg = (T)0;
+    for (int b = 0; b < A; ++b) eg += N[b] * de[b];
+    if constexpr (PHYS == ADJ_NEOHOOKE || PHYS == ADJ_STVK) {
+      T gN[A][D];
+      const T wd = (T)w * global_gradients<ELEM, T, false>(X, dN, gN);
+      T Gu[D][D], Gl[D][D], bl = (T)0;
+      for (int i = 0; i < D; ++i) {
+        T lgi = (T)0;
+        for (int b = 0; b < A; ++b) lgi += N[b] * le[b * D + i];
+        bl += P.v[2 + i] * lgi;
+        for (int j = 0; j < D; ++j) {
+          T su = (T)0, sl = (T)0;
+          for (int b = 0; b < A; ++b) {
+            su += gN[b][j] * ue[b * D + i];
+            sl += gN[b][j] * le[b * D + i];
+          }
+          Gu[i][j] = su;
+          Gl[i][j] = sl;
+        }
+      }
+      T F[D][D], Sm[D][D];
+      const T f1 = finite_strain_point_f<T, T, D, PHYS>(Gu, Gl, P.v[1], F, Sm);
+      T Au[D][D], Al[D][D];
+      for (int c = 0; c < D; ++c)                       // Al = F S (closed form)
+        for (int j = 0; j < D; ++j) {
+          T acc = (T)0;
+          for (int i = 0; i < D; ++i) acc += F[c][i] * Sm[i][j];
+          Al[c][j] = acc;
+        }
+      {                                                 // Au = df/dGu: dim^2 forward sweeps of the point function
+        using S = Dual<T>;
+        S Gd[D][D];
+        for (int i = 0; i < D; ++i)
+          for (int j = 0; j < D; ++j) Gd[i][j] = S(Gu[i][j], (T)0);
+        for (int i = 0; i < D; ++i)
+          for (int j = 0; j < D; ++j) {
+            Gd[i][j].d = (T)1;
+            Au[i][j] = finite_strain_point_f<S, T, D, PHYS>(Gd, Gl, P.v[1], nullptr, nullptr).d;
+            Gd[i][j].d = (T)0;
+          }
+      }
+      T M[D][D];
+      for (int k = 0; k < D; ++k)
+        for (int j = 0; j < D; ++j) {
+          T acc = (T)0;
+          for (int i = 0; i < D; ++i) acc += Gu[i][k] * Au[i][j] + Gl[i][k] * Al[i][j];
+          M[k][j] = eg * acc;
+        }
+      const T val = eg * f1 - bl;
+      for (int b = 0; b < A; ++b) {
+        dK[b] += wd * N[b] * f1;
+        for (int k = 0; k < D; ++k) {
+          T mg = (T)0;
+          for (int j = 0; j < D; ++j) mg += M[k][j] * gN[b][j];
+          dX[b * 3 + k] += wd * (val * gN[b][k] - mg);
+        }
+      }
+    } else {
+      // implicit-Euler scalar losses: phi_g = w detJ [c1(f_n, f_c) (N lam) + c2(f_n) gl.gf] with the gradient convention
+      // of transient_thermal.py:57-58 / phase_field.py:47-48, gT_a = inv(J) dN_a (J^-1 un-transposed).  For that
+      // convention  d gT_a[k] / d x_bm = -inv[k][m] (dN_b . gT_a),  while d detJ / d x_bm = detJ (dN_b inv)[m].
+      T J[D][D];
+      for (int i = 0; i < D; ++i)
+        for (int j = 0; j < D; ++j) {
+          T acc = (T)0;
+          for (int a = 0; a < A; ++a) acc += X[a * 3 + i] * dN[a][j];
+          J[i][j] = acc;
+        }
+      T inv[D][D];
+      const T det = det_small<T, D>(J);
+      {
+        const T r = (T)1 / det;
+        if constexpr (D == 2) {
+          inv[0][0] = J[1][1] * r; inv[0][1] = -J[0][1] * r; inv[1][0] = -J[1][0] * r; inv[1][1] = J[0][0] * r;
+        } else {
+          inv[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * r;
+          inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * r;
+          inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * r;
+          inv[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) * r;
+          inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * r;
+          inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * r;
+          inv[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * r;
+          inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * r;
+          inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * r;
+        }
+      }
+      const T wd = (T)w * det;
+      T fn = (T)0, lg = (T)0, kg = (T)0, gf[D], gl[D];
+      for (int b = 0; b < A; ++b) {
+        fn += N[b] * ue[b];
+        lg += N[b] * le[b];
+        if (aux) kg += N[b] * aux[b];
+      }
+      for (int k = 0; k < D; ++k) {
+        T sf = (T)0, sl = (T)0;
+        for (int b = 0; b < A; ++b) {
+          T gt = (T)0;                                   // gT_b[k] = sum_j dN_b[j] inv[k][j]
+          for (int j = 0; j < D; ++j) gt += dN[b][j] * inv[k][j];
+          sf += gt * ue[b];
+          sl += gt * le[b];
+        }
+        gf[k] = sf;
+        gl[k] = sl;
+      }
+      T q = (T)0;
+      for (int k = 0; k < D; ++k) q += gf[k] * gl[k];
+      const T dt = P.v[10];
+      T c1, c2, dc1;                                     // dc1 = d c1 / d(N.de)
+      if constexpr (PHYS == ADJ_TTHERMAL) {
+        const T beta = P.v[5], rcp = P.v[8] * P.v[9];
+        c1 = rcp * (fn - eg);
+        dc1 = -rcp;
+        c2 = dt * kg * ((T)1 + ((beta != (T)0) ? beta * fol_pow(fn, (double)P.v[6]) : (T)0));
+      } else {
+        const T ie2 = (T)1 / (P.v[11] * P.v[11]);
+        c1 = (fn - eg) + dt * ie2 * (fn * fn - (T)1) * fn;
+        dc1 = (T)-1;
+        c2 = dt;
+      }
+      const T val = c1 * lg + c2 * q;
+      T il[D], jf[D];                                    // (inv^T gl)_m, (inv^T gf)_m
+      for (int m = 0; m < D; ++m) {
+        T a1 = (T)0, a2 = (T)0;
+        for (int k = 0; k < D; ++k) {
+          a1 += gl[k] * inv[k][m];
+          a2 += gf[k] * inv[k][m];
+        }
+        il[m] = a1;
+        jf[m] = a2;
+      }
+      for (int b = 0; b < A; ++b) {
+        dK[b] += wd * N[b] * dc1 * lg;
+        T df = (T)0, dl = (T)0;                          // dN_b . gf, dN_b . gl
+        for (int n = 0; n < D; ++n) {
+          df += dN[b][n] * gf[n];
+          dl += dN[b][n] * gl[n];
+        }
+        for (int m = 0; m < D; ++m) {
+          T gstd = (T)0;                                 // standard gradient (dN_b inv)[m]: d detJ / d x_bm = detJ * it
+          for (int j = 0; j < D; ++j) gstd += dN[b][j] * inv[j][m];
+          dX[b * 3 + m] += wd * (val * gstd - c2 * (il[m] * df + jf[m] * dl));
+        }
+      }
+    }
+  }
+}
+
 // Element energy, the first return value of ComputeElement (fe_loss.py:149-176: ComputeElementsEnergies):
 //   mechanical.py:116-117 / thermal.py:45-49   u^T (Ke u - Fe)                  (= phi with lam = u)
 //   mechanical_neohooke.py:262, 271            sum_g w detJ psi,  psi of neo_hooke.py:14-58 / 64-109

@@ -99,8 +99,8 @@ __host__ __device__ inline void residual_adjoint_thread(long long e, const Adjoi
   T dK[A], dX[A * 3];
   if constexpr (PHYS == ADJ_MECH || PHYS == ADJ_THERMAL)
     residual_adjoint_element<T, ELEM, ORDER, PHYS>(X, de, ue, le, a.p, dK, dX);          // closed forms
-  else
-    residual_adjoint_element_dual<T, ELEM, ORDER, PHYS>(X, de, ue, le, a.aux ? ax : nullptr, a.p, dK, dX);
+  else   // point-law route (closed-form geometry + dim^2 dual sweeps of the point function where needed)
+    residual_adjoint_element_point<T, ELEM, ORDER, PHYS>(X, de, ue, le, a.aux ? ax : nullptr, a.p, dK, dX);
   if (a.dk)
     for (int b = 0; b < A; ++b) {
       T* o = a.dk + e * A + b;
@@ -129,22 +129,24 @@ __host__ __device__ inline void element_energy_thread(long long e, const Adjoint
   a.dk[e] = element_energy<T, ELEM, ORDER, PHYS>(X, de, ue, a.aux ? ax : nullptr, a.p);
 }
 
-// the forward-mode route on a physics that also has a closed form (test cross-check only)
+// the whole-element forward-mode sweeps (A*dim + A directions): the cross-check of the tests for every physics
 template <class T, int ELEM, int ORDER, int PHYS>
 __host__ __device__ inline void residual_adjoint_dual_reference_thread(long long e, const AdjointArgs<T>& a) {
   constexpr int A = elem_nnode(ELEM), D = elem_dim(ELEM);
-  constexpr int DPN = (PHYS == ADJ_THERMAL) ? 1 : D;
-  T X[A * 3], de[A], ue[A * DPN], le[A * DPN];
+  constexpr int DPN = (PHYS == ADJ_THERMAL || PHYS == ADJ_TTHERMAL || PHYS == ADJ_ALLENCAHN) ? 1 : D;
+  T X[A * 3], de[A], ue[A * DPN], le[A * DPN], ax[A];
   for (int b = 0; b < A; ++b) {
     const long long n = a.conn[e * A + b];
     for (int k = 0; k < 3; ++k) X[b * 3 + k] = a.xyz[n * 3 + k];
     de[b] = a.ctrl[n];
+    ax[b] = a.aux ? a.aux[n] : (T)0;
     for (int k = 0; k < DPN; ++k) {
       ue[b * DPN + k] = a.u[n * DPN + k];
       le[b * DPN + k] = a.lam[n * DPN + k];
     }
   }
-  residual_adjoint_element_dual<T, ELEM, ORDER, PHYS>(X, de, ue, le, nullptr, a.p, a.dk + e * A, a.dx + e * (A * 3));
+  residual_adjoint_element_dual<T, ELEM, ORDER, PHYS>(X, de, ue, le, a.aux ? ax : nullptr, a.p, a.dk + e * A,
+                                                      a.dx + e * (A * 3));
 }
 
 }  // namespace fol

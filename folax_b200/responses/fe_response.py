@@ -11,8 +11,9 @@ order, no atomics).  The formula is the caller's Python expression, exactly as i
 pointwise over the (ne, g) Gauss-point arrays on the device, and its partials df/dK, df/dU come from one
 torch.autograd.grad over those arrays (the reference uses jax.grad for the same purpose).  No CPU fallback.
 
-Residual sensitivities: closed forms for the mechanical and thermal loss families, forward-mode sweeps for
-Neo-Hooke, St-Venant, transient thermal and Allen-Cahn; the history-dependent J2 loss raises FolaxError.
+Residual sensitivities: closed forms for the mechanical, thermal, transient-thermal and Allen-Cahn families,
+closed-form geometry + dual-number derivatives of the point law for Neo-Hooke and St-Venant; the history-dependent J2
+loss raises FolaxError.
 """
 import math
 

@@ -220,10 +220,10 @@ int fol_response_elements(fol_stream_t s, int dtype, int element, int num_gp, in
 
 /* dk_elem[e, a] (+)= adj_e^T d re/d ctrl_a,  dx_elem[e, a*3+k] (+)= adj_e^T d re/d x_ak, re = the element
  * residual of ComputeElement BEFORE the Dirichlet mask (fe_response.py:312-331, 424-442: jacrev there).
- * accumulate != 0 adds to the arrays (they hold the response part).  Mechanical and thermal: closed forms;
- * Neo-Hooke, St-Venant, transient thermal (aux = nodal k0, (ctrl, u) = (current, next) field) and Allen-Cahn:
- * forward-mode sweeps of the element's A*dim + A directions; J2 returns FOL_ERR_UNSUPPORTED.  aux: NULL unless
- * the physics has an auxiliary nodal field. */
+ * accumulate != 0 adds to the arrays (they hold the response part).  Mechanical, thermal, transient thermal
+ * (aux = nodal k0, (ctrl, u) = (current, next) field) and Allen-Cahn: closed forms; Neo-Hooke and St-Venant:
+ * closed-form geometry + dim^2 dual-number evaluations of the point law; J2 returns FOL_ERR_UNSUPPORTED.
+ * aux: NULL unless the physics has an auxiliary nodal field. */
 int fol_residual_adjoint_elements(fol_stream_t s, int dtype, int physics, int element, int num_gp, int accumulate,
                                   int64_t ne, const void* xyz, const int32_t* conn, const void* ctrl, const void* u,
                                   const void* adj, const void* aux, const double* params_host, void* dk_elem,

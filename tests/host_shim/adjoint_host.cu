@@ -94,18 +94,25 @@ int host_element_energies(int physics, int element, int num_gp, long long ne, co
   return -3;
 }
 
-// forward-mode route on the two physics that also have closed forms (cross-check of the two routes)
+// whole-element forward-mode sweeps for every physics (cross-check of the product routes)
 int host_residual_adjoint_dual_reference(int physics, int element, int num_gp, long long ne, const double* xyz,
                                          const int32_t* conn, const double* ctrl, const double* u, const double* lam,
-                                         const double* params, double* dk, double* dx) {
-  AdjointArgs<double> a{xyz, conn, ctrl, u, lam, nullptr, dk, dx, ne, 0, make_params<double>(params)};
-#define X(E, O)                                                                                   \
-  if (element == E && num_gp == O) {                                                              \
-    for (long long e = 0; e < ne; ++e) {                                                          \
-      if (physics == 0) residual_adjoint_dual_reference_thread<double, E, O, ADJ_MECH>(e, a);     \
-      else residual_adjoint_dual_reference_thread<double, E, O, ADJ_THERMAL>(e, a);               \
-    }                                                                                             \
-    return 0;                                                                                     \
+                                         const double* aux, const double* params, double* dk, double* dx) {
+  AdjointArgs<double> a{xyz, conn, ctrl, u, lam, aux, dk, dx, ne, 0, make_params<double>(params)};
+#define X(E, O)                                                                                        \
+  if (element == E && num_gp == O) {                                                                   \
+    for (long long e = 0; e < ne; ++e) {                                                               \
+      switch (physics) {                                                                               \
+        case 0: residual_adjoint_dual_reference_thread<double, E, O, ADJ_MECH>(e, a); break;           \
+        case 1: residual_adjoint_dual_reference_thread<double, E, O, ADJ_THERMAL>(e, a); break;        \
+        case 2: residual_adjoint_dual_reference_thread<double, E, O, ADJ_NEOHOOKE>(e, a); break;       \
+        case 4: residual_adjoint_dual_reference_thread<double, E, O, ADJ_STVK>(e, a); break;           \
+        case 5: residual_adjoint_dual_reference_thread<double, E, O, ADJ_TTHERMAL>(e, a); break;       \
+        case 6: residual_adjoint_dual_reference_thread<double, E, O, ADJ_ALLENCAHN>(e, a); break;      \
+        default: return -3;                                                                            \
+      }                                                                                                \
+    }                                                                                                  \
+    return 0;                                                                                          \
   }
   CASES(X)
 #undef X

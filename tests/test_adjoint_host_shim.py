@@ -91,19 +91,25 @@ def test_residual_adjoint_sensitivities(shim, physics, etype, num_gp):
     assert np.abs(dk2 - rK).max() <= 1e-11 * np.abs(rK).max()
 
 
-@pytest.mark.parametrize("physics", ["mechanical", "thermal"])
+@pytest.mark.parametrize("physics", list(PHYS))
 @pytest.mark.parametrize("etype,num_gp", [("hexahedron", 2), ("quad", 3), ("tetra", 2), ("triangle", 1)])
-def test_closed_forms_equal_forward_mode(shim, physics, etype, num_gp):
-    """The two differentiation routes of csrc/adjoint.cuh on the same inputs."""
+def test_product_routes_equal_whole_element_forward_mode(shim, physics, etype, num_gp):
+    """The routes the kernels use (closed forms; point-law derivatives + closed-form geometry) against the
+    whole-element dual-number sweeps of csrc/adjoint.cuh on the same inputs."""
     coords, conn, d, K, u, lam = _case(etype, physics, seed=5)
+    if physics in ("neohooke", "stvenant"):
+        u = 0.05 * (u - 0.5)
     ne, a = conn.shape
-    arr, _, _ = _params(physics, 3 if etype in ("hexahedron", "tetra") else 2)
+    arr, _, aux = _params(physics, 3 if etype in ("hexahedron", "tetra") else 2, conn, coords.shape[0])
     dk, dx, dk2, dx2 = np.zeros((ne, a)), np.zeros((ne, a * 3)), np.zeros((ne, a)), np.zeros((ne, a * 3))
     assert shim.host_residual_adjoint_elements(PHYS[physics], ELEM[etype], num_gp, 0, C.c_longlong(ne), _p(coords),
-                                               _p(conn), _p(K), _p(u), _p(lam), None, _p(arr), _p(dk), _p(dx)) == 0
+                                               _p(conn), _p(K), _p(u), _p(lam), _p(aux), _p(arr), _p(dk), _p(dx)) == 0
     assert shim.host_residual_adjoint_dual_reference(PHYS[physics], ELEM[etype], num_gp, C.c_longlong(ne), _p(coords),
-                                                     _p(conn), _p(K), _p(u), _p(lam), _p(arr), _p(dk2), _p(dx2)) == 0
-    assert np.abs(dk - dk2).max() <= 1e-12 * np.abs(dk).max() and np.abs(dx - dx2).max() <= 1e-12 * np.abs(dx).max()
+                                                     _p(conn), _p(K), _p(u), _p(lam), _p(aux), _p(arr), _p(dk2),
+                                                     _p(dx2)) == 0
+    assert np.abs(dk - dk2).max() <= 1e-12 * np.abs(dk2).max() and np.abs(dx - dx2).max() <= 1e-12 * np.abs(dx2).max()
+
+
 @pytest.mark.parametrize("etype", list(ELEM))
 @pytest.mark.parametrize("num_gp", [1, 2, 3])
 def test_gauss_interpolation_and_response(shim, etype, num_gp):
