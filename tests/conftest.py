@@ -17,3 +17,17 @@ def pytest_configure(config):
 def goldens():
     with open(os.path.join(ROOT, "tests", "golden", "reference_unit_goldens.json")) as fh:
         return json.load(fh)
+
+
+@pytest.fixture(scope="session")
+def shim():
+    """The kernels' __host__ __device__ per-thread code compiled for the CPU (tests/host_shim; built once, cached)."""
+    from tests import cpu_backend
+    return cpu_backend.build_shim()
+
+
+@pytest.fixture()
+def cpu_backend(monkeypatch, shim):
+    """install(loss) -> stand-in of the C ABI on top of the host shim (tests/cpu_backend.py), for one test."""
+    from tests import cpu_backend as cb
+    return cb.make_cpu_backend(monkeypatch, shim)

@@ -11,7 +11,6 @@ import subprocess
 import types
 
 import numpy as np
-import pytest
 import scipy.sparse as sp
 import torch
 
@@ -22,20 +21,40 @@ from oracle import assembly
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def build_shim(out_dir):
-    """nvcc -shared of the host shims (host code only is ever called)."""
+def build_shim(out_dir=None):
+    """nvcc -shared of the host shims (host code only is ever called).  The library is cached next to the sources
+    (tests/host_shim/_build, git-ignored like every .so), keyed by a hash of everything it is compiled from."""
+    import concurrent.futures as cf
+    import hashlib
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    out = os.path.join(str(out_dir), "libfolax_host_shim.so")
-    srcs = [os.path.join(ROOT, "tests", "host_shim", f) for f in ("adjoint_host.cu", "krylov_host.cu", "assemble_ad_host.cu")]
-    r = subprocess.run([nvcc, "-O2", "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-shared",
-                        "-Xcompiler", "-fPIC"] + srcs + ["-o", out], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr
+    shim_dir = os.path.join(ROOT, "tests", "host_shim")
+    srcs = [os.path.join(shim_dir, f) for f in ("adjoint_host.cu", "krylov_host.cu", "assemble_ad_host.cu")]
+    csrc = os.path.join(ROOT, "folax_b200", "csrc")
+    deps = srcs + [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith((".cuh", ".h"))] + \
+        [os.path.join(ROOT, "include", "folax_b200.h")]
+    h = hashlib.sha256()
+    for f in deps:
+        with open(f, "rb") as fh:
+            h.update(f.encode() + fh.read())
+    tag = h.hexdigest()[:16]
+    build_dir = str(out_dir) if out_dir is not None else os.path.join(shim_dir, "_build")
+    os.makedirs(build_dir, exist_ok=True)
+    out = os.path.join(build_dir, f"libfolax_host_shim_{tag}.so")
+    if not os.path.exists(out):
+        def compile_one(src):
+            obj = os.path.join(build_dir, f"{os.path.basename(src)[:-3]}_{tag}.o")
+            r = subprocess.run([nvcc, "-O1", "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets",
+                                "-Xcompiler", "-fPIC", "-c", src, "-o", obj], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            return obj
+        with cf.ThreadPoolExecutor(max_workers=len(srcs)) as ex:
+            objs = list(ex.map(compile_one, srcs))
+        tmp = f"{out}.{os.getpid()}.tmp"
+        r = subprocess.run([nvcc, "-shared", "-Wno-deprecated-gpu-targets"] + objs + ["-o", tmp],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        os.replace(tmp, out)
     return C.CDLL(out)
-
-
-@pytest.fixture(scope="session")
-def shim(tmp_path_factory):
-    return build_shim(tmp_path_factory.mktemp("shim"))
 
 
 def arr(ptr, n, ctype=C.c_double):
@@ -178,9 +197,9 @@ def install_globally(loss, shim_lib):
     return fake
 
 
-@pytest.fixture()
-def cpu_backend(monkeypatch, shim):
-    """install(loss) -> FakeLib: routes folax_b200._lib to the stand-ins for the duration of one test."""
+def make_cpu_backend(monkeypatch, shim):
+    """install(loss) -> FakeLib: routes folax_b200._lib to the stand-ins for the duration of one test
+    (the `cpu_backend` fixture of tests/conftest.py)."""
     def install(loss):
         fake = FakeLib(shim, loss._ne, loss._nnode)
         monkeypatch.setattr(_lib, "load", lambda: fake)

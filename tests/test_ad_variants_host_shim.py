@@ -11,7 +11,6 @@ import numpy as np
 import pytest
 
 from oracle import assembly, losses
-from tests.cpu_backend import shim  # noqa: F401
 from tests.gpu_helpers import make_mesh
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -23,7 +22,7 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def _run(shim, law, etype, num_gp, coords, conn, K, u, flags, nu, body, transpose):  # noqa: F811
+def _run(shim, law, etype, num_gp, coords, conn, K, u, flags, nu, body, transpose):
     ne, a = conn.shape
     d = 3 if etype in ("hexahedron", "tetra") else 2
     nd = a * d
@@ -39,7 +38,7 @@ def _run(shim, law, etype, num_gp, coords, conn, K, u, flags, nu, body, transpos
 @pytest.mark.parametrize("test,etype,num_gp,ckey", [("test_tetra", "tetra", 1, "tet_points_coordinates"),
                                                     ("test_hexa", "hexahedron", 2, "hex_points_coordinates"),
                                                     ("test_quad", "quad", 2, "quad_points_coordinates")])
-def test_reference_ad_goldens(shim, test, etype, num_gp, ckey):  # noqa: F811
+def test_reference_ad_goldens(shim, test, etype, num_gp, ckey):
     with open(os.path.join(ROOT, "tests", "golden", "reference_unit_goldens.json")) as fh:
         rec = json.load(fh)["tests/unit/test_neo_hooke_mechanical_loss_AD.py"][test]
     X = np.ascontiguousarray(rec["assign"][ckey], dtype=np.float64)
@@ -57,7 +56,7 @@ def test_reference_ad_goldens(shim, test, etype, num_gp, ckey):  # noqa: F811
 @pytest.mark.parametrize("etype,num_gp", [("hexahedron", 2), ("tetra", 1), ("tetra", 2), ("quad", 2), ("quad", 3),
                                           ("triangle", 1), ("hexahedron", 1)])
 @pytest.mark.parametrize("transpose", [False, True])
-def test_mesh_assembly_against_oracle(shim, law, etype, num_gp, transpose):  # noqa: F811
+def test_mesh_assembly_against_oracle(shim, law, etype, num_gp, transpose):
     mesh = make_mesh(etype, 2, perturb=0.2, seed=4)
     coords = np.ascontiguousarray(mesh.GetNodesCoordinates(), dtype=np.float64)
     conn = np.ascontiguousarray(mesh.GetElementsNodes(etype), dtype=np.int32)
@@ -86,7 +85,7 @@ def test_mesh_assembly_against_oracle(shim, law, etype, num_gp, transpose):  # n
     assert np.all(off[rows] == 0.0)
 
 
-def test_saint_venant_ad_equals_the_analytic_class_at_identity(shim):  # noqa: F811
+def test_saint_venant_ad_equals_the_analytic_class_at_identity(shim):
     """What the reference's own test asserts (test_saint_venant_mechanical_loss.py:41-42, u = ones => F = I):
     AD and analytic St-Venant agree there (and only there: away from F = I the AD stress carries doubled shear)."""
     X = np.array([[0.1, 0.1, 0.1], [0.28739360416666665, 0.27808503701741405, 0.05672979583333333],

@@ -21,7 +21,6 @@ NGP = {("hexahedron", 1): 1, ("hexahedron", 2): 8, ("hexahedron", 3): 27, ("quad
        ("triangle", 2): 3, ("triangle", 3): 4}
 
 
-from tests.cpu_backend import shim  # noqa: E402,F401  (session fixture: the compiled host shim)
 
 
 def _p(a):

@@ -19,7 +19,7 @@ from folax_b200 import _lib
 from folax_b200.responses import FiniteElementResponse, NodalControl
 from folax_b200.sparse import BCOO
 from oracle import assembly
-from tests.cpu_backend import cpu_backend, fake_loss, shim  # noqa: F401  (fixtures)
+from tests.cpu_backend import fake_loss
 from tests.test_oracle_golden import _square_mesh
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

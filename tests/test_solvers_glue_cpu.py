@@ -21,7 +21,7 @@ from folax_b200.responses import FiniteElementResponse, NodalControl
 from folax_b200.solvers import (AdjointFiniteElementSolver, FiniteElementLinearResidualBasedSolver,
                                 FiniteElementNonLinearResidualBasedSolver)
 from oracle import assembly
-from tests.cpu_backend import cpu_backend, fake_loss, shim  # noqa: F401  (fixtures)
+from tests.cpu_backend import fake_loss
 from tests.test_oracle_golden import _square_mesh
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -34,7 +34,7 @@ def _mech_loss(N):
     return fake_loss("mechanical", "quad", 2, coords, conn, sets, ["Ux", "Uy"], BC, MAT, [1.0, 0.3] + [0.0] * 10)
 
 
-def test_sell_plan_and_spmv_on_a_fe_matrix(shim):  # noqa: F811
+def test_sell_plan_and_spmv_on_a_fe_matrix(shim):
     """Sliced-ELLPACK product (the kernel's per-thread code) == SciPy CSR product, on a 3-D hex elasticity matrix
     whose row lengths vary (corner / edge / face / interior dofs) and whose row count is not a multiple of 32."""
     mesh = folax_b200.create_3D_box_mesh(3, 4, 2, 1.0, 1.0, 1.0)
@@ -73,7 +73,7 @@ def test_sell_plan_and_spmv_on_a_fe_matrix(shim):  # noqa: F811
     assert sell_plan.build(B.indptr, B.indices, 3)["node_cols"] is None
 
 
-def test_block_kernel_is_used_and_equals_the_scalar_one(cpu_backend):  # noqa: F811
+def test_block_kernel_is_used_and_equals_the_scalar_one(cpu_backend):
     L = _mech_loss(6)                                            # 2 dofs per node
     fake = cpu_backend(L)
     K = np.random.default_rng(3).uniform(0.2, 1.0, L._nn)
@@ -88,7 +88,7 @@ def test_block_kernel_is_used_and_equals_the_scalar_one(cpu_backend):  # noqa: F
 
 
 @pytest.mark.parametrize("precond", [None, "jacobi"])
-def test_bicgstab_matches_direct_solve(cpu_backend, precond):  # noqa: F811
+def test_bicgstab_matches_direct_solve(cpu_backend, precond):
     L = _mech_loss(9)
     fake = cpu_backend(L)
     rng = np.random.default_rng(1)
@@ -108,7 +108,7 @@ def test_bicgstab_matches_direct_solve(cpu_backend, precond):  # noqa: F811
     assert np.abs(A.matvec(v).numpy() - A.to_scipy_csr() @ v.numpy()).max() <= 1e-13
 
 
-def test_linear_and_adjoint_solvers_reproduce_the_reference_integration_golden(cpu_backend):  # noqa: F811
+def test_linear_and_adjoint_solvers_reproduce_the_reference_integration_golden(cpu_backend):
     """tests/integration/test_mechanical_2D_sa.py with its own settings (JAX-direct for both solves)."""
     with open(os.path.join(ROOT, "tests", "golden", "reference_unit_goldens.json")) as fh:
         rec = json.load(fh)["tests/integration/test_mechanical_2D_sa.py"]
@@ -145,7 +145,7 @@ def test_linear_and_adjoint_solvers_reproduce_the_reference_integration_golden(c
     assert np.abs(lam_it.numpy() - FE_adj_UV.numpy()).max() <= 1e-8 * np.abs(FE_adj_UV.numpy()).max()
 
 
-def test_newton_solver_follows_the_reference_loop(cpu_backend):  # noqa: F811
+def test_newton_solver_follows_the_reference_loop(cpu_backend):
     """fe_nonlinear_residual_based_solver.py:107-170 on a Neo-Hooke quad mesh: same iterates as the loop written
     out with the oracle and SciPy, including the reference's habit of NOT applying the update of the converged
     iteration."""
@@ -213,7 +213,7 @@ def _slab_solve_worker(rank, world, port, shim_path, out):
         dist.destroy_process_group()
 
 
-def test_slab_partitioned_bicgstab_matches_the_undivided_solve(shim):  # noqa: F811
+def test_slab_partitioned_bicgstab_matches_the_undivided_solve(shim):
     """One linear elastic solve on a hex box cut into 2 z-slabs (one process each, gloo): local SELL products +
     the interface exchange + ownership-weighted, all-reduced dot products give the solution of the undivided mesh,
     identical on both copies of the interface plane."""
