@@ -35,9 +35,12 @@ def build(conn, nn, d):
     if nnz >= 2 ** 31 or len(order) >= 2 ** 31:
         raise ValueError("CSR plan exceeds int32 indexing")
     indices = np.empty(nnz, dtype=np.int32)
-    base = out_base[:, None, None] + np.arange(d)[None, :, None] * row_stride[:, None, None] + np.arange(d)[None, None, :]
-    indices[base.reshape(-1)] = (d * pm[:, None, None] + np.arange(d)[None, None, :] +
-                                 np.zeros((1, d, 1), dtype=np.int64)).reshape(-1).astype(np.int32)
+    ar = np.arange(d)
+    for p0 in range(0, npairs, 1 << 22):          # in chunks of pairs: the d*d-fold expansion is the memory peak otherwise
+        sl = slice(p0, min(npairs, p0 + (1 << 22)))
+        base = out_base[sl, None, None] + ar[None, :, None] * row_stride[sl, None, None] + ar[None, None, :]
+        indices[base.reshape(-1)] = np.broadcast_to(d * pm[sl, None, None] + ar[None, None, :],
+                                                    base.shape).reshape(-1).astype(np.int32)
     i32 = lambda x: np.ascontiguousarray(x, dtype=np.int32)
     return {"indptr": i32(indptr), "indices": indices, "pair_ptr": i32(pair_ptr), "contrib": i32(order),
             "out_base": i32(out_base), "row_stride": i32(row_stride), "npairs": npairs, "nnz": nnz, "ndof": ndof}
