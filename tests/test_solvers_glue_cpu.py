@@ -245,3 +245,27 @@ def test_slab_partitioned_bicgstab_matches_the_undivided_solve(shim):
     a = u_0.reshape(-1, 3)[np.searchsorted(g0, shared)]
     b = u_1.reshape(-1, 3)[np.searchsorted(g1, shared)]
     assert len(shared) == (n + 1) ** 2 and np.abs(a - b).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_sell_plan_edge_cases(shim):
+    """Empty matrix, empty rows, a row count that is not a multiple of the slice height, no diagonal entry."""
+    empty = sp.csr_array((0, 0))
+    plan = sell_plan.build(empty.indptr, empty.indices)
+    assert plan["nrows"] == 0 and plan["total"] == 0 and plan["slice_ptr"].tolist() == [0]
+    rng = np.random.default_rng(5)
+    dense = rng.standard_normal((45, 45)) * (rng.uniform(size=(45, 45)) < 0.2)
+    dense[[3, 17, 44], :] = 0.0                                   # empty rows (one of them the last)
+    np.fill_diagonal(dense[:10, :10], 0.0)                        # rows without a diagonal entry
+    A = sp.csr_array(dense)
+    A.sort_indices()
+    plan = sell_plan.build(A.indptr, A.indices, chunk_rows=32)
+    assert plan["node_cols"] is None
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    vals = np.zeros(plan["total"])
+    assert shim.host_gather_values(C.c_longlong(plan["total"]), p(plan["src"]), p(np.ascontiguousarray(A.data)), p(vals)) == 0
+    x, y = rng.standard_normal(45), np.full(45, np.nan)
+    assert shim.host_sell_spmv(C.c_longlong(45), p(plan["slice_ptr"]), p(plan["cols"]), p(vals), p(x), p(y)) == 0
+    assert np.abs(y - A @ x).max() <= 1e-14 and y[3] == 0.0 and y[44] == 0.0
+    diag = np.full(45, np.nan)
+    assert shim.host_gather_values(C.c_longlong(45), p(plan["diag_src"]), p(np.ascontiguousarray(A.data)), p(diag)) == 0
+    assert np.array_equal(diag, A.diagonal())                     # missing diagonals gather as 0
