@@ -91,6 +91,16 @@ ffi::Error EnergyAndGradsImpl(cudaStream_t stream, ffi::AnyBuffer geom, ffi::Buf
                                      energy->untyped_data(), work->untyped_data()));
 }
 
+// geometry_cache: per-element, per-Gauss-point geometry factors shared by all samples of the batched loss.
+ffi::Error GeometryCacheImpl(cudaStream_t stream, ffi::AnyBuffer xyz, ffi::Buffer<ffi::S32> conn,
+                             ffi::Result<ffi::AnyBuffer> geom, int32_t physics, int32_t element, int32_t num_gp) {
+  const int dt = DtypeOf(xyz.element_type());
+  if (dt < 0) return ffi::Error::InvalidArgument("Unsupported data type for FFI call.");
+  return FromRc(fol_geometry_cache_physics(stream, dt, physics, element, num_gp, conn.dimensions()[0],
+                                           xyz.untyped_data(), conn.typed_data(), /*aux=*/nullptr,
+                                           geom->untyped_data()));
+}
+
 // apply_jacobian_elements: ye_elem = Ke'(ctrl, u) v_e without forming Ke (what `BCOO @ v` does, fe_solver.py:61).
 ffi::Error ApplyJacobianElementsImpl(cudaStream_t stream, ffi::AnyBuffer xyz, ffi::Buffer<ffi::S32> conn,
                                      ffi::AnyBuffer ctrl, ffi::AnyBuffer u, ffi::Buffer<ffi::U8> dir_flag,
@@ -145,6 +155,16 @@ ffi::Error ResidualAdjointElementsImpl(cudaStream_t stream, ffi::AnyBuffer xyz, 
 }
 
 }  // namespace
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(FolGeometryCache, GeometryCacheImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::AnyBuffer>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Ret<ffi::AnyBuffer>()
+                                  .Attr<int32_t>("physics")
+                                  .Attr<int32_t>("element")
+                                  .Attr<int32_t>("num_gp"));
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(FolApplyJacobianElements, ApplyJacobianElementsImpl,
                               ffi::Ffi::Bind()

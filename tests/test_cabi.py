@@ -89,5 +89,22 @@ def test_xla_ffi_shim_compiles_against_a_stub_of_the_ffi_header(tmp_path):
     assert r.returncode == 0, r.stderr
     syms = subprocess.run(["nm", obj], capture_output=True, text=True).stdout
     for name in ("FolAssembleElements", "FolResidualGather", "FolEnergyAndGrads", "FolApplyJacobianElements",
-                 "FolGaussInterpolate", "FolResponseElements", "FolResidualAdjointElements"):
+                 "FolGaussInterpolate", "FolResponseElements", "FolResidualAdjointElements", "FolGeometryCache"):
         assert f"{name}_stub_marker" in syms, f"{name} was not compiled (is the shim still header-guarded away?)"
+
+
+def test_jax_binding_module_is_importable_and_says_what_it_needs():
+    """folax_b200/ffi/jax_binding.py (the reference-side jax.ffi + custom_vjp classes) cannot run here: it must
+    import cleanly and fail with a clear message instead of an ImportError deep inside."""
+    import importlib.util
+    from folax_b200.ffi import jax_binding
+    assert set(jax_binding.HANDLERS) >= {"FolAssembleElements", "FolResidualGather", "FolEnergyAndGrads"}
+    if importlib.util.find_spec("jax") is None:
+        with pytest.raises(_lib.FolaxError, match="needs JAX"):
+            jax_binding.register()
+        with pytest.raises(_lib.FolaxError, match="needs JAX"):
+            jax_binding.accelerate(object, "mechanical")
+    # every handler the module registers exists in the shim
+    shim_src = open(os.path.join(ROOT, "folax_b200", "ffi", "xla_ffi_shim.cc")).read()
+    for name in jax_binding.HANDLERS:
+        assert f"XLA_FFI_DEFINE_HANDLER_SYMBOL({name}," in shim_src, name
