@@ -4,7 +4,8 @@ The reference converts the duplicate-keeping BCOO to a SciPy CSR on the host (fe
 `jax.scipy.sparse.linalg.bicgstab` (:62-67).  Here the Jacobian never leaves the device: `fol_csr_values` sums the
 duplicates in a fixed order, `fol_gather_values` permutes the values into the sliced-ELLPACK layout, and the Krylov
 iteration runs on `fol_sell_spmv` / `fol_vec_op` / `fol_dot` (csrc/krylov.cu).  PyTorch only owns the vectors.
-The host reads five scalars per iteration (the BiCGSTAB coefficients); everything else stays on the stream.
+The host reads the BiCGSTAB coefficients back four times per iteration (six scalars); everything else stays on the
+stream.
 """
 import math
 
@@ -126,7 +127,7 @@ class _Vectors:
         if self.weights is not None:
             import torch.distributed as dist
             if dist.is_initialized() and dist.get_world_size(self.group) > 1:
-                dist.all_reduce(self.slots, op=dist.ReduceOp.SUM, group=self.group)
+                dist.all_reduce(self.slots[:count], op=dist.ReduceOp.SUM, group=self.group)   # only what was just written
         vals = self.slots[:count].tolist()             # one device -> host read for `count` scalars
         return vals[0] if count == 1 else vals
 
@@ -161,12 +162,12 @@ def bicgstab(A, b, x0=None, tol=1e-5, atol=0.0, maxiter=None, M_diagonal=None):
     q.zero_()
     v.dot_into(b, b, 0)
     v.dot_into(r, r, 1)
-    bb, rs = v.read(2)
+    v.dot_into(rhat, r, 2)
+    bb, rs, rho_new = v.read(3)                          # rho of the next iteration rides along with |r|^2: one read
     atol2 = max(tol * tol * bb, atol * atol)
     rho = alpha = omega = 1.0
     k = 0
     while rs > atol2 and 0 <= k < maxiter:
-        rho_new = v.dot(rhat, r)
         if rho_new == 0.0:
             k = -10
             break
@@ -189,7 +190,7 @@ def bicgstab(A, b, x0=None, tol=1e-5, atol=0.0, maxiter=None, M_diagonal=None):
             v.axpby(1.0, x, alpha, phat, x)
             r, s = s, r
             rs, rho, k = ss, rho_new, k + 1
-            continue
+            break                                       # rs = ss < atol2: the loop condition is false anyway
         if M_diagonal is not None:
             v.divide(s, M_diagonal, shat)
         else:
@@ -202,8 +203,10 @@ def bicgstab(A, b, x0=None, tol=1e-5, atol=0.0, maxiter=None, M_diagonal=None):
         v.axpby(1.0, x, alpha, phat, x)
         v.axpby(1.0, x, omega, shat, x)
         v.axpby(1.0, s, -omega, t, r)
-        rs = v.dot(r, r)
         rho = rho_new
+        v.dot_into(r, r, 0)
+        v.dot_into(rhat, r, 1)
+        rs, rho_new = v.read(2)
         if omega == 0.0 or alpha == 0.0:
             k = -11
             break
