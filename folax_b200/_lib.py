@@ -60,6 +60,9 @@ SIGNATURES = {
     "fol_sell_spmv": (_int, [_vp, _int, _i64, _vp, _i32p, _vp, _vp, _vp]),
     "fol_sell_spmv_block": (_int, [_vp, _int, _int, _i64, _vp, _i32p, _vp, _vp, _vp]),
     "fol_vec_op": (_int, [_vp, _int, _int, _i64, _dbl, _vp, _dbl, _vp, _vp]),
+    "fol_bicg_scalar_count": (_int, []),
+    "fol_bicg_scalars": (_int, [_vp, _int, _int, _vp]),
+    "fol_vec_op_dev": (_int, [_vp, _int, _i64, _vp, _int, _int, _dbl, _vp, _int, _dbl, _vp, _vp]),
     "fol_dot_work_size": (_i64, []),
     "fol_dot": (_int, [_vp, _int, _i64, _vp, _vp, _vp, _vp]),
     "fol_plan_create": (_int, [C.POINTER(_vp), _int, _int, _int, _int, _i64, _i64, _vp, _i32p, _i32p, _i64,

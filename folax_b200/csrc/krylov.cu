@@ -39,6 +39,19 @@ __global__ void __launch_bounds__(256) vec_op_kernel(long long n, int op, T a, c
     vec_op_thread<T>(i, op, a, x, b, y, out);
 }
 
+template <class T>
+__global__ void bicg_scalar_kernel(int stage, T* sc) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) bicg_scalar_stage<T>(stage, sc);
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) vec_op_dev_kernel(long long n, const T* __restrict__ sc, int mask, int ia, T sa,
+                                                         const T* x, int ib, T sb, const T* y, T* out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    vec_op_dev_thread<T>(i, sc, mask, ia, sa, x, ib, sb, y, out);
+}
+
 constexpr int kDotBlocks = 592;   // 4 per SM on 148 SMs; FIXED, so the reduction tree never depends on the device state
 constexpr int kDotThreads = 256;
 
@@ -152,6 +165,34 @@ int fol_vec_op(fol_stream_t s, int dtype, int op, int64_t n, double a, const voi
   else
     return fail(FOL_ERR_INVALID, "fol_vec_op: unknown dtype");
   return check_launch("vec_op_kernel");
+}
+
+int fol_bicg_scalar_count(void) { return BS_COUNT; }
+
+int fol_bicg_scalars(fol_stream_t s, int dtype, int stage, void* scalars) {
+  FOL_REQUIRE(scalars && stage >= BSTAGE_TOP && stage <= BSTAGE_END, "fol_bicg_scalars: bad arguments");
+  if (dtype == FOL_F64) bicg_scalar_kernel<double><<<1, 32, 0, (cudaStream_t)s>>>(stage, (double*)scalars);
+  else if (dtype == FOL_F32) bicg_scalar_kernel<float><<<1, 32, 0, (cudaStream_t)s>>>(stage, (float*)scalars);
+  else return fail(FOL_ERR_INVALID, "fol_bicg_scalars: unknown dtype");
+  return check_launch("bicg_scalar_kernel");
+}
+
+int fol_vec_op_dev(fol_stream_t s, int dtype, int64_t n, const void* scalars, int state_mask, int ia, double sa,
+                   const void* x, int ib, double sb, const void* y, void* out) {
+  FOL_REQUIRE(n >= 0 && scalars && x && out, "fol_vec_op_dev: null pointer / negative size");
+  FOL_REQUIRE(ia < BS_COUNT && ib < BS_COUNT, "fol_vec_op_dev: scalar index out of range");
+  if (n == 0) return FOL_OK;
+  if (dtype == FOL_F64)
+    vec_op_dev_kernel<double><<<stream_grid(n), 256, 0, (cudaStream_t)s>>>(n, (const double*)scalars, state_mask, ia, sa,
+                                                                          (const double*)x, ib, sb, (const double*)y,
+                                                                          (double*)out);
+  else if (dtype == FOL_F32)
+    vec_op_dev_kernel<float><<<stream_grid(n), 256, 0, (cudaStream_t)s>>>(n, (const float*)scalars, state_mask, ia,
+                                                                         (float)sa, (const float*)x, ib, (float)sb,
+                                                                         (const float*)y, (float*)out);
+  else
+    return fail(FOL_ERR_INVALID, "fol_vec_op_dev: unknown dtype");
+  return check_launch("vec_op_dev_kernel");
 }
 
 int64_t fol_dot_work_size(void) { return kDotBlocks; }

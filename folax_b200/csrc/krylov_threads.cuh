@@ -87,4 +87,76 @@ __host__ __device__ inline void vec_op_thread(long long i, int op, T a, const T*
   else out[i] = a * x[i] / y[i];
 }
 
+
+// ---- BiCGSTAB with its scalars on the device --------------------------------------------------------------------
+// The recurrence coefficients live in a small device array; a one-thread kernel advances them between the vector
+// kernels, which read their coefficients through that array and do nothing once the iteration has stopped.  The host
+// enqueues whole iterations without reading anything back and looks at (state, k) once per batch -- same iterates,
+// same stopping iteration and the same break-down codes as the host-scalar loop of folax_b200/linalg.py.
+enum : int { BS_BB = 0, BS_RS, BS_RHO, BS_ALPHA, BS_OMEGA, BS_RHO_NEW, BS_BETA, BS_RQ, BS_SS, BS_TS, BS_TT, BS_ATOL2,
+             BS_STATE, BS_K, BS_RS_NEXT, BS_RHO_NEXT, BS_MAXITER, BS_COUNT };
+enum : int { BS_RUN = 0, BS_HALF_EXIT = 1, BS_DONE = 2, BS_BROKEN = 3 };            // values of sc[BS_STATE]
+enum : int { BSTAGE_TOP = 0, BSTAGE_ALPHA = 1, BSTAGE_HALF = 2, BSTAGE_OMEGA = 3, BSTAGE_END = 4 };
+
+template <class T>
+__host__ __device__ inline void bicg_scalar_stage(int stage, T* sc) {
+  const int state = (int)sc[BS_STATE];
+  if (stage == BSTAGE_TOP) {
+    if (state != BS_RUN) return;
+    if (!(sc[BS_RS] > sc[BS_ATOL2] && sc[BS_K] >= (T)0 && sc[BS_K] < sc[BS_MAXITER])) {
+      sc[BS_STATE] = (T)BS_DONE;
+    } else if (sc[BS_RHO_NEW] == (T)0) {
+      sc[BS_STATE] = (T)BS_BROKEN;
+      sc[BS_K] = (T)-10;
+    } else {
+      sc[BS_BETA] = sc[BS_RHO_NEW] / sc[BS_RHO] * sc[BS_ALPHA] / sc[BS_OMEGA];
+    }
+  } else if (stage == BSTAGE_ALPHA) {
+    if (state != BS_RUN) return;
+    if (sc[BS_RQ] == (T)0) {
+      sc[BS_STATE] = (T)BS_BROKEN;
+      sc[BS_K] = (T)-11;
+    } else {
+      sc[BS_ALPHA] = sc[BS_RHO_NEW] / sc[BS_RQ];
+    }
+  } else if (stage == BSTAGE_HALF) {
+    if (state == BS_RUN && sc[BS_SS] < sc[BS_ATOL2]) sc[BS_STATE] = (T)BS_HALF_EXIT;
+  } else if (stage == BSTAGE_OMEGA) {
+    if (state == BS_RUN) sc[BS_OMEGA] = (sc[BS_TT] != (T)0) ? sc[BS_TS] / sc[BS_TT] : (T)0;
+  } else {  // BSTAGE_END
+    if (state == BS_HALF_EXIT) {
+      sc[BS_RS] = sc[BS_SS];
+      sc[BS_RHO] = sc[BS_RHO_NEW];
+      sc[BS_K] += (T)1;
+      sc[BS_STATE] = (T)BS_DONE;
+    } else if (state == BS_RUN) {
+      sc[BS_RHO] = sc[BS_RHO_NEW];
+      sc[BS_RS] = sc[BS_RS_NEXT];
+      sc[BS_RHO_NEW] = sc[BS_RHO_NEXT];
+      if (sc[BS_OMEGA] == (T)0 || sc[BS_ALPHA] == (T)0) {
+        sc[BS_STATE] = (T)BS_BROKEN;
+        sc[BS_K] = (T)-11;
+      } else {
+        sc[BS_K] += (T)1;
+      }
+    }
+  }
+}
+
+// out[i] = a x[i] + b y[i] with a = sa * (ia >= 0 ? sc[ia] : 1), b likewise; executed only while sc[BS_STATE] is one of
+// the states in `mask` (bit s set = state s allowed).  y may be null when sb == 0.
+template <class T>
+__host__ __device__ inline void vec_op_dev_thread(long long i, const T* sc, int mask, int ia, T sa, const T* x, int ib,
+                                                  T sb, const T* y, T* out) {
+  const int state = (int)sc[BS_STATE];
+  if (!((mask >> state) & 1)) return;
+  const T a = sa * (ia >= 0 ? sc[ia] : (T)1);
+  if (y == nullptr) {
+    out[i] = a * x[i];
+    return;
+  }
+  const T b = sb * (ib >= 0 ? sc[ib] : (T)1);
+  out[i] = a * x[i] + b * y[i];
+}
+
 }  // namespace fol

@@ -212,3 +212,93 @@ def bicgstab(A, b, x0=None, tol=1e-5, atol=0.0, maxiter=None, M_diagonal=None):
             break
         k += 1
     return x, k
+
+
+# slots of the device scalar array (csrc/krylov_threads.cuh, enum BS_*)
+(_BB, _RS, _RHO, _ALPHA, _OMEGA, _RHO_NEW, _BETA, _RQ, _SS, _TS, _TT, _ATOL2, _STATE, _K, _RS_NEXT, _RHO_NEXT,
+ _MAXITER) = range(17)
+_RUN, _HALF, _DONE, _BROKEN = 1, 2, 4, 8                # state masks (bit s = state s)
+
+
+def bicgstab_device(A, b, x0=None, tol=1e-5, atol=0.0, maxiter=None, M_diagonal=None, check_every=8):
+    """`bicgstab` with the recurrence scalars kept on the device: the host enqueues `check_every` whole iterations
+    (two products, the vector updates gated by the device-side state, five dot products, five one-thread scalar
+    stages) without reading anything back, then looks at (state, k) once.  Same iterates, same stopping iteration
+    and break-down codes as `bicgstab` (tests/test_solvers_glue_cpu.py compares them); not for SlabOperator (its dot
+    products need a collective between the dot and the scalar stage)."""
+    L = A.loss
+    lib = _lib.load()
+    n = b.numel()
+    if hasattr(A, "vectors"):
+        raise ValueError("bicgstab_device: slab-partitioned operators use bicgstab")
+    if maxiter is None:
+        maxiter = 10 * n
+    s_ptr = _lib.stream_ptr
+    v = _Vectors(L._dt, n, L.dtype, L.device)
+    nsc = int(lib.fol_bicg_scalar_count())
+    sc = torch.zeros(nsc, dtype=L.dtype, device=L.device)
+    esz = sc.element_size()
+    slot = lambda i: sc.data_ptr() + i * esz
+
+    def dot(x, y, i):
+        _lib.check(lib.fol_dot(s_ptr(), L._dt, n, _lib.ptr(x), _lib.ptr(y), _lib.ptr(v.work), slot(i)))
+
+    def vec(mask, ia, sa, x, ib, sb, y, out):
+        _lib.check(lib.fol_vec_op_dev(s_ptr(), L._dt, n, _lib.ptr(sc), mask, ia, float(sa), _lib.ptr(x), ib, float(sb),
+                                      _lib.ptr(y) if y is not None else None, _lib.ptr(out)))
+
+    def stage(k):
+        _lib.check(lib.fol_bicg_scalars(s_ptr(), L._dt, k, _lib.ptr(sc)))
+
+    new = lambda: torch.zeros_like(b)      # the un-gated kernels (products, dots) read these even after the stop
+    x = b.new_zeros(n) if x0 is None else _lib.to_device(x0, L.dtype).reshape(-1).clone()
+    q, r = A.matvec(x), new()
+    v.axpby(1.0, b, -1.0, q, r)
+    rhat = r.clone()
+    p, phat, s, shat, t, tmp = b.new_zeros(n), new(), new(), new(), new(), new()
+    q.zero_()
+    dot(b, b, _BB)
+    dot(r, r, _RS)
+    dot(rhat, r, _RHO_NEW)
+    bb = float(sc[_BB])                                  # the only read before the loop: atol2 = max(tol^2 |b|^2, atol^2)
+    init = torch.zeros(nsc, dtype=torch.float64)
+    init[_RHO] = init[_ALPHA] = init[_OMEGA] = 1.0
+    init[_ATOL2] = max(tol * tol * bb, atol * atol)
+    init[_MAXITER] = float(maxiter)
+    keep = torch.zeros(nsc, dtype=torch.bool)
+    keep[[_BB, _RS, _RHO_NEW]] = True
+    sc.copy_(torch.where(keep.to(sc.device), sc, init.to(device=sc.device, dtype=sc.dtype)))
+    done = 0
+    while True:
+        for _ in range(check_every):
+            stage(0)                                                     # beta | stop test | rho break-down
+            vec(_RUN, -1, 1.0, p, _OMEGA, -1.0, q, tmp)                  # tmp = p - omega q
+            vec(_RUN, -1, 1.0, r, _BETA, 1.0, tmp, p)                    # p = r + beta tmp
+            if M_diagonal is not None:
+                v.divide(p, M_diagonal, phat)
+            else:
+                phat = p
+            A.matvec(phat, q)
+            dot(rhat, q, _RQ)
+            stage(1)                                                     # alpha | break-down
+            vec(_RUN, -1, 1.0, r, _ALPHA, -1.0, q, s)                    # s = r - alpha q
+            dot(s, s, _SS)
+            stage(2)                                                     # converged on the half step?
+            if M_diagonal is not None:
+                v.divide(s, M_diagonal, shat)
+            else:
+                shat = s
+            A.matvec(shat, t)
+            dot(t, s, _TS)
+            dot(t, t, _TT)
+            stage(3)                                                     # omega
+            vec(_RUN | _HALF, -1, 1.0, x, _ALPHA, 1.0, phat, x)          # x += alpha phat
+            vec(_RUN, -1, 1.0, x, _OMEGA, 1.0, shat, x)                  # x += omega shat
+            vec(_RUN, -1, 1.0, s, _OMEGA, -1.0, t, r)                    # r = s - omega t
+            dot(r, r, _RS_NEXT)
+            dot(rhat, r, _RHO_NEXT)
+            stage(4)                                                     # commit the iteration | (alpha, omega) break-down
+        done += check_every
+        state, k = sc[[_STATE, _K]].tolist()                             # one host read per batch
+        if int(state) != 0 or done >= maxiter + check_every:
+            return x, int(k)

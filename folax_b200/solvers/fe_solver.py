@@ -7,7 +7,9 @@
                              what changes is that 1/2.4 of the bytes cross PCIe (no duplicates) and no host sort
   "PETSc-*"                  petsc4py is not in this image: falls back to BiCGSTAB with a warning, as :47-49 does
 
-Extra setting (not in the reference): "pre-conditioner": "jacobi" applies the diagonal to BiCGSTAB.
+Extra settings (not in the reference): "pre-conditioner": "jacobi" applies the diagonal to BiCGSTAB;
+"device_scalars": True keeps the BiCGSTAB recurrence scalars on the device (linalg.bicgstab_device: same iterates,
+one host read per "check_every" iterations instead of four per iteration).
 """
 import numpy as np
 import torch
@@ -53,8 +55,12 @@ class FiniteElementSolver(Solver):
                                           _lib.ptr(rhs)))
         s = self.linear_solver_settings
         diag = A.diagonal() if str(s.get("pre-conditioner", "")).lower() == "jacobi" else None
-        x, info = linalg.bicgstab(A, rhs, x0=dofs_vector, tol=s["tol"], atol=s["atol"], maxiter=s["maxiter"],
-                                  M_diagonal=diag)
+        if s.get("device_scalars"):       # extra setting: recurrence scalars on the device, one host read per batch
+            x, info = linalg.bicgstab_device(A, rhs, x0=dofs_vector, tol=s["tol"], atol=s["atol"], maxiter=s["maxiter"],
+                                             M_diagonal=diag, check_every=int(s.get("check_every", 8)))
+        else:
+            x, info = linalg.bicgstab(A, rhs, x0=dofs_vector, tol=s["tol"], atol=s["atol"], maxiter=s["maxiter"],
+                                      M_diagonal=diag)
         self.last_linear_solve_info = info
         return x
 

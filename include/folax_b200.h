@@ -260,6 +260,17 @@ int fol_sell_spmv_block(fol_stream_t s, int dtype, int dofs_per_node, int64_t nr
 /* op 0: out = a x + b y (y may be NULL when b == 0)   op 1: out = a x*y   op 2: out = a x/y;  out may alias x or y */
 int fol_vec_op(fol_stream_t s, int dtype, int op, int64_t n, double a, const void* x, double b, const void* y,
                void* out);
+/* BiCGSTAB with its scalars on the device (no host read inside an iteration).  `scalars` is an array of
+ * fol_bicg_scalar_count() values of the call's dtype (layout: csrc/krylov_threads.cuh, enum BS_*): the dot products
+ * are written into it by fol_dot, fol_bicg_scalars advances the recurrence between the vector kernels (stage 0..4:
+ * top of the iteration, alpha, half-step test, omega, end), and fol_vec_op_dev computes
+ *   out = sa*c_a*x + sb*c_b*y,  c_a = scalars[ia] (1 when ia < 0), likewise c_b; y may be NULL,
+ * only while scalars[state] is one of the states in state_mask (bit s = state s; 0 running, 1 converged on the half
+ * step, 2 done, 3 broken down) -- so a stopped iteration is frozen whatever the host still enqueues. */
+int fol_bicg_scalar_count(void);
+int fol_bicg_scalars(fol_stream_t s, int dtype, int stage, void* scalars);
+int fol_vec_op_dev(fol_stream_t s, int dtype, int64_t n, const void* scalars, int state_mask, int ia, double sa,
+                   const void* x, int ib, double sb, const void* y, void* out);
 /* out[0] = x . y on the device (fixed two-stage reduction tree: run-to-run identical); `work` needs
  * fol_dot_work_size() elements of the call's dtype */
 int64_t fol_dot_work_size(void);

@@ -68,6 +68,13 @@ torch.cuda.synchronize()
 out["bicgstab_iterations"], out["bicgstab_s"] = info, time.time() - t0
 if info > 0:
     out["bicgstab_ms_per_iteration"] = 1e3 * out["bicgstab_s"] / info
+torch.cuda.synchronize()
+t0 = time.time()
+x2, info2 = linalg.bicgstab_device(A, -R, x0=None, tol=1e-8, atol=0.0, maxiter=int(os.environ.get("MAXITER", 200)),
+                                   M_diagonal=A.diagonal(), check_every=8)
+torch.cuda.synchronize()
+out["bicgstab_device_scalars_iterations"], out["bicgstab_device_scalars_s"] = info2, time.time() - t0
+out["bicgstab_device_scalars_identical"] = bool(info2 == info and torch.equal(x, x2))
 
 resp = FiniteElementResponse("r", "(E**2)*U[0]", loss, NodalControl("E", mesh))
 resp.Initialize()

@@ -121,6 +121,18 @@ class FakeLib:
         return self.shim.host_vec_op(op, C.c_longlong(n), C.c_double(a), C.c_void_p(x), C.c_double(b), C.c_void_p(y),
                                      C.c_void_p(out))
 
+    def fol_bicg_scalar_count(self):
+        return self.shim.host_bicg_scalar_count()
+
+    def fol_bicg_scalars(self, s, dt, stage, sc):
+        self._count("bicg_scalars")
+        return self.shim.host_bicg_scalars(stage, C.c_void_p(sc))
+
+    def fol_vec_op_dev(self, s, dt, n, sc, mask, ia, sa, x, ib, sb, y, out):
+        self._count("vec_op_dev")
+        return self.shim.host_vec_op_dev(C.c_longlong(n), C.c_void_p(sc), mask, ia, C.c_double(sa), C.c_void_p(x), ib,
+                                         C.c_double(sb), C.c_void_p(y), C.c_void_p(out))
+
     def fol_dot_work_size(self):
         return 592
 

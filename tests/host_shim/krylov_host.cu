@@ -33,4 +33,17 @@ int host_vec_op(int op, long long n, double a, const double* x, double b, const 
   return 0;
 }
 
+int host_bicg_scalar_count(void) { return BS_COUNT; }
+
+int host_bicg_scalars(int stage, double* sc) {
+  bicg_scalar_stage<double>(stage, sc);
+  return 0;
+}
+
+int host_vec_op_dev(long long n, const double* sc, int mask, int ia, double sa, const double* x, int ib, double sb,
+                    const double* y, double* out) {
+  for (long long i = 0; i < n; ++i) vec_op_dev_thread<double>(i, sc, mask, ia, sa, x, ib, sb, y, out);
+  return 0;
+}
+
 }  // extern "C"

@@ -269,3 +269,27 @@ def test_sell_plan_edge_cases(shim):
     diag = np.full(45, np.nan)
     assert shim.host_gather_values(C.c_longlong(45), p(plan["diag_src"]), p(np.ascontiguousarray(A.data)), p(diag)) == 0
     assert np.array_equal(diag, A.diagonal())                     # missing diagonals gather as 0
+
+
+@pytest.mark.parametrize("precond", [None, "jacobi"])
+@pytest.mark.parametrize("check_every", [1, 8])
+def test_device_scalar_bicgstab_equals_the_host_scalar_loop(cpu_backend, precond, check_every):
+    """Same iterates, same stopping iteration: the scalar recurrences run in bicg_scalar_stage (device) instead of
+    Python, the vector kernels are gated by the device-side state, the host reads (state, k) once per batch."""
+    L = _mech_loss(8)
+    fake = cpu_backend(L)
+    K = np.random.default_rng(7).uniform(0.2, 1.0, L._nn)
+    u0 = L.ApplyDirichletBCOnDofVector(np.zeros(L.total_number_of_dofs))
+    jac, R = L.ComputeJacobianMatrixAndResidualVector(K, u0)
+    A = linalg.SellOperator(L, jac)
+    diag = A.diagonal() if precond else None
+    for tol, maxiter in ((1e-10, 2000), (1e-10, 7), (1e-3, 2000)):          # converged | stopped by maxiter | loose
+        x_h, k_h = linalg.bicgstab(A, -R, x0=u0, tol=tol, atol=0.0, maxiter=maxiter, M_diagonal=diag)
+        x_d, k_d = linalg.bicgstab_device(A, -R, x0=u0, tol=tol, atol=0.0, maxiter=maxiter, M_diagonal=diag,
+                                          check_every=check_every)
+        assert k_d == k_h, (tol, maxiter, k_d, k_h)
+        assert torch.equal(x_d, x_h)
+    assert fake.calls["bicg_scalars"] > 0 and fake.calls["vec_op_dev"] > 0
+    # zero right-hand side: nothing to do, x0 comes back
+    x_d, k_d = linalg.bicgstab_device(A, torch.zeros_like(R), x0=None, tol=1e-8, check_every=check_every)
+    assert k_d == 0 and not x_d.any()

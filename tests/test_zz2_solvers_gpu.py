@@ -95,6 +95,27 @@ def test_config0_linear_solve_with_device_bicgstab(precond):
     assert np.abs(u - ref).max() <= 1e-7 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("precond", [None, "jacobi"])
+def test_device_scalar_bicgstab_equals_the_host_scalar_loop(precond):
+    """linalg.bicgstab_device (recurrence scalars on the device, gated vector kernels, one host read per batch) against
+    linalg.bicgstab: same stopping iteration, bit-identical solution."""
+    mesh = gh.make_mesh("hexahedron", 4, perturb=0.2, seed=3)
+    loss = gh.make_loss("mechanical", "hexahedron", mesh, num_gp=2)
+    K, _ = gh.fields("mechanical", mesh, loss, seed=1)
+    u0 = loss.ApplyDirichletBCOnDofVector(np.zeros(loss.total_number_of_dofs))
+    jac, R = loss.ComputeJacobianMatrixAndResidualVector(K, u0)
+    A = linalg.SellOperator(loss, jac)
+    diag = A.diagonal() if precond else None
+    rhs = -R
+    for tol, maxiter in ((1e-10, 3000), (1e-10, 5), (1e-3, 3000)):
+        x_h, k_h = linalg.bicgstab(A, rhs, x0=u0, tol=tol, atol=0.0, maxiter=maxiter, M_diagonal=diag)
+        for every in (1, 8):
+            x_d, k_d = linalg.bicgstab_device(A, rhs, x0=u0, tol=tol, atol=0.0, maxiter=maxiter, M_diagonal=diag,
+                                              check_every=every)
+            assert k_d == k_h, (tol, maxiter, every, k_d, k_h)
+            assert torch.equal(x_d, x_h)
+
+
 def test_reference_integration_golden_through_the_solver_classes():
     """tests/integration/test_mechanical_2D_sa.py:21-113, same objects, same settings."""
     with open(os.path.join(ROOT, "tests", "golden", "reference_unit_goldens.json")) as fh:
