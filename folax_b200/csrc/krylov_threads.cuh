@@ -9,9 +9,18 @@
 // the per-row sum runs in the fixed CSR order, so products are deterministic.  FE rows have near-uniform length
 // (81 entries for interior Hex8 elasticity dofs), so the padding (value 0, column 0) is a few per cent.
 #pragma once
+#include <math.h>
+
 #include "common.cuh"
 
 namespace fol {
+
+// Sums of products are written with EXPLICIT fused multiply-adds (a x + b y as fma(a, x, b*y); row sums as
+// acc = fma(v, x, acc)) in every kernel that forms them: left to the compiler, the contraction could pick a different
+// product in two kernels (or none on the host build of the tests), and the scalar- and block-column products, or the
+// host-scalar and device-scalar BiCGSTAB loops, would drift apart by an ulp per update instead of being bit-identical.
+__host__ __device__ inline double fol_fma(double a, double b, double c) { return fma(a, b, c); }
+__host__ __device__ inline float fol_fma(float a, float b, float c) { return fmaf(a, b, c); }
 
 template <class T>
 struct SellArgs {
@@ -32,7 +41,7 @@ __host__ __device__ inline void sell_spmv_thread(long long row, const SellArgs<T
   T acc = (T)0;
   for (int k = 0; k < width; ++k) {
     const long long idx = base + (long long)k * 32 + lane;
-    acc += a.vals[idx] * a.x[a.cols[idx]];
+    acc = fol_fma(a.vals[idx], a.x[a.cols[idx]], acc);
   }
   a.y[row] = acc;
 }
@@ -65,7 +74,7 @@ __host__ __device__ inline void sell_spmv_block_thread(long long row, const Bloc
     const T* xm = a.x + m * D;
     const T* v = a.vals + base + (long long)q * (D * 32) + lane;
 #pragma unroll
-    for (int j = 0; j < D; ++j) acc += v[j * 32] * xm[j];
+    for (int j = 0; j < D; ++j) acc = fol_fma(v[j * 32], xm[j], acc);
   }
   a.y[row] = acc;
 }
@@ -79,10 +88,11 @@ __host__ __device__ inline void gather_values_thread(long long i, const int32_t*
 
 enum : int { VEC_AXPBY = 0, VEC_AXY = 1, VEC_AX_OVER_Y = 2 };
 
+
 // op 0: out = a x + b y (y may be null when b == 0);  op 1: out = a x * y;  op 2: out = a x / y
 template <class T>
 __host__ __device__ inline void vec_op_thread(long long i, int op, T a, const T* x, T b, const T* y, T* out) {
-  if (op == VEC_AXPBY) out[i] = y ? a * x[i] + b * y[i] : a * x[i];
+  if (op == VEC_AXPBY) out[i] = y ? fol_fma(a, x[i], b * y[i]) : a * x[i];
   else if (op == VEC_AXY) out[i] = a * x[i] * y[i];
   else out[i] = a * x[i] / y[i];
 }
@@ -156,7 +166,7 @@ __host__ __device__ inline void vec_op_dev_thread(long long i, const T* sc, int 
     return;
   }
   const T b = sb * (ib >= 0 ? sc[ib] : (T)1);
-  out[i] = a * x[i] + b * y[i];
+  out[i] = fol_fma(a, x[i], b * y[i]);
 }
 
 }  // namespace fol
