@@ -220,12 +220,15 @@ def bicgstab(A, b, x0=None, tol=1e-5, atol=0.0, maxiter=None, M_diagonal=None):
 _RUN, _HALF, _DONE, _BROKEN = 1, 2, 4, 8                # state masks (bit s = state s)
 
 
-def bicgstab_device(A, b, x0=None, tol=1e-5, atol=0.0, maxiter=None, M_diagonal=None, check_every=8):
+def bicgstab_device(A, b, x0=None, tol=1e-5, atol=0.0, maxiter=None, M_diagonal=None, check_every=8, use_graph=False):
     """`bicgstab` with the recurrence scalars kept on the device: the host enqueues `check_every` whole iterations
     (two products, the vector updates gated by the device-side state, five dot products, five one-thread scalar
     stages) without reading anything back, then looks at (state, k) once.  Same iterates, same stopping iteration
     and break-down codes as `bicgstab` (tests/test_solvers_glue_cpu.py compares them); not for SlabOperator (its dot
-    products need a collective between the dot and the scalar stage)."""
+    products need a collective between the dot and the scalar stage).
+    use_graph: the batch of `check_every` iterations contains no host decision, no allocation and no synchronisation,
+    so it is captured once in a CUDA graph (after one eager batch) and replayed -- one launch per batch instead of
+    ~25 per iteration.  (Written without GPU time; tests/test_zzz_graph_bicgstab_gpu.py is its first run.)"""
     L = A.loss
     lib = _lib.load()
     n = b.numel()
@@ -269,7 +272,10 @@ def bicgstab_device(A, b, x0=None, tol=1e-5, atol=0.0, maxiter=None, M_diagonal=
     keep[[_BB, _RS, _RHO_NEW]] = True
     sc.copy_(torch.where(keep.to(sc.device), sc, init.to(device=sc.device, dtype=sc.dtype)))
     done = 0
-    while True:
+    graph = None
+
+    def run_batch():
+        nonlocal phat, shat
         for _ in range(check_every):
             stage(0)                                                     # beta | stop test | rho break-down
             vec(_RUN, -1, 1.0, p, _OMEGA, -1.0, q, tmp)                  # tmp = p - omega q
@@ -298,6 +304,17 @@ def bicgstab_device(A, b, x0=None, tol=1e-5, atol=0.0, maxiter=None, M_diagonal=
             dot(r, r, _RS_NEXT)
             dot(rhat, r, _RHO_NEXT)
             stage(4)                                                     # commit the iteration | (alpha, omega) break-down
+
+    while True:
+        if graph is not None:
+            graph.replay()
+        else:
+            run_batch()
+            if use_graph and done == 0:                                  # the first batch ran eagerly: capture the next ones
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    run_batch()
         done += check_every
         state, k = sc[[_STATE, _K]].tolist()                             # one host read per batch
         if int(state) != 0 or done >= maxiter + check_every:

@@ -75,6 +75,15 @@ x2, info2 = linalg.bicgstab_device(A, -R, x0=None, tol=1e-8, atol=0.0, maxiter=i
 torch.cuda.synchronize()
 out["bicgstab_device_scalars_iterations"], out["bicgstab_device_scalars_s"] = info2, time.time() - t0
 out["bicgstab_device_scalars_identical"] = bool(info2 == info and torch.equal(x, x2))
+try:
+    torch.cuda.synchronize()
+    t0 = time.time()
+    x3, info3 = linalg.bicgstab_device(A, -R, x0=None, tol=1e-8, atol=0.0, maxiter=int(os.environ.get("MAXITER", 200)),
+                                       M_diagonal=A.diagonal(), check_every=8, use_graph=True)
+    torch.cuda.synchronize()
+    out["bicgstab_graph_s"], out["bicgstab_graph_identical"] = time.time() - t0, bool(info3 == info and torch.equal(x, x3))
+except Exception as ex:                                   # first run of the graph path: keep the other numbers
+    out["bicgstab_graph_error"] = str(ex)[:200]
 
 resp = FiniteElementResponse("r", "(E**2)*U[0]", loss, NodalControl("E", mesh))
 resp.Initialize()
