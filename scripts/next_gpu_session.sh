@@ -11,6 +11,7 @@ echo "new tests rc=$?"; tail -5 gpurun_out/new_tests.log
 python -m pytest tests -m gpu -q -x > gpurun_out/all_tests.log 2>&1
 echo "all tests rc=$?"; tail -3 gpurun_out/all_tests.log
 python examples/sensitivity_analysis_2D.py 81 > gpurun_out/example_sa.log 2>&1; echo "example rc=$?"; tail -6 gpurun_out/example_sa.log
+python examples/neo_hooke_newton_3D.py 12 > gpurun_out/example_newton.log 2>&1; echo "example rc=$?"; tail -7 gpurun_out/example_newton.log | cut -c1-200
 N=${N:-128} python scripts/solver_bench.py > gpurun_out/solver_bench.json 2> gpurun_out/solver_bench.err
 echo "solver bench rc=$?"; cat gpurun_out/solver_bench.json
 N=${NT:-70} python scripts/newton_bench.py > gpurun_out/newton_bench.json 2> gpurun_out/newton_bench.err
