@@ -15,3 +15,4 @@ from .transient_thermal import (TransientThermalLoss, TransientThermalLoss2DQuad
                                 TransientThermalLoss3DHexa, TransientThermalLoss3DTetra)
 from .phase_field import AllenCahnLoss, AllenCahnLoss2DQuad, AllenCahnLoss2DTri, AllenCahnLoss3DHexa
 from .kratos_small_displacement import KratosSmallDisplacement3DTetra
+from .regression_loss import RegressionLoss

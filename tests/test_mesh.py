@@ -55,3 +55,21 @@ def test_orientation_fix():
     assert (m.elements_nodes["tetra"][2] != conn[2]).any()
     X = m.GetNodesCoordinates()[m.GetElementsNodes("tetra")]
     assert (geometry.point_data(geometry.ELEMENTS["tetra"], X, 1)[2] > 0).all()
+
+
+def test_regression_loss_matches_its_definition():
+    """fol/loss_functions/regression_loss.py:69-96: mean / min / max of the squared error over (batch, -1)."""
+    import torch
+    from folax_b200.loss_functions import RegressionLoss
+    mesh = folax_b200.create_2D_square_mesh(1.0, 3)
+    loss = RegressionLoss("reg", {"nodal_unknows": ["Ux", "Uy"]}, mesh)
+    loss.Initialize()
+    assert loss.non_dirichlet_indices.size == 18 and loss.GetFullDofVector(None, 5) == 5
+    rng = np.random.default_rng(0)
+    gt, pred = rng.standard_normal((4, 9, 2)), rng.standard_normal((4, 18))
+    p = torch.tensor(pred, requires_grad=True)
+    mean, (mn, mx, mean2) = loss.ComputeBatchLoss(gt, p)
+    err = (gt.reshape(4, -1) - pred) ** 2
+    assert np.allclose([float(mean), float(mn), float(mx), float(mean2)], [err.mean(), err.min(), err.max(), err.mean()])
+    mean.backward()
+    assert np.allclose(p.grad.numpy(), -2.0 * (gt.reshape(4, -1) - pred) / err.size)
