@@ -6,7 +6,7 @@
 # 4. the headline bench, 5. launch list + one full ncu capture of the SELL SpMV.  Everything lands in gpurun_out/.
 mkdir -p gpurun_out
 python -m pytest tests/test_zz1_responses_gpu.py tests/test_zz2_solvers_gpu.py tests/test_zz7_second_order_gpu.py \
-       tests/test_zz3_config3_newton_gpu.py tests/test_zz4_config5_slabs_gpu.py tests/test_zz8_ad_variants_gpu.py tests/test_zz6_kratos_class_gpu.py tests/test_zz5_element_api_gpu.py tests/test_zzz_graph_bicgstab_gpu.py -m gpu -q > gpurun_out/new_tests.log 2>&1
+       tests/test_zy1_config3_newton_gpu.py tests/test_zy2_config5_slabs_gpu.py tests/test_zz8_ad_variants_gpu.py tests/test_zy3_kratos_class_gpu.py tests/test_zz5_element_api_gpu.py tests/test_zzz_graph_bicgstab_gpu.py -m gpu -q > gpurun_out/new_tests.log 2>&1
 echo "new tests rc=$?"; tail -5 gpurun_out/new_tests.log
 python -m pytest tests -m gpu -q -x > gpurun_out/all_tests.log 2>&1
 echo "all tests rc=$?"; tail -3 gpurun_out/all_tests.log
