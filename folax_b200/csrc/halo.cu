@@ -34,7 +34,12 @@ __global__ void halo_gather_push_kernel(long long n0, long long count, int d, co
   if (peer_arrive) {
     __threadfence_system();                      // this thread's peer stores are visible system-wide ...
     __syncthreads();                             // ... for every thread of the CTA, before the CTA reports in
-    if (threadIdx.x == 0) atomicAdd_system(peer_arrive, 1ULL);
+    if (threadIdx.x == 0) {
+      // the reporting thread fences AFTER the barrier too: under the PTX memory model only a fence that follows
+      // the barrier (which ordered the other threads' stores before it) is cumulative over the whole CTA's stores
+      __threadfence_system();
+      atomicAdd_system(peer_arrive, 1ULL);
+    }
   }
 }
 

@@ -32,8 +32,8 @@ __global__ void __launch_bounds__(256) gather_values_kernel(long long n, const i
 }
 
 template <class T>
-__global__ void __launch_bounds__(256) vec_op_kernel(long long n, int op, T a, const T* __restrict__ x, T b,
-                                                     const T* __restrict__ y, T* __restrict__ out) {
+__global__ void __launch_bounds__(256) vec_op_kernel(long long n, int op, T a, const T* x, T b, const T* y, T* out) {
+  // no __restrict__: the Krylov loops update in place (out aliases x or y)
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     vec_op_thread<T>(i, op, a, x, b, y, out);

@@ -288,8 +288,23 @@ class FiniteElementLoss(Loss):
 
     # ------------------------------------------------------------------ small API
     def GetFullDofVector(self, known_dofs, unknown_dofs):
-        """fe_loss.py:91-92: all_dofs[:, dirichlet_indices] = dirichlet_values (out of place)."""
+        """fe_loss.py:91-100, 123-124: all_dofs[:, dirichlet_indices] = dirichlet_values (out of place); with
+        `parametric_boundary_learning` the per-sample `known_dofs` (B, n_dirichlet) are written instead
+        (ConstructFullDofVectorParametricLearning -- what the Predict paths call,
+        explicit_parametric_operator_learning.py:117)."""
         u = self._as_batch(unknown_dofs, self.total_number_of_dofs).clone()
+        if self._parametric:
+            if known_dofs is None:
+                raise ValueError(f"{self.GetName()}: parametric_boundary_learning needs known_dofs (B, n_dirichlet)")
+            known = self._as_batch(known_dofs, self.dirichlet_indices.size)
+            if known.shape[0] == 1 and u.shape[0] > 1:
+                known = known.expand(u.shape[0], -1).contiguous()
+            if known.shape[0] != u.shape[0]:
+                raise ValueError(f"{self.GetName()}: {known.shape[0]} samples of known dofs for {u.shape[0]} dof vectors")
+            _lib.check(_lib.load().fol_apply_dirichlet(_lib.stream_ptr(), self._dt, u.shape[0],
+                                                       self.total_number_of_dofs, _lib.ptr(self._dir_idx),
+                                                       self._dir_idx.numel(), _lib.ptr(known), 1, 1.0, _lib.ptr(u)))
+            return u
         _lib.check(_lib.load().fol_apply_dirichlet(_lib.stream_ptr(), self._dt, u.shape[0],
                                                    self.total_number_of_dofs, _lib.ptr(self._dir_idx),
                                                    self._dir_idx.numel(), _lib.ptr(self._dir_val), 0, 1.0,

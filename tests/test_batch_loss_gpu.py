@@ -129,3 +129,9 @@ def test_parametric_boundary_learning():
     want = gU.copy()
     want[:, loss.dirichlet_indices] = 0.0
     assert np.abs(ut.grad.cpu().numpy() - want).max() <= 1e-12 * scale
+    # fe_loss.py:94-95, 123-124: GetFullDofVector writes the PER-SAMPLE known dofs in this mode (what the Predict
+    # paths call, explicit_parametric_operator_learning.py:117), not the settings' boundary values
+    got = loss.GetFullDofVector(known, u).cpu().numpy()
+    assert np.array_equal(got, full)
+    with pytest.raises(ValueError):
+        loss.GetFullDofVector(None, u)
