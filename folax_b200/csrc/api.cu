@@ -21,6 +21,7 @@ int assemble_stvk_f32(cudaStream_t, int, int, const AsmArgs<float>&);
 int assemble_j2_f64(cudaStream_t, int, int, const AsmArgs<double>&);
 int assemble_j2_f32(cudaStream_t, int, int, const AsmArgs<float>&);
 int assemble_hex_mech_f64(cudaStream_t, const AsmArgs<double>&);
+int assemble_hex_j2_f64(cudaStream_t, const AsmArgs<double>&);
 template <class T>
 int assemble_ad(cudaStream_t, int, int, int, const AdAsmArgs<T>&);
 extern std::atomic<int> g_grid_margin;
@@ -91,8 +92,13 @@ static int assemble_typed(cudaStream_t s, int physics, int element, int num_gp, 
 #ifdef FOL_HAVE_J2
     case FOL_J2PLASTICITY:
       if (!st_in || (!st_out && !v)) return fail(FOL_ERR_INVALID, "J2 plasticity needs state_in/state_out");
-      if constexpr (f64) return assemble_j2_f64(s, element, num_gp, a);
-      else return assemble_j2_f32(s, element, num_gp, a);
+      if constexpr (f64) {
+        // tuned Hex8 kernel (csrc/assemble_hex_j2.cu); transpose and the matrix-free mode use the generic kernel
+        if (element == HEX && num_gp == 2 && !transpose && !v && st_out && g_tuned.load()) return assemble_hex_j2_f64(s, a);
+        return assemble_j2_f64(s, element, num_gp, a);
+      } else {
+        return assemble_j2_f32(s, element, num_gp, a);
+      }
 #endif
   }
   return fail(FOL_ERR_UNSUPPORTED, "fol_assemble_elements: unsupported physics");

@@ -16,6 +16,7 @@
 // Ke is symmetric only to rounding here (the scale s_g rides on the A operand of the DMMA), so calls
 // with transpose_jacobian=True are served by the generic kernel, which transposes exactly.
 #include "assemble.cuh"
+#include "assemble_hex_common.cuh"
 
 namespace fol {
 
@@ -33,7 +34,8 @@ constexpr int kSlots = FOL_HEX_SLOTS;   // Ke staging slots per warp
 #define FOL_HEX_HALVES 0
 #endif
 constexpr bool kHalves = FOL_HEX_HALVES != 0;   // release / refill the staging slot in two halves
-constexpr int kTile = 4;             // elements per warp iteration
+using hexk::kTile;
+using namespace hexk;
 
 struct __align__(128) WarpSmem {
   double stage[kSlots][576];         // Ke staging slots (bulk-copy sources)
@@ -50,31 +52,6 @@ struct __align__(128) WarpSmem {
   double wd[kTile][8];               // w detJ per Gauss point (body force)
   float bc[kTile][24];               // 1 = free dof, 0 = Dirichlet dof
 };
-
-__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(d0), "+d"(d1)
-               : "d"(a), "d"(b));
-}
-
-__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, unsigned bytes) {
-  const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(saddr), "r"(bytes)
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
-__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
-  const unsigned saddr = (unsigned)__cvta_generic_to_shared(sdst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 }  // namespace
 
@@ -351,19 +328,10 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
 std::atomic<int> g_grid_margin{0};
 
 int assemble_hex_mech_f64(cudaStream_t s, const AsmArgs<double>& args) {
-  static int grid = 0;
-  static PerDeviceOnce configured;
+  static PerDeviceGrid per_device;
   const size_t smem = sizeof(WarpSmem) * kWarps;
-  if (configured.need() || !grid) {
-    FOL_CUDA(cudaFuncSetAttribute(assemble_hex_mech_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    int dev = 0, sms = 148, per_sm = 1;
-    FOL_CUDA(cudaGetDevice(&dev));
-    FOL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    FOL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, assemble_hex_mech_f64_kernel, kWarps * 32, smem));
-    grid = sms * (per_sm > 0 ? per_sm : 1);
-    configured.done();
-  }
+  int grid = 0;
+  FOL_CUDA(per_device.get(assemble_hex_mech_f64_kernel, kWarps * 32, smem, &grid));
   if (args.ne == 0) return FOL_OK;
   const long long ntiles = cdiv(args.ne, kTile);
   const long long want = cdiv(ntiles, kWarps);

@@ -1,0 +1,362 @@
+// Tuned element-stage kernel for BASELINE.json configs[4]: 3-D Hex8 J2 elastoplasticity with Gauss-point history,
+// float64, 2x2x2 rule (ElastoplasticityLoss3DHexa; mechanical_elastoplasticity.py:32-94, 153-235,
+// plasticity.py:136-325, fe_loss.py:191-230, 299).
+//
+// Same machine mapping as assemble_hex.cu (persistent warps, tiles of 4 elements, cp.async gathers one tile ahead,
+// FP64 tensor-path MMAs, one 4608-byte bulk copy per element matrix), with the point law of j2_point.cuh in phase 1:
+//   * phase 1, lane (element, Gauss point): geometry, strain = B u, radial return + scalar forward-mode tangent
+//     (j2_radial: ~60 registers, no local memory), staged per point: d = dev(e_trial), w detJ sigma and the three
+//     tangent scalars.  The history of the tile arrives by cp.async one tile ahead and the new history leaves as ONE
+//     1792-byte bulk copy per tile (the (ne, 8, 7) layout is contiguous per tile);
+//   * phase 2, lane (row node a, column pair k): the point tangent is C_el - a Dev - b d (x) (w . d), so
+//       Ke_ab = lam P1 + P2/3 + [2G tr(P1) - tr(P2)] I + offdiag(2G P1^T - P2^T) - sum_g (w detJ b) p_a (x) pt_b
+//     with P1 = sum_g w detJ g_a (x) g_b, P2 = sum_g w detJ a_g g_a (x) g_b, p_a = d . g_a, pt_a = (w . d) . g_a:
+//     three 24x24x8 products on the FP64 tensor path (18 DMMA m8n8k4 each), the last one accumulating straight into
+//     the Ke fragment.  Elements without a plastic point (warp-uniform test) skip P2 and the rank-one family: they
+//     cost what the elastic kernel costs.  f_int = sum_g w detJ B^T sigma from the staged stresses (butterfly over
+//     the 4 k-lanes).
+// The reference's strain convention is kept: engineering shears enter the strain TENSOR unhalved
+// (mechanical_elastoplasticity.py:50-55), so the shear stiffness is 2G and C_el = lam 1(x)1 + 2G I_6.
+// transpose_jacobian=True and the matrix-free mode are served by the generic kernel (assemble.cuh).
+#include "assemble.cuh"
+#include "assemble_hex_common.cuh"
+
+namespace fol {
+
+namespace {
+
+using namespace hexk;
+
+constexpr int kWarpsJ2 = 4;          // warps per CTA, each fully independent (2 CTAs = 8 warps / SM: 26 KB of staging each)
+
+struct __align__(128) WarpSmemJ2 {
+  double stage[576];                 // Ke staging slot (bulk-copy source)
+  double2 gxy[kTile][8][8];          // [element][gauss][node ^ swz(gauss)]: (dN/dx, dN/dy), see assemble_hex.cu
+  double2 gzs[kTile][8][8];          //                                      (dN/dz, w detJ)
+  double X[2][3][32];                // nodal data of the tile, SoA over the 32 (element, node) lanes, double-buffered
+  double u[2][3][32];
+  double st[2][7][32];               // history of the tile, SoA over the 32 (element, Gauss point) lanes, double-buffered
+  double dv[6][32];                  // dev of the trial elastic strain          } per (element, Gauss point),
+  double ws[6][32];                  // w detJ sigma                             } SoA: conflict-free phase-1 stores,
+  double wa[32], wb[32], wd[32];     // w detJ a, w detJ b, w detJ               } broadcast phase-2 loads
+  double sto[32 * 7];                // new history in the global (element, point, 7) layout: one bulk copy per tile
+  float bc[kTile][24];               // 1 = free dof, 0 = Dirichlet dof
+};
+
+}  // namespace
+
+__global__ void __launch_bounds__(kWarpsJ2 * 32, 2)
+assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, const int has_body) {
+  extern __shared__ __align__(128) unsigned char smem_raw_j2[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WarpSmemJ2& sm = reinterpret_cast<WarpSmemJ2*>(smem_raw_j2)[warp];
+  const long long nwarps = (long long)gridDim.x * kWarpsJ2;
+  long long tile = (long long)blockIdx.x * kWarpsJ2 + warp;
+  if (tile >= ntiles) return;
+
+  const double E = args.p.v[0], nu = args.p.v[1], y0 = args.p.v[5], h1 = args.p.v[6], h2 = args.p.v[7];
+  const double lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu)), G = E / (2.0 * (1.0 + nu));
+
+  const int el_p = lane >> 3, sub = lane & 7;   // phases 0/1: (element in tile, node | Gauss point)
+  const int ra = lane >> 2, kq = lane & 3;      // phase 2: (row node a, column pair k)
+  const int swz_p = ((sub & 3) << 1) | (sub >> 2);
+
+  // Gauss point `sub` of the 2x2x2 rule (hexahedra_3d_8.py:23-33), trilinear shape data factorised per axis
+  const double px = sgn_x(sub) * FOL_S3, py = sgn_y(sub) * FOL_S3, pz = sgn_z(sub) * FOL_S3;
+  double fyz[2][2], fxz[2][2], fxy[2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      fyz[i][j] = 0.125 * (i ? 1.0 + py : 1.0 - py) * (j ? 1.0 + pz : 1.0 - pz);
+      fxz[i][j] = 0.125 * (i ? 1.0 + px : 1.0 - px) * (j ? 1.0 + pz : 1.0 - pz);
+      fxy[i][j] = 0.125 * (i ? 1.0 + px : 1.0 - px) * (j ? 1.0 + py : 1.0 - py);
+    }
+
+  // software pipeline of the gathers (node ids two tiles ahead, nodal data and history one tile ahead); see
+  // assemble_hex.cu for why the id is held back in its register
+  auto node_of = [&](long long t) -> int {
+    const long long e = t * kTile + el_p;
+    const int ok = (t < ntiles && e < args.ne) ? 1 : 0;
+    const int32_t* src = args.conn + (ok ? e * 8 + sub : 0);
+    int n;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\tmov.s32 %0, 0;\n\t@p ld.global.nc.s32 %0, [%1];\n\t}\n"
+        : "=r"(n)
+        : "l"(src), "r"(ok));
+    return n;
+  };
+  auto hold_back = [](int& a, unsigned& b, unsigned& c, unsigned& d) {
+    asm volatile("" : "+r"(a), "+r"(b), "+r"(c), "+r"(d));
+  };
+  auto gather_async = [&](int buf, long long n, long long t) {
+    const double* gx = args.xyz + n * 3;
+    const double* gu = args.u + n * 3;
+    cp_async8(&sm.X[buf][0][lane], gx); cp_async8(&sm.X[buf][1][lane], gx + 1); cp_async8(&sm.X[buf][2][lane], gx + 2);
+    cp_async8(&sm.u[buf][0][lane], gu); cp_async8(&sm.u[buf][1][lane], gu + 1); cp_async8(&sm.u[buf][2][lane], gu + 2);
+    // history of (element, Gauss point) = this lane; tiles past the end read element 0 (never used)
+    const long long e = t * kTile + el_p;
+    const double* gs = args.state_in + ((t < ntiles && e < args.ne) ? (e * 8 + sub) * 7 : 0);
+#pragma unroll
+    for (int s = 0; s < 7; ++s) cp_async8(&sm.st[buf][s][lane], gs + s);
+    cp_async_commit();
+  };
+  int n_next = node_of(tile + nwarps);
+  const long long n_first = node_of(tile);
+  gather_async(0, n_first, tile);
+  const uint8_t* pf0 = args.dir + n_first * 3;
+  unsigned f0 = __ldg(pf0), f1 = __ldg(pf0 + 1), f2 = __ldg(pf0 + 2);
+  int buf = 0;
+
+  for (; tile < ntiles; tile += nwarps, buf ^= 1) {
+    const long long e0 = tile * kTile;
+    hold_back(n_next, f0, f1, f2);
+
+    // ---- phase 0: this tile's nodal data and history have landed; start the next gather
+    sm.bc[el_p][sub * 3 + 0] = f0 ? 0.f : 1.f;
+    sm.bc[el_p][sub * 3 + 1] = f1 ? 0.f : 1.f;
+    sm.bc[el_p][sub * 3 + 2] = f2 ? 0.f : 1.f;
+    cp_async_wait_all();
+    __syncwarp();
+    gather_async(buf ^ 1, (long long)n_next, tile + nwarps);
+    {
+      const uint8_t* pf = args.dir + (long long)n_next * 3;
+      f0 = __ldg(pf); f1 = __ldg(pf + 1); f2 = __ldg(pf + 2);
+    }
+    n_next = node_of(tile + 2 * nwarps);
+
+    // ---- phase 1: lane (element, Gauss point): geometry (geometry.py:88-97), strain = B u, return mapping
+    unsigned plastic_mask;
+    {
+      double J[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double j0 = 0.0, j1 = 0.0, j2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          const int bx = ((a & 3) == 1 || (a & 3) == 2), by = (a >> 1) & 1, bz = (a >> 2) & 1;
+          const double x = sm.X[buf][i][el_p * 8 + a];
+          j0 += (bx ? x : -x) * fyz[by][bz];
+          j1 += (by ? x : -x) * fxz[bx][bz];
+          j2 += (bz ? x : -x) * fxy[bx][by];
+        }
+        J[i][0] = j0; J[i][1] = j1; J[i][2] = j2;
+      }
+      const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+      const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+      const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+      const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+      const double rd = 1.0 / det;
+      double inv[3][3];
+      inv[0][0] = c00 * rd; inv[1][0] = c01 * rd; inv[2][0] = c02 * rd;
+      inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * rd;
+      inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * rd;
+      inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * rd;
+      inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * rd;
+      inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * rd;
+      inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * rd;
+      const double wd = det;  // Gauss weight is 1
+      double H[3][3];         // displacement gradient H[i][k] = sum_a u_a[i] dN_a/dx_k
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) H[i][k] = 0.0;
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        const int bx = ((a & 3) == 1 || (a & 3) == 2), by = (a >> 1) & 1, bz = (a >> 2) & 1;
+        const double d0 = bx ? fyz[by][bz] : -fyz[by][bz];
+        const double d1 = by ? fxz[bx][bz] : -fxz[bx][bz];
+        const double d2 = bz ? fxy[bx][by] : -fxy[bx][by];
+        double g[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) g[k] = d0 * inv[0][k] + d1 * inv[1][k] + d2 * inv[2][k];
+        sm.gxy[el_p][sub][a ^ swz_p] = make_double2(g[0], g[1]);
+        sm.gzs[el_p][sub][a ^ swz_p] = make_double2(g[2], wd);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const double ui = sm.u[buf][i][el_p * 8 + a];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) H[i][k] += ui * g[k];
+        }
+      }
+      // rows of the linear B matrix (mechanical.py:46-58): [xx, yy, zz, xy, yz, xz], engineering shears
+      const double e_tot[6] = {H[0][0], H[1][1], H[2][2], H[0][1] + H[1][0], H[1][2] + H[2][1], H[0][2] + H[2][0]};
+      double ep[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) ep[k] = sm.st[buf][k][lane];
+      const double xi = sm.st[buf][6][lane];
+      J2Point<double> p;
+      j2_radial<double>(e_tot, ep, xi, lam, G, y0, h1, h2, p);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        sm.dv[k][lane] = p.d[k];
+        sm.ws[k][lane] = wd * p.sig[k];
+        sm.sto[lane * 7 + k] = ep[k] + p.c * p.d[k];
+      }
+      sm.sto[lane * 7 + 6] = xi + p.dl;
+      sm.wa[lane] = wd * p.a;
+      sm.wb[lane] = wd * p.b;
+      sm.wd[lane] = wd;
+      plastic_mask = __ballot_sync(0xffffffffu, (p.a != 0.0) | (p.b != 0.0));
+    }
+    fence_async_smem();
+    __syncwarp();
+    {  // new history of the tile: one contiguous bulk copy (mechanical_elastoplasticity.py:217)
+      long long cnt = args.ne - e0;
+      cnt = cnt > kTile ? kTile : cnt;
+      if (lane == 0) bulk_store(args.state_out + e0 * 56, sm.sto, (unsigned)(cnt * 56 * sizeof(double)));
+    }
+
+    // ---- phase 2: one element at a time, lane (a, k)
+#pragma unroll 1
+    for (int el = 0; el < kTile; ++el) {
+      const long long e = e0 + el;
+      if (e >= args.ne) break;
+      const bool plastic = ((plastic_mask >> (el * 8)) & 0xffu) != 0u;   // warp-uniform
+      double c1[3][3][2], K[2][3][3];
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) c1[t][s][0] = c1[t][s][1] = 0.0;
+      double bf[2][3], r[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int gp = 4 * kk + kq;
+        const double2 xy = sm.gxy[el][gp][ra ^ ((kq << 1) | kk)];
+        const double2 zs = sm.gzs[el][gp][ra ^ ((kq << 1) | kk)];
+        bf[kk][0] = xy.x; bf[kk][1] = xy.y; bf[kk][2] = zs.x;
+        const double af[3] = {zs.y * xy.x, zs.y * xy.y, zs.y * zs.x};
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+          for (int s = 0; s < 3; ++s) dmma884(c1[t][s][0], c1[t][s][1], af[t], bf[kk][s]);
+        // f_int share of this lane's two Gauss points: (w detJ sigma) . grad N_a
+        const int ix = el * 8 + gp;
+        const double s0 = sm.ws[0][ix], s1 = sm.ws[1][ix], s2 = sm.ws[2][ix];
+        const double s3 = sm.ws[3][ix], s4 = sm.ws[4][ix], s5 = sm.ws[5][ix];
+        r[0] += s0 * xy.x + s3 * xy.y + s5 * zs.x;
+        r[1] += s3 * xy.x + s1 * xy.y + s4 * zs.x;
+        r[2] += s5 * xy.x + s4 * xy.y + s2 * zs.x;
+      }
+      if (!plastic) {
+        // all eight points elastic: C_el = lam 1(x)1 + 2G I_6
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double tr = c1[0][0][h] + c1[1][1][h] + c1[2][2][h];
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              K[h][i][j] = lam * c1[i][j][h] + (i == j ? 2.0 * G * tr : 2.0 * G * c1[j][i][h]);
+        }
+      } else {
+        double c2[3][3][2];
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+          for (int s = 0; s < 3; ++s) c2[t][s][0] = c2[t][s][1] = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const double wa = sm.wa[el * 8 + 4 * kk + kq];
+          const double af[3] = {wa * bf[kk][0], wa * bf[kk][1], wa * bf[kk][2]};
+#pragma unroll
+          for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) dmma884(c2[t][s][0], c2[t][s][1], af[t], bf[kk][s]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double tr = 2.0 * G * (c1[0][0][h] + c1[1][1][h] + c1[2][2][h]) - (c2[0][0][h] + c2[1][1][h] + c2[2][2][h]);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              K[h][i][j] = lam * c1[i][j][h] + (1.0 / 3.0) * c2[i][j][h] +
+                           (i == j ? tr : 2.0 * G * c1[j][i][h] - c2[j][i][h]);
+        }
+        // rank-one family: Ke -= sum_g (w detJ b) p (x) pt, accumulated on the tensor path into the Ke fragment
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const int ix = el * 8 + 4 * kk + kq;
+          const double d0 = sm.dv[0][ix], d1 = sm.dv[1][ix], d2 = sm.dv[2][ix];
+          const double d3 = sm.dv[3][ix], d4 = sm.dv[4][ix], d5 = sm.dv[5][ix];
+          const double wb = -sm.wb[ix];
+          const double gx = bf[kk][0], gy = bf[kk][1], gz = bf[kk][2];
+          const double sx = d3 * gy + d5 * gz, sy = d3 * gx + d4 * gz, sz = d5 * gx + d4 * gy;   // shear parts
+          const double nx = d0 * gx, ny = d1 * gy, nz = d2 * gz;
+          const double af[3] = {wb * (nx + sx), wb * (ny + sy), wb * (nz + sz)};
+          const double pt[3] = {nx + 2.0 * sx, ny + 2.0 * sy, nz + 2.0 * sz};
+#pragma unroll
+          for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) dmma884(K[0][t][s], K[1][t][s], af[t], pt[s]);
+        }
+      }
+      // f_int of node a: butterfly over the 4 k-lanes (each holds two of the eight Gauss points)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        r[i] += __shfl_xor_sync(0xffffffffu, r[i], 1);
+        r[i] += __shfl_xor_sync(0xffffffffu, r[i], 2);
+      }
+      if (has_body) {  // Fe_a = b * sum_g w detJ N_a(g)
+        double nw = 0.0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const double gx = 1.0 + sgn_x(ra) * sgn_x(g) * FOL_S3, gy = 1.0 + sgn_y(ra) * sgn_y(g) * FOL_S3;
+          const double gz = 1.0 + sgn_z(ra) * sgn_z(g) * FOL_S3;
+          nw += sm.wd[el * 8 + g] * (0.125 * gx * gy * gz);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) r[i] -= args.p.v[2 + i] * nw;
+      }
+      // Dirichlet row mask (fe_loss.py:191-207): only for elements touching a fixed dof (warp-uniform test)
+      const bool fixed_rows = (sm.bc[el][ra * 3 + 0] == 0.f) | (sm.bc[el][ra * 3 + 1] == 0.f) |
+                              (sm.bc[el][ra * 3 + 2] == 0.f);
+      const bool any_fixed = __any_sync(0xffffffffu, fixed_rows);
+      if (lane == 0) bulk_wait_read<0>();   // the copies that last used the staging slot / the history buffer are done
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int row = ra * 3 + i;
+        const bool freerow = !any_fixed || sm.bc[el][row] != 0.f;
+        double v[6];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const int col = (2 * kq + h) * 3 + j;
+            v[h * 3 + j] = (freerow || col == row) ? K[h][i][j] : 0.0;
+          }
+        double2* dst = reinterpret_cast<double2*>(sm.stage + row * 24 + kq * 6);
+        dst[0] = make_double2(v[0], v[1]);
+        dst[1] = make_double2(v[2], v[3]);
+        dst[2] = make_double2(v[4], v[5]);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) bulk_store(args.ke + e * 576, sm.stage, 576 * sizeof(double));
+      if (kq == 0) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          args.re[e * 24 + ra * 3 + i] = (any_fixed && sm.bc[el][ra * 3 + i] == 0.f) ? 0.0 : r[i];
+      }
+    }
+    __syncwarp();  // everyone is done with X / u / history / gradients of this tile
+  }
+  if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last copies
+}
+
+int assemble_hex_j2_f64(cudaStream_t s, const AsmArgs<double>& args) {
+  static PerDeviceGrid grid;
+  const size_t smem = sizeof(WarpSmemJ2) * kWarpsJ2;
+  int g = 0;
+  FOL_CUDA(grid.get(assemble_hex_j2_f64_kernel, kWarpsJ2 * 32, smem, &g));
+  if (args.ne == 0) return FOL_OK;
+  const long long ntiles = cdiv(args.ne, kTile);
+  const long long want = cdiv(ntiles, kWarpsJ2);
+  const int has_body = (args.p.v[2] != 0.0 || args.p.v[3] != 0.0 || args.p.v[4] != 0.0) ? 1 : 0;
+  assemble_hex_j2_f64_kernel<<<(unsigned)(want < g ? want : g), kWarpsJ2 * 32, smem, s>>>(args, ntiles, has_body);
+  return check_launch("assemble_hex_j2_f64_kernel");
+}
+
+}  // namespace fol

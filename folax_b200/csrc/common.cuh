@@ -56,6 +56,35 @@ struct PerDeviceOnce {
   }
 };
 
+// Persistent-kernel grid (SMs x resident CTAs per SM) of one kernel, configured and remembered PER DEVICE (a process
+// may drive several GPUs with different SM counts); devices >= 64 are re-queried on every call.
+struct PerDeviceGrid {
+  std::atomic<int> grid[64] = {};
+  template <class Kernel>
+  cudaError_t get(Kernel kernel, int block, size_t smem, int* out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) {
+      const int g = grid[dev].load(std::memory_order_relaxed);
+      if (g > 0) {
+        *out = g;
+        return cudaSuccess;
+      }
+    }
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int sms = 148, per_sm = 1;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
+    if (e != cudaSuccess) return e;
+    *out = sms * (per_sm > 0 ? per_sm : 1);
+    if (dev >= 0 && dev < 64) grid[dev].store(*out, std::memory_order_relaxed);
+    return cudaSuccess;
+  }
+};
+
 // material / loss parameters in the arithmetic type of the call (see FOL_NUM_PARAMS)
 template <class T>
 struct Params {

@@ -47,6 +47,7 @@ _bicg = linalg.bicgstab
 def bicg(*a, **k):
     x, info = timed(_bicg, "krylov_s")(*a, **k)
     split["krylov_iterations"] += max(info, 0)
+    print(f"bicgstab info {info}  |x| {float(torch.linalg.norm(x)):.3e}", file=sys.stderr)
     split["newton_iterations"] += 1
     return x, info
 

@@ -28,7 +28,7 @@ def build_shim(out_dir=None):
     import hashlib
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     shim_dir = os.path.join(ROOT, "tests", "host_shim")
-    srcs = [os.path.join(shim_dir, f) for f in ("adjoint_host.cu", "krylov_host.cu", "assemble_ad_host.cu")]
+    srcs = [os.path.join(shim_dir, f) for f in ("adjoint_host.cu", "krylov_host.cu", "assemble_ad_host.cu", "j2_host.cu")]
     csrc = os.path.join(ROOT, "folax_b200", "csrc")
     deps = srcs + [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith((".cuh", ".h"))] + \
         [os.path.join(ROOT, "include", "folax_b200.h")]
