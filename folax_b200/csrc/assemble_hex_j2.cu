@@ -8,13 +8,14 @@
 //     (j2_radial: ~60 registers, no local memory), staged per point: d = dev(e_trial), w detJ sigma and the three
 //     tangent scalars.  The history of the tile arrives by cp.async one tile ahead and the new history leaves as ONE
 //     1792-byte bulk copy per tile (the (ne, 8, 7) layout is contiguous per tile);
-//   * phase 2, lane (row node a, column pair k): the point tangent is C_el - a Dev - b d (x) (w . d), so
-//       Ke_ab = lam P1 + P2/3 + [2G tr(P1) - tr(P2)] I + offdiag(2G P1^T - P2^T) - sum_g (w detJ b) p_a (x) pt_b
-//     with P1 = sum_g w detJ g_a (x) g_b, P2 = sum_g w detJ a_g g_a (x) g_b, p_a = d . g_a, pt_a = (w . d) . g_a:
-//     three 24x24x8 products on the FP64 tensor path (18 DMMA m8n8k4 each), the last one accumulating straight into
-//     the Ke fragment.  Elements without a plastic point (warp-uniform test) skip P2 and the rank-one family: they
-//     cost what the elastic kernel costs.  f_int = sum_g w detJ B^T sigma from the staged stresses (butterfly over
-//     the 4 k-lanes).
+//   * phase 2, lane (row node a, column pair k): the point tangent is C_el - a Dev - b d (x) (w . d), i.e. an isotropic
+//     matrix with point-wise moduli (lam + a/3, 2G - a) minus a rank-one term, so
+//       Ke_ab = P1 + tr(P2) I + offdiag(P2^T) - sum_g (w detJ b) p_a (x) pt_b,
+//     P1 = sum_g w detJ (lam + a_g/3) g_a (x) g_b,  P2 = sum_g w detJ (2G - a_g) g_a (x) g_b,  p_a = d . g_a,
+//     pt_a = (w . d) . g_a: three 24x24x8 products on the FP64 tensor path (18 DMMA m8n8k4 each); P1 and the rank-one
+//     family accumulate straight into the Ke fragment.  Elements without a plastic point (warp-uniform test) run ONE
+//     family and apply the constant moduli afterwards: they cost what the elastic kernel costs.
+//     f_int = sum_g w detJ B^T sigma from the staged stresses (butterfly over the 4 k-lanes).
 // The reference's strain convention is kept: engineering shears enter the strain TENSOR unhalved
 // (mechanical_elastoplasticity.py:50-55), so the shear stiffness is 2G and C_el = lam 1(x)1 + 2G I_6.
 // transpose_jacobian=True and the matrix-free mode are served by the generic kernel (assemble.cuh).
@@ -27,7 +28,10 @@ namespace {
 
 using namespace hexk;
 
-constexpr int kWarpsJ2 = 4;          // warps per CTA, each fully independent (2 CTAs = 8 warps / SM: 26 KB of staging each)
+#ifndef FOL_J2_WARPS
+#define FOL_J2_WARPS 5
+#endif
+constexpr int kWarpsJ2 = FOL_J2_WARPS;   // warps per CTA, each fully independent (2 CTAs / SM, 22 KB of staging per warp)
 
 struct __align__(128) WarpSmemJ2 {
   double stage[576];                 // Ke staging slot (bulk-copy source)
@@ -38,7 +42,8 @@ struct __align__(128) WarpSmemJ2 {
   double st[2][7][32];               // history of the tile, SoA over the 32 (element, Gauss point) lanes, double-buffered
   double dv[6][32];                  // dev of the trial elastic strain          } per (element, Gauss point),
   double ws[6][32];                  // w detJ sigma                             } SoA: conflict-free phase-1 stores,
-  double wa[32], wb[32], wd[32];     // w detJ a, w detJ b, w detJ               } broadcast phase-2 loads
+  double wl[32], wm[32], wb[32];     // w detJ (lam + a/3), w detJ (2G - a), w detJ b   } broadcast phase-2 loads
+  double wd[32];                     // w detJ (body force)
   double sto[32 * 7];                // new history in the global (element, point, 7) layout: one bulk copy per tile
   float bc[kTile][24];               // 1 = free dof, 0 = Dirichlet dof
 };
@@ -194,7 +199,8 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
         sm.sto[lane * 7 + k] = ep[k] + p.c * p.d[k];
       }
       sm.sto[lane * 7 + 6] = xi + p.dl;
-      sm.wa[lane] = wd * p.a;
+      sm.wl[lane] = wd * (lam + p.a * (1.0 / 3.0));
+      sm.wm[lane] = wd * (2.0 * G - p.a);
       sm.wb[lane] = wd * p.b;
       sm.wd[lane] = wd;
       plastic_mask = __ballot_sync(0xffffffffu, (p.a != 0.0) | (p.b != 0.0));
@@ -213,66 +219,66 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
       const long long e = e0 + el;
       if (e >= args.ne) break;
       const bool plastic = ((plastic_mask >> (el * 8)) & 0xffu) != 0u;   // warp-uniform
-      double c1[3][3][2], K[2][3][3];
+      // K[t][s][h]: Ke blocks (a, 2k + h), entry (t, s); cs: the second family (plastic elements only)
+      double K[3][3][2], cs[3][3][2];
 #pragma unroll
       for (int t = 0; t < 3; ++t)
 #pragma unroll
-        for (int s = 0; s < 3; ++s) c1[t][s][0] = c1[t][s][1] = 0.0;
+        for (int s = 0; s < 3; ++s) K[t][s][0] = K[t][s][1] = cs[t][s][0] = cs[t][s][1] = 0.0;
       double bf[2][3], r[3] = {0.0, 0.0, 0.0};
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
-        const int gp = 4 * kk + kq;
+        const int gp = 4 * kk + kq, ix = el * 8 + gp;
         const double2 xy = sm.gxy[el][gp][ra ^ ((kq << 1) | kk)];
         const double2 zs = sm.gzs[el][gp][ra ^ ((kq << 1) | kk)];
         bf[kk][0] = xy.x; bf[kk][1] = xy.y; bf[kk][2] = zs.x;
-        const double af[3] = {zs.y * xy.x, zs.y * xy.y, zs.y * zs.x};
-#pragma unroll
-        for (int t = 0; t < 3; ++t)
-#pragma unroll
-          for (int s = 0; s < 3; ++s) dmma884(c1[t][s][0], c1[t][s][1], af[t], bf[kk][s]);
         // f_int share of this lane's two Gauss points: (w detJ sigma) . grad N_a
-        const int ix = el * 8 + gp;
         const double s0 = sm.ws[0][ix], s1 = sm.ws[1][ix], s2 = sm.ws[2][ix];
         const double s3 = sm.ws[3][ix], s4 = sm.ws[4][ix], s5 = sm.ws[5][ix];
         r[0] += s0 * xy.x + s3 * xy.y + s5 * zs.x;
         r[1] += s3 * xy.x + s1 * xy.y + s4 * zs.x;
         r[2] += s5 * xy.x + s4 * xy.y + s2 * zs.x;
-      }
-      if (!plastic) {
-        // all eight points elastic: C_el = lam 1(x)1 + 2G I_6
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const double tr = c1[0][0][h] + c1[1][1][h] + c1[2][2][h];
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-              K[h][i][j] = lam * c1[i][j][h] + (i == j ? 2.0 * G * tr : 2.0 * G * c1[j][i][h]);
-        }
-      } else {
-        double c2[3][3][2];
-#pragma unroll
-        for (int t = 0; t < 3; ++t)
-#pragma unroll
-          for (int s = 0; s < 3; ++s) c2[t][s][0] = c2[t][s][1] = 0.0;
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          const double wa = sm.wa[el * 8 + 4 * kk + kq];
-          const double af[3] = {wa * bf[kk][0], wa * bf[kk][1], wa * bf[kk][2]};
+        if (!plastic) {
+          // all eight points elastic: one family P = sum_g w detJ g_a (x) g_b, moduli applied afterwards
+          const double af[3] = {zs.y * xy.x, zs.y * xy.y, zs.y * zs.x};
 #pragma unroll
           for (int t = 0; t < 3; ++t)
 #pragma unroll
-            for (int s = 0; s < 3; ++s) dmma884(c2[t][s][0], c2[t][s][1], af[t], bf[kk][s]);
+            for (int s = 0; s < 3; ++s) dmma884(K[t][s][0], K[t][s][1], af[t], bf[kk][s]);
+        } else {
+          // the moduli differ from point to point: family 1 weighted by w detJ (lam + a/3) accumulates straight into
+          // Ke, family 2 weighted by w detJ (2G - a) enters transposed within the 3x3 blocks
+          const double wl = sm.wl[ix], wm = sm.wm[ix];
+          const double al[3] = {wl * xy.x, wl * xy.y, wl * zs.x};
+          const double am[3] = {wm * xy.x, wm * xy.y, wm * zs.x};
+#pragma unroll
+          for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              dmma884(K[t][s][0], K[t][s][1], al[t], bf[kk][s]);
+              dmma884(cs[t][s][0], cs[t][s][1], am[t], bf[kk][s]);
+            }
         }
+      }
+      if (!plastic) {
+        // C_el = lam 1(x)1 + 2G I_6:  Ke = lam P + 2G [tr(P) I + offdiag(P^T)]
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const double tr = 2.0 * G * (c1[0][0][h] + c1[1][1][h] + c1[2][2][h]) - (c2[0][0][h] + c2[1][1][h] + c2[2][2][h]);
+          const double p00 = K[0][0][h], p01 = K[0][1][h], p02 = K[0][2][h], p10 = K[1][0][h], p11 = K[1][1][h],
+                       p12 = K[1][2][h], p20 = K[2][0][h], p21 = K[2][1][h], p22 = K[2][2][h];
+          const double tr = 2.0 * G * (p00 + p11 + p22);
+          K[0][0][h] = lam * p00 + tr; K[0][1][h] = lam * p01 + 2.0 * G * p10; K[0][2][h] = lam * p02 + 2.0 * G * p20;
+          K[1][0][h] = lam * p10 + 2.0 * G * p01; K[1][1][h] = lam * p11 + tr; K[1][2][h] = lam * p12 + 2.0 * G * p21;
+          K[2][0][h] = lam * p20 + 2.0 * G * p02; K[2][1][h] = lam * p21 + 2.0 * G * p12; K[2][2][h] = lam * p22 + tr;
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double tr = cs[0][0][h] + cs[1][1][h] + cs[2][2][h];
 #pragma unroll
           for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j)
-              K[h][i][j] = lam * c1[i][j][h] + (1.0 / 3.0) * c2[i][j][h] +
-                           (i == j ? tr : 2.0 * G * c1[j][i][h] - c2[j][i][h]);
+            for (int j = 0; j < 3; ++j) K[i][j][h] += (i == j) ? tr : cs[j][i][h];
         }
         // rank-one family: Ke -= sum_g (w detJ b) p (x) pt, accumulated on the tensor path into the Ke fragment
 #pragma unroll
@@ -289,7 +295,7 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
 #pragma unroll
           for (int t = 0; t < 3; ++t)
 #pragma unroll
-            for (int s = 0; s < 3; ++s) dmma884(K[0][t][s], K[1][t][s], af[t], pt[s]);
+            for (int s = 0; s < 3; ++s) dmma884(K[t][s][0], K[t][s][1], af[t], pt[s]);
         }
       }
       // f_int of node a: butterfly over the 4 k-lanes (each holds two of the eight Gauss points)
@@ -315,22 +321,32 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
       const bool any_fixed = __any_sync(0xffffffffu, fixed_rows);
       if (lane == 0) bulk_wait_read<0>();   // the copies that last used the staging slot / the history buffer are done
       __syncwarp();
+      if (!any_fixed) {
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int row = ra * 3 + i;
-        const bool freerow = !any_fixed || sm.bc[el][row] != 0.f;
-        double v[6];
+        for (int i = 0; i < 3; ++i) {
+          double2* dst = reinterpret_cast<double2*>(sm.stage + (ra * 3 + i) * 24 + kq * 6);
+          dst[0] = make_double2(K[i][0][0], K[i][1][0]);
+          dst[1] = make_double2(K[i][2][0], K[i][0][1]);
+          dst[2] = make_double2(K[i][1][1], K[i][2][1]);
+        }
+      } else {
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int i = 0; i < 3; ++i) {
+          const int row = ra * 3 + i;
+          const bool freerow = sm.bc[el][row] != 0.f;
+          double v[6];
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const int col = (2 * kq + h) * 3 + j;
-            v[h * 3 + j] = (freerow || col == row) ? K[h][i][j] : 0.0;
-          }
-        double2* dst = reinterpret_cast<double2*>(sm.stage + row * 24 + kq * 6);
-        dst[0] = make_double2(v[0], v[1]);
-        dst[1] = make_double2(v[2], v[3]);
-        dst[2] = make_double2(v[4], v[5]);
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const int col = (2 * kq + h) * 3 + j;
+              v[h * 3 + j] = (freerow || col == row) ? K[i][j][h] : 0.0;
+            }
+          double2* dst = reinterpret_cast<double2*>(sm.stage + row * 24 + kq * 6);
+          dst[0] = make_double2(v[0], v[1]);
+          dst[1] = make_double2(v[2], v[3]);
+          dst[2] = make_double2(v[4], v[5]);
+        }
       }
       fence_async_smem();
       __syncwarp();
