@@ -75,6 +75,9 @@ SIGNATURES = {
     "fol_halo_gather_push": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _int, _i32p, _i32p, _vp, _vp]),
     "fol_halo_add": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _int, _vp]),
     "fol_halo_timeouts": (_i64, [_vp]),
+    "fol_assemble_elements_halo": (_int, [_vp, _int, _int, _int, _int, _i64, _i64, _vp, _i32p, _vp, _vp, _u8p, C.POINTER(_dbl), _vp,
+                                          _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32p, _i32p, _vp]),
+    "fol_residual_gather_halo": (_int, [_vp, _vp, _i64, _i64, _i64, _i32p, _i32p, _vp, _vp]),
     "fol_plan_assemble_host": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
     "fol_plan_assemble_device": (_int, [_vp, _int, _vp, _vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "fol_plan_stream": (_vp, [_vp]),

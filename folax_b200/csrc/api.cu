@@ -20,8 +20,9 @@ int assemble_stvk_f64(cudaStream_t, int, int, const AsmArgs<double>&);
 int assemble_stvk_f32(cudaStream_t, int, int, const AsmArgs<float>&);
 int assemble_j2_f64(cudaStream_t, int, int, const AsmArgs<double>&);
 int assemble_j2_f32(cudaStream_t, int, int, const AsmArgs<float>&);
-int assemble_hex_mech_f64(cudaStream_t, const AsmArgs<double>&);
-int assemble_hex_j2_f64(cudaStream_t, const AsmArgs<double>&);
+namespace hexk { struct HaloFuse; }
+int assemble_hex_mech_f64(cudaStream_t, const AsmArgs<double>&, const hexk::HaloFuse* = nullptr);
+int assemble_hex_j2_f64(cudaStream_t, const AsmArgs<double>&, const hexk::HaloFuse* = nullptr);
 template <class T>
 int assemble_ad(cudaStream_t, int, int, int, const AdAsmArgs<T>&);
 extern std::atomic<int> g_grid_margin;

@@ -55,14 +55,21 @@ struct __align__(128) WarpSmem {
 
 }  // namespace
 
+template <bool FUSE>
 __global__ void __launch_bounds__(kWarps * 32)
-assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles, const int has_body) {
+assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles, const int has_body, const HaloFuse hf) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
   const long long nwarps = (long long)gridDim.x * kWarps;
-  long long tile = (long long)blockIdx.x * kWarps + warp;
-  if (tile >= ntiles) return;
+  // vt: position in the visiting order (interface layers first when FUSE), tile: the tile itself
+  long long vt = (long long)blockIdx.x * kWarps + warp;
+  if (vt >= ntiles) return;
+  auto real_tile = [&](long long v) -> long long {
+    if constexpr (FUSE) return v < ntiles ? halo_real_tile(hf, v, ntiles) : v;
+    else return v;
+  };
+  bool push_done = !FUSE;
 
   const double E = args.p.v[0], nu = args.p.v[1];
   const double c1 = E / ((1.0 + nu) * (1.0 - 2.0 * nu));
@@ -92,7 +99,8 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
   // The id comes back through a predicated load straight into its 32-bit register and is widened only where it is
   // used, one tile later (hold_back below): any earlier dependent instruction -- a select, a sign extension --
   // would make the warp sit out the full DRAM latency of the connectivity load (21 % of the stall samples before).
-  auto node_of = [&](long long t) -> int {
+  auto node_of = [&](long long v) -> int {
+    const long long t = real_tile(v);
     const long long e = t * kTile + el_p;
     const int ok = (t < ntiles && e < args.ne) ? 1 : 0;
     const int32_t* src = args.conn + (ok ? e * 8 + sub : 0);
@@ -117,15 +125,15 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
   };
   // Dirichlet flags of the next tile's node: three byte loads kept in three registers, consumed one
   // tile later (packing them right away would stall on the load latency)
-  int n_next = node_of(tile + nwarps);
-  const long long n_first = node_of(tile);
+  int n_next = node_of(vt + nwarps);
+  const long long n_first = node_of(vt);
   gather_async(0, n_first);
   const uint8_t* pf0 = args.dir + n_first * 3;
   unsigned f0 = __ldg(pf0), f1 = __ldg(pf0 + 1), f2 = __ldg(pf0 + 2);
   int buf = 0;
 
-  for (; tile < ntiles; tile += nwarps, buf ^= 1) {
-    const long long e0 = tile * kTile;
+  for (; vt < ntiles; vt += nwarps, buf ^= 1) {
+    const long long e0 = real_tile(vt) * kTile;
     hold_back(n_next, f0, f1, f2);   // loaded one tile ago; nothing may consume them before this point
 
     // ---- phase 0: this tile's nodal data has landed in shared memory; start the next gather
@@ -139,7 +147,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
       const uint8_t* pf = args.dir + (long long)n_next * 3;
       f0 = __ldg(pf); f1 = __ldg(pf + 1); f2 = __ldg(pf + 2);
     }
-    n_next = node_of(tile + 2 * nwarps);
+    n_next = node_of(vt + 2 * nwarps);
 
     // ---- phase 1: lane (element, Gauss point): J, det J, grad N, coefficient (geometry.py:88-97)
     {
@@ -321,17 +329,25 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
       }
     }
     __syncwarp();  // everyone is done with X / u / gradients of this tile
+    if constexpr (FUSE) {
+      if (vt < hf.tiles_lo + hf.tiles_hi) halo_tile_done(hf, lane);
+      if (!push_done) push_done = halo_try_push(hf, lane);
+    }
+  }
+  if constexpr (FUSE) {
+    if (!push_done) halo_drain(hf, lane);
   }
   if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last copies
 }
 
 std::atomic<int> g_grid_margin{0};
 
-int assemble_hex_mech_f64(cudaStream_t s, const AsmArgs<double>& args) {
-  static PerDeviceGrid per_device;
+int assemble_hex_mech_f64(cudaStream_t s, const AsmArgs<double>& args, const HaloFuse* hf) {
+  static PerDeviceGrid per_device, per_device_fused;
   const size_t smem = sizeof(WarpSmem) * kWarps;
   int grid = 0;
-  FOL_CUDA(per_device.get(assemble_hex_mech_f64_kernel, kWarps * 32, smem, &grid));
+  if (hf) FOL_CUDA(per_device_fused.get(assemble_hex_mech_f64_kernel<true>, kWarps * 32, smem, &grid));
+  else FOL_CUDA(per_device.get(assemble_hex_mech_f64_kernel<false>, kWarps * 32, smem, &grid));
   if (args.ne == 0) return FOL_OK;
   const long long ntiles = cdiv(args.ne, kTile);
   const long long want = cdiv(ntiles, kWarps);
@@ -339,7 +355,9 @@ int assemble_hex_mech_f64(cudaStream_t s, const AsmArgs<double>& args) {
   // persistent grid, optionally leaving room for communication kernels that must run concurrently
   int g = grid - g_grid_margin.load();
   if (g < 1) g = 1;
-  assemble_hex_mech_f64_kernel<<<(unsigned)(want < g ? want : g), kWarps * 32, smem, s>>>(args, ntiles, has_body);
+  const unsigned blocks = (unsigned)(want < g ? want : g);
+  if (hf) assemble_hex_mech_f64_kernel<true><<<blocks, kWarps * 32, smem, s>>>(args, ntiles, has_body, *hf);
+  else assemble_hex_mech_f64_kernel<false><<<blocks, kWarps * 32, smem, s>>>(args, ntiles, has_body, HaloFuse{});
   return check_launch("assemble_hex_mech_f64_kernel");
 }
 

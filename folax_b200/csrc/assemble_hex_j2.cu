@@ -50,14 +50,21 @@ struct __align__(128) WarpSmemJ2 {
 
 }  // namespace
 
+template <bool FUSE>
 __global__ void __launch_bounds__(kWarpsJ2 * 32, 2)
-assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, const int has_body) {
+assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, const int has_body, const HaloFuse hf) {
   extern __shared__ __align__(128) unsigned char smem_raw_j2[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpSmemJ2& sm = reinterpret_cast<WarpSmemJ2*>(smem_raw_j2)[warp];
   const long long nwarps = (long long)gridDim.x * kWarpsJ2;
-  long long tile = (long long)blockIdx.x * kWarpsJ2 + warp;
-  if (tile >= ntiles) return;
+  // vt: position in the visiting order (interface layers first when FUSE, see assemble_hex_common.cuh)
+  long long vt = (long long)blockIdx.x * kWarpsJ2 + warp;
+  if (vt >= ntiles) return;
+  auto real_tile = [&](long long v) -> long long {
+    if constexpr (FUSE) return v < ntiles ? halo_real_tile(hf, v, ntiles) : v;
+    else return v;
+  };
+  bool push_done = !FUSE;
 
   const double E = args.p.v[0], nu = args.p.v[1], y0 = args.p.v[5], h1 = args.p.v[6], h2 = args.p.v[7];
   const double lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu)), G = E / (2.0 * (1.0 + nu));
@@ -80,7 +87,8 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
 
   // software pipeline of the gathers (node ids two tiles ahead, nodal data and history one tile ahead); see
   // assemble_hex.cu for why the id is held back in its register
-  auto node_of = [&](long long t) -> int {
+  auto node_of = [&](long long v) -> int {
+    const long long t = real_tile(v);
     const long long e = t * kTile + el_p;
     const int ok = (t < ntiles && e < args.ne) ? 1 : 0;
     const int32_t* src = args.conn + (ok ? e * 8 + sub : 0);
@@ -94,7 +102,8 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
   auto hold_back = [](int& a, unsigned& b, unsigned& c, unsigned& d) {
     asm volatile("" : "+r"(a), "+r"(b), "+r"(c), "+r"(d));
   };
-  auto gather_async = [&](int buf, long long n, long long t) {
+  auto gather_async = [&](int buf, long long n, long long v) {
+    const long long t = real_tile(v);
     const double* gx = args.xyz + n * 3;
     const double* gu = args.u + n * 3;
     cp_async8(&sm.X[buf][0][lane], gx); cp_async8(&sm.X[buf][1][lane], gx + 1); cp_async8(&sm.X[buf][2][lane], gx + 2);
@@ -106,15 +115,15 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
     for (int s = 0; s < 7; ++s) cp_async8(&sm.st[buf][s][lane], gs + s);
     cp_async_commit();
   };
-  int n_next = node_of(tile + nwarps);
-  const long long n_first = node_of(tile);
-  gather_async(0, n_first, tile);
+  int n_next = node_of(vt + nwarps);
+  const long long n_first = node_of(vt);
+  gather_async(0, n_first, vt);
   const uint8_t* pf0 = args.dir + n_first * 3;
   unsigned f0 = __ldg(pf0), f1 = __ldg(pf0 + 1), f2 = __ldg(pf0 + 2);
   int buf = 0;
 
-  for (; tile < ntiles; tile += nwarps, buf ^= 1) {
-    const long long e0 = tile * kTile;
+  for (; vt < ntiles; vt += nwarps, buf ^= 1) {
+    const long long e0 = real_tile(vt) * kTile;
     hold_back(n_next, f0, f1, f2);
 
     // ---- phase 0: this tile's nodal data and history have landed; start the next gather
@@ -123,12 +132,12 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
     sm.bc[el_p][sub * 3 + 2] = f2 ? 0.f : 1.f;
     cp_async_wait_all();
     __syncwarp();
-    gather_async(buf ^ 1, (long long)n_next, tile + nwarps);
+    gather_async(buf ^ 1, (long long)n_next, vt + nwarps);
     {
       const uint8_t* pf = args.dir + (long long)n_next * 3;
       f0 = __ldg(pf); f1 = __ldg(pf + 1); f2 = __ldg(pf + 2);
     }
-    n_next = node_of(tile + 2 * nwarps);
+    n_next = node_of(vt + 2 * nwarps);
 
     // ---- phase 1: lane (element, Gauss point): geometry (geometry.py:88-97), strain = B u, return mapping
     unsigned plastic_mask;
@@ -358,20 +367,30 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
       }
     }
     __syncwarp();  // everyone is done with X / u / history / gradients of this tile
+    if constexpr (FUSE) {
+      if (vt < hf.tiles_lo + hf.tiles_hi) halo_tile_done(hf, lane);
+      if (!push_done) push_done = halo_try_push(hf, lane);
+    }
+  }
+  if constexpr (FUSE) {
+    if (!push_done) halo_drain(hf, lane);
   }
   if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last copies
 }
 
-int assemble_hex_j2_f64(cudaStream_t s, const AsmArgs<double>& args) {
-  static PerDeviceGrid grid;
+int assemble_hex_j2_f64(cudaStream_t s, const AsmArgs<double>& args, const HaloFuse* hf) {
+  static PerDeviceGrid per_device, per_device_fused;
   const size_t smem = sizeof(WarpSmemJ2) * kWarpsJ2;
   int g = 0;
-  FOL_CUDA(grid.get(assemble_hex_j2_f64_kernel, kWarpsJ2 * 32, smem, &g));
+  if (hf) FOL_CUDA(per_device_fused.get(assemble_hex_j2_f64_kernel<true>, kWarpsJ2 * 32, smem, &g));
+  else FOL_CUDA(per_device.get(assemble_hex_j2_f64_kernel<false>, kWarpsJ2 * 32, smem, &g));
   if (args.ne == 0) return FOL_OK;
   const long long ntiles = cdiv(args.ne, kTile);
   const long long want = cdiv(ntiles, kWarpsJ2);
   const int has_body = (args.p.v[2] != 0.0 || args.p.v[3] != 0.0 || args.p.v[4] != 0.0) ? 1 : 0;
-  assemble_hex_j2_f64_kernel<<<(unsigned)(want < g ? want : g), kWarpsJ2 * 32, smem, s>>>(args, ntiles, has_body);
+  const unsigned blocks = (unsigned)(want < g ? want : g);
+  if (hf) assemble_hex_j2_f64_kernel<true><<<blocks, kWarpsJ2 * 32, smem, s>>>(args, ntiles, has_body, *hf);
+  else assemble_hex_j2_f64_kernel<false><<<blocks, kWarpsJ2 * 32, smem, s>>>(args, ntiles, has_body, HaloFuse{});
   return check_launch("assemble_hex_j2_f64_kernel");
 }
 

@@ -12,9 +12,14 @@
 #include <cuda_runtime.h>
 #include <string.h>
 
+#include "assemble.cuh"
+#include "assemble_hex_common.cuh"
 #include "common.cuh"
 
 namespace fol {
+
+int assemble_hex_mech_f64(cudaStream_t, const AsmArgs<double>&, const hexk::HaloFuse*);
+int assemble_hex_j2_f64(cudaStream_t, const AsmArgs<double>&, const hexk::HaloFuse*);
 
 template <class T>
 __global__ void halo_gather_push_kernel(long long n0, long long count, int d, const int32_t* __restrict__ ptr,
@@ -64,6 +69,56 @@ __global__ void halo_add_kernel(long long n0, long long count, int d, const T* _
   if (t < count * d) R[n0 * d + t] += __ldcv(recv + t);
 }
 
+
+// Completes a step of the fused path (assemble_hex_common.cuh): blocks [0, nb_int) gather the interior nodes in the
+// fixed adjacency order; the following 2 * nb_plane blocks wait (system-scope acquire) for the neighbour's chunk
+// arrivals -- long there by then -- and add what it pushed to the plane sums the element-stage launch left in R.
+// IEEE addition commutes, so both copies of an interface plane end up bit-identical.
+template <class T>
+__global__ void gather_halo_kernel(long long plane, long long nn, int d, const int32_t* __restrict__ ptr,
+                                   const int32_t* __restrict__ adj, const T* __restrict__ re, T* __restrict__ R,
+                                   long long nb_int, long long nb_plane, const T* recv_lo, const T* recv_hi,
+                                   const unsigned long long* arrive_lo, const unsigned long long* arrive_hi,
+                                   unsigned long long target, unsigned long long* timeouts,
+                                   unsigned long long* iface_done, unsigned long long* chunk_next) {
+  const long long b = blockIdx.x;
+  if (b == 0 && threadIdx.x == 0) {      // the element-stage launch of this step is complete (stream order)
+    *iface_done = 0ULL;
+    *chunk_next = 0ULL;
+  }
+  if (b < nb_int) {
+    const long long t = b * blockDim.x + threadIdx.x;
+    if (t < (nn - 2 * plane) * d) {
+      const long long n = plane + t / d;
+      const int k = (int)(t % d);
+      T acc = (T)0;
+      const int lo = ptr[n], hi = ptr[n + 1];
+      for (int i = lo; i < hi; ++i) acc += __ldg(re + (long long)adj[i] * d + k);
+      R[n * d + k] = acc;
+    }
+    return;
+  }
+  const int side = (b - nb_int) >= nb_plane ? 1 : 0;
+  const T* recv = side ? recv_hi : recv_lo;
+  if (!recv) return;
+  const unsigned long long* arrive = side ? arrive_hi : arrive_lo;
+  if (threadIdx.x == 0) {
+    unsigned long long seen;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(arrive) : "memory");
+      if (seen < target && clock64() - t0 > 4000000000LL) {
+        atomicAdd(timeouts, 1ULL);
+        break;
+      }
+    } while (seen < target);
+  }
+  __syncthreads();
+  const long long t = (b - nb_int - side * nb_plane) * blockDim.x + threadIdx.x;
+  const long long n0 = side ? nn - plane : 0;
+  if (t < plane * d) R[n0 * d + t] += __ldcv(recv + t);
+}
+
 }  // namespace fol
 
 using namespace fol;
@@ -79,6 +134,10 @@ struct fol_halo {
   size_t recv_off(int side, int parity) const { return ((size_t)side * 2 + parity) * plane_dofs * esz; }
   size_t arrive_off(int side, int parity) const { return (size_t)4 * plane_dofs * esz + ((size_t)side * 2 + parity) * 8; }
   size_t timeout_off() const { return (size_t)4 * plane_dofs * esz + 32; }
+  // fused path (element stage pushes the planes itself): its own arrival counters + the two work counters
+  size_t fused_arrive_off(int side, int parity) const { return (size_t)4 * plane_dofs * esz + 64 + ((size_t)side * 2 + parity) * 8; }
+  size_t iface_done_off() const { return (size_t)4 * plane_dofs * esz + 96; }
+  size_t chunk_next_off() const { return (size_t)4 * plane_dofs * esz + 104; }
 };
 
 extern "C" {
@@ -90,7 +149,7 @@ int fol_halo_create(fol_halo** out, int dtype, int64_t plane_dofs) {
   h->esz = dtype == FOL_F64 ? 8 : 4;
   h->plane_dofs = plane_dofs;
   h->ctas = (unsigned)cdiv(plane_dofs, 256);
-  const size_t bytes = (size_t)4 * plane_dofs * h->esz + 64;
+  const size_t bytes = (size_t)4 * plane_dofs * h->esz + 128;
   cudaError_t e = cudaMalloc(&h->base, bytes);
   if (e == cudaSuccess) e = cudaMemset(h->base, 0, bytes);
   if (e != cudaSuccess) {
@@ -166,6 +225,74 @@ int fol_halo_add(fol_stream_t s, fol_halo* h, int side, int64_t step, int64_t n0
     halo_add_kernel<float><<<h->ctas, 256, 0, (cudaStream_t)s>>>(n0, count, d, (const float*)recv, arrive, target,
                                                                 timeouts, (float*)residual);
   return check_launch("halo_add_kernel");
+}
+
+/* Element stage of a slab with its two interface element layers FIRST and the plane gather + NVLink push riding inside
+ * the same launch (csrc/assemble_hex_common.cuh).  Tuned Hex8 float64 kernels only (FOL_MECHANICAL / FOL_J2PLASTICITY,
+ * num_gp = 2); FOL_ERR_UNSUPPORTED otherwise -- callers then use the layered path (fol_halo_gather_push / fol_halo_add).
+ * layer_elems: elements per z-layer (the bottom layer is [0, layer_elems), the top one the last layer_elems). */
+int fol_assemble_elements_halo(fol_stream_t s, int dtype, int physics, int element, int num_gp, int64_t ne, int64_t nn,
+                               const void* xyz, const int32_t* conn, const void* ctrl, const void* u, const uint8_t* dir,
+                               const double* params, void* ke, void* re, const void* state_in, void* state_out,
+                               fol_halo* h, int64_t step, int64_t layer_elems, int64_t plane_nodes,
+                               const int32_t* adj_ptr, const int32_t* adj, void* residual) {
+  FOL_REQUIRE(h && xyz && conn && ctrl && u && dir && ke && re && adj_ptr && adj && residual, "fol_assemble_elements_halo: null pointer");
+  if (dtype != FOL_F64 || element != HEX || num_gp != 2 || (physics != FOL_MECHANICAL && physics != FOL_J2PLASTICITY))
+    return fail(FOL_ERR_UNSUPPORTED, "fol_assemble_elements_halo: tuned Hex8 float64 kernels only");
+  FOL_REQUIRE(h->dtype == FOL_F64 && plane_nodes * 3 == h->plane_dofs, "fol_assemble_elements_halo: plane size differs from the halo object");
+  FOL_REQUIRE(layer_elems > 0 && ne % layer_elems == 0 && nn >= 2 * plane_nodes, "fol_assemble_elements_halo: bad layer / plane sizes");
+  if (physics == FOL_J2PLASTICITY) FOL_REQUIRE(state_in && state_out, "fol_assemble_elements_halo: J2 needs state_in / state_out");
+  AsmArgs<double> a;
+  a.xyz = (const double*)xyz; a.conn = conn; a.ctrl = (const double*)ctrl; a.u = (const double*)u; a.dir = dir;
+  a.ke = (double*)ke; a.re = (double*)re; a.state_in = (const double*)state_in; a.state_out = (double*)state_out;
+  a.ne = ne; a.transpose = 0; a.p = make_params<double>(params);
+  const long long ntiles = cdiv(ne, hexk::kTile);
+  hexk::HaloFuse hf;
+  hf.tiles_lo = cdiv(layer_elems, hexk::kTile);
+  hf.tiles_hi = ntiles - (ne - layer_elems) / hexk::kTile;
+  if (hf.tiles_lo + hf.tiles_hi >= ntiles) {   // one or two layers: every tile is an interface tile
+    hf.tiles_lo = ntiles;
+    hf.tiles_hi = 0;
+  }
+  hf.plane_dofs = h->plane_dofs;
+  hf.n0[0] = 0;
+  hf.n0[1] = nn - plane_nodes;
+  hf.adj_ptr = adj_ptr; hf.adj = adj; hf.re = (const double*)re; hf.R = (double*)residual;
+  const int parity = (int)(step & 1);
+  for (int side = 0; side < 2; ++side) {
+    unsigned char* peer = h->peer[side];
+    hf.peer_recv[side] = peer ? reinterpret_cast<double*>(peer + h->recv_off(1 - side, parity)) : nullptr;
+    hf.peer_arrive[side] = peer ? reinterpret_cast<unsigned long long*>(peer + h->fused_arrive_off(1 - side, parity)) : nullptr;
+  }
+  hf.iface_done = reinterpret_cast<unsigned long long*>(h->base + h->iface_done_off());
+  hf.chunk_next = reinterpret_cast<unsigned long long*>(h->base + h->chunk_next_off());
+  hf.timeouts = reinterpret_cast<unsigned long long*>(h->base + h->timeout_off());
+  if (physics == FOL_MECHANICAL) return assemble_hex_mech_f64((cudaStream_t)s, a, &hf);
+  return assemble_hex_j2_f64((cudaStream_t)s, a, &hf);
+}
+
+/* Completes the step started by fol_assemble_elements_halo: gather of the interior nodes + add of what the neighbours
+ * pushed into the two interface planes (device-side wait for their arrivals), one launch. */
+int fol_residual_gather_halo(fol_stream_t s, fol_halo* h, int64_t step, int64_t nn, int64_t plane_nodes,
+                             const int32_t* adj_ptr, const int32_t* adj, const void* re, void* residual) {
+  FOL_REQUIRE(h && adj_ptr && adj && re && residual, "fol_residual_gather_halo: null pointer");
+  FOL_REQUIRE(h->dtype == FOL_F64 && plane_nodes * 3 == h->plane_dofs && nn >= 2 * plane_nodes, "fol_residual_gather_halo: bad sizes");
+  const int parity = (int)(step & 1);
+  const long long per_side = cdiv(h->plane_dofs, hexk::kHaloChunk);
+  const unsigned long long target = (unsigned long long)(step / 2 + 1) * (unsigned long long)per_side;
+  const long long nb_int = cdiv((nn - 2 * plane_nodes) * 3, 256), nb_plane = cdiv(h->plane_dofs, 256);
+  const double* recv[2];
+  const unsigned long long* arrive[2];
+  for (int side = 0; side < 2; ++side) {
+    recv[side] = h->peer[side] ? reinterpret_cast<const double*>(h->base + h->recv_off(side, parity)) : nullptr;
+    arrive[side] = reinterpret_cast<const unsigned long long*>(h->base + h->fused_arrive_off(side, parity));
+  }
+  gather_halo_kernel<double><<<(unsigned)(nb_int + 2 * nb_plane), 256, 0, (cudaStream_t)s>>>(
+      plane_nodes, nn, 3, adj_ptr, adj, (const double*)re, (double*)residual, nb_int, nb_plane, recv[0], recv[1],
+      arrive[0], arrive[1], target, reinterpret_cast<unsigned long long*>(h->base + h->timeout_off()),
+      reinterpret_cast<unsigned long long*>(h->base + h->iface_done_off()),
+      reinterpret_cast<unsigned long long*>(h->base + h->chunk_next_off()));
+  return check_launch("gather_halo_kernel");
 }
 
 /* number of arrival waits that gave up (a neighbour never pushed): synchronising read, 0 in a healthy run */

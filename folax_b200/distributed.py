@@ -118,6 +118,7 @@ class SlabPartition:
                 raise _lib.FolaxError(f"halo exchange: {lost} arrival waits timed out (a neighbour rank never pushed)")
 
 
+FUSED_HALO = True          # False: force the layered path (A/B in tests and scripts/halo_diag.py)
 GRID_MARGIN_CTAS = 0   # measured on 2/4/8 B200: a margin does not pay; NCCL's kernels fit next to the persistent CTAs
 
 
@@ -179,9 +180,22 @@ def assemble_overlapped(loss, part, controls, dofs, ke_out, comm_stream, group=N
                                            _lib.ptr(re), R.data_ptr() + esz * d * n0))
 
     if part.world > 1 and part._halo is not None:
-        # NVLink peer path: plane gather + push in one kernel, add after the interior work (no NCCL, no side stream)
         step, h = part._halo_step, part._halo
         part._halo_step += 1
+        if (FUSED_HALO and dt == _lib.F64 and elem == 0 and loss.num_gp == 2 and d == 3
+                and loss.physics in ("mechanical", "j2plasticity")):
+            # fused path: ONE element-stage launch that visits the interface layers first and pushes the two planes
+            # over NVLink from inside (csrc/assemble_hex_common.cuh), ONE launch for the interior gather + halo add
+            _lib.check(lib.fol_assemble_elements_halo(
+                s, dt, phys, elem, loss.num_gp, ne, nn, _lib.ptr(loss._xyz), _lib.ptr(loss._conn), _lib.ptr(K),
+                _lib.ptr(u), _lib.ptr(loss._dir_flag), loss._params, _lib.ptr(ke_out), _lib.ptr(re),
+                _lib.ptr(state_in) if st_bytes else None, _lib.ptr(state_out) if st_bytes else None,
+                h, step, layer, plane, _lib.ptr(loss._adj_ptr), _lib.ptr(loss._adj), _lib.ptr(R)))
+            _lib.check(lib.fol_residual_gather_halo(s, h, step, nn, plane, _lib.ptr(loss._adj_ptr), _lib.ptr(loss._adj),
+                                                    _lib.ptr(re), _lib.ptr(R)))
+            return ke_out, R
+        # layered NVLink peer path: plane gather + push in one kernel, add after the interior work (no NCCL, no side
+        # stream); serves the element types / precisions the fused kernels do not cover
 
         def push(side, n0):
             _lib.check(lib.fol_halo_gather_push(s, h, side, step, n0, plane, d, _lib.ptr(loss._adj_ptr),

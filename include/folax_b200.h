@@ -321,6 +321,21 @@ int fol_halo_gather_push(fol_stream_t s, fol_halo* halo, int side, int64_t step,
                          const int32_t* adj, const void* re_elem, void* residual);
 int fol_halo_add(fol_stream_t s, fol_halo* halo, int side, int64_t step, int64_t n0, int64_t count,
                  int dofs_per_node, void* residual);
+/* Fused path (two launches per step instead of seven): fol_assemble_elements_halo runs the element stage of the slab
+ * with its two interface element layers FIRST and hands the plane work -- the fixed-order residual gather of both
+ * interface node planes, the NVLink peer stores and the arrival counts -- to the warps of the SAME launch as they
+ * finish their tiles; fol_residual_gather_halo then gathers the interior nodes and adds what the neighbours pushed
+ * (device-side wait).  Tuned Hex8 float64 kernels only (FOL_MECHANICAL / FOL_J2PLASTICITY, num_gp = 2), otherwise
+ * FOL_ERR_UNSUPPORTED and the caller uses push / add above.  Same results, bit for bit, as the layered path.
+ * Replaces the single-device scatter of fe_loss.py:301-306 for a slab (the reference has no domain decomposition). */
+int fol_assemble_elements_halo(fol_stream_t s, int dtype, int physics, int element, int num_gp, int64_t ne,
+                               int64_t nn, const void* xyz, const int32_t* conn, const void* controls,
+                               const void* dofs, const uint8_t* dir_flag, const double* params, void* ke_data,
+                               void* re_elem, const void* state_in, void* state_out, fol_halo* halo, int64_t step,
+                               int64_t layer_elems, int64_t plane_nodes, const int32_t* adj_ptr,
+                               const int32_t* adj, void* residual);
+int fol_residual_gather_halo(fol_stream_t s, fol_halo* halo, int64_t step, int64_t nn, int64_t plane_nodes,
+                             const int32_t* adj_ptr, const int32_t* adj, const void* re_elem, void* residual);
 /* arrival waits that gave up after ~2 s (a neighbour never pushed); synchronises; 0 in a healthy run */
 int64_t fol_halo_timeouts(fol_halo* halo);
 

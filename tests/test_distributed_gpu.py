@@ -36,12 +36,41 @@ def _worker(rank, world, port, out):
             data, R = assemble_overlapped(loss, part, K, u, ke, comm)
         torch.cuda.synchronize()
         R_nccl = R.clone()
-        # same exchange over NVLink peer memory (csrc/halo.cu): gather fused with the push, device-side arrival wait
-        assert part.enable_peer_halo(loss)
-        for _ in range(5):                         # several steps: both buffer parities, counters keep counting
-            data, R = assemble_overlapped(loss, part, K, u, ke, comm)
+        # same exchange over NVLink peer memory: first the FUSED path (the element-stage launch visits the interface
+        # layers first and pushes the planes itself, csrc/assemble_hex_common.cuh), then the layered path
+        # (csrc/halo.cu: plane gather fused with the push, separate add) on a fresh halo object
+        import folax_b200.distributed as D
+        for fused in (True, False):
+            D.FUSED_HALO = fused
+            assert part.enable_peer_halo(loss)
+            ke.fill_(float("nan"))
+            for _ in range(5):                     # several steps: both buffer parities, counters re-armed / counting
+                data, R = assemble_overlapped(loss, part, K, u, ke, comm)
+            torch.cuda.synchronize()
+            assert bool((R == R_nccl).all()), f"peer-memory halo sum (fused={fused}) differs from the NCCL send/recv path"
+            dist.barrier()
+            part.close_peer_halo()
+            dist.barrier()
+        D.FUSED_HALO = True
+        # J2 elastoplasticity with Gauss-point history through the fused path against the NCCL path
+        from folax_b200.loss_functions import ElastoplasticityLoss3DHexa
+        mat = {"young_modulus": 3.0, "poisson_ratio": 0.3, "iso_hardening_parameter_1": 0.4,
+               "iso_hardening_param_2": 10.0, "yield_limit": 0.2}
+        lj = ElastoplasticityLoss3DHexa("ep", {"dirichlet_bc_dict": bc, "material_dict": mat}, part.mesh)
+        lj.Initialize()
+        st0 = torch.zeros(lj.GetStateShape(), dtype=torch.float64, device="cuda")
+        st_a, st_b = torch.empty_like(st0), torch.empty_like(st0)
+        ke2 = torch.empty_like(ke)
+        uj = 0.5 * u
+        _, Rj_nccl = assemble_overlapped(lj, part, K, uj, ke2, comm, state_in=st0, state_out=st_a)
         torch.cuda.synchronize()
-        assert bool((R == R_nccl).all()), "peer-memory halo sum differs from the NCCL send/recv path"
+        Rj_nccl = Rj_nccl.clone()
+        assert part.enable_peer_halo(lj)
+        for _ in range(3):
+            _, Rj = assemble_overlapped(lj, part, K, uj, ke, comm, state_in=st0, state_out=st_b)
+        torch.cuda.synchronize()
+        assert bool((Rj == Rj_nccl).all()) and torch.equal(st_a, st_b) and torch.equal(ke, ke2), "fused J2 slab step"
+        assert float((st_b[..., -1] > 0).double().mean()) > 0.05
         dist.barrier()
         part.close_peer_halo()
         out[rank] = (gids, R.cpu().numpy(), data.cpu().numpy(), part.element_offset)
