@@ -68,6 +68,8 @@ SIGNATURES = {
     "fol_plan_create": (_int, [C.POINTER(_vp), _int, _int, _int, _int, _i64, _i64, _vp, _i32p, _i32p, _i64,
                                C.POINTER(_dbl)]),
     "fol_plan_destroy": (None, [_vp]),
+    "fol_plan_set_csr": (_int, [_vp, _i64, _i64, _i32p, _i32p, _i32p, _i32p]),
+    "fol_plan_assemble_host_csr": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
     "fol_halo_create": (_int, [C.POINTER(_vp), _int, _i64]),
     "fol_halo_destroy": (None, [_vp]),
     "fol_halo_export": (_int, [_vp, _vp]),

@@ -120,6 +120,11 @@ struct fol_plan {
   void *xyz = nullptr, *ctrl = nullptr, *u = nullptr, *ke = nullptr, *re = nullptr, *R = nullptr;
   int32_t *conn = nullptr, *adj_ptr = nullptr, *adj = nullptr, *work = nullptr, *dir_idx = nullptr;
   uint8_t* dir = nullptr;
+  // duplicate-free CSR hand-off (fol_plan_set_csr): integer plan of folax_b200/csr_plan.py + the value buffer
+  int32_t *pair_ptr = nullptr, *contrib = nullptr, *out_base = nullptr, *row_stride = nullptr;
+  void* vals = nullptr;
+  long long npairs = 0, nnz = 0;
+  std::vector<long long> pair_cut;   // chunk boundaries in pairs, each on a node boundary (contiguous value ranges)
 };
 
 extern "C" {
@@ -258,7 +263,8 @@ int fol_scale_grads(fol_stream_t s, int dtype, int64_t nb, int64_t ndof, int64_t
 // ---- plan ------------------------------------------------------------------------------------
 void fol_plan_destroy(fol_plan* p) {
   if (!p) return;
-  void* bufs[] = {p->xyz, p->ctrl, p->u, p->ke, p->re, p->R, p->conn, p->adj_ptr, p->adj, p->work, p->dir_idx, p->dir};
+  void* bufs[] = {p->xyz, p->ctrl, p->u, p->ke, p->re, p->R, p->conn, p->adj_ptr, p->adj, p->work, p->dir_idx, p->dir,
+                  p->pair_ptr, p->contrib, p->out_base, p->row_stride, p->vals};
   for (void* b : bufs)
     if (b) cudaFree(b);
   for (cudaEvent_t ev : p->chunk_done)
@@ -369,6 +375,74 @@ int fol_plan_assemble_host(fol_plan* p, int transpose, const void* ctrl_host, co
   }
   if (int rc = fol_residual_gather(p->stream, p->dtype, p->nn, p->nnode, p->dpn, p->adj_ptr, p->adj, p->re, p->R)) return rc;
   FOL_CUDA(cudaMemcpyAsync(R_host, p->R, p->esz * p->ndof, cudaMemcpyDeviceToHost, p->stream));
+  FOL_CUDA(cudaStreamSynchronize(p->stream));
+  FOL_CUDA(cudaStreamSynchronize(p->copy_stream));
+  return FOL_OK;
+}
+
+/* Uploads the integer plan of the duplicate-free CSR (host arrays of folax_b200/csr_plan.py: pairs sorted by (row
+ * node, column node), contributors per pair in ascending (element, a, b) order) once per mesh. */
+int fol_plan_set_csr(fol_plan* p, int64_t npairs, int64_t nnz, const int32_t* pair_ptr_host, const int32_t* contrib_host,
+                     const int32_t* out_base_host, const int32_t* row_stride_host) {
+  FOL_REQUIRE(p && pair_ptr_host && contrib_host && out_base_host && row_stride_host && npairs > 0 && nnz > 0,
+              "fol_plan_set_csr: bad arguments");
+  const size_t ncontrib = (size_t)p->ne * p->nnode * p->nnode;
+  FOL_REQUIRE((size_t)pair_ptr_host[npairs] == ncontrib, "fol_plan_set_csr: the plan does not belong to this mesh");
+  void** slots[] = {(void**)&p->pair_ptr, (void**)&p->contrib, (void**)&p->out_base, (void**)&p->row_stride, &p->vals};
+  for (void** sl : slots) {
+    if (*sl) cudaFree(*sl);
+    *sl = nullptr;
+  }
+  FOL_CUDA(cudaMalloc((void**)&p->pair_ptr, sizeof(int32_t) * (size_t)(npairs + 1)));
+  FOL_CUDA(cudaMalloc((void**)&p->contrib, sizeof(int32_t) * ncontrib));
+  FOL_CUDA(cudaMalloc((void**)&p->out_base, sizeof(int32_t) * (size_t)npairs));
+  FOL_CUDA(cudaMalloc((void**)&p->row_stride, sizeof(int32_t) * (size_t)npairs));
+  FOL_CUDA(cudaMalloc(&p->vals, p->esz * (size_t)nnz));
+  FOL_CUDA(cudaMemcpyAsync(p->pair_ptr, pair_ptr_host, sizeof(int32_t) * (size_t)(npairs + 1), cudaMemcpyHostToDevice, p->stream));
+  FOL_CUDA(cudaMemcpyAsync(p->contrib, contrib_host, sizeof(int32_t) * ncontrib, cudaMemcpyHostToDevice, p->stream));
+  FOL_CUDA(cudaMemcpyAsync(p->out_base, out_base_host, sizeof(int32_t) * (size_t)npairs, cudaMemcpyHostToDevice, p->stream));
+  FOL_CUDA(cudaMemcpyAsync(p->row_stride, row_stride_host, sizeof(int32_t) * (size_t)npairs, cudaMemcpyHostToDevice, p->stream));
+  p->npairs = npairs;
+  p->nnz = nnz;
+  // chunk boundaries: a pair P opens the rows of a node exactly where out_base[P] == d*d*P (its index within the
+  // node's pairs is 0), and the values of whole nodes are one contiguous range of the CSR value array
+  constexpr int kChunks = 16;
+  const long long dd = (long long)p->dpn * p->dpn;
+  p->pair_cut.assign(1, 0);
+  for (int c = 1; c < kChunks; ++c) {
+    long long P = npairs * c / kChunks;
+    while (P < npairs && (long long)out_base_host[P] != dd * P) ++P;
+    if (P > p->pair_cut.back() && P < npairs) p->pair_cut.push_back(P);
+  }
+  p->pair_cut.push_back(npairs);
+  FOL_CUDA(cudaStreamSynchronize(p->stream));
+  return FOL_OK;
+}
+
+/* Host hand-off of what the reference's solvers actually consume (fe_solver.py:71-72: the duplicates of the BCOO
+ * summed into a CSR): H2D of the inputs, element stage, de-duplication on the device in chunks of whole node rows,
+ * each chunk's values starting their way to the host as soon as they exist.  vals_host: nnz values in the order of
+ * the plan's (indptr, indices); 1/2.4 of the bytes of the duplicate-keeping hand-off for Hex8. */
+int fol_plan_assemble_host_csr(fol_plan* p, int transpose, const void* ctrl_host, const void* u_host, void* vals_host,
+                               void* R_host) {
+  FOL_REQUIRE(p && ctrl_host && u_host && vals_host && R_host, "fol_plan_assemble_host_csr: null pointer");
+  FOL_REQUIRE(p->vals && p->npairs > 0, "fol_plan_assemble_host_csr: call fol_plan_set_csr first");
+  FOL_CUDA(cudaMemcpyAsync(p->ctrl, ctrl_host, p->esz * p->nn, cudaMemcpyHostToDevice, p->stream));
+  FOL_CUDA(cudaMemcpyAsync(p->u, u_host, p->esz * p->ndof, cudaMemcpyHostToDevice, p->stream));
+  if (int rc = plan_run(p, transpose, p->ctrl, p->u)) return rc;
+  FOL_CUDA(cudaMemcpyAsync(R_host, p->R, p->esz * p->ndof, cudaMemcpyDeviceToHost, p->stream));
+  const long long dd = (long long)p->dpn * p->dpn;
+  for (size_t c = 0; c + 1 < p->pair_cut.size(); ++c) {
+    const long long p0 = p->pair_cut[c], p1 = p->pair_cut[c + 1];
+    // the kernel indexes pairs from 0: pass the sub-range through offset pointers; out_base stays absolute
+    int rc = fol_csr_values(p->stream, p->dtype, p1 - p0, p->dpn, p->nnode, p->pair_ptr + p0, p->contrib,
+                            p->out_base + p0, p->row_stride + p0, p->ke, p->vals);
+    if (rc) return rc;
+    FOL_CUDA(cudaEventRecord(p->chunk_done[c], p->stream));
+    FOL_CUDA(cudaStreamWaitEvent(p->copy_stream, p->chunk_done[c], 0));
+    const size_t v0 = (size_t)(dd * p0) * p->esz, v1 = (p1 == p->npairs ? (size_t)p->nnz : (size_t)(dd * p1)) * p->esz;
+    FOL_CUDA(cudaMemcpyAsync((char*)vals_host + v0, (char*)p->vals + v0, v1 - v0, cudaMemcpyDeviceToHost, p->copy_stream));
+  }
   FOL_CUDA(cudaStreamSynchronize(p->stream));
   FOL_CUDA(cudaStreamSynchronize(p->copy_stream));
   return FOL_OK;

@@ -31,22 +31,29 @@ using namespace hexk;
 #ifndef FOL_J2_WARPS
 #define FOL_J2_WARPS 5
 #endif
-constexpr int kWarpsJ2 = FOL_J2_WARPS;   // warps per CTA, each fully independent (2 CTAs / SM, 22 KB of staging per warp)
+constexpr int kWarpsJ2 = FOL_J2_WARPS;   // warps per CTA, each fully independent (2 CTAs = 10 warps / SM, 19.9 KB of staging per warp)
 
 struct __align__(128) WarpSmemJ2 {
-  double stage[576];                 // Ke staging slot (bulk-copy source)
+  // Ke staging slot (bulk-copy source).  Its first 224 doubles double as the staging of the tile's NEW history in the
+  // global (element, point, 7) layout (one 1792-byte bulk copy per tile): the history copy is issued before the
+  // element loop, whose first staging write waits for it, and the last Ke copy of a tile is waited for before the
+  // next tile's history is written.
+  double stage[576];
   double2 gxy[kTile][8][8];          // [element][gauss][node ^ swz(gauss)]: (dN/dx, dN/dy), see assemble_hex.cu
   double2 gzs[kTile][8][8];          //                                      (dN/dz, w detJ)
-  double X[2][3][32];                // nodal data of the tile, SoA over the 32 (element, node) lanes, double-buffered
-  double u[2][3][32];
-  double st[2][7][32];               // history of the tile, SoA over the 32 (element, Gauss point) lanes, double-buffered
+  // nodal data and history of the tile, SoA over the 32 lanes.  SINGLE buffers: phase 1 consumes them completely, so
+  // the gather of the next tile is issued right after phase 1 and lands behind phase 2 (20.6 KB per warp: 10 warps / SM)
+  double X[3][32];
+  double u[3][32];
+  double st[7][32];
   double dv[6][32];                  // dev of the trial elastic strain          } per (element, Gauss point),
   double ws[6][32];                  // w detJ sigma                             } SoA: conflict-free phase-1 stores,
   double wl[32], wm[32], wb[32];     // w detJ (lam + a/3), w detJ (2G - a), w detJ b   } broadcast phase-2 loads
-  double wd[32];                     // w detJ (body force)
-  double sto[32 * 7];                // new history in the global (element, point, 7) layout: one bulk copy per tile
   float bc[kTile][24];               // 1 = free dof, 0 = Dirichlet dof
 };
+
+// two CTAs per SM must fit the 227 KB of shared memory (1 KB per CTA is reserved by the system)
+static_assert(2 * (sizeof(WarpSmemJ2) * kWarpsJ2 + 1024) <= 227 * 1024, "WarpSmemJ2: two CTAs per SM do not fit");
 
 }  // namespace
 
@@ -102,43 +109,35 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
   auto hold_back = [](int& a, unsigned& b, unsigned& c, unsigned& d) {
     asm volatile("" : "+r"(a), "+r"(b), "+r"(c), "+r"(d));
   };
-  auto gather_async = [&](int buf, long long n, long long v) {
+  auto gather_async = [&](long long n, long long v) {
     const long long t = real_tile(v);
     const double* gx = args.xyz + n * 3;
     const double* gu = args.u + n * 3;
-    cp_async8(&sm.X[buf][0][lane], gx); cp_async8(&sm.X[buf][1][lane], gx + 1); cp_async8(&sm.X[buf][2][lane], gx + 2);
-    cp_async8(&sm.u[buf][0][lane], gu); cp_async8(&sm.u[buf][1][lane], gu + 1); cp_async8(&sm.u[buf][2][lane], gu + 2);
+    cp_async8(&sm.X[0][lane], gx); cp_async8(&sm.X[1][lane], gx + 1); cp_async8(&sm.X[2][lane], gx + 2);
+    cp_async8(&sm.u[0][lane], gu); cp_async8(&sm.u[1][lane], gu + 1); cp_async8(&sm.u[2][lane], gu + 2);
     // history of (element, Gauss point) = this lane; tiles past the end read element 0 (never used)
     const long long e = t * kTile + el_p;
     const double* gs = args.state_in + ((t < ntiles && e < args.ne) ? (e * 8 + sub) * 7 : 0);
 #pragma unroll
-    for (int s = 0; s < 7; ++s) cp_async8(&sm.st[buf][s][lane], gs + s);
+    for (int s = 0; s < 7; ++s) cp_async8(&sm.st[s][lane], gs + s);
     cp_async_commit();
   };
   int n_next = node_of(vt + nwarps);
   const long long n_first = node_of(vt);
-  gather_async(0, n_first, vt);
+  gather_async(n_first, vt);
   const uint8_t* pf0 = args.dir + n_first * 3;
   unsigned f0 = __ldg(pf0), f1 = __ldg(pf0 + 1), f2 = __ldg(pf0 + 2);
-  int buf = 0;
 
-  for (; vt < ntiles; vt += nwarps, buf ^= 1) {
+  for (; vt < ntiles; vt += nwarps) {
     const long long e0 = real_tile(vt) * kTile;
     hold_back(n_next, f0, f1, f2);
 
-    // ---- phase 0: this tile's nodal data and history have landed; start the next gather
+    // ---- phase 0: this tile's nodal data and history have landed
     sm.bc[el_p][sub * 3 + 0] = f0 ? 0.f : 1.f;
     sm.bc[el_p][sub * 3 + 1] = f1 ? 0.f : 1.f;
     sm.bc[el_p][sub * 3 + 2] = f2 ? 0.f : 1.f;
     cp_async_wait_all();
     __syncwarp();
-    gather_async(buf ^ 1, (long long)n_next, vt + nwarps);
-    {
-      const uint8_t* pf = args.dir + (long long)n_next * 3;
-      f0 = __ldg(pf); f1 = __ldg(pf + 1); f2 = __ldg(pf + 2);
-    }
-    n_next = node_of(vt + 2 * nwarps);
-
     // ---- phase 1: lane (element, Gauss point): geometry (geometry.py:88-97), strain = B u, return mapping
     unsigned plastic_mask;
     {
@@ -149,7 +148,7 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
           const int bx = ((a & 3) == 1 || (a & 3) == 2), by = (a >> 1) & 1, bz = (a >> 2) & 1;
-          const double x = sm.X[buf][i][el_p * 8 + a];
+          const double x = sm.X[i][el_p * 8 + a];
           j0 += (bx ? x : -x) * fyz[by][bz];
           j1 += (by ? x : -x) * fxz[bx][bz];
           j2 += (bz ? x : -x) * fxy[bx][by];
@@ -188,7 +187,7 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
         sm.gzs[el_p][sub][a ^ swz_p] = make_double2(g[2], wd);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          const double ui = sm.u[buf][i][el_p * 8 + a];
+          const double ui = sm.u[i][el_p * 8 + a];
 #pragma unroll
           for (int k = 0; k < 3; ++k) H[i][k] += ui * g[k];
         }
@@ -197,29 +196,37 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
       const double e_tot[6] = {H[0][0], H[1][1], H[2][2], H[0][1] + H[1][0], H[1][2] + H[2][1], H[0][2] + H[2][0]};
       double ep[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) ep[k] = sm.st[buf][k][lane];
-      const double xi = sm.st[buf][6][lane];
+      for (int k = 0; k < 6; ++k) ep[k] = sm.st[k][lane];
+      const double xi = sm.st[6][lane];
       J2Point<double> p;
       j2_radial<double>(e_tot, ep, xi, lam, G, y0, h1, h2, p);
+      if (lane == 0) bulk_wait_read<0>();   // the previous tile's last Ke copy has left the staging slot
+      __syncwarp();
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         sm.dv[k][lane] = p.d[k];
         sm.ws[k][lane] = wd * p.sig[k];
-        sm.sto[lane * 7 + k] = ep[k] + p.c * p.d[k];
+        sm.stage[lane * 7 + k] = ep[k] + p.c * p.d[k];
       }
-      sm.sto[lane * 7 + 6] = xi + p.dl;
+      sm.stage[lane * 7 + 6] = xi + p.dl;
       sm.wl[lane] = wd * (lam + p.a * (1.0 / 3.0));
       sm.wm[lane] = wd * (2.0 * G - p.a);
       sm.wb[lane] = wd * p.b;
-      sm.wd[lane] = wd;
       plastic_mask = __ballot_sync(0xffffffffu, (p.a != 0.0) | (p.b != 0.0));
     }
     fence_async_smem();
     __syncwarp();
+    // X / u / history of this tile are consumed: the next tile's gather lands behind phase 2
+    gather_async((long long)n_next, vt + nwarps);
+    {
+      const uint8_t* pf = args.dir + (long long)n_next * 3;
+      f0 = __ldg(pf); f1 = __ldg(pf + 1); f2 = __ldg(pf + 2);
+    }
+    n_next = node_of(vt + 2 * nwarps);
     {  // new history of the tile: one contiguous bulk copy (mechanical_elastoplasticity.py:217)
       long long cnt = args.ne - e0;
       cnt = cnt > kTile ? kTile : cnt;
-      if (lane == 0) bulk_store(args.state_out + e0 * 56, sm.sto, (unsigned)(cnt * 56 * sizeof(double)));
+      if (lane == 0) bulk_store(args.state_out + e0 * 56, sm.stage, (unsigned)(cnt * 56 * sizeof(double)));
     }
 
     // ---- phase 2: one element at a time, lane (a, k)
@@ -319,7 +326,7 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
         for (int g = 0; g < 8; ++g) {
           const double gx = 1.0 + sgn_x(ra) * sgn_x(g) * FOL_S3, gy = 1.0 + sgn_y(ra) * sgn_y(g) * FOL_S3;
           const double gz = 1.0 + sgn_z(ra) * sgn_z(g) * FOL_S3;
-          nw += sm.wd[el * 8 + g] * (0.125 * gx * gy * gz);
+          nw += sm.gzs[el][g][((g & 3) << 1) | (g >> 2)].y * (0.125 * gx * gy * gz);   // w detJ rides with node 0's gradient
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) r[i] -= args.p.v[2 + i] * nw;

@@ -291,6 +291,15 @@ void fol_plan_destroy(fol_plan* plan);
  * be pinned for full PCIe rate. */
 int fol_plan_assemble_host(fol_plan* plan, int transpose, const void* ctrl_host,
                            const void* u_host, void* ke_data_host, void* residual_host);
+/* Duplicate-free CSR hand-off -- what the reference's solvers consume after summing the BCOO on the host
+ * (fol/solvers/fe_solver.py:71-72).  fol_plan_set_csr uploads the integer plan once per mesh (host arrays of
+ * folax_b200/csr_plan.py); fol_plan_assemble_host_csr then does H2D of the inputs, the element stage, the
+ * de-duplication on the device and the D2H of nnz values (in the order of the plan's indptr / indices) + residual,
+ * pipelined in chunks of whole node rows.  Returns after the copies have landed. */
+int fol_plan_set_csr(fol_plan* plan, int64_t npairs, int64_t nnz, const int32_t* pair_ptr_host,
+                     const int32_t* contrib_host, const int32_t* out_base_host, const int32_t* row_stride_host);
+int fol_plan_assemble_host_csr(fol_plan* plan, int transpose, const void* controls_host, const void* dofs_host,
+                               void* csr_values_host, void* residual_host);
 /* same plan, device-resident outputs owned by the plan (for timing without the copies) */
 int fol_plan_assemble_device(fol_plan* plan, int transpose, const void* ctrl_dev,
                              const void* u_dev, void** ke_data_dev, void** residual_dev);

@@ -13,13 +13,16 @@ from folax_b200.solvers import FiniteElementNonLinearResidualBasedSolver
 
 n = int(os.environ.get("N", 30))
 mesh = folax_b200.create_3D_tetra_box_mesh(n, n, n, 1.0, 1.0, 1.0)
-bc = {"Ux": {"left": 0.0, "right": 0.1}, "Uy": {"left": 0.0, "right": 0.02}, "Uz": {"left": 0.0, "right": -0.02}}
+# the boundary displacement per load step must stay a fraction of the element size h = 1/n: Newton without a line
+# search (the reference's, fe_nonlinear_residual_based_solver.py:111-166) applies it to the undeformed interior at once
+disp = float(os.environ.get("DISP", 0.02))
+bc = {"Ux": {"left": 0.0, "right": disp}, "Uy": {"left": 0.0, "right": 0.2 * disp}, "Uz": {"left": 0.0, "right": -0.2 * disp}}
 loss = NeoHookeMechanicalLoss3DTetra("nh", {"dirichlet_bc_dict": bc, "material_dict": {"young_modulus": 1.0,
                                                                                       "poisson_ratio": 0.3}}, mesh)
 settings = {"linear_solver_settings": {"solver": "JAX-bicgstab", "tol": float(os.environ.get("TOL", 1e-8)), "atol": 0.0,
                                        "maxiter": int(os.environ.get("MAXITER", 2000)), "pre-conditioner": "jacobi"},
             "nonlinear_solver_settings": {"rel_tol": 1e-8, "abs_tol": 1e-8, "maxiter": 10,
-                                          "load_incr": int(os.environ.get("LOAD_STEPS", 2))}}
+                                          "load_incr": int(os.environ.get("LOAD_STEPS", 5))}}
 solver = FiniteElementNonLinearResidualBasedSolver("nl", loss, settings)
 loss.Initialize()
 solver.Initialize()
