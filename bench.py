@@ -5,14 +5,19 @@
 
 Metric (BASELINE.json): assembled elements/s (residual + Jacobian), 3-D hex linear elasticity,
 float64, 128^3 elements per GPU (configs[1]).  One JSON line on stdout (rank 0).
-  value       device-resident inputs, whole job (all ranks), CUDA-event timed, max over ranks
-  e2e         same metric through the host-buffer C-ABI call fol_plan_assemble_host (pinned host
-              inputs -> H2D, kernels, D2H of the BCOO data + residual inside the timed region)
-  roofline    dominant kernel (element stage) vs measured HBM copy bandwidth
-  cpu_baseline  C/OpenMP port of the reference arithmetic (oracle/c) on all host cores, bounded sample
-  fol_loss_grad secondary metric: FOL physics loss + VJP samples/s (thermal 256x256 quads), with its own
-              cpu_baseline (C/OpenMP port of the batched loss + gradient, physics only) at N = 1
-`--impl reference` times the CPU port alone (the reference itself needs JAX, absent here).
+  value         device-resident inputs, whole job (all ranks), CUDA-event timed, max over ranks
+  e2e           same metric through the host-buffer C-ABI call fol_plan_assemble_host (pinned host inputs -> H2D,
+                kernels, D2H of the BCOO data + residual inside the timed region); e2e.csr = the duplicate-free CSR
+                hand-off (fol_plan_assemble_host_csr), what the reference's solvers consume after their host-side sum
+  roofline      dominant kernel (element stage), timed by CUDA events INSIDE the measured steps, vs the measured HBM
+                copy bandwidth; traffic = DRAM bytes per launch from the ncu capture named in traffic_source
+  cpu_baseline  C/OpenMP port of the reference arithmetic (oracle/c) on all host cores, same 128^3 mesh, bounded time
+  halo_check    N > 1: both copies of every interface plane bit-identical across neighbours, and one plane against a
+                single-rank re-assembly of the two element layers that meet there
+Extra keys (each with its own config / roofline): fol_loss_grad (configs[2], weak and strong scaling), j2 (configs[4]:
+J2 elastoplasticity with Gauss-point history, 128^3 per GPU, slab-partitioned with the fused halo at N > 1), spmv and
+newton (configs[3]) at N = 1.
+`--impl reference` times the CPU port alone on the same mesh (the reference itself needs JAX, absent here).
 """
 import argparse
 import ctypes
@@ -28,6 +33,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 
 _REAL_STDOUT = None
+_T0 = time.time()
 
 
 def emit(line):
@@ -36,8 +42,14 @@ def emit(line):
     out.flush()
 
 
-ALG_BYTES_PER_ELEMENT_F64 = 4720.0   # 4608 Ke + 32 conn + 56 nodal in + 24 residual
+ALG_BYTES_PER_ELEMENT_F64 = 4720.0      # 4608 Ke + 32 conn + 56 nodal in + 24 residual
+ALG_BYTES_PER_ELEMENT_J2_F64 = 5616.0   # + Gauss-point history in and out: 2 x 8 x 7 x 8 B
 MATERIAL = {"young_modulus": 1.0, "poisson_ratio": 0.3}
+J2_MATERIAL = {"young_modulus": 3.0, "poisson_ratio": 0.3, "iso_hardening_parameter_1": 0.4,
+               "iso_hardening_param_2": 10.0, "yield_limit": 0.2}       # tests/unit/test_elastoplasticity.py:34-40
+BC = {d: {"left": 0.0, "right": 0.1} for d in ("Ux", "Uy", "Uz")}
+TRAFFIC_FILES = {"hex": os.path.join("profiles", "r2", "assemble_hex_traffic.json"),
+                 "j2": os.path.join("profiles", "r2", "assemble_hex_j2_traffic.json")}
 
 
 def measured_peaks():
@@ -46,6 +58,16 @@ def measured_peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_of(which, n, world):
+    """DRAM bytes per launch from the committed ncu capture of this round (profiles/extract_traffic.py wrote the file);
+    only meaningful for the size it was captured at."""
+    path = os.path.join(ROOT, TRAFFIC_FILES[which])
+    if n != 128 or not os.path.exists(path):
+        return None, None
+    d = json.load(open(path))
+    return d["dram_bytes"], f"{TRAFFIC_FILES[which]} (ncu --set full of `{d.get('command', '?')}`, dram read + write per launch)"
 
 
 class ClockSampler:
@@ -100,32 +122,63 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-# ------------------------------------------------------------------------------------ CPU leg
-def cpu_assembly_rate(n_side, min_seconds, threads):
-    """CPU baseline: the plain-C / OpenMP restatement of the reference arithmetic (oracle/c/hex_mech.c,
-    dense B^T D B per Gauss point exactly as mechanical.py:98-117 writes it) on an n_side^3 hex box, all
-    host threads.  Returns (elements/s, elements done, seconds)."""
-    import folax_b200
-    from oracle import assembly, c_oracle
-    threads = c_oracle.set_threads(threads)   # torchrun exports OMP_NUM_THREADS=1: set the count explicitly
-    mesh = folax_b200.create_3D_box_mesh(n_side, n_side, n_side, 1.0, 1.0, 1.0)
-    coords, conn = np.asarray(mesh.GetNodesCoordinates()), mesh.GetElementsNodes("hexahedron")
-    rng = np.random.default_rng(0)
-    K = rng.uniform(0.1, 1.0, len(coords))
-    u = 0.01 * rng.standard_normal(3 * len(coords))
-    didx, _ = assembly.dirichlet_vectors(["Ux", "Uy", "Uz"], {d: {"left": 0.0, "right": 0.1} for d in ("Ux", "Uy", "Uz")},
-                                         mesh.node_sets)
-    ne = len(conn)
-    out = np.empty(ne * 576)
-    c_oracle.hex_mech_assemble(coords, conn, K, u, didx, 1.0, 0.3, out=out)  # warm-up (page faults, threads)
-    t0, done = time.perf_counter(), 0
-    while True:
-        c_oracle.hex_mech_assemble(coords, conn, K, u, didx, 1.0, 0.3, out=out)
-        done += ne
-        if time.perf_counter() - t0 >= min_seconds:
-            break
-    dt = time.perf_counter() - t0
-    return done / dt, done, dt
+# ------------------------------------------------------------------------------------ synthetic fields
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def hashed_uniform(ids, stream):
+    """U(0,1) as a pure function of (global id, stream): the same node gets the same value on every rank."""
+    with np.errstate(over="ignore"):
+        z = _splitmix64(np.asarray(ids, dtype=np.uint64) * np.uint64(0xD1342543DE82EF95) + np.uint64(stream) * np.uint64(0x632BE59BD9B4E019))
+    return ((z >> np.uint64(11)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+
+
+def global_fields(gids, d=3):
+    """K ~ U(0.1, 1) per node and u ~ 0.01 N(0,1) per dof (Box-Muller on hashed uniforms), keyed by GLOBAL ids."""
+    K = 0.1 + 0.9 * hashed_uniform(gids, 1)
+    dof = (np.asarray(gids, dtype=np.uint64)[:, None] * np.uint64(d) + np.arange(d, dtype=np.uint64)[None, :]).reshape(-1)
+    u = 0.01 * np.sqrt(-2.0 * np.log(hashed_uniform(dof, 2))) * np.cos(2.0 * np.pi * hashed_uniform(dof, 3))
+    return K, u
+
+
+# ------------------------------------------------------------------------------------ CPU legs
+class CpuAssembly:
+    """CPU baseline: the plain-C / OpenMP restatement of the reference arithmetic (oracle/c/hex_mech.c, dense B^T D B
+    per Gauss point exactly as mechanical.py:98-117 writes it) on an n_side^3 hex box, all host threads.  The mesh and
+    the output buffer are built once; run(min_seconds) -> (elements/s, elements done, seconds) of whole passes."""
+
+    def __init__(self, n_side, threads):
+        import folax_b200
+        from oracle import assembly, c_oracle
+        self.c = c_oracle
+        self.threads = c_oracle.set_threads(threads)   # torchrun exports OMP_NUM_THREADS=1: set the count explicitly
+        mesh = folax_b200.create_3D_box_mesh(n_side, n_side, n_side, 1.0, 1.0, 1.0)
+        self.coords, self.conn = np.asarray(mesh.GetNodesCoordinates()), mesh.GetElementsNodes("hexahedron")
+        rng = np.random.default_rng(0)
+        self.K = rng.uniform(0.1, 1.0, len(self.coords))
+        self.u = 0.01 * rng.standard_normal(3 * len(self.coords))
+        self.didx, _ = assembly.dirichlet_vectors(["Ux", "Uy", "Uz"], BC, mesh.node_sets)
+        self.ne = len(self.conn)
+        self.out = np.empty(self.ne * 576)
+        self.once()                                    # warm-up (page faults, thread pool)
+
+    def once(self):
+        self.c.hex_mech_assemble(self.coords, self.conn, self.K, self.u, self.didx, 1.0, 0.3, out=self.out)
+
+    def run(self, min_seconds):
+        t0, done = time.perf_counter(), 0
+        while True:
+            self.once()
+            done += self.ne
+            if time.perf_counter() - t0 >= min_seconds:
+                break
+        dt = time.perf_counter() - t0
+        return done / dt, done, dt
 
 
 def cpu_fol_rate(min_seconds, threads):
@@ -154,30 +207,31 @@ def cpu_fol_rate(min_seconds, threads):
 
 
 def run_reference(args):
+    """The CPU arm on the SAME configuration (n^3 hex elements, f64): every step is whole passes over the mesh for a
+    bounded time."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_side = 64
-    per_step = []
+    n_side = args.n
+    cpu = CpuAssembly(n_side, threads)
     for _ in range(args.warmup):
-        cpu_assembly_rate(n_side, 0.0, threads)
-    t_budget = max(1.0, 20.0 / max(args.steps, 1))
-    total, total_t = 0, 0.0
+        cpu.once()
+    t_budget = max(0.5, 20.0 / max(args.steps, 1))
+    per_step, total, total_t = [], 0, 0.0
     for _ in range(args.steps):
-        rate, done, dt = cpu_assembly_rate(n_side, t_budget, threads)
+        rate, done, dt = cpu.run(t_budget)
         per_step.append(dt)
         total += done
         total_t += dt
     value = total / total_t
-    sample = f"{n_side}^3 hex elements (f64) per pass, repeated for >= {t_budget:.1f} s per step"
+    sample = f"whole passes over the {n_side}^3-element hex box (f64) for >= {t_budget:.1f} s per step ({total} elements)"
     line = {"impl": "reference", "metric": "assembled_elements_per_s", "value": value, "unit": "elements/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * float(np.mean(per_step)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"hex{args.n}_linear_elastic_residual_jacobian_f64", "num_gp": 2,
-                       "output": "BCOO data with duplicates + residual",
-                       "sample_note": f"CPU leg timed on a bounded {n_side}^3-element sample of the same mesh family"},
+            "config": {"workload": f"hex{args.n}_linear_elastic_residual_jacobian_f64", "elements_per_gpu": n_side ** 3,
+                       "num_gp": 2, "output": "BCOO data with duplicates + residual"},
             "cpu_baseline": {"value": value, "unit": "elements/s", "cores": threads, "kind": "port", "sample": sample,
                              "note": "restated reference arithmetic (plain C + OpenMP, oracle/c/hex_mech.c), not the JAX "
                                      "path: JAX is not installable in this image"},
@@ -186,7 +240,7 @@ def run_reference(args):
     emit(line)
 
 
-# ------------------------------------------------------------------------------------ GPU leg
+# ------------------------------------------------------------------------------------ GPU legs
 def event_time_ms(torch, fn, steps, stream=None):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -197,12 +251,21 @@ def event_time_ms(torch, fn, steps, stream=None):
     return e0.elapsed_time(e1) / steps
 
 
+def max_over_ranks(torch, dist, world, values):
+    t = torch.tensor(list(values), device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
 def fol_loss_grad_bench(torch, dist, rank, world, steps, warmup):
-    """configs[2]: batch of 1024 random conductivity fields on a 256x256 thermal quad mesh,
-    physics loss + VJP through a small MLP, samples sharded over ranks, NCCL grad all-reduce."""
+    """configs[2]: batch of 1024 random conductivity fields on a 256x256 thermal quad mesh, physics loss + VJP through
+    a small MLP, samples sharded over ranks, NCCL all-reduce of the network gradients overlapped with backward.
+    Weak scaling (1024 samples per GPU) is the headline of this key; `strong` is the configuration as BASELINE.json
+    words it: ONE batch of 1024 sharded over the ranks (deep_network.py:225-235)."""
     import folax_b200
     from folax_b200 import _lib
-    from folax_b200.distributed import allreduce_gradients, shard_batch
+    from folax_b200.distributed import GradientReducer
     from folax_b200.loss_functions import ThermalLoss2DQuad
     B, N = 1024, 257
     mesh = folax_b200.create_2D_square_mesh(1.0, N)
@@ -210,28 +273,35 @@ def fol_loss_grad_bench(torch, dist, rank, world, steps, warmup):
                                              "beta": 2.0, "c": 4}, mesh)
     loss.Initialize()
     nn = mesh.GetNumberOfNodes()
-    sl = shard_batch(B * world, rank, world)       # weak scaling: 1024 samples per GPU
     g = torch.Generator(device="cuda").manual_seed(1234 + rank)
     Kb = torch.rand((B, nn), generator=g, device="cuda", dtype=torch.float64) * 0.9 + 0.1
     latent = torch.randn((B, 64), generator=g, device="cuda", dtype=torch.float64)
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(64, 256), torch.nn.Tanh(), torch.nn.Linear(256, nn)).to("cuda", torch.float64)
+    reducer = GradientReducer(list(net.parameters()))
 
-    def step():
-        for p in net.parameters():
-            p.grad = None
-        u = torch.sigmoid(net(latent))
-        mean, _ = loss.ComputeBatchLoss(Kb, u)
-        mean.backward()
-        allreduce_gradients(list(net.parameters()))
+    def make_step(nb):
+        kb, lat = Kb[:nb], latent[:nb]
 
-    def physics_only():
-        u = ub.detach().requires_grad_(True)
-        k = Kb.detach().requires_grad_(True)
-        mean, _ = loss.ComputeBatchLoss(k, u)
-        mean.backward()
+        def step():
+            for p in net.parameters():
+                p.grad = None
+            u = torch.sigmoid(net(lat))
+            mean, _ = loss.ComputeBatchLoss(kb, u)
+            mean.backward()            # the hooks start each parameter's all-reduce as its gradient appears
+            reducer.wait()
+        return step
+
+    def make_physics(nb, L, kb, ub):
+        def physics_only():
+            u = ub[:nb].detach().requires_grad_(True)
+            k = kb[:nb].detach().requires_grad_(True)
+            mean, _ = L.ComputeBatchLoss(k, u)
+            mean.backward()
+        return physics_only
 
     ub = torch.sigmoid(net(latent)).detach()
+    step, physics_only = make_step(B), make_physics(B, loss, Kb, ub)
     for _ in range(warmup):
         step()
         physics_only()
@@ -240,10 +310,34 @@ def fol_loss_grad_bench(torch, dist, rank, world, steps, warmup):
         dist.barrier()
     ms_step = event_time_ms(torch, step, steps)
     ms_phys = event_time_ms(torch, physics_only, steps)
-    t = torch.tensor([ms_step, ms_phys], device="cuda", dtype=torch.float64)
+    ms_step, ms_phys = max_over_ranks(torch, dist, world, [ms_step, ms_phys])
+
+    # ---- strong scaling: the 1024-sample batch of configs[2] sharded over the ranks
+    nb_s = B // world
+    step_s, phys_s = make_step(nb_s), make_physics(nb_s, loss, Kb, ub)
+    for _ in range(3):
+        step_s()
+        phys_s()
+    torch.cuda.synchronize()
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step, ms_phys = t.tolist()
+        dist.barrier()
+    ms_step_s = event_time_ms(torch, step_s, steps)
+    ms_phys_s = event_time_ms(torch, phys_s, steps)
+    ms_step_s, ms_phys_s = max_over_ranks(torch, dist, world, [ms_step_s, ms_phys_s])
+    # the all-reduce alone (what bounds the strong-scaling step once the per-rank physics is ~0.2 ms)
+    ms_ar = 0.0
+    if world > 1:
+        grads = [torch.zeros_like(p) for p in net.parameters()]
+
+        def ar():
+            for t in grads:
+                dist.all_reduce(t)
+        for _ in range(3):
+            ar()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms_ar, = max_over_ranks(torch, dist, world, [event_time_ms(torch, ar, steps)])
+
     hbm, _ = measured_peaks()
     bytes_per_sample = 32.0 * nn  # read u, K; write dE/du, dE/dK (f64)
     # f64 work per sample (SASS count of energy_tile2_kernel, profiles/r1/energy_tile2_sass_hist.txt):
@@ -254,12 +348,7 @@ def fol_loss_grad_bench(torch, dist, rank, world, steps, warmup):
                                                  "beta": 2.0, "c": 4, "dtype": "float32"}, mesh)
     loss32.Initialize()
     K32, u32 = Kb.float(), ub.float()
-
-    def physics_only32():
-        uu = u32.detach().requires_grad_(True)
-        kk = K32.detach().requires_grad_(True)
-        mean, _ = loss32.ComputeBatchLoss(kk, uu)
-        mean.backward()
+    physics_only32 = make_physics(B, loss32, K32, u32)
     for _ in range(3):
         physics_only32()
     ms_phys32 = event_time_ms(torch, physics_only32, steps)
@@ -267,6 +356,7 @@ def fol_loss_grad_bench(torch, dist, rank, world, steps, warmup):
     torch.manual_seed(0)
     net32 = torch.nn.Sequential(torch.nn.Linear(64, 256), torch.nn.Tanh(), torch.nn.Linear(256, nn)).to("cuda")
     latent32 = latent.float()
+    reducer32 = GradientReducer(list(net32.parameters()))
 
     def step_mixed():
         for p in net32.parameters():
@@ -274,24 +364,31 @@ def fol_loss_grad_bench(torch, dist, rank, world, steps, warmup):
         uu = torch.sigmoid(net32(latent32)).double()
         mean, _ = loss.ComputeBatchLoss(Kb, uu)
         mean.backward()
-        allreduce_gradients(list(net32.parameters()))
+        reducer32.wait()
     for _ in range(3):
         step_mixed()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    ms_mixed = event_time_ms(torch, step_mixed, steps)
-    t = torch.tensor([ms_mixed], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_mixed = t.item()
+    ms_mixed, = max_over_ranks(torch, dist, world, [event_time_ms(torch, step_mixed, steps)])
+    reducer.close()
+    reducer32.close()
     tf = ctypes.c_double()
     fp64_peak = tf.value if (rank == 0 and _lib.load().fol_measure_fma_peak(_lib.F64, ctypes.byref(tf)) == 0) else None
     ach_tf = flops_per_sample * B / (ms_phys * 1e-3) / 1e12
     return {"metric": "fol_loss_grad_samples_per_s", "value": B * world / (ms_step * 1e-3), "unit": "samples/s",
-            "physics_only_samples_per_s": B * world / (ms_phys * 1e-3), "ms_per_step": ms_step,
+            "scaling": "weak", "physics_only_samples_per_s": B * world / (ms_phys * 1e-3), "ms_per_step": ms_step,
             "ms_per_step_physics_only": ms_phys,
             "physics_only_f32_samples_per_s_per_gpu": B / (ms_phys32 * 1e-3),
+            "headline_note": "the path's own number is physics_only_samples_per_s (loss + VJP kernels); `value` adds "
+                             "the caller's f64 MLP (torch / cuBLAS) and the gradient all-reduce",
+            "strong": {"scaling": "strong", "global_batch": B, "batch_per_gpu": nb_s,
+                       "value": B / (ms_step_s * 1e-3), "unit": "samples/s", "ms_per_step": ms_step_s,
+                       "physics_only_samples_per_s": B / (ms_phys_s * 1e-3), "ms_per_step_physics_only": ms_phys_s,
+                       "allreduce_alone_ms": ms_ar,
+                       "limiter": ("the all-reduce of the 135 MB output-layer gradient (its size does not shrink with "
+                                   "the per-rank batch) and the fixed launch cost of the ~20 kernels of a step, against "
+                                   "a per-rank physics time that does shrink") if world > 1 else "single GPU"},
             "f32_network_f64_physics": {"value": B * world / (ms_mixed * 1e-3), "unit": "samples/s",
                                         "ms_per_step": ms_mixed,
                                         "note": "MLP in float32 (flax default parameter dtype), physics loss + VJP in "
@@ -299,7 +396,9 @@ def fol_loss_grad_bench(torch, dist, rank, world, steps, warmup):
             "config": {"workload": "thermal_quad256_loss_vjp_f64", "batch_per_gpu": B, "mesh": "256x256 quads",
                        "beta": 2.0, "c": 4, "network": "MLP 64-256-66049 (f64, torch/cuBLAS: caller code, not the path)",
                        "kernel": "energy_tile2_kernel (pipelined fused loss + VJP, Dirichlet overwrite and 1/B scale fused)",
-                       "parallelism": f"dp{world}"},
+                       "parallelism": f"dp{world}, gradient all-reduce started per parameter from autograd hooks "
+                                      "(overlaps the rest of backward)",
+                       "tolerance": "f64 1e-12, f32 1e-5, norm-wise (|x - ref|_max <= tol |ref|_max) in the parity tests"},
             "roofline_physics": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                                  "frac": (ach_tf / fp64_peak) if fp64_peak else None,
                                  "flops_per_sample": flops_per_sample,
@@ -310,11 +409,211 @@ def fol_loss_grad_bench(torch, dist, rank, world, steps, warmup):
                                      "algorithmic_bytes_per_sample": bytes_per_sample}}
 
 
+def j2_bench(torch, dist, rank, world, n, steps, ke):
+    """configs[4]: J2 elastoplasticity with per-Gauss-point history on a hex box, element-partitioned into z-slabs with
+    the halo-DOF exchange (n^3 elements and their (ne, 8, 7) history per GPU: 256^3 over 8 GPUs at n = 128).  Two load
+    steps: the timed one starts from the non-zero history the first one returned."""
+    from folax_b200 import _lib
+    from folax_b200.distributed import SlabPartition, assemble_overlapped
+    from folax_b200.loss_functions import ElastoplasticityLoss3DHexa
+    lib = _lib.load()
+    part = SlabPartition(n, n, n * world, 1.0, 1.0, float(world), rank, world)
+    loss = ElastoplasticityLoss3DHexa("j2", {"dirichlet_bc_dict": BC, "num_gp": 2, "material_dict": dict(J2_MATERIAL)},
+                                      part.mesh)
+    loss.Initialize()
+    ne = loss._ne
+    _, u1 = global_fields(part.global_node_ids())
+    h = 1.0 / n
+    u1 = torch.tensor(u1 * (2.0 * h), device="cuda")       # 0.02 h N(0,1) (SURVEY.md 8d): elastic and plastic points mixed
+    K = torch.ones(loss._nn, dtype=torch.float64, device="cuda")
+    st0 = torch.zeros(loss.GetStateShape(), dtype=torch.float64, device="cuda")
+    st1, st2 = torch.empty_like(st0), torch.empty_like(st0)
+    halo = "single GPU"
+    if world > 1:
+        halo = "fused into the element-stage launch (NVLink peer stores)" if part.enable_peer_halo(loss) else "nccl"
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+
+    def step(u, s_in, s_out, events=None):
+        if world > 1:
+            return assemble_overlapped(loss, part, K, u, ke, None, state_in=s_in, state_out=s_out, kernel_events=events)
+        if events is not None:
+            events[0].record()
+        re = torch.empty(ne * 24, dtype=torch.float64, device="cuda")
+        _lib.check(lib.fol_assemble_elements(_lib.stream_ptr(), loss._dt, _lib.PHYSICS["j2plasticity"], 0, 2, 0, ne,
+                                             loss._nn, _lib.ptr(loss._xyz), _lib.ptr(loss._conn), _lib.ptr(K), _lib.ptr(u),
+                                             _lib.ptr(loss._dir_flag), loss._params, _lib.ptr(ke), _lib.ptr(re),
+                                             _lib.ptr(s_in), _lib.ptr(s_out)))
+        if events is not None:
+            events[1].record()
+        R = torch.empty(loss.total_number_of_dofs, dtype=torch.float64, device="cuda")
+        _lib.check(lib.fol_residual_gather(_lib.stream_ptr(), loss._dt, loss._nn, 8, 3, _lib.ptr(loss._adj_ptr),
+                                           _lib.ptr(loss._adj), _lib.ptr(re), _lib.ptr(R)))
+        return ke, R
+    step(u1, st0, st1)                          # load step 1 (from zero history)
+    u2 = 2.0 * u1
+    for _ in range(3):
+        step(u2, st1, st2)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(u2, st1, st2, ev[i])
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    ms, ms_kernel = max_over_ranks(torch, dist, world, [ms, ms_kernel])
+    plastic = float((st2[..., -1] > st1[..., -1]).double().mean())
+    plastic_before = float((st1[..., -1] > 0).double().mean())
+    hbm, peak_src = measured_peaks()
+    achieved = ALG_BYTES_PER_ELEMENT_J2_F64 * ne / (ms_kernel * 1e-3) / 1e9
+    traffic, tsrc = traffic_of("j2", n, world)
+    if world > 1:
+        part.close_peer_halo()
+    return {"metric": "assembled_elements_per_s", "value": ne * world / (ms * 1e-3), "unit": "elements/s",
+            "ms_per_step": ms, "scaling": "weak", "dtype": "f64",
+            "config": {"workload": f"hex{n}_j2_elastoplastic_residual_jacobian_state_f64", "elements_per_gpu": ne,
+                       "global_mesh": f"{n}x{n}x{n * world} hex elements", "state": "(ne, 8, 7) f64 in and out",
+                       "plastic_points_in_timed_step": plastic, "plastic_points_in_history": plastic_before,
+                       "parallelism": f"element slabs x{world} + halo-DOF sum ({halo})" if world > 1 else "single GPU"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                         "traffic": traffic, "traffic_source": tsrc, "kernel": "assemble_hex_j2_f64_kernel",
+                         "kernel_ms": ms_kernel, "kernel_timing": "CUDA events around the launch inside every timed step",
+                         "algorithmic_bytes_per_element": ALG_BYTES_PER_ELEMENT_J2_F64, "peak_source": peak_src}}
+
+
+def spmv_bench(torch, loss, K, u):
+    """(f.1) duplicate-free CSR + SELL SpMV on the 128^3 elasticity Jacobian: the solver hand-off of fe_solver.py:60-103."""
+    from folax_b200 import linalg
+    jac, R = loss.ComputeJacobianMatrixAndResidualVector(K, u)
+    t0 = time.time()
+    loss._csr_plan()
+    sp = loss._sell_plan()
+    plan_s = time.time() - t0
+    ms_csr = event_time_ms(torch, lambda: loss.JacobianToCSR(jac), 3)
+    A = linalg.SellOperator(loss, jac)
+    v = torch.randn(loss.total_number_of_dofs, device="cuda", dtype=torch.float64)
+    y = torch.empty_like(v)
+    for _ in range(3):
+        A.matvec(v, y)
+    ms = event_time_ms(torch, lambda: A.matvec(v, y), 20)
+    nbytes = (8.0 + 4.0 / 3.0) * sp["total"] + 16.0 * sp["nrows"]
+    hbm, _ = measured_peaks()
+    x, info = linalg.bicgstab(A, -R, x0=None, tol=1e-8, atol=0.0, maxiter=50, M_diagonal=A.diagonal())
+    torch.cuda.synchronize()
+    t0 = time.time()
+    x, info = linalg.bicgstab(A, -R, x0=None, tol=1e-8, atol=0.0, maxiter=50, M_diagonal=A.diagonal())
+    torch.cuda.synchronize()
+    it_ms = 1e3 * (time.time() - t0) / max(info, 1)
+    del A, jac
+    return {"workload": "SELL SpMV of the de-duplicated 128^3 Hex8 elasticity Jacobian, f64", "nnz": sp["nnz"],
+            "stored_entries": sp["total"], "ms": ms, "gbs": nbytes / (ms * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                         "frac": nbytes / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": nbytes,
+                         "note": "9.33 B per stored entry (value + one node column per run of 3) + 16 B per row"},
+            "csr_values_ms": ms_csr, "bicgstab_jacobi_ms_per_iteration": it_ms, "host_plans_s": plan_s}
+
+
+def newton_bench(torch):
+    """configs[3]: Neo-Hooke on a Kuhn-split tetra box (70^3 cells = 2.06 M Tet4), ONE load step of the incremental
+    Newton-Raphson (Jacobian re-assembled every iteration, Jacobi-BiCGSTAB on the device-resident SELL matrix)."""
+    import folax_b200
+    from folax_b200 import linalg
+    from folax_b200.loss_functions import NeoHookeMechanicalLoss3DTetra
+    from folax_b200.solvers import FiniteElementNonLinearResidualBasedSolver
+    n, disp = 70, 0.004
+    mesh = folax_b200.create_3D_tetra_box_mesh(n, n, n, 1.0, 1.0, 1.0)
+    bc = {"Ux": {"left": 0.0, "right": disp}, "Uy": {"left": 0.0, "right": 0.2 * disp}, "Uz": {"left": 0.0, "right": -0.2 * disp}}
+    loss = NeoHookeMechanicalLoss3DTetra("nh", {"dirichlet_bc_dict": bc, "material_dict": dict(MATERIAL)}, mesh)
+    solver = FiniteElementNonLinearResidualBasedSolver("nl", loss, {
+        "linear_solver_settings": {"solver": "JAX-bicgstab", "tol": 1e-8, "atol": 0.0, "maxiter": 3000,
+                                   "pre-conditioner": "jacobi"},
+        "nonlinear_solver_settings": {"rel_tol": 1e-8, "abs_tol": 1e-8, "maxiter": 10, "load_incr": 1}})
+    loss.Initialize()
+    solver.Initialize()
+    K = np.random.default_rng(0).uniform(0.5, 1.0, mesh.GetNumberOfNodes())
+    split = {"assembly_s": 0.0, "operator_s": 0.0, "krylov_s": 0.0, "newton_iterations": 0, "krylov_iterations": 0}
+
+    def timed(fn, key):
+        def wrapper(*a, **k):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = fn(*a, **k)
+            torch.cuda.synchronize()
+            split[key] += time.perf_counter() - t0
+            return out
+        return wrapper
+    t0 = time.time()
+    loss._csr_plan()
+    loss._sell_plan()
+    plans = time.time() - t0
+    loss.ComputeJacobianMatrixAndResidualVector = timed(loss.ComputeJacobianMatrixAndResidualVector, "assembly_s")
+    sell, bicg = linalg.SellOperator, linalg.bicgstab
+    linalg.SellOperator = timed(sell, "operator_s")
+
+    def counted(*a, **k):
+        x, info = timed(bicg, "krylov_s")(*a, **k)
+        split["krylov_iterations"] += max(info, 0)
+        split["newton_iterations"] += 1
+        return x, info
+    linalg.bicgstab = counted
+    try:
+        solver.Solve(K, np.zeros(loss.GetTotalNumberOfDOFs()))
+    finally:
+        linalg.SellOperator, linalg.bicgstab = sell, bicg
+    it = max(split["newton_iterations"], 1)
+    return {"workload": "tet_neo_hooke_newton_f64 (70^3 Kuhn cells)", "elements": loss._ne,
+            "dofs": loss.total_number_of_dofs, **split, "host_plans_s": plans,
+            "final_residual_norm": solver.convergence_history[1]["res_norm"][-1],
+            "per_newton_iteration_ms": {k[:-2]: 1e3 * split[k] / it for k in ("assembly_s", "operator_s", "krylov_s")},
+            "assembly_elements_per_s": loss._ne * it / max(split["assembly_s"], 1e-12),
+            "note": "Krylov time is launch / host-read latency at this size (0.4 ms per BiCGSTAB iteration for 1.07 M "
+                    "dofs), not bandwidth: see profiles/r2"}
+
+
+def halo_check(torch, dist, rank, world, part, loss, R, n):
+    """N > 1: (1) both copies of every interface plane, gathered from all ranks, are bit-identical; (2) this rank's
+    upper interface plane equals a single-rank re-assembly of the two element layers that meet there."""
+    from folax_b200.distributed import SlabPartition
+    from folax_b200.loss_functions import MechanicalLoss3DHexa
+    d, plane = 3, part.plane_nodes
+    lo, up = R[:plane * d].contiguous(), R[-plane * d:].contiguous()
+    los = [torch.empty_like(lo) for _ in range(world)]
+    ups = [torch.empty_like(up) for _ in range(world)]
+    dist.all_gather(los, lo)
+    dist.all_gather(ups, up)
+    equal = all(bool(torch.equal(ups[r], los[r + 1])) for r in range(world - 1))
+    rel = 0.0
+    if rank < world - 1:
+        nz = part.nz_local
+        two = SlabPartition(n, n, 2, 1.0, 1.0, 2.0 / n, 0, 1)          # two layers around the interface
+        gids = np.arange(two.mesh.GetNumberOfNodes(), dtype=np.int64) + ((rank + 1) * nz - 1) * plane
+        Kc, uc = global_fields(gids)
+        l2 = MechanicalLoss3DHexa("chk", {"dirichlet_bc_dict": BC, "num_gp": 2, "material_dict": dict(MATERIAL)}, two.mesh)
+        l2.Initialize()
+        X = np.array(two.mesh.nodes_coordinates)
+        X[:, 2] += ((rank + 1) * nz - 1) * (1.0 / n)
+        l2._xyz = _to_dev(torch, X)
+        uc = l2.ApplyDirichletBCOnDofVector(torch.tensor(uc, device="cuda"))
+        _, R2 = l2._assemble(torch.tensor(Kc, device="cuda"), uc, False)
+        mid = R2[plane * d:2 * plane * d]
+        rel = float((mid - up).abs().max() / mid.abs().max())
+    rel, = max_over_ranks(torch, dist, world, [rel])
+    return {"planes": world - 1, "bitwise_equal": bool(equal), "max_rel_vs_single": rel,
+            "note": "interface-plane residual after the timed steps; single = one-rank assembly of the two adjacent "
+                    "element layers (summation order differs: rounding-level agreement expected)"}
+
+
+def _to_dev(torch, a):
+    return torch.tensor(np.ascontiguousarray(a, dtype=np.float64), device="cuda")
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    import folax_b200
     from folax_b200 import _lib
     from folax_b200.distributed import SlabPartition, assemble_overlapped
     from folax_b200.loss_functions import MechanicalLoss3DHexa
@@ -330,33 +629,47 @@ def run_ours(args):
     # weak scaling: every rank owns an n^3 slab of an (n, n, n*world) box; interface planes shared
     part = SlabPartition(n, n, n * world, 1.0, 1.0, float(world), rank, world)
     mesh = part.mesh
-    bc = {d: {"left": 0.0, "right": 0.1} for d in ("Ux", "Uy", "Uz")}
-    loss = MechanicalLoss3DHexa("bench", {"dirichlet_bc_dict": bc, "num_gp": 2, "material_dict": dict(MATERIAL)}, mesh)
+    loss = MechanicalLoss3DHexa("bench", {"dirichlet_bc_dict": BC, "num_gp": 2, "material_dict": dict(MATERIAL)}, mesh)
     loss.Initialize()
     ne, nn, ndof = loss._ne, loss._nn, loss.total_number_of_dofs
-    rng = np.random.default_rng(rank)
-    K_host = rng.uniform(0.1, 1.0, nn)
-    u_host = 0.01 * rng.standard_normal(ndof)
+    if world == 1:
+        rng = np.random.default_rng(0)
+        K_host = rng.uniform(0.1, 1.0, nn)
+        u_host = 0.01 * rng.standard_normal(ndof)
+    else:   # fields keyed by global node ids: the two copies of an interface plane carry the same values
+        K_host, u_host = global_fields(part.global_node_ids())
     K = torch.tensor(K_host, device="cuda")
     u = loss.ApplyDirichletBCOnDofVector(torch.tensor(u_host, device="cuda"))
     ke = torch.empty(ne * 576, dtype=torch.float64, device="cuda")
+    re = torch.empty(ne * 24, dtype=torch.float64, device="cuda")
+    R = torch.empty(ndof, dtype=torch.float64, device="cuda")
 
-    comm_stream = torch.cuda.Stream() if world > 1 else None
     halo_mode = "none"
     if world > 1:
-        try:   # NVLink peer stores fused with the interface-plane gather (csrc/halo.cu); NCCL send/recv otherwise
-            halo_mode = "nvlink peer stores fused with the plane gather" if part.enable_peer_halo(loss) else "nccl send/recv"
+        try:   # NVLink peer stores from inside the element-stage launch (csrc/assemble_hex_common.cuh); NCCL otherwise
+            halo_mode = ("interface layers first, plane gather + NVLink peer stores inside the element-stage launch"
+                         if part.enable_peer_halo(loss) else "nccl send/recv")
         except Exception as ex:
             halo_mode = f"nccl send/recv (peer memory unavailable: {str(ex)[:80]})"
+    comm_stream = torch.cuda.Stream() if (world > 1 and part._halo is None) else None
+    last = {}
 
-    def step():
-        if world > 1:   # halo-DOF exchange hidden behind the interior element stage
-            return assemble_overlapped(loss, part, K, u, ke, comm_stream)
-        return loss._assemble(K, u, False, ke_out=ke)
+    def step(events=None):
+        if world > 1:   # halo-DOF exchange hidden behind the interior element tiles
+            last["R"] = assemble_overlapped(loss, part, K, u, ke, comm_stream, kernel_events=events)[1]
+            return
+        if events is not None:
+            events[0].record()
+        _lib.check(lib.fol_assemble_elements(_lib.stream_ptr(), loss._dt, 0, 0, 2, 0, ne, nn, _lib.ptr(loss._xyz),
+                                             _lib.ptr(loss._conn), _lib.ptr(K), _lib.ptr(u), _lib.ptr(loss._dir_flag),
+                                             loss._params, _lib.ptr(ke), _lib.ptr(re), None, None))
+        if events is not None:
+            events[1].record()
+        _lib.check(lib.fol_residual_gather(_lib.stream_ptr(), loss._dt, nn, 8, 3, _lib.ptr(loss._adj_ptr),
+                                           _lib.ptr(loss._adj), _lib.ptr(re), _lib.ptr(R)))
+        last["R"] = R
 
-    # multi-GPU: NCCL's first send/recv rounds (connection set-up, proxy warm-up) take tens of iterations to
-    # reach steady state, so the W requested warm-up steps are preceded by extra untimed ones
-    for _ in range(args.warmup + (40 if world > 1 else 0)):
+    for _ in range(args.warmup + (20 if world > 1 else 0)):
         step()
     torch.cuda.synchronize()
     if world > 1:
@@ -365,14 +678,23 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)
     clocks.__enter__()
     torch.cuda.synchronize()
-    ms = event_time_ms(torch, step, args.steps)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(ev[i])
+    e1.record()
+    e1.synchronize()
     torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
     launches = lib.fol_launch_count() - launches0
-    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    have_kernel_events = world == 1 or part._halo is not None
+    ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in ev])) if have_kernel_events else 0.0
     if world > 1:
         dist.barrier()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t.item()
+    ms, ms_kernel = max_over_ranks(torch, dist, world, [ms, ms_kernel])
+    if not have_kernel_events:      # NCCL fallback path: several element-stage launches per step, no single kernel time
+        ms_kernel = ms
     # the timed region is only tens of milliseconds: keep the same step running (untimed) under the clock sampler for
     # ~0.25 s more.  The count comes from the all-reduced time, so every rank runs the same number of exchanges.
     for _ in range(int(min(2000, max(10, 250.0 / ms)))):
@@ -381,24 +703,15 @@ def run_ours(args):
     clocks.__exit__()
     value = ne * world / (ms * 1e-3)
 
-    # dominant kernel alone (element stage), CUDA events on the launching stream
-    re_tmp = torch.empty(ne * 24, dtype=torch.float64, device="cuda")
-
-    def element_stage():
-        _lib.check(lib.fol_assemble_elements(_lib.stream_ptr(), loss._dt, 0, 0, 2, 0, ne, nn, _lib.ptr(loss._xyz),
-                                             _lib.ptr(loss._conn), _lib.ptr(K), _lib.ptr(u), _lib.ptr(loss._dir_flag),
-                                             loss._params, _lib.ptr(ke), _lib.ptr(re_tmp), None, None))
-    for _ in range(3):
-        element_stage()
-    ms_kernel = event_time_ms(torch, element_stage, max(args.steps, 5))
     hbm, peak_src = measured_peaks()
     achieved = ALG_BYTES_PER_ELEMENT_F64 * ne / (ms_kernel * 1e-3) / 1e9
-    # DRAM bytes per launch of this kernel from the committed ncu --set full capture (128^3 only)
-    traffic = 10.356e9 if (n == 128 and world == 1) else None
+    traffic, traffic_src = traffic_of("hex", n, world)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                "traffic": traffic, "traffic_source": "profiles/r1/assemble_hex_ncu_summary.txt (dram read + write)", "kernel": "assemble_hex_mech_f64_kernel (element stage: DMMA m8n8k4 + cp.async.bulk stores)",
-                "kernel_ms": ms_kernel, "algorithmic_bytes_per_element": ALG_BYTES_PER_ELEMENT_F64,
-                "peak_source": peak_src}
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "assemble_hex_mech_f64_kernel (element stage: DMMA m8n8k4 + cp.async.bulk stores)",
+                "kernel_ms": ms_kernel, "kernel_timing": "CUDA events around the launch inside every timed step (mean; "
+                                                         "max over ranks), so kernel_ms <= ms_per_step by construction",
+                "algorithmic_bytes_per_element": ALG_BYTES_PER_ELEMENT_F64, "peak_source": peak_src}
 
     line = {"metric": "assembled_elements_per_s", "value": value, "unit": "elements/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -406,11 +719,21 @@ def run_ours(args):
             "config": {"workload": f"hex{n}_linear_elastic_residual_jacobian_f64", "elements_per_gpu": ne,
                        "dofs_per_gpu": ndof, "num_gp": 2, "output": "BCOO data with duplicates + residual",
                        "parallelism": f"element slabs x{world} + halo-DOF sum ({halo_mode})" if world > 1 else "single GPU",
-                       "l2_policy": "per-step working set (9.7 GB Ke stream) >> 126 MB L2"},
+                       "l2_policy": "per-step working set (9.7 GB Ke stream) >> 126 MB L2",
+                       "tolerance": "parity tests: indices bit-exact; values norm-wise |x - ref|_max <= 1e-12 |ref|_max "
+                                    "(f64), 1e-5 (f32)"},
             "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks.summary()}
 
+    if world > 1:
+        try:
+            line["halo_check"] = halo_check(torch, dist, rank, world, part, loss, last["R"], n)
+        except Exception as ex:
+            line["halo_check"] = {"error": str(ex)[:300]}
+        part.close_peer_halo()   # raises if a halo wait ever timed out
+        dist.barrier()
+
     if rank == 0 and world == 1 and not args.no_extras:
-        # ---- e2e through the host-buffer C-ABI entry point (pinned host buffers)
+        # ---- e2e through the host-buffer C-ABI entry points (pinned host buffers)
         try:
             line["e2e"] = e2e_host(torch, lib, _lib, loss, mesh, K_host, u.cpu().numpy(), ne, nn, ndof, args)
         except Exception as ex:  # report, never fake
@@ -422,18 +745,33 @@ def run_ours(args):
         wb = ctypes.c_double()
         if lib.fol_measure_write_bandwidth(4 << 30, ctypes.byref(wb)) == 0:
             line["roofline"]["write_stream_gbs_measured"] = wb.value   # pure store stream on this GPU, for context
-        # ---- CPU baseline (bounded sample)
-        del ke
-        torch.cuda.empty_cache()
-        threads = os.cpu_count() or 1
-        rate, done, dt = cpu_assembly_rate(64, 10.0, threads)
-        line["cpu_baseline"] = {"value": rate, "unit": "elements/s", "cores": threads, "kind": "port",
-                                "sample": f"64^3-element hex box passes for {dt:.1f} s ({done} elements), C/OpenMP "
-                                          "restatement of the reference arithmetic (oracle/c), not the JAX path"}
     if not args.no_extras:
+        extras = []
+        try:
+            line["j2"] = j2_bench(torch, dist, rank, world, n, max(3, min(args.steps, 10)), ke)
+            extras.append("j2")
+        except Exception as ex:
+            line["j2"] = {"error": str(ex)[:300]}
+        if rank == 0 and world == 1:
+            try:
+                line["spmv"] = spmv_bench(torch, loss, K, u)
+                extras.append("spmv")
+            except Exception as ex:
+                line["spmv"] = {"error": str(ex)[:300]}
+        del ke
+        loss._cplan = loss._splan = None
+        torch.cuda.empty_cache()
+        if rank == 0 and world == 1:
+            try:
+                line["newton"] = newton_bench(torch)
+                extras.append("newton")
+            except Exception as ex:
+                line["newton"] = {"error": str(ex)[:300]}
+            torch.cuda.empty_cache()
         try:
             sec = fol_loss_grad_bench(torch, dist, rank, world, max(3, min(args.steps, 10)), 3)
             line["fol_loss_grad"] = sec
+            extras.append("fol_loss_grad")
             if rank == 0 and world == 1:
                 try:
                     threads = os.cpu_count() or 1
@@ -448,10 +786,22 @@ def run_ours(args):
                     sec["cpu_baseline"] = {"error": str(ex)[:200]}
         except Exception as ex:
             line["fol_loss_grad"] = {"error": str(ex)[:200]}
+        line["extra_keys"] = extras
+        if rank == 0 and world == 1:
+            # ---- CPU baseline on the SAME mesh (bounded time), after the GPU work so that it cannot disturb it
+            threads = os.cpu_count() or 1
+            try:
+                rate, done, dt = CpuAssembly(n, threads).run(10.0)
+                line["cpu_baseline"] = {"value": rate, "unit": "elements/s", "cores": threads, "kind": "port",
+                                        "sample": f"whole passes over the same {n}^3-element hex box for {dt:.1f} s "
+                                                  f"({done} elements), C/OpenMP restatement of the reference arithmetic "
+                                                  "(oracle/c), not the JAX path"}
+            except Exception as ex:
+                line["cpu_baseline"] = {"error": str(ex)[:200]}
+    line["bench_wall_s"] = time.time() - _T0
     if rank == 0:
         emit(line)
     if world > 1:
-        part.close_peer_halo()   # raises if a halo wait ever timed out
         dist.barrier()
         dist.destroy_process_group()
 
@@ -480,6 +830,7 @@ def e2e_host(torch, lib, _lib, loss, mesh, K_host, u_host, ne, nn, ndof, args):
         dt = (time.perf_counter() - t0) / steps
         h2d = (nn + ndof) * 8
         d2h = (ne * 576 + ndof) * 8
+        del ke_host
         # the PCIe ceiling of this box: a plain pinned device->host copy of 1 GiB
         probe_d = torch.empty(1 << 27, dtype=torch.float64, device="cuda")
         probe_h = torch.empty(1 << 27, dtype=torch.float64, pin_memory=True)
@@ -490,12 +841,39 @@ def e2e_host(torch, lib, _lib, loss, mesh, K_host, u_host, ne, nn, ndof, args):
         torch.cuda.synchronize()
         pcie_gbs = (1 << 30) / (time.perf_counter() - t1) / 1e9
         del probe_d, probe_h
-        return {"value": ne / dt, "unit": "elements/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": dt * 1e3, "steps": steps, "d2h_gbs_achieved": d2h / dt / 1e9,
-                "pcie_d2h_gbs_measured": pcie_gbs,
-                "api": "fol_plan_assemble_host (C ABI, pinned host buffers, returns after D2H)",
-                "note": "PCIe-bound: the reference contract hands the full duplicate-keeping BCOO (4608 B/element) "
-                        "to the host solver"}
+        out = {"value": ne / dt, "unit": "elements/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": dt * 1e3, "steps": steps, "d2h_gbs_achieved": d2h / dt / 1e9,
+               "pcie_d2h_gbs_measured": pcie_gbs,
+               "api": "fol_plan_assemble_host (C ABI, pinned host buffers, returns after D2H)",
+               "note": "PCIe-bound: the reference contract hands the full duplicate-keeping BCOO (4608 B/element) "
+                       "to the host solver"}
+        # ---- the hand-off the reference's solvers consume after their host-side sum (fe_solver.py:71-72): CSR values
+        try:
+            cp = loss._csr_plan()
+            host = {k: np.ascontiguousarray(cp[k].cpu().numpy(), dtype=np.int32)
+                    for k in ("pair_ptr", "contrib", "out_base", "row_stride")}
+            _lib.check(lib.fol_plan_set_csr(plan, cp["npairs"], cp["nnz"], host["pair_ptr"].ctypes.data,
+                                            host["contrib"].ctypes.data, host["out_base"].ctypes.data,
+                                            host["row_stride"].ctypes.data))
+            vals_host = torch.empty(cp["nnz"], dtype=torch.float64, pin_memory=True)
+
+            def call_csr():
+                _lib.check(lib.fol_plan_assemble_host_csr(plan, 0, Kp.data_ptr(), up.data_ptr(), vals_host.data_ptr(),
+                                                          R_host.data_ptr()))
+            call_csr()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                call_csr()
+            dtc = (time.perf_counter() - t0) / steps
+            out["csr"] = {"value": ne / dtc, "unit": "elements/s", "ms_per_step": dtc * 1e3,
+                          "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (cp["nnz"] + ndof) * 8,
+                          "d2h_gbs_achieved": (cp["nnz"] + ndof) * 8 / dtc / 1e9,
+                          "api": "fol_plan_assemble_host_csr (duplicates summed on the device, nnz values + residual to "
+                                 "the host, pipelined in chunks of whole node rows)"}
+            del vals_host
+        except Exception as ex:
+            out["csr"] = {"error": str(ex)[:200]}
+        return out
     finally:
         lib.fol_plan_destroy(plan)
 
@@ -518,7 +896,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=128, help="hex elements per side per GPU")
-    ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu baseline / secondary metric")
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu baseline / secondary metrics")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

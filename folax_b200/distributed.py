@@ -122,7 +122,8 @@ FUSED_HALO = True          # False: force the layered path (A/B in tests and scr
 GRID_MARGIN_CTAS = 0   # measured on 2/4/8 B200: a margin does not pay; NCCL's kernels fit next to the persistent CTAs
 
 
-def assemble_overlapped(loss, part, controls, dofs, ke_out, comm_stream, group=None, state_in=None, state_out=None):
+def assemble_overlapped(loss, part, controls, dofs, ke_out, comm_stream, group=None, state_in=None, state_out=None,
+                        kernel_events=None):
     """Residual + Jacobian of one slab with the halo-DOF exchange hidden behind the element stage.
 
     The element layers touching the slab interfaces are contiguous element ranges (the generator
@@ -136,6 +137,8 @@ def assemble_overlapped(loss, part, controls, dofs, ke_out, comm_stream, group=N
     History-dependent elements (J2 elastoplasticity, BASELINE.json configs[4]): `state_in` / `state_out` are this
     slab's Gauss-point history (ne, g, 7|4); the state is element-local, so like the Jacobian blocks it needs no
     exchange -- every element-range launch reads and writes its own slice.
+    kernel_events: optional (start, end) torch events recorded around the element-stage launch of the fused path
+    (bench.py times the dominant kernel inside the measured step with them).
     Returns (ke_out, residual)."""
     from . import _lib
     lib = _lib.load()
@@ -186,11 +189,15 @@ def assemble_overlapped(loss, part, controls, dofs, ke_out, comm_stream, group=N
                 and loss.physics in ("mechanical", "j2plasticity")):
             # fused path: ONE element-stage launch that visits the interface layers first and pushes the two planes
             # over NVLink from inside (csrc/assemble_hex_common.cuh), ONE launch for the interior gather + halo add
+            if kernel_events is not None:
+                kernel_events[0].record()
             _lib.check(lib.fol_assemble_elements_halo(
                 s, dt, phys, elem, loss.num_gp, ne, nn, _lib.ptr(loss._xyz), _lib.ptr(loss._conn), _lib.ptr(K),
                 _lib.ptr(u), _lib.ptr(loss._dir_flag), loss._params, _lib.ptr(ke_out), _lib.ptr(re),
                 _lib.ptr(state_in) if st_bytes else None, _lib.ptr(state_out) if st_bytes else None,
                 h, step, layer, plane, _lib.ptr(loss._adj_ptr), _lib.ptr(loss._adj), _lib.ptr(R)))
+            if kernel_events is not None:
+                kernel_events[1].record()
             _lib.check(lib.fol_residual_gather_halo(s, h, step, nn, plane, _lib.ptr(loss._adj_ptr), _lib.ptr(loss._adj),
                                                     _lib.ptr(re), _lib.ptr(R)))
             return ke_out, R
@@ -272,6 +279,40 @@ def allreduce_gradients(parameters, group=None, bucket_bytes=64 << 20):
         if size >= bucket_bytes:
             flush()
     flush()
+
+
+class GradientReducer:
+    """All-reduce of the network gradients OVERLAPPED with the backward pass: a post-accumulate hook on every
+    parameter starts the NCCL all-reduce of its gradient on a side stream the moment autograd has produced it, so
+    the reduction of the (large) output-layer gradient of a FOL network runs behind the rest of the backward pass
+    instead of after it.  `wait()` joins the side stream before the optimizer step.  Same sums as
+    `allreduce_gradients` (one all-reduce per parameter, NCCL's fixed ring / tree order)."""
+
+    def __init__(self, parameters, group=None):
+        self.group = group
+        self.active = dist.is_initialized() and dist.get_world_size(group) > 1
+        self.stream = torch.cuda.Stream() if self.active else None
+        self.handles = []
+        if self.active:
+            for p in parameters:
+                if p.requires_grad:
+                    self.handles.append(p.register_post_accumulate_grad_hook(self._hook))
+
+    def _hook(self, p):
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group)
+
+    def wait(self):
+        if self.active:
+            torch.cuda.current_stream().wait_stream(self.stream)
+
+    def close(self):
+        for h in self.handles:
+            h.remove()
+        self.handles = []
 
 
 def allreduce_loss_statistics(mean, stats, group=None):
