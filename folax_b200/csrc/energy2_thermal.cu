@@ -35,8 +35,15 @@ int dispatch_thermal2(cudaStream_t s, const EnergyArgs<T>& args, int ncap, int* 
 }
 
 template <class T>
+int energy_qt_thermal(cudaStream_t, const EnergyArgs<T>&, int, int*);
+
+template <class T>
 int energy2_thermal(cudaStream_t s, int element, int num_gp, const EnergyArgs<T>& args, int ncap, int* parts) {
   if (energy2_env_int("FOL_ENERGY_V1", 0)) return 1;
+  if (element == QUAD && num_gp == 2) {   // north-star configuration: sample-vectorised kernel (energy_qt.cuh)
+    const int rc = energy_qt_thermal<T>(s, args, ncap, parts);
+    if (rc != 1) return rc;
+  }
 #define FOL_CASE(E, O) \
   if (element == E && num_gp == O) return dispatch_thermal2<T, E, O>(s, args, ncap, parts);
   FOL_CASE(QUAD, 1) FOL_CASE(QUAD, 2) FOL_CASE(TRI, 1) FOL_CASE(TRI, 2) FOL_CASE(TET, 1) FOL_CASE(HEX, 1)

@@ -1,0 +1,244 @@
+// Sample-vectorised form of the pipelined batched loss + VJP kernel for the north-star FOL configuration
+// (BASELINE.json configs[2]): ThermalLoss on Quad4 with the 2x2 rule (thermal.py:28-49, fe_loss.py:250-262 and the
+// JAX-AD gradient of it).
+//
+// Same tile plan, same fixed summation order, same results as energy_tile2_kernel (energy2.cuh); what changes is the
+// shared-memory layout: the S = 16 / sizeof(T) samples of a pass (2 doubles or 4 floats) sit NEXT to each other, so
+//   * phase A (thread = tile element) reads the 4 + 4 nodal values of ALL its samples with 8 LDS.128 and stores the
+//     8 element-vector rows with 8 STS.128 -- 1/S of the shared-memory instructions and address arithmetic of the
+//     sample-major layout -- and evaluates the S samples as independent instruction streams (ILP S on the FP chains);
+//   * phase B (thread = tile node) takes one LDS.128 per adjacency entry and row for all samples.
+// energy_tile2_kernel measured 342 issued instructions per element-sample with 161 FP64 among them, FP64 pipe 51 %
+// busy, stalls on shared-memory latency and fixed-latency dependencies (profiles/r1/energy_tile2_ncu_summary.txt);
+// the float32 variant was issue-bound at 0.16 of HBM.  Double-buffered element vectors, ONE barrier per pass, the
+// two phases of neighbouring warps in opposite order, cp.async staging with the Dirichlet overwrite fused -- as there.
+#pragma once
+#include "energy2.cuh"
+
+namespace fol {
+
+template <class T> struct SampleVec;
+template <> struct SampleVec<double> { using type = double2; };
+template <> struct SampleVec<float> { using type = float4; };
+
+__device__ __forceinline__ void unpack(const double2& v, double (&o)[2]) { o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ void unpack(const float4& v, float (&o)[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ double2 pack(const double (&o)[2]) { return make_double2(o[0], o[1]); }
+__device__ __forceinline__ float4 pack(const float (&o)[4]) { return make_float4(o[0], o[1], o[2], o[3]); }
+
+template <class T, int NL, int BLOCK, int MINB, int LCAP>
+__global__ void __launch_bounds__(BLOCK, MINB) energy_qt_kernel(const EnergyArgs<T> args) {
+  constexpr int S = 16 / (int)sizeof(T);    // samples per pass = one 16-byte vector
+  constexpr int A = 4, KW = 8, NW = BLOCK / 32, GW = 4 * 9;
+  constexpr int MAXADJ = 8;                 // adjacency entries held in registers; longer lists continue from global
+  constexpr int SVB = KW * BLOCK;           // one element-vector buffer (in sample vectors)
+  using V = typename SampleVec<T>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  V* sv = reinterpret_cast<V*>(smem_raw);   // [2][KW][BLOCK]: rows re_0..3, dK_0..3 of the tile's elements
+  V* stage = sv + 2 * SVB;                  // [2][2][LCAP]:   rows T, K of the tile's local nodes
+  const int t = blockIdx.x, tid = threadIdx.x;
+  const int e_beg = __ldg(args.tile_elem_ptr + t), n_el = __ldg(args.tile_elem_ptr + t + 1) - e_beg;
+  const int n_beg = __ldg(args.tile_node_ptr + t), n_nd = __ldg(args.tile_node_ptr + t + 1) - n_beg;
+  const int l_beg = __ldg(args.tile_lnode_ptr + t), n_ln = __ldg(args.tile_lnode_ptr + t + 1) - l_beg;
+  const long long nn = args.nn;
+  const int npart = args.ntiles * NW;
+
+  // ---- node role (phase B): the tile's nodes dealt to the warps in equal contiguous chunks
+  const int per_warp = (n_nd + NW - 1) / NW;
+  const int lnode = (tid >> 5) * per_warp + (tid & 31);
+  const bool has_node = (tid & 31) < per_warp && lnode < n_nd;
+  const int n = has_node ? __ldg(args.tile_nodes + n_beg + lnode) : 0;
+  const int a_beg = has_node ? __ldg(args.adj_ptr + n) : 0, a_end = has_node ? __ldg(args.adj_ptr + n + 1) : 0;
+  const int cnt = a_end - a_beg;
+  int off[MAXADJ];                          // re row of the entry; its dK row is 4 * BLOCK further
+#pragma unroll
+  for (int i = 0; i < MAXADJ; ++i) {
+    off[i] = 0;
+    if (i < cnt) {
+      const int ja = __ldg(args.adj_local + a_beg + i);
+      const int jl = ja / A, a = ja - jl * A;
+      off[i] = jl + a * BLOCK;
+    }
+  }
+
+  // ---- element role (phase A): element tid of the tile; geometry factors and local node ids in registers
+  const bool has_el = tid < n_el;
+  T greg[GW];
+  int my_ln[A];
+  if (has_el) {
+    const long long my_el = __ldg(args.tile_elems + e_beg + tid);
+#pragma unroll
+    for (int b = 0; b < A; ++b) my_ln[b] = __ldg(args.tile_conn + (long long)(e_beg + tid) * A + b);
+#pragma unroll
+    for (int k = 0; k < GW; ++k) greg[k] = __ldg(args.geom + (long long)k * args.ne + my_el);
+  } else {
+#pragma unroll
+    for (int b = 0; b < A; ++b) my_ln[b] = 0;
+#pragma unroll
+    for (int k = 0; k < GW; ++k) greg[k] = (T)0;
+  }
+
+  // ---- staging role: this thread copies the rows of local nodes tid and tid + BLOCK (LCAP <= 2 BLOCK)
+  static_assert(LCAP <= 2 * BLOCK, "two staged local nodes per thread");
+  int gnode[2];
+  T dval[2];                                // Dirichlet value (NaN = free) of the rows this thread stages
+  bool any_dir = false;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    gnode[j] = (tid + j * BLOCK < n_ln) ? __ldg(args.tile_lnodes + l_beg + tid + j * BLOCK) : -1;
+    dval[j] = (args.dir_values && gnode[j] >= 0) ? __ldg(args.dir_values + gnode[j]) : (T)NAN;
+    any_dir |= (dval[j] == dval[j]);
+  }
+  auto stage_pass = [&](int buf, long long b0) {
+    T* dst0 = reinterpret_cast<T*>(stage + (size_t)buf * 2 * LCAP);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (gnode[j] >= 0) {
+        T* du = dst0 + (size_t)(tid + j * BLOCK) * S;
+        T* dk = du + (size_t)LCAP * S;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const long long bb = (b0 + s < args.nb) ? b0 + s : args.nb - 1;
+          cp_async_elem<T>(du + s, args.u + bb * nn + gnode[j]);
+          cp_async_elem<T>(dk + s, args.ctrl + bb * nn + gnode[j]);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  // Dirichlet overwrite (fe_loss.py:91-92, 255) of the rows this thread staged, once its own copies have landed
+  auto patch_pass = [&](int buf) {
+    if (!any_dir) return;
+    T* dst0 = reinterpret_cast<T*>(stage + (size_t)buf * 2 * LCAP);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (dval[j] == dval[j]) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) dst0[(size_t)(tid + j * BLOCK) * S + s] = dval[j];
+      }
+    }
+  };
+
+  bool cut = false;                         // the node's cotangent is cut (Dirichlet)
+  if (has_node && args.dir_flag) cut = args.dir_flag[n] != 0;
+  T* const gu_node = args.grad_u + n;
+  T* const gk_node = args.grad_k ? args.grad_k + n : nullptr;
+  T ukeep[S];                               // this thread's node values of the pass whose phase B is pending
+#pragma unroll
+  for (int s = 0; s < S; ++s) ukeep[s] = (T)0;
+
+  // phase B of one pass: fixed-order adjacency sums from the element vectors in `svb`
+  auto phase_b = [&](const V* svb, long long b0, int ns) {
+    T en[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) en[s] = (T)0;
+    if (has_node) {
+      T R[S], dk[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) R[s] = dk[s] = (T)0;
+#pragma unroll
+      for (int i = 0; i < MAXADJ; ++i) {
+        if (i >= cnt) break;
+        T r[S], k[S];
+        unpack(svb[off[i]], r);
+        unpack(svb[off[i] + 4 * BLOCK], k);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          R[s] += r[s];
+          dk[s] += k[s];
+        }
+      }
+      for (int it = a_beg + MAXADJ; it < a_end; ++it) {
+        const int ja = __ldg(args.adj_local + it);
+        const int jl = ja / A, a = ja - jl * A;
+        T r[S], k[S];
+        unpack(svb[jl + a * BLOCK], r);
+        unpack(svb[jl + (4 + a) * BLOCK], k);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          R[s] += r[s];
+          dk[s] += k[s];
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (s < ns) {
+          en[s] = ukeep[s] * R[s];          // E_b = T_b . R_b (thermal.py:45-49)
+          gu_node[(b0 + s) * nn] = cut ? (T)0 : args.out_scale * R[s];
+          if (gk_node) gk_node[(b0 + s) * nn] = args.out_scale * dk[s];
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      T v = en[s];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((tid & 31) == 0 && s < ns) args.partial[(b0 + s) * npart + t * NW + (tid >> 5)] = v;
+    }
+  };
+
+  // phase A of one pass: this thread's element for the S samples of the pass (independent instruction streams)
+  auto phase_a = [&](const V* st, V* out) {
+    if (!has_el) return;
+    T Te[S][A], Ke[S][A], re[S][A], dK[S][A];
+#pragma unroll
+    for (int b = 0; b < A; ++b) {
+      T tv[S], kv[S];
+      unpack(st[my_ln[b]], tv);
+      unpack(st[LCAP + my_ln[b]], kv);
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        Te[s][b] = tv[s];
+        Ke[s][b] = kv[s];
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) thermal_vectors<T, QUAD, 2, NL>(greg, Te[s], Ke[s], args.p.v[5], args.p.v[6], re[s], dK[s]);
+#pragma unroll
+    for (int b = 0; b < A; ++b) {
+      T rv[S], kv[S];
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        rv[s] = re[s][b];
+        kv[s] = dK[s][b];
+      }
+      out[b * BLOCK] = pack(rv);
+      out[(4 + b) * BLOCK] = pack(kv);
+    }
+  };
+
+  long long b0 = (long long)blockIdx.y * S;
+  const long long bstep = (long long)gridDim.y * S;
+  if (b0 >= args.nb) return;
+  stage_pass(0, b0);
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  patch_pass(0);
+  __syncthreads();
+  // warps sharing a scheduler take the two phases in opposite order (one warp's FP stream covers the other's
+  // shared-memory latencies)
+  const int wid = tid >> 5;
+  const bool a_first = (((wid >> 2) ^ wid ^ (int)blockIdx.x ^ (int)blockIdx.y) & 1) != 0;
+  int buf = 0;
+  long long bprev = -1;
+  for (; b0 < args.nb; b0 += bstep, buf ^= 1) {
+    if (b0 + bstep < args.nb) stage_pass(buf ^ 1, b0 + bstep);
+    const V* st0 = stage + (size_t)buf * 2 * LCAP;
+    const int nsprev = (args.nb - bprev < S) ? (int)(args.nb - bprev) : S;
+    if (a_first) {
+      phase_a(st0, sv + buf * SVB + tid);
+      if (bprev >= 0) phase_b(sv + (buf ^ 1) * SVB, bprev, nsprev);
+    } else {
+      if (bprev >= 0) phase_b(sv + (buf ^ 1) * SVB, bprev, nsprev);
+      phase_a(st0, sv + buf * SVB + tid);
+    }
+    if (has_node) unpack(st0[lnode], ukeep);
+    bprev = b0;
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    patch_pass(buf ^ 1);
+    __syncthreads();   // sv[buf] complete and the next pass's rows visible; sv[buf^1] / stage[buf] free again
+  }
+  phase_b(sv + (buf ^ 1) * SVB, bprev, (args.nb - bprev < S) ? (int)(args.nb - bprev) : S);
+}
+
+}  // namespace fol
