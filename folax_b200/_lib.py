@@ -17,6 +17,7 @@ ELEMENTS = {"hexahedron": 0, "quad": 1, "tetra": 2, "triangle": 3}
 PHYSICS = {"mechanical": 0, "thermal": 1, "neohooke": 2, "j2plasticity": 3, "stvenant": 4,
            "transient_thermal": 5, "allen_cahn": 6, "neohooke_ad": 7, "stvenant_ad": 8}
 NUM_PARAMS = 12
+MESH_AFFINE = 1     # FOL_MESH_AFFINE
 
 _vp, _i32p, _u8p, _i64, _int, _dbl = C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double
 
@@ -45,6 +46,9 @@ SIGNATURES = {
     "fol_energy_and_grads": (_int, [_vp, _int, _int, _int, _int, _i64, _i64, _i64, _vp, _i32p, _i32p, _i32p,
                                     _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i64, _i64, _i64, _i64,
                                     _vp, _vp, _vp, _u8p, _dbl, C.POINTER(_dbl), _vp, _vp, _vp, _vp]),
+    "fol_energy_and_grads_flags": (_int, [_vp, _int, _int, _int, _int, _i64, _i64, _i64, _vp, _i32p, _i32p, _i32p,
+                                    _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, _i64, _i64, _i64, _i64,
+                                    _vp, _vp, _vp, _u8p, _dbl, C.POINTER(_dbl), _vp, _vp, _vp, _vp, _i64]),
     "fol_loss_reduce": (_int, [_vp, _int, _i64, _dbl, _vp, _vp, _vp]),
     "fol_scale_grads": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _dbl, _vp, _int, _u8p, _vp, _vp]),
     "fol_apply_dirichlet": (_int, [_vp, _int, _i64, _i64, _i32p, _i64, _vp, _int, _dbl, _vp]),

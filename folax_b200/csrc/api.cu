@@ -209,7 +209,7 @@ int fol_geometry_cache(fol_stream_t s, int dtype, int element, int num_gp, int64
 
 int64_t fol_energy_work_size(int64_t ntiles, int64_t nb) { return ntiles * nb * 10 + 16; }  // <= 10 warps per tile
 
-int fol_energy_and_grads(fol_stream_t s, int dtype, int physics, int element, int num_gp, int64_t ne, int64_t nn,
+int fol_energy_and_grads_flags(fol_stream_t s, int dtype, int physics, int element, int num_gp, int64_t ne, int64_t nn,
                          int64_t nb, const void* geom, const int32_t* conn, const int32_t* adj_ptr,
                          const int32_t* adj_local, const int32_t* tile_node_ptr, const int32_t* tile_nodes,
                          const int32_t* tile_elem_ptr, const int32_t* tile_elems, const int32_t* tile_conn,
@@ -217,7 +217,7 @@ int fol_energy_and_grads(fol_stream_t s, int dtype, int physics, int element, in
                          int64_t lcap, int64_t ncap, const void* ctrl, const void* u, const void* dir_values,
                          const uint8_t* dir_flag, double out_scale, const double* params_host, void* grad_u,
                          void* grad_k,
-                         void* energy, void* work) {
+                         void* energy, void* work, int64_t mesh_flags) {
   FOL_REQUIRE(valid_element(element), "fol_energy_and_grads: unknown element");
   FOL_REQUIRE(geom && conn && adj_ptr && adj_local && tile_node_ptr && tile_nodes && tile_elem_ptr && tile_elems &&
                   tile_conn && tile_lnode_ptr && tile_lnodes &&
@@ -229,7 +229,7 @@ int fol_energy_and_grads(fol_stream_t s, int dtype, int physics, int element, in
                          tile_elems, tile_conn, tile_lnode_ptr, tile_lnodes, (const double*)ctrl, (const double*)u,
                          (double*)grad_u, (double*)grad_k, (double*)work, (const double*)dir_values, dir_flag, out_scale,
                          ne, nn, nb, (int)ntiles, (int)ecap, (int)lcap,
-                         make_params<double>(params_host)};
+                         make_params<double>(params_host), (long long)mesh_flags};
     return energy_and_grads<double>((cudaStream_t)s, physics, element, num_gp, a, (int)ncap, (double*)energy);
   }
   FOL_REQUIRE(dtype == FOL_F32, "fol_energy_and_grads: bad dtype");
@@ -237,8 +237,22 @@ int fol_energy_and_grads(fol_stream_t s, int dtype, int physics, int element, in
                       tile_elems, tile_conn, tile_lnode_ptr, tile_lnodes, (const float*)ctrl, (const float*)u,
                       (float*)grad_u, (float*)grad_k, (float*)work, (const float*)dir_values, dir_flag, (float)out_scale,
                       ne, nn, nb, (int)ntiles, (int)ecap, (int)lcap,
-                      make_params<float>(params_host)};
+                      make_params<float>(params_host), (long long)mesh_flags};
   return energy_and_grads<float>((cudaStream_t)s, physics, element, num_gp, a, (int)ncap, (float*)energy);
+}
+
+int fol_energy_and_grads(fol_stream_t s, int dtype, int physics, int element, int num_gp, int64_t ne, int64_t nn,
+                         int64_t nb, const void* geom, const int32_t* conn, const int32_t* adj_ptr,
+                         const int32_t* adj_local, const int32_t* tile_node_ptr, const int32_t* tile_nodes,
+                         const int32_t* tile_elem_ptr, const int32_t* tile_elems, const int32_t* tile_conn,
+                         const int32_t* tile_lnode_ptr, const int32_t* tile_lnodes, int64_t ntiles, int64_t ecap,
+                         int64_t lcap, int64_t ncap, const void* ctrl, const void* u, const void* dir_values,
+                         const uint8_t* dir_flag, double out_scale, const double* params_host, void* grad_u,
+                         void* grad_k, void* energy, void* work) {
+  return fol_energy_and_grads_flags(s, dtype, physics, element, num_gp, ne, nn, nb, geom, conn, adj_ptr, adj_local,
+                                    tile_node_ptr, tile_nodes, tile_elem_ptr, tile_elems, tile_conn, tile_lnode_ptr,
+                                    tile_lnodes, ntiles, ecap, lcap, ncap, ctrl, u, dir_values, dir_flag, out_scale,
+                                    params_host, grad_u, grad_k, energy, work, 0);
 }
 
 int fol_loss_reduce(fol_stream_t s, int dtype, int64_t nb, double exponent, const void* energy, void* out4,

@@ -47,6 +47,7 @@ struct EnergyArgs {
   long long ne, nn, nb;
   int ntiles, ecap, lcap;     // tiles, max elements per tile, max local nodes per tile (shared-memory rows)
   Params<T> p;
+  long long mesh_flags = 0;   // FOL_MESH_* bits of include/folax_b200.h (facts about the mesh the host plan established)
 };
 
 // integer powers are evaluated by repeated multiplication, like lax.integer_pow does for the

@@ -6,13 +6,13 @@
 namespace fol {
 
 // returns 0 launched, 1 not applicable (the caller falls back to energy_tile2_kernel), <0 error
-template <class T, int NL, int BLOCK, int MINB>
+template <class T, int NL, int BLOCK, int MINB, bool AFFINE>
 int launch_energy_qt(cudaStream_t s, const EnergyArgs<T>& args, int ncap, int* parts) {
   constexpr int LCAP = BLOCK + 64, S = 16 / (int)sizeof(T);
   constexpr size_t smem = 16 * ((size_t)2 * 8 * BLOCK + (size_t)2 * 2 * LCAP);
   if (args.lcap > LCAP || args.ecap > BLOCK || ncap > BLOCK) return 1;
   *parts = BLOCK / 32;
-  auto kern = energy_qt_kernel<T, NL, BLOCK, MINB, LCAP>;
+  auto kern = energy_qt_kernel<T, NL, BLOCK, MINB, LCAP, AFFINE>;
   static PerDeviceOnce configured;
   if (configured.need()) {
     FOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -39,14 +39,19 @@ template <class T>
 int energy_qt_thermal(cudaStream_t s, const EnergyArgs<T>& args, int ncap, int* parts) {
   static const int enabled = energy2_env_int("FOL_ENERGY_QT", 1);
   if (!enabled) return 1;
-  static const int minb = energy2_env_int("FOL_ENERGY_QT_MINB", 2);
+  // affine meshes (all elements parallelograms; the host plan checked it) keep 5 geometry values per element in
+  // registers instead of 36: three CTAs per SM instead of two
+  const bool affine = (args.mesh_flags & FOL_MESH_AFFINE) != 0 && energy2_env_int("FOL_ENERGY_AFFINE", 1) != 0;
+  static const int minb_env = energy2_env_int("FOL_ENERGY_QT_MINB", 0);
+  const int minb = minb_env ? minb_env : (affine ? 3 : 2);
   const T beta = args.p.v[5], c = args.p.v[6];
   const int ci = (int)c;
   const int nl = (beta == (T)0) ? 0 : (((T)ci == c && ci >= 1 && ci <= 4) ? ci : -1);
 #define FOL_QT(NLV)                                                                         \
   if (nl == NLV) {                                                                          \
-    if (minb >= 3) return launch_energy_qt<T, NLV, 192, 3>(s, args, ncap, parts);           \
-    return launch_energy_qt<T, NLV, 192, 2>(s, args, ncap, parts);                          \
+    if (affine && minb >= 3) return launch_energy_qt<T, NLV, 192, 3, true>(s, args, ncap, parts);  \
+    if (affine) return launch_energy_qt<T, NLV, 192, 2, true>(s, args, ncap, parts);               \
+    return launch_energy_qt<T, NLV, 192, 2, false>(s, args, ncap, parts);                          \
   }
   FOL_QT(0) FOL_QT(1) FOL_QT(2) FOL_QT(3) FOL_QT(4) FOL_QT(-1)
 #undef FOL_QT

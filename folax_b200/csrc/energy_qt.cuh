@@ -26,10 +26,47 @@ __device__ __forceinline__ void unpack(const float4& v, float (&o)[4]) { o[0] = 
 __device__ __forceinline__ double2 pack(const double (&o)[2]) { return make_double2(o[0], o[1]); }
 __device__ __forceinline__ float4 pack(const float (&o)[4]) { return make_float4(o[0], o[1], o[2], o[3]); }
 
-template <class T, int NL, int BLOCK, int MINB, int LCAP>
+// Thermal element vectors of ONE sample on an AFFINE Quad4 (a parallelogram: J is the same at every Gauss point), from
+// J^-1 (row-major, jinv[j*2+k] = d xi_j / d x_k) and w detJ instead of the 36 cached gradient values:
+// grad N_b(g) = dN_b(xi_g) . J^-1 with dN_b(xi_g) compile-time constants, so
+//   grad T_g = J^-T (sum_b dN_b(g) T_b),   re_b += dN_b(g) . (cf_g J^-1 grad T_g)
+// Same sums as thermal_vectors up to rounding (the general kernel reads gradients that were rounded once more).
+template <class T, int NL>
+__device__ __forceinline__ void thermal_vectors_affine(const T (&jinv)[4], T wd, const T (&Te)[4], const T (&Ke)[4],
+                                                       T beta, T cexp, T (&re)[4], T (&dK)[4]) {
+#pragma unroll
+  for (int b = 0; b < 4; ++b) re[b] = dK[b] = (T)0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    double xi[3], w;
+    gauss_point<QUAD, 2>(g, xi, w);
+    T N[4], dN[4][2];
+    shape_functions<QUAD, T>(xi, N, dN);
+    T eg = (T)0, tg = (T)0, t0 = (T)0, t1 = (T)0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      eg += N[b] * Ke[b];
+      tg += N[b] * Te[b];
+      t0 += dN[b][0] * Te[b];
+      t1 += dN[b][1] * Te[b];
+    }
+    const T gx = t0 * jinv[0] + t1 * jinv[2], gy = t0 * jinv[1] + t1 * jinv[3];   // grad T = J^-T (dN^T T)
+    const T nl = conductivity_factor<T, NL>(tg, beta, cexp);
+    const T g2 = gx * gx + gy * gy;
+    const T cf = wd * eg * nl, ck = wd * nl * g2;
+    const T w0 = cf * (jinv[0] * gx + jinv[1] * gy), w1 = cf * (jinv[2] * gx + jinv[3] * gy);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      re[b] += dN[b][0] * w0 + dN[b][1] * w1;
+      dK[b] += ck * N[b];
+    }
+  }
+}
+
+template <class T, int NL, int BLOCK, int MINB, int LCAP, bool AFFINE>
 __global__ void __launch_bounds__(BLOCK, MINB) energy_qt_kernel(const EnergyArgs<T> args) {
   constexpr int S = 16 / (int)sizeof(T);    // samples per pass = one 16-byte vector
-  constexpr int A = 4, KW = 8, NW = BLOCK / 32, GW = 4 * 9;
+  constexpr int A = 4, KW = 8, NW = BLOCK / 32, GW = AFFINE ? 5 : 4 * 9;
   constexpr int MAXADJ = 8;                 // adjacency entries held in registers; longer lists continue from global
   constexpr int SVB = KW * BLOCK;           // one element-vector buffer (in sample vectors)
   using V = typename SampleVec<T>::type;
@@ -69,8 +106,25 @@ __global__ void __launch_bounds__(BLOCK, MINB) energy_qt_kernel(const EnergyArgs
     const long long my_el = __ldg(args.tile_elems + e_beg + tid);
 #pragma unroll
     for (int b = 0; b < A; ++b) my_ln[b] = __ldg(args.tile_conn + (long long)(e_beg + tid) * A + b);
+    if constexpr (AFFINE) {
+      // J^-1 from the cached gradients of nodes 0 and 1 at Gauss point 0: [dN_0; dN_1] J^-1 = [grad N_0; grad N_1]
+      double xi[3], w;
+      gauss_point<QUAD, 2>(0, xi, w);
+      T N[4], dN[4][2];
+      shape_functions<QUAD, T>(xi, N, dN);
+      const T idet = (T)1 / (dN[0][0] * dN[1][1] - dN[0][1] * dN[1][0]);
+      T gn[4];
 #pragma unroll
-    for (int k = 0; k < GW; ++k) greg[k] = __ldg(args.geom + (long long)k * args.ne + my_el);
+      for (int k = 0; k < 4; ++k) gn[k] = __ldg(args.geom + (long long)k * args.ne + my_el);   // gN_0x, gN_0y, gN_1x, gN_1y
+      greg[0] = idet * (dN[1][1] * gn[0] - dN[0][1] * gn[2]);
+      greg[1] = idet * (dN[1][1] * gn[1] - dN[0][1] * gn[3]);
+      greg[2] = idet * (dN[0][0] * gn[2] - dN[1][0] * gn[0]);
+      greg[3] = idet * (dN[0][0] * gn[3] - dN[1][0] * gn[1]);
+      greg[4] = __ldg(args.geom + (long long)8 * args.ne + my_el);                               // w detJ
+    } else {
+#pragma unroll
+      for (int k = 0; k < GW; ++k) greg[k] = __ldg(args.geom + (long long)k * args.ne + my_el);
+    }
   } else {
 #pragma unroll
     for (int b = 0; b < A; ++b) my_ln[b] = 0;
@@ -194,7 +248,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) energy_qt_kernel(const EnergyArgs
       }
     }
 #pragma unroll
-    for (int s = 0; s < S; ++s) thermal_vectors<T, QUAD, 2, NL>(greg, Te[s], Ke[s], args.p.v[5], args.p.v[6], re[s], dK[s]);
+    for (int s = 0; s < S; ++s) {
+      if constexpr (AFFINE) {
+        const T jinv[4] = {greg[0], greg[1], greg[2], greg[3]};
+        thermal_vectors_affine<T, NL>(jinv, greg[4], Te[s], Ke[s], args.p.v[5], args.p.v[6], re[s], dK[s]);
+      } else {
+        thermal_vectors<T, QUAD, 2, NL>(greg, Te[s], Ke[s], args.p.v[5], args.p.v[6], re[s], dK[s]);
+      }
+    }
 #pragma unroll
     for (int b = 0; b < A; ++b) {
       T rv[S], kv[S];

@@ -62,6 +62,30 @@ def build(coords, conn, tile_nodes=TILE_NODES, max_elems=MAX_ELEMS, method="rcb"
     unbounded one (3-D / high-valence meshes); the generic kernel then loops over the element list, which
     only has to fit its shared-memory rows (generic_max_elems)."""
     ne = len(conn)
+    affine = is_affine(coords, conn)
+
+    def tag(plan):
+        plan["affine"] = affine
+        return plan
+    return tag(_choose(coords, conn, tile_nodes, max_elems, method, generic_max_elems, ne))
+
+
+def is_affine(coords, conn):
+    """True when every Quad4 is a parallelogram (x0 - x1 + x2 - x3 = 0 to rounding): the isoparametric map is affine
+    and the Jacobian the same at every Gauss point (FOL_MESH_AFFINE of include/folax_b200.h).  Other element types:
+    False (Tri3 / Tet4 are always affine but their kernels already keep one gradient set per element)."""
+    conn = np.asarray(conn)
+    if conn.ndim != 2 or conn.shape[1] != 4 or len(conn) == 0 or np.asarray(coords).shape[1] < 2:
+        return False
+    X = np.asarray(coords, dtype=np.float64)[:, :2][conn]
+    if np.asarray(coords).shape[1] > 2 and np.ptp(np.asarray(coords)[:, 2]) != 0.0:
+        return False                                     # a 4-node element of a 3-D mesh is a tetrahedron, not a quad
+    skew = np.abs(X[:, 0] - X[:, 1] + X[:, 2] - X[:, 3]).max(axis=1)
+    size = np.abs(X[:, 2] - X[:, 0]).max(axis=1)
+    return bool((skew <= 1e-13 * size).all())
+
+
+def _choose(coords, conn, tile_nodes, max_elems, method, generic_max_elems, ne):
     target, generic = tile_nodes, None
     for _ in range(12):
         generic = _build(coords, conn, target, method)

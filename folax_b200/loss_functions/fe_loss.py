@@ -579,7 +579,7 @@ class FiniteElementLoss(Loss):
         grad_k = torch.empty_like(batch_params) if self._has_control_gradient else None
         energy = torch.empty(nb, dtype=self.dtype, device=self.device)
         work = self._energy_work(nb)
-        _lib.check(lib.fol_energy_and_grads(_lib.stream_ptr(), self._dt, _lib.PHYSICS[self._batch_physics()],
+        _lib.check(lib.fol_energy_and_grads_flags(_lib.stream_ptr(), self._dt, _lib.PHYSICS[self._batch_physics()],
                                             self.fe_element.code, self.num_gp, self._ne, self._nn, nb,
                                             _lib.ptr(geom), _lib.ptr(self._conn), _lib.ptr(ep["adj_ptr"]),
                                             _lib.ptr(ep["adj_local"]), _lib.ptr(ep["tile_node_ptr"]),
@@ -591,7 +591,8 @@ class FiniteElementLoss(Loss):
                                             _lib.ptr(dir_values) if dir_values is not None else None,
                                             _lib.ptr(dir_flag) if dir_flag is not None else None, float(out_scale),
                                             self._params,
-                                            _lib.ptr(grad_u), _lib.ptr(grad_k), _lib.ptr(energy), _lib.ptr(work)))
+                                            _lib.ptr(grad_u), _lib.ptr(grad_k), _lib.ptr(energy), _lib.ptr(work),
+                                            _lib.MESH_AFFINE if ep.get("affine") else 0))
         return energy, grad_u, grad_k
 
     # how the reference's energy behaves under a SECOND differentiation:

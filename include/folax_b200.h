@@ -177,6 +177,23 @@ int fol_energy_and_grads(fol_stream_t s, int dtype, int physics, int element, in
                          const uint8_t* dir_flag, double out_scale, const double* params_host,
                          void* grad_u, void* grad_k, void* energy, void* work);
 
+/* Same call with facts about the mesh that the host plan established (FOL_MESH_* bits); the kernels may take a
+ * cheaper route that gives the same results to rounding.  FOL_MESH_AFFINE: every element is a parallelogram /
+ * parallelepiped image of the reference element (constant Jacobian), e.g. the structured meshes of
+ * fol/tools/usefull_functions.py:213-258 -- the Quad4 thermal loss then keeps J^-1 and w detJ (5 values) per element
+ * instead of 36 cached gradient values. */
+#define FOL_MESH_AFFINE 1
+int fol_energy_and_grads_flags(fol_stream_t s, int dtype, int physics, int element, int num_gp,
+                               int64_t ne, int64_t nn, int64_t nb, const void* geom,
+                               const int32_t* conn, const int32_t* adj_ptr, const int32_t* adj_local,
+                               const int32_t* tile_node_ptr, const int32_t* tile_nodes,
+                               const int32_t* tile_elem_ptr, const int32_t* tile_elems,
+                               const int32_t* tile_conn, const int32_t* tile_lnode_ptr,
+                               const int32_t* tile_lnodes, int64_t ntiles, int64_t ecap, int64_t lcap,
+                               int64_t ncap, const void* ctrl, const void* u, const void* dir_values,
+                               const uint8_t* dir_flag, double out_scale, const double* params_host,
+                               void* grad_u, void* grad_k, void* energy, void* work, int64_t mesh_flags);
+
 /* loss tail: L = mean_b E_b^p, stats = (min, max, mean) of E_b^p, scale[b] = p E_b^(p-1)/nb.
  * out[0..3] = L, min, max, mean (device). */
 int fol_loss_reduce(fol_stream_t s, int dtype, int64_t nb, double exponent, const void* energy,
