@@ -16,6 +16,8 @@ int launch_energy_qt(cudaStream_t s, const EnergyArgs<T>& args, int ncap, int* p
   static PerDeviceOnce configured;
   if (configured.need()) {
     FOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // MINB CTAs of this size only fit with the largest shared-memory carve-out
+    FOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured.done();
   }
   // sample chunks per tile: whole rounds of the 148 * MINB resident CTAs, >= 16 passes per CTA (energy2_launch.cuh)
@@ -40,18 +42,17 @@ int energy_qt_thermal(cudaStream_t s, const EnergyArgs<T>& args, int ncap, int* 
   static const int enabled = energy2_env_int("FOL_ENERGY_QT", 1);
   if (!enabled) return 1;
   // affine meshes (all elements parallelograms; the host plan checked it) keep 5 geometry values per element in
-  // registers instead of 36: three CTAs per SM instead of two
+  // registers instead of 36, which is what lets 256-thread CTAs (tiles of up to 256 elements, 16 warps / SM) fit
   const bool affine = (args.mesh_flags & FOL_MESH_AFFINE) != 0 && energy2_env_int("FOL_ENERGY_AFFINE", 1) != 0;
-  static const int minb_env = energy2_env_int("FOL_ENERGY_QT_MINB", 0);
-  const int minb = minb_env ? minb_env : (affine ? 3 : 2);
+  const bool wide = affine && (args.ecap > 192 || ncap > 192 || energy2_env_int("FOL_ENERGY_QT_BLOCK", 0) == 256);
   const T beta = args.p.v[5], c = args.p.v[6];
   const int ci = (int)c;
   const int nl = (beta == (T)0) ? 0 : (((T)ci == c && ci >= 1 && ci <= 4) ? ci : -1);
 #define FOL_QT(NLV)                                                                         \
   if (nl == NLV) {                                                                          \
-    if (affine && minb >= 3) return launch_energy_qt<T, NLV, 192, 3, true>(s, args, ncap, parts);  \
-    if (affine) return launch_energy_qt<T, NLV, 192, 2, true>(s, args, ncap, parts);               \
-    return launch_energy_qt<T, NLV, 192, 2, false>(s, args, ncap, parts);                          \
+    if (wide) return launch_energy_qt<T, NLV, 256, 2, true>(s, args, ncap, parts);          \
+    if (affine) return launch_energy_qt<T, NLV, 192, 2, true>(s, args, ncap, parts);        \
+    return launch_energy_qt<T, NLV, 192, 2, false>(s, args, ncap, parts);                   \
   }
   FOL_QT(0) FOL_QT(1) FOL_QT(2) FOL_QT(3) FOL_QT(4) FOL_QT(-1)
 #undef FOL_QT

@@ -64,7 +64,9 @@ __device__ __forceinline__ void thermal_vectors_affine(const T (&jinv)[4], T wd,
 }
 
 template <class T, int NL, int BLOCK, int MINB, int LCAP, bool AFFINE>
-__global__ void __launch_bounds__(BLOCK, MINB) energy_qt_kernel(const EnergyArgs<T> args) {
+// Register caps follow the PER-SCHEDULER register file (16 K registers for the warps a scheduler hosts): two 192-thread
+// CTAs put 3 warps on a scheduler (168 registers), two 256-thread CTAs 4 warps (128 registers, 16 warps / SM).
+__global__ void __maxnreg__(BLOCK * MINB <= 384 ? 168 : 128) energy_qt_kernel(const EnergyArgs<T> args) {
   constexpr int S = 16 / (int)sizeof(T);    // samples per pass = one 16-byte vector
   constexpr int A = 4, KW = 8, NW = BLOCK / 32, GW = AFFINE ? 5 : 4 * 9;
   constexpr int MAXADJ = 8;                 // adjacency entries held in registers; longer lists continue from global
@@ -87,6 +89,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) energy_qt_kernel(const EnergyArgs
   const int n = has_node ? __ldg(args.tile_nodes + n_beg + lnode) : 0;
   const int a_beg = has_node ? __ldg(args.adj_ptr + n) : 0, a_end = has_node ? __ldg(args.adj_ptr + n + 1) : 0;
   const int cnt = a_end - a_beg;
+  int cnt_warp = cnt > MAXADJ ? MAXADJ : cnt;   // longest register-held list among the warp's nodes
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt_warp = max(cnt_warp, __shfl_xor_sync(0xffffffffu, cnt_warp, o));
   int off[MAXADJ];                          // re row of the entry; its dK row is 4 * BLOCK further
 #pragma unroll
   for (int i = 0; i < MAXADJ; ++i) {
@@ -190,16 +195,29 @@ __global__ void __launch_bounds__(BLOCK, MINB) energy_qt_kernel(const EnergyArgs
       T R[S], dk[S];
 #pragma unroll
       for (int s = 0; s < S; ++s) R[s] = dk[s] = (T)0;
+      // all loads of a group of four entries are issued before the first add (entries past the node's count read
+      // row 0 of element 0 -- a valid address -- and are discarded); the trip count is warp-uniform
 #pragma unroll
-      for (int i = 0; i < MAXADJ; ++i) {
-        if (i >= cnt) break;
-        T r[S], k[S];
-        unpack(svb[off[i]], r);
-        unpack(svb[off[i] + 4 * BLOCK], k);
+      for (int i0 = 0; i0 < MAXADJ; i0 += 4) {
+        if (i0 >= cnt_warp) break;
+        V rv[4], kv[4];
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-          R[s] += r[s];
-          dk[s] += k[s];
+        for (int i = 0; i < 4; ++i) {
+          rv[i] = svb[off[i0 + i]];
+          kv[i] = svb[off[i0 + i] + 4 * BLOCK];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i0 + i < cnt) {                  // fixed order: entry i0, i0 + 1, ...
+            T r[S], k[S];
+            unpack(rv[i], r);
+            unpack(kv[i], k);
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              R[s] += r[s];
+              dk[s] += k[s];
+            }
+          }
         }
       }
       for (int it = a_beg + MAXADJ; it < a_end; ++it) {
