@@ -60,6 +60,9 @@ int energy_and_grads(cudaStream_t s, int physics, int element, int num_gp, const
                                     : energy2_mech<T>(s, physics, element, num_gp, a, ncap, &parts);
   if (rc == 1) {
     parts = 1;
+    // energy_tile_kernel gives every owned node of a tile its own thread (192 per CTA)
+    if (ncap > 192) return fail(FOL_ERR_INVALID, "fol_energy_and_grads: tiles own more than 192 nodes and no pipelined kernel "
+                                                 "covers this (physics, element, rule): rebuild the plan with smaller tiles");
     if (physics == FOL_MECHANICAL) rc = dispatch_energy<T, MECH>(s, element, num_gp, a);
     else if (physics == FOL_THERMAL) rc = dispatch_energy<T, THERMAL>(s, element, num_gp, a);
     else if (physics == FOL_NEOHOOKE) rc = dispatch_energy<T, NEOHOOKE>(s, element, num_gp, a);

@@ -39,8 +39,10 @@ int launch_energy_qt(cudaStream_t s, const EnergyArgs<T>& args, int ncap, int* p
 
 template <class T>
 int energy_qt_thermal(cudaStream_t s, const EnergyArgs<T>& args, int ncap, int* parts) {
+  // float32: the sample-major kernel with three CTAs per SM (energy2.cuh) measured 9 % faster than this one
+  // (profiles/r2/energy_kernels_ab.md), so this kernel serves float64 unless FOL_ENERGY_QT=2 forces it
   static const int enabled = energy2_env_int("FOL_ENERGY_QT", 1);
-  if (!enabled) return 1;
+  if (!enabled || (sizeof(T) == 4 && enabled != 2)) return 1;
   // affine meshes (all elements parallelograms; the host plan checked it) keep 5 geometry values per element in
   // registers instead of 36, which is what lets 256-thread CTAs (tiles of up to 256 elements, 16 warps / SM) fit
   const bool affine = (args.mesh_flags & FOL_MESH_AFFINE) != 0 && energy2_env_int("FOL_ENERGY_AFFINE", 1) != 0;

@@ -554,7 +554,7 @@ class FiniteElementLoss(Loss):
             coords = np.asarray(self.fe_mesh.GetNodesCoordinates())
             conn = self.fe_mesh.GetElementsNodes(self.element_type)
             if (self._batch_physics() == "thermal" and self.element_type == "quad" and self.num_gp == 2
-                    and energy_plan.is_affine(coords, conn)):
+                    and self.dtype == torch.float64 and energy_plan.is_affine(coords, conn)):
                 # affine Quad4 meshes run the 256-thread sample-vectorised kernel (csrc/energy_qt.cuh): larger tiles,
                 # fewer border elements evaluated twice (1.16x instead of 1.19x at 256x256)
                 kw.update(max_elems=256, tile_nodes=225)

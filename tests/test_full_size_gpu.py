@@ -117,11 +117,18 @@ def test_fol_config3_full_size_batched_loss():
     a = run()
     b = run()
     assert all(bool((x == y).all()) for x, y in zip(a, b))                     # deterministic
-    os.environ["FOL_ENERGY_V1"] = "1"                                          # generic kernel, same plan
+    # generic kernel (one thread per owned node, <= 192 per tile) on its own 160-node tile plan; the node sums have the
+    # same fixed order whatever the tiling, the per-tile energy shares are added in a different order
+    os.environ.update(FOL_ENERGY_V1="1", FOL_ENERGY_MAX_ELEMS="192", FOL_ENERGY_TILE_NODES="160")
     try:
+        loss_g = ThermalLoss2DQuad("fol_g", {"dirichlet_bc_dict": {"T": {"left": 1.0, "right": 0.1}}, "beta": 2.0, "c": 4}, mesh)
+        loss_g.Initialize()
+        loss, loss_keep = loss_g, loss
         c = run()
+        loss = loss_keep
     finally:
-        del os.environ["FOL_ENERGY_V1"]
+        for k in ("FOL_ENERGY_V1", "FOL_ENERGY_MAX_ELEMS", "FOL_ENERGY_TILE_NODES"):
+            del os.environ[k]
     for x, y in zip(a, c):
         assert (x - y).abs().max().item() <= 1e-13 * y.abs().max().item()
     coords, conn = np.asarray(mesh.GetNodesCoordinates()), mesh.GetElementsNodes("quad")
