@@ -669,7 +669,9 @@ def run_ours(args):
                                            _lib.ptr(loss._adj), _lib.ptr(re), _lib.ptr(R)))
         last["R"] = R
 
-    for _ in range(args.warmup + (20 if world > 1 else 0)):
+    # the same untimed steps at every N (W requested + 5: first-touch of the peer buffers, allocator warm-up), so the
+    # timed region sits in the same power / clock state at N = 1 and N > 1
+    for _ in range(args.warmup + 5):
         step()
     torch.cuda.synchronize()
     if world > 1:
@@ -695,12 +697,21 @@ def run_ours(args):
     ms, ms_kernel = max_over_ranks(torch, dist, world, [ms, ms_kernel])
     if not have_kernel_events:      # NCCL fallback path: several element-stage launches per step, no single kernel time
         ms_kernel = ms
-    # the timed region is only tens of milliseconds: keep the same step running (untimed) under the clock sampler for
-    # ~0.25 s more.  The count comes from the all-reduced time, so every rank runs the same number of exchanges.
-    for _ in range(int(min(2000, max(10, 250.0 / ms)))):
+    # The timed region is only tens of milliseconds, i.e. it ends before the board's power-cap loop has settled: the
+    # same step keeps running under the clock sampler for ~0.5 s more and the LAST 100 steps of that soak are timed
+    # too -- `sustained` below is the throughput a long-running job sees (sw_power_cap lowers the SM clock by then).
+    soak = int(min(4000, max(150, 500.0 / ms)))       # from the all-reduced time: the same count on every rank
+    for _ in range(soak - 100):
         step()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(100):
+        step()
+    s1.record()
+    s1.synchronize()
     torch.cuda.synchronize()
     clocks.__exit__()
+    ms_sustained, = max_over_ranks(torch, dist, world, [s0.elapsed_time(s1) / 100])
     value = ne * world / (ms * 1e-3)
 
     hbm, peak_src = measured_peaks()
@@ -722,7 +733,11 @@ def run_ours(args):
                        "l2_policy": "per-step working set (9.7 GB Ke stream) >> 126 MB L2",
                        "tolerance": "parity tests: indices bit-exact; values norm-wise |x - ref|_max <= 1e-12 |ref|_max "
                                     "(f64), 1e-5 (f32)"},
-            "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks.summary()}
+            "roofline": roofline, "gpu_launches": int(launches), "clocks": clocks.summary(),
+            "sustained": {"value": ne * world / (ms_sustained * 1e-3), "unit": "elements/s", "ms_per_step": ms_sustained,
+                          "after_steps": soak - 100 + args.steps + args.warmup + 5,
+                          "note": "same step, timed over 100 steps at the end of a ~0.5 s soak (power-capped clocks); "
+                                  "`value` above is the K steps right after the warm-up, as the contract asks"}}
 
     if world > 1:
         try:

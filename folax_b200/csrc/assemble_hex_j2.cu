@@ -260,7 +260,7 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
 #pragma unroll
           for (int t = 0; t < 3; ++t)
 #pragma unroll
-            for (int s = 0; s < 3; ++s) dmma884(K[t][s][0], K[t][s][1], af[t], bf[kk][s]);
+            for (int s = t; s < 3; ++s) dmma884(K[t][s][0], K[t][s][1], af[t], bf[kk][s]);
         } else {
           // the moduli differ from point to point: family 1 weighted by w detJ (lam + a/3) accumulates straight into
           // Ke, family 2 weighted by w detJ (2G - a) enters transposed within the 3x3 blocks
@@ -270,11 +270,32 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
 #pragma unroll
           for (int t = 0; t < 3; ++t)
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
+            for (int s = t; s < 3; ++s) {
               dmma884(K[t][s][0], K[t][s][1], al[t], bf[kk][s]);
               dmma884(cs[t][s][0], cs[t][s][1], am[t], bf[kk][s]);
             }
         }
+      }
+      {
+        // both weighted sums of g_a (x) g_b are symmetric, P[(a,t),(b,s)] = P[(b,s),(a,t)]: the tiles below the diagonal
+        // are mirrored from the ones above by shuffles instead of being computed (see assemble_hex.cu)
+        const int src0 = ((2 * kq) << 2) | (ra >> 1), src1 = ((2 * kq + 1) << 2) | (ra >> 1);
+        const bool odd = (ra & 1) != 0;
+#pragma unroll
+        for (int t = 1; t < 3; ++t)
+#pragma unroll
+          for (int s = 0; s < t; ++s) {
+            const double a0 = __shfl_sync(0xffffffffu, K[s][t][0], src0), a1 = __shfl_sync(0xffffffffu, K[s][t][1], src0);
+            const double b0 = __shfl_sync(0xffffffffu, K[s][t][0], src1), b1 = __shfl_sync(0xffffffffu, K[s][t][1], src1);
+            K[t][s][0] = odd ? a1 : a0;
+            K[t][s][1] = odd ? b1 : b0;
+            if (plastic) {
+              const double c0 = __shfl_sync(0xffffffffu, cs[s][t][0], src0), c1 = __shfl_sync(0xffffffffu, cs[s][t][1], src0);
+              const double d0 = __shfl_sync(0xffffffffu, cs[s][t][0], src1), d1 = __shfl_sync(0xffffffffu, cs[s][t][1], src1);
+              cs[t][s][0] = odd ? c1 : c0;
+              cs[t][s][1] = odd ? d1 : d0;
+            }
+          }
       }
       if (!plastic) {
         // C_el = lam 1(x)1 + 2G I_6:  Ke = lam P + 2G [tr(P) I + offdiag(P^T)]

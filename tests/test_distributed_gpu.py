@@ -52,6 +52,7 @@ def _worker(rank, world, port, out):
             part.close_peer_halo()
             dist.barrier()
         D.FUSED_HALO = True
+        data, R = data.clone(), R.clone()           # the J2 section below reuses the `ke` buffer
         # J2 elastoplasticity with Gauss-point history through the fused path against the NCCL path
         from folax_b200.loss_functions import ElastoplasticityLoss3DHexa
         mat = {"young_modulus": 3.0, "poisson_ratio": 0.3, "iso_hardening_parameter_1": 0.4,
