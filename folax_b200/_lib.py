@@ -39,6 +39,11 @@ SIGNATURES = {
     "fol_csr_values": (_int, [_vp, _int, _i64, _int, _int, _i32p, _i32p, _i32p, _i32p, _vp, _vp]),
     "fol_apply_jacobian_elements": (_int, [_vp, _int, _int, _int, _int, _int, _i64, _i64, _vp, _i32p, _vp, _vp, _u8p,
                                            C.POINTER(_dbl), _vp, _vp, _vp]),
+    "fol_apply_jacobian_elements_batched": (_int, [_vp, _int, _int, _int, _int, _int, _i64, _i64, _i64, _vp, _i32p, _vp,
+                                                   _vp, _u8p, C.POINTER(_dbl), _vp, _vp]),
+    "fol_residual_gather_batched": (_int, [_vp, _int, _i64, _int, _int, _i64, _i64, _i32p, _i32p, _vp, _vp]),
+    "fol_residual_adjoint_elements_batched": (_int, [_vp, _int, _int, _int, _int, _i64, _i64, _i64, _vp, _i32p, _vp, _vp,
+                                                     _vp, _vp, C.POINTER(_dbl), _vp]),
     "fol_geometry_cache": (_int, [_vp, _int, _int, _int, _i64, _vp, _i32p, _vp]),
     "fol_geometry_width": (_int, [_int, _int]),
     "fol_geometry_cache_physics": (_int, [_vp, _int, _int, _int, _int, _i64, _vp, _i32p, _vp, _vp]),

@@ -18,9 +18,20 @@ __global__ void __launch_bounds__(128) response_kernel(const ResponseArgs<T> a) 
 }
 
 template <class T, int ELEM, int ORDER, int PHYS>
-__global__ void __launch_bounds__(128) residual_adjoint_kernel(const AdjointArgs<T> a) {
+__global__ void __launch_bounds__(128) residual_adjoint_kernel(const AdjointArgs<T> a_in) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < a.ne) residual_adjoint_thread<T, ELEM, ORDER, PHYS>(e, a);
+  if (e >= a_in.ne) return;
+  if (a_in.batch_count > 0) {   // sample blockIdx.y of a batch: its own slices of ctrl / u / lam / dk
+    AdjointArgs<T> a = a_in;
+    const long long b = blockIdx.y;
+    a.ctrl += b * a_in.batch_node;
+    a.u += b * a_in.batch_dof;
+    a.lam += b * a_in.batch_dof;
+    if (a.dk) a.dk += b * a_in.batch_dk;
+    residual_adjoint_thread<T, ELEM, ORDER, PHYS>(e, a);
+  } else {
+    residual_adjoint_thread<T, ELEM, ORDER, PHYS>(e, a_in);
+  }
 }
 
 template <class T, int ELEM, int ORDER, int PHYS>
@@ -82,7 +93,7 @@ static int launch_adjoint(cudaStream_t s, int element, int num_gp, const Adjoint
   const unsigned grid = (unsigned)cdiv(a.ne, 128);
 #define X(E, O)                                                            \
   if (element == E && num_gp == O) {                                       \
-    residual_adjoint_kernel<T, E, O, PHYS><<<grid, 128, 0, s>>>(a);        \
+    residual_adjoint_kernel<T, E, O, PHYS><<<dim3(grid, (unsigned)(a.batch_count > 0 ? a.batch_count : 1)), 128, 0, s>>>(a); \
     return check_launch("residual_adjoint_kernel");                        \
   }
   FOL_ELEM_ORDER_CASES(X)
@@ -169,8 +180,15 @@ static int response_typed(cudaStream_t s, int element, int num_gp, int dpn, long
 template <class T>
 static int adjoint_typed(cudaStream_t s, int physics, int element, int num_gp, int accumulate, long long ne,
                          const void* xyz, const int32_t* conn, const void* ctrl, const void* u, const void* lam,
-                         const void* aux, const double* params, void* dk, void* dx) {
+                         const void* aux, const double* params, void* dk, void* dx, long long nb = 0, long long nn = 0) {
   AdjointArgs<T> a;
+  if (nb > 0) {   // batched: per-sample strides of ctrl / (u, lam) / dk
+    const int dpn = (physics == FOL_THERMAL || physics == FOL_TRANSIENT_THERMAL || physics == FOL_ALLEN_CAHN) ? 1 : elem_dim(element);
+    a.batch_count = (int)nb;
+    a.batch_node = nn;
+    a.batch_dof = nn * dpn;
+    a.batch_dk = ne * (long long)elem_nnode(element);
+  }
   a.xyz = (const T*)xyz;
   a.conn = conn;
   a.ctrl = (const T*)ctrl;
@@ -245,6 +263,25 @@ int fol_residual_adjoint_elements(fol_stream_t s, int dtype, int physics, int el
     return adjoint_typed<float>((cudaStream_t)s, physics, element, num_gp, accumulate, ne, xyz, conn, ctrl, u, adj,
                                 aux, params_host, dk_elem, dx_elem);
   return fail(FOL_ERR_INVALID, "fol_residual_adjoint_elements: unknown dtype");
+}
+
+/* lam^T d(re)/dK of a BATCH of samples in one launch (grid.y = sample): ctrl (nb, nn), u and adj (nb, ndof) ->
+ * dk_elem (nb, ne*A).  The nested VJP of the batched loss (fe_loss.py _SecondOrderFn) needs it per sample. */
+int fol_residual_adjoint_elements_batched(fol_stream_t s, int dtype, int physics, int element, int num_gp, int64_t ne,
+                                          int64_t nn, int64_t nb, const void* xyz, const int32_t* conn,
+                                          const void* ctrl, const void* u, const void* adj, const void* aux,
+                                          const double* params_host, void* dk_elem) {
+  FOL_REQUIRE(element >= 0 && element <= 3 && num_gp >= 1 && num_gp <= 3,
+              "fol_residual_adjoint_elements_batched: bad element / num_gp");
+  FOL_REQUIRE(ne >= 0 && nn >= 1 && nb >= 1 && nb <= 65535 && xyz && conn && ctrl && u && adj && params_host && dk_elem,
+              "fol_residual_adjoint_elements_batched: null pointer / bad size (1 <= nb <= 65535)");
+  if (dtype == FOL_F64)
+    return adjoint_typed<double>((cudaStream_t)s, physics, element, num_gp, 0, ne, xyz, conn, ctrl, u, adj, aux,
+                                 params_host, dk_elem, nullptr, nb, nn);
+  if (dtype == FOL_F32)
+    return adjoint_typed<float>((cudaStream_t)s, physics, element, num_gp, 0, ne, xyz, conn, ctrl, u, adj, aux,
+                                params_host, dk_elem, nullptr, nb, nn);
+  return fail(FOL_ERR_INVALID, "fol_residual_adjoint_elements_batched: unknown dtype");
 }
 
 int fol_element_energies(fol_stream_t s, int dtype, int physics, int element, int num_gp, int64_t ne, const void* xyz,

@@ -46,6 +46,9 @@ struct AdjointArgs {
   long long ne;
   int accumulate;  // add to dk / dx instead of overwriting (response part + residual part, fe_response.py:385, 515)
   Params<T> p;
+  // batch of samples (grid.y = sample): per-sample strides, in values, of ctrl / (u, lam) / dk (dx is not batched)
+  long long batch_node = 0, batch_dof = 0, batch_dk = 0;
+  int batch_count = 0;
 };
 
 template <class T, int ELEM, int ORDER>

@@ -43,9 +43,16 @@ template <class T>
 static int assemble_typed(cudaStream_t s, int physics, int element, int num_gp, int transpose, long long ne,
                           const void* xyz, const int32_t* conn, const void* ctrl, const void* u, const uint8_t* dir,
                           const double* params, void* ke, void* re, const void* st_in, void* st_out,
-                          const void* v = nullptr) {
+                          const void* v = nullptr, long long nb = 0, long long nn = 0) {
   AsmArgs<T> a;
   a.v = (const T*)v;
+  if (nb > 0) {   // batched matrix-free mode: per-sample strides of ctrl / (u, v) / ye
+    const int dpn = (physics == FOL_THERMAL || physics == FOL_TRANSIENT_THERMAL || physics == FOL_ALLEN_CAHN) ? 1 : elem_dim(element);
+    a.batch_count = (int)nb;
+    a.batch_node = nn;
+    a.batch_dof = nn * dpn;
+    a.batch_elem = ne * (long long)elem_nnode(element) * dpn;
+  }
   a.xyz = (const T*)xyz;
   a.conn = conn;
   a.ctrl = (const T*)ctrl;
@@ -185,6 +192,25 @@ int fol_apply_jacobian_elements(fol_stream_t s, int dtype, int physics, int elem
     return assemble_typed<float>((cudaStream_t)s, physics, element, num_gp, transpose, ne, xyz, conn, ctrl, u,
                                  dir_flag, params_host, nullptr, ye_elem, state_in, nullptr, v);
   return fail(FOL_ERR_INVALID, "fol_apply_jacobian_elements: dtype must be FOL_F32 or FOL_F64");
+}
+
+int fol_apply_jacobian_elements_batched(fol_stream_t s, int dtype, int physics, int element, int num_gp, int transpose,
+                                        int64_t ne, int64_t nn, int64_t nb, const void* xyz, const int32_t* conn,
+                                        const void* ctrl, const void* u, const uint8_t* dir_flag,
+                                        const double* params_host, const void* v, void* ye_elem) {
+  FOL_REQUIRE(valid_element(element), "fol_apply_jacobian_elements_batched: unknown element");
+  FOL_REQUIRE(num_gp >= 1 && num_gp <= 3, "fol_apply_jacobian_elements_batched: num_gp must be 1, 2 or 3");
+  FOL_REQUIRE(xyz && conn && ctrl && u && dir_flag && v && ye_elem && params_host,
+              "fol_apply_jacobian_elements_batched: null pointer");
+  FOL_REQUIRE(ne >= 0 && nb >= 1 && nb <= 65535 && nn >= 1, "fol_apply_jacobian_elements_batched: bad sizes (1 <= nb <= 65535)");
+  FOL_REQUIRE(physics != FOL_J2PLASTICITY, "fol_apply_jacobian_elements_batched: history-dependent elements are not batched");
+  if (dtype == FOL_F64)
+    return assemble_typed<double>((cudaStream_t)s, physics, element, num_gp, transpose, ne, xyz, conn, ctrl, u,
+                                  dir_flag, params_host, nullptr, ye_elem, nullptr, nullptr, v, nb, nn);
+  if (dtype == FOL_F32)
+    return assemble_typed<float>((cudaStream_t)s, physics, element, num_gp, transpose, ne, xyz, conn, ctrl, u,
+                                 dir_flag, params_host, nullptr, ye_elem, nullptr, nullptr, v, nb, nn);
+  return fail(FOL_ERR_INVALID, "fol_apply_jacobian_elements_batched: dtype must be FOL_F32 or FOL_F64");
 }
 
 int fol_geometry_width(int physics, int element) {

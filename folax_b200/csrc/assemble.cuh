@@ -49,6 +49,9 @@ struct AsmArgs {
   int transpose;
   Params<T> p;
   const T* v = nullptr;   // matrix-free mode: re <- Ke'(u) v_e (element products of J v), ke is not written
+  // matrix-free mode over a batch of samples (grid.y = sample): strides, in values, of ctrl / (u, v) / re per sample
+  long long batch_node = 0, batch_dof = 0, batch_elem = 0;
+  int batch_count = 0;    // samples (grid.y); 0 = unbatched
 };
 
 // per-Gauss-point constitutive data handed from phase 1 to phase 2
@@ -321,7 +324,20 @@ namespace fol {
 // MATVEC = matrix-free mode (args.v): a separate instantiation, so the assembling kernels carry none of its
 // registers or branches (as a run-time flag it cost them 10-20 %)
 template <class T, int ELEM, int ORDER, int PHYS, int BLOCK, bool MATVEC = false>
-__global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args) {
+__global__ void __launch_bounds__(BLOCK) assemble_kernel(const AsmArgs<T> args_in) {
+  // batched matrix-free mode: sample blockIdx.y reads / writes its own slices (the assembling kernels see args_in as is)
+  AsmArgs<T> shifted;
+  const AsmArgs<T>* ap = &args_in;
+  if constexpr (MATVEC) {
+    shifted = args_in;
+    const long long b = blockIdx.y;
+    shifted.ctrl += b * args_in.batch_node;
+    shifted.u += b * args_in.batch_dof;
+    shifted.v += b * args_in.batch_dof;
+    shifted.re += b * args_in.batch_elem;
+    ap = &shifted;
+  }
+  const AsmArgs<T>& args = *ap;
   using SM = GroupSmem<T, ELEM, ORDER, PHYS>;
   constexpr int A = SM::A, D = SM::D, DPN = SM::DPN, ND = SM::ND, NGP = SM::NGP, PD = SM::PD;
   constexpr int GW = (A == 8) ? 8 : 4;  // lanes per element group (tri pads 3 -> 4)
@@ -809,7 +825,7 @@ int launch_assemble(cudaStream_t s, const AsmArgs<T>& args) {
       configured.done();
     }
     if (grid == 0) return FOL_OK;
-    kern<<<(unsigned)grid, BLOCK, smem, s>>>(args);
+    kern<<<dim3((unsigned)grid, (unsigned)(args.batch_count > 0 ? args.batch_count : 1)), BLOCK, smem, s>>>(args);
     return check_launch("assemble_kernel (matrix-free)");
   }
   auto kern = assemble_kernel<T, ELEM, ORDER, PHYS, BLOCK, false>;

@@ -105,6 +105,22 @@ __global__ void residual_gather_kernel(long long nn, int d, const int32_t* __res
   R[t] = acc;
 }
 
+// the same gather for a batch of samples (grid.y = sample): re is (nb, ne*A*d), R is (nb, nn*d)
+template <class T>
+__global__ void residual_gather_batched_kernel(long long nn, int d, long long re_stride, const int32_t* __restrict__ ptr,
+                                               const int32_t* __restrict__ adj, const T* __restrict__ re,
+                                               T* __restrict__ R) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nn * d) return;
+  const long long n = t / d;
+  const int k = (int)(t - n * d);
+  const T* src = re + (long long)blockIdx.y * re_stride;
+  T acc = (T)0;
+  const int lo = ptr[n], hi = ptr[n + 1];
+  for (int i = lo; i < hi; ++i) acc += __ldg(src + (long long)adj[i] * d + k);
+  R[(long long)blockIdx.y * nn * d + t] = acc;
+}
+
 template <class T>
 __global__ void apply_dirichlet_kernel(long long nb, long long ndof, const int32_t* __restrict__ idx, long long nd,
                                        const T* __restrict__ values, int per_sample, T load, T* __restrict__ u) {
@@ -176,6 +192,22 @@ int fol_residual_gather(fol_stream_t s, int dtype, int64_t nn, int nnode, int d,
     residual_gather_kernel<float><<<grid, 256, 0, (cudaStream_t)s>>>(nn, d, adj_ptr, adj, (const float*)re_elem,
                                                                      (float*)residual);
   return check_launch("residual_gather_kernel");
+}
+
+int fol_residual_gather_batched(fol_stream_t s, int dtype, int64_t nn, int nnode, int d, int64_t nb, int64_t ne,
+                                const int32_t* adj_ptr, const int32_t* adj, const void* re_elem, void* residual) {
+  FOL_REQUIRE(adj_ptr && adj && re_elem && residual && nb >= 1 && nb <= 65535, "fol_residual_gather_batched: bad arguments");
+  const long long total = (long long)nn * d;
+  if (total == 0) return FOL_OK;
+  const dim3 grid((unsigned)cdiv(total, 256), (unsigned)nb);
+  const long long stride = (long long)ne * nnode * d;
+  if (dtype == FOL_F64)
+    residual_gather_batched_kernel<double><<<grid, 256, 0, (cudaStream_t)s>>>(nn, d, stride, adj_ptr, adj,
+                                                                              (const double*)re_elem, (double*)residual);
+  else
+    residual_gather_batched_kernel<float><<<grid, 256, 0, (cudaStream_t)s>>>(nn, d, stride, adj_ptr, adj,
+                                                                             (const float*)re_elem, (float*)residual);
+  return check_launch("residual_gather_batched_kernel");
 }
 
 int fol_apply_dirichlet(fol_stream_t s, int dtype, int64_t nb, int64_t ndof, const int32_t* idx, int64_t nd,

@@ -121,7 +121,7 @@ class _SecondOrderFn(torch.autograd.Function):
         d/dK_b = (up/B) (mask (.) w_u[b])^T dF_int/dK          (F_int is linear in K, so d2E/dK2 = 0)
     K_T v is the matrix-free product of fol_apply_jacobian_elements without the Dirichlet row mask, the last
     line is fol_residual_adjoint_elements, F_int(u; w_K) is one more call of the batched energy kernel.
-    One launch per sample for the first and the last (no batched variant of those kernels yet)."""
+    Every kernel runs once for the whole batch (grid.y = sample)."""
 
     @staticmethod
     def forward(ctx, loss, batch_params, batch_dofs, up, payload):
@@ -146,24 +146,26 @@ class _SecondOrderFn(torch.autograd.Function):
             w_u = w_u.to(loss.dtype).contiguous().clone()
             if pl.mask_dirichlet:
                 w_u[:, loss._dir_idx.to(torch.int64)] = 0
-            ye = torch.empty(max(loss._ne * loss._nd, 1), dtype=loss.dtype, device=loss.device)
-            dk_e = torch.empty(max(loss._ne * loss._nnode, 1), dtype=loss.dtype, device=loss.device)
+            # ONE launch per kernel for the whole batch (grid.y = sample): K_T v, its fixed-order node sums, v^T dF_int/dK
             phys = _lib.PHYSICS[loss.physics]
-            for b in range(nb):
-                _lib.check(lib.fol_apply_jacobian_elements(
-                    s, loss._dt, phys, loss.fe_element.code, loss.num_gp, 0, loss._ne, loss._nn, _lib.ptr(loss._xyz),
-                    _lib.ptr(loss._conn), _lib.ptr(params[b]), _lib.ptr(u_full[b]), _lib.ptr(loss._no_flag),
-                    loss._params, _lib.ptr(w_u[b]), _lib.ptr(ye), None))
-                _lib.check(lib.fol_residual_gather(s, loss._dt, loss._nn, loss._nnode, loss.number_dofs_per_node,
-                                                   _lib.ptr(loss._adj_ptr), _lib.ptr(loss._adj), _lib.ptr(ye),
-                                                   _lib.ptr(d_dofs[b])))
-                if d_params is not None:
-                    _lib.check(lib.fol_residual_adjoint_elements(
-                        s, loss._dt, phys, loss.fe_element.code, loss.num_gp, 0, loss._ne, _lib.ptr(loss._xyz),
-                        _lib.ptr(loss._conn), _lib.ptr(params[b]), _lib.ptr(u_full[b]), _lib.ptr(w_u[b]), None,
-                        loss._params, _lib.ptr(dk_e), None))
-                    _lib.check(lib.fol_residual_gather(s, loss._dt, loss._nn, loss._nnode, 1, _lib.ptr(loss._adj_ptr),
-                                                       _lib.ptr(loss._adj), _lib.ptr(dk_e), _lib.ptr(d_params[b])))
+            params_c, u_c = params.contiguous(), u_full.contiguous()
+            ye = torch.empty((nb, max(loss._ne * loss._nd, 1)), dtype=loss.dtype, device=loss.device)
+            _lib.check(lib.fol_apply_jacobian_elements_batched(
+                s, loss._dt, phys, loss.fe_element.code, loss.num_gp, 0, loss._ne, loss._nn, nb, _lib.ptr(loss._xyz),
+                _lib.ptr(loss._conn), _lib.ptr(params_c), _lib.ptr(u_c), _lib.ptr(loss._no_flag), loss._params,
+                _lib.ptr(w_u), _lib.ptr(ye)))
+            _lib.check(lib.fol_residual_gather_batched(s, loss._dt, loss._nn, loss._nnode, loss.number_dofs_per_node, nb,
+                                                       loss._ne, _lib.ptr(loss._adj_ptr), _lib.ptr(loss._adj),
+                                                       _lib.ptr(ye), _lib.ptr(d_dofs)))
+            if d_params is not None:
+                dk_e = torch.empty((nb, max(loss._ne * loss._nnode, 1)), dtype=loss.dtype, device=loss.device)
+                _lib.check(lib.fol_residual_adjoint_elements_batched(
+                    s, loss._dt, phys, loss.fe_element.code, loss.num_gp, loss._ne, loss._nn, nb, _lib.ptr(loss._xyz),
+                    _lib.ptr(loss._conn), _lib.ptr(params_c), _lib.ptr(u_c), _lib.ptr(w_u), None, loss._params,
+                    _lib.ptr(dk_e)))
+                _lib.check(lib.fol_residual_gather_batched(s, loss._dt, loss._nn, loss._nnode, 1, nb, loss._ne,
+                                                           _lib.ptr(loss._adj_ptr), _lib.ptr(loss._adj),
+                                                           _lib.ptr(dk_e), _lib.ptr(d_params)))
         if w_k is not None:
             # F_int is linear in the control field: dF_int/dK . w_K = F_int(u; controls = w_K)
             _, fint, _ = loss._energy_and_grads(w_k.to(loss.dtype).contiguous(), u_full.contiguous())

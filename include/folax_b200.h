@@ -134,6 +134,18 @@ int fol_apply_jacobian_elements(fol_stream_t s, int dtype, int physics, int elem
                                 const int32_t* conn, const void* ctrl, const void* u,
                                 const uint8_t* dir_flag, const double* params_host, const void* v,
                                 void* ye_elem, const void* state_in);
+/* The same products for a BATCH of samples in one launch (grid.y = sample): controls (nb, nn), dofs and v (nb, ndof)
+ * -> ye_elem (nb, ne*nd); fol_residual_gather_batched sums them per sample in the residual's fixed order.  What the
+ * nested VJP of the batched loss needs (the latent-code steps of meta_implicit_parametric_operator_learning.py:95-105
+ * differentiate through jax.vmap(jax.grad(loss))).  Not for history-dependent (J2) elements. */
+int fol_apply_jacobian_elements_batched(fol_stream_t s, int dtype, int physics, int element, int num_gp,
+                                        int transpose, int64_t ne, int64_t nn, int64_t nb, const void* xyz,
+                                        const int32_t* conn, const void* controls, const void* dofs,
+                                        const uint8_t* dir_flag, const double* params, const void* v,
+                                        void* ye_elem);
+int fol_residual_gather_batched(fol_stream_t s, int dtype, int64_t nn, int nnode, int dofs_per_node, int64_t nb,
+                                int64_t ne, const int32_t* adj_ptr, const int32_t* adj, const void* re_elem,
+                                void* residual);
 
 /* per-element, per-Gauss-point geometry factors shared by all samples, SoA over elements:
  * geom[(g*(a*dim+1) + k)*ne + e] = grad N flattened (k < a*dim) | w*detJ (k = a*dim).   */
@@ -245,6 +257,12 @@ int fol_residual_adjoint_elements(fol_stream_t s, int dtype, int physics, int el
                                   int64_t ne, const void* xyz, const int32_t* conn, const void* ctrl, const void* u,
                                   const void* adj, const void* aux, const double* params_host, void* dk_elem,
                                   void* dx_elem);
+/* lam^T d(re)/dK for a BATCH of samples in one launch: controls (nb, nn), dofs and adjoint (nb, ndof) -> dk_elem (nb, ne*A) */
+int fol_residual_adjoint_elements_batched(fol_stream_t s, int dtype, int physics, int element, int num_gp,
+                                          int64_t ne, int64_t nn, int64_t nb, const void* xyz,
+                                          const int32_t* conn, const void* controls, const void* dofs,
+                                          const void* adjoint, const void* aux, const double* params,
+                                          void* dk_elem);
 
 /* energy_elem[e] = the element energy ComputeElement returns first (ComputeElementsEnergies, fe_loss.py:149-176):
  * u^T(Ke u - Fe) for the mechanical / thermal losses, sum_g w detJ psi for Neo-Hooke / St-Venant, the implicit-Euler

@@ -74,3 +74,33 @@ def test_apply_jacobian_float32_and_transient():
                                      H.oracle_params(loss))
     ref = _dense_apply(data, idx, loss.total_number_of_dofs, v)
     assert np.abs(y - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("physics,etype,num_gp", [("mechanical", "hexahedron", 2), ("thermal", "quad", 2),
+                                                  ("neohooke", "tetra", 1)])
+@pytest.mark.parametrize("transpose", [0, 1])
+def test_batched_products_equal_per_sample_products(physics, etype, num_gp, transpose):
+    """fol_apply_jacobian_elements_batched + fol_residual_gather_batched (grid.y = sample) against one call per sample:
+    bit for bit (same kernel, same fixed summation order)."""
+    import torch
+    from folax_b200 import _lib
+    lib = _lib.load()
+    mesh = H.make_mesh(etype, 3, seed=9)
+    loss = H.make_loss(physics, etype, mesh, num_gp)
+    nb = 4
+    K, u = H.fields(physics, mesh, loss, seed=2, batch=nb)
+    rng = np.random.default_rng(3)
+    V = rng.standard_normal(u.shape)
+    Kt, ut, vt = (torch.tensor(a, device="cuda") for a in (K, u, V))
+    ye = torch.empty((nb, loss._ne * loss._nd), dtype=torch.float64, device="cuda")
+    y = torch.empty((nb, loss.total_number_of_dofs), dtype=torch.float64, device="cuda")
+    s = _lib.stream_ptr()
+    _lib.check(lib.fol_apply_jacobian_elements_batched(
+        s, loss._dt, _lib.PHYSICS[physics], loss.fe_element.code, num_gp, transpose, loss._ne, loss._nn, nb,
+        _lib.ptr(loss._xyz), _lib.ptr(loss._conn), _lib.ptr(Kt), _lib.ptr(ut), _lib.ptr(loss._dir_flag), loss._params,
+        _lib.ptr(vt), _lib.ptr(ye)))
+    _lib.check(lib.fol_residual_gather_batched(s, loss._dt, loss._nn, loss._nnode, loss.number_dofs_per_node, nb, loss._ne,
+                                               _lib.ptr(loss._adj_ptr), _lib.ptr(loss._adj), _lib.ptr(ye), _lib.ptr(y)))
+    for b in range(nb):
+        ref = loss.ApplyJacobian(K[b], u[b], V[b], transpose_jacobian=bool(transpose))
+        assert torch.equal(y[b], ref), f"sample {b}"
