@@ -516,6 +516,41 @@ def spmv_bench(torch, loss, K, u):
             "csr_values_ms": ms_csr, "bicgstab_jacobi_ms_per_iteration": it_ms, "host_plans_s": plan_s}
 
 
+def config1_bench(torch):
+    """configs[0]: examples/mechanical_square -- 2-D linear elasticity on the generated 50x50 quad mesh, residual +
+    Jacobian assembly and the linear solve of FiniteElementLinearResidualBasedSolver (device-resident Jacobi-BiCGSTAB
+    here, host sparse direct solve in the reference: fe_solver.py:70-80).  Launch-latency-bound at this size."""
+    import folax_b200
+    from folax_b200.loss_functions import MechanicalLoss2DQuad
+    from folax_b200.solvers import FiniteElementLinearResidualBasedSolver
+    mesh = folax_b200.create_2D_square_mesh(1.0, 51)
+    bc = {"Ux": {"left": 0.0, "right": 0.05}, "Uy": {"left": 0.0, "right": 0.05}}
+    loss = MechanicalLoss2DQuad("mechanical_loss_2d", {"dirichlet_bc_dict": bc, "num_gp": 2, "material_dict": dict(MATERIAL)}, mesh)
+    loss.Initialize()
+    nn, ndof = mesh.GetNumberOfNodes(), loss.GetTotalNumberOfDOFs()
+    K = torch.tensor(np.random.default_rng(25).uniform(0.1, 1.0, nn), device="cuda")
+    u0 = loss.ApplyDirichletBCOnDofVector(np.zeros(ndof))
+    for _ in range(3):
+        loss.ComputeJacobianMatrixAndResidualVector(K, u0)
+    ms_asm = event_time_ms(torch, lambda: loss.ComputeJacobianMatrixAndResidualVector(K, u0), 50)
+    solver = FiniteElementLinearResidualBasedSolver("lin", loss, {"linear_solver_settings": {
+        "solver": "JAX-bicgstab", "tol": 1e-10, "atol": 0.0, "maxiter": 5000, "pre-conditioner": "jacobi"}})
+    solver.Initialize()
+    solver.Solve(K, np.zeros(ndof))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    u = solver.Solve(K, np.zeros(ndof))
+    torch.cuda.synchronize()
+    solve_s = time.perf_counter() - t0
+    _, R = loss.ComputeJacobianMatrixAndResidualVector(K, u)
+    free = torch.as_tensor(loss.non_dirichlet_indices, device="cuda", dtype=torch.int64)
+    return {"workload": "mechanical_square_50x50_quads_f64 (2 500 elements, 5 202 dofs)", "assembly_ms": ms_asm,
+            "assembly_elements_per_s": 2500 / (ms_asm * 1e-3), "assemble_and_solve_ms": 1e3 * solve_s,
+            "bicgstab_iterations": int(solver.last_linear_solve_info),
+            "free_dof_residual_max": float(R[free].abs().max()),
+            "note": "2 launches + allocations per assembly: latency-bound, the mesh is 0.1 % of configs[1]"}
+
+
 def newton_bench(torch):
     """configs[3]: Neo-Hooke on a Kuhn-split tetra box (70^3 cells = 2.06 M Tet4), ONE load step of the incremental
     Newton-Raphson (Jacobian re-assembled every iteration, Jacobi-BiCGSTAB on the device-resident SELL matrix)."""
@@ -782,6 +817,11 @@ def run_ours(args):
                 extras.append("newton")
             except Exception as ex:
                 line["newton"] = {"error": str(ex)[:300]}
+            try:
+                line["config1"] = config1_bench(torch)
+                extras.append("config1")
+            except Exception as ex:
+                line["config1"] = {"error": str(ex)[:300]}
             torch.cuda.empty_cache()
         try:
             sec = fol_loss_grad_bench(torch, dist, rank, world, max(3, min(args.steps, 10)), 3)

@@ -9,7 +9,8 @@
 
 Extra settings (not in the reference): "pre-conditioner": "jacobi" applies the diagonal to BiCGSTAB;
 "device_scalars": True keeps the BiCGSTAB recurrence scalars on the device (linalg.bicgstab_device: same iterates,
-one host read per "check_every" iterations instead of four per iteration).
+one host read per "check_every" iterations instead of four per iteration); with "use_graph": True a batch of
+"check_every" iterations is captured once in a CUDA graph and replayed (one launch per batch).
 """
 import numpy as np
 import torch
@@ -57,7 +58,8 @@ class FiniteElementSolver(Solver):
         diag = A.diagonal() if str(s.get("pre-conditioner", "")).lower() == "jacobi" else None
         if s.get("device_scalars"):       # extra setting: recurrence scalars on the device, one host read per batch
             x, info = linalg.bicgstab_device(A, rhs, x0=dofs_vector, tol=s["tol"], atol=s["atol"], maxiter=s["maxiter"],
-                                             M_diagonal=diag, check_every=int(s.get("check_every", 8)))
+                                             M_diagonal=diag, check_every=int(s.get("check_every", 8)),
+                                             use_graph=bool(s.get("use_graph", False)))
         else:
             x, info = linalg.bicgstab(A, rhs, x0=dofs_vector, tol=s["tol"], atol=s["atol"], maxiter=s["maxiter"],
                                       M_diagonal=diag)

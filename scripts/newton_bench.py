@@ -20,7 +20,10 @@ bc = {"Ux": {"left": 0.0, "right": disp}, "Uy": {"left": 0.0, "right": 0.2 * dis
 loss = NeoHookeMechanicalLoss3DTetra("nh", {"dirichlet_bc_dict": bc, "material_dict": {"young_modulus": 1.0,
                                                                                       "poisson_ratio": 0.3}}, mesh)
 settings = {"linear_solver_settings": {"solver": "JAX-bicgstab", "tol": float(os.environ.get("TOL", 1e-8)), "atol": 0.0,
-                                       "maxiter": int(os.environ.get("MAXITER", 2000)), "pre-conditioner": "jacobi"},
+                                       "maxiter": int(os.environ.get("MAXITER", 2000)), "pre-conditioner": "jacobi",
+                                       "device_scalars": bool(int(os.environ.get("DEVICE_SCALARS", 0))),
+                                       "use_graph": bool(int(os.environ.get("USE_GRAPH", 0))),
+                                       "check_every": int(os.environ.get("CHECK_EVERY", 8))},
             "nonlinear_solver_settings": {"rel_tol": 1e-8, "abs_tol": 1e-8, "maxiter": 10,
                                           "load_incr": int(os.environ.get("LOAD_STEPS", 5))}}
 solver = FiniteElementNonLinearResidualBasedSolver("nl", loss, settings)
@@ -56,6 +59,17 @@ def bicg(*a, **k):
 
 
 linalg.bicgstab = bicg
+_bicg_dev = linalg.bicgstab_device
+
+
+def bicg_dev(*a, **k):
+    x, info = timed(_bicg_dev, "krylov_s")(*a, **k)
+    split["krylov_iterations"] += max(info, 0)
+    split["newton_iterations"] += 1
+    return x, info
+
+
+linalg.bicgstab_device = bicg_dev
 t0 = time.time()
 plan_t0 = time.time()
 loss._csr_plan(); loss._sell_plan()
