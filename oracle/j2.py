@@ -14,8 +14,10 @@ carried through the same iteration (same start x0 = 0, same stopping test on pri
 same 1e-12 regulariser).  Pure-Python loops per Gauss point: small cases only.
 
 Parity status: the elastic branch is pinned by test_elastoplasticity.py:70-160; the plastic branch
-has no golden in the reference and is pinned by this restatement of the cited lines, cross-checked
-by finite differences and yield consistency (tests/test_oracle_j2.py).
+has no golden in the reference.  It is pinned by the agreement (<= 1e-12) of this restatement with
+oracle/j2_torch.py -- a literal torch transcription of the reference differentiated by torch.func --
+and cross-checked by finite differences and yield consistency (tests/test_oracle_j2.py,
+tests/test_j2_host_shim.py).
 """
 import numpy as np
 
