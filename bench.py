@@ -727,8 +727,14 @@ def run_ours(args):
     launches = lib.fol_launch_count() - launches0
     have_kernel_events = world == 1 or part._halo is not None
     ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in ev])) if have_kernel_events else 0.0
+    per_rank = None
     if world > 1:
         dist.barrier()
+        mine = torch.tensor([ms, ms_kernel], device="cuda", dtype=torch.float64)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank = {"ms_per_step": [float(t[0]) for t in every], "kernel_ms": [float(t[1]) for t in every],
+                    "note": "each rank's own CUDA-event times over the same K steps; the line's values are the maxima"}
     ms, ms_kernel = max_over_ranks(torch, dist, world, [ms, ms_kernel])
     if not have_kernel_events:      # NCCL fallback path: several element-stage launches per step, no single kernel time
         ms_kernel = ms
@@ -774,6 +780,8 @@ def run_ours(args):
                           "note": "same step, timed over 100 steps at the end of a ~0.5 s soak (power-capped clocks); "
                                   "`value` above is the K steps right after the warm-up, as the contract asks"}}
 
+    if per_rank is not None:
+        line["per_rank"] = per_rank
     if world > 1:
         try:
             line["halo_check"] = halo_check(torch, dist, rank, world, part, loss, last["R"], n)

@@ -15,6 +15,8 @@
 //     store instructions on the LSU path; the copy of element i drains while element i+1 is computed.
 // Ke is symmetric only to rounding here (the scale s_g rides on the A operand of the DMMA), so calls
 // with transpose_jacobian=True are served by the generic kernel, which transposes exactly.
+#include <cstdlib>
+
 #include "assemble.cuh"
 #include "assemble_hex_common.cuh"
 
@@ -270,7 +272,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         r[i] = acc;
       }
-      if (has_body) {  // Fe_a = b * sum_g w detJ N_a(g)   (mechanical.py:110)
+      if (has_body & 1) {  // Fe_a = b * sum_g w detJ N_a(g)   (mechanical.py:110)
         double nw = 0.0;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -345,7 +347,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
         write_rows();
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) bulk_store(args.ke + e * 576, slot, 576 * sizeof(double));
+        if (lane == 0 && !(has_body & 2)) bulk_store(args.ke + e * 576, slot, 576 * sizeof(double));
         store_re();
       }
     }
@@ -372,7 +374,11 @@ int assemble_hex_mech_f64(cudaStream_t s, const AsmArgs<double>& args, const Hal
   if (args.ne == 0) return FOL_OK;
   const long long ntiles = cdiv(args.ne, kTile);
   const long long want = cdiv(ntiles, kWarps);
-  const int has_body = (args.p.v[2] != 0.0 || args.p.v[3] != 0.0 || args.p.v[4] != 0.0) ? 1 : 0;
+  int has_body = (args.p.v[2] != 0.0 || args.p.v[3] != 0.0 || args.p.v[4] != 0.0) ? 1 : 0;
+  // diagnostic only (scripts/fused_ab.py): FOL_HEX_DIAG=nostore runs the kernel without its Ke bulk stores, which
+  // separates the compute / latency time of the kernel from its HBM write stream
+  static const bool nostore = [] { const char* v = std::getenv("FOL_HEX_DIAG"); return v && std::string(v) == "nostore"; }();
+  if (nostore) has_body |= 2;
   // persistent grid, optionally leaving room for communication kernels that must run concurrently
   int g = grid - g_grid_margin.load();
   if (g < 1) g = 1;

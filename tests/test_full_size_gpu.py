@@ -143,3 +143,87 @@ def test_fol_config3_full_size_batched_loss():
     assert np.abs(gk - gK).max() <= 1e-12 * np.abs(gK).max()
     energies = loss._energy_and_grads(K, loss.GetFullDofVector(None, u))[0][rows].cpu().numpy()
     assert np.abs(energies - Eb).max() <= 1e-12 * np.abs(Eb).max()
+
+
+def test_j2_config5_full_size_per_gpu():
+    """configs[4] at the per-GPU size of the 8-GPU partition (128^3 Hex8 with (ne, 8, 7) history, two load steps):
+    sampled elements against the oracle's literal 7-unknown replay (Ke, residual contributions, new history), the elastic
+    points' history bit-identical, yield consistency of every plastic point (sigma_eq = y(xi_new) within the Newton
+    tolerance), run-to-run bit-identity, tuned == generic kernel on the sample."""
+    from folax_b200.loss_functions import ElastoplasticityLoss3DHexa
+    from oracle import j2
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs a large-memory GPU")
+    mat = {"young_modulus": 3.0, "poisson_ratio": 0.3, "iso_hardening_parameter_1": 0.4, "iso_hardening_param_2": 10.0,
+           "yield_limit": 0.2}
+    mesh = folax_b200.perturb_interior_nodes(folax_b200.create_3D_box_mesh(N, N, N, 1.0, 1.0, 1.0), 0.1, 2)
+    bc = {d: {"left": 0.0, "right": 0.1} for d in ("Ux", "Uy", "Uz")}
+    loss = ElastoplasticityLoss3DHexa("c5", {"dirichlet_bc_dict": bc, "num_gp": 2, "material_dict": mat}, mesh)
+    loss.Initialize()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    K = torch.ones(loss._nn, dtype=torch.float64, device="cuda")
+    u1 = (0.02 / N) * torch.randn(loss.total_number_of_dofs, generator=g, device="cuda", dtype=torch.float64)
+    st0 = torch.zeros(loss.GetStateShape(), dtype=torch.float64, device="cuda")
+    st1, _, _ = loss.ComputeJacobianMatrixAndResidualVector(K, u1, st0)
+    u2 = 2.0 * u1
+    st2, jac, R = loss.ComputeJacobianMatrixAndResidualVector(K, u2, st1)
+    st2b, jac_b, Rb = loss.ComputeJacobianMatrixAndResidualVector(K, u2, st1)
+    assert torch.equal(jac.data, jac_b.data) and torch.equal(R, Rb) and torch.equal(st2, st2b)     # deterministic
+    del jac_b
+    plastic = st2[..., -1] > st1[..., -1]
+    frac = float(plastic.double().mean())
+    assert 0.2 < frac < 1.0, frac
+    assert torch.equal(st2[~plastic], st1[~plastic])                      # elastic points: history untouched, bit for bit
+    # sampled elements against the oracle
+    rng = np.random.default_rng(3)
+    conn = mesh.GetElementsNodes("hexahedron")
+    sample = np.unique(np.concatenate([rng.integers(0, len(conn), 60), [0, len(conn) - 1], np.arange(0, len(conn), N)[:6]]))
+    coords = np.asarray(mesh.GetNodesCoordinates())
+    dofs = assembly.element_dof_ids(conn[sample], 3)
+    uh = u2.cpu().numpy()
+    sidx = torch.as_tensor(sample, device="cuda")
+    _, st_ref, re_ref, Ke_ref = j2.j2_element("hexahedron", 2, coords[conn[sample]], uh[dofs], st1[sidx].cpu().numpy(),
+                                              mat["young_modulus"], mat["poisson_ratio"], mat["yield_limit"],
+                                              mat["iso_hardening_parameter_1"], mat["iso_hardening_param_2"])
+    bc_vec = np.ones(loss.total_number_of_dofs)
+    bc_vec[loss.dirichlet_indices] = 0.0
+    _, Ke_ref = assembly.apply_dirichlet(re_ref, Ke_ref, bc_vec[dofs], False)
+    got = jac.data.view(-1, 576)[sidx].cpu().numpy().reshape(Ke_ref.shape)
+    assert np.abs(got - Ke_ref).max() <= 1e-11 * np.abs(Ke_ref).max()
+    assert np.abs(st2[sidx].cpu().numpy() - st_ref).max() <= 1e-11 * np.abs(st_ref).max()
+    # tuned == generic kernel on a slice of elements (the generic kernel at 128^3 takes a while: 4096 elements)
+    lib = _lib.load()
+    sl = slice(N * N * 5, N * N * 5 + 4096)
+    sub = folax_b200.Mesh("", ".")
+    sub.node_ids, sub.nodes_coordinates = np.arange(len(coords)), coords
+    sub.elements_nodes = {"hexahedron": conn[sl]}
+    sub.node_sets = mesh.node_sets
+    lsub = ElastoplasticityLoss3DHexa("c5s", {"dirichlet_bc_dict": bc, "num_gp": 2, "material_dict": mat}, sub)
+    lsub.Initialize()
+    prev = lib.fol_set_tuned_kernels(0)
+    try:
+        st_g, jac_g, _ = lsub.ComputeJacobianMatrixAndResidualVector(K, u2, st1[sl])
+    finally:
+        lib.fol_set_tuned_kernels(prev)
+    blk = jac.data.view(-1, 576)[sl]
+    assert (blk.reshape(-1) - jac_g.data).abs().max().item() <= 1e-12 * jac_g.data.abs().max().item()
+    assert (st2[sl] - st_g).abs().max().item() <= 1e-13 * max(st_g.abs().max().item(), 1e-300)
+    # yield consistency of the kernel's own output on the sampled elements: sigma_eq(eps - eps_p_new) = y(xi_new) within
+    # the Newton stop tolerance (1e-6 on the residual norm) at every plastic point
+    del jac
+    from oracle.geometry import ELEMENTS, point_data
+    from oracle.losses import b_matrix
+    _, gradN, _, _ = point_data(ELEMENTS["hexahedron"], coords[conn[sample]], 2)
+    eps = np.einsum("egvn,en->egv", b_matrix(gradN), uh[dofs])                      # (ns, 8, 6), engineering shears
+    st_new = st2[sidx].cpu().numpy()
+    ee = eps - st_new[..., :6]                                                       # tensor components, shears unhalved
+    G = mat["young_modulus"] / (2.0 * (1.0 + mat["poisson_ratio"]))
+    dev = ee.copy()
+    dev[..., :3] -= ee[..., :3].mean(axis=-1, keepdims=True)
+    s_dev = 2.0 * G * dev
+    sig_eq = np.sqrt(1.5 * ((s_dev[..., :3] ** 2).sum(-1) + 2.0 * (s_dev[..., 3:] ** 2).sum(-1)))
+    y_new = mat["yield_limit"] + mat["iso_hardening_parameter_1"] * (1.0 - np.exp(-mat["iso_hardening_param_2"] * st_new[..., 6]))
+    pl = st_new[..., 6] > st1[sidx].cpu().numpy()[..., 6]
+    assert pl.sum() > 50
+    assert np.abs(sig_eq[pl] - y_new[pl]).max() <= 2e-6
+    assert (sig_eq[~pl] <= y_new[~pl] + 1e-12).all()                                 # elastic points are inside the surface
