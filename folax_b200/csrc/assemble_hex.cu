@@ -43,7 +43,19 @@ constexpr bool kSym = FOL_HEX_SYM != 0;         // tiles of P below the diagonal
 using hexk::kTile;
 using namespace hexk;
 
-struct __align__(128) WarpSmem {
+// LAYOUT 0: the round-1 layout (one Ke staging slot, (dN/dz, coefficient) pairs, double-buffered X / u / de).
+// LAYOUT 1: compact -- dN/dz and the coefficient stored separately (the coefficient is per Gauss point, not per node),
+//           X / de single-buffered (phase 1 consumes them; the next gather is issued right after it), byte Dirichlet
+//           flags -- which makes room for a SECOND Ke staging slot at the same 12 warps / SM: the bulk copy of element
+//           i can take until element i + 2 needs the slot, instead of stalling the warp when the write queue is deep
+//           Measured: no gain (profiles/r2/hex_kernel_experiments.md) -- what the stores cost under sustained load is
+//           board power, not slot waits.  Kept selectable (FOL_HEX_LAYOUT=1) for A/B runs; layout 0 is the default.
+template <int LAYOUT>
+struct __align__(128) WarpSmemT;
+
+template <>
+struct __align__(128) WarpSmemT<0> {
+  static constexpr int kStage = kSlots;
   double stage[kSlots][576];         // Ke staging slots (bulk-copy sources)
   // [element][gauss][node ^ swz(gauss)]: (dN/dx, dN/dy) and (dN/dz, w detJ E_g).  The XOR swizzle
   // swz(g) = ((g & 3) << 1) | (g >> 2) makes both the phase-1 stores (lane = row) and the DMMA
@@ -59,11 +71,36 @@ struct __align__(128) WarpSmem {
   float bc[kTile][24];               // 1 = free dof, 0 = Dirichlet dof
 };
 
+template <>
+struct __align__(128) WarpSmemT<1> {
+  static constexpr int kStage = 2;
+  double stage[2][576];              // two Ke staging slots
+  double2 gxy[kTile][8][8];          // [element][gauss][node ^ swz(gauss)]: (dN/dx, dN/dy)
+  double gz[kTile][8][8];            // [element][gauss][node ^ swz(gauss) ^ 2 (element & 1)]: dN/dz (8-byte accesses are
+                                     //   served per half-warp = two elements: the element bit keeps them on distinct banks)
+  double coef[kTile * 8];            // w detJ E_g per (element, gauss)
+  double X[3][32];                   // single-buffered
+  double u[2][3][32];                // double-buffered: phase 2 of this tile still reads it while the next lands
+  double de[32];                     // single-buffered
+  double wd[kTile][8];
+  uint8_t bc[kTile][24];             // 1 = free dof, 0 = Dirichlet dof
+};
+static_assert(2 * (sizeof(WarpSmemT<1>) * kWarps + 1024) <= 227 * 1024, "compact layout: two CTAs per SM must fit");
+
 }  // namespace
 
-template <bool FUSE>
+namespace {
+__device__ __forceinline__ double sm_x(const WarpSmemT<0>& sm, int buf, int i, int k) { return sm.X[buf][i][k]; }
+__device__ __forceinline__ double sm_x(const WarpSmemT<1>& sm, int, int i, int k) { return sm.X[i][k]; }
+__device__ __forceinline__ double sm_de(const WarpSmemT<0>& sm, int buf, int k) { return sm.de[buf][k]; }
+__device__ __forceinline__ double sm_de(const WarpSmemT<1>& sm, int, int k) { return sm.de[k]; }
+}  // namespace
+
+template <bool FUSE, int LAYOUT>
 __global__ void __launch_bounds__(kWarps * 32)
 assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles, const int has_body, const HaloFuse hf) {
+  using WarpSmem = WarpSmemT<LAYOUT>;
+  constexpr int kStage = WarpSmem::kStage;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
@@ -124,11 +161,17 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
   auto gather_async = [&](int buf, long long n) {
     const double* px = args.xyz + n * 3;
     const double* pu = args.u + n * 3;
-    cp_async8(&sm.X[buf][0][lane], px); cp_async8(&sm.X[buf][1][lane], px + 1); cp_async8(&sm.X[buf][2][lane], px + 2);
+    if constexpr (LAYOUT == 0) {
+      cp_async8(&sm.X[buf][0][lane], px); cp_async8(&sm.X[buf][1][lane], px + 1); cp_async8(&sm.X[buf][2][lane], px + 2);
+      cp_async8(&sm.de[buf][lane], args.ctrl + n);
+    } else {
+      cp_async8(&sm.X[0][lane], px); cp_async8(&sm.X[1][lane], px + 1); cp_async8(&sm.X[2][lane], px + 2);
+      cp_async8(&sm.de[lane], args.ctrl + n);
+    }
     cp_async8(&sm.u[buf][0][lane], pu); cp_async8(&sm.u[buf][1][lane], pu + 1); cp_async8(&sm.u[buf][2][lane], pu + 2);
-    cp_async8(&sm.de[buf][lane], args.ctrl + n);
     cp_async_commit();
   };
+
   // Dirichlet flags of the next tile's node: three byte loads kept in three registers, consumed one
   // tile later (packing them right away would stall on the load latency)
   int n_next = node_of(vt + nwarps);
@@ -143,17 +186,20 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
     hold_back(n_next, f0, f1, f2);   // loaded one tile ago; nothing may consume them before this point
 
     // ---- phase 0: this tile's nodal data has landed in shared memory; start the next gather
-    sm.bc[el_p][sub * 3 + 0] = f0 ? 0.f : 1.f;
-    sm.bc[el_p][sub * 3 + 1] = f1 ? 0.f : 1.f;
-    sm.bc[el_p][sub * 3 + 2] = f2 ? 0.f : 1.f;
+    sm.bc[el_p][sub * 3 + 0] = f0 ? 0 : 1;
+    sm.bc[el_p][sub * 3 + 1] = f1 ? 0 : 1;
+    sm.bc[el_p][sub * 3 + 2] = f2 ? 0 : 1;
     cp_async_wait_all();
     __syncwarp();
-    gather_async(buf ^ 1, (long long)n_next);               // in flight during this tile
-    {
+    // the next tile's gather (and its Dirichlet flags / the node ids two tiles ahead): in flight during this tile.
+    // LAYOUT 1 single-buffers X / de, which phase 1 still reads: there it is issued right after phase 1.
+    auto issue_next = [&]() {
+      gather_async(buf ^ 1, (long long)n_next);
       const uint8_t* pf = args.dir + (long long)n_next * 3;
       f0 = __ldg(pf); f1 = __ldg(pf + 1); f2 = __ldg(pf + 2);
-    }
-    n_next = node_of(vt + 2 * nwarps);
+      n_next = node_of(vt + 2 * nwarps);
+    };
+    if constexpr (LAYOUT == 0) issue_next();
 
     // ---- phase 1: lane (element, Gauss point): J, det J, grad N, coefficient (geometry.py:88-97)
     {
@@ -164,7 +210,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
           const int bx = ((a & 3) == 1 || (a & 3) == 2), by = (a >> 1) & 1, bz = (a >> 2) & 1;
-          const double x = sm.X[buf][i][el_p * 8 + a];
+          const double x = sm_x(sm, buf, i, el_p * 8 + a);
           j0 += (bx ? x : -x) * fyz[by][bz];
           j1 += (by ? x : -x) * fxz[bx][bz];
           j2 += (bz ? x : -x) * fxy[bx][by];
@@ -188,7 +234,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
 #pragma unroll
       for (int a = 0; a < 8; ++a) {
         const int bx = ((a & 3) == 1 || (a & 3) == 2), by = (a >> 1) & 1, bz = (a >> 2) & 1;
-        eg += fx[bx] * fyz[by][bz] * sm.de[buf][el_p * 8 + a];
+        eg += fx[bx] * fyz[by][bz] * sm_de(sm, buf, el_p * 8 + a);
       }
       const double wd = det;  // Gauss weight is 1
       const double coef = wd * eg;
@@ -202,11 +248,14 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
 #pragma unroll
         for (int k = 0; k < 3; ++k) g[k] = d0 * inv[0][k] + d1 * inv[1][k] + d2 * inv[2][k];
         sm.gxy[el_p][sub][a ^ swz_p] = make_double2(g[0], g[1]);
-        sm.gzs[el_p][sub][a ^ swz_p] = make_double2(g[2], coef);
+        if constexpr (LAYOUT == 0) sm.gzs[el_p][sub][a ^ swz_p] = make_double2(g[2], coef);
+        else sm.gz[el_p][sub][a ^ swz_p ^ ((el_p & 1) << 1)] = g[2];
       }
+      if constexpr (LAYOUT == 1) sm.coef[lane] = coef;
       sm.wd[el_p][sub] = wd;
     }
     __syncwarp();
+    if constexpr (LAYOUT == 1) issue_next();   // X / de of this tile are consumed
 
     // ---- phase 2: one element at a time, lane (a, k)
 #pragma unroll 1
@@ -222,7 +271,13 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
         const double2 xy = sm.gxy[el][4 * kk + kq][ra ^ ((kq << 1) | kk)];
-        const double2 zs = sm.gzs[el][4 * kk + kq][ra ^ ((kq << 1) | kk)];
+        double2 zs;
+        if constexpr (LAYOUT == 0) {
+          zs = sm.gzs[el][4 * kk + kq][ra ^ ((kq << 1) | kk)];
+        } else {
+          zs.x = sm.gz[el][4 * kk + kq][ra ^ ((kq << 1) | kk) ^ ((el & 1) << 1)];
+          zs.y = sm.coef[el * 8 + 4 * kk + kq];
+        }
         const double bf[3] = {xy.x, xy.y, zs.x};
         const double af[3] = {zs.y * xy.x, zs.y * xy.y, zs.y * zs.x};
 #pragma unroll
@@ -285,10 +340,9 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
       }
       // stage the rows and hand them to the bulk-copy engine.  The Dirichlet row mask
       // (fe_loss.py:191-207) only matters for elements touching a fixed dof: warp-uniform test.
-      const bool fixed_rows = (sm.bc[el][ra * 3 + 0] == 0.f) | (sm.bc[el][ra * 3 + 1] == 0.f) |
-                              (sm.bc[el][ra * 3 + 2] == 0.f);
+      const bool fixed_rows = (sm.bc[el][ra * 3 + 0] == 0) | (sm.bc[el][ra * 3 + 1] == 0) | (sm.bc[el][ra * 3 + 2] == 0);
       const bool any_fixed = __any_sync(0xffffffffu, fixed_rows);
-      double* const slot = sm.stage[kSlots > 1 ? (el & (kSlots - 1)) : 0];
+      double* const slot = sm.stage[kStage > 1 ? (el & (kStage - 1)) : 0];
       auto write_rows = [&]() {
         if (!any_fixed) {
 #pragma unroll
@@ -302,7 +356,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             const int row = ra * 3 + i;
-            const bool freerow = sm.bc[el][row] != 0.f;
+            const bool freerow = sm.bc[el][row] != 0;
             double v[6];
 #pragma unroll
             for (int h = 0; h < 2; ++h)
@@ -322,7 +376,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
         if (kq == 0) {
 #pragma unroll
           for (int i = 0; i < 3; ++i)
-            args.re[e * 24 + ra * 3 + i] = (any_fixed && sm.bc[el][ra * 3 + i] == 0.f) ? 0.0 : r[i];
+            args.re[e * 24 + ra * 3 + i] = (any_fixed && sm.bc[el][ra * 3 + i] == 0) ? 0.0 : r[i];
         }
       };
       if constexpr (kHalves) {
@@ -342,7 +396,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
         __syncwarp();
         if (lane == 0) bulk_store(args.ke + e * 576 + 288, slot + 288, 288 * sizeof(double));
       } else {
-        if (lane == 0) bulk_wait_read<kSlots - 1>();   // the copy that last used this slot has drained it
+        if (lane == 0) bulk_wait_read<kStage - 1>();   // the copy that last used this slot has drained it
         __syncwarp();
         write_rows();
         fence_async_smem();
@@ -365,12 +419,12 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
 
 std::atomic<int> g_grid_margin{0};
 
-int assemble_hex_mech_f64(cudaStream_t s, const AsmArgs<double>& args, const HaloFuse* hf) {
-  static PerDeviceGrid per_device, per_device_fused;
-  const size_t smem = sizeof(WarpSmem) * kWarps;
+template <bool FUSE, int LAYOUT>
+static int launch_hex(cudaStream_t s, const AsmArgs<double>& args, const HaloFuse* hf) {
+  static PerDeviceGrid per_device;
+  const size_t smem = sizeof(WarpSmemT<LAYOUT>) * kWarps;
   int grid = 0;
-  if (hf) FOL_CUDA(per_device_fused.get(assemble_hex_mech_f64_kernel<true>, kWarps * 32, smem, &grid));
-  else FOL_CUDA(per_device.get(assemble_hex_mech_f64_kernel<false>, kWarps * 32, smem, &grid));
+  FOL_CUDA(per_device.get(assemble_hex_mech_f64_kernel<FUSE, LAYOUT>, kWarps * 32, smem, &grid));
   if (args.ne == 0) return FOL_OK;
   const long long ntiles = cdiv(args.ne, kTile);
   const long long want = cdiv(ntiles, kWarps);
@@ -383,9 +437,16 @@ int assemble_hex_mech_f64(cudaStream_t s, const AsmArgs<double>& args, const Hal
   int g = grid - g_grid_margin.load();
   if (g < 1) g = 1;
   const unsigned blocks = (unsigned)(want < g ? want : g);
-  if (hf) assemble_hex_mech_f64_kernel<true><<<blocks, kWarps * 32, smem, s>>>(args, ntiles, has_body, *hf);
-  else assemble_hex_mech_f64_kernel<false><<<blocks, kWarps * 32, smem, s>>>(args, ntiles, has_body, HaloFuse{});
+  assemble_hex_mech_f64_kernel<FUSE, LAYOUT><<<blocks, kWarps * 32, smem, s>>>(args, ntiles, has_body, hf ? *hf : HaloFuse{});
   return check_launch("assemble_hex_mech_f64_kernel");
+}
+
+int assemble_hex_mech_f64(cudaStream_t s, const AsmArgs<double>& args, const HaloFuse* hf) {
+  // FOL_HEX_LAYOUT=1 selects the compact shared-memory layout with two staging slots (A/B runs; measured equal to
+  // layout 0 under sustained load and not better in the first steps: profiles/r2/hex_kernel_experiments.md)
+  static const int layout = [] { const char* v = std::getenv("FOL_HEX_LAYOUT"); return v ? std::atoi(v) : 0; }();
+  if (layout == 0) return hf ? launch_hex<true, 0>(s, args, hf) : launch_hex<false, 0>(s, args, hf);
+  return hf ? launch_hex<true, 1>(s, args, hf) : launch_hex<false, 1>(s, args, hf);
 }
 
 }  // namespace fol
