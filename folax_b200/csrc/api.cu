@@ -23,6 +23,7 @@ int assemble_j2_f32(cudaStream_t, int, int, const AsmArgs<float>&);
 namespace hexk { struct HaloFuse; }
 int assemble_hex_mech_f64(cudaStream_t, const AsmArgs<double>&, const hexk::HaloFuse* = nullptr);
 int assemble_hex_j2_f64(cudaStream_t, const AsmArgs<double>&, const hexk::HaloFuse* = nullptr);
+int assemble_hex_mech_f32(cudaStream_t, const AsmArgs<float>&);
 template <class T>
 int assemble_ad(cudaStream_t, int, int, int, const AdAsmArgs<T>&);
 extern std::atomic<int> g_grid_margin;
@@ -73,6 +74,10 @@ static int assemble_typed(cudaStream_t s, int physics, int element, int num_gp, 
         if (element == HEX && num_gp == 2 && !transpose && !v && g_tuned.load()) return assemble_hex_mech_f64(s, a);
         return assemble_mech_f64(s, element, num_gp, a);
       } else {
+        if (element == HEX && num_gp == 2 && !transpose && !v && g_tuned.load()) {
+          const int rc = assemble_hex_mech_f32(s, a);     // 1 = not applicable (unaligned output): generic kernel
+          if (rc != 1) return rc;
+        }
         return assemble_mech_f32(s, element, num_gp, a);
       }
     case FOL_THERMAL:

@@ -65,7 +65,7 @@ bc3 = {d: {"left": 0.0, "right": 0.1} for d in ("Ux", "Uy", "Uz")}
 bc2 = {d: {"left": 0.0, "right": 0.1} for d in ("Ux", "Uy")}
 small = lambda x: 0.01 * x
 hex128 = folax_b200.create_3D_box_mesh(128, 128, 128, 1.0, 1.0, 1.0)
-case("hex128_mech_f32_generic", lf.MechanicalLoss3DHexa, hex128, "hexahedron", {"dirichlet_bc_dict": bc3, "material_dict": MAT}, "float32", small)
+case("hex128_mech_f32", lf.MechanicalLoss3DHexa, hex128, "hexahedron", {"dirichlet_bc_dict": bc3, "material_dict": MAT}, "float32", small)
 case("hex128_thermal_f64", lf.ThermalLoss3DHexa, hex128, "hexahedron", {"dirichlet_bc_dict": {"T": {"left": 1.0, "right": 0.1}}}, "float64", lambda x: 0.5 + 0.1 * x)
 del hex128
 quad = folax_b200.create_2D_square_mesh(1.0, 2049)

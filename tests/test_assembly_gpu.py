@@ -170,3 +170,44 @@ def test_tuned_hex_kernel_matches_oracle_and_generic(shape, body):
         _close(out[tuned][2], dataT, 1e-12)
     masked = np.isin(idx[:, 0], loss.dirichlet_indices) & (idx[:, 0] != idx[:, 1])
     assert not out[1][0][masked].any()
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (5, 3, 3), (7, 6, 5), (16, 9, 11)])
+@pytest.mark.parametrize("body", [None, [0.3, -0.2, 0.1]])
+def test_tuned_hex_f32_kernel_matches_oracle_and_generic(shape, body):
+    """The float32 tuned kernel (assemble_hex_f32.cu) against the float64 oracle at north_star's float32 tolerance
+    (1e-5, norm-wise) and against the generic float32 kernel, including ragged tiles and exact zeros in masked rows."""
+    import folax_b200
+    from folax_b200 import _lib
+    from folax_b200.loss_functions import MechanicalLoss3DHexa
+    mesh = folax_b200.create_3D_box_mesh(*shape, 1.0, 0.8, 1.1)
+    if min(shape) > 1:
+        folax_b200.perturb_interior_nodes(mesh, 0.25, seed=sum(shape))
+    settings = {"dirichlet_bc_dict": {d: {"left": 0.0, "right": 0.1} for d in ("Ux", "Uy", "Uz")},
+                "material_dict": dict(H.MATERIAL), "dtype": "float32"}
+    if body:
+        settings["body_foce"] = body
+    loss = MechanicalLoss3DHexa("tuned32", settings, mesh)
+    loss.Initialize()
+    K, u = H.fields("mechanical", mesh, loss, seed=11)
+    K32, u32 = K.astype(np.float32), u.astype(np.float32)
+    lib = _lib.load()
+    out = {}
+    for tuned in (1, 0):
+        prev = lib.fol_set_tuned_kernels(tuned)
+        try:
+            jac, R = loss.ComputeJacobianMatrixAndResidualVector(K32, u32)
+            out[tuned] = (jac.data.cpu().numpy().astype(np.float64), R.cpu().numpy().astype(np.float64))
+        finally:
+            lib.fol_set_tuned_kernels(prev)
+    coords32 = np.asarray(mesh.GetNodesCoordinates()).astype(np.float32).astype(np.float64)
+    data, idx, Rref = assembly.assemble("mechanical", "hexahedron", 2, coords32, mesh.GetElementsNodes("hexahedron"),
+                                        K32.astype(np.float64), u32.astype(np.float64), loss.dirichlet_indices,
+                                        H.oracle_params(loss))
+    assert np.array_equal(jac.indices.cpu().numpy(), idx)
+    for tuned in (1, 0):
+        _close(out[tuned][0], data, 1e-5)
+        _close(out[tuned][1], Rref, 4e-5)
+    _close(out[1][0], out[0][0], 2e-6)                       # the two float32 kernels agree far inside the tolerance
+    masked = np.isin(idx[:, 0], loss.dirichlet_indices) & (idx[:, 0] != idx[:, 1])
+    assert not out[1][0][masked].any()
