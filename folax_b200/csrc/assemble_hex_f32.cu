@@ -3,13 +3,14 @@
 // (1e-5) as a first-class precision next to float64; the generic kernel reached 0.40 of the HBM roofline there.
 //
 // Same machine mapping as assemble_hex.cu -- persistent warps, tiles of 4 consecutive elements, cp.async gathers one
-// tile ahead, one bulk (TMA-engine) copy per element matrix -- with the float64 tensor-path product replaced by plain
-// FFMA (there is no fp32-accurate tensor path: TF32 keeps 10 mantissa bits):
+// tile ahead, one bulk (TMA-engine) copy per element matrix -- with the float64 DMMA product replaced by 3xTF32
+// tensor-core products (each fp32 operand split into a tf32 head and a tf32 tail; hi*hi + hi*lo + lo*hi accumulated in
+// fp32 recovers fp32-grade products, which one TF32 pass -- 10 mantissa bits -- would not):
 //   * phase 1, lane (element, Gauss point): J, det J, grad N, coefficient in float32; staged per (element, point, node)
 //     as ONE float4 (dN/dx, dN/dy, dN/dz, w detJ E_g), XOR-swizzled like the float64 kernel (16-byte cells, 128-byte rows);
-//   * phase 2, lane (row node a, column pair k): P = sum_g s_g g_a (x) g_b for its 3x3 blocks (a, 2k), (a, 2k+1):
-//     per Gauss point three LDS.128 (row node: 8 distinct cells of one row; column nodes: broadcast) and 18 FFMA;
-//     Ke = lam P + mu P^T + mu tr(P) I, re = Ke u - Fe (butterfly over the 4 k-lanes), Dirichlet mask in registers;
+//   * phase 2, lane (row node a, column pair k): P = sum_g s_g v_g v_g^T as 6 m16n8k8 tile positions x 3 split terms =
+//     18 mma.sync per element, fed from two LDS.128 per lane; the accumulator fragment is the lane's 3x3 blocks
+//     (a, 2k), (a, 2k+1); Ke = lam P + mu P^T + mu tr(P) I, re = Ke u - Fe (butterfly over the 4 k-lanes), Dirichlet mask in registers;
 //   * the 2304-byte element matrix is staged in shared memory and leaves as one cp.async.bulk.
 // Algorithmic bytes: 2376 B/element (2304 Ke + 32 conn + 28 nodal in + 12 residual out).
 #include "assemble.cuh"
@@ -43,6 +44,19 @@ __device__ __forceinline__ void bulk_store_f(float* gdst, const float* ssrc, uns
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(saddr), "r"(bytes)
                : "memory");
   asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+
+// float -> (hi, lo) tf32 pair: x = hi + lo to ~2^-21 relative (3xTF32: hi*hi + hi*lo + lo*hi recovers fp32-grade products
+// on the tensor path; the lo*lo term is below fp32 rounding)
+__device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  const float rest = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
 }  // namespace
@@ -181,26 +195,40 @@ assemble_hex_mech_f32_kernel(const AsmArgs<float> args, const long long ntiles, 
     for (int el = 0; el < kTile; ++el) {
       const long long e = e0 + el;
       if (e >= args.ne) break;
+      // P = sum_g s_g v_g v_g^T (24 x 24 x 8) on the tensor path with fp32-grade accuracy (3xTF32): rows ordered
+      // m = 8 * dim + node, so an m16n8k8 tile covers dims (0, 1) of the 8 row nodes against one dim of the 8 column
+      // nodes and a second tile covers dim 2 (upper half unused); its accumulator fragment of lane (a, k) is exactly the
+      // 3x3 blocks (a, 2k), (a, 2k + 1).  The lane feeds ONLY its own node a at Gauss points k and k + 4 (two LDS.128).
       float c[3][3][2];
+      {
+        const float4 g0 = sm.g[el][kq][ra ^ (kq << 1)];                 // swz(g) = ((g & 3) << 1) | (g >> 2)
+        const float4 g1 = sm.g[el][4 + kq][ra ^ ((kq << 1) | 1)];
+        const float bv[3][2] = {{g0.x, g1.x}, {g0.y, g1.y}, {g0.z, g1.z}};
+        unsigned ahi[3][2], alo[3][2], bhi[3][2], blo[3][2];
 #pragma unroll
-      for (int t = 0; t < 3; ++t)
+        for (int t = 0; t < 3; ++t) {
+          split_tf32(g0.w * bv[t][0], ahi[t][0], alo[t][0]);
+          split_tf32(g1.w * bv[t][1], ahi[t][1], alo[t][1]);
+          split_tf32(bv[t][0], bhi[t][0], blo[t][0]);
+          split_tf32(bv[t][1], bhi[t][1], blo[t][1]);
+        }
+        // A fragments: a0 (row a, k), a1 (row a + 8, k), a2 (row a, k + 4), a3 (row a + 8, k + 4)
+        const unsigned A01h[4] = {ahi[0][0], ahi[1][0], ahi[0][1], ahi[1][1]}, A01l[4] = {alo[0][0], alo[1][0], alo[0][1], alo[1][1]};
+        const unsigned A2h[4] = {ahi[2][0], 0u, ahi[2][1], 0u}, A2l[4] = {alo[2][0], 0u, alo[2][1], 0u};
 #pragma unroll
-        for (int s = 0; s < 3; ++s) c[t][s][0] = c[t][s][1] = 0.f;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const int sw = ((g & 3) << 1) | (g >> 2);
-        const float4 ar = sm.g[el][g][ra ^ sw];
-        const float4 b0 = sm.g[el][g][(2 * kq) ^ sw];
-        const float4 b1 = sm.g[el][g][(2 * kq + 1) ^ sw];
-        const float af[3] = {ar.w * ar.x, ar.w * ar.y, ar.w * ar.z};
-        const float bf0[3] = {b0.x, b0.y, b0.z}, bf1[3] = {b1.x, b1.y, b1.z};
-#pragma unroll
-        for (int t = 0; t < 3; ++t)
-#pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            c[t][s][0] += af[t] * bf0[s];
-            c[t][s][1] += af[t] * bf1[s];
-          }
+        for (int s = 0; s < 3; ++s) {
+          const unsigned Bh[2] = {bhi[s][0], bhi[s][1]}, Bl[2] = {blo[s][0], blo[s][1]};
+          float d01[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+          mma_tf32(d01, A01l, Bh);      // small terms first
+          mma_tf32(d01, A01h, Bl);
+          mma_tf32(d01, A01h, Bh);
+          mma_tf32(d2, A2l, Bh);
+          mma_tf32(d2, A2h, Bl);
+          mma_tf32(d2, A2h, Bh);
+          c[0][s][0] = d01[0]; c[0][s][1] = d01[1];
+          c[1][s][0] = d01[2]; c[1][s][1] = d01[3];
+          c[2][s][0] = d2[0];  c[2][s][1] = d2[1];
+        }
       }
       // Ke blocks (a, 2k) and (a, 2k+1): lam P + mu P^T + mu tr(P) I  (B^T D B of an isotropic D)
       float K[2][3][3];
@@ -242,22 +270,32 @@ assemble_hex_mech_f32_kernel(const AsmArgs<float> args, const long long ntiles, 
       const bool any_fixed = __any_sync(0xffffffffu, fixed_rows);
       if (lane == 0) bulk_wait_read<0>();   // the copy that last used the staging slot has drained it
       __syncwarp();
+      if (!any_fixed) {
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int row = ra * 3 + i;
-        const bool freerow = !any_fixed || sm.bc[el][row] != 0;
-        float v[6];
+        for (int i = 0; i < 3; ++i) {
+          float2* dst = reinterpret_cast<float2*>(sm.stage + (ra * 3 + i) * 24 + kq * 6);
+          dst[0] = make_float2(K[0][i][0], K[0][i][1]);
+          dst[1] = make_float2(K[0][i][2], K[1][i][0]);
+          dst[2] = make_float2(K[1][i][1], K[1][i][2]);
+        }
+      } else {
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int i = 0; i < 3; ++i) {
+          const int row = ra * 3 + i;
+          const bool freerow = sm.bc[el][row] != 0;
+          float v[6];
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const int col = (2 * kq + h) * 3 + j;
-            v[h * 3 + j] = (freerow || col == row) ? K[h][i][j] : 0.f;
-          }
-        float2* dst = reinterpret_cast<float2*>(sm.stage + row * 24 + kq * 6);
-        dst[0] = make_float2(v[0], v[1]);
-        dst[1] = make_float2(v[2], v[3]);
-        dst[2] = make_float2(v[4], v[5]);
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const int col = (2 * kq + h) * 3 + j;
+              v[h * 3 + j] = (freerow || col == row) ? K[h][i][j] : 0.f;
+            }
+          float2* dst = reinterpret_cast<float2*>(sm.stage + row * 24 + kq * 6);
+          dst[0] = make_float2(v[0], v[1]);
+          dst[1] = make_float2(v[2], v[3]);
+          dst[2] = make_float2(v[4], v[5]);
+        }
       }
       fence_async_smem();
       __syncwarp();
