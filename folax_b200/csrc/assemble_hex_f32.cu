@@ -11,7 +11,7 @@
 //   * phase 2, lane (row node a, column pair k): P = sum_g s_g v_g v_g^T as 6 m16n8k8 tile positions x 3 split terms =
 //     18 mma.sync per element, fed from two LDS.128 per lane; the accumulator fragment is the lane's 3x3 blocks
 //     (a, 2k), (a, 2k+1); Ke = lam P + mu P^T + mu tr(P) I, re = Ke u - Fe (butterfly over the 4 k-lanes), Dirichlet mask in registers;
-//   * the 2304-byte element matrix is staged in shared memory and leaves as one cp.async.bulk.
+//   * the 2304-byte element matrix is staged in one of two shared-memory slots and leaves as one cp.async.bulk.
 // Algorithmic bytes: 2376 B/element (2304 Ke + 32 conn + 28 nodal in + 12 residual out).
 #include "assemble.cuh"
 #include "assemble_hex_common.cuh"
@@ -25,7 +25,8 @@ using namespace hexk;
 constexpr int kWarpsF = 8;           // warps per CTA, each fully independent (2 CTAs = 16 warps / SM)
 
 struct __align__(128) WarpSmemF {
-  float stage[576];                  // Ke staging slot (bulk-copy source), 2304 B
+  float stage[2][576];               // two Ke staging slots (bulk-copy sources), 2304 B each: the copy of element i may
+                                     // drain until element i + 2 needs its slot
   float4 g[kTile][8][8];             // [element][gauss][node ^ swz(gauss)]: (dN/dx, dN/dy, dN/dz, w detJ E_g)
   float X[2][3][32];                 // nodal data of the tile, SoA over the 32 (element, node) lanes, double-buffered
   float u[2][3][32];
@@ -48,10 +49,13 @@ __device__ __forceinline__ void bulk_store_f(float* gdst, const float* ssrc, uns
 
 // float -> (hi, lo) tf32 pair: x = hi + lo to ~2^-21 relative (3xTF32: hi*hi + hi*lo + lo*hi recovers fp32-grade products
 // on the tensor path; the lo*lo term is below fp32 rounding)
+// (round-to-nearest, ties away, done on the bit pattern: add half an ulp of the 10-bit mantissa and clear the 13 low
+// bits -- what cvt.rna.tf32.f32 computes for finite values, in 2 integer instructions instead of the ~6 the compiler
+// emits for the cvt on sm_100a, which showed as a quarter of the kernel's instructions)
+__device__ __forceinline__ unsigned round_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float rest = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rest));
+  hi = round_tf32(x);
+  lo = round_tf32(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -268,12 +272,13 @@ assemble_hex_mech_f32_kernel(const AsmArgs<float> args, const long long ntiles, 
       // Dirichlet row mask (fe_loss.py:191-207): only for elements touching a fixed dof (warp-uniform test)
       const bool fixed_rows = (sm.bc[el][ra * 3 + 0] == 0) | (sm.bc[el][ra * 3 + 1] == 0) | (sm.bc[el][ra * 3 + 2] == 0);
       const bool any_fixed = __any_sync(0xffffffffu, fixed_rows);
-      if (lane == 0) bulk_wait_read<0>();   // the copy that last used the staging slot has drained it
+      float* const slot = sm.stage[el & 1];
+      if (lane == 0) bulk_wait_read<1>();   // the copy that last used THIS slot (two elements ago) has drained it
       __syncwarp();
       if (!any_fixed) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          float2* dst = reinterpret_cast<float2*>(sm.stage + (ra * 3 + i) * 24 + kq * 6);
+          float2* dst = reinterpret_cast<float2*>(slot + (ra * 3 + i) * 24 + kq * 6);
           dst[0] = make_float2(K[0][i][0], K[0][i][1]);
           dst[1] = make_float2(K[0][i][2], K[1][i][0]);
           dst[2] = make_float2(K[1][i][1], K[1][i][2]);
@@ -291,7 +296,7 @@ assemble_hex_mech_f32_kernel(const AsmArgs<float> args, const long long ntiles, 
               const int col = (2 * kq + h) * 3 + j;
               v[h * 3 + j] = (freerow || col == row) ? K[h][i][j] : 0.f;
             }
-          float2* dst = reinterpret_cast<float2*>(sm.stage + row * 24 + kq * 6);
+          float2* dst = reinterpret_cast<float2*>(slot + row * 24 + kq * 6);
           dst[0] = make_float2(v[0], v[1]);
           dst[1] = make_float2(v[2], v[3]);
           dst[2] = make_float2(v[4], v[5]);
@@ -299,7 +304,7 @@ assemble_hex_mech_f32_kernel(const AsmArgs<float> args, const long long ntiles, 
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) bulk_store_f(args.ke + e * 576, sm.stage, 576 * sizeof(float));
+      if (lane == 0) bulk_store_f(args.ke + e * 576, slot, 576 * sizeof(float));
       if (kq == 0) {
 #pragma unroll
         for (int i = 0; i < 3; ++i)
