@@ -64,7 +64,7 @@ CLASSES = {("neohooke_ad", "hexahedron"): nh_ad.NeoHookeMechanicalLoss3DHexa, ("
 
 @pytest.mark.parametrize("law", ["neohooke_ad", "stvenant_ad"])
 @pytest.mark.parametrize("etype", ["hexahedron", "tetra", "quad", "triangle"])
-@pytest.mark.parametrize("dtype,tol", [("float64", 1e-11), ("float32", 2e-4)])
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-11), ("float32", 1e-5)])
 def test_mesh_assembly_against_oracle(law, etype, dtype, tol):
     mesh = gh.make_mesh(etype, 3, perturb=0.2, seed=4)
     dofs = gh.dofs_of("mechanical", etype)
@@ -78,6 +78,11 @@ def test_mesh_assembly_against_oracle(law, etype, dtype, tol):
     nn = len(coords)
     rng = np.random.default_rng(8)
     K, u = rng.uniform(0.2, 1.0, nn), 0.03 * rng.standard_normal(nn * d)
+    if dtype == "float32":
+        # north_star's float32 bar (1e-5) is about the ARITHMETIC: the oracle gets the inputs the kernel gets, i.e. the
+        # float32 roundings of coordinates, controls and dofs (measured 3-4e-7; against un-rounded inputs the input
+        # rounding alone is 1e-4 for these finite-strain laws, which is what the earlier 2e-4 tolerance absorbed)
+        coords, K, u = (x.astype(np.float32).astype(np.float64) for x in (coords, K, u))
     g = assembly.element_dof_ids(conn, d)
     bc = np.ones(nn * d)
     bc[loss.dirichlet_indices] = 0.0
