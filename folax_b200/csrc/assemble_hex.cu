@@ -97,7 +97,7 @@ __device__ __forceinline__ double sm_de(const WarpSmemT<1>& sm, int, int k) { re
 }  // namespace
 
 template <bool FUSE, int LAYOUT>
-__global__ void __launch_bounds__(kWarps * 32, 2)   // two CTAs per SM: <= 168 registers
+__global__ void __launch_bounds__(kWarps * 32)
 assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles, const int has_body, const HaloFuse hf) {
   using WarpSmem = WarpSmemT<LAYOUT>;
   constexpr int kStage = WarpSmem::kStage;
@@ -108,17 +108,9 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
   // vt: position in the visiting order (interface layers first when FUSE), tile: the tile itself
   long long vt = (long long)blockIdx.x * kWarps + warp;
   if (vt >= ntiles) return;
-  // (32-bit arithmetic: the visiting-order map runs three times per tile; in 64 bits it cost 90 instructions per tile,
-  // 6.5 % of the kernel -- profiles/r2/fused_vs_plain_ncu.md)
-  const int nt32 = (int)ntiles, tl32 = (int)hf.tiles_lo, th32 = (int)hf.tiles_hi;
   auto real_tile = [&](long long v) -> long long {
-    if constexpr (FUSE) {
-      const int iv = (int)v;
-      if (v >= ntiles) return v;
-      return iv < tl32 ? iv : (iv < tl32 + th32 ? nt32 - th32 + (iv - tl32) : iv - th32);
-    } else {
-      return v;
-    }
+    if constexpr (FUSE) return v < ntiles ? halo_real_tile(hf, v, ntiles) : v;
+    else return v;
   };
   bool push_done = !FUSE;
 
@@ -150,7 +142,8 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
   // The id comes back through a predicated load straight into its 32-bit register and is widened only where it is
   // used, one tile later (hold_back below): any earlier dependent instruction -- a select, a sign extension --
   // would make the warp sit out the full DRAM latency of the connectivity load (21 % of the stall samples before).
-  auto node_of = [&](long long t) -> int {   // t: a real tile index (>= ntiles: no tile)
+  auto node_of = [&](long long v) -> int {
+    const long long t = real_tile(v);
     const long long e = t * kTile + el_p;
     const int ok = (t < ntiles && e < args.ne) ? 1 : 0;
     const int32_t* src = args.conn + (ok ? e * 8 + sub : 0);
@@ -181,17 +174,15 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
 
   // Dirichlet flags of the next tile's node: three byte loads kept in three registers, consumed one
   // tile later (packing them right away would stall on the load latency)
-  int n_next = node_of(real_tile(vt + nwarps));
-  const long long n_first = node_of(real_tile(vt));
+  int n_next = node_of(vt + nwarps);
+  const long long n_first = node_of(vt);
   gather_async(0, n_first);
   const uint8_t* pf0 = args.dir + n_first * 3;
   unsigned f0 = __ldg(pf0), f1 = __ldg(pf0 + 1), f2 = __ldg(pf0 + 2);
   int buf = 0;
 
-  // One tile.  `tile` is the real tile index, `tile_ahead2` the real index of the tile this warp visits two steps later
-  // (its node ids are fetched now); `iface`: the tile belongs to an interface layer (FUSE only).
-  auto do_tile = [&](const long long tile, const long long tile_ahead2, const bool iface) {
-    const long long e0 = tile * kTile;
+  for (; vt < ntiles; vt += nwarps, buf ^= 1) {
+    const long long e0 = real_tile(vt) * kTile;
     hold_back(n_next, f0, f1, f2);   // loaded one tile ago; nothing may consume them before this point
 
     // ---- phase 0: this tile's nodal data has landed in shared memory; start the next gather
@@ -206,7 +197,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
       gather_async(buf ^ 1, (long long)n_next);
       const uint8_t* pf = args.dir + (long long)n_next * 3;
       f0 = __ldg(pf); f1 = __ldg(pf + 1); f2 = __ldg(pf + 2);
-      n_next = node_of(tile_ahead2);
+      n_next = node_of(vt + 2 * nwarps);
     };
     if constexpr (LAYOUT == 0) issue_next();
 
@@ -416,20 +407,12 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
     }
     __syncwarp();  // everyone is done with X / u / gradients of this tile
     if constexpr (FUSE) {
-      if (iface) halo_tile_done(hf, lane);
+      if (vt < hf.tiles_lo + hf.tiles_hi) halo_tile_done(hf, lane);
       if (!push_done) push_done = halo_try_push(hf, lane);
     }
-  };
+  }
   if constexpr (FUSE) {
-    // interface tiles first (a few iterations per warp, non-linear index map), then the interior tiles with a LINEAR
-    // real index, so that the address arithmetic of the steady-state loop is strength-reduced exactly as in the plain
-    // kernel (with the map inside one loop the fused kernel issued 6.5 % more instructions: profiles/r2/fused_vs_plain_ncu.md)
-    const long long n_iface = (long long)tl32 + th32;
-    for (; vt < n_iface && vt < ntiles; vt += nwarps, buf ^= 1) do_tile(real_tile(vt), real_tile(vt + 2 * nwarps), true);
-    for (long long tile = vt - th32; tile < ntiles; tile += nwarps, buf ^= 1) do_tile(tile, tile + 2 * nwarps, false);
     if (!push_done) halo_drain(hf, lane);
-  } else {
-    for (long long tile = vt; tile < ntiles; tile += nwarps, buf ^= 1) do_tile(tile, tile + 2 * nwarps, false);
   }
   if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last copies
 }

@@ -67,17 +67,9 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
   // vt: position in the visiting order (interface layers first when FUSE, see assemble_hex_common.cuh)
   long long vt = (long long)blockIdx.x * kWarpsJ2 + warp;
   if (vt >= ntiles) return;
-  // (32-bit arithmetic: the visiting-order map runs three times per tile; in 64 bits it cost 90 instructions per tile,
-  // 6.5 % of the kernel -- profiles/r2/fused_vs_plain_ncu.md)
-  const int nt32 = (int)ntiles, tl32 = (int)hf.tiles_lo, th32 = (int)hf.tiles_hi;
   auto real_tile = [&](long long v) -> long long {
-    if constexpr (FUSE) {
-      const int iv = (int)v;
-      if (v >= ntiles) return v;
-      return iv < tl32 ? iv : (iv < tl32 + th32 ? nt32 - th32 + (iv - tl32) : iv - th32);
-    } else {
-      return v;
-    }
+    if constexpr (FUSE) return v < ntiles ? halo_real_tile(hf, v, ntiles) : v;
+    else return v;
   };
   bool push_done = !FUSE;
 
@@ -102,7 +94,8 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
 
   // software pipeline of the gathers (node ids two tiles ahead, nodal data and history one tile ahead); see
   // assemble_hex.cu for why the id is held back in its register
-  auto node_of = [&](long long t) -> int {   // t: a real tile index (>= ntiles: no tile)
+  auto node_of = [&](long long v) -> int {
+    const long long t = real_tile(v);
     const long long e = t * kTile + el_p;
     const int ok = (t < ntiles && e < args.ne) ? 1 : 0;
     const int32_t* src = args.conn + (ok ? e * 8 + sub : 0);
@@ -116,7 +109,8 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
   auto hold_back = [](int& a, unsigned& b, unsigned& c, unsigned& d) {
     asm volatile("" : "+r"(a), "+r"(b), "+r"(c), "+r"(d));
   };
-  auto gather_async = [&](long long n, long long t) {   // t: real index of the tile the history is fetched for
+  auto gather_async = [&](long long n, long long v) {
+    const long long t = real_tile(v);
     const double* gx = args.xyz + n * 3;
     const double* gu = args.u + n * 3;
     cp_async8(&sm.X[0][lane], gx); cp_async8(&sm.X[1][lane], gx + 1); cp_async8(&sm.X[2][lane], gx + 2);
@@ -128,16 +122,14 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
     for (int s = 0; s < 7; ++s) cp_async8(&sm.st[s][lane], gs + s);
     cp_async_commit();
   };
-  int n_next = node_of(real_tile(vt + nwarps));
-  const long long n_first = node_of(real_tile(vt));
-  gather_async(n_first, real_tile(vt));
+  int n_next = node_of(vt + nwarps);
+  const long long n_first = node_of(vt);
+  gather_async(n_first, vt);
   const uint8_t* pf0 = args.dir + n_first * 3;
   unsigned f0 = __ldg(pf0), f1 = __ldg(pf0 + 1), f2 = __ldg(pf0 + 2);
 
-  // One tile: `tile` its real index, `tile_ahead1` / `tile_ahead2` the real indices of the tiles this warp visits one and
-  // two steps later (history / node ids fetched now), `iface`: the tile belongs to an interface layer (FUSE only).
-  auto do_tile = [&](const long long tile, const long long tile_ahead1, const long long tile_ahead2, const bool iface) {
-    const long long e0 = tile * kTile;
+  for (; vt < ntiles; vt += nwarps) {
+    const long long e0 = real_tile(vt) * kTile;
     hold_back(n_next, f0, f1, f2);
 
     // ---- phase 0: this tile's nodal data and history have landed
@@ -225,12 +217,12 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
     fence_async_smem();
     __syncwarp();
     // X / u / history of this tile are consumed: the next tile's gather lands behind phase 2
-    gather_async((long long)n_next, tile_ahead1);
+    gather_async((long long)n_next, vt + nwarps);
     {
       const uint8_t* pf = args.dir + (long long)n_next * 3;
       f0 = __ldg(pf); f1 = __ldg(pf + 1); f2 = __ldg(pf + 2);
     }
-    n_next = node_of(tile_ahead2);
+    n_next = node_of(vt + 2 * nwarps);
     {  // new history of the tile: one contiguous bulk copy (mechanical_elastoplasticity.py:217)
       long long cnt = args.ne - e0;
       cnt = cnt > kTile ? kTile : cnt;
@@ -404,20 +396,12 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
     }
     __syncwarp();  // everyone is done with X / u / history / gradients of this tile
     if constexpr (FUSE) {
-      if (iface) halo_tile_done(hf, lane);
+      if (vt < hf.tiles_lo + hf.tiles_hi) halo_tile_done(hf, lane);
       if (!push_done) push_done = halo_try_push(hf, lane);
     }
-  };
+  }
   if constexpr (FUSE) {
-    // interface tiles first (non-linear index map, a few iterations per warp), then the interior with a linear real index
-    // (strength-reduced address arithmetic, as in the plain kernel; see assemble_hex.cu)
-    const long long n_iface = (long long)tl32 + th32;
-    for (; vt < n_iface && vt < ntiles; vt += nwarps)
-      do_tile(real_tile(vt), real_tile(vt + nwarps), real_tile(vt + 2 * nwarps), true);
-    for (long long tile = vt - th32; tile < ntiles; tile += nwarps) do_tile(tile, tile + nwarps, tile + 2 * nwarps, false);
     if (!push_done) halo_drain(hf, lane);
-  } else {
-    for (long long tile = vt; tile < ntiles; tile += nwarps) do_tile(tile, tile + nwarps, tile + 2 * nwarps, false);
   }
   if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last copies
 }
