@@ -73,6 +73,8 @@ SIGNATURES = {
     "fol_bicg_scalars": (_int, [_vp, _int, _int, _vp]),
     "fol_vec_op_dev": (_int, [_vp, _int, _i64, _vp, _int, _int, _dbl, _vp, _int, _dbl, _vp, _vp]),
     "fol_dot_work_size": (_i64, []),
+    "fol_bicgstab_fused_work_size": (_i64, [_i64]),
+    "fol_bicgstab_fused": (_int, [_vp, _int, _int, _i64, _vp, _i32p, _vp, _vp, _vp, _vp, _dbl, _dbl, _i64, _vp]),
     "fol_dot": (_int, [_vp, _int, _i64, _vp, _vp, _vp, _vp]),
     "fol_plan_create": (_int, [C.POINTER(_vp), _int, _int, _int, _int, _i64, _i64, _vp, _i32p, _i32p, _i64,
                                C.POINTER(_dbl)]),

@@ -214,6 +214,33 @@ def bicgstab(A, b, x0=None, tol=1e-5, atol=0.0, maxiter=None, M_diagonal=None):
     return x, k
 
 
+def bicgstab_fused(A, b, x0=None, tol=1e-5, atol=0.0, maxiter=None, M_diagonal=None):
+    """`bicgstab` as ONE persistent launch (csrc/krylov_fused.cu): same recurrences, stopping rule and break-down codes,
+    dot products summed per CTA instead of per fixed block (iterates equal to rounding, deterministic run to run).  For
+    the sizes where the multi-launch loop is launch-latency-bound; one host read when the solve is over.  Not for
+    SlabOperator (its dot products need a collective)."""
+    L = A.loss
+    lib = _lib.load()
+    if hasattr(A, "vectors"):
+        raise ValueError("bicgstab_fused: slab-partitioned operators use bicgstab")
+    n = b.numel()
+    if maxiter is None:
+        maxiter = 10 * n
+    x = b.new_zeros(n) if x0 is None else _lib.to_device(x0, L.dtype).reshape(-1).clone()
+    work = torch.empty(int(lib.fol_bicgstab_fused_work_size(n)), dtype=L.dtype, device=L.device)
+    block = A.plan.get("node_cols") is not None and A.use_block_kernel
+    d = int(A.plan["dofs_per_node"]) if block else 0
+    cols = A.plan["node_cols"] if block else A.plan["cols"]
+    _lib.check(lib.fol_bicgstab_fused(_lib.stream_ptr(), L._dt, d, n, _lib.ptr(A.plan["slice_ptr"]), _lib.ptr(cols),
+                                      _lib.ptr(A.values), _lib.ptr(b.contiguous()), _lib.ptr(x),
+                                      _lib.ptr(M_diagonal) if M_diagonal is not None else None, float(tol), float(atol),
+                                      int(maxiter), _lib.ptr(work)))
+    k, _, lost = work[8 * n + 16384: 8 * n + 16384 + 3].tolist()          # the one host read
+    if lost:
+        raise _lib.FolaxError("bicgstab_fused: a grid barrier timed out (the persistent grid was not fully resident)")
+    return x, int(k)
+
+
 # slots of the device scalar array (csrc/krylov_threads.cuh, enum BS_*)
 (_BB, _RS, _RHO, _ALPHA, _OMEGA, _RHO_NEW, _BETA, _RQ, _SS, _TS, _TT, _ATOL2, _STATE, _K, _RS_NEXT, _RHO_NEXT,
  _MAXITER) = range(17)

@@ -310,6 +310,17 @@ int fol_vec_op_dev(fol_stream_t s, int dtype, int64_t n, const void* scalars, in
  * fol_dot_work_size() elements of the call's dtype */
 int64_t fol_dot_work_size(void);
 int fol_dot(fol_stream_t s, int dtype, int64_t n, const void* x, const void* y, void* work, void* out);
+/* The whole BiCGSTAB solve (same recurrences, start, stopping rule and break-down codes as the loop above and as
+ * jax.scipy.sparse.linalg.bicgstab behind fol/solvers/fe_solver.py:62-67) as ONE persistent launch: SELL products, fused
+ * vector passes and grid barriers inside, recurrence scalars in shared memory, no host read until the end.  For the
+ * sizes where the multi-launch loop is latency-bound (configs[0], configs[3]).  dofs_per_node 2 / 3: `cols` are the node
+ * columns of fol_sell_spmv_block; 0: scalar columns of fol_sell_spmv.  x: in x0, out solution.  work:
+ * fol_bicgstab_fused_work_size(n) values of the call's dtype; after the stream has drained, work[8n + 16384 + 0..2] =
+ * (iterations or -10 / -11, final |r|^2, barrier waits that gave up -- 0 in a healthy run). */
+int64_t fol_bicgstab_fused_work_size(int64_t n);
+int fol_bicgstab_fused(fol_stream_t s, int dtype, int dofs_per_node, int64_t n, const int64_t* slice_ptr,
+                       const int32_t* cols, const void* values, const void* b, void* x, const void* m_diagonal,
+                       double tol, double atol, int64_t maxiter, void* work);
 
 /* ---- host-buffer entry point (what a non-GPU caller binds; used for the e2e measurement) -- */
 

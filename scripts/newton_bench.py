@@ -22,6 +22,7 @@ loss = NeoHookeMechanicalLoss3DTetra("nh", {"dirichlet_bc_dict": bc, "material_d
 settings = {"linear_solver_settings": {"solver": "JAX-bicgstab", "tol": float(os.environ.get("TOL", 1e-8)), "atol": 0.0,
                                        "maxiter": int(os.environ.get("MAXITER", 2000)), "pre-conditioner": "jacobi",
                                        "device_scalars": bool(int(os.environ.get("DEVICE_SCALARS", 0))),
+                                       "fused": bool(int(os.environ.get("FUSED", 0))),
                                        "use_graph": bool(int(os.environ.get("USE_GRAPH", 0))),
                                        "check_every": int(os.environ.get("CHECK_EVERY", 8))},
             "nonlinear_solver_settings": {"rel_tol": 1e-8, "abs_tol": 1e-8, "maxiter": 10,
@@ -70,6 +71,17 @@ def bicg_dev(*a, **k):
 
 
 linalg.bicgstab_device = bicg_dev
+_bicg_fused = linalg.bicgstab_fused
+
+
+def bicg_fused(*a, **k):
+    x, info = timed(_bicg_fused, "krylov_s")(*a, **k)
+    split["krylov_iterations"] += max(info, 0)
+    split["newton_iterations"] += 1
+    return x, info
+
+
+linalg.bicgstab_fused = bicg_fused
 t0 = time.time()
 plan_t0 = time.time()
 loss._csr_plan(); loss._sell_plan()
