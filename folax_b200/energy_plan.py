@@ -85,6 +85,51 @@ def is_affine(coords, conn):
     return bool((skew <= 1e-13 * size).all())
 
 
+def grid_structure(coords, conn, rtol=1e-12):
+    """Facts behind fol_energy_and_grads_grid (csrc/energy_grid.cu), or None: the Quad4 mesh is an nx x ny grid with
+    row-major node numbers (node(c, r) = r (nx + 1) + c), elements [n, n + 1, n + nx + 2, n + nx + 1] in row-major
+    order (what usefull_functions.py:213-258 builds) and ONE element shape, a parallelogram, to `rtol` of its size.
+    Returns {"nx", "ny", "jinv" (row-major d xi_j / d x_k), "wdetj" (2 x 2 rule: weight 1 x det J)}."""
+    conn = np.asarray(conn)
+    X = np.asarray(coords, dtype=np.float64)
+    if conn.ndim != 2 or conn.shape[1] != 4 or len(conn) == 0 or X.shape[1] < 2:
+        return None
+    if X.shape[1] > 2 and np.ptp(X[:, 2]) != 0.0:
+        return None
+    ne, nn = len(conn), len(X)
+    nx = int(conn[0, 3] - conn[0, 0]) - 1                    # node stride between rows = nx + 1
+    if nx < 1 or ne % nx != 0:
+        return None
+    ny = ne // nx
+    if (nx + 1) * (ny + 1) != nn:
+        return None
+    r, c = np.divmod(np.arange(ne, dtype=np.int64), nx)
+    n0 = r * (nx + 1) + c
+    want = np.stack([n0, n0 + 1, n0 + nx + 2, n0 + nx + 1], axis=1)
+    if not np.array_equal(conn.astype(np.int64), want):
+        return None
+    P = X[:, :2][conn]                                        # (ne, 4, 2)
+    d_xi = ((P[:, 1] - P[:, 0]) + (P[:, 2] - P[:, 3])) / 4.0  # d x / d xi
+    d_eta = ((P[:, 3] - P[:, 0]) + (P[:, 2] - P[:, 1])) / 4.0
+    skew = np.abs(P[:, 0] - P[:, 1] + P[:, 2] - P[:, 3]).max()
+    size = max(np.abs(d_xi[0]).max(), np.abs(d_eta[0]).max())
+    if size == 0.0 or skew > rtol * size:
+        return None
+    if np.abs(d_xi - d_xi[0]).max() > rtol * size or np.abs(d_eta - d_eta[0]).max() > rtol * size:
+        return None
+    # one shape for all elements: the mean edge vectors (exact zeros stay exact zeros: axis-aligned grids keep a
+    # diagonal J^-1, which the kernel exploits)
+    a, b = d_xi.mean(axis=0), d_eta.mean(axis=0)
+    a = np.where(np.abs(d_xi).max(axis=0) == 0.0, 0.0, a)
+    b = np.where(np.abs(d_eta).max(axis=0) == 0.0, 0.0, b)
+    A = np.array([[a[0], b[0]], [a[1], b[1]]])                # A[k][j] = d x_k / d xi_j
+    det = A[0, 0] * A[1, 1] - A[0, 1] * A[1, 0]
+    if not det > 0.0:
+        return None
+    jinv = np.array([A[1, 1], -A[0, 1], -A[1, 0], A[0, 0]]) / det   # row-major d xi_j / d x_k
+    return {"nx": nx, "ny": ny, "jinv": jinv, "wdetj": float(det)}
+
+
 def _choose(coords, conn, tile_nodes, max_elems, method, generic_max_elems, ne):
     target, generic = tile_nodes, None
     for _ in range(12):

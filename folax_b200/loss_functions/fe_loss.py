@@ -568,6 +568,22 @@ class FiniteElementLoss(Loss):
                            for k, v in plan.items()}
         return self._eplan
 
+    def _grid_plan(self):
+        """Structured-grid facts for csrc/energy_grid.cu (thermal Quad4, 2 x 2 rule), or None (tile kernels).
+        FOL_ENERGY_GRID=0 keeps the tile kernels (A/B measurements)."""
+        if "_grid" not in self.__dict__:
+            import os
+            from .. import energy_plan
+            g = None
+            if (self._batch_physics() == "thermal" and self.element_type == "quad" and self.num_gp == 2
+                    and os.environ.get("FOL_ENERGY_GRID", "1") != "0"):
+                g = energy_plan.grid_structure(np.asarray(self.fe_mesh.GetNodesCoordinates()),
+                                               self.fe_mesh.GetElementsNodes(self.element_type))
+                if g is not None:
+                    g["jinv_c"] = (C.c_double * 4)(*[float(v) for v in g["jinv"]])
+            self._grid = g
+        return self._grid
+
     def _energy_work(self, nb):
         """Scratch of the batched-loss kernel, cached per batch size (no allocation on the hot call)."""
         cache = self.__dict__.setdefault("_work_cache", {})
@@ -582,10 +598,23 @@ class FiniteElementLoss(Loss):
         the dofs are BC-applied already, or dir_values (ndof, NaN = free) is applied by the kernel."""
         lib = _lib.load()
         nb = batch_dofs.shape[0]
-        geom, ep = self._geometry_cache(), self._energy_plan()
         grad_u = torch.empty_like(batch_dofs)
         grad_k = torch.empty_like(batch_params) if self._has_control_gradient else None
         energy = torch.empty(nb, dtype=self.dtype, device=self.device)
+        grid = self._grid_plan()
+        if grid is not None:              # structured Quad4 grid: the marching kernel (no connectivity, no tile plan)
+            cache = self.__dict__.setdefault("_grid_work_cache", {})
+            if nb not in cache:
+                cache.clear()
+                cache[nb] = torch.empty(int(lib.fol_energy_grid_work_size(grid["nx"], grid["ny"], nb)),
+                                        dtype=self.dtype, device=self.device)
+            _lib.check(lib.fol_energy_and_grads_grid(
+                _lib.stream_ptr(), self._dt, grid["nx"], grid["ny"], nb, grid["jinv_c"], grid["wdetj"],
+                _lib.ptr(batch_params), _lib.ptr(batch_dofs), _lib.ptr(dir_values) if dir_values is not None else None,
+                _lib.ptr(dir_flag) if dir_flag is not None else None, float(out_scale), self._params,
+                _lib.ptr(grad_u), _lib.ptr(grad_k), _lib.ptr(energy), _lib.ptr(cache[nb])))
+            return energy, grad_u, grad_k
+        geom, ep = self._geometry_cache(), self._energy_plan()
         work = self._energy_work(nb)
         _lib.check(lib.fol_energy_and_grads_flags(_lib.stream_ptr(), self._dt, _lib.PHYSICS[self._batch_physics()],
                                             self.fe_element.code, self.num_gp, self._ne, self._nn, nb,

@@ -322,6 +322,20 @@ int fol_bicgstab_fused(fol_stream_t s, int dtype, int dofs_per_node, int64_t n, 
                        const int32_t* cols, const void* values, const void* b, void* x, const void* m_diagonal,
                        double tol, double atol, int64_t maxiter, void* work);
 
+/* Batched thermal loss + VJP (ThermalLoss2DQuad.ComputeBatchLoss and its gradient: thermal.py:28-49,
+ * fe_loss.py:250-262) on a STRUCTURED Quad4 grid, 2 x 2 rule: nodes numbered row-major (node(c, r) = r (nx + 1) + c),
+ * elements [n, n + 1, n + nx + 2, n + nx + 1] as fol/tools/usefull_functions.py:213-258 builds them, every element the
+ * same parallelogram.  The caller (folax_b200/energy_plan.py::grid_structure) establishes those facts; other meshes use
+ * fol_energy_and_grads.  jinv_host: row-major d xi_j / d x_k of the element shape; w_detj: Gauss weight x det J;
+ * params_host[5], [6]: beta, c.  ctrl, u, grad_u, grad_k (may be null): (nb, (nx+1)(ny+1)); dir_values / dir_flag /
+ * out_scale as in fol_energy_and_grads; energy: (nb); work: fol_energy_grid_work_size values of the call's dtype.
+ * Same results as the tile kernels to rounding (another summation order), deterministic. */
+int64_t fol_energy_grid_work_size(int64_t nx, int64_t ny, int64_t nb);
+int fol_energy_and_grads_grid(fol_stream_t s, int dtype, int64_t nx, int64_t ny, int64_t nb, const double* jinv_host,
+                              double w_detj, const void* ctrl, const void* u, const void* dir_values,
+                              const uint8_t* dir_flag, double out_scale, const double* params_host, void* grad_u,
+                              void* grad_k, void* energy, void* work);
+
 /* ---- host-buffer entry point (what a non-GPU caller binds; used for the e2e measurement) -- */
 
 typedef struct fol_plan fol_plan;
