@@ -40,6 +40,11 @@ class ElementInfo:
         return a.value, d.value, g.value
 
 
+def _aligned16(t):
+    """The bulk copies of csrc/energy_grid.cu read from 16-byte aligned arrays (fresh torch tensors always are)."""
+    return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
+
+
 class _BatchLossFn(torch.autograd.Function):
     """custom_vjp of ComputeBatchLoss: forward runs the fused energy+gradient kernel and the loss
     tail, backward only rescales the saved cotangents -- SURVEY.md A.7.
@@ -581,6 +586,9 @@ class FiniteElementLoss(Loss):
                                                self.fe_mesh.GetElementsNodes(self.element_type))
                 if g is not None:
                     g["jinv_c"] = (C.c_double * 4)(*[float(v) for v in g["jinv"]])
+                    col = np.zeros(g["nx"] + 1, dtype=np.uint8)      # node columns that hold a Dirichlet node
+                    col[np.asarray(self.dirichlet_indices, dtype=np.int64) % (g["nx"] + 1)] = 1
+                    g["col_dir"] = torch.as_tensor(col, device=self.device)
             self._grid = g
         return self._grid
 
@@ -610,8 +618,10 @@ class FiniteElementLoss(Loss):
                                         dtype=self.dtype, device=self.device)
             _lib.check(lib.fol_energy_and_grads_grid(
                 _lib.stream_ptr(), self._dt, grid["nx"], grid["ny"], nb, grid["jinv_c"], grid["wdetj"],
-                _lib.ptr(batch_params), _lib.ptr(batch_dofs), _lib.ptr(dir_values) if dir_values is not None else None,
-                _lib.ptr(dir_flag) if dir_flag is not None else None, float(out_scale), self._params,
+                _lib.ptr(_aligned16(batch_params)), _lib.ptr(_aligned16(batch_dofs)),
+                _lib.ptr(dir_values) if dir_values is not None else None,
+                _lib.ptr(dir_flag) if dir_flag is not None else None, _lib.ptr(grid["col_dir"]), float(out_scale),
+                self._params,
                 _lib.ptr(grad_u), _lib.ptr(grad_k), _lib.ptr(energy), _lib.ptr(cache[nb])))
             return energy, grad_u, grad_k
         geom, ep = self._geometry_cache(), self._energy_plan()

@@ -328,13 +328,15 @@ int fol_bicgstab_fused(fol_stream_t s, int dtype, int dofs_per_node, int64_t n, 
  * same parallelogram.  The caller (folax_b200/energy_plan.py::grid_structure) establishes those facts; other meshes use
  * fol_energy_and_grads.  jinv_host: row-major d xi_j / d x_k of the element shape; w_detj: Gauss weight x det J;
  * params_host[5], [6]: beta, c.  ctrl, u, grad_u, grad_k (may be null): (nb, (nx+1)(ny+1)); dir_values / dir_flag /
- * out_scale as in fol_energy_and_grads; energy: (nb); work: fol_energy_grid_work_size values of the call's dtype.
+ * out_scale as in fol_energy_and_grads; col_dir: (nx + 1) bytes, 1 where the node column holds a Dirichlet node, or
+ * null (every column may) -- the Dirichlet work then runs only in the warps that need it; ctrl, u and dir_values must be
+ * 16-byte aligned; energy: (nb); work: fol_energy_grid_work_size values of the call's dtype.
  * Same results as the tile kernels to rounding (another summation order), deterministic. */
 int64_t fol_energy_grid_work_size(int64_t nx, int64_t ny, int64_t nb);
 int fol_energy_and_grads_grid(fol_stream_t s, int dtype, int64_t nx, int64_t ny, int64_t nb, const double* jinv_host,
                               double w_detj, const void* ctrl, const void* u, const void* dir_values,
-                              const uint8_t* dir_flag, double out_scale, const double* params_host, void* grad_u,
-                              void* grad_k, void* energy, void* work);
+                              const uint8_t* dir_flag, const uint8_t* col_dir, double out_scale,
+                              const double* params_host, void* grad_u, void* grad_k, void* energy, void* work);
 
 /* ---- host-buffer entry point (what a non-GPU caller binds; used for the e2e measurement) -- */
 
