@@ -100,6 +100,29 @@ __device__ __forceinline__ double op_sub(double a, double b) { return __dsub_rn(
 __device__ __forceinline__ float op_sub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ double op_fma(double a, double b, double c) { return fma(a, b, c); }
 __device__ __forceinline__ float op_fma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double op_neg(double a) { return -a; }
+__device__ __forceinline__ float op_neg(float a) { return -a; }
+// Two float32 samples per lane: the packed instructions of sm_100 (FMUL2 / FADD2 / FFMA2: one issue slot for the two
+// samples' operations, each rounded like the scalar instruction) -- the float32 kernel is bound by issue slots.
+__device__ __forceinline__ float2 op_mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 op_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 op_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 op_sub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }   // a - b, one rounding
+__device__ __forceinline__ float2 op_neg(float2 a) { return make_float2(-a.x, -a.y); }
+
+// lane type: S (one sample per lane) or float2 (two float32 samples per lane)
+template <class S, int NS> struct LaneT { using type = S; };
+template <> struct LaneT<float, 2> { using type = float2; };
+template <class V> struct ScalarOf { using type = V; };
+template <> struct ScalarOf<float2> { using type = float; };
+template <class V>
+__device__ __forceinline__ V bc(typename ScalarOf<V>::type x) {
+  if constexpr (std::is_same<V, float2>::value) return make_float2(x, x);
+  else return x;
+}
+template <class V>
+__device__ __forceinline__ V bcd(double x) { return bc<V>((typename ScalarOf<V>::type)x); }
+
 // a x + b y
 template <class T>
 __device__ __forceinline__ T lin2(T a, T x, T b, T y) {
@@ -109,40 +132,61 @@ __device__ __forceinline__ T lin2(T a, T x, T b, T y) {
 // 1 + beta T^c (thermal.py:34); integer powers by repeated multiplication like lax.integer_pow
 template <class T, int NL>
 __device__ __forceinline__ T grid_conductivity(T tg, T beta, T c) {
-  if constexpr (NL == 0) return (T)1;
-  else if constexpr (NL == 1) return op_fma(beta, tg, (T)1);
-  else if constexpr (NL == 2) return op_fma(beta, op_mul(tg, tg), (T)1);
-  else if constexpr (NL == 3) return op_fma(beta, op_mul(tg, op_mul(tg, tg)), (T)1);
-  else if constexpr (NL == 4) { const T t2 = op_mul(tg, tg); return op_fma(beta, op_mul(t2, t2), (T)1); }
-  else return op_fma(beta, pow_c<T>(tg, c), (T)1);
+  const T one = bcd<T>(1.0);
+  if constexpr (NL == 0) return one;
+  else if constexpr (NL == 1) return op_fma(beta, tg, one);
+  else if constexpr (NL == 2) return op_fma(beta, op_mul(tg, tg), one);
+  else if constexpr (NL == 3) return op_fma(beta, op_mul(tg, op_mul(tg, tg)), one);
+  else if constexpr (NL == 4) { const T t2 = op_mul(tg, tg); return op_fma(beta, op_mul(t2, t2), one); }
+  else {
+    if constexpr (std::is_same<T, float2>::value)
+      return op_fma(beta, make_float2(pow_c<float>(tg.x, c.x), pow_c<float>(tg.y, c.y)), one);
+    else return op_fma(beta, pow_c<T>(tg, c), one);
+  }
+}
+
+// Values a node row contributes to the elements below and above it, for the lane's column pair (own, right): T and K
+// on the edge at xi = -s / +s (1-D Lagrange weights a = (1 - s)/2, b = (1 + s)/2, s = 1/sqrt(3)) and the difference of
+// T along the edge.  Computed ONCE per node row and lane: the top edge of an element row is the bottom edge of the next.
+template <class T>
+struct GridEdge {
+  T m, p, d, km, kp;
+};
+template <class T>
+__device__ __forceinline__ GridEdge<T> grid_edge(T t_own, T t_right, T k_own, T k_right) {
+  constexpr double s = FOL_S3;
+  const T a = bcd<T>(0.5 * (1.0 - s)), b = bcd<T>(0.5 * (1.0 + s));
+  GridEdge<T> e;
+  e.m = lin2(b, t_own, a, t_right);
+  e.p = lin2(a, t_own, b, t_right);
+  e.d = op_sub(t_right, t_own);
+  e.km = lin2(b, k_own, a, k_right);
+  e.kp = lin2(a, k_own, b, k_right);
+  return e;
 }
 
 // Element vectors re = dE/dT_e and dK = dE/dK_e of the thermal Quad4 with the 2 x 2 rule on a parallelogram, local
-// nodes 0 (-,-), 1 (+,-), 2 (+,+), 3 (-,+) and Gauss points in the same order (quadrilateral_2d_4.py:54-58), written
-// through the 1-D Lagrange weights a = (1 - s)/2, b = (1 + s)/2 at the abscissae -+s, s = 1/sqrt(3):
-//   values on the bottom / top edge at xi = -+s, then at the four points; dT/dxi depends on eta only, dT/deta on xi only
-//   (so do their products with J^-1 on an axis-aligned grid); the weighted fluxes go back to the nodes through the same
-//   weights.  Same sums as thermal_vectors_affine (energy_qt.cuh) in another association: equal to rounding.
-// e_el = T_e . re (thermal.py:45-49).  124 instructions on an axis-aligned grid (DIAG), 148 on a sheared one.
+// nodes 0 (-,-), 1 (+,-), 2 (+,+), 3 (-,+) and Gauss points in the same order (quadrilateral_2d_4.py:54-58), from the
+// edge values of its bottom (B) and top (U) node rows: values at the four points by the same weights across eta;
+// dT/dxi depends on eta only, dT/deta on xi only (so do their products with J^-1 on an axis-aligned grid); the weighted
+// fluxes go back to the nodes through the same weights.  Same sums as thermal_vectors_affine (energy_qt.cuh) in
+// another association: equal to rounding.  e_el = T_e . re (thermal.py:45-49) = sum_g K_g (w detJ nl_g |grad T_g|^2).
+// 115 instructions on an axis-aligned grid (DIAG), 139 on a sheared one.  T: the lane type (one or two samples).
 template <class T, int NL, bool DIAG, bool GK>
-__device__ __forceinline__ void grid_element(const T (&Tn)[4], const T (&Kn)[4], const T (&ji)[4], T wd, T beta, T cexp,
-                                             T (&re)[4], T (&dK)[4], T& e_el) {
+__device__ __forceinline__ void grid_element(const GridEdge<T>& B, const GridEdge<T>& U, const T (&ji)[4], T wd, T beta,
+                                             T cexp, T (&re)[4], T (&dK)[4], T& e_el) {
   constexpr double s = FOL_S3;
-  const T a = (T)(0.5 * (1.0 - s)), b = (T)(0.5 * (1.0 + s)), ah = (T)(0.25 * (1.0 - s)), bh = (T)(0.25 * (1.0 + s));
-  const T Bm = lin2(b, Tn[0], a, Tn[1]), Bp = lin2(a, Tn[0], b, Tn[1]);     // T on the bottom edge at xi = -s, +s
-  const T Um = lin2(b, Tn[3], a, Tn[2]), Up = lin2(a, Tn[3], b, Tn[2]);     // ... on the top edge
-  const T dB = op_sub(Tn[1], Tn[0]), dU = op_sub(Tn[2], Tn[3]);
-  const T t0e[2] = {lin2(bh, dB, ah, dU), lin2(ah, dB, bh, dU)};            // dT/dxi at eta = -s, +s
-  const T t1x[2] = {op_sub(Um, Bm), op_sub(Up, Bp)};                        // 2 dT/deta at xi = -s, +s
-  const T KBm = lin2(b, Kn[0], a, Kn[1]), KBp = lin2(a, Kn[0], b, Kn[1]);
-  const T KUm = lin2(b, Kn[3], a, Kn[2]), KUp = lin2(a, Kn[3], b, Kn[2]);
-  const T tg[4] = {lin2(b, Bm, a, Um), lin2(b, Bp, a, Up), lin2(a, Bp, b, Up), lin2(a, Bm, b, Um)};
-  const T eg[4] = {lin2(b, KBm, a, KUm), lin2(b, KBp, a, KUp), lin2(a, KBp, b, KUp), lin2(a, KBm, b, KUm)};
+  const T a = bcd<T>(0.5 * (1.0 - s)), b = bcd<T>(0.5 * (1.0 + s)), ah = bcd<T>(0.25 * (1.0 - s)),
+          bh = bcd<T>(0.25 * (1.0 + s)), half = bcd<T>(0.5);
+  const T t0e[2] = {lin2(bh, B.d, ah, U.d), lin2(ah, B.d, bh, U.d)};        // dT/dxi at eta = -s, +s
+  const T t1x[2] = {op_sub(U.m, B.m), op_sub(U.p, B.p)};                    // 2 dT/deta at xi = -s, +s
+  const T tg[4] = {lin2(b, B.m, a, U.m), lin2(b, B.p, a, U.p), lin2(a, B.p, b, U.p), lin2(a, B.m, b, U.m)};
+  const T eg[4] = {lin2(b, B.km, a, U.km), lin2(b, B.kp, a, U.kp), lin2(a, B.kp, b, U.kp), lin2(a, B.km, b, U.km)};
   constexpr int ETA[4] = {0, 0, 1, 1}, XI[4] = {0, 1, 1, 0};                // eta / xi index of Gauss point g
   T w0[4], w1[4], ck[4];
   if constexpr (DIAG) {
     // grad T = (j00 dT/dxi, j11 dT/deta): two values each; so are the flux factors j00 gx, j11 gy and the squares
-    const T j3h = op_mul((T)0.5, ji[3]);
+    const T j3h = op_mul(half, ji[3]);
     T gx[2], gy[2], fx[2], fy[2], gx2[2], gy2[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -157,19 +201,19 @@ __device__ __forceinline__ void grid_element(const T (&Tn)[4], const T (&Kn)[4],
     for (int g = 0; g < 4; ++g) {
       const T wn = op_mul(wd, grid_conductivity<T, NL>(tg[g], beta, cexp));
       const T cf = op_mul(wn, eg[g]);
-      if constexpr (GK) ck[g] = op_mul(wn, op_add(gx2[ETA[g]], gy2[XI[g]]));
+      ck[g] = op_mul(wn, op_add(gx2[ETA[g]], gy2[XI[g]]));
       w0[g] = op_mul(cf, fx[ETA[g]]);
       w1[g] = op_mul(cf, fy[XI[g]]);
     }
   } else {
-    const T j2h = op_mul((T)0.5, ji[2]), j3h = op_mul((T)0.5, ji[3]);
+    const T j2h = op_mul(half, ji[2]), j3h = op_mul(half, ji[3]);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const T gx = lin2(t0e[ETA[g]], ji[0], t1x[XI[g]], j2h);                // grad T = J^-T (dN^T T)
       const T gy = lin2(t0e[ETA[g]], ji[1], t1x[XI[g]], j3h);
       const T wn = op_mul(wd, grid_conductivity<T, NL>(tg[g], beta, cexp));
       const T cf = op_mul(wn, eg[g]);
-      if constexpr (GK) ck[g] = op_mul(wn, lin2(gx, gx, gy, gy));
+      ck[g] = op_mul(wn, lin2(gx, gx, gy, gy));
       w0[g] = op_mul(cf, lin2(ji[0], gx, ji[1], gy));
       w1[g] = op_mul(cf, lin2(ji[2], gx, ji[3], gy));
     }
@@ -178,7 +222,7 @@ __device__ __forceinline__ void grid_element(const T (&Tn)[4], const T (&Kn)[4],
   const T s1l = op_add(w1[0], w1[3]), s1r = op_add(w1[1], w1[2]);
   const T S0b = lin2(bh, s0lo, ah, s0hi), S0t = lin2(ah, s0lo, bh, s0hi);  // sum_g dN/dxi weights, bottom / top nodes
   const T S1l = lin2(bh, s1l, ah, s1r), S1r = lin2(ah, s1l, bh, s1r);      // sum_g dN/deta weights, left / right nodes
-  re[0] = -op_add(S0b, S1l);
+  re[0] = op_neg(op_add(S0b, S1l));
   re[1] = op_sub(S0b, S1r);
   re[2] = op_add(S0t, S1r);
   re[3] = op_sub(S1l, S0t);
@@ -190,9 +234,9 @@ __device__ __forceinline__ void grid_element(const T (&Tn)[4], const T (&Kn)[4],
     dK[2] = lin2(a, Cmr, b, Cpr);
     dK[3] = lin2(a, Cml, b, Cpl);
   } else {
-    dK[0] = dK[1] = dK[2] = dK[3] = (T)0;
+    dK[0] = dK[1] = dK[2] = dK[3] = bcd<T>(0.0);
   }
-  e_el = op_fma(Tn[3], re[3], op_fma(Tn[2], re[2], op_fma(Tn[1], re[1], op_mul(Tn[0], re[0]))));
+  e_el = op_fma(eg[3], ck[3], op_fma(eg[2], ck[2], op_fma(eg[1], ck[1], op_mul(eg[0], ck[0]))));
 }
 
 }  // namespace
@@ -231,28 +275,35 @@ __device__ __forceinline__ void copy_bulk(const RowCopy& r, const T* base, T* ds
   if (r.bytes) bulk_g2s(smem_u32(dst), base + r.a0, r.bytes, bar);
 }
 
-template <class T, int NL, bool DIAG, bool GK>
+template <class S, int NS, int NL, bool DIAG, bool GK>
 // 9 warps per CTA (8 consumers + the producer).  Registers are per SCHEDULER (16 K each): 96 registers let a scheduler
-// host 5 float64 warps (two CTAs = 18 warps per SM), 72 registers 7 float32 warps (three CTAs = 27 warps)
-__global__ void __launch_bounds__(288) __maxnreg__(sizeof(T) == 8 ? 96 : 72) energy_grid_kernel(const GridArgs<T> args) {
+// host 5 warps (two CTAs = 18 warps per SM: float64, and float32 with two samples per lane), 72 registers 7 warps
+// (three CTAs = 27 warps: float32, one sample per lane)
+__global__ void __launch_bounds__(288) __maxnreg__((sizeof(S) == 8 || NS == 2) ? 96 : 72)
+    energy_grid_kernel(const GridArgs<S> args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  using Pair = NodePair<T>;
-  constexpr int PER = 16 / (int)sizeof(T);
+  using V = typename LaneT<S, NS>::type;                     // lane value: one sample, or two float32 samples
+  using Pair = NodePair<V>;
+  constexpr int PER = 16 / (int)sizeof(S);
+  constexpr int NROW = 2 * NS + 1;                           // ring rows per slot: T (per sample), K (per sample), D
   const int W = args.W, tid = threadIdx.x, w = tid >> 5, l = tid & 31;
-  // shared memory: ring [kRing][3 rows: T, K, D][row_bytes] | left [W][rows] | right [W][rows] | barriers
+  // shared memory: ring [kRing][NROW][row_bytes] | left [W][rows] | right [W][rows] | barriers
   unsigned char* const ring = smem_raw;
-  const int slot_bytes = 3 * args.row_bytes;
+  const int slot_bytes = NROW * args.row_bytes;
   Pair* const left = reinterpret_cast<Pair*>(smem_raw + (size_t)kRing * slot_bytes);
   Pair* const right = left + (size_t)W * args.rows;
   unsigned long long* const bars = reinterpret_cast<unsigned long long*>(right + (size_t)W * args.rows);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kRing);
 
-  // item = (sample, chunk of node rows, panel of element columns)
+  // item = (sample group, chunk of node rows, panel of element columns)
   long long item = blockIdx.x;
   const int panel = (int)(item % args.npanels);
   item /= args.npanels;
   const int chunk = (int)(item % args.nchunks);
-  const long long smp = item / args.nchunks;
+  long long smp[NS];                                         // the lane's samples (an odd batch repeats its last one)
+  smp[0] = (item / args.nchunks) * NS;
+  if constexpr (NS == 2) smp[1] = smp[0] + 1 < args.nb ? smp[0] + 1 : smp[0];
+  const bool second = NS == 2 && smp[0] + 1 < args.nb;       // the second sample is a real one
   const int nx = args.nx, ny = args.ny, NXn = nx + 1;
   const int sp = panel * (32 * W - 1);                       // first element column of the panel
   const int ncols = min(32 * W + 1, NXn - sp);               // node columns the panel stages
@@ -277,23 +328,30 @@ __global__ void __launch_bounds__(288) __maxnreg__(sizeof(T) == 8 ? 96 : 72) ene
       for (int i = 0; i < nstage; ++i) {
         const int slot = i % kRing;
         if (i >= kRing) mbar_wait(empty0 + 8 * slot, ((i / kRing) - 1) & 1);
-        const long long first = smp * args.nn + (long long)(e_beg + i) * NXn + sp;
-        const long long first_d = (long long)(e_beg + i) * NXn + sp;
-        T* const dT = reinterpret_cast<T*>(ring + (size_t)slot * slot_bytes);
-        T* const dK = reinterpret_cast<T*>(ring + (size_t)slot * slot_bytes + args.row_bytes);
-        T* const dD = reinterpret_cast<T*>(ring + (size_t)slot * slot_bytes + 2 * args.row_bytes);
+        unsigned char* const base = ring + (size_t)slot * slot_bytes;
         const uint32_t bar = full0 + 8 * slot;
-        const RowCopy cu = plan_row<T>(total, first, ncols);           // u and ctrl: same shape, same offsets
-        const RowCopy cd = plan_row<T>(args.nn, first_d, ncols);
+        const long long first_d = (long long)(e_beg + i) * NXn + sp;
+        RowCopy cu[NS];                                      // u and ctrl: same shape, same offsets
+#pragma unroll
+        for (int j = 0; j < NS; ++j) cu[j] = plan_row<S>(total, smp[j] * args.nn + first_d, ncols);
+        const RowCopy cd = plan_row<S>(args.nn, first_d, ncols);
         // plain tail stores (the last row of the last sample only) first, then the arrive that publishes them and
         // arms the transaction count, then the bulk copies that complete it
-        copy_tail<T>(cu, args.u, dT);
-        copy_tail<T>(cu, args.ctrl, dK);
-        if (has_dirv) copy_tail<T>(cd, args.dir_values, dD);
-        mbar_expect_tx(bar, 2 * cu.bytes + (has_dirv ? cd.bytes : 0u));
-        copy_bulk<T>(cu, args.u, dT, bar);
-        copy_bulk<T>(cu, args.ctrl, dK, bar);
-        if (has_dirv) copy_bulk<T>(cd, args.dir_values, dD, bar);
+        uint32_t bytes = has_dirv ? cd.bytes : 0u;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          copy_tail<S>(cu[j], args.u, reinterpret_cast<S*>(base + j * args.row_bytes));
+          copy_tail<S>(cu[j], args.ctrl, reinterpret_cast<S*>(base + (NS + j) * args.row_bytes));
+          bytes += 2 * cu[j].bytes;
+        }
+        if (has_dirv) copy_tail<S>(cd, args.dir_values, reinterpret_cast<S*>(base + 2 * NS * args.row_bytes));
+        mbar_expect_tx(bar, bytes);
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          copy_bulk<S>(cu[j], args.u, reinterpret_cast<S*>(base + j * args.row_bytes), bar);
+          copy_bulk<S>(cu[j], args.ctrl, reinterpret_cast<S*>(base + (NS + j) * args.row_bytes), bar);
+        }
+        if (has_dirv) copy_bulk<S>(cd, args.dir_values, reinterpret_cast<S*>(base + 2 * NS * args.row_bytes), bar);
       }
     }
   } else {
@@ -315,45 +373,65 @@ __global__ void __launch_bounds__(288) __maxnreg__(sizeof(T) == 8 ? 96 : 72) ene
     const bool wdirv = wdir && has_dirv, wcut = wdir && args.dir_flag != nullptr;
     const bool has_gk = GK && args.grad_k != nullptr;
 
-    const T ji[4] = {args.jinv[0], args.jinv[1], args.jinv[2], args.jinv[3]};
-    const T wd = args.wd, beta = args.beta, cexp = args.cexp, scale = args.out_scale;
-    // shared-memory addresses of this lane's entries in ring slot 0 (T row; the K and D rows follow at row_bytes)
-    const uint32_t ring_bytes = (uint32_t)(kRing * slot_bytes);
-    const uint32_t a_own = smem_u32(ring) + (uint32_t)i_own * (uint32_t)sizeof(T);
+    const V ji[4] = {bc<V>(args.jinv[0]), bc<V>(args.jinv[1]), bc<V>(args.jinv[2]), bc<V>(args.jinv[3])};
+    const V wd = bc<V>(args.wd), beta = bc<V>(args.beta), cexp = bc<V>(args.cexp), scale = bc<V>(args.out_scale);
+    const V zero = bcd<V>(0.0);
+    // shared-memory addresses of this lane's entries in ring slot 0 (first T row; the other rows follow at row_bytes)
+    const uint32_t ring_bytes = (uint32_t)(kRing * slot_bytes), rb = (uint32_t)args.row_bytes;
+    const uint32_t a_own = smem_u32(ring) + (uint32_t)i_own * (uint32_t)sizeof(S);
     uint32_t slot_off = 0, parity = 0, slot_bar = 0;         // ring position of the next row to take
-    uint32_t sh_u = (uint32_t)((smp * args.nn + (long long)e_beg * NXn + sp) & (PER - 1)) * (uint32_t)sizeof(T);
-    uint32_t sh_d = (uint32_t)(((long long)e_beg * NXn + sp) & (PER - 1)) * (uint32_t)sizeof(T);
-    const uint32_t sh_step = (uint32_t)(NXn & (PER - 1)) * (uint32_t)sizeof(T);
+    const long long row_d = (long long)e_beg * NXn + sp;
+    uint32_t sh_u[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) sh_u[j] = (uint32_t)((smp[j] * args.nn + row_d) & (PER - 1)) * (uint32_t)sizeof(S);
+    uint32_t sh_d = (uint32_t)(row_d & (PER - 1)) * (uint32_t)sizeof(S);
+    const uint32_t sh_step = (uint32_t)(NXn & (PER - 1)) * (uint32_t)sizeof(S);
     // global element offset of node (cc, row) within the sample, as 32 bits (nn < 2^31 is checked by the host)
     unsigned node = (unsigned)e_beg * (unsigned)NXn + (unsigned)cc;
-    T* const gu0 = args.grad_u + smp * args.nn;
-    T* const gk0 = has_gk ? args.grad_k + smp * args.nn : gu0;
+    S* gu0[NS];
+    S* gk0[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      gu0[j] = args.grad_u + smp[j] * args.nn;
+      gk0[j] = has_gk ? args.grad_k + smp[j] * args.nn : gu0[j];
+    }
     const uint8_t* const fl0 = wcut ? args.dir_flag : args.col_dir;   // never read unless wcut
     uint32_t a_left = smem_u32(left + (size_t)w * args.rows), a_right = smem_u32(right + (size_t)w * args.rows);
 
     auto lds = [](uint32_t a) {
-      T v;
-      if constexpr (sizeof(T) == 8) asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(a));
+      S v;
+      if constexpr (sizeof(S) == 8) asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(a));
       else asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(a));
       return v;
     };
-    auto sts_pair = [](uint32_t a, T x, T y) {
-      if constexpr (sizeof(T) == 8) asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(a), "d"(x), "d"(y) : "memory");
+    // value of ring row `row0` (+ 1 for the second sample) at byte address a
+    auto ldv = [&](uint32_t a, const uint32_t (&sh)[NS]) {
+      if constexpr (NS == 2) return make_float2(lds(a + sh[0]), lds(a + rb + sh[1]));
+      else return lds(a + sh[0]);
+    };
+    auto sts_pair = [](uint32_t a, V x, V y) {
+      if constexpr (sizeof(V) == 8 && NS == 1) asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(a), "d"(x), "d"(y) : "memory");
+      else if constexpr (NS == 2)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "f"(x.x), "f"(x.y), "f"(y.x), "f"(y.y) : "memory");
       else asm volatile("st.shared.v2.f32 [%0], {%1, %2};\n" ::"r"(a), "f"(x), "f"(y) : "memory");
     };
+    auto shfl_up = [](V v) {
+      if constexpr (NS == 2) return make_float2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
+      else return __shfl_up_sync(0xffffffffu, v, 1);
+    };
     // the four values of the next staged node row: own / right column of T and K
-    auto take = [&](T& t0, T& k0, T& t1, T& k1) {
+    auto take = [&](V& t0, V& k0, V& t1, V& k1) {
       mbar_wait(full0 + slot_bar, parity);
-      const uint32_t aT = a_own + slot_off + sh_u, aK = aT + (uint32_t)args.row_bytes;
-      t0 = lds(aT);
-      t1 = lds(aT + (uint32_t)sizeof(T));
-      k0 = lds(aK);
-      k1 = lds(aK + (uint32_t)sizeof(T));
+      const uint32_t aT = a_own + slot_off, aK = aT + NS * rb;
+      t0 = ldv(aT, sh_u);
+      t1 = ldv(aT + (uint32_t)sizeof(S), sh_u);
+      k0 = ldv(aK, sh_u);
+      k1 = ldv(aK + (uint32_t)sizeof(S), sh_u);
       if (wdirv) {                                           // Dirichlet overwrite (fe_loss.py:91-92, 255)
-        const uint32_t aD = a_own + slot_off + 2u * (uint32_t)args.row_bytes + sh_d;
-        const T d0 = lds(aD), d1 = lds(aD + (uint32_t)sizeof(T));
-        t0 = (d0 == d0) ? d0 : t0;
-        t1 = (d1 == d1) ? d1 : t1;
+        const uint32_t aD = aT + 2u * NS * rb + sh_d;
+        const S d0 = lds(aD), d1 = lds(aD + (uint32_t)sizeof(S));
+        if (d0 == d0) t0 = bc<V>(d0);
+        if (d1 == d1) t1 = bc<V>(d1);
       }
       __syncwarp();
       if (l == 0) mbar_arrive(empty0 + slot_bar);
@@ -364,84 +442,113 @@ __global__ void __launch_bounds__(288) __maxnreg__(sizeof(T) == 8 ? 96 : 72) ene
         slot_bar = 0;
         parity ^= 1;
       }
-      sh_u = (sh_u + sh_step) & 15u;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) sh_u[j] = (sh_u[j] + sh_step) & 15u;
       sh_d = (sh_d + sh_step) & 15u;
     };
 
-    T en = (T)0;
+    V en = zero;
     // node row (at offset `node`) is complete once the element rows below and above it are in: left half (own lane:
     // below + above) + right half of the lane to the left; the column two warps share waits for `combine`
     uint8_t cut_now = 0;                                     // dir_flag of node (cc, current row), loaded one row ahead
     if (wcut) cut_now = fl0[node + (e_beg < r0 ? (unsigned)NXn : 0u)];
-    auto finish_row = [&](T leftR, T leftK, T rpR, T rpK, bool more) {
-      const T inR = shfl_up1(rpR), inK = shfl_up1(rpK);
+    auto finish_row = [&](V leftR, V leftK, V rpR, V rpK, bool more) {
+      const V inR = shfl_up(rpR), inK = shfl_up(rpK);
       uint8_t cut_next = 0;
       if (wcut && more) cut_next = fl0[node + (unsigned)NXn];
       if (keep_left) sts_pair(a_left, leftR, leftK);
       if (keep_right) sts_pair(a_right, rpR, rpK);
-      a_left += 2 * (uint32_t)sizeof(T);
-      a_right += 2 * (uint32_t)sizeof(T);
-      T R = (l > 0) ? op_add(leftR, inR) : leftR;
-      const T K = (l > 0) ? op_add(leftK, inK) : leftK;
-      if (wcut && cut_now != 0) R = (T)0;
+      a_left += (uint32_t)sizeof(Pair);
+      a_right += (uint32_t)sizeof(Pair);
+      V R = (l > 0) ? op_add(leftR, inR) : leftR;
+      const V K = (l > 0) ? op_add(leftK, inK) : leftK;
+      if (wcut && cut_now != 0) R = zero;
       if (write_own) {
-        gu0[node] = op_mul(scale, R);
-        if (has_gk) gk0[node] = op_mul(scale, K);
+        const V oR = op_mul(scale, R), oK = op_mul(scale, K);
+        if constexpr (NS == 2) {
+          gu0[0][node] = oR.x;
+          if (has_gk) gk0[0][node] = oK.x;
+          if (second) {
+            gu0[1][node] = oR.y;
+            if (has_gk) gk0[1][node] = oK.y;
+          }
+        } else {
+          gu0[0][node] = oR;
+          if (has_gk) gk0[0][node] = oK;
+        }
       }
       cut_now = cut_next;
     };
-    // one element row: corners (b0, b1) below, (t0, t1) above, carries of the row below in (oc, rc)
-    T ocR = (T)0, ocK = (T)0, rcR = (T)0, rcK = (T)0;
-    auto element = [&](T Tb0, T Kb0, T Tb1, T Kb1, T Tt0, T Kt0, T Tt1, T Kt1, T (&re)[4], T (&dK)[4], T& e_el) {
-      const T Tn[4] = {Tb0, Tb1, Tt1, Tt0}, Kn[4] = {Kb0, Kb1, Kt1, Kt0};
-      grid_element<T, NL, DIAG, GK>(Tn, Kn, ji, wd, beta, cexp, re, dK, e_el);
+    // one element row between the edge values of the node rows below (B) and above (U); carries of the row below in
+    // (oc, rc)
+    using Edge = GridEdge<V>;
+    V ocR = zero, ocK = zero, rcR = zero, rcK = zero;
+    auto element = [&](const Edge& B, const Edge& U, V (&re)[4], V (&dK)[4], V& e_el) {
+      grid_element<V, NL, DIAG, GK>(B, U, ji, wd, beta, cexp, re, dK, e_el);
       if (!all_valid) {                                      // warp-uniform: a ragged last warp only
         if (!el_valid) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) re[q] = dK[q] = (T)0;
-          e_el = (T)0;
+          for (int q = 0; q < 4; ++q) re[q] = dK[q] = zero;
+          e_el = zero;
         }
       }
     };
-    auto step = [&](T Tb0, T Kb0, T Tb1, T Kb1, T Tt0, T Kt0, T Tt1, T Kt1) {
-      T re[4], dK[4], e_el;
-      element(Tb0, Kb0, Tb1, Kb1, Tt0, Kt0, Tt1, Kt1, re, dK, e_el);
+    auto step = [&](const Edge& B, const Edge& U) {
+      V re[4], dK[4], e_el;
+      element(B, U, re, dK, e_el);
       en = op_add(en, e_el);
       finish_row(op_add(ocR, re[0]), op_add(ocK, dK[0]), op_add(rcR, re[1]), op_add(rcK, dK[1]), true);
       node += (unsigned)NXn;
       ocR = re[3]; ocK = dK[3]; rcR = re[2]; rcK = dK[2];
     };
+    auto take_edge = [&]() {
+      V t0, k0, t1, k1;
+      take(t0, k0, t1, k1);
+      return grid_edge<V>(t0, t1, k0, k1);
+    };
 
-    T A0, AK0, A1, AK1, B0, BK0, B1, BK1;                    // two register sets of corner values, used alternately
-    take(A0, AK0, A1, AK1);
+    Edge EA = take_edge(), EB;                               // two register sets of edge values, used alternately
     int e = e_beg;
     if (e_beg < r0) {
       // the recomputed element row below the chunk: only its shares of node row r0 (the carries) are kept
-      take(B0, BK0, B1, BK1);
-      T re[4], dK[4], e_el;
-      element(A0, AK0, A1, AK1, B0, BK0, B1, BK1, re, dK, e_el);
+      EB = take_edge();
+      V re[4], dK[4], e_el;
+      element(EA, EB, re, dK, e_el);
       ocR = re[3]; ocK = dK[3]; rcR = re[2]; rcK = dK[2];
       node += (unsigned)NXn;
-      A0 = B0; AK0 = BK0; A1 = B1; AK1 = BK1;
+      EA = EB;
       ++e;
     }
     for (; e + 1 < e_end; e += 2) {
-      take(B0, BK0, B1, BK1);
-      step(A0, AK0, A1, AK1, B0, BK0, B1, BK1);
-      take(A0, AK0, A1, AK1);
-      step(B0, BK0, B1, BK1, A0, AK0, A1, AK1);
+      EB = take_edge();
+      step(EA, EB);
+      EA = take_edge();
+      step(EB, EA);
     }
     if (e < e_end) {
-      take(B0, BK0, B1, BK1);
-      step(A0, AK0, A1, AK1, B0, BK0, B1, BK1);
+      EB = take_edge();
+      step(EA, EB);
     }
     if (r1 == ny + 1) finish_row(ocR, ocK, rcR, rcK, false);  // the top node row of the grid closes with the carries alone
 
-    // energy share of this warp
-    if (!count) en = (T)0;
+    // energy shares of this warp
+    if (!count) en = zero;
+    const long long pslot = ((long long)panel * args.nchunks + chunk) * W + w;
+    if constexpr (NS == 2) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) en += __shfl_xor_sync(0xffffffffu, en, o);
-    if (l == 0) args.partial[smp * args.npart + ((long long)panel * args.nchunks + chunk) * W + w] = en;
+      for (int o = 16; o > 0; o >>= 1) {
+        en.x += __shfl_xor_sync(0xffffffffu, en.x, o);
+        en.y += __shfl_xor_sync(0xffffffffu, en.y, o);
+      }
+      if (l == 0) {
+        args.partial[smp[0] * args.npart + pslot] = en.x;
+        if (second) args.partial[smp[1] * args.npart + pslot] = en.y;
+      }
+    } else {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) en += __shfl_xor_sync(0xffffffffu, en, o);
+      if (l == 0) args.partial[smp[0] * args.npart + pslot] = en;
+    }
   }
 
   // combine: node columns sp + 32 b (b = 1..W) got their left half from lane 31 of warp b - 1 and their right half from
@@ -453,7 +560,7 @@ __global__ void __launch_bounds__(288) __maxnreg__(sizeof(T) == 8 ? 96 : 72) ene
     const int col = sp + 32 * bnd;
     if (col > nx || (bnd == W && col != nx)) continue;
     const Pair lo = right[(size_t)(bnd - 1) * args.rows + i];
-    T R = lo.t, K = lo.k;
+    V R = lo.t, K = lo.k;
     if (bnd < W) {
       const Pair hi = left[(size_t)bnd * args.rows + i];
       R = op_add(hi.t, R);                                   // same order as finish_row: own (left) half + incoming
@@ -461,8 +568,18 @@ __global__ void __launch_bounds__(288) __maxnreg__(sizeof(T) == 8 ? 96 : 72) ene
     }
     const long long node = (long long)(r0 + i) * NXn + col;
     const bool cut = args.dir_flag ? args.dir_flag[node] != 0 : false;
-    args.grad_u[smp * args.nn + node] = cut ? (T)0 : op_mul(args.out_scale, R);
-    if (GK && args.grad_k) args.grad_k[smp * args.nn + node] = op_mul(args.out_scale, K);
+    const V oR = op_mul(bc<V>(args.out_scale), R), oK = op_mul(bc<V>(args.out_scale), K);
+    if constexpr (NS == 2) {
+      args.grad_u[smp[0] * args.nn + node] = cut ? 0.f : oR.x;
+      if (GK && args.grad_k) args.grad_k[smp[0] * args.nn + node] = oK.x;
+      if (second) {
+        args.grad_u[smp[1] * args.nn + node] = cut ? 0.f : oR.y;
+        if (GK && args.grad_k) args.grad_k[smp[1] * args.nn + node] = oK.y;
+      }
+    } else {
+      args.grad_u[smp[0] * args.nn + node] = cut ? (S)0 : oR;
+      if (GK && args.grad_k) args.grad_k[smp[0] * args.nn + node] = oK;
+    }
   }
 }
 
@@ -484,19 +601,19 @@ int grid_row_bytes(int W, long long nx) {
   const long long ncols = (32LL * W + 1 < nx + 1) ? 32LL * W + 1 : nx + 1;
   return (int)(((ncols + 16 / sizeof(T)) * sizeof(T) + 15) / 16 * 16);   // + shift + one entry read past the last column
 }
-template <class T>
+template <class T, int NS>
 size_t grid_smem(int W, long long nx, int rows) {
-  return (size_t)kRing * 3 * grid_row_bytes<T>(W, nx) + (size_t)2 * W * rows * 2 * sizeof(T) + 2 * kRing * 8;
+  return (size_t)kRing * (2 * NS + 1) * grid_row_bytes<T>(W, nx) + (size_t)2 * W * rows * 2 * NS * sizeof(T) + 2 * kRing * 8;
 }
 
-template <class T, int NL, bool DIAG, bool GK>
+template <class T, int NS, int NL, bool DIAG, bool GK>
 int launch_grid(cudaStream_t s, GridArgs<T> a, T* energy) {
-  auto kern = energy_grid_kernel<T, NL, DIAG, GK>;
+  auto kern = energy_grid_kernel<T, NS, NL, DIAG, GK>;
   const GridShape g = grid_shape(a.nx);
   const int threads = 32 * (g.W + 1);
   static PerDeviceOnce configured;
   if (configured.need()) {
-    FOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_smem<T>(8, 256, 128)));
+    FOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_smem<T, NS>(8, 256, 128)));
     FOL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured.done();
   }
@@ -508,14 +625,15 @@ int launch_grid(cudaStream_t s, GridArgs<T> a, T* energy) {
   FOL_CUDA(cudaGetDevice(&dev));
   FOL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int nrows_total = a.ny + 1;
+  const long long groups = cdiv(a.nb, NS);
   for (int rows = kMinRows; rows <= 128; ++rows) {
     if (rows > nrows_total && rows != kMinRows) break;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, grid_smem<T>(g.W, a.nx, rows)) != cudaSuccess ||
-        per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, grid_smem<T, NS>(g.W, a.nx, rows)) !=
+            cudaSuccess || per_sm < 1)
       continue;
     const long long nchunks = cdiv(nrows_total, rows);
-    const long long items = nchunks * g.npanels * a.nb, slots = (long long)sms * per_sm;
+    const long long items = nchunks * g.npanels * groups, slots = (long long)sms * per_sm;
     const double waves = (double)cdiv(items, slots);
     const double work = (double)(a.ny + (nchunks - 1)) + 3.0 * nchunks;     // element rows computed + fill, per sample
     const double eff = ((double)a.ny / work) * ((double)items / (waves * slots));
@@ -532,13 +650,23 @@ int launch_grid(cudaStream_t s, GridArgs<T> a, T* energy) {
   a.W = g.W;
   a.row_bytes = grid_row_bytes<T>(g.W, a.nx);
   a.npart = a.nchunks * a.npanels * g.W;
-  const long long items = (long long)a.nchunks * a.npanels * a.nb;
+  const long long items = (long long)a.nchunks * a.npanels * groups;
   FOL_REQUIRE(items < (1LL << 31), "fol_energy_and_grads_grid: too many work items for one launch");
-  kern<<<(unsigned)items, threads, grid_smem<T>(g.W, a.nx, best_rows), s>>>(a);
+  kern<<<(unsigned)items, threads, grid_smem<T, NS>(g.W, a.nx, best_rows), s>>>(a);
   int rc = check_launch("energy_grid_kernel");
   if (rc) return rc;
   energy_sum_kernel<T><<<(unsigned)cdiv(a.nb, 8), 256, 0, s>>>(a.partial, a.nb, a.npart, energy);
   return check_launch("energy_sum_kernel");
+}
+
+template <class T, int NL, bool DIAG, bool GK>
+int launch_grid_ns(cudaStream_t s, const GridArgs<T>& a, T* energy) {
+  if constexpr (sizeof(T) == 4) {
+    // float32: two samples per lane (packed FP32 instructions) unless the batch is a single sample
+    static const int pair = energy2_env_int("FOL_ENERGY_GRID_PAIR", 1);
+    if (pair && a.nb >= 2) return launch_grid<T, 2, NL, DIAG, GK>(s, a, energy);
+  }
+  return launch_grid<T, 1, NL, DIAG, GK>(s, a, energy);
 }
 
 template <class T>
@@ -550,8 +678,8 @@ int dispatch_grid(cudaStream_t s, const GridArgs<T>& a, T* energy) {
   const bool gk = a.grad_k != nullptr;
 #define FOL_GRID(NLV)                                                                   \
   if (nl == NLV) {                                                                      \
-    if (diag) return gk ? launch_grid<T, NLV, true, true>(s, a, energy) : launch_grid<T, NLV, true, false>(s, a, energy);   \
-    return gk ? launch_grid<T, NLV, false, true>(s, a, energy) : launch_grid<T, NLV, false, false>(s, a, energy);           \
+    if (diag) return gk ? launch_grid_ns<T, NLV, true, true>(s, a, energy) : launch_grid_ns<T, NLV, true, false>(s, a, energy);   \
+    return gk ? launch_grid_ns<T, NLV, false, true>(s, a, energy) : launch_grid_ns<T, NLV, false, false>(s, a, energy);           \
   }
   FOL_GRID(0) FOL_GRID(1) FOL_GRID(2) FOL_GRID(3) FOL_GRID(4) FOL_GRID(-1)
 #undef FOL_GRID
