@@ -340,9 +340,18 @@ def fol_loss_grad_bench(torch, dist, rank, world, steps, warmup):
 
     hbm, _ = measured_peaks()
     bytes_per_sample = 32.0 * nn  # read u, K; write dE/du, dE/dK (f64)
-    # f64 work per sample (SASS count of energy_tile2_kernel, profiles/r1/energy_tile2_sass_hist.txt):
-    # element phase 133 DFMA + 28 DMUL per element, node phase 8 DADD + 1 DFMA + 2 DMUL per node
+    # ALGORITHMIC f64 work per sample (200-500 flop per element): the generic Quad4 / 2 x 2 formulation as
+    # the round-1 kernel executed it (SASS count, profiles/r1/energy_tile2_sass_hist.txt): element phase 133 DFMA +
+    # 28 DMUL per element, node phase 8 DADD + 1 DFMA + 2 DMUL per node.  Kept as the unit of work so that rounds compare.
     flops_per_sample = (2 * 133 + 28) * 65536.0 + (8 + 2 + 2) * float(nn)
+    # what the structured-grid kernel (csrc/energy_grid.cu) EXECUTES per element row step and lane: 69 DMUL + 21 DADD +
+    # 33 DFMA = 123 FP64 instructions (sum-factorised element 114, node sums / scaling 9), each 2 pipe cycles
+    fp64_instr_per_element, exec_flops_per_element = 123.0, 69.0 + 21.0 + 2 * 33.0
+    # the loss + VJP kernel alone (C ABI call fol_energy_and_grads_grid + its energy sum), CUDA events
+    kern = lambda: loss._energy_and_grads(Kb, ub, dir_values=loss._dir_full, dir_flag=loss._dir_flag, out_scale=1.0 / B)
+    for _ in range(3):
+        kern()
+    ms_kernel, = max_over_ranks(torch, dist, world, [event_time_ms(torch, kern, steps)])
     # same physics step in float32 (the reference's default precision: jax_enable_x64 is off in its examples)
     loss32 = ThermalLoss2DQuad("fol_thermal32", {"dirichlet_bc_dict": {"T": {"left": 1.0, "right": 0.1}},
                                                  "beta": 2.0, "c": 4, "dtype": "float32"}, mesh)
@@ -352,6 +361,11 @@ def fol_loss_grad_bench(torch, dist, rank, world, steps, warmup):
     for _ in range(3):
         physics_only32()
     ms_phys32 = event_time_ms(torch, physics_only32, steps)
+    kern32 = lambda: loss32._energy_and_grads(K32, u32, dir_values=loss32._dir_full, dir_flag=loss32._dir_flag,
+                                              out_scale=1.0 / B)
+    for _ in range(3):
+        kern32()
+    ms_kernel32 = event_time_ms(torch, kern32, steps)
     # same FOL step with the network in float32 (flax's default parameter dtype) feeding the float64 physics loss
     torch.manual_seed(0)
     net32 = torch.nn.Sequential(torch.nn.Linear(64, 256), torch.nn.Tanh(), torch.nn.Linear(256, nn)).to("cuda")
@@ -371,15 +385,38 @@ def fol_loss_grad_bench(torch, dist, rank, world, steps, warmup):
     if world > 1:
         dist.barrier()
     ms_mixed, = max_over_ranks(torch, dist, world, [event_time_ms(torch, step_mixed, steps)])
+
+    # the whole step in float32: the reference's default precision (jax_enable_x64 is off in its examples)
+    def step_f32():
+        for p in net32.parameters():
+            p.grad = None
+        uu = torch.sigmoid(net32(latent32))
+        mean, _ = loss32.ComputeBatchLoss(K32, uu)
+        mean.backward()
+        reducer32.wait()
+    for _ in range(3):
+        step_f32()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_f32, = max_over_ranks(torch, dist, world, [event_time_ms(torch, step_f32, steps)])
     reducer.close()
     reducer32.close()
     tf = ctypes.c_double()
     fp64_peak = tf.value if (rank == 0 and _lib.load().fol_measure_fma_peak(_lib.F64, ctypes.byref(tf)) == 0) else None
     ach_tf = flops_per_sample * B / (ms_phys * 1e-3) / 1e12
+    grid = loss._grid_plan() is not None
+    kernel_name = ("energy_grid_kernel (structured-grid march: producer warp + bulk-copy row ring, sum-factorised Quad4, "
+                   "Dirichlet overwrite and 1/B scale fused; float32: two samples per lane on FMUL2 / FFMA2)" if grid else
+                   "energy_qt_kernel / energy_tile2_kernel (tile plan through the connectivity)")
     return {"metric": "fol_loss_grad_samples_per_s", "value": B * world / (ms_step * 1e-3), "unit": "samples/s",
             "scaling": "weak", "physics_only_samples_per_s": B * world / (ms_phys * 1e-3), "ms_per_step": ms_step,
             "ms_per_step_physics_only": ms_phys,
             "physics_only_f32_samples_per_s_per_gpu": B / (ms_phys32 * 1e-3),
+            "kernel_only": {"f64_ms": ms_kernel, "f64_samples_per_s_per_gpu": B / (ms_kernel * 1e-3),
+                            "f32_ms": ms_kernel32, "f32_samples_per_s_per_gpu": B / (ms_kernel32 * 1e-3),
+                            "note": "fol_energy_and_grads_grid + energy sum alone (CUDA events); physics_only adds the "
+                                    "loss tail, the autograd node and the (no-op) backward scaling kernel"},
             "headline_note": "the path's own number is physics_only_samples_per_s (loss + VJP kernels); `value` adds "
                              "the caller's f64 MLP (torch / cuBLAS) and the gradient all-reduce",
             "strong": {"scaling": "strong", "global_batch": B, "batch_per_gpu": nb_s,
@@ -393,15 +430,30 @@ def fol_loss_grad_bench(torch, dist, rank, world, steps, warmup):
                                         "ms_per_step": ms_mixed,
                                         "note": "MLP in float32 (flax default parameter dtype), physics loss + VJP in "
                                                 "float64; the headline value above keeps the whole step in float64"},
+            "f32_network_f32_physics": {"value": B * world / (ms_f32 * 1e-3), "unit": "samples/s", "ms_per_step": ms_f32,
+                                        "note": "network, loss and VJP in float32 (the reference's default precision; "
+                                                "parity tolerance 1e-5)"},
             "config": {"workload": "thermal_quad256_loss_vjp_f64", "batch_per_gpu": B, "mesh": "256x256 quads",
                        "beta": 2.0, "c": 4, "network": "MLP 64-256-66049 (f64, torch/cuBLAS: caller code, not the path)",
-                       "kernel": "energy_tile2_kernel (pipelined fused loss + VJP, Dirichlet overwrite and 1/B scale fused)",
+                       "kernel": kernel_name,
                        "parallelism": f"dp{world}, gradient all-reduce started per parameter from autograd hooks "
                                       "(overlaps the rest of backward)",
                        "tolerance": "f64 1e-12, f32 1e-5, norm-wise (|x - ref|_max <= tol |ref|_max) in the parity tests"},
             "roofline_physics": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                                  "frac": (ach_tf / fp64_peak) if fp64_peak else None,
                                  "flops_per_sample": flops_per_sample,
+                                 "flops_convention": "ALGORITHMIC work of the generic Quad4 / 2 x 2 formulation (306 flop "
+                                                     "per element, SURVEY.md 8d), the same unit as round 1",
+                                 "executed": ({"fp64_instructions_per_element": fp64_instr_per_element,
+                                               "flops_per_element": exec_flops_per_element,
+                                               "tflops": exec_flops_per_element * 65536.0 * B / (ms_kernel * 1e-3) / 1e12,
+                                               "fp64_pipe_busy_of_kernel": (fp64_instr_per_element * 65536.0 * B / 32.0
+                                                                            * 2.0 / (148 * 4 * (ms_kernel * 1e-3)
+                                                                                     * 1.85e9)),
+                                               "note": "what csrc/energy_grid.cu issues (sum-factorised element): 2 pipe "
+                                                       "cycles per FP64 warp instruction, 148 SMs x 4 schedulers at the "
+                                                       "1.85 GHz of the measured DFMA peak; ncu: profiles/r2/"
+                                                       "energy_grid_f64_ncu_summary.txt"} if grid else None),
                                  "note": "the f64 loss+VJP kernel is FP64-pipe-bound (SURVEY.md 8d); HBM view below"},
             "roofline_physics_hbm": {"bound": "hbm", "achieved": bytes_per_sample * B / (ms_phys * 1e-3) / 1e9,
                                      "peak": hbm, "unit": "GB/s",
@@ -585,27 +637,31 @@ def newton_bench(torch):
     loss._sell_plan()
     plans = time.time() - t0
     loss.ComputeJacobianMatrixAndResidualVector = timed(loss.ComputeJacobianMatrixAndResidualVector, "assembly_s")
-    sell, bicg = linalg.SellOperator, linalg.bicgstab
+    sell, bicg, fused = linalg.SellOperator, linalg.bicgstab, linalg.bicgstab_fused
     linalg.SellOperator = timed(sell, "operator_s")
 
-    def counted(*a, **k):
-        x, info = timed(bicg, "krylov_s")(*a, **k)
-        split["krylov_iterations"] += max(info, 0)
-        split["newton_iterations"] += 1
-        return x, info
-    linalg.bicgstab = counted
+    def counted(fn):
+        def wrapper(*a, **k):
+            x, info = timed(fn, "krylov_s")(*a, **k)
+            split["krylov_iterations"] += max(info, 0)
+            split["newton_iterations"] += 1
+            return x, info
+        return wrapper
+    linalg.bicgstab, linalg.bicgstab_fused = counted(bicg), counted(fused)   # the solver picks the one-launch loop here
     try:
         solver.Solve(K, np.zeros(loss.GetTotalNumberOfDOFs()))
     finally:
-        linalg.SellOperator, linalg.bicgstab = sell, bicg
+        linalg.SellOperator, linalg.bicgstab, linalg.bicgstab_fused = sell, bicg, fused
     it = max(split["newton_iterations"], 1)
     return {"workload": "tet_neo_hooke_newton_f64 (70^3 Kuhn cells)", "elements": loss._ne,
             "dofs": loss.total_number_of_dofs, **split, "host_plans_s": plans,
             "final_residual_norm": solver.convergence_history[1]["res_norm"][-1],
             "per_newton_iteration_ms": {k[:-2]: 1e3 * split[k] / it for k in ("assembly_s", "operator_s", "krylov_s")},
             "assembly_elements_per_s": loss._ne * it / max(split["assembly_s"], 1e-12),
-            "note": "Krylov time is launch / host-read latency at this size (0.4 ms per BiCGSTAB iteration for 1.07 M "
-                    "dofs), not bandwidth: see profiles/r2"}
+            "krylov_ms_per_iteration": 1e3 * split["krylov_s"] / max(split["krylov_iterations"], 1),
+            "note": "Krylov loop: the one-launch cooperative BiCGSTAB (csrc/krylov_fused.cu; 0.26 ms per iteration at "
+                    "1.07 M dofs against 0.39 ms for the multi-launch loop with four host reads per iteration, two "
+                    "0.08 ms SELL products inside): see profiles/r2"}
 
 
 def halo_check(torch, dist, rank, world, part, loss, R, n):

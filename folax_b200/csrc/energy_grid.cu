@@ -52,7 +52,16 @@ struct GridArgs {
 
 namespace {
 
-constexpr int kRing = 8;      // node rows in flight per CTA
+#ifndef FOL_GRID_RING
+#define FOL_GRID_RING 8
+#endif
+#ifndef FOL_GRID_REGS64
+#define FOL_GRID_REGS64 96
+#endif
+#ifndef FOL_GRID_REGS32P
+#define FOL_GRID_REGS32P 72
+#endif
+constexpr int kRing = FOL_GRID_RING;      // node rows in flight per CTA (a power of two)
 
 template <class T>
 struct alignas(2 * sizeof(T)) NodePair {
@@ -277,9 +286,9 @@ __device__ __forceinline__ void copy_bulk(const RowCopy& r, const T* base, T* ds
 
 template <class S, int NS, int NL, bool DIAG, bool GK>
 // 9 warps per CTA (8 consumers + the producer).  Registers are per SCHEDULER (16 K each): 96 registers let a scheduler
-// host 5 warps (two CTAs = 18 warps per SM: float64, and float32 with two samples per lane), 72 registers 7 warps
-// (three CTAs = 27 warps: float32, one sample per lane)
-__global__ void __launch_bounds__(288) __maxnreg__((sizeof(S) == 8 || NS == 2) ? 96 : 72)
+// host 5 float64 warps (two CTAs = 18 warps per SM), 72 registers 7 float32 warps (three CTAs = 27 warps; measured
+// with two samples per lane: 0.337 ms at 72 registers, 0.382 ms at 96; float64 at 72 registers spills and gains nothing)
+__global__ void __launch_bounds__(288) __maxnreg__(sizeof(S) == 8 ? FOL_GRID_REGS64 : (NS == 2 ? FOL_GRID_REGS32P : 72))
     energy_grid_kernel(const GridArgs<S> args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using V = typename LaneT<S, NS>::type;                     // lane value: one sample, or two float32 samples
@@ -662,9 +671,11 @@ int launch_grid(cudaStream_t s, GridArgs<T> a, T* energy) {
 template <class T, int NL, bool DIAG, bool GK>
 int launch_grid_ns(cudaStream_t s, const GridArgs<T>& a, T* energy) {
   if constexpr (sizeof(T) == 4) {
-    // float32: two samples per lane (packed FP32 instructions) unless the batch is a single sample
+    // float32: two samples per lane on the packed FP32 instructions -- also for a single sample (evaluated twice,
+    // stored once), so that a sample's result never depends on the batch it came in (the packed and the scalar
+    // instruction streams were measured 1 ulp apart in a third of the entries)
     static const int pair = energy2_env_int("FOL_ENERGY_GRID_PAIR", 1);
-    if (pair && a.nb >= 2) return launch_grid<T, 2, NL, DIAG, GK>(s, a, energy);
+    if (pair) return launch_grid<T, 2, NL, DIAG, GK>(s, a, energy);
   }
   return launch_grid<T, 1, NL, DIAG, GK>(s, a, energy);
 }
@@ -681,7 +692,11 @@ int dispatch_grid(cudaStream_t s, const GridArgs<T>& a, T* energy) {
     if (diag) return gk ? launch_grid_ns<T, NLV, true, true>(s, a, energy) : launch_grid_ns<T, NLV, true, false>(s, a, energy);   \
     return gk ? launch_grid_ns<T, NLV, false, true>(s, a, energy) : launch_grid_ns<T, NLV, false, false>(s, a, energy);           \
   }
+#ifdef FOL_GRID_ONLY_NL4      /* tuning builds: one conductivity law, a sixth of the compile time */
+  FOL_GRID(4)
+#else
   FOL_GRID(0) FOL_GRID(1) FOL_GRID(2) FOL_GRID(3) FOL_GRID(4) FOL_GRID(-1)
+#endif
 #undef FOL_GRID
   return fail(FOL_ERR_INVALID, "fol_energy_and_grads_grid: bad conductivity law");
 }

@@ -148,6 +148,48 @@ def test_grid_kernel_float32():
     assert np.abs(gk - gK).max() <= 1e-5 * np.abs(gK).max()
 
 
+@pytest.mark.parametrize("B", [1, 2, 3, 7])
+@pytest.mark.parametrize("shear", [0.0, 0.25])
+def test_grid_kernel_float32_sample_pairs(B, shear):
+    """float32 runs two samples per lane on the packed FP32 instructions: even, odd and single-sample batches (an odd
+    batch evaluates its last sample twice and stores it once), each sample against the float64 oracle."""
+    mesh = grid_mesh(70, 23, shear=shear)
+    loss = make(mesh, dtype="float32")
+    rng = np.random.default_rng(60 + B)
+    K = rng.uniform(0.1, 1.0, (B, mesh.GetNumberOfNodes())).astype(np.float32)
+    u = rng.uniform(0.1, 1.0, (B, mesh.GetNumberOfNodes())).astype(np.float32)
+    mean, gu, gk = run(loss, K, u)
+    ref_mean, Eb, gU, gK = oracle(loss, mesh, K.astype(np.float64), u.astype(np.float64))
+    assert abs(mean - ref_mean) <= 1e-5 * np.abs(Eb).max()
+    for b in range(B):
+        assert np.abs(gu[b] - gU[b]).max() <= 1e-5 * np.abs(gU).max(), b
+        assert np.abs(gk[b] - gK[b]).max() <= 1e-5 * np.abs(gK).max(), b
+    # the pairing does not change a sample's result: sample 0 alone gives the same bits
+    if B > 1:
+        _, gu1, gk1 = run(make(mesh, dtype="float32"), K[:1], u[:1])
+        scale = np.float32(1.0 / B)                         # the kernel writes fl(scale * R) with scale = 1 / B
+        assert np.array_equal((scale * gu1[0]).astype(np.float32), gu[0])
+        assert np.array_equal((scale * gk1[0]).astype(np.float32), gk[0])
+
+
+def test_dirichlet_on_interior_and_top_rows_float32():
+    nx, ny = 70, 20
+    mesh = grid_mesh(nx, ny)
+    ids = np.arange((nx + 1) * (ny + 1))
+    mesh.node_sets["left"] = ids[(ids % (nx + 1) == 32) | (ids // (nx + 1) == ny) | (ids == 5)].astype(np.int32)
+    mesh.node_sets["right"] = ids[(ids % (nx + 1) == 64) & (ids // (nx + 1) < ny)].astype(np.int32)
+    loss = make(mesh, dtype="float32")
+    rng = np.random.default_rng(9)
+    K = rng.uniform(0.1, 1.0, (3, len(ids))).astype(np.float32)
+    u = rng.uniform(0.1, 1.0, (3, len(ids))).astype(np.float32)
+    mean, gu, gk = run(loss, K, u)
+    ref_mean, Eb, gU, gK = oracle(loss, mesh, K.astype(np.float64), u.astype(np.float64))
+    assert abs(mean - ref_mean) <= 1e-5 * np.abs(Eb).max()
+    assert np.abs(gu - gU).max() <= 1e-5 * np.abs(gU).max()
+    assert np.abs(gk - gK).max() <= 1e-5 * np.abs(gK).max()
+    assert not gu[:, loss.dirichlet_indices].any()
+
+
 def test_dirichlet_on_interior_and_top_rows():
     """Dirichlet nodes anywhere (not only on the left / right columns): overwrite while staging, cut at the store,
     also on the columns two warps share and on the top row."""
