@@ -24,6 +24,7 @@ namespace hexk { struct HaloFuse; }
 int assemble_hex_mech_f64(cudaStream_t, const AsmArgs<double>&, const hexk::HaloFuse* = nullptr);
 int assemble_hex_j2_f64(cudaStream_t, const AsmArgs<double>&, const hexk::HaloFuse* = nullptr);
 int assemble_hex_mech_f32(cudaStream_t, const AsmArgs<float>&);
+int assemble_hex_thermal_f64(cudaStream_t, const AsmArgs<double>&);
 template <class T>
 int assemble_ad(cudaStream_t, int, int, int, const AdAsmArgs<T>&);
 extern std::atomic<int> g_grid_margin;
@@ -81,8 +82,16 @@ static int assemble_typed(cudaStream_t s, int physics, int element, int num_gp, 
         return assemble_mech_f32(s, element, num_gp, a);
       }
     case FOL_THERMAL:
-      if constexpr (f64) return assemble_thermal_f64(s, element, num_gp, a);
-      else return assemble_thermal_f32(s, element, num_gp, a);
+      if constexpr (f64) {
+        // tuned Hex8 kernel (csrc/assemble_hex_thermal.cu); transpose and the matrix-free mode use the generic kernel
+        if (element == HEX && num_gp == 2 && !transpose && !v && g_tuned.load()) {
+          const int rc = assemble_hex_thermal_f64(s, a);  // 1 = not applicable (unaligned output): generic kernel
+          if (rc != 1) return rc;
+        }
+        return assemble_thermal_f64(s, element, num_gp, a);
+      } else {
+        return assemble_thermal_f32(s, element, num_gp, a);
+      }
     case FOL_NEOHOOKE:
       if constexpr (f64) return assemble_neohooke_f64(s, element, num_gp, a);
       else return assemble_neohooke_f32(s, element, num_gp, a);

@@ -28,7 +28,12 @@ def timeit(fn, steps=10):
     return e0.elapsed_time(e1) / steps
 
 
+ONLY = os.environ.get("ONLY", "")      # substring filter on the case names
+
+
 def case(name, cls, mesh, etype, settings, dtype, ufun, state=False):
+    if ONLY and ONLY not in name:
+        return
     loss = cls(name, {**settings, "dtype": dtype}, mesh)
     loss.Initialize()
     ne, nn, nd, d, a = loss._ne, loss._nn, loss._nd, loss.number_dofs_per_node, loss._nnode

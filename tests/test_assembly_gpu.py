@@ -173,6 +173,47 @@ def test_tuned_hex_kernel_matches_oracle_and_generic(shape, body):
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 1), (5, 3, 3), (7, 6, 5), (16, 9, 11)])
+@pytest.mark.parametrize("law", [{}, {"beta": 2.0, "c": 4}, {"beta": 0.7, "c": 2.5}])
+def test_tuned_hex_thermal_kernel_matches_oracle_and_generic(shape, law):
+    """The DMMA kernel for Hex8 heat conduction (assemble_hex_thermal.cu) against the oracle (thermal.py:28-49) and
+    against the generic kernel: ragged tiles, linear / integer-power / real-power conductivity laws, Dirichlet rows
+    (exact zeros off the diagonal, the diagonal kept), the transposed request (served by the generic kernel)."""
+    import folax_b200
+    from folax_b200 import _lib
+    from folax_b200.loss_functions import ThermalLoss3DHexa
+    mesh = folax_b200.create_3D_box_mesh(*shape, 1.0, 0.8, 1.1)
+    if min(shape) > 1:
+        folax_b200.perturb_interior_nodes(mesh, 0.25, seed=sum(shape))
+    loss = ThermalLoss3DHexa("tuned_t", {"dirichlet_bc_dict": {"T": {"left": 1.0, "right": 0.1}}, **law}, mesh)
+    loss.Initialize()
+    K, u = H.fields("thermal", mesh, loss, seed=12)
+    lib = _lib.load()
+    out = {}
+    for tuned in (1, 0):
+        prev = lib.fol_set_tuned_kernels(tuned)
+        try:
+            jac, R = loss.ComputeJacobianMatrixAndResidualVector(K, u)
+            jt, _ = loss.ComputeJacobianMatrixAndResidualVector(K, u, transpose_jacobian=True)
+            out[tuned] = (jac.data.cpu().numpy(), R.cpu().numpy(), jt.data.cpu().numpy())
+        finally:
+            lib.fol_set_tuned_kernels(prev)
+    args = ("thermal", "hexahedron", 2, np.asarray(mesh.GetNodesCoordinates()), mesh.GetElementsNodes("hexahedron"),
+            K, u, loss.dirichlet_indices, H.oracle_params(loss))
+    data, idx, Rref = assembly.assemble(*args)
+    dataT, _, _ = assembly.assemble(*args, transpose=True)
+    for tuned in (1, 0):
+        _close(out[tuned][0], data, 1e-12)
+        _close(out[tuned][1], Rref, 4e-12)
+        _close(out[tuned][2], dataT, 1e-12)
+    masked = np.isin(idx[:, 0], loss.dirichlet_indices) & (idx[:, 0] != idx[:, 1])
+    assert not out[1][0][masked].any()
+    assert not out[1][1][loss.dirichlet_indices].any()
+    # run-to-run bit-identity of the tuned kernel
+    jac2, R2 = loss.ComputeJacobianMatrixAndResidualVector(K, u)
+    assert np.array_equal(jac2.data.cpu().numpy(), out[1][0]) and np.array_equal(R2.cpu().numpy(), out[1][1])
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (5, 3, 3), (7, 6, 5), (16, 9, 11)])
 @pytest.mark.parametrize("body", [None, [0.3, -0.2, 0.1]])
 def test_tuned_hex_f32_kernel_matches_oracle_and_generic(shape, body):
     """The float32 tuned kernel (assemble_hex_f32.cu) against the float64 oracle at north_star's float32 tolerance
