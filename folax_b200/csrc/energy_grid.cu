@@ -55,6 +55,9 @@ namespace {
 #ifndef FOL_GRID_RING
 #define FOL_GRID_RING 8
 #endif
+#ifndef FOL_GRID_PREFETCH
+#define FOL_GRID_PREFETCH 0
+#endif
 #ifndef FOL_GRID_REGS64
 #define FOL_GRID_REGS64 96
 #endif
@@ -528,6 +531,29 @@ __global__ void __launch_bounds__(288) __maxnreg__(sizeof(S) == 8 ? FOL_GRID_REG
       EA = EB;
       ++e;
     }
+#if FOL_GRID_PREFETCH
+    // variant (measured SLOWER: 0.692 vs 0.660 ms float64, 0.365 vs 0.338 ms float32, profiles/r2/
+    // energy_grid_variants.txt): the next node row is taken between an element's arithmetic and its node sums, so that
+    // the barrier wait and the shared-memory loads of row e + 2 overlap the shuffles / stores that close row e
+    if (e < e_end) {
+      EB = take_edge();
+      for (;;) {
+        V re[4], dK[4], e_el;
+        element(EA, EB, re, dK, e_el);
+        const bool more = e + 1 < e_end;
+        Edge EN = EB;
+        if (more) EN = take_edge();
+        en = op_add(en, e_el);
+        finish_row(op_add(ocR, re[0]), op_add(ocK, dK[0]), op_add(rcR, re[1]), op_add(rcK, dK[1]), true);
+        node += (unsigned)NXn;
+        ocR = re[3]; ocK = dK[3]; rcR = re[2]; rcK = dK[2];
+        if (!more) break;
+        EA = EB;
+        EB = EN;
+        ++e;
+      }
+    }
+#else
     for (; e + 1 < e_end; e += 2) {
       EB = take_edge();
       step(EA, EB);
@@ -538,6 +564,7 @@ __global__ void __launch_bounds__(288) __maxnreg__(sizeof(S) == 8 ? FOL_GRID_REG
       EB = take_edge();
       step(EA, EB);
     }
+#endif
     if (r1 == ny + 1) finish_row(ocR, ocK, rcR, rcK, false);  // the top node row of the grid closes with the carries alone
 
     // energy shares of this warp

@@ -11,9 +11,5 @@ run() {
   done
 }
 run base
-run ring16 -DFOL_GRID_RING=16
-run ring4 -DFOL_GRID_RING=4
-run regs64_80 -DFOL_GRID_REGS64=80
-run regs64_72 -DFOL_GRID_REGS64=72
-run regs32p_72 -DFOL_GRID_REGS32P=72
-run regs64_112 -DFOL_GRID_REGS64=112
+run prefetch -DFOL_GRID_PREFETCH=1
+run prefetch_r80 -DFOL_GRID_PREFETCH=1 -DFOL_GRID_REGS64=80
