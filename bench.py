@@ -463,19 +463,23 @@ def fol_loss_grad_bench(torch, dist, rank, world, steps, warmup):
 
 def j2_bench(torch, dist, rank, world, n, steps, ke):
     """configs[4]: J2 elastoplasticity with per-Gauss-point history on a hex box, element-partitioned into z-slabs with
-    the halo-DOF exchange (n^3 elements and their (ne, 8, 7) history per GPU: 256^3 over 8 GPUs at n = 128).  Two load
+    the halo-DOF exchange (n^3 elements and their (ne, 8, 7) history per GPU as slabs of a (2n)^2 cross-section: the
+    256^3 mesh over 8 GPUs at n = 128).  Two load
     steps: the timed one starts from the non-zero history the first one returned."""
     from folax_b200 import _lib
     from folax_b200.distributed import SlabPartition, assemble_overlapped
     from folax_b200.loss_functions import ElastoplasticityLoss3DHexa
     lib = _lib.load()
-    part = SlabPartition(n, n, n * world, 1.0, 1.0, float(world), rank, world)
+    # configs[4]'s own geometry: a (2n) x (2n) cross-section cut into slabs of n/4 element layers -- n^3 elements per GPU
+    # as in the headline case, and at 8 GPUs exactly the 256^3 mesh with its 257^2-node interface planes
+    nx, nzl = (2 * n, n // 4) if n % 4 == 0 else (n, n)
+    part = SlabPartition(nx, nx, nzl * world, 1.0, 1.0, float(nzl * world) / nx, rank, world)
     loss = ElastoplasticityLoss3DHexa("j2", {"dirichlet_bc_dict": BC, "num_gp": 2, "material_dict": dict(J2_MATERIAL)},
                                       part.mesh)
     loss.Initialize()
     ne = loss._ne
     _, u1 = global_fields(part.global_node_ids())
-    h = 1.0 / n
+    h = 1.0 / nx
     u1 = torch.tensor(u1 * (2.0 * h), device="cuda")       # 0.02 h N(0,1) (SURVEY.md 8d): elastic and plastic points mixed
     K = torch.ones(loss._nn, dtype=torch.float64, device="cuda")
     st0 = torch.zeros(loss.GetStateShape(), dtype=torch.float64, device="cuda")
@@ -527,7 +531,8 @@ def j2_bench(torch, dist, rank, world, n, steps, ke):
     return {"metric": "assembled_elements_per_s", "value": ne * world / (ms * 1e-3), "unit": "elements/s",
             "ms_per_step": ms, "scaling": "weak", "dtype": "f64",
             "config": {"workload": f"hex{n}_j2_elastoplastic_residual_jacobian_state_f64", "elements_per_gpu": ne,
-                       "global_mesh": f"{n}x{n}x{n * world} hex elements", "state": "(ne, 8, 7) f64 in and out",
+                       "global_mesh": f"{nx}x{nx}x{nzl * world} hex elements",
+                       "interface_plane_nodes": (nx + 1) * (nx + 1), "state": "(ne, 8, 7) f64 in and out",
                        "plastic_points_in_timed_step": plastic, "plastic_points_in_history": plastic_before,
                        "parallelism": f"element slabs x{world} + halo-DOF sum ({halo})" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
@@ -764,21 +769,27 @@ def run_ours(args):
     # timed region sits in the same power / clock state at N = 1 and N > 1
     for _ in range(args.warmup + 5):
         step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     launches0 = lib.fol_launch_count()
     clocks = ClockSampler(local_rank)
     clocks.__enter__()
-    torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # barrier + synchronize right before the timed region (nothing host-side between them and the first step: the
+    # ranks of a slab-partitioned step wait for each other's planes, so a late rank's delay lands in its neighbours'
+    # times), then a device-side barrier on the stream itself so that all GPUs start the K steps together
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        dist.all_reduce(torch.zeros(1, device="cuda"))
     e0.record()
     for i in range(args.steps):
         step(ev[i])
     e1.record()
     e1.synchronize()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     ms = e0.elapsed_time(e1) / args.steps
     launches = lib.fol_launch_count() - launches0
     have_kernel_events = world == 1 or part._halo is not None
