@@ -140,7 +140,16 @@ def dtype_code(dt):
     raise FolaxError(f"unsupported dtype {dt}")
 
 
+try:                                   # the raw handle without building a torch.cuda.Stream object: current_stream()
+    _raw_stream, _cur_device = torch._C._cuda_getCurrentRawStream, torch._C._cuda_getDevice   # costs ~20 us per call
+except AttributeError:                 # (a torch without these private entry points: the public, slower route)
+    _raw_stream = _cur_device = None
+
+
 def stream_ptr():
+    """cudaStream_t of torch's current stream on the current device (what every C-ABI call launches on)."""
+    if _raw_stream is not None:
+        return _raw_stream(_cur_device())
     return torch.cuda.current_stream().cuda_stream
 
 
