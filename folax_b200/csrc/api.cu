@@ -25,6 +25,7 @@ int assemble_hex_mech_f64(cudaStream_t, const AsmArgs<double>&, const hexk::Halo
 int assemble_hex_j2_f64(cudaStream_t, const AsmArgs<double>&, const hexk::HaloFuse* = nullptr);
 int assemble_hex_mech_f32(cudaStream_t, const AsmArgs<float>&);
 int assemble_hex_thermal_f64(cudaStream_t, const AsmArgs<double>&);
+int assemble_quad_mech_f64(cudaStream_t, const AsmArgs<double>&);
 template <class T>
 int assemble_ad(cudaStream_t, int, int, int, const AdAsmArgs<T>&);
 extern std::atomic<int> g_grid_margin;
@@ -73,6 +74,10 @@ static int assemble_typed(cudaStream_t s, int physics, int element, int num_gp, 
       if constexpr (f64) {
         // (the tuned kernel writes Ke itself; the transpose switch of fe_loss.py:216-230 uses the generic kernel)
         if (element == HEX && num_gp == 2 && !transpose && !v && g_tuned.load()) return assemble_hex_mech_f64(s, a);
+        if (element == QUAD && num_gp == 2 && !transpose && !v && g_tuned.load()) {
+          const int rc = assemble_quad_mech_f64(s, a);    // 1 = not applicable (unaligned output): generic kernel
+          if (rc != 1) return rc;
+        }
         return assemble_mech_f64(s, element, num_gp, a);
       } else {
         if (element == HEX && num_gp == 2 && !transpose && !v && g_tuned.load()) {

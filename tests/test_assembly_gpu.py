@@ -172,6 +172,50 @@ def test_tuned_hex_kernel_matches_oracle_and_generic(shape, body):
     assert not out[1][0][masked].any()
 
 
+@pytest.mark.parametrize("n", [1, 2, 7, 9, 33])
+@pytest.mark.parametrize("body", [None, [0.3, -0.2]])
+def test_tuned_quad_mech_kernel_matches_oracle_and_generic(n, body):
+    """The one-DMMA-per-element kernel for Quad4 plane-stress elasticity (assemble_quad_mech.cu) against the oracle
+    (mechanical.py:98-117) and against the generic kernel: element counts that are not a multiple of its 8-element
+    tile, perturbed geometry, body force, Dirichlet rows, the transposed request (served by the generic kernel)."""
+    import folax_b200
+    from folax_b200 import _lib
+    from folax_b200.loss_functions import MechanicalLoss2DQuad
+    mesh = folax_b200.create_2D_square_mesh(1.3, n + 1)
+    if n > 1:
+        folax_b200.perturb_interior_nodes(mesh, 0.25, seed=n)
+    settings = {"dirichlet_bc_dict": {d: {"left": 0.0, "right": 0.1} for d in ("Ux", "Uy")},
+                "material_dict": dict(H.MATERIAL)}
+    if body:
+        settings["body_foce"] = body
+    loss = MechanicalLoss2DQuad("tuned_q", settings, mesh)
+    loss.Initialize()
+    K, u = H.fields("mechanical", mesh, loss, seed=13)
+    lib = _lib.load()
+    out = {}
+    for tuned in (1, 0):
+        prev = lib.fol_set_tuned_kernels(tuned)
+        try:
+            jac, R = loss.ComputeJacobianMatrixAndResidualVector(K, u)
+            jt, _ = loss.ComputeJacobianMatrixAndResidualVector(K, u, transpose_jacobian=True)
+            out[tuned] = (jac.data.cpu().numpy(), R.cpu().numpy(), jt.data.cpu().numpy())
+        finally:
+            lib.fol_set_tuned_kernels(prev)
+    args = ("mechanical", "quad", 2, np.asarray(mesh.GetNodesCoordinates()), mesh.GetElementsNodes("quad"), K, u,
+            loss.dirichlet_indices, H.oracle_params(loss))
+    data, idx, Rref = assembly.assemble(*args)
+    dataT, _, _ = assembly.assemble(*args, transpose=True)
+    for tuned in (1, 0):
+        _close(out[tuned][0], data, 1e-12)
+        _close(out[tuned][1], Rref, 4e-12)
+        _close(out[tuned][2], dataT, 1e-12)
+    masked = np.isin(idx[:, 0], loss.dirichlet_indices) & (idx[:, 0] != idx[:, 1])
+    assert not out[1][0][masked].any()
+    assert not out[1][1][loss.dirichlet_indices].any()
+    jac2, R2 = loss.ComputeJacobianMatrixAndResidualVector(K, u)
+    assert np.array_equal(jac2.data.cpu().numpy(), out[1][0]) and np.array_equal(R2.cpu().numpy(), out[1][1])
+
+
 @pytest.mark.parametrize("shape", [(1, 1, 1), (5, 3, 3), (7, 6, 5), (16, 9, 11)])
 @pytest.mark.parametrize("law", [{}, {"beta": 2.0, "c": 4}, {"beta": 0.7, "c": 2.5}])
 def test_tuned_hex_thermal_kernel_matches_oracle_and_generic(shape, law):
