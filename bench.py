@@ -658,7 +658,19 @@ def newton_bench(torch):
     finally:
         linalg.SellOperator, linalg.bicgstab, linalg.bicgstab_fused = sell, bicg, fused
     it = max(split["newton_iterations"], 1)
+    # HBM view of one BiCGSTAB iteration: two SELL products (9.33 B per stored entry: value + one node column per run of
+    # 3, + x / y) and the fused vector passes (23 vector reads / writes of n doubles: the 12 vectors of the solve do not
+    # stay in L2 next to a 450 MB matrix stream)
+    sp = loss._sell_plan()
+    n_dof = loss.total_number_of_dofs
+    iter_bytes = 2.0 * ((8.0 + 4.0 / 3.0) * sp["total"] + 16.0 * n_dof) + 23.0 * 8.0 * n_dof
+    ms_iter = 1e3 * split["krylov_s"] / max(split["krylov_iterations"], 1)
+    hbm, _ = measured_peaks()
     return {"workload": "tet_neo_hooke_newton_f64 (70^3 Kuhn cells)", "elements": loss._ne,
+            "krylov_roofline": {"bound": "hbm", "algorithmic_bytes_per_iteration": iter_bytes,
+                                "achieved": iter_bytes / (ms_iter * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                "frac": iter_bytes / (ms_iter * 1e-3) / 1e9 / hbm,
+                                "stored_entries": int(sp["total"])},
             "dofs": loss.total_number_of_dofs, **split, "host_plans_s": plans,
             "final_residual_norm": solver.convergence_history[1]["res_norm"][-1],
             "per_newton_iteration_ms": {k[:-2]: 1e3 * split[k] / it for k in ("assembly_s", "operator_s", "krylov_s")},

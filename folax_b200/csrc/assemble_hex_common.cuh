@@ -30,6 +30,10 @@ __device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
   const unsigned saddr = (unsigned)__cvta_generic_to_shared(sdst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+  const unsigned saddr = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 

@@ -38,7 +38,7 @@ struct __align__(128) QuadWarpSmem {
   double wd[kTileQ][4];              // w detJ per Gauss point (body force)
   // nodal data of the tile, SoA over (element, node) = 32 lanes, double-buffered
   double X[2][2][32];
-  double u[2][2][32];
+  double2 u[2][32];                  // (ux, uy) of a node: one 16-byte cp.async, one 16-byte load in phase 2
   double de[2][32];
   float bc[kTileQ][8];               // 1 = free dof, 0 = Dirichlet dof
 };
@@ -92,8 +92,7 @@ assemble_quad_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles
     const double* pu = args.u + n * 2;
     cp_async8(&sm.X[buf][0][lane], pxy);
     cp_async8(&sm.X[buf][1][lane], pxy + 1);
-    cp_async8(&sm.u[buf][0][lane], pu);
-    cp_async8(&sm.u[buf][1][lane], pu + 1);
+    cp_async16(&sm.u[buf][lane], pu);            // 16-byte aligned: two dofs per node
     cp_async8(&sm.de[buf][lane], args.ctrl + n);
     cp_async_commit();
   };
@@ -161,7 +160,8 @@ assemble_quad_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles
       double k0 = lam * c0 + mu * pt0, k1 = lam * c1 + mu * pt1;
       if (ia) k1 += mu * tr; else k0 += mu * tr;
       // re = Ke u - Fe: partial over this lane's two columns (node b = kq), then butterfly over the 4 k-lanes
-      double r = k0 * sm.u[buf][0][el * 4 + kq] + k1 * sm.u[buf][1][el * 4 + kq];
+      const double2 ub = sm.u[buf][el * 4 + kq];
+      double r = k0 * ub.x + k1 * ub.y;
       r += __shfl_xor_sync(0xffffffffu, r, 1);
       r += __shfl_xor_sync(0xffffffffu, r, 2);
       if (has_body) {                                    // Fe_(a,i) = b_i sum_g w detJ N_a(g)   (mechanical.py:110)
@@ -193,7 +193,8 @@ int assemble_quad_mech_f64(cudaStream_t s, const AsmArgs<double>& args) {
   int grid = 0;
   FOL_CUDA(per_device.get(assemble_quad_mech_f64_kernel, kWarpsQ * 32, smem, &grid));
   if (args.ne == 0) return FOL_OK;
-  if ((reinterpret_cast<uintptr_t>(args.ke) & 15) != 0) return 1;   // 16-byte stores: the generic kernel takes it
+  if (((reinterpret_cast<uintptr_t>(args.ke) | reinterpret_cast<uintptr_t>(args.u)) & 15) != 0)
+    return 1;                        // 16-byte stores / dof gathers: the generic kernel takes unaligned buffers
   const long long ntiles = cdiv(args.ne, kTileQ);
   const long long want = cdiv(ntiles, kWarpsQ);
   const unsigned blocks = (unsigned)(want < grid ? want : grid);
