@@ -7,9 +7,9 @@
 //
 // What the structure buys: no connectivity, no geometry cache, no adjacency lists, no CTA barrier per pass and almost
 // no address arithmetic -- the float64 kernel is left with the FP64 pipe as its bound.
-//   * A CTA owns `rows` node rows of ONE sample over a panel of 32 W element columns (W <= 8 consumer warps) and
-//     marches UP the grid: lane l of warp w owns node column c0 + 32 w + l and, per step, the element between rows
-//     e, e + 1 and columns c, c + 1.
+//   * A CTA owns `rows` node rows of ONE sample (float32: of TWO samples, packed per lane -- FMUL2 / FADD2 / FFMA2)
+//     over a panel of 32 W element columns (W <= 8 consumer warps) and marches UP the grid: lane l of warp w owns node
+//     column c0 + 32 w + l and, per step, the element between rows e, e + 1 and columns c, c + 1.
 //   * One PRODUCER warp streams the node rows of T, K (and the Dirichlet values) into a shared-memory ring with 1-D bulk
 //     copies (cp.async.bulk + mbarrier complete_tx: one instruction per array and row for the whole CTA; sources
 //     aligned down to 16 bytes, the lanes read at the row's shift); the consumer warps wait on the row's `full`
@@ -18,8 +18,10 @@
 //   * The element-vector entries leave through registers: the two left corners accumulate in the lane, the two right
 //     corners are summed per lane over consecutive rows and handed to lane l + 1 by one shuffle: every node sum has a
 //     fixed order, no atomics, deterministic.
-//   * The element arithmetic is sum-factorised for the bilinear element with the 2 x 2 rule (131 FP instructions per
-//     element on axis-aligned grids; `grid_element`).
+//   * The element arithmetic is sum-factorised for the bilinear element with the 2 x 2 rule and the edge values of a
+//     node row are computed once for the element rows below and above it (115 FP instructions per element on
+//     axis-aligned grids, 123 with the node sums; `grid_edge`, `grid_element`), every operation with its rounding
+//     written out, so the results do not depend on chunk height, batch size or code path.
 //   * The node column shared by two warps gets its two halves through shared memory once per chunk (`combine`), the
 //     only CTA barrier of the kernel.  The chunk recomputes the element row below it (1 / rows extra work) instead of
 //     exchanging partial sums with the chunk below; panels overlap by one element column in the same way (nx > 256).
