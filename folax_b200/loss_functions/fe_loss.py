@@ -56,6 +56,7 @@ class _BatchLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, loss, batch_params, batch_dofs, mask_dirichlet=True, fuse_dirichlet=False):
         ctx.mask_dirichlet = mask_dirichlet
+        ctx.set_materialize_grads(False)      # cotangents of unused outputs stay None: no zero-fill / add kernels per step
         nb = batch_dofs.shape[0]
         ctx.prescaled = float(loss.loss_function_exponent) == 1.0
         energy, grad_u, grad_k = loss._energy_and_grads(
