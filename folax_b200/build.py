@@ -38,7 +38,8 @@ def _stamp():
 
 # per-file extras (register caps of the tuned kernels)
 EXTRA = {"assemble_hex.cu": ["-maxrregcount=144"] + os.environ.get("FOL_HEX_DEFS", "").split(),
-         "energy_grid.cu": os.environ.get("FOL_GRID_DEFS", "").split()}
+         "energy_grid.cu": os.environ.get("FOL_GRID_DEFS", "").split(),
+         "krylov_fused.cu": os.environ.get("FOL_FUSED_DEFS", "").split()}
 
 
 def _headers_hash():

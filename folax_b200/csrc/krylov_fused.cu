@@ -35,7 +35,13 @@ struct FusedBicgArgs {
 namespace {
 
 constexpr int kFusedThreads = 256;
-constexpr int kFusedCtasPerSm = 4;   // 64 registers: 32 warps per SM to hide the gather latency of the products
+#ifndef FOL_FUSED_CTAS
+#define FOL_FUSED_CTAS 5
+#endif
+// CTAs of 256 threads per SM.  Measured at 1.07 M dofs (ms per iteration): 3 CTAs / 80 registers 0.255, 4 / 64 0.258,
+// 5 / 48 0.235, 6 / 40 0.248 -- the products want warps in flight to hide their gather latency, up to the point where
+// the register cap spills the row loop
+constexpr int kFusedCtasPerSm = FOL_FUSED_CTAS;
 
 __device__ __forceinline__ void grid_sync(unsigned long long* sync, unsigned long long& epoch) {
   __syncthreads();
