@@ -35,6 +35,9 @@ struct FusedBicgArgs {
 namespace {
 
 constexpr int kFusedThreads = 256;
+#ifndef FOL_FUSED_UNROLL
+#define FOL_FUSED_UNROLL 4
+#endif
 #ifndef FOL_FUSED_CTAS
 #define FOL_FUSED_CTAS 5
 #endif
@@ -42,6 +45,7 @@ constexpr int kFusedThreads = 256;
 // 5 / 48 0.235, 6 / 40 0.248 -- the products want warps in flight to hide their gather latency, up to the point where
 // the register cap spills the row loop
 constexpr int kFusedCtasPerSm = FOL_FUSED_CTAS;
+constexpr int kFusedUnroll = FOL_FUSED_UNROLL;   // runs of a SELL row in flight per thread
 
 __device__ __forceinline__ void grid_sync(unsigned long long* sync, unsigned long long& epoch) {
   __syncthreads();
@@ -129,7 +133,7 @@ __device__ __forceinline__ T sell_row(const FusedBicgArgs<T>& a, long long row, 
     const int runs = width / D;
     const int32_t* c = a.cols + base / D + lane;
     const T* v = a.vals + base + lane;
-#pragma unroll 4
+#pragma unroll(kFusedUnroll)
     for (int q = 0; q < runs; ++q) {
       const T* xm = x + (long long)c[(long long)q * 32] * D;
 #pragma unroll
