@@ -283,36 +283,94 @@ def allreduce_gradients(parameters, group=None, bucket_bytes=64 << 20):
 
 class GradientReducer:
     """All-reduce of the network gradients OVERLAPPED with the backward pass: a post-accumulate hook on every
-    parameter starts the NCCL all-reduce of its gradient on a side stream the moment autograd has produced it, so
-    the reduction of the (large) output-layer gradient of a FOL network runs behind the rest of the backward pass
-    instead of after it.  `wait()` joins the side stream before the optimizer step.  Same sums as
-    `allreduce_gradients` (one all-reduce per parameter, NCCL's fixed ring / tree order)."""
+    parameter starts the NCCL all-reduce of its gradient on a side stream the moment autograd has produced it;
+    `wait()` joins the side stream before the optimizer step.  Same sums as `allreduce_gradients` (one all-reduce per
+    parameter, NCCL's fixed ring / tree order).
 
-    def __init__(self, parameters, group=None):
+    A hook fires when autograd ACCUMULATES a gradient, i.e. after the whole backward node that produced it -- for a
+    Linear layer after both its weight-gradient and its input-gradient GEMMs are enqueued.  For the (large) output
+    layer of a FOL network that is too late: nothing sizeable is left of the backward pass to hide its 135 MB
+    all-reduce behind.  `EarlyReduceLinear` is a Linear layer whose backward computes the weight / bias gradients
+    FIRST, starts their all-reduce here (`reduce_now`) and only then computes the input gradient, which overlaps it;
+    its parameters are passed in `exclude` so that no hook reduces them a second time.  On CPU tensors (gloo tests)
+    everything runs synchronously."""
+
+    def __init__(self, parameters, group=None, exclude=()):
         self.group = group
         self.active = dist.is_initialized() and dist.get_world_size(group) > 1
-        self.stream = torch.cuda.Stream() if self.active else None
+        self.stream = torch.cuda.Stream() if (self.active and torch.cuda.is_available()) else None
         self.handles = []
+        skip = {id(p) for p in exclude}
         if self.active:
             for p in parameters:
-                if p.requires_grad:
+                if p.requires_grad and id(p) not in skip:
                     self.handles.append(p.register_post_accumulate_grad_hook(self._hook))
 
-    def _hook(self, p):
+    def _start(self, tensors):
+        if self.stream is None or not tensors[0].is_cuda:
+            for t in tensors:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            return
         ready = torch.cuda.Event()
         ready.record()
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ready)
-            dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group)
+            for t in tensors:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _hook(self, p):
+        self._start([p.grad])
+
+    def reduce_now(self, *tensors):
+        """Start the in-place all-reduce of tensors that were just produced on the current stream (no-op when single
+        rank); `wait()` must follow before they are read."""
+        tensors = [t for t in tensors if t is not None]
+        if self.active and tensors:
+            self._start(tensors)
 
     def wait(self):
-        if self.active:
+        if self.active and self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
 
     def close(self):
         for h in self.handles:
             h.remove()
         self.handles = []
+
+
+class _EarlyReduceLinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, reducer):
+        ctx.save_for_backward(x, weight)
+        ctx.reducer, ctx.has_bias = reducer, bias is not None
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g2, x2 = g.reshape(-1, g.shape[-1]), x.reshape(-1, x.shape[-1])
+        gw = g2.t().mm(x2) if ctx.needs_input_grad[1] else None          # (out, in): first, so that its all-reduce ...
+        gb = g2.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        ctx.reducer.reduce_now(gw, gb)
+        gx = g.matmul(w) if ctx.needs_input_grad[0] else None            # ... runs behind this GEMM
+        ctx.reducer.wait()       # enqueued after the GEMM: gw / gb are complete before autograd accumulates them
+        return gx, gw, gb, None
+
+
+class EarlyReduceLinear(torch.nn.Linear):
+    """torch.nn.Linear for the data-parallel FOL step: identical forward and gradients; in backward the weight / bias
+    gradients are produced first and their all-reduce (through `reducer`, a GradientReducer that EXCLUDES this
+    layer's parameters from its hooks) overlaps the input-gradient GEMM.  Without a reducer, or on one rank, it is a
+    plain Linear."""
+
+    def __init__(self, in_features, out_features, bias=True, reducer=None, **kw):
+        super().__init__(in_features, out_features, bias=bias, **kw)
+        self.reducer = reducer
+
+    def forward(self, x):
+        if self.reducer is None or not self.reducer.active:
+            return super().forward(x)
+        return _EarlyReduceLinearFn.apply(x, self.weight, self.bias, self.reducer)
 
 
 def allreduce_loss_statistics(mean, stats, group=None):

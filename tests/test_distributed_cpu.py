@@ -9,7 +9,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from folax_b200.distributed import SlabPartition, allreduce_gradients, allreduce_loss_statistics, shard_batch
+from folax_b200.distributed import (EarlyReduceLinear, GradientReducer, SlabPartition, allreduce_gradients,
+                                    allreduce_loss_statistics, shard_batch)
 
 
 def _free_port():
@@ -87,6 +88,45 @@ def _grad_worker(rank, world, port, out):
             np.testing.assert_allclose(p.grad.numpy(), g, atol=1e-15)
     finally:
         dist.destroy_process_group()
+
+
+def _early_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        first = torch.nn.Linear(4, 8)                   # same construction order (= same initial weights) as the check
+        last = EarlyReduceLinear(8, 3)
+        net = torch.nn.Sequential(first, torch.nn.Tanh(), last).double()
+        reducer = GradientReducer(list(net.parameters()), exclude=list(last.parameters()))
+        last.reducer = reducer
+        x = torch.arange(24, dtype=torch.float64).reshape(6, 4) / 10
+        sl = shard_batch(6, rank, world)
+        (net(x[sl]).pow(2).sum() / 6).backward()       # hooks + the early reduce of the last layer: all grads summed
+        reducer.wait()
+        out[rank] = [p.grad.numpy().copy() for p in net.parameters()]
+        reducer.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_early_reduce_linear_sums_like_the_plain_all_reduce():
+    """GradientReducer (hooks) + EarlyReduceLinear (weight / bias gradients reduced from inside backward, before the
+    input gradient): every rank ends with the gradient of the undivided batch, the excluded layer reduced exactly once."""
+    world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_early_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.Tanh(), torch.nn.Linear(8, 3)).double()
+    x = torch.arange(24, dtype=torch.float64).reshape(6, 4) / 10
+    (net(x).pow(2).sum() / 6).backward()
+    for rank in range(world):
+        for g, p in zip(out[rank], net.parameters()):
+            np.testing.assert_allclose(g, p.grad.numpy(), rtol=1e-13, atol=1e-15)
+    # single process: a plain Linear
+    lone = EarlyReduceLinear(8, 3).double()
+    y = lone(torch.ones(2, 8, dtype=torch.float64))
+    assert y.shape == (2, 3)
 
 
 def test_data_parallel_gradient_allreduce():
