@@ -57,6 +57,9 @@ SIGNATURES = {
     "fol_energy_grid_work_size": (_i64, [_i64, _i64, _i64]),
     "fol_energy_and_grads_grid": (_int, [_vp, _int, _i64, _i64, _i64, C.POINTER(_dbl), _dbl, _vp, _vp, _vp, _u8p, _u8p,
                                          _dbl, C.POINTER(_dbl), _vp, _vp, _vp, _vp]),
+    "fol_energy_grid_mech_work_size": (_i64, [_i64, _i64, _i64]),
+    "fol_energy_and_grads_grid_mech": (_int, [_vp, _int, _i64, _i64, _i64, C.POINTER(_dbl), _dbl, _vp, _vp, _vp, _u8p,
+                                              _u8p, _dbl, C.POINTER(_dbl), _vp, _vp, _vp]),
     "fol_loss_reduce": (_int, [_vp, _int, _i64, _dbl, _vp, _vp, _vp]),
     "fol_scale_grads": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _dbl, _vp, _int, _u8p, _vp, _vp]),
     "fol_apply_dirichlet": (_int, [_vp, _int, _i64, _i64, _i32p, _i64, _vp, _int, _dbl, _vp]),

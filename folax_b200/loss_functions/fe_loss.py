@@ -581,14 +581,15 @@ class FiniteElementLoss(Loss):
             import os
             from .. import energy_plan
             g = None
-            if (self._batch_physics() == "thermal" and self.element_type == "quad" and self.num_gp == 2
+            if (self._batch_physics() in ("thermal", "mechanical") and self.element_type == "quad" and self.num_gp == 2
                     and os.environ.get("FOL_ENERGY_GRID", "1") != "0"):
                 g = energy_plan.grid_structure(np.asarray(self.fe_mesh.GetNodesCoordinates()),
                                                self.fe_mesh.GetElementsNodes(self.element_type))
                 if g is not None:
                     g["jinv_c"] = (C.c_double * 4)(*[float(v) for v in g["jinv"]])
                     col = np.zeros(g["nx"] + 1, dtype=np.uint8)      # node columns that hold a Dirichlet node
-                    col[np.asarray(self.dirichlet_indices, dtype=np.int64) % (g["nx"] + 1)] = 1
+                    nodes = np.asarray(self.dirichlet_indices, dtype=np.int64) // self.number_dofs_per_node
+                    col[nodes % (g["nx"] + 1)] = 1
                     g["col_dir"] = torch.as_tensor(col, device=self.device)
             self._grid = g
         return self._grid
@@ -615,8 +616,17 @@ class FiniteElementLoss(Loss):
             cache = self.__dict__.setdefault("_grid_work_cache", {})
             if nb not in cache:
                 cache.clear()
-                cache[nb] = torch.empty(int(lib.fol_energy_grid_work_size(grid["nx"], grid["ny"], nb)),
-                                        dtype=self.dtype, device=self.device)
+                size = max(int(lib.fol_energy_grid_work_size(grid["nx"], grid["ny"], nb)),
+                           int(lib.fol_energy_grid_mech_work_size(grid["nx"], grid["ny"], nb)))
+                cache[nb] = torch.empty(size, dtype=self.dtype, device=self.device)
+            if self._batch_physics() == "mechanical":          # csrc/energy_grid_mech.cu: two dofs per node, dE/dK = 0
+                _lib.check(lib.fol_energy_and_grads_grid_mech(
+                    _lib.stream_ptr(), self._dt, grid["nx"], grid["ny"], nb, grid["jinv_c"], grid["wdetj"],
+                    _lib.ptr(_aligned16(batch_params)), _lib.ptr(_aligned16(batch_dofs)),
+                    _lib.ptr(dir_values) if dir_values is not None else None,
+                    _lib.ptr(dir_flag) if dir_flag is not None else None, _lib.ptr(grid["col_dir"]), float(out_scale),
+                    self._params, _lib.ptr(grad_u), _lib.ptr(energy), _lib.ptr(cache[nb])))
+                return energy, grad_u, grad_k
             _lib.check(lib.fol_energy_and_grads_grid(
                 _lib.stream_ptr(), self._dt, grid["nx"], grid["ny"], nb, grid["jinv_c"], grid["wdetj"],
                 _lib.ptr(_aligned16(batch_params)), _lib.ptr(_aligned16(batch_dofs)),

@@ -338,6 +338,17 @@ int fol_energy_and_grads_grid(fol_stream_t s, int dtype, int64_t nx, int64_t ny,
                               const uint8_t* dir_flag, const uint8_t* col_dir, double out_scale,
                               const double* params_host, void* grad_u, void* grad_k, void* energy, void* work);
 
+/* The same for the elasticity loss: MechanicalLoss2DQuad.ComputeBatchLoss and its gradient (mechanical.py:98-117,
+ * fe_loss.py:250-262; plane stress, 2 x 2 rule) on the structured Quad4 grids of fol_energy_and_grads_grid.  u, grad_u,
+ * dir_values, dir_flag: two dofs per node, interleaved ((nb,) 2 (nx+1)(ny+1)); ctrl: (nb, (nx+1)(ny+1)); the control
+ * gradient of this loss is zero (its element matrix sits under stop_gradient) and is not written.  params_host[0..3]:
+ * E, nu, body force x, y.  ctrl, u, dir_values and grad_u must be 16-byte aligned. */
+int64_t fol_energy_grid_mech_work_size(int64_t nx, int64_t ny, int64_t nb);
+int fol_energy_and_grads_grid_mech(fol_stream_t s, int dtype, int64_t nx, int64_t ny, int64_t nb, const double* jinv_host,
+                                   double w_detj, const void* ctrl, const void* u, const void* dir_values,
+                                   const uint8_t* dir_flag, const uint8_t* col_dir, double out_scale,
+                                   const double* params_host, void* grad_u, void* energy, void* work);
+
 /* ---- host-buffer entry point (what a non-GPU caller binds; used for the e2e measurement) -- */
 
 typedef struct fol_plan fol_plan;

@@ -12,7 +12,7 @@ import torch
 
 import folax_b200
 from folax_b200 import energy_plan
-from folax_b200.loss_functions import ThermalLoss2DQuad
+from folax_b200.loss_functions import MechanicalLoss2DQuad, ThermalLoss2DQuad
 from folax_b200.mesh import Mesh, _finish
 from oracle import assembly
 
@@ -206,4 +206,103 @@ def test_dirichlet_on_interior_and_top_rows():
     assert abs(mean - ref_mean) <= 1e-12 * np.abs(Eb).max()
     assert np.abs(gu - gU).max() <= 1e-12 * np.abs(gU).max()
     assert np.abs(gk - gK).max() <= 1e-12 * np.abs(gK).max()
+    assert not gu[:, loss.dirichlet_indices].any()
+
+
+# ---------------------------------------------------------------------------------------------- elasticity (two dofs / node)
+MAT = {"young_modulus": 1.3, "poisson_ratio": 0.3}
+
+
+def make_mech(mesh, dtype="float64", exponent=1.0, body=None):
+    settings = {"dirichlet_bc_dict": {"Ux": {"left": 0.0, "right": 0.05}, "Uy": {"left": 0.0, "right": -0.02}},
+                "material_dict": dict(MAT), "dtype": dtype, "loss_function_exponent": exponent}
+    if body is not None:
+        settings["body_foce"] = body
+    loss = MechanicalLoss2DQuad("m", settings, mesh)
+    loss.Initialize()
+    return loss
+
+
+def oracle_mech(loss, mesh, K, u, exponent=1.0):
+    coords, conn = np.asarray(mesh.GetNodesCoordinates()), mesh.GetElementsNodes("quad")
+    params = {"young_modulus": MAT["young_modulus"], "poisson_ratio": MAT["poisson_ratio"]}
+    if "body_foce" in loss.loss_settings:
+        params["body_force"] = np.asarray(loss.loss_settings["body_foce"], float).reshape(-1)
+    args = ("mechanical", "quad", 2, coords, conn, K, u, loss.dirichlet_indices, loss.dirichlet_values, params)
+    mean, _, Eb = assembly.batch_loss(*args, exponent=exponent)
+    gU, _ = assembly.batch_loss_grads(*args, exponent=exponent)
+    return mean, Eb, gU
+
+
+def run_mech(loss, K, u):
+    Kt = torch.tensor(K, device="cuda", dtype=loss.dtype, requires_grad=True)
+    ut = torch.tensor(u, device="cuda", dtype=loss.dtype, requires_grad=True)
+    mean, _ = loss.ComputeBatchLoss(Kt, ut)
+    mean.backward()
+    assert Kt.grad is None or not Kt.grad.any()            # dE/dK = 0: Se sits under stop_gradient (mechanical.py:116)
+    return mean.item(), ut.grad.cpu().numpy()
+
+
+@pytest.mark.parametrize("nx,ny", SHAPES)
+@pytest.mark.parametrize("shear,body", [(0.0, None), (0.3, [0.3, -0.2])])
+def test_mech_grid_kernel_matches_the_oracle(nx, ny, shear, body):
+    mesh = grid_mesh(nx, ny, shear=shear)
+    loss = make_mech(mesh, body=body)
+    assert loss._grid_plan() is not None
+    rng = np.random.default_rng(nx * 1000 + ny + 7)
+    B, nn = 3, mesh.GetNumberOfNodes()
+    K, u = rng.uniform(0.1, 1.0, (B, nn)), 0.01 * rng.standard_normal((B, 2 * nn))
+    mean, gu = run_mech(loss, K, u)
+    ref_mean, Eb, gU = oracle_mech(loss, mesh, K, u)
+    assert abs(mean - ref_mean) <= 1e-12 * np.abs(Eb).max()
+    assert np.abs(gu - gU).max() <= 1e-12 * np.abs(gU).max()
+    assert not gu[:, loss.dirichlet_indices].any()
+    mean2, gu2 = run_mech(loss, K, u)
+    assert mean2 == mean and np.array_equal(gu2, gu)       # deterministic
+
+
+def test_mech_grid_kernel_equals_the_tile_kernels(monkeypatch):
+    mesh = folax_b200.create_2D_square_mesh(1.0, 48)
+    rng = np.random.default_rng(4)
+    K, u = rng.uniform(0.1, 1.0, (4, 48 * 48)), 0.01 * rng.standard_normal((4, 2 * 48 * 48))
+    grid = run_mech(make_mech(mesh, body=[0.1, 0.2]), K, u)
+    monkeypatch.setenv("FOL_ENERGY_GRID", "0")
+    loss = make_mech(mesh, body=[0.1, 0.2])
+    assert loss._grid_plan() is None
+    tile = run_mech(loss, K, u)
+    assert abs(grid[0] - tile[0]) <= 1e-13 * abs(tile[0])
+    assert np.abs(grid[1] - tile[1]).max() <= 1e-13 * np.abs(tile[1]).max()
+
+
+@pytest.mark.parametrize("B", [1, 2, 5])
+@pytest.mark.parametrize("exponent", [1.0, 2.0])
+def test_mech_grid_kernel_float32_and_exponent(B, exponent):
+    mesh = grid_mesh(70, 23, shear=0.2)
+    loss = make_mech(mesh, dtype="float32", exponent=exponent, body=[0.2, 0.1])
+    rng = np.random.default_rng(70 + B)
+    nn = mesh.GetNumberOfNodes()
+    K = rng.uniform(0.1, 1.0, (B, nn)).astype(np.float32)
+    u = (0.01 * rng.standard_normal((B, 2 * nn))).astype(np.float32)
+    mean, gu = run_mech(loss, K, u)
+    ref_mean, Eb, gU = oracle_mech(loss, mesh, K.astype(np.float64), u.astype(np.float64), exponent)
+    assert abs(mean - ref_mean) <= 2e-5 * (np.abs(Eb) ** exponent).max()
+    assert np.abs(gu - gU).max() <= 2e-5 * np.abs(gU).max()
+
+
+def test_mech_dirichlet_dofs_anywhere():
+    """Dirichlet dofs on single components of interior nodes, on the columns two warps share and on the top row."""
+    nx, ny = 70, 20
+    mesh = grid_mesh(nx, ny)
+    ids = np.arange((nx + 1) * (ny + 1))
+    mesh.node_sets["left"] = ids[(ids % (nx + 1) == 32) | (ids // (nx + 1) == ny) | (ids == 5)].astype(np.int32)
+    mesh.node_sets["right"] = ids[(ids % (nx + 1) == 64) & (ids // (nx + 1) < ny)].astype(np.int32)
+    loss = MechanicalLoss2DQuad("m", {"dirichlet_bc_dict": {"Ux": {"left": 0.01}, "Uy": {"right": -0.02}},
+                                      "material_dict": dict(MAT)}, mesh)
+    loss.Initialize()
+    rng = np.random.default_rng(8)
+    K, u = rng.uniform(0.1, 1.0, (2, len(ids))), 0.01 * rng.standard_normal((2, 2 * len(ids)))
+    mean, gu = run_mech(loss, K, u)
+    ref_mean, Eb, gU = oracle_mech(loss, mesh, K, u)
+    assert abs(mean - ref_mean) <= 1e-12 * np.abs(Eb).max()
+    assert np.abs(gu - gU).max() <= 1e-12 * np.abs(gU).max()
     assert not gu[:, loss.dirichlet_indices].any()
