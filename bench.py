@@ -369,6 +369,27 @@ def fol_loss_grad_bench(torch, dist, rank, world, steps, warmup):
     for _ in range(3):
         kern32()
     ms_kernel32 = event_time_ms(torch, kern32, steps)
+    # the other 2-D FOL loss on the same mesh: MechanicalLoss2DQuad (two dofs per node; csrc/energy_grid_mech.cu)
+    from folax_b200.loss_functions import MechanicalLoss2DQuad
+    mech = {}
+    for name, dt in (("f64", torch.float64), ("f32", torch.float32)):
+        lm = MechanicalLoss2DQuad("fol_mech", {"dirichlet_bc_dict": {"Ux": {"left": 0.0, "right": 0.05},
+                                                                     "Uy": {"left": 0.0, "right": 0.0}},
+                                               "material_dict": dict(MATERIAL),
+                                               "dtype": "float64" if dt == torch.float64 else "float32"}, mesh)
+        lm.Initialize()
+        Km = Kb.to(dt)
+        um = (0.01 * torch.randn((B, 2 * nn), generator=g, device="cuda", dtype=torch.float64)).to(dt)
+        km = lambda: lm._energy_and_grads(Km, um, dir_values=lm._dir_full, dir_flag=lm._dir_flag, out_scale=1.0 / B)
+        pm = make_physics(B, lm, Km, um)
+        for _ in range(3):
+            km()
+            pm()
+        mech[name] = {"kernel_ms": event_time_ms(torch, km, steps), "physics_only_ms": event_time_ms(torch, pm, steps)}
+        mech[name]["kernel_samples_per_s_per_gpu"] = B / (mech[name]["kernel_ms"] * 1e-3)
+        del lm, Km, um
+    mech["note"] = ("MechanicalLoss2DQuad.ComputeBatchLoss + VJP on the same 256x256 mesh, 1024 samples: structured-grid kernel "
+                    "energy_grid_mech_kernel (tile kernels: 3.55 ms float64, 1.76 ms float32)")
     # same FOL step with the network in float32 (flax's default parameter dtype) feeding the float64 physics loss
     torch.manual_seed(0)
     net32 = torch.nn.Sequential(torch.nn.Linear(64, 256), torch.nn.Tanh(), EarlyReduceLinear(256, nn)).to("cuda")
@@ -434,6 +455,7 @@ def fol_loss_grad_bench(torch, dist, rank, world, steps, warmup):
                                         "ms_per_step": ms_mixed,
                                         "note": "MLP in float32 (flax default parameter dtype), physics loss + VJP in "
                                                 "float64; the headline value above keeps the whole step in float64"},
+            "mechanical_quad256": mech,
             "f32_network_f32_physics": {"value": B * world / (ms_f32 * 1e-3), "unit": "samples/s", "ms_per_step": ms_f32,
                                         "note": "network, loss and VJP in float32 (the reference's default precision; "
                                                 "parity tolerance 1e-5)"},
