@@ -2,7 +2,7 @@
 // 2x2x2 Gauss rule (MechanicalLoss3DHexa, mechanical.py:98-117 + fe_loss.py:191-230, 299).
 //
 // Same results as the generic kernel (assemble.cuh); different machine mapping:
-//   * persistent warps, each iteration owns a tile of 4 consecutive elements;
+//   * persistent warps (16 per SM), each iteration owns a tile of 4 consecutive elements;
 //   * nodal gathers for tile i+1 (and connectivity for tile i+2) are in flight while tile i computes;
 //   * phase 1: lane (element, Gauss point) -> J, det J, grad N, coefficient: 32 independent
 //     geometry evaluations per warp, nothing computed twice;
@@ -49,7 +49,12 @@ using namespace hexk;
 //           flags -- which makes room for a SECOND Ke staging slot at the same 12 warps / SM: the bulk copy of element
 //           i can take until element i + 2 needs the slot, instead of stalling the warp when the write queue is deep
 //           Measured: no gain (profiles/r2/hex_kernel_experiments.md) -- what the stores cost under sustained load is
-//           board power, not slot waits.  Kept selectable (FOL_HEX_LAYOUT=1) for A/B runs; layout 0 is the default.
+//           board power, not slot waits.  Kept selectable (FOL_HEX_LAYOUT=0 / 1) for A/B runs.
+// LAYOUT 2 (the default): the compact layout with ONE staging slot: 13.6 KB per warp, i.e. 16 warps per SM (two CTAs of
+//           8 warps at 128 registers, no spills) instead of 12.  The kernel's phase 2 is a chain of dependent DMMA /
+//           DFMA / shuffle instructions (stall reasons `wait` and `math_pipe_throttle`), so a third more warps per
+//           scheduler is what shortens it: same box, alternating processes, 128^3: 2.56 -> 1.92 ms per step right after
+//           the warm-up, 2.56 -> 2.10 ms sustained; outputs bit-identical to layout 0 (profiles/r2/hex_layout_ab.jsonl).
 template <int LAYOUT>
 struct __align__(128) WarpSmemT;
 
@@ -71,10 +76,10 @@ struct __align__(128) WarpSmemT<0> {
   float bc[kTile][24];               // 1 = free dof, 0 = Dirichlet dof
 };
 
-template <>
-struct __align__(128) WarpSmemT<1> {
-  static constexpr int kStage = 2;
-  double stage[2][576];              // two Ke staging slots
+template <int SLOTS>
+struct __align__(128) CompactSmem {
+  static constexpr int kStage = SLOTS;
+  double stage[SLOTS][576];          // Ke staging slots
   double2 gxy[kTile][8][8];          // [element][gauss][node ^ swz(gauss)]: (dN/dx, dN/dy)
   double gz[kTile][8][8];            // [element][gauss][node ^ swz(gauss) ^ 2 (element & 1)]: dN/dz (8-byte accesses are
                                      //   served per half-warp = two elements: the element bit keeps them on distinct banks)
@@ -85,21 +90,36 @@ struct __align__(128) WarpSmemT<1> {
   double wd[kTile][8];
   uint8_t bc[kTile][24];             // 1 = free dof, 0 = Dirichlet dof
 };
+template <>
+struct __align__(128) WarpSmemT<1> : CompactSmem<2> {};
+// LAYOUT 2: the compact layout with ONE staging slot, which fits 16 warps per SM (2 CTAs of 8 warps, 128 registers, no
+//           spills) instead of 12: a third more warps to cover the DMMA / FP64 dependency stalls of phase 2.
+template <>
+struct __align__(128) WarpSmemT<2> : CompactSmem<1> {};
+constexpr int kWarpsDense = 8;
 static_assert(2 * (sizeof(WarpSmemT<1>) * kWarps + 1024) <= 227 * 1024, "compact layout: two CTAs per SM must fit");
+static_assert(2 * (sizeof(WarpSmemT<2>) * kWarpsDense + 1024) <= 227 * 1024, "dense layout: two CTAs of 8 warps per SM must fit");
+template <int LAYOUT>
+constexpr int warps_of() { return LAYOUT == 2 ? kWarpsDense : kWarps; }
+template <int LAYOUT>
+constexpr int min_ctas_of() { return 2; }   // every layout is sized for two CTAs per SM
 
 }  // namespace
 
 namespace {
 __device__ __forceinline__ double sm_x(const WarpSmemT<0>& sm, int buf, int i, int k) { return sm.X[buf][i][k]; }
-__device__ __forceinline__ double sm_x(const WarpSmemT<1>& sm, int, int i, int k) { return sm.X[i][k]; }
+template <int S>
+__device__ __forceinline__ double sm_x(const CompactSmem<S>& sm, int, int i, int k) { return sm.X[i][k]; }
 __device__ __forceinline__ double sm_de(const WarpSmemT<0>& sm, int buf, int k) { return sm.de[buf][k]; }
-__device__ __forceinline__ double sm_de(const WarpSmemT<1>& sm, int, int k) { return sm.de[k]; }
+template <int S>
+__device__ __forceinline__ double sm_de(const CompactSmem<S>& sm, int, int k) { return sm.de[k]; }
 }  // namespace
 
 template <bool FUSE, int LAYOUT>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(warps_of<LAYOUT>() * 32, min_ctas_of<LAYOUT>())
 assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles, const int has_body, const HaloFuse hf) {
   using WarpSmem = WarpSmemT<LAYOUT>;
+  constexpr int kWarps = warps_of<LAYOUT>();
   constexpr int kStage = WarpSmem::kStage;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -251,11 +271,11 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
         if constexpr (LAYOUT == 0) sm.gzs[el_p][sub][a ^ swz_p] = make_double2(g[2], coef);
         else sm.gz[el_p][sub][a ^ swz_p ^ ((el_p & 1) << 1)] = g[2];
       }
-      if constexpr (LAYOUT == 1) sm.coef[lane] = coef;
+      if constexpr (LAYOUT != 0) sm.coef[lane] = coef;
       sm.wd[el_p][sub] = wd;
     }
     __syncwarp();
-    if constexpr (LAYOUT == 1) issue_next();   // X / de of this tile are consumed
+    if constexpr (LAYOUT != 0) issue_next();   // X / de of this tile are consumed
 
     // ---- phase 2: one element at a time, lane (a, k)
 #pragma unroll 1
@@ -401,7 +421,10 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
         write_rows();
         fence_async_smem();
         __syncwarp();
-        if (lane == 0 && !(has_body & 2)) bulk_store(args.ke + e * 576, slot, 576 * sizeof(double));
+        if (lane == 0 && !(has_body & 2)) {
+          if (has_body & 4) bulk_store_evict_first(args.ke + e * 576, slot, 576 * sizeof(double));
+          else bulk_store(args.ke + e * 576, slot, 576 * sizeof(double));
+        }
         store_re();
       }
     }
@@ -421,6 +444,7 @@ std::atomic<int> g_grid_margin{0};
 
 template <bool FUSE, int LAYOUT>
 static int launch_hex(cudaStream_t s, const AsmArgs<double>& args, const HaloFuse* hf) {
+  constexpr int kWarps = warps_of<LAYOUT>();
   static PerDeviceGrid per_device;
   const size_t smem = sizeof(WarpSmemT<LAYOUT>) * kWarps;
   int grid = 0;
@@ -433,6 +457,8 @@ static int launch_hex(cudaStream_t s, const AsmArgs<double>& args, const HaloFus
   // separates the compute / latency time of the kernel from its HBM write stream
   static const bool nostore = [] { const char* v = std::getenv("FOL_HEX_DIAG"); return v && std::string(v) == "nostore"; }();
   if (nostore) has_body |= 2;
+  static const bool hint = [] { const char* v = std::getenv("FOL_HEX_HINT"); return v && std::atoi(v) != 0; }();
+  if (hint) has_body |= 4;
   // persistent grid, optionally leaving room for communication kernels that must run concurrently
   int g = grid - g_grid_margin.load();
   if (g < 1) g = 1;
@@ -442,10 +468,11 @@ static int launch_hex(cudaStream_t s, const AsmArgs<double>& args, const HaloFus
 }
 
 int assemble_hex_mech_f64(cudaStream_t s, const AsmArgs<double>& args, const HaloFuse* hf) {
-  // FOL_HEX_LAYOUT=1 selects the compact shared-memory layout with two staging slots (A/B runs; measured equal to
-  // layout 0 under sustained load and not better in the first steps: profiles/r2/hex_kernel_experiments.md)
-  static const int layout = [] { const char* v = std::getenv("FOL_HEX_LAYOUT"); return v ? std::atoi(v) : 0; }();
+  // default: layout 2 (16 warps / SM).  FOL_HEX_LAYOUT=0 / 1 select the 12-warp layouts for A/B runs
+  // (profiles/r2/hex_kernel_experiments.md); all three produce the same bits.
+  static const int layout = [] { const char* v = std::getenv("FOL_HEX_LAYOUT"); return v ? std::atoi(v) : 2; }();
   if (layout == 0) return hf ? launch_hex<true, 0>(s, args, hf) : launch_hex<false, 0>(s, args, hf);
+  if (layout == 2) return hf ? launch_hex<true, 2>(s, args, hf) : launch_hex<false, 2>(s, args, hf);
   return hf ? launch_hex<true, 1>(s, args, hf) : launch_hex<false, 1>(s, args, hf);
 }
 

@@ -19,6 +19,8 @@
 // The reference's strain convention is kept: engineering shears enter the strain TENSOR unhalved
 // (mechanical_elastoplasticity.py:50-55), so the shear stiffness is 2G and C_el = lam 1(x)1 + 2G I_6.
 // transpose_jacobian=True and the matrix-free mode are served by the generic kernel (assemble.cuh).
+#include <cstdlib>
+
 #include "assemble.cuh"
 #include "assemble_hex_common.cuh"
 
@@ -31,35 +33,58 @@ using namespace hexk;
 #ifndef FOL_J2_WARPS
 #define FOL_J2_WARPS 5
 #endif
-constexpr int kWarpsJ2 = FOL_J2_WARPS;   // warps per CTA, each fully independent (2 CTAs = 10 warps / SM, 19.9 KB of staging per warp)
+constexpr int kWarpsJ2 = FOL_J2_WARPS;   // warps per CTA of layout 0, each fully independent (2 CTAs = 10 warps / SM, 19.9 KB of staging per warp)
 
-struct __align__(128) WarpSmemJ2 {
+// LAYOUT 0: (dN/dz, w detJ) pairs and float Dirichlet flags, 5 warps per CTA (10 warps / SM).
+// LAYOUT 1: compact -- dN/dz alone (w detJ is per Gauss point, not per node: 32 doubles instead of 256) and byte flags:
+//           17.9 KB per warp, which fits 6 warps per CTA (12 warps / SM at the same two CTAs, 162 registers).  The default:
+//           same box, alternating processes, 128^3, all points plastic: 4.55 -> 3.87 ms per step, outputs bit-identical
+//           (profiles/r2/hex_layout_ab.jsonl) -- like the elastic kernel, phase 2 is latency-bound, not throughput-bound.
+template <int LAYOUT>
+struct GzStore;
+template <>
+struct GzStore<0> { double2 v[kTile][8][8]; };
+template <>
+struct GzStore<1> { double v[kTile][8][8]; };
+
+template <int LAYOUT>
+struct __align__(128) WarpSmemJ2T {
   // Ke staging slot (bulk-copy source).  Its first 224 doubles double as the staging of the tile's NEW history in the
   // global (element, point, 7) layout (one 1792-byte bulk copy per tile): the history copy is issued before the
   // element loop, whose first staging write waits for it, and the last Ke copy of a tile is waited for before the
   // next tile's history is written.
   double stage[576];
   double2 gxy[kTile][8][8];          // [element][gauss][node ^ swz(gauss)]: (dN/dx, dN/dy), see assemble_hex.cu
-  double2 gzs[kTile][8][8];          //                                      (dN/dz, w detJ)
+  // LAYOUT 0: gz2 = (dN/dz, w detJ) pairs; LAYOUT 1: gz1[element][gauss][node ^ swz(gauss) ^ 2 (element & 1)] = dN/dz
+  // (8-byte accesses are served per half-warp = two elements in phase 1: the element bit keeps them on distinct banks)
+  // and wdj[element * 8 + gauss] = w detJ
+  GzStore<LAYOUT> gz;
+  double wdj[32];
   // nodal data and history of the tile, SoA over the 32 lanes.  SINGLE buffers: phase 1 consumes them completely, so
-  // the gather of the next tile is issued right after phase 1 and lands behind phase 2 (20.6 KB per warp: 10 warps / SM)
+  // the gather of the next tile is issued right after phase 1 and lands behind phase 2
   double X[3][32];
   double u[3][32];
   double st[7][32];
   double dv[6][32];                  // dev of the trial elastic strain          } per (element, Gauss point),
   double ws[6][32];                  // w detJ sigma                             } SoA: conflict-free phase-1 stores,
   double wl[32], wm[32], wb[32];     // w detJ (lam + a/3), w detJ (2G - a), w detJ b   } broadcast phase-2 loads
-  float bc[kTile][24];               // 1 = free dof, 0 = Dirichlet dof
+  uint8_t bc[kTile][24];             // 1 = free dof, 0 = Dirichlet dof
 };
+constexpr int kWarpsJ2Dense = 6;
+template <int LAYOUT>
+constexpr int j2_warps_of() { return LAYOUT == 1 ? kWarpsJ2Dense : kWarpsJ2; }
 
 // two CTAs per SM must fit the 227 KB of shared memory (1 KB per CTA is reserved by the system)
-static_assert(2 * (sizeof(WarpSmemJ2) * kWarpsJ2 + 1024) <= 227 * 1024, "WarpSmemJ2: two CTAs per SM do not fit");
+static_assert(2 * (sizeof(WarpSmemJ2T<0>) * kWarpsJ2 + 1024) <= 227 * 1024, "WarpSmemJ2: two CTAs per SM do not fit");
+static_assert(2 * (sizeof(WarpSmemJ2T<1>) * kWarpsJ2Dense + 1024) <= 227 * 1024, "compact WarpSmemJ2: two CTAs of 6 warps do not fit");
 
 }  // namespace
 
-template <bool FUSE>
-__global__ void __launch_bounds__(kWarpsJ2 * 32, 2)
+template <bool FUSE, int LAYOUT>
+__global__ void __launch_bounds__(j2_warps_of<LAYOUT>() * 32, 2)
 assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, const int has_body, const HaloFuse hf) {
+  using WarpSmemJ2 = WarpSmemJ2T<LAYOUT>;
+  constexpr int kWarpsJ2 = j2_warps_of<LAYOUT>();
   extern __shared__ __align__(128) unsigned char smem_raw_j2[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpSmemJ2& sm = reinterpret_cast<WarpSmemJ2*>(smem_raw_j2)[warp];
@@ -133,9 +158,9 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
     hold_back(n_next, f0, f1, f2);
 
     // ---- phase 0: this tile's nodal data and history have landed
-    sm.bc[el_p][sub * 3 + 0] = f0 ? 0.f : 1.f;
-    sm.bc[el_p][sub * 3 + 1] = f1 ? 0.f : 1.f;
-    sm.bc[el_p][sub * 3 + 2] = f2 ? 0.f : 1.f;
+    sm.bc[el_p][sub * 3 + 0] = f0 ? 0 : 1;
+    sm.bc[el_p][sub * 3 + 1] = f1 ? 0 : 1;
+    sm.bc[el_p][sub * 3 + 2] = f2 ? 0 : 1;
     cp_async_wait_all();
     __syncwarp();
     // ---- phase 1: lane (element, Gauss point): geometry (geometry.py:88-97), strain = B u, return mapping
@@ -184,7 +209,8 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
 #pragma unroll
         for (int k = 0; k < 3; ++k) g[k] = d0 * inv[0][k] + d1 * inv[1][k] + d2 * inv[2][k];
         sm.gxy[el_p][sub][a ^ swz_p] = make_double2(g[0], g[1]);
-        sm.gzs[el_p][sub][a ^ swz_p] = make_double2(g[2], wd);
+        if constexpr (LAYOUT == 0) sm.gz.v[el_p][sub][a ^ swz_p] = make_double2(g[2], wd);
+        else sm.gz.v[el_p][sub][a ^ swz_p ^ ((el_p & 1) << 1)] = g[2];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           const double ui = sm.u[i][el_p * 8 + a];
@@ -212,6 +238,7 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
       sm.wl[lane] = wd * (lam + p.a * (1.0 / 3.0));
       sm.wm[lane] = wd * (2.0 * G - p.a);
       sm.wb[lane] = wd * p.b;
+      sm.wdj[lane] = wd;
       plastic_mask = __ballot_sync(0xffffffffu, (p.a != 0.0) | (p.b != 0.0));
     }
     fence_async_smem();
@@ -246,7 +273,13 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
       for (int kk = 0; kk < 2; ++kk) {
         const int gp = 4 * kk + kq, ix = el * 8 + gp;
         const double2 xy = sm.gxy[el][gp][ra ^ ((kq << 1) | kk)];
-        const double2 zs = sm.gzs[el][gp][ra ^ ((kq << 1) | kk)];
+        double2 zs;
+        if constexpr (LAYOUT == 0) {
+          zs = sm.gz.v[el][gp][ra ^ ((kq << 1) | kk)];
+        } else {
+          zs.x = sm.gz.v[el][gp][ra ^ ((kq << 1) | kk) ^ ((el & 1) << 1)];
+          zs.y = sm.wdj[ix];
+        }
         bf[kk][0] = xy.x; bf[kk][1] = xy.y; bf[kk][2] = zs.x;
         // f_int share of this lane's two Gauss points: (w detJ sigma) . grad N_a
         const double s0 = sm.ws[0][ix], s1 = sm.ws[1][ix], s2 = sm.ws[2][ix];
@@ -347,14 +380,14 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
         for (int g = 0; g < 8; ++g) {
           const double gx = 1.0 + sgn_x(ra) * sgn_x(g) * FOL_S3, gy = 1.0 + sgn_y(ra) * sgn_y(g) * FOL_S3;
           const double gz = 1.0 + sgn_z(ra) * sgn_z(g) * FOL_S3;
-          nw += sm.gzs[el][g][((g & 3) << 1) | (g >> 2)].y * (0.125 * gx * gy * gz);   // w detJ rides with node 0's gradient
+          nw += sm.wdj[el * 8 + g] * (0.125 * gx * gy * gz);
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) r[i] -= args.p.v[2 + i] * nw;
       }
       // Dirichlet row mask (fe_loss.py:191-207): only for elements touching a fixed dof (warp-uniform test)
-      const bool fixed_rows = (sm.bc[el][ra * 3 + 0] == 0.f) | (sm.bc[el][ra * 3 + 1] == 0.f) |
-                              (sm.bc[el][ra * 3 + 2] == 0.f);
+      const bool fixed_rows = (sm.bc[el][ra * 3 + 0] == 0) | (sm.bc[el][ra * 3 + 1] == 0) |
+                              (sm.bc[el][ra * 3 + 2] == 0);
       const bool any_fixed = __any_sync(0xffffffffu, fixed_rows);
       if (lane == 0) bulk_wait_read<0>();   // the copies that last used the staging slot / the history buffer are done
       __syncwarp();
@@ -370,7 +403,7 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           const int row = ra * 3 + i;
-          const bool freerow = sm.bc[el][row] != 0.f;
+          const bool freerow = sm.bc[el][row] != 0;
           double v[6];
 #pragma unroll
           for (int h = 0; h < 2; ++h)
@@ -387,11 +420,14 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) bulk_store(args.ke + e * 576, sm.stage, 576 * sizeof(double));
+      if (lane == 0) {
+        if (has_body & 4) bulk_store_evict_first(args.ke + e * 576, sm.stage, 576 * sizeof(double));
+        else bulk_store(args.ke + e * 576, sm.stage, 576 * sizeof(double));
+      }
       if (kq == 0) {
 #pragma unroll
         for (int i = 0; i < 3; ++i)
-          args.re[e * 24 + ra * 3 + i] = (any_fixed && sm.bc[el][ra * 3 + i] == 0.f) ? 0.0 : r[i];
+          args.re[e * 24 + ra * 3 + i] = (any_fixed && sm.bc[el][ra * 3 + i] == 0) ? 0.0 : r[i];
       }
     }
     __syncwarp();  // everyone is done with X / u / history / gradients of this tile
@@ -406,20 +442,29 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
   if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last copies
 }
 
-int assemble_hex_j2_f64(cudaStream_t s, const AsmArgs<double>& args, const HaloFuse* hf) {
-  static PerDeviceGrid per_device, per_device_fused;
-  const size_t smem = sizeof(WarpSmemJ2) * kWarpsJ2;
+template <bool FUSE, int LAYOUT>
+static int launch_hex_j2(cudaStream_t s, const AsmArgs<double>& args, const HaloFuse* hf) {
+  constexpr int kW = j2_warps_of<LAYOUT>();
+  static PerDeviceGrid per_device;
+  const size_t smem = sizeof(WarpSmemJ2T<LAYOUT>) * kW;
   int g = 0;
-  if (hf) FOL_CUDA(per_device_fused.get(assemble_hex_j2_f64_kernel<true>, kWarpsJ2 * 32, smem, &g));
-  else FOL_CUDA(per_device.get(assemble_hex_j2_f64_kernel<false>, kWarpsJ2 * 32, smem, &g));
+  FOL_CUDA(per_device.get(assemble_hex_j2_f64_kernel<FUSE, LAYOUT>, kW * 32, smem, &g));
   if (args.ne == 0) return FOL_OK;
   const long long ntiles = cdiv(args.ne, kTile);
-  const long long want = cdiv(ntiles, kWarpsJ2);
-  const int has_body = (args.p.v[2] != 0.0 || args.p.v[3] != 0.0 || args.p.v[4] != 0.0) ? 1 : 0;
+  const long long want = cdiv(ntiles, kW);
+  int has_body = (args.p.v[2] != 0.0 || args.p.v[3] != 0.0 || args.p.v[4] != 0.0) ? 1 : 0;
+  static const bool hint = [] { const char* v = std::getenv("FOL_HEX_HINT"); return v && std::atoi(v) != 0; }();
+  if (hint) has_body |= 4;   // A/B switch: L2 evict-first policy on the Ke bulk stores
   const unsigned blocks = (unsigned)(want < g ? want : g);
-  if (hf) assemble_hex_j2_f64_kernel<true><<<blocks, kWarpsJ2 * 32, smem, s>>>(args, ntiles, has_body, *hf);
-  else assemble_hex_j2_f64_kernel<false><<<blocks, kWarpsJ2 * 32, smem, s>>>(args, ntiles, has_body, HaloFuse{});
+  assemble_hex_j2_f64_kernel<FUSE, LAYOUT><<<blocks, kW * 32, smem, s>>>(args, ntiles, has_body, hf ? *hf : HaloFuse{});
   return check_launch("assemble_hex_j2_f64_kernel");
+}
+
+int assemble_hex_j2_f64(cudaStream_t s, const AsmArgs<double>& args, const HaloFuse* hf) {
+  // default: layout 1 (compact, 12 warps / SM); FOL_J2_LAYOUT=0 selects the 10-warp layout for A/B runs
+  static const int layout = [] { const char* v = std::getenv("FOL_J2_LAYOUT"); return v ? std::atoi(v) : 1; }();
+  if (layout == 0) return hf ? launch_hex_j2<true, 0>(s, args, hf) : launch_hex_j2<false, 0>(s, args, hf);
+  return hf ? launch_hex_j2<true, 1>(s, args, hf) : launch_hex_j2<false, 1>(s, args, hf);
 }
 
 }  // namespace fol
