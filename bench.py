@@ -667,6 +667,10 @@ def newton_bench(torch):
     loss._csr_plan()
     loss._sell_plan()
     plans = time.time() - t0
+    # one untimed assembly first: the 2.4 GB of element matrices come from a fresh cudaMalloc of torch's caching
+    # allocator on the first call (20-110 ms of host time, depending on what the earlier keys left cached)
+    loss.ComputeJacobianMatrixAndResidualVector(K, np.zeros(loss.GetTotalNumberOfDOFs()))
+    torch.cuda.synchronize()
     loss.ComputeJacobianMatrixAndResidualVector = timed(loss.ComputeJacobianMatrixAndResidualVector, "assembly_s")
     sell, bicg, fused = linalg.SellOperator, linalg.bicgstab, linalg.bicgstab_fused
     linalg.SellOperator = timed(sell, "operator_s")

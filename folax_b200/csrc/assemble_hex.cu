@@ -416,6 +416,24 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
         __syncwarp();
         if (lane == 0) bulk_store(args.ke + e * 576 + 288, slot + 288, 288 * sizeof(double));
       } else {
+        if (has_body & 8) {
+          // A/B variant (FOL_HEX_STORE=1 / 2): the staged rows leave through the LSU as coalesced 16-byte stores (512
+          // contiguous bytes per warp instruction) instead of the bulk-copy engine: no slot wait, no async-proxy fence
+          __syncwarp();   // every lane has read its share of the previous element out of the slot
+          write_rows();
+          __syncwarp();
+          double2* g = reinterpret_cast<double2*>(args.ke + e * 576);
+          const double2* sl = reinterpret_cast<const double2*>(slot);
+          if (has_body & 16) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) __stcs(g + k * 32 + lane, sl[k * 32 + lane]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) g[k * 32 + lane] = sl[k * 32 + lane];
+          }
+          store_re();
+          continue;
+        }
         if (lane == 0) bulk_wait_read<kStage - 1>();   // the copy that last used this slot has drained it
         __syncwarp();
         write_rows();
@@ -459,6 +477,9 @@ static int launch_hex(cudaStream_t s, const AsmArgs<double>& args, const HaloFus
   if (nostore) has_body |= 2;
   static const bool hint = [] { const char* v = std::getenv("FOL_HEX_HINT"); return v && std::atoi(v) != 0; }();
   if (hint) has_body |= 4;
+  static const int store_path = [] { const char* v = std::getenv("FOL_HEX_STORE"); return v ? std::atoi(v) : 0; }();
+  if (store_path == 1) has_body |= 8;
+  if (store_path == 2) has_body |= 8 | 16;
   // persistent grid, optionally leaving room for communication kernels that must run concurrently
   int g = grid - g_grid_margin.load();
   if (g < 1) g = 1;

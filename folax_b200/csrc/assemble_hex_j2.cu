@@ -374,7 +374,7 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
         r[i] += __shfl_xor_sync(0xffffffffu, r[i], 1);
         r[i] += __shfl_xor_sync(0xffffffffu, r[i], 2);
       }
-      if (has_body) {  // Fe_a = b * sum_g w detJ N_a(g)
+      if (has_body & 1) {  // Fe_a = b * sum_g w detJ N_a(g)
         double nw = 0.0;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
