@@ -96,11 +96,16 @@ struct __align__(128) WarpSmemT<1> : CompactSmem<2> {};
 //           spills) instead of 12: a third more warps to cover the DMMA / FP64 dependency stalls of phase 2.
 template <>
 struct __align__(128) WarpSmemT<2> : CompactSmem<1> {};
+// LAYOUT 3: layout 2 with a leaner hand-off to the copy engine (A/B: FOL_HEX_LAYOUT=3): the Dirichlet flags of the
+//           lane's three rows are read once per element and reused for the row mask and the residual (no branches
+//           around the three residual stores), and every lane executes the bulk-copy wait (no divergent region).
+template <>
+struct __align__(128) WarpSmemT<3> : CompactSmem<1> {};
 constexpr int kWarpsDense = 8;
 static_assert(2 * (sizeof(WarpSmemT<1>) * kWarps + 1024) <= 227 * 1024, "compact layout: two CTAs per SM must fit");
 static_assert(2 * (sizeof(WarpSmemT<2>) * kWarpsDense + 1024) <= 227 * 1024, "dense layout: two CTAs of 8 warps per SM must fit");
 template <int LAYOUT>
-constexpr int warps_of() { return LAYOUT == 2 ? kWarpsDense : kWarps; }
+constexpr int warps_of() { return LAYOUT >= 2 ? kWarpsDense : kWarps; }
 template <int LAYOUT>
 constexpr int min_ctas_of() { return 2; }   // every layout is sized for two CTAs per SM
 
@@ -360,7 +365,8 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
       }
       // stage the rows and hand them to the bulk-copy engine.  The Dirichlet row mask
       // (fe_loss.py:191-207) only matters for elements touching a fixed dof: warp-uniform test.
-      const bool fixed_rows = (sm.bc[el][ra * 3 + 0] == 0) | (sm.bc[el][ra * 3 + 1] == 0) | (sm.bc[el][ra * 3 + 2] == 0);
+      const bool fx[3] = {sm.bc[el][ra * 3 + 0] == 0, sm.bc[el][ra * 3 + 1] == 0, sm.bc[el][ra * 3 + 2] == 0};
+      const bool fixed_rows = fx[0] | fx[1] | fx[2];
       const bool any_fixed = __any_sync(0xffffffffu, fixed_rows);
       double* const slot = sm.stage[kStage > 1 ? (el & (kStage - 1)) : 0];
       auto write_rows = [&]() {
@@ -376,7 +382,7 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             const int row = ra * 3 + i;
-            const bool freerow = sm.bc[el][row] != 0;
+            const bool freerow = LAYOUT == 3 ? !fx[i] : sm.bc[el][row] != 0;
             double v[6];
 #pragma unroll
             for (int h = 0; h < 2; ++h)
@@ -393,7 +399,12 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
         }
       };
       auto store_re = [&]() {
-        if (kq == 0) {
+        if constexpr (LAYOUT == 3) {
+          if (kq == 0) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) args.re[e * 24 + ra * 3 + i] = fx[i] ? 0.0 : r[i];
+          }
+        } else if (kq == 0) {
 #pragma unroll
           for (int i = 0; i < 3; ++i)
             args.re[e * 24 + ra * 3 + i] = (any_fixed && sm.bc[el][ra * 3 + i] == 0) ? 0.0 : r[i];
@@ -416,33 +427,14 @@ assemble_hex_mech_f64_kernel(const AsmArgs<double> args, const long long ntiles,
         __syncwarp();
         if (lane == 0) bulk_store(args.ke + e * 576 + 288, slot + 288, 288 * sizeof(double));
       } else {
-        if (has_body & 8) {
-          // A/B variant (FOL_HEX_STORE=1 / 2): the staged rows leave through the LSU as coalesced 16-byte stores (512
-          // contiguous bytes per warp instruction) instead of the bulk-copy engine: no slot wait, no async-proxy fence
-          __syncwarp();   // every lane has read its share of the previous element out of the slot
-          write_rows();
-          __syncwarp();
-          double2* g = reinterpret_cast<double2*>(args.ke + e * 576);
-          const double2* sl = reinterpret_cast<const double2*>(slot);
-          if (has_body & 16) {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) __stcs(g + k * 32 + lane, sl[k * 32 + lane]);
-          } else {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) g[k * 32 + lane] = sl[k * 32 + lane];
-          }
-          store_re();
-          continue;
-        }
-        if (lane == 0) bulk_wait_read<kStage - 1>();   // the copy that last used this slot has drained it
+        // the copy that last used this slot has drained it (lanes other than 0 have no copies of their own: for them
+        // the wait returns at once, and LAYOUT 3 lets them execute it instead of branching around it)
+        if (LAYOUT == 3 || lane == 0) bulk_wait_read<kStage - 1>();
         __syncwarp();
         write_rows();
         fence_async_smem();
         __syncwarp();
-        if (lane == 0 && !(has_body & 2)) {
-          if (has_body & 4) bulk_store_evict_first(args.ke + e * 576, slot, 576 * sizeof(double));
-          else bulk_store(args.ke + e * 576, slot, 576 * sizeof(double));
-        }
+        if (lane == 0 && !(has_body & 2)) bulk_store(args.ke + e * 576, slot, 576 * sizeof(double));
         store_re();
       }
     }
@@ -475,11 +467,6 @@ static int launch_hex(cudaStream_t s, const AsmArgs<double>& args, const HaloFus
   // separates the compute / latency time of the kernel from its HBM write stream
   static const bool nostore = [] { const char* v = std::getenv("FOL_HEX_DIAG"); return v && std::string(v) == "nostore"; }();
   if (nostore) has_body |= 2;
-  static const bool hint = [] { const char* v = std::getenv("FOL_HEX_HINT"); return v && std::atoi(v) != 0; }();
-  if (hint) has_body |= 4;
-  static const int store_path = [] { const char* v = std::getenv("FOL_HEX_STORE"); return v ? std::atoi(v) : 0; }();
-  if (store_path == 1) has_body |= 8;
-  if (store_path == 2) has_body |= 8 | 16;
   // persistent grid, optionally leaving room for communication kernels that must run concurrently
   int g = grid - g_grid_margin.load();
   if (g < 1) g = 1;
@@ -494,6 +481,7 @@ int assemble_hex_mech_f64(cudaStream_t s, const AsmArgs<double>& args, const Hal
   static const int layout = [] { const char* v = std::getenv("FOL_HEX_LAYOUT"); return v ? std::atoi(v) : 2; }();
   if (layout == 0) return hf ? launch_hex<true, 0>(s, args, hf) : launch_hex<false, 0>(s, args, hf);
   if (layout == 2) return hf ? launch_hex<true, 2>(s, args, hf) : launch_hex<false, 2>(s, args, hf);
+  if (layout == 3) return hf ? launch_hex<true, 3>(s, args, hf) : launch_hex<false, 3>(s, args, hf);
   return hf ? launch_hex<true, 1>(s, args, hf) : launch_hex<false, 1>(s, args, hf);
 }
 

@@ -20,17 +20,6 @@ __device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, uns
                : "memory");
   asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
 }
-// same copy with an L2 evict-first policy on the written lines (the element matrices are a write-once stream far larger
-// than the L2: A/B switch FOL_HEX_HINT=1, see profiles/r2/hex_kernel_experiments.md)
-__device__ __forceinline__ void bulk_store_evict_first(double* gdst, const double* ssrc, unsigned bytes) {
-  const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
-  unsigned long long policy;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(policy));
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n" ::"l"(gdst), "r"(saddr),
-               "r"(bytes), "l"(policy)
-               : "memory");
-  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-}
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");

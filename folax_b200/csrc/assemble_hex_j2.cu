@@ -46,6 +46,8 @@ template <>
 struct GzStore<0> { double2 v[kTile][8][8]; };
 template <>
 struct GzStore<1> { double v[kTile][8][8]; };
+template <>
+struct GzStore<2> { double v[kTile][8][8]; };   // LAYOUT 2 = layout 1 + the leaner hand-off (A/B: FOL_J2_LAYOUT=2)
 
 template <int LAYOUT>
 struct __align__(128) WarpSmemJ2T {
@@ -72,7 +74,7 @@ struct __align__(128) WarpSmemJ2T {
 };
 constexpr int kWarpsJ2Dense = 6;
 template <int LAYOUT>
-constexpr int j2_warps_of() { return LAYOUT == 1 ? kWarpsJ2Dense : kWarpsJ2; }
+constexpr int j2_warps_of() { return LAYOUT >= 1 ? kWarpsJ2Dense : kWarpsJ2; }
 
 // two CTAs per SM must fit the 227 KB of shared memory (1 KB per CTA is reserved by the system)
 static_assert(2 * (sizeof(WarpSmemJ2T<0>) * kWarpsJ2 + 1024) <= 227 * 1024, "WarpSmemJ2: two CTAs per SM do not fit");
@@ -386,10 +388,12 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
         for (int i = 0; i < 3; ++i) r[i] -= args.p.v[2 + i] * nw;
       }
       // Dirichlet row mask (fe_loss.py:191-207): only for elements touching a fixed dof (warp-uniform test)
-      const bool fixed_rows = (sm.bc[el][ra * 3 + 0] == 0) | (sm.bc[el][ra * 3 + 1] == 0) |
-                              (sm.bc[el][ra * 3 + 2] == 0);
+      const bool fx[3] = {sm.bc[el][ra * 3 + 0] == 0, sm.bc[el][ra * 3 + 1] == 0, sm.bc[el][ra * 3 + 2] == 0};
+      const bool fixed_rows = fx[0] | fx[1] | fx[2];
       const bool any_fixed = __any_sync(0xffffffffu, fixed_rows);
-      if (lane == 0) bulk_wait_read<0>();   // the copies that last used the staging slot / the history buffer are done
+      // the copies that last used the staging slot / the history buffer are done (LAYOUT 2: every lane executes the
+      // wait -- lanes other than 0 have no copies of their own -- instead of branching around it)
+      if (LAYOUT == 2 || lane == 0) bulk_wait_read<0>();
       __syncwarp();
       if (!any_fixed) {
 #pragma unroll
@@ -403,7 +407,7 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
           const int row = ra * 3 + i;
-          const bool freerow = sm.bc[el][row] != 0;
+          const bool freerow = LAYOUT == 2 ? !fx[i] : sm.bc[el][row] != 0;
           double v[6];
 #pragma unroll
           for (int h = 0; h < 2; ++h)
@@ -420,14 +424,13 @@ assemble_hex_j2_f64_kernel(const AsmArgs<double> args, const long long ntiles, c
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        if (has_body & 4) bulk_store_evict_first(args.ke + e * 576, sm.stage, 576 * sizeof(double));
-        else bulk_store(args.ke + e * 576, sm.stage, 576 * sizeof(double));
-      }
+      if (lane == 0) bulk_store(args.ke + e * 576, sm.stage, 576 * sizeof(double));
       if (kq == 0) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
-          args.re[e * 24 + ra * 3 + i] = (any_fixed && sm.bc[el][ra * 3 + i] == 0) ? 0.0 : r[i];
+        for (int i = 0; i < 3; ++i) {
+          if constexpr (LAYOUT == 2) args.re[e * 24 + ra * 3 + i] = fx[i] ? 0.0 : r[i];
+          else args.re[e * 24 + ra * 3 + i] = (any_fixed && sm.bc[el][ra * 3 + i] == 0) ? 0.0 : r[i];
+        }
       }
     }
     __syncwarp();  // everyone is done with X / u / history / gradients of this tile
@@ -452,9 +455,7 @@ static int launch_hex_j2(cudaStream_t s, const AsmArgs<double>& args, const Halo
   if (args.ne == 0) return FOL_OK;
   const long long ntiles = cdiv(args.ne, kTile);
   const long long want = cdiv(ntiles, kW);
-  int has_body = (args.p.v[2] != 0.0 || args.p.v[3] != 0.0 || args.p.v[4] != 0.0) ? 1 : 0;
-  static const bool hint = [] { const char* v = std::getenv("FOL_HEX_HINT"); return v && std::atoi(v) != 0; }();
-  if (hint) has_body |= 4;   // A/B switch: L2 evict-first policy on the Ke bulk stores
+  const int has_body = (args.p.v[2] != 0.0 || args.p.v[3] != 0.0 || args.p.v[4] != 0.0) ? 1 : 0;
   const unsigned blocks = (unsigned)(want < g ? want : g);
   assemble_hex_j2_f64_kernel<FUSE, LAYOUT><<<blocks, kW * 32, smem, s>>>(args, ntiles, has_body, hf ? *hf : HaloFuse{});
   return check_launch("assemble_hex_j2_f64_kernel");
@@ -464,6 +465,7 @@ int assemble_hex_j2_f64(cudaStream_t s, const AsmArgs<double>& args, const HaloF
   // default: layout 1 (compact, 12 warps / SM); FOL_J2_LAYOUT=0 selects the 10-warp layout for A/B runs
   static const int layout = [] { const char* v = std::getenv("FOL_J2_LAYOUT"); return v ? std::atoi(v) : 1; }();
   if (layout == 0) return hf ? launch_hex_j2<true, 0>(s, args, hf) : launch_hex_j2<false, 0>(s, args, hf);
+  if (layout == 2) return hf ? launch_hex_j2<true, 2>(s, args, hf) : launch_hex_j2<false, 2>(s, args, hf);
   return hf ? launch_hex_j2<true, 1>(s, args, hf) : launch_hex_j2<false, 1>(s, args, hf);
 }
 
