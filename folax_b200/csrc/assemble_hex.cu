@@ -50,7 +50,7 @@ using namespace hexk;
 //           i can take until element i + 2 needs the slot, instead of stalling the warp when the write queue is deep
 //           Measured: no gain (profiles/r2/hex_kernel_experiments.md) -- what the stores cost under sustained load is
 //           board power, not slot waits.  Kept selectable (FOL_HEX_LAYOUT=0 / 1) for A/B runs.
-// LAYOUT 2 (the default): the compact layout with ONE staging slot: 13.6 KB per warp, i.e. 16 warps per SM (two CTAs of
+// LAYOUT 2 (LAYOUT 3, the default, = LAYOUT 2 + a leaner hand-off, below): the compact layout with ONE staging slot: 13.6 KB per warp, i.e. 16 warps per SM (two CTAs of
 //           8 warps at 128 registers, no spills) instead of 12.  The kernel's phase 2 is a chain of dependent DMMA /
 //           DFMA / shuffle instructions (stall reasons `wait` and `math_pipe_throttle`), so a third more warps per
 //           scheduler is what shortens it: same box, alternating processes, 128^3: 2.56 -> 1.92 ms per step right after
@@ -99,6 +99,8 @@ struct __align__(128) WarpSmemT<2> : CompactSmem<1> {};
 // LAYOUT 3: layout 2 with a leaner hand-off to the copy engine (A/B: FOL_HEX_LAYOUT=3): the Dirichlet flags of the
 //           lane's three rows are read once per element and reused for the row mask and the residual (no branches
 //           around the three residual stores), and every lane executes the bulk-copy wait (no divergent region).
+//           Same box, alternating processes: 2.10-2.11 -> 2.07 ms sustained, 1.92 ms right after the warm-up either
+//           way, outputs bit-identical (profiles/r2/hex_lean_ab.jsonl).  The default.
 template <>
 struct __align__(128) WarpSmemT<3> : CompactSmem<1> {};
 constexpr int kWarpsDense = 8;
@@ -476,9 +478,10 @@ static int launch_hex(cudaStream_t s, const AsmArgs<double>& args, const HaloFus
 }
 
 int assemble_hex_mech_f64(cudaStream_t s, const AsmArgs<double>& args, const HaloFuse* hf) {
-  // default: layout 2 (16 warps / SM).  FOL_HEX_LAYOUT=0 / 1 select the 12-warp layouts for A/B runs
+  // default: layout 3 (16 warps / SM, lean hand-off).  FOL_HEX_LAYOUT=0 / 1 select the 12-warp layouts, 2 the 16-warp
+  // layout with the original hand-off, for A/B runs
   // (profiles/r2/hex_kernel_experiments.md); all three produce the same bits.
-  static const int layout = [] { const char* v = std::getenv("FOL_HEX_LAYOUT"); return v ? std::atoi(v) : 2; }();
+  static const int layout = [] { const char* v = std::getenv("FOL_HEX_LAYOUT"); return v ? std::atoi(v) : 3; }();
   if (layout == 0) return hf ? launch_hex<true, 0>(s, args, hf) : launch_hex<false, 0>(s, args, hf);
   if (layout == 2) return hf ? launch_hex<true, 2>(s, args, hf) : launch_hex<false, 2>(s, args, hf);
   if (layout == 3) return hf ? launch_hex<true, 3>(s, args, hf) : launch_hex<false, 3>(s, args, hf);

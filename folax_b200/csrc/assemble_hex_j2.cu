@@ -462,11 +462,12 @@ static int launch_hex_j2(cudaStream_t s, const AsmArgs<double>& args, const Halo
 }
 
 int assemble_hex_j2_f64(cudaStream_t s, const AsmArgs<double>& args, const HaloFuse* hf) {
-  // default: layout 1 (compact, 12 warps / SM); FOL_J2_LAYOUT=0 selects the 10-warp layout for A/B runs
-  static const int layout = [] { const char* v = std::getenv("FOL_J2_LAYOUT"); return v ? std::atoi(v) : 1; }();
+  // default: layout 2 (compact, 12 warps / SM, lean hand-off: 3.91 -> 3.87 ms sustained on the same box);
+  // FOL_J2_LAYOUT=0 selects the 10-warp layout, 1 the 12-warp layout with the original hand-off, for A/B runs
+  static const int layout = [] { const char* v = std::getenv("FOL_J2_LAYOUT"); return v ? std::atoi(v) : 2; }();
   if (layout == 0) return hf ? launch_hex_j2<true, 0>(s, args, hf) : launch_hex_j2<false, 0>(s, args, hf);
-  if (layout == 2) return hf ? launch_hex_j2<true, 2>(s, args, hf) : launch_hex_j2<false, 2>(s, args, hf);
-  return hf ? launch_hex_j2<true, 1>(s, args, hf) : launch_hex_j2<false, 1>(s, args, hf);
+  if (layout == 1) return hf ? launch_hex_j2<true, 1>(s, args, hf) : launch_hex_j2<false, 1>(s, args, hf);
+  return hf ? launch_hex_j2<true, 2>(s, args, hf) : launch_hex_j2<false, 2>(s, args, hf);
 }
 
 }  // namespace fol
