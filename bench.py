@@ -70,6 +70,22 @@ def traffic_of(which, n, world):
     return d["dram_bytes"], f"{TRAFFIC_FILES[which]} (ncu --set full of `{d.get('command', '?')}`, dram read + write per launch)"
 
 
+def store_path_alone():
+    """The kernel's write stream WITHOUT its arithmetic (scripts/micro/store_path_bench.cu on a B200, committed output):
+    same 9.66 GB, same visiting order, same 4608-byte bulk copies from a per-warp slot refilled before every copy.  Says
+    how much of the gap to the roofline is the access pattern (little) and how much the hand-off between arithmetic and
+    copy engine (the rest): profiles/r2/hex_kernel_experiments.md."""
+    path = os.path.join(ROOT, "profiles", "r2", "store_path_micro_2.jsonl")
+    try:
+        rows = [json.loads(l) for l in open(path) if l.startswith("{")]
+        r = next(x for x in rows if x.get("mode") == 2 and x.get("spin") == 0 and x.get("warps_per_sm") == 16)
+        hbm, _ = measured_peaks()
+        return {"ms": r["ms"], "gbs": r["gbs"], "frac_of_peak": r["gbs"] / hbm,
+                "source": "profiles/r2/store_path_micro_2.jsonl (not measured in this run)"}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples SM clock + throttle reasons during the timed region (NVML)."""
 
@@ -875,7 +891,11 @@ def run_ours(args):
                 "kernel": "assemble_hex_mech_f64_kernel (element stage: DMMA m8n8k4 + cp.async.bulk stores)",
                 "kernel_ms": ms_kernel, "kernel_timing": "CUDA events around the launch inside every timed step (mean; "
                                                          "max over ranks), so kernel_ms <= ms_per_step by construction",
-                "algorithmic_bytes_per_element": ALG_BYTES_PER_ELEMENT_F64, "peak_source": peak_src}
+                "algorithmic_bytes_per_element": ALG_BYTES_PER_ELEMENT_F64, "peak_source": peak_src,
+                "launch_shape": "persistent, 2 CTAs x 8 warps per SM (16 warps / SM, 128 registers, 13.6 KB shared memory per warp)"}
+    sp = store_path_alone()
+    if sp is not None and n == 128:
+        roofline["store_path_alone"] = sp
 
     line = {"metric": "assembled_elements_per_s", "value": value, "unit": "elements/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
