@@ -110,16 +110,17 @@ def test_jax_binding_module_is_importable_and_says_what_it_needs():
         assert f"XLA_FFI_DEFINE_HANDLER_SYMBOL({name}," in shim_src, name
 
 
-def test_store_path_microbenchmark_compiles_for_sm100a(tmp_path):
-    """scripts/micro/store_path_bench.cu (the store-path microbenchmark behind profiles/r2/store_path_micro_*.jsonl)
-    stays buildable: nvcc cross-compiles it for sm_100a without a GPU."""
+@pytest.mark.parametrize("name", ["store_path_bench", "cabi_selfcheck"])
+def test_micro_programs_compile_for_sm100a(tmp_path, name):
+    """scripts/micro/*.cu (the store-path microbenchmark behind profiles/r2/store_path_micro_*.jsonl and the torch-free
+    tuned-vs-generic check through the C ABI) stay buildable: nvcc cross-compiles them for sm_100a without a GPU."""
     import shutil
     import subprocess
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
     src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "micro",
-                       "store_path_bench.cu")
+                       name + ".cu")
     r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-c", src, "-o",
-                        str(tmp_path / "store_path_bench.o")], capture_output=True, text=True)
+                        str(tmp_path / (name + ".o"))], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
