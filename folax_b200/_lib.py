@@ -36,6 +36,11 @@ SIGNATURES = {
     "fol_assemble_elements": (_int, [_vp, _int, _int, _int, _int, _int, _i64, _i64, _vp, _i32p, _vp, _vp,
                                      _u8p, C.POINTER(_dbl), _vp, _vp, _vp, _vp]),
     "fol_residual_gather": (_int, [_vp, _int, _i64, _int, _int, _i32p, _i32p, _vp, _vp]),
+    "fol_csr_plan_count_host": (_int, [_i32p, _i64, _int, _i64, _i32p, _i32p, _i32p]),
+    "fol_csr_plan_fill_host": (_int, [_i32p, _i64, _int, _i64, _int, _i32p, _i32p, _vp, _i32p, _i32p, _i32p, _i32p,
+                                      _i32p, _i32p]),
+    "fol_sell_plan_fill_host": (_int, [_vp, _i32p, _i64, _int, _int, _vp, _i32p, _i32p, _i32p, _i32p,
+                                       C.POINTER(_int)]),
     "fol_csr_values": (_int, [_vp, _int, _i64, _int, _int, _i32p, _i32p, _i32p, _i32p, _vp, _vp]),
     "fol_apply_jacobian_elements": (_int, [_vp, _int, _int, _int, _int, _int, _i64, _i64, _vp, _i32p, _vp, _vp, _u8p,
                                            C.POINTER(_dbl), _vp, _vp, _vp]),

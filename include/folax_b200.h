@@ -378,6 +378,29 @@ int fol_plan_assemble_device(fol_plan* plan, int transpose, const void* ctrl_dev
                              const void* u_dev, void** ke_data_dev, void** residual_dev);
 fol_stream_t fol_plan_stream(fol_plan* plan);
 
+/* ---- host-side integer plans of the solver hand-off (no device work; all host threads) ------------------------ */
+/* Structure of the duplicate-free CSR the reference's solvers get from scipy.sparse.csr_array + sum_duplicates
+ * (fol/solvers/fe_solver.py:71-72) and the fixed-order value plan of fol_csr_values; folax_b200/csr_plan.py drives the
+ * two calls and holds the NumPy restatement the tests compare them with.  All pointers are HOST pointers.
+ *   count: node -> (element, local node) adjacency (adj_ptr (nn+1), adj (ne*nnode), ascending e*nnode+a) and the number
+ *          of distinct neighbour nodes deg (nn);
+ *   fill:  with node_ptr (nn+1, int64) = exclusive prefix sum of deg: pair_ptr (npairs+1), contrib (ne*nnode*nnode: BCOO
+ *          block positions (e*nnode+a)*nnode+b grouped by node pair, ascending inside a pair), out_base / row_stride
+ *          (npairs), indptr (d*nn+1), indices (d*d*npairs). */
+int fol_csr_plan_count_host(const int32_t* conn_host, int64_t ne, int nnode, int64_t nn, int32_t* adj_ptr_host,
+                            int32_t* adj_host, int32_t* deg_host);
+int fol_csr_plan_fill_host(const int32_t* conn_host, int64_t ne, int nnode, int64_t nn, int dofs_per_node,
+                           const int32_t* adj_ptr_host, const int32_t* adj_host, const int64_t* node_ptr_host,
+                           int32_t* pair_ptr_host, int32_t* contrib_host, int32_t* out_base_host,
+                           int32_t* row_stride_host, int32_t* indptr_host, int32_t* indices_host);
+/* Sliced-ELLPACK copy of a CSR structure for fol_sell_spmv / fol_sell_spmv_block (folax_b200/sell_plan.py): fills
+ * cols / src (slice_ptr[nslices], pre-set to 0 / -1 by the caller), diag_src (nrows, pre-set to -1) and, when
+ * node_cols_host is not NULL, one node column per run of dofs_per_node entries; *blocked_host = 1 if every row is made
+ * of such runs (else node_cols is meaningless). */
+int fol_sell_plan_fill_host(const int64_t* indptr_host, const int32_t* indices_host, int64_t nrows, int dofs_per_node,
+                            int slice_height, const int64_t* slice_ptr_host, int32_t* cols_host, int32_t* src_host,
+                            int32_t* diag_src_host, int32_t* node_cols_host, int* blocked_host);
+
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* FP64 (or FP32) FMA peak microbenchmark: returns achieved TFLOP/s through *tflops. */
 int fol_measure_fma_peak(int dtype, double* tflops);

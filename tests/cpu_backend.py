@@ -61,6 +61,9 @@ def arr(ptr, n, ctype=C.c_double):
     return np.ctypeslib.as_array((ctype * n).from_address(ptr)) if n else np.zeros(0)
 
 
+_REAL_LOAD = _lib.load     # captured before any test swaps _lib.load for a FakeLib
+
+
 class FakeLib:
     """fol_* entry points used by the response / solver classes, on host pointers (float64 only)."""
 
@@ -95,6 +98,16 @@ class FakeLib:
             for k in range(width):
                 o[n * width + k] = sum(ev[int(x) * width + k] for x in ad[ap[n]:ap[n + 1]])
         return 0
+
+    # ---- host-side integer plans (csrc/plan_host.cu): pure host code, served by the real library
+    def fol_csr_plan_count_host(self, *a):
+        return _REAL_LOAD().fol_csr_plan_count_host(*a)
+
+    def fol_csr_plan_fill_host(self, *a):
+        return _REAL_LOAD().fol_csr_plan_fill_host(*a)
+
+    def fol_sell_plan_fill_host(self, *a):
+        return _REAL_LOAD().fol_sell_plan_fill_host(*a)
 
     def fol_sum(self, s, dt, n, x, out):
         arr(out, 1)[0] = arr(x, n).sum()
